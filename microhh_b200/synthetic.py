@@ -1,0 +1,77 @@
+"""
+Synthetic dry-CBL-LES-shaped inputs for tests and bench.py:
+smooth divergence-free-ish modes plus seeded noise for u, v, w; a stably stratified `th`
+profile with near-surface noise; Boussinesq (rhoref = 1) or anelastic base state; smooth
+positive 2-D Monin-Obukhov gradients as the surface-model inputs.  Pure numpy, host side.
+"""
+import numpy as np
+
+
+def make_case(gd, seed=2, anelastic=False, noise=0.05, ns=1):
+    TF = gd.TF
+    rng = np.random.default_rng(seed)
+    kc, jc, ic = gd.shape
+    x = (np.arange(ic) - gd.igc + 0.5)*float(gd.dx)
+    xh = (np.arange(ic) - gd.igc)*float(gd.dx)
+    y = (np.arange(jc) - gd.jgc + 0.5)*float(gd.dy)
+    yh = (np.arange(jc) - gd.jgc)*float(gd.dy)
+    z = gd.z.astype(np.float64); zh = gd.zh.astype(np.float64)
+    Lx, Ly, Lz = float(gd.xsize), float(gd.ysize), float(gd.zsize)
+    twopi = 2.*np.pi
+
+    def modes(xx, yy, zz, phase):
+        X = xx[None, None, :]; Y = yy[None, :, None]; Z = zz[:, None, None]
+        return (np.sin(twopi*X/Lx + phase)*np.cos(twopi*2*Y/Ly)*np.cos(np.pi*Z/Lz)
+                + 0.5*np.cos(twopi*3*X/Lx)*np.sin(twopi*Y/Ly + phase)*np.sin(twopi*Z/Lz))
+
+    def interior_noise(amp):
+        a = np.zeros((kc, jc, ic))
+        a[gd.kstart:gd.kend, gd.jstart:gd.jend, gd.istart:gd.iend] = amp*(
+            rng.random((gd.kmax, gd.jmax, gd.imax)) - 0.5)
+        return a
+
+    u = modes(xh, y, z, 0.3) + interior_noise(noise)
+    v = modes(x, yh, z, 1.1) + interior_noise(noise)
+    w = 0.5*modes(x, y, zh, 2.0)*np.sin(np.pi*zh/Lz)[:, None, None] + interior_noise(noise)
+    w[:gd.kstart+1] = 0.
+    w[gd.kend:] = 0.
+    th = 300. + 0.003*z[:, None, None] + 0.1*modes(x, y, z, 0.7) + interior_noise(0.1)*(z[:, None, None] < 0.1*Lz)
+    fields = dict(u=u, v=v, w=w, th=th)
+    scal = ["th"]
+    for n in range(1, ns):
+        name = f"s{n}"
+        fields[name] = 1. + 0.5*modes(x, y, z, 0.5*n) + interior_noise(noise)
+        scal.append(name)
+
+    if anelastic:
+        rhoref = np.exp(-z/8000.); rhorefh = np.exp(-zh/8000.)
+    else:
+        rhoref = np.ones(kc); rhorefh = np.ones(kc)
+    thref = np.full(kc, 300.); threfh = np.full(kc, 300.)
+
+    X2 = x[None, :]; Y2 = y[:, None]
+    smooth2 = lambda ph: 1. + 0.3*np.sin(twopi*X2/Lx + ph)*np.cos(twopi*Y2/Ly)
+    two_d = dict(
+        dudz_mo=0.05*smooth2(0.2), dvdz_mo=0.03*smooth2(1.3), dbdz_mo=-1e-4*smooth2(0.6),
+        z0m=np.full((jc, ic), 0.1),
+        u_fluxbot=-0.02*smooth2(0.9), v_fluxbot=-0.01*smooth2(2.1),
+        u_fluxtop=np.zeros((jc, ic)), v_fluxtop=np.zeros((jc, ic)),
+        u_gradbot=0.05*smooth2(0.2), v_gradbot=0.03*smooth2(1.3),
+        u_gradtop=np.zeros((jc, ic)), v_gradtop=np.zeros((jc, ic)),
+    )
+    for s in scal:
+        two_d[f"{s}_fluxbot"] = 0.1*smooth2(0.4)
+        two_d[f"{s}_fluxtop"] = np.zeros((jc, ic))
+        two_d[f"{s}_gradbot"] = -0.01*smooth2(0.4)
+        two_d[f"{s}_gradtop"] = np.full((jc, ic), 0.003)
+
+    cast = lambda a: np.ascontiguousarray(a.astype(TF))
+    out = {k: cast(a) for k, a in fields.items()}
+    out.update({k: cast(a) for k, a in two_d.items()})
+    out.update(rhoref=cast(rhoref), rhorefh=cast(rhorefh), thref=cast(thref), threfh=cast(threfh))
+    out["scalars"] = scal
+    for name in ["u", "v", "w"] + scal:
+        out[name + "t"] = np.zeros(gd.shape, TF)
+    out["evisc"] = np.zeros(gd.shape, TF)
+    out["p"] = np.zeros(gd.shape, TF)
+    return out

@@ -1,0 +1,833 @@
+"""
+TEST INFRASTRUCTURE ONLY -- the parity oracle.  Nothing in the product path
+(`microhh_b200/`) may import this module; only `tests/`, `__graft_entry__.smoke()`
+and `bench.py`'s cpu_baseline / `--impl reference` leg do.
+
+A CPU restatement, in numpy, of MicroHH's dynamical-core hot path.  Every function
+cites the reference file:line it follows.  Arrays are C-ordered `(kcells, jcells, icells)`
+views of the reference's `ijk = i + j*icells + k*ijcells` layout, so `a[k, j, i]`
+is the reference's `a[ijk]`.  Expression grouping follows the reference so that the
+results are bit-identical to the reference's own CPU kernels compiled with
+`-ffp-contract=off` (`oracle/_ref/libmhh_ref.so`; checked in tests/test_oracle_vs_ref.py
+and pinned by the golden vectors in tests/golden/).
+
+Parity status: PINNED for advec_2i5 / diff_smag2 / thermo_dry / boundary / rk3 / tdma
+against the reference's own compiled kernels (bit-exact).  The FFT (FFTW3, a system
+package that is not vendored in the reference; call sites reference src/fft.cxx:145-155,
+338-452) is restated from its published definition with numpy.fft (pocketfft):
+"parity unpinned" at the FFTW boundary, pinned instead by the DFT definition and by the
+post-pressure divergence.
+"""
+import numpy as np
+
+# --------------------------------------------------------------------------------------
+# Grid (reference src/grid.cxx:141-170 sizes, :245-304 metrics for swspatialorder=2)
+# --------------------------------------------------------------------------------------
+class Grid:
+    def __init__(self, itot, jtot, ktot, xsize, ysize, zsize, igc, jgc, kgc, dtype=np.float64, z=None):
+        TF = np.dtype(dtype).type
+        self.TF = TF
+        self.itot, self.jtot, self.ktot = itot, jtot, ktot
+        self.imax, self.jmax, self.kmax = itot, jtot, ktot
+        self.igc, self.jgc, self.kgc = igc, jgc, kgc
+        self.icells, self.jcells, self.kcells = itot + 2*igc, jtot + 2*jgc, ktot + 2*kgc
+        self.ijcells = self.icells*self.jcells
+        self.ncells = self.ijcells*self.kcells
+        self.istart, self.iend = igc, igc + itot
+        self.jstart, self.jend = jgc, jgc + jtot
+        self.kstart, self.kend = kgc, kgc + ktot
+        self.xsize, self.ysize, self.zsize = TF(xsize), TF(ysize), TF(zsize)
+        # src/grid.cxx:250-253
+        self.dx = TF(self.xsize / itot)
+        self.dy = TF(self.ysize / jtot)
+        kc = self.kcells
+        ks, ke = self.kstart, self.kend
+        self.z = np.zeros(kc, TF); self.zh = np.zeros(kc, TF)
+        self.dz = np.zeros(kc, TF); self.dzh = np.zeros(kc, TF)
+        self.dzi = np.zeros(kc, TF); self.dzhi = np.zeros(kc, TF)
+        if z is None:
+            # uniform grid as cases/drycblles/drycblles_input.py:17-27 builds it
+            dz = zsize / ktot
+            z = np.linspace(0.5*dz, zsize - 0.5*dz, ktot)
+        self.z[ks:ke] = np.asarray(z, TF)
+        self._calculate_2nd()
+
+    def _calculate_2nd(self):
+        """src/grid.cxx:274-304"""
+        TF = self.TF
+        ks, ke, kc = self.kstart, self.kend, self.kcells
+        z, zh, dz, dzh, dzi, dzhi = self.z, self.zh, self.dz, self.dzh, self.dzi, self.dzhi
+        z[ks-1] = -z[ks]
+        z[ke] = TF(2.)*self.zsize - z[ke-1]
+        for k in range(ks+1, ke):
+            zh[k] = TF(0.5)*(z[k-1] + z[k])
+        zh[ks] = TF(0.)
+        zh[ke] = self.zsize
+        for k in range(1, kc):
+            dzh[k] = z[k] - z[k-1]
+            dzhi[k] = TF(1.)/dzh[k]
+        dzh[ks-1] = dzh[ks+1]
+        dzhi[ks-1] = dzhi[ks+1]
+        for k in range(1, kc-1):
+            dz[k] = zh[k+1] - zh[k]
+            dzi[k] = TF(1.)/dz[k]
+        dz[ks-1] = dz[ks]; dzi[ks-1] = dzi[ks]
+        dz[ke] = dz[ke-1]; dzi[ke] = dzi[ke-1]
+
+    def field(self, fill=0.):
+        return np.full((self.kcells, self.jcells, self.icells), fill, self.TF)
+
+    def field2d(self, fill=0.):
+        return np.full((self.jcells, self.icells), fill, self.TF)
+
+
+def _S(g, a, dk=0, dj=0, di=0, k0=None, k1=None):
+    """Interior view of `a` shifted by (dk,dj,di); k-range defaults to kstart..kend."""
+    k0 = g.kstart if k0 is None else k0
+    k1 = g.kend if k1 is None else k1
+    return a[k0+dk:k1+dk, g.jstart+dj:g.jend+dj, g.istart+di:g.iend+di]
+
+
+def _K(g, v, dk=0, k0=None, k1=None):
+    """1-D profile slice broadcastable over an interior view."""
+    k0 = g.kstart if k0 is None else k0
+    k1 = g.kend if k1 is None else k1
+    return v[k0+dk:k1+dk, None, None]
+
+
+# --------------------------------------------------------------------------------------
+# Finite-difference helpers (reference include/finite_difference.h:33-158)
+# --------------------------------------------------------------------------------------
+def interp2(a, b):
+    return a.dtype.type(0.5)*(a + b)
+
+def interp4_ws(a, b, c, d):
+    T = a.dtype.type
+    return T(7./12.)*(b + c) - T(1./12.)*(a + d)
+
+def interp3_ws(a, b, c, d):
+    T = a.dtype.type
+    return T(3./12.)*(c - b) - T(1./12.)*(d - a)
+
+def interp6_ws(a, b, c, d, e, f):
+    T = a.dtype.type
+    return T(37./60.)*(c + d) - T(8./60.)*(b + e) + T(1./60.)*(a + f)
+
+def interp5_ws(a, b, c, d, e, f):
+    T = a.dtype.type
+    return T(10./60.)*(d - c) - T(5./60.)*(e - b) + T(1./60.)*(f - a)
+
+
+# --------------------------------------------------------------------------------------
+# Boundary_cyclic (reference src/boundary_cyclic.cxx:369-443, 445-507)
+# --------------------------------------------------------------------------------------
+EDGE_EW, EDGE_NS, EDGE_BOTH = 0, 1, 2
+
+def boundary_cyclic(g, a, edge=EDGE_BOTH):
+    igc, jgc = g.igc, g.jgc
+    if edge in (EDGE_EW, EDGE_BOTH):
+        a[:, :, 0:igc] = a[:, :, g.iend-igc:g.iend]
+        a[:, :, g.iend:g.iend+igc] = a[:, :, g.istart:g.istart+igc]
+    if edge in (EDGE_NS, EDGE_BOTH):
+        if g.jtot > 1:
+            a[:, 0:jgc, :] = a[:, g.jend-jgc:g.jend, :]
+            a[:, g.jend:g.jend+jgc, :] = a[:, g.jstart:g.jstart+jgc, :]
+        else:
+            ref = a[g.kstart:g.kend, g.jstart:g.jstart+1, :]
+            a[g.kstart:g.kend, 0:jgc, :] = ref
+            a[g.kstart:g.kend, g.jend:g.jend+jgc, :] = ref
+
+def boundary_cyclic_2d(g, a):
+    igc, jgc = g.igc, g.jgc
+    a[:, 0:igc] = a[:, g.iend-igc:g.iend]
+    a[:, g.iend:g.iend+igc] = a[:, g.istart:g.istart+igc]
+    if g.jtot > 1:
+        a[0:jgc, :] = a[g.jend-jgc:g.jend, :]
+        a[g.jend:g.jend+jgc, :] = a[g.jstart:g.jstart+jgc, :]
+    else:
+        a[0:jgc, :] = a[g.jstart:g.jstart+1, :]
+        a[g.jend:g.jend+jgc, :] = a[g.jstart:g.jstart+1, :]
+
+
+# --------------------------------------------------------------------------------------
+# Vertical ghost cells, 2nd order (reference src/boundary.cxx:700-772)
+# --------------------------------------------------------------------------------------
+BC_DIRICHLET, BC_NEUMANN = 0, 1
+
+def ghost_cells_bot_2nd(g, a, bc, abot, agradbot):
+    ks = g.kstart
+    if bc == BC_DIRICHLET:
+        a[ks-1] = g.TF(2.)*abot - a[ks]
+    else:
+        a[ks-1] = -agradbot*g.dzh[ks] + a[ks]
+
+def ghost_cells_top_2nd(g, a, bc, atop, agradtop):
+    ke = g.kend
+    if bc == BC_DIRICHLET:
+        a[ke] = g.TF(2.)*atop - a[ke-1]
+    else:
+        a[ke] = agradtop*g.dzh[ke] + a[ke-1]
+
+
+# --------------------------------------------------------------------------------------
+# Advec_2i5 (reference src/advec_2i5.cxx:151-728)
+# --------------------------------------------------------------------------------------
+def _advec_2i5_vertical(g, at, a, wface, rho_f, rho_c, dzx, lo, hi):
+    """Shared vertical structure of advec_u/v/s (faces k, k+1 of cell k; weights
+    rhorefh[k+1], rhorefh[k] / rhoref[k] * dzi[k]) -- src/advec_2i5.cxx:203-299.
+    wface(dk, k0, k1) returns the advecting velocity on face k+dk for cells k0..k1."""
+    ks, ke = g.kstart, g.kend
+    A = lambda dk, k0, k1: _S(g, a, dk, 0, 0, k0, k1)
+    R = lambda v, dk, k0, k1: _K(g, v, dk, k0, k1)
+
+    # interior, full 5/6th order (:204-217)
+    k0, k1 = ks+3, ke-3
+    if k1 > k0:
+        wt_, wb_ = wface(1, k0, k1), wface(0, k0, k1)
+        _S(g, at, 0, 0, 0, k0, k1)[...] += (
+            - ( R(rho_f, 1, k0, k1) * wt_ * interp6_ws(A(-2,k0,k1), A(-1,k0,k1), A(0,k0,k1), A(1,k0,k1), A(2,k0,k1), A(3,k0,k1))
+              - R(rho_f, 0, k0, k1) * wb_ * interp6_ws(A(-3,k0,k1), A(-2,k0,k1), A(-1,k0,k1), A(0,k0,k1), A(1,k0,k1), A(2,k0,k1)) ) / R(rho_c, 0, k0, k1) * R(dzx, 0, k0, k1)
+            + ( R(rho_f, 1, k0, k1) * np.abs(wt_) * interp5_ws(A(-2,k0,k1), A(-1,k0,k1), A(0,k0,k1), A(1,k0,k1), A(2,k0,k1), A(3,k0,k1))
+              - R(rho_f, 0, k0, k1) * np.abs(wb_) * interp5_ws(A(-3,k0,k1), A(-2,k0,k1), A(-1,k0,k1), A(0,k0,k1), A(1,k0,k1), A(2,k0,k1)) ) / R(rho_c, 0, k0, k1) * R(dzx, 0, k0, k1) )
+
+    # k = kstart (:220-229)
+    k0, k1 = ks, ks+1
+    wt_ = wface(1, k0, k1)
+    _S(g, at, 0, 0, 0, k0, k1)[...] += (
+        - ( R(rho_f, 1, k0, k1) * wt_ * interp2(A(0,k0,k1), A(1,k0,k1)) ) / R(rho_c, 0, k0, k1) * R(dzx, 0, k0, k1) )
+
+    # k = kstart+1 (:231-243)
+    k0, k1 = ks+1, ks+2
+    wt_, wb_ = wface(1, k0, k1), wface(0, k0, k1)
+    _S(g, at, 0, 0, 0, k0, k1)[...] += (
+        - ( R(rho_f, 1, k0, k1) * wt_ * interp4_ws(A(-1,k0,k1), A(0,k0,k1), A(1,k0,k1), A(2,k0,k1))
+          - R(rho_f, 0, k0, k1) * wb_ * interp2(A(-1,k0,k1), A(0,k0,k1)) ) / R(rho_c, 0, k0, k1) * R(dzx, 0, k0, k1)
+        + ( R(rho_f, 1, k0, k1) * np.abs(wt_) * interp3_ws(A(-1,k0,k1), A(0,k0,k1), A(1,k0,k1), A(2,k0,k1)) ) / R(rho_c, 0, k0, k1) * R(dzx, 0, k0, k1) )
+
+    # k = kstart+2 (:246-259)
+    k0, k1 = ks+2, ks+3
+    wt_, wb_ = wface(1, k0, k1), wface(0, k0, k1)
+    _S(g, at, 0, 0, 0, k0, k1)[...] += (
+        - ( R(rho_f, 1, k0, k1) * wt_ * interp6_ws(A(-2,k0,k1), A(-1,k0,k1), A(0,k0,k1), A(1,k0,k1), A(2,k0,k1), A(3,k0,k1))
+          - R(rho_f, 0, k0, k1) * wb_ * interp4_ws(A(-2,k0,k1), A(-1,k0,k1), A(0,k0,k1), A(1,k0,k1)) ) / R(rho_c, 0, k0, k1) * R(dzx, 0, k0, k1)
+        + ( R(rho_f, 1, k0, k1) * np.abs(wt_) * interp5_ws(A(-2,k0,k1), A(-1,k0,k1), A(0,k0,k1), A(1,k0,k1), A(2,k0,k1), A(3,k0,k1))
+          - R(rho_f, 0, k0, k1) * np.abs(wb_) * interp3_ws(A(-2,k0,k1), A(-1,k0,k1), A(0,k0,k1), A(1,k0,k1)) ) / R(rho_c, 0, k0, k1) * R(dzx, 0, k0, k1) )
+
+    # k = kend-3 (:261-274)
+    k0, k1 = ke-3, ke-2
+    wt_, wb_ = wface(1, k0, k1), wface(0, k0, k1)
+    _S(g, at, 0, 0, 0, k0, k1)[...] += (
+        - ( R(rho_f, 1, k0, k1) * wt_ * interp4_ws(A(-1,k0,k1), A(0,k0,k1), A(1,k0,k1), A(2,k0,k1))
+          - R(rho_f, 0, k0, k1) * wb_ * interp6_ws(A(-3,k0,k1), A(-2,k0,k1), A(-1,k0,k1), A(0,k0,k1), A(1,k0,k1), A(2,k0,k1)) ) / R(rho_c, 0, k0, k1) * R(dzx, 0, k0, k1)
+        + ( R(rho_f, 1, k0, k1) * np.abs(wt_) * interp3_ws(A(-1,k0,k1), A(0,k0,k1), A(1,k0,k1), A(2,k0,k1))
+          - R(rho_f, 0, k0, k1) * np.abs(wb_) * interp5_ws(A(-3,k0,k1), A(-2,k0,k1), A(-1,k0,k1), A(0,k0,k1), A(1,k0,k1), A(2,k0,k1)) ) / R(rho_c, 0, k0, k1) * R(dzx, 0, k0, k1) )
+
+    # k = kend-2 (:276-288)
+    k0, k1 = ke-2, ke-1
+    wt_, wb_ = wface(1, k0, k1), wface(0, k0, k1)
+    _S(g, at, 0, 0, 0, k0, k1)[...] += (
+        - ( R(rho_f, 1, k0, k1) * wt_ * interp2(A(0,k0,k1), A(1,k0,k1))
+          - R(rho_f, 0, k0, k1) * wb_ * interp4_ws(A(-2,k0,k1), A(-1,k0,k1), A(0,k0,k1), A(1,k0,k1)) ) / R(rho_c, 0, k0, k1) * R(dzx, 0, k0, k1)
+        - ( R(rho_f, 0, k0, k1) * np.abs(wb_) * interp3_ws(A(-2,k0,k1), A(-1,k0,k1), A(0,k0,k1), A(1,k0,k1)) ) / R(rho_c, 0, k0, k1) * R(dzx, 0, k0, k1) )
+
+    # k = kend-1 (:290-299)
+    k0, k1 = ke-1, ke
+    wb_ = wface(0, k0, k1)
+    _S(g, at, 0, 0, 0, k0, k1)[...] += (
+        - ( -R(rho_f, 0, k0, k1) * wb_ * interp2(A(-1,k0,k1), A(0,k0,k1)) ) / R(rho_c, 0, k0, k1) * R(dzx, 0, k0, k1) )
+
+
+def advec_2i5_u(g, ut, u, v, w, rhoref, rhorefh):
+    """src/advec_2i5.cxx:151-300"""
+    TF = g.TF
+    dxi, dyi = TF(1.)/g.dx, TF(1.)/g.dy
+    U = lambda di=0, dj=0: _S(g, u, 0, dj, di)
+    V = lambda di=0, dj=0: _S(g, v, 0, dj, di)
+    _S(g, ut)[...] += (
+        - ( interp2(U(0), U(1)) * interp6_ws(U(-2), U(-1), U(0), U(1), U(2), U(3))
+          - interp2(U(-1), U(0)) * interp6_ws(U(-3), U(-2), U(-1), U(0), U(1), U(2)) ) * dxi
+        + ( np.abs(interp2(U(0), U(1))) * interp5_ws(U(-2), U(-1), U(0), U(1), U(2), U(3))
+          - np.abs(interp2(U(-1), U(0))) * interp5_ws(U(-3), U(-2), U(-1), U(0), U(1), U(2)) ) * dxi
+        - ( interp2(V(-1, 1), V(0, 1)) * interp6_ws(U(0,-2), U(0,-1), U(0,0), U(0,1), U(0,2), U(0,3))
+          - interp2(V(-1, 0), V(0, 0)) * interp6_ws(U(0,-3), U(0,-2), U(0,-1), U(0,0), U(0,1), U(0,2)) ) * dyi
+        + ( np.abs(interp2(V(-1, 1), V(0, 1))) * interp5_ws(U(0,-2), U(0,-1), U(0,0), U(0,1), U(0,2), U(0,3))
+          - np.abs(interp2(V(-1, 0), V(0, 0))) * interp5_ws(U(0,-3), U(0,-2), U(0,-1), U(0,0), U(0,1), U(0,2)) ) * dyi )
+    wface = lambda dk, k0, k1: interp2(_S(g, w, dk, 0, -1, k0, k1), _S(g, w, dk, 0, 0, k0, k1))
+    _advec_2i5_vertical(g, ut, u, wface, rhorefh, rhoref, g.dzi, 0, 0)
+
+
+def advec_2i5_v(g, vt, u, v, w, rhoref, rhorefh):
+    """src/advec_2i5.cxx:303-450"""
+    TF = g.TF
+    dxi, dyi = TF(1.)/g.dx, TF(1.)/g.dy
+    U = lambda di=0, dj=0: _S(g, u, 0, dj, di)
+    V = lambda di=0, dj=0: _S(g, v, 0, dj, di)
+    _S(g, vt)[...] += (
+        - ( interp2(U(1,-1), U(1,0)) * interp6_ws(V(-2), V(-1), V(0), V(1), V(2), V(3))
+          - interp2(U(0,-1), U(0,0)) * interp6_ws(V(-3), V(-2), V(-1), V(0), V(1), V(2)) ) * dxi
+        + ( np.abs(interp2(U(1,-1), U(1,0))) * interp5_ws(V(-2), V(-1), V(0), V(1), V(2), V(3))
+          - np.abs(interp2(U(0,-1), U(0,0))) * interp5_ws(V(-3), V(-2), V(-1), V(0), V(1), V(2)) ) * dxi
+        - ( interp2(V(0,0), V(0,1)) * interp6_ws(V(0,-2), V(0,-1), V(0,0), V(0,1), V(0,2), V(0,3))
+          - interp2(V(0,-1), V(0,0)) * interp6_ws(V(0,-3), V(0,-2), V(0,-1), V(0,0), V(0,1), V(0,2)) ) * dyi
+        + ( np.abs(interp2(V(0,0), V(0,1))) * interp5_ws(V(0,-2), V(0,-1), V(0,0), V(0,1), V(0,2), V(0,3))
+          - np.abs(interp2(V(0,-1), V(0,0))) * interp5_ws(V(0,-3), V(0,-2), V(0,-1), V(0,0), V(0,1), V(0,2)) ) * dyi )
+    wface = lambda dk, k0, k1: interp2(_S(g, w, dk, -1, 0, k0, k1), _S(g, w, dk, 0, 0, k0, k1))
+    _advec_2i5_vertical(g, vt, v, wface, rhorefh, rhoref, g.dzi, 0, 0)
+
+
+def advec_2i5_s(g, st, s, u, v, w, rhoref, rhorefh):
+    """src/advec_2i5.cxx:582-728"""
+    TF = g.TF
+    dxi, dyi = TF(1.)/g.dx, TF(1.)/g.dy
+    S = lambda di=0, dj=0: _S(g, s, 0, dj, di)
+    U = lambda di=0, dj=0: _S(g, u, 0, dj, di)
+    V = lambda di=0, dj=0: _S(g, v, 0, dj, di)
+    _S(g, st)[...] += (
+        - ( U(1) * interp6_ws(S(-2), S(-1), S(0), S(1), S(2), S(3))
+          - U(0) * interp6_ws(S(-3), S(-2), S(-1), S(0), S(1), S(2)) ) * dxi
+        + ( np.abs(U(1)) * interp5_ws(S(-2), S(-1), S(0), S(1), S(2), S(3))
+          - np.abs(U(0)) * interp5_ws(S(-3), S(-2), S(-1), S(0), S(1), S(2)) ) * dxi
+        - ( V(0,1) * interp6_ws(S(0,-2), S(0,-1), S(0,0), S(0,1), S(0,2), S(0,3))
+          - V(0,0) * interp6_ws(S(0,-3), S(0,-2), S(0,-1), S(0,0), S(0,1), S(0,2)) ) * dyi
+        + ( np.abs(V(0,1)) * interp5_ws(S(0,-2), S(0,-1), S(0,0), S(0,1), S(0,2), S(0,3))
+          - np.abs(V(0,0)) * interp5_ws(S(0,-3), S(0,-2), S(0,-1), S(0,0), S(0,1), S(0,2)) ) * dyi )
+    wface = lambda dk, k0, k1: _S(g, w, dk, 0, 0, k0, k1)
+    _advec_2i5_vertical(g, st, s, wface, rhorefh, rhoref, g.dzi, 0, 0)
+    # NOTE: kend-2 abs term in advec_s is written "+ ( -rhorefh[k]*abs(w)*interp3 )" (:715) which is
+    # bit-identical to the "- ( rhorefh[k]*abs(w)*interp3 )" form of advec_u/v used above.
+
+
+def advec_2i5_w(g, wt, u, v, w, rhoref, rhorefh):
+    """src/advec_2i5.cxx:453-579"""
+    TF = g.TF
+    ks, ke = g.kstart, g.kend
+    dxi, dyi = TF(1.)/g.dx, TF(1.)/g.dy
+    k0, k1 = ks+1, ke
+    W = lambda di=0, dj=0: _S(g, w, 0, dj, di, k0, k1)
+    U = lambda di=0, dj=0, dk=0: _S(g, u, dk, dj, di, k0, k1)
+    V = lambda di=0, dj=0, dk=0: _S(g, v, dk, dj, di, k0, k1)
+    _S(g, wt, 0, 0, 0, k0, k1)[...] += (
+        - ( interp2(U(1,0,-1), U(1,0,0)) * interp6_ws(W(-2), W(-1), W(0), W(1), W(2), W(3))
+          - interp2(U(0,0,-1), U(0,0,0)) * interp6_ws(W(-3), W(-2), W(-1), W(0), W(1), W(2)) ) * dxi
+        + ( np.abs(interp2(U(1,0,-1), U(1,0,0))) * interp5_ws(W(-2), W(-1), W(0), W(1), W(2), W(3))
+          - np.abs(interp2(U(0,0,-1), U(0,0,0))) * interp5_ws(W(-3), W(-2), W(-1), W(0), W(1), W(2)) ) * dxi
+        - ( interp2(V(0,1,-1), V(0,1,0)) * interp6_ws(W(0,-2), W(0,-1), W(0,0), W(0,1), W(0,2), W(0,3))
+          - interp2(V(0,0,-1), V(0,0,0)) * interp6_ws(W(0,-3), W(0,-2), W(0,-1), W(0,0), W(0,1), W(0,2)) ) * dyi
+        + ( np.abs(interp2(V(0,1,-1), V(0,1,0))) * interp5_ws(W(0,-2), W(0,-1), W(0,0), W(0,1), W(0,2), W(0,3))
+          - np.abs(interp2(V(0,0,-1), V(0,0,0))) * interp5_ws(W(0,-3), W(0,-2), W(0,-1), W(0,0), W(0,1), W(0,2)) ) * dyi )
+
+    A = lambda dk, a0, a1: _S(g, w, dk, 0, 0, a0, a1)
+    R = lambda vv, dk, a0, a1: _K(g, vv, dk, a0, a1)
+    dzhi = g.dzhi
+
+    # interior (:506-519)
+    a0, a1 = ks+3, ke-2
+    if a1 > a0:
+        wt_ = interp2(A(0,a0,a1), A(1,a0,a1)); wb_ = interp2(A(-1,a0,a1), A(0,a0,a1))
+        _S(g, wt, 0, 0, 0, a0, a1)[...] += (
+            - ( R(rhoref, 0, a0, a1) * wt_ * interp6_ws(A(-2,a0,a1), A(-1,a0,a1), A(0,a0,a1), A(1,a0,a1), A(2,a0,a1), A(3,a0,a1))
+              - R(rhoref,-1, a0, a1) * wb_ * interp6_ws(A(-3,a0,a1), A(-2,a0,a1), A(-1,a0,a1), A(0,a0,a1), A(1,a0,a1), A(2,a0,a1)) ) / R(rhorefh, 0, a0, a1) * R(dzhi, 0, a0, a1)
+            + ( R(rhoref, 0, a0, a1) * np.abs(wt_) * interp5_ws(A(-2,a0,a1), A(-1,a0,a1), A(0,a0,a1), A(1,a0,a1), A(2,a0,a1), A(3,a0,a1))
+              - R(rhoref,-1, a0, a1) * np.abs(wb_) * interp5_ws(A(-3,a0,a1), A(-2,a0,a1), A(-1,a0,a1), A(0,a0,a1), A(1,a0,a1), A(2,a0,a1)) ) / R(rhorefh, 0, a0, a1) * R(dzhi, 0, a0, a1) )
+
+    # k = kstart+1 (:522-534)
+    a0, a1 = ks+1, ks+2
+    wt_ = interp2(A(0,a0,a1), A(1,a0,a1)); wb_ = interp2(A(-1,a0,a1), A(0,a0,a1))
+    _S(g, wt, 0, 0, 0, a0, a1)[...] += (
+        - ( R(rhoref, 0, a0, a1) * wt_ * interp4_ws(A(-1,a0,a1), A(0,a0,a1), A(1,a0,a1), A(2,a0,a1))
+          - R(rhoref,-1, a0, a1) * wb_ * interp2(A(-1,a0,a1), A(0,a0,a1)) ) / R(rhorefh, 0, a0, a1) * R(dzhi, 0, a0, a1)
+        + ( R(rhoref, 0, a0, a1) * np.abs(wt_) * interp3_ws(A(-1,a0,a1), A(0,a0,a1), A(1,a0,a1), A(2,a0,a1)) ) / R(rhorefh, 0, a0, a1) * R(dzhi, 0, a0, a1) )
+
+    # k = kstart+2 (:536-549)
+    a0, a1 = ks+2, ks+3
+    wt_ = interp2(A(0,a0,a1), A(1,a0,a1)); wb_ = interp2(A(-1,a0,a1), A(0,a0,a1))
+    _S(g, wt, 0, 0, 0, a0, a1)[...] += (
+        - ( R(rhoref, 0, a0, a1) * wt_ * interp6_ws(A(-2,a0,a1), A(-1,a0,a1), A(0,a0,a1), A(1,a0,a1), A(2,a0,a1), A(3,a0,a1))
+          - R(rhoref,-1, a0, a1) * wb_ * interp4_ws(A(-2,a0,a1), A(-1,a0,a1), A(0,a0,a1), A(1,a0,a1)) ) / R(rhorefh, 0, a0, a1) * R(dzhi, 0, a0, a1)
+        + ( R(rhoref, 0, a0, a1) * np.abs(wt_) * interp5_ws(A(-2,a0,a1), A(-1,a0,a1), A(0,a0,a1), A(1,a0,a1), A(2,a0,a1), A(3,a0,a1))
+          - R(rhoref,-1, a0, a1) * np.abs(wb_) * interp3_ws(A(-2,a0,a1), A(-1,a0,a1), A(0,a0,a1), A(1,a0,a1)) ) / R(rhorefh, 0, a0, a1) * R(dzhi, 0, a0, a1) )
+
+    # k = kend-2 (:551-564)
+    a0, a1 = ke-2, ke-1
+    wt_ = interp2(A(0,a0,a1), A(1,a0,a1)); wb_ = interp2(A(-1,a0,a1), A(0,a0,a1))
+    _S(g, wt, 0, 0, 0, a0, a1)[...] += (
+        - ( R(rhoref, 0, a0, a1) * wt_ * interp4_ws(A(-1,a0,a1), A(0,a0,a1), A(1,a0,a1), A(2,a0,a1))
+          - R(rhoref,-1, a0, a1) * wb_ * interp6_ws(A(-3,a0,a1), A(-2,a0,a1), A(-1,a0,a1), A(0,a0,a1), A(1,a0,a1), A(2,a0,a1)) ) / R(rhorefh, 0, a0, a1) * R(dzhi, 0, a0, a1)
+        + ( R(rhoref, 0, a0, a1) * np.abs(wt_) * interp3_ws(A(-1,a0,a1), A(0,a0,a1), A(1,a0,a1), A(2,a0,a1))
+          - R(rhoref,-1, a0, a1) * np.abs(wb_) * interp5_ws(A(-3,a0,a1), A(-2,a0,a1), A(-1,a0,a1), A(0,a0,a1), A(1,a0,a1), A(2,a0,a1)) ) / R(rhorefh, 0, a0, a1) * R(dzhi, 0, a0, a1) )
+
+    # k = kend-1 (:566-578)
+    a0, a1 = ke-1, ke
+    wt_ = interp2(A(0,a0,a1), A(1,a0,a1)); wb_ = interp2(A(-1,a0,a1), A(0,a0,a1))
+    _S(g, wt, 0, 0, 0, a0, a1)[...] += (
+        - ( R(rhoref, 0, a0, a1) * wt_ * interp2(A(0,a0,a1), A(1,a0,a1))
+          - R(rhoref,-1, a0, a1) * wb_ * interp4_ws(A(-2,a0,a1), A(-1,a0,a1), A(0,a0,a1), A(1,a0,a1)) ) / R(rhorefh, 0, a0, a1) * R(dzhi, 0, a0, a1)
+        - ( R(rhoref,-1, a0, a1) * np.abs(wb_) * interp3_ws(A(-2,a0,a1), A(-1,a0,a1), A(0,a0,a1), A(1,a0,a1)) ) / R(rhorefh, 0, a0, a1) * R(dzhi, 0, a0, a1) )
+
+
+def advec_2i5_cfl(g, u, v, w, dt):
+    """src/advec_2i5.cxx:60-148 (returns cfl*dt in TF, as the reference does)"""
+    TF = g.TF
+    ks, ke = g.kstart, g.kend
+    dxi, dyi = TF(1.)/g.dx, TF(1.)/g.dy
+    cfl = TF(0.)
+    def horiz(k0, k1):
+        U = lambda di: _S(g, u, 0, 0, di, k0, k1)
+        V = lambda dj: _S(g, v, 0, dj, 0, k0, k1)
+        return (np.abs(interp6_ws(U(-2), U(-1), U(0), U(1), U(2), U(3)))*dxi
+              + np.abs(interp6_ws(V(-2), V(-1), V(0), V(1), V(2), V(3)))*dyi)
+    W = lambda dk, k0, k1: _S(g, w, dk, 0, 0, k0, k1)
+    parts = []
+    for (k0, k1) in ((ks, ks+1), (ke-1, ke)):
+        parts.append(horiz(k0, k1) + np.abs(interp2(W(0,k0,k1), W(1,k0,k1)))*_K(g, g.dzi, 0, k0, k1))
+    for (k0, k1) in ((ks+1, ks+2), (ke-2, ke-1)):
+        parts.append(horiz(k0, k1) + np.abs(interp4_ws(W(-1,k0,k1), W(0,k0,k1), W(1,k0,k1), W(2,k0,k1)))*_K(g, g.dzi, 0, k0, k1))
+    k0, k1 = ks+2, ke-2
+    if k1 > k0:
+        parts.append(horiz(k0, k1) + np.abs(interp6_ws(W(-2,k0,k1), W(-1,k0,k1), W(0,k0,k1), W(1,k0,k1), W(2,k0,k1), W(3,k0,k1)))*_K(g, g.dzi, 0, k0, k1))
+    for p_ in parts:
+        cfl = max(cfl, TF(p_.max()))
+    return TF(cfl*TF(dt))
+
+
+# --------------------------------------------------------------------------------------
+# Diff_smag2 (reference include/diff_kernels.h:34-511, src/diff_smag2.cxx:148-269)
+# --------------------------------------------------------------------------------------
+DSMALL = 1.e-9   # Constants::dsmall (reference include/constants.h)
+KAPPA = 0.4      # Constants::kappa
+GRAV = 9.81      # Constants::grav
+
+def _pow2(a):
+    return a*a
+
+def _add_dsmall(val):
+    # `strain2[ijk] += Constants::dsmall` with a *double* constant: the sum is formed in double
+    # and rounded back to TF (include/diff_kernels.h:101,140; include/constants.h:97).
+    return (val.astype(np.float64) + DSMALL).astype(val.dtype)
+
+def diff_strain2(g, strain2, u, v, w, ugradbot, vgradbot, surface):
+    """include/diff_kernels.h:34-142"""
+    TF = g.TF
+    ks, ke = g.kstart, g.kend
+    dxi, dyi = TF(1.)/g.dx, TF(1.)/g.dy
+    e = TF(0.125); h = TF(0.5); two = TF(2.)
+    k_offset = 1 if surface else 0
+
+    def common(k0, k1):
+        U = lambda di=0, dj=0, dk=0: _S(g, u, dk, dj, di, k0, k1)
+        V = lambda di=0, dj=0, dk=0: _S(g, v, dk, dj, di, k0, k1)
+        W = lambda di=0, dj=0, dk=0: _S(g, w, dk, dj, di, k0, k1)
+        return U, V, W
+
+    if surface:
+        k0, k1 = ks, ks+1
+        U, V, W = common(k0, k1)
+        ij = (slice(g.jstart, g.jend), slice(g.istart, g.iend))
+        val = two*(
+            + _pow2((U(1)-U(0))*dxi)
+            + _pow2((V(0,1)-V(0,0))*dyi)
+            + _pow2((W(0,0,1)-W(0,0,0))*g.dzi[ks])
+            + e*_pow2((U(0,0)-U(0,-1))*dyi + (V(0,0)-V(-1,0))*dxi)
+            + e*_pow2((U(1,0)-U(1,-1))*dyi + (V(1,0)-V(0,0))*dxi)
+            + e*_pow2((U(0,1)-U(0,0))*dyi + (V(0,1)-V(-1,1))*dxi)
+            + e*_pow2((U(1,1)-U(1,0))*dyi + (V(1,1)-V(0,1))*dxi)
+            + h*_pow2(ugradbot[ij])
+            + e*_pow2((W(0,0,0)-W(-1,0,0))*dxi)
+            + e*_pow2((W(1,0,0)-W(0,0,0))*dxi)
+            + e*_pow2((W(0,0,1)-W(-1,0,1))*dxi)
+            + e*_pow2((W(1,0,1)-W(0,0,1))*dxi)
+            + h*_pow2(vgradbot[ij])
+            + e*_pow2((W(0,0,0)-W(0,-1,0))*dyi)
+            + e*_pow2((W(0,1,0)-W(0,0,0))*dyi)
+            + e*_pow2((W(0,0,1)-W(0,-1,1))*dyi)
+            + e*_pow2((W(0,1,1)-W(0,0,1))*dyi) )
+        _S(g, strain2, 0, 0, 0, k0, k1)[...] = _add_dsmall(val)
+
+    k0, k1 = ks + k_offset, ke
+    U, V, W = common(k0, k1)
+    dzi = _K(g, g.dzi, 0, k0, k1)
+    dzhi0 = _K(g, g.dzhi, 0, k0, k1)
+    dzhi1 = _K(g, g.dzhi, 1, k0, k1)
+    val = two*(
+        + _pow2((U(1)-U(0))*dxi)
+        + _pow2((V(0,1)-V(0,0))*dyi)
+        + _pow2((W(0,0,1)-W(0,0,0))*dzi)
+        + e*_pow2((U(0,0)-U(0,-1))*dyi + (V(0,0)-V(-1,0))*dxi)
+        + e*_pow2((U(1,0)-U(1,-1))*dyi + (V(1,0)-V(0,0))*dxi)
+        + e*_pow2((U(0,1)-U(0,0))*dyi + (V(0,1)-V(-1,1))*dxi)
+        + e*_pow2((U(1,1)-U(1,0))*dyi + (V(1,1)-V(0,1))*dxi)
+        + e*_pow2((U(0,0,0)-U(0,0,-1))*dzhi0 + (W(0,0,0)-W(-1,0,0))*dxi)
+        + e*_pow2((U(1,0,0)-U(1,0,-1))*dzhi0 + (W(1,0,0)-W(0,0,0))*dxi)
+        + e*_pow2((U(0,0,1)-U(0,0,0))*dzhi1 + (W(0,0,1)-W(-1,0,1))*dxi)
+        + e*_pow2((U(1,0,1)-U(1,0,0))*dzhi1 + (W(1,0,1)-W(0,0,1))*dxi)
+        + e*_pow2((V(0,0,0)-V(0,0,-1))*dzhi0 + (W(0,0,0)-W(0,-1,0))*dyi)
+        + e*_pow2((V(0,1,0)-V(0,1,-1))*dzhi0 + (W(0,1,0)-W(0,0,0))*dyi)
+        + e*_pow2((V(0,0,1)-V(0,0,0))*dzhi1 + (W(0,0,1)-W(0,-1,1))*dyi)
+        + e*_pow2((V(0,1,1)-V(0,1,0))*dzhi1 + (W(0,1,1)-W(0,0,1))*dyi) )
+    _S(g, strain2, 0, 0, 0, k0, k1)[...] = _add_dsmall(val)
+
+
+def diff_evisc(g, evisc, N2, bgradbot, z0m, cs, tPr, surface, mason=True):
+    """src/diff_smag2.cxx:148-269 (calc_evisc; ends with boundary_cyclic.exec(evisc))"""
+    TF = g.TF
+    ks, ke = g.kstart, g.kend
+    cs, tPr = TF(cs), TF(tPr)
+    one_m = TF(1. - DSMALL)
+    third = TF(1./3.)
+    mlen0_k = cs*np.power(g.dx*g.dy*g.dz, third).astype(TF)
+    ij = (slice(g.jstart, g.jend), slice(g.istart, g.iend))
+    if not surface:
+        k0, k1 = ks, ke
+        fac = _K(g, _pow2(mlen0_k), 0, k0, k1)
+        ev = _S(g, evisc, 0, 0, 0, k0, k1)
+        rit = _S(g, N2, 0, 0, 0, k0, k1) / ev / tPr
+        rit = np.minimum(rit, one_m)
+        ev[...] = fac * np.sqrt(ev) * np.sqrt(TF(1.) - rit)
+        evisc[ks-1] = evisc[ks]
+        evisc[ke] = evisc[ke-1]
+    else:
+        n_mason = TF(2.)
+        def mlen_of(k0, k1):
+            m0 = _K(g, mlen0_k, 0, k0, k1)
+            if not mason:
+                return m0 + np.zeros_like(_S(g, evisc, 0, 0, 0, k0, k1))
+            zz = _K(g, g.z, 0, k0, k1) + z0m[ij][None, :, :]
+            return np.power(TF(1.)/(TF(1.)/np.power(m0, n_mason) + TF(1.)/(np.power(TF(KAPPA)*zz, n_mason))), TF(1.)/n_mason)
+        # bottom (:216-239)
+        k0, k1 = ks, ks+1
+        ev = _S(g, evisc, 0, 0, 0, k0, k1)
+        rit = bgradbot[ij][None, :, :] / ev / tPr
+        rit = np.minimum(rit, one_m)
+        ev[...] = _pow2(mlen_of(k0, k1)) * np.sqrt(ev) * np.sqrt(TF(1.) - rit)
+        # interior (:241-265)
+        k0, k1 = ks+1, ke
+        ev = _S(g, evisc, 0, 0, 0, k0, k1)
+        rit = _S(g, N2, 0, 0, 0, k0, k1) / ev / tPr
+        rit = np.minimum(rit, one_m)
+        ev[...] = _pow2(mlen_of(k0, k1)) * np.sqrt(ev) * np.sqrt(TF(1.) - rit)
+    boundary_cyclic(g, evisc)
+
+
+def _diff_uv(g, at, a, b, w, evisc, fluxbot, fluxtop, rhoref, rhorefh, visc, surface, is_u):
+    """diff_u (include/diff_kernels.h:144-244) / diff_v (:246-347); `a` is the component
+    being diffused, `b` the other horizontal component.  For diff_v the roles of x and y swap."""
+    TF = g.TF
+    ks, ke = g.kstart, g.kend
+    dxi, dyi = TF(1.)/g.dx, TF(1.)/g.dy
+    visc = TF(visc)
+    q = TF(0.25); two = TF(2.)
+    ij = (slice(g.jstart, g.jend), slice(g.istart, g.iend))
+
+    def sh(arr, k0, k1):
+        # offsets given as (d_along, d_cross, dk): along = own direction of component a
+        if is_u:
+            return lambda da=0, dc=0, dk=0: _S(g, arr, dk, dc, da, k0, k1)
+        return lambda da=0, dc=0, dk=0: _S(g, arr, dk, da, dc, k0, k1)
+    d_al, d_cr = (dxi, dyi) if is_u else (dyi, dxi)
+
+    def horizontal(k0, k1):
+        E = sh(evisc, k0, k1); A = sh(a, k0, k1); B = sh(b, k0, k1)
+        if is_u:
+            ev_p = E(0) + visc                       # evisce
+            ev_m = E(-1) + visc                      # eviscw
+            ev_cp = q*(E(-1,0) + E(0,0) + E(-1,1) + E(0,1)) + visc     # eviscn
+            ev_cm = q*(E(-1,-1) + E(0,-1) + E(-1,0) + E(0,0)) + visc   # eviscs
+            return (
+                + ( ev_p*(A(1)-A(0))*d_al - ev_m*(A(0)-A(-1))*d_al ) * two*d_al
+                + ( ev_cp*((A(0,1)-A(0,0))*d_cr + (B(0,1)-B(-1,1))*d_al)
+                  - ev_cm*((A(0,0)-A(0,-1))*d_cr + (B(0,0)-B(-1,0))*d_al) ) * d_cr )
+        else:
+            # diff_v: evisce/eviscw are the 4-point means (cross = x), eviscn/s plain
+            # reference order: evisc[ijk-jj] + evisc[ijk] + evisc[ijk+ii-jj] + evisc[ijk+ii]
+            ev_e = q*(E(-1,0) + E(0,0) + E(-1,1) + E(0,1)) + visc
+            ev_w = q*(E(-1,-1) + E(0,-1) + E(-1,0) + E(0,0)) + visc
+            ev_n = E(0) + visc
+            ev_s = E(-1) + visc
+            return (
+                + ( ev_e*((A(0,1)-A(0,0))*d_cr + (B(0,1)-B(-1,1))*d_al)
+                  - ev_w*((A(0,0)-A(0,-1))*d_cr + (B(0,0)-B(-1,0))*d_al) ) * d_cr
+                + ( ev_n*(A(1)-A(0))*d_al - ev_s*(A(0)-A(-1))*d_al ) * two*d_al )
+
+    def ev_t(k0, k1):
+        E = sh(evisc, k0, k1)
+        return q*(E(-1,0,0) + E(0,0,0) + E(-1,0,1) + E(0,0,1)) + visc
+    def ev_b(k0, k1):
+        E = sh(evisc, k0, k1)
+        return q*(E(-1,0,-1) + E(0,0,-1) + E(-1,0,0) + E(0,0,0)) + visc
+    def top_flux(k0, k1):
+        A = sh(a, k0, k1); W = sh(w, k0, k1)
+        return _K(g, rhorefh, 1, k0, k1) * ev_t(k0, k1)*((A(0,0,1)-A(0,0,0))*_K(g, g.dzhi, 1, k0, k1) + (W(0,0,1)-W(-1,0,1))*d_al)
+    def bot_flux(k0, k1):
+        A = sh(a, k0, k1); W = sh(w, k0, k1)
+        return _K(g, rhorefh, 0, k0, k1) * ev_b(k0, k1)*((A(0,0,0)-A(0,0,-1))*_K(g, g.dzhi, 0, k0, k1) + (W(0,0,0)-W(-1,0,0))*d_al)
+
+    k_offset = 1 if surface else 0
+    if surface:
+        k0, k1 = ks, ks+1
+        _S(g, at, 0, 0, 0, k0, k1)[...] += (
+            horizontal(k0, k1)
+            + ( top_flux(k0, k1) + rhorefh[ks] * fluxbot[ij][None] ) / rhoref[ks] * g.dzi[ks] )
+        k0, k1 = ke-1, ke
+        _S(g, at, 0, 0, 0, k0, k1)[...] += (
+            horizontal(k0, k1)
+            + ( - rhorefh[ke] * fluxtop[ij][None] - bot_flux(k0, k1) ) / rhoref[ke-1] * g.dzi[ke-1] )
+    k0, k1 = ks + k_offset, ke - k_offset
+    if k1 > k0:
+        _S(g, at, 0, 0, 0, k0, k1)[...] += (
+            horizontal(k0, k1)
+            + ( top_flux(k0, k1) - bot_flux(k0, k1) ) / _K(g, rhoref, 0, k0, k1) * _K(g, g.dzi, 0, k0, k1) )
+
+
+def diff_u(g, ut, u, v, w, evisc, fluxbot, fluxtop, rhoref, rhorefh, visc, surface):
+    _diff_uv(g, ut, u, v, w, evisc, fluxbot, fluxtop, rhoref, rhorefh, visc, surface, True)
+
+def diff_v(g, vt, u, v, w, evisc, fluxbot, fluxtop, rhoref, rhorefh, visc, surface):
+    _diff_uv(g, vt, v, u, w, evisc, fluxbot, fluxtop, rhoref, rhorefh, visc, surface, False)
+
+
+def diff_w(g, wt, u, v, w, evisc, rhoref, rhorefh, visc):
+    """include/diff_kernels.h:349-392"""
+    TF = g.TF
+    ks, ke = g.kstart, g.kend
+    dxi, dyi = TF(1.)/g.dx, TF(1.)/g.dy
+    visc = TF(visc); q = TF(0.25); two = TF(2.)
+    k0, k1 = ks+1, ke
+    E = lambda di=0, dj=0, dk=0: _S(g, evisc, dk, dj, di, k0, k1)
+    U = lambda di=0, dj=0, dk=0: _S(g, u, dk, dj, di, k0, k1)
+    V = lambda di=0, dj=0, dk=0: _S(g, v, dk, dj, di, k0, k1)
+    W = lambda di=0, dj=0, dk=0: _S(g, w, dk, dj, di, k0, k1)
+    evisce = q*(E(0,0,-1) + E(0,0,0) + E(1,0,-1) + E(1,0,0)) + visc
+    eviscw = q*(E(-1,0,-1) + E(-1,0,0) + E(0,0,-1) + E(0,0,0)) + visc
+    eviscn = q*(E(0,0,-1) + E(0,0,0) + E(0,1,-1) + E(0,1,0)) + visc
+    eviscs = q*(E(0,-1,-1) + E(0,-1,0) + E(0,0,-1) + E(0,0,0)) + visc
+    evisct = E(0,0,0) + visc
+    eviscb = E(0,0,-1) + visc
+    dzhi = _K(g, g.dzhi, 0, k0, k1)
+    _S(g, wt, 0, 0, 0, k0, k1)[...] += (
+        + ( evisce*((W(1)-W(0))*dxi + (U(1,0,0)-U(1,0,-1))*dzhi)
+          - eviscw*((W(0)-W(-1))*dxi + (U(0,0,0)-U(0,0,-1))*dzhi) ) * dxi
+        + ( eviscn*((W(0,1)-W(0,0))*dyi + (V(0,1,0)-V(0,1,-1))*dzhi)
+          - eviscs*((W(0,0)-W(0,-1))*dyi + (V(0,0,0)-V(0,0,-1))*dzhi) ) * dyi
+        + ( _K(g, rhoref, 0, k0, k1) * evisct*(W(0,0,1)-W(0,0,0))*_K(g, g.dzi, 0, k0, k1)
+          - _K(g, rhoref,-1, k0, k1) * eviscb*(W(0,0,0)-W(0,0,-1))*_K(g, g.dzi,-1, k0, k1) ) / _K(g, rhorefh, 0, k0, k1) * two*dzhi )
+
+
+def diff_c(g, at, a, evisc, fluxbot, fluxtop, rhoref, rhorefh, tPr, visc, surface):
+    """include/diff_kernels.h:394-484.  dxidxi = 1./(dx*dx) computed in double then cast (src/diff_smag2.cxx:445)."""
+    TF = g.TF
+    ks, ke = g.kstart, g.kend
+    dxidxi = TF(1./(float(g.dx)*float(g.dx))); dyidyi = TF(1./(float(g.dy)*float(g.dy)))
+    visc = TF(visc); h = TF(0.5)
+    tPr_i = TF(1)/TF(tPr)
+    ij = (slice(g.jstart, g.jend), slice(g.istart, g.iend))
+
+    def parts(k0, k1):
+        E = lambda di=0, dj=0, dk=0: _S(g, evisc, dk, dj, di, k0, k1)
+        A = lambda di=0, dj=0, dk=0: _S(g, a, dk, dj, di, k0, k1)
+        evisce = h*(E(0)+E(1)) * tPr_i + visc
+        eviscw = h*(E(-1)+E(0)) * tPr_i + visc
+        eviscn = h*(E(0,0)+E(0,1)) * tPr_i + visc
+        eviscs = h*(E(0,-1)+E(0,0)) * tPr_i + visc
+        hor_x = ( evisce*(A(1)-A(0)) - eviscw*(A(0)-A(-1)) ) * dxidxi
+        hor_y = ( eviscn*(A(0,1)-A(0,0)) - eviscs*(A(0,0)-A(0,-1)) ) * dyidyi
+        top = lambda: _K(g, rhorefh, 1, k0, k1) * (h*(E(0,0,0)+E(0,0,1)) * tPr_i + visc)*(A(0,0,1)-A(0,0,0))*_K(g, g.dzhi, 1, k0, k1)
+        bot = lambda: _K(g, rhorefh, 0, k0, k1) * (h*(E(0,0,-1)+E(0,0,0)) * tPr_i + visc)*(A(0,0,0)-A(0,0,-1))*_K(g, g.dzhi, 0, k0, k1)
+        return hor_x, hor_y, top, bot
+
+    k_offset = 1 if surface else 0
+    if surface:
+        k0, k1 = ks, ks+1
+        hx, hy, top, bot = parts(k0, k1)
+        _S(g, at, 0, 0, 0, k0, k1)[...] += (
+            + hx + hy + ( top() + rhorefh[ks] * fluxbot[ij][None] ) / rhoref[ks] * g.dzi[ks] )
+        k0, k1 = ke-1, ke
+        hx, hy, top, bot = parts(k0, k1)
+        _S(g, at, 0, 0, 0, k0, k1)[...] += (
+            + hx + hy + ( -rhorefh[ke] * fluxtop[ij][None] - bot() ) / rhoref[ke-1] * g.dzi[ke-1] )
+    k0, k1 = ks + k_offset, ke - k_offset
+    if k1 > k0:
+        hx, hy, top, bot = parts(k0, k1)
+        _S(g, at, 0, 0, 0, k0, k1)[...] += (
+            + hx + hy + ( top() - bot() ) / _K(g, rhoref, 0, k0, k1) * _K(g, g.dzi, 0, k0, k1) )
+
+
+def diff_dnmul(g, evisc, tPr):
+    """include/diff_kernels.h:486-511; dxidxi passed as double 1./(dx*dx) cast to TF (src/diff_smag2.cxx:317-326)"""
+    TF = g.TF
+    dxidxi = TF(1./(float(g.dx)*float(g.dx))); dyidyi = TF(1./(float(g.dy)*float(g.dy)))
+    tPrfac_i = TF(1)/min(TF(1.), TF(tPr))
+    dzi = _K(g, g.dzi)
+    return TF(np.abs(_S(g, evisc)*tPrfac_i*(dxidxi + dyidyi + dzi*dzi)).max())
+
+
+# --------------------------------------------------------------------------------------
+# Thermo_dry (reference src/thermo_dry.cxx:66-78, 165-179)
+# --------------------------------------------------------------------------------------
+def thermo_dry_N2(g, N2, th, thref):
+    TF = g.TF
+    _S(g, N2)[...] = TF(GRAV)/_K(g, thref)*TF(0.5)*(_S(g, th, 1) - _S(g, th, -1))*_K(g, g.dzi)
+
+def thermo_dry_buoyancy_tend_2nd(g, wt, th, threfh):
+    TF = g.TF
+    k0, k1 = g.kstart+1, g.kend
+    _S(g, wt, 0, 0, 0, k0, k1)[...] += TF(GRAV)/_K(g, threfh, 0, k0, k1) * (
+        interp2(_S(g, th, -1, 0, 0, k0, k1), _S(g, th, 0, 0, 0, k0, k1)) - _K(g, threfh, 0, k0, k1))
+
+
+# --------------------------------------------------------------------------------------
+# FFTW r2r semantics (reference call sites src/fft.cxx:145-155; FFTW3 manual "The Halfcomplex-format DFT")
+# --------------------------------------------------------------------------------------
+def r2hc(x, axis):
+    """FFTW_R2HC along `axis`: [r0, r1, ..., r_{n/2}, i_{(n+1)/2-1}, ..., i_1], unnormalised."""
+    n = x.shape[axis]
+    X = np.fft.rfft(x.astype(np.float64), axis=axis)
+    out = np.empty(x.shape, np.float64)
+    sl = [slice(None)]*x.ndim
+    def put(dst, src):
+        d = list(sl); d[axis] = dst
+        out[tuple(d)] = src
+    nre = n//2 + 1
+    put(slice(0, nre), X.real)
+    nim = (n+1)//2 - 1
+    if nim > 0:
+        s = list(sl); s[axis] = slice(nim, 0, -1)
+        put(slice(nre, n), X.imag[tuple(s)])
+    return out.astype(x.dtype)
+
+def hc2r(x, axis):
+    """FFTW_HC2R along `axis` (unnormalised inverse of r2hc)."""
+    n = x.shape[axis]
+    nre = n//2 + 1
+    shp = list(x.shape); shp[axis] = nre
+    X = np.zeros(shp, np.complex128)
+    sl = [slice(None)]*x.ndim
+    s = list(sl); s[axis] = slice(0, nre)
+    X.real[...] = x[tuple(s)]
+    nim = (n+1)//2 - 1
+    if nim > 0:
+        d = list(sl); d[axis] = slice(1, nim+1)
+        s2 = list(sl); s2[axis] = slice(n-1, nre-1, -1)
+        X.imag[tuple(d)] = x[tuple(s2)]
+    out = np.fft.irfft(X, n=n, axis=axis) * n
+    return out.astype(x.dtype)
+
+
+# --------------------------------------------------------------------------------------
+# Pres_2 (reference src/pres_2.cxx:124-422)
+# --------------------------------------------------------------------------------------
+class Pres2:
+    def __init__(self, g, rhoref, rhorefh):
+        """set_values: src/pres_2.cxx:124-153"""
+        TF = g.TF
+        self.g = g
+        dxidxi = TF(1./(g.dx*g.dx)); dyidyi = TF(1./(g.dy*g.dy))
+        pi = TF(np.arccos(TF(-1.)))
+        self.bmati = np.zeros(g.itot, TF); self.bmatj = np.zeros(g.jtot, TF)
+        for j in range(g.jtot//2+1):
+            self.bmatj[j] = TF(2.) * (np.cos(TF(2.)*pi*TF(j)/TF(g.jtot))-TF(1.)) * dyidyi
+        for j in range(g.jtot//2+1, g.jtot):
+            self.bmatj[j] = self.bmatj[g.jtot-j]
+        for i in range(g.itot//2+1):
+            self.bmati[i] = TF(2.) * (np.cos(TF(2.)*pi*TF(i)/TF(g.itot))-TF(1.)) * dxidxi
+        for i in range(g.itot//2+1, g.itot):
+            self.bmati[i] = self.bmati[g.itot-i]
+        kgc = g.kgc
+        self.a = np.zeros(g.kmax, TF); self.c = np.zeros(g.kmax, TF)
+        for k in range(g.kmax):
+            self.a[k] = g.dz[k+kgc] * rhorefh[k+kgc]*g.dzhi[k+kgc]
+            self.c[k] = g.dz[k+kgc] * rhorefh[k+kgc+1]*g.dzhi[k+kgc+1]
+        self.rhoref, self.rhorefh = rhoref, rhorefh
+
+    def input(self, u, v, w, ut, vt, wt, dt):
+        """src/pres_2.cxx:155-196; returns compact p (kmax, jmax, imax)"""
+        g = self.g; TF = g.TF
+        dxi, dyi = TF(1.)/g.dx, TF(1.)/g.dy
+        dti = TF(TF(1.)/dt)       # TF(1.)/double dt, then stored in a TF
+        boundary_cyclic(g, ut, EDGE_EW)
+        boundary_cyclic(g, vt, EDGE_NS)
+        rho = _K(g, self.rhoref)
+        return ( rho * ( (_S(g, ut, 0, 0, 1) + _S(g, u, 0, 0, 1) * dti) - (_S(g, ut) + _S(g, u) * dti) ) * dxi
+               + rho * ( (_S(g, vt, 0, 1, 0) + _S(g, v, 0, 1, 0) * dti) - (_S(g, vt) + _S(g, v) * dti) ) * dyi
+               + ( _K(g, self.rhorefh, 1) * (_S(g, wt, 1) + _S(g, w, 1) * dti)
+                 - _K(g, self.rhorefh, 0) * (_S(g, wt) + _S(g, w) * dti) ) * _K(g, g.dzi) )
+
+    def tdma(self, p, b):
+        """src/pres_2.cxx:202-263 (vectorised over the i,j plane; same per-column operation order)"""
+        a, c = self.a, self.c
+        kmax = self.g.kmax
+        work3d = np.zeros_like(p)
+        work2d = b[0].copy()
+        p[0] /= work2d
+        for k in range(1, kmax):
+            work3d[k] = c[k-1] / work2d
+            work2d = b[k] - a[k]*work3d[k]
+            p[k] -= a[k]*p[k-1]
+            p[k] /= work2d
+        for k in range(kmax-2, -1, -1):
+            p[k] -= work3d[k+1]*p[k+1]
+
+    def solve(self, pc, p, tdma=None):
+        """src/pres_2.cxx:266-362.  pc: compact rhs; p: ghosted output array."""
+        g = self.g; TF = g.TF
+        kgc = g.kgc
+        # fft.exec_forward: x then y (src/fft.cxx:338-394)
+        pc = r2hc(pc, axis=2)
+        pc = r2hc(pc, axis=1)
+        dz = g.dz[kgc:kgc+g.kmax][:, None, None]
+        rho = self.rhoref[kgc:kgc+g.kmax][:, None, None]
+        b = dz*dz * rho*(self.bmati[None, None, :] + self.bmatj[None, :, None]) - (self.a + self.c)[:, None, None]
+        pc = dz*dz * pc
+        b[0] += self.a[0]
+        top = np.full((g.jtot, g.itot), self.c[g.kmax-1], TF)
+        top[0, 0] = -self.c[g.kmax-1]
+        b[g.kmax-1] += top
+        pc = np.ascontiguousarray(pc); b = np.ascontiguousarray(b.astype(TF))
+        (tdma or self.tdma)(pc, b)
+        # fft.exec_backward: y then x with /jtot, /itot (src/fft.cxx:396-452)
+        pc = hc2r(pc, axis=1) / TF(g.jtot)
+        pc = hc2r(pc, axis=2) / TF(g.itot)
+        _S(g, p)[...] = pc
+        p[g.kstart-1, g.jstart:g.jend, g.istart:g.iend] = p[g.kstart, g.jstart:g.jend, g.istart:g.iend]
+        boundary_cyclic(g, p)
+
+    def output(self, ut, vt, wt, p):
+        """src/pres_2.cxx:364-387"""
+        g = self.g; TF = g.TF
+        dxi, dyi = TF(1.)/g.dx, TF(1.)/g.dy
+        _S(g, ut)[...] -= (_S(g, p) - _S(g, p, 0, 0, -1)) * dxi
+        _S(g, vt)[...] -= (_S(g, p) - _S(g, p, 0, -1, 0)) * dyi
+        _S(g, wt)[...] -= (_S(g, p) - _S(g, p, -1, 0, 0)) * _K(g, g.dzhi)
+
+    def exec(self, p, u, v, w, ut, vt, wt, dt, tdma=None):
+        """src/pres_2.cxx:66-94"""
+        pc = self.input(u, v, w, ut, vt, wt, dt)
+        self.solve(pc, p, tdma)
+        self.output(ut, vt, wt, p)
+
+    def divergence(self, u, v, w):
+        """src/pres_2.cxx:390-422"""
+        g = self.g; TF = g.TF
+        dxi, dyi = TF(1.)/g.dx, TF(1.)/g.dy
+        div = ( _K(g, self.rhoref)*((_S(g, u, 0, 0, 1)-_S(g, u))*dxi + (_S(g, v, 0, 1, 0)-_S(g, v))*dyi)
+              + (_K(g, self.rhorefh, 1)*_S(g, w, 1)-_K(g, self.rhorefh, 0)*_S(g, w))*_K(g, g.dzi) )
+        return TF(np.abs(div).max())
+
+
+# --------------------------------------------------------------------------------------
+# Timeloop rk3 (reference src/timeloop.cxx:250-286, 415-423)
+# --------------------------------------------------------------------------------------
+RK3_CA = (0., -5./9., -153./128.)
+RK3_CB = (1./3., 15./16., 8./15.)
+
+def rk3(g, a, at, substep, dt):
+    TF = g.TF
+    _S(g, a)[...] += TF(RK3_CB[substep])*TF(dt)*_S(g, at)
+    substepn = (substep+1) % 3
+    if substepn == 0:
+        at[...] = TF(0.)
+    else:
+        _S(g, at)[...] *= TF(RK3_CA[substepn])
+
+def rk3_subdt(dt, substep):
+    """get_sub_time_step: double arithmetic (src/timeloop.cxx:338-342, 415-423)"""
+    return RK3_CB[substep]*float(dt)
