@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""
+bench.py -- grid-point RK3 steps/s of the dynamical-core hot path (BASELINE.json metric).
+
+  python bench.py --gpus 1 --steps K --warmup W            our arm (CUDA, libmhhb200.so)
+  python bench.py --impl reference ...                      the reference's own CPU kernels on host cores
+
+One "step" = one full RK3 time step (3 sub-steps: cyclic + vertical ghost cells, eddy viscosity,
+advection + diffusion + buoyancy tendencies, FFT/tridiagonal pressure solve, pressure correction
++ RK3 update) of a drycblles-shaped LES (advec_2i5 + diff_smag2 + pres_2 + thermo_dry, S = 1
+scalar) on a synthetic grid.  Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+METRIC = "grid-point RK3 steps/s"
+UNIT = "grid-point-steps/s"
+
+
+def parse_workload(s):
+    it, jt, kt = (int(x) for x in s.lower().split("x"))
+    return it, jt, kt
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return json.load(fh), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm)//2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def algorithmic_bytes_per_point_substep(S, B):
+    """(41 + 7 S) * sizeof(TF) bytes per grid point per sub-step."""
+    return (41 + 7*S)*B
+
+
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from microhh_b200 import dycore as D
+    from microhh_b200.grid import GridData
+    from microhh_b200.synthetic import make_case
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dtype = np.float64 if args.dtype == "f64" else np.float32
+    B = np.dtype(dtype).itemsize
+    itot, jtot, ktot = parse_workload(args.workload)
+    S = 1
+
+    # replicas: each rank owns an independent LES domain of the named shape (weak scaling; the
+    # slab-decomposed single-domain path is the multi-GPU context)
+    gd = GridData(itot, jtot, ktot, 25.*itot, 25.*jtot, 25.*ktot, 3, 3, 1, dtype)
+    case = make_case(gd, seed=2 + rank, noise=0.01)
+    ctx = D.Context(gd, local_rank)
+    ctx.set_basestate(case["rhoref"], case["rhorefh"], case["thref"], case["threfh"])
+    f = D.Fields(ctx, case)
+    prm = D.make_params()
+    dyc = D.Dycore(ctx, prm)
+    dt = args.dt
+    npts = gd.npoints
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        dyc.step(f, dt)
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launch_count
+    ctx.profile_start()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        dyc.step(f, dt)
+    e1.record()
+    barrier()
+    prof = ctx.profile_stop()
+    launches = ctx.launch_count - l0
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    if rank == 0:
+        sampler.stop_flag.set(); sampler.join(timeout=2)
+    finite = bool(torch.isfinite(f["u"]).all().item())
+
+    # ---- end to end through the C ABI with HOST (pinned) buffers ------------------------------
+    e2e = None
+    if not args.no_e2e:
+        names = ["u", "v", "w", "th"]
+        host = {n: torch.empty(gd.shape, dtype=ctx.torch_dtype).pin_memory() for n in names}
+        for n in names:
+            host[n].copy_(torch.from_numpy(case[n]))
+        for n in ("ut", "vt", "wt", "tht"):
+            f[n].zero_()
+        k_e2e = max(1, min(args.steps, args.e2e_steps))
+        dyc.step_host(f, dt, 1, host["u"], host["v"], host["w"], [host["th"]])   # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(k_e2e):
+            dyc.step_host(f, dt, 1, host["u"], host["v"], host["w"], [host["th"]])
+        torch.cuda.synchronize()
+        t_e2e = (time.perf_counter() - t0)
+        if world > 1:
+            t = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_e2e = float(t.item())
+        nbytes = 4*gd.ncells*B
+        e2e = {"value": world*npts*k_e2e/t_e2e, "unit": UNIT, "h2d_bytes_per_step": nbytes,
+               "d2h_bytes_per_step": nbytes, "steps": k_e2e}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_src = measured_peaks()
+    ms_per_step = ms/args.steps
+    value = world*npts*args.steps/(ms*1e-3)
+    # dominant kernel from the live CUDA-event profile
+    top = max(prof.items(), key=lambda kv: kv[1]["ms"]) if prof else (None, None)
+    alg = {  # algorithmic array passes per launch, in units of N*B bytes
+        "tend_uvw_kernel": 4 + 6, "tend_s_kernel": 5 + 2, "evisc_kernel": 5,
+        "fft_x_forward_kernel": 7, "fft_y_forward_kernel": 2, "fft_y_backward_kernel": 2,
+        "tdma_solve_kernel": 2, "fft_x_backward_kernel": 2, "pres_out_rk3_kernel": 13, "rk3_kernel": 4,
+    }
+    roofline = None
+    if top[0] is not None:
+        name, st = top
+        per_launch_ms = st["ms"]/st["n"]
+        passes = alg.get(name, 0)
+        achieved = passes*npts*B/(per_launch_ms*1e-3)/1e9
+        roofline = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": achieved/peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                    "share_of_step": st["ms"]/ms, "algorithmic_passes": passes}
+    step_alg_bytes = 3*algorithmic_bytes_per_point_substep(S, B)*npts
+    whole = {"algorithmic_bytes_per_step": step_alg_bytes,
+             "achieved_gbs": step_alg_bytes/(ms_per_step*1e-3)/1e9,
+             "frac_of_hbm": step_alg_bytes/(ms_per_step*1e-3)/1e9/peaks["hbm_gbs"]}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            cpu = cpu_baseline(dtype, args.cpu_sample, dt)
+        except Exception as ex:   # the baseline is a report, never a reason to lose the GPU number
+            cpu = {"value": None, "unit": UNIT, "error": str(ex)[:200]}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": f"drycblles-shaped LES {itot}x{jtot}x{ktot} per GPU, advec_2i5+diff_smag2+pres_2+thermo_dry, S=1",
+                       "parallelism": "replicas only" if world > 1 else "single GPU",
+                       "l2": "inputs larger than L2 (each field >> 126 MB)", "dt": dt},
+            "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": launches,
+            "roofline": roofline, "whole_step_roofline": whole, "cpu_baseline": cpu,
+            "kernels_ms_per_step": {k: v["ms"]/args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
+            "finite": finite}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------
+def cpu_baseline(dtype, sample, dt, max_threads=None, min_seconds=8.0):
+    """Reference CPU kernels (oracle/_ref, built from the reference's own sources with its release
+    flags) -- or the numpy port when that library is absent -- timed on the host cores: every
+    thread advances its own independent sub-domain of shape `sample` by full RK3 steps."""
+    from oracle import oracle as O, step as ostep, refbind
+    from microhh_b200.grid import GridData
+    from microhh_b200.synthetic import make_case
+    it, jt, kt = parse_workload(sample)
+    cores = max_threads or (os.cpu_count() or 1)
+    use_ref = refbind.available(fast=True)
+    kind = "reference" if use_ref else "port"
+    if not use_ref:
+        cores = min(cores, 4)
+    work = []
+    for t in range(cores):
+        g = O.Grid(it, jt, kt, 25.*it, 25.*jt, 25.*kt, 3, 3, 1, dtype)
+        gd = GridData(it, jt, kt, 25.*it, 25.*jt, 25.*kt, 3, 3, 1, dtype)
+        K = refbind.RefKernels(g, fast=True) if use_ref else O.NumpyKernels(g)
+        work.append((g, K, make_case(gd, seed=10 + t, noise=0.01)))
+    prm = ostep.default_params()
+    counts = [0]*cores
+    stop = threading.Event()
+
+    def worker(i):
+        g, K, c = work[i]
+        pres = None
+        while not stop.is_set():
+            for ss in range(3):
+                pres = ostep.dycore_substep(g, K, c, prm, ss, dt, pres)
+            counts[i] += 1
+
+    # NOTE: ref_set_geom is process-global in the harness; all threads use the same geometry.
+    threads = [threading.Thread(target=worker, args=(i,), daemon=True) for i in range(cores)]
+    t0 = time.perf_counter()
+    for th in threads:
+        th.start()
+    time.sleep(min_seconds)
+    stop.set()
+    for th in threads:
+        th.join()
+    el = time.perf_counter() - t0
+    total = sum(counts)
+    return {"value": total*it*jt*kt/el, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{total} RK3 steps of {cores} independent {it}x{jt}x{kt} sub-domains (one per thread) in {el:.1f} s; "
+                      "FFT = numpy pocketfft stand-in for FFTW"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    dtype = np.float64 if args.dtype == "f64" else np.float32
+    itot, jtot, ktot = parse_workload(args.workload)
+    t0 = time.perf_counter()
+    secs = max(4.0, min(20.0, 4.0*(args.steps + args.warmup)))
+    cpu = cpu_baseline(dtype, args.cpu_sample, args.dt, min_seconds=secs)
+    el = time.perf_counter() - t0
+    it, jt, kt = parse_workload(args.cpu_sample)
+    line = {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT,
+            "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3*it*jt*kt*cpu["cores"]/cpu["value"] if cpu["value"] else None,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": f"drycblles-shaped LES {itot}x{jtot}x{ktot} per GPU, advec_2i5+diff_smag2+pres_2+thermo_dry, S=1",
+                       "note": "CPU arm times a bounded sample of the same workload: " + cpu["sample"]},
+            "cpu_baseline": cpu,
+            "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": el}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("MHH_BENCH_WORKLOAD", "512x512x512"))
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--dt", type=float, default=1.0)
+    ap.add_argument("--cpu-sample", default="64x64x64")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

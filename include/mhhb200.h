@@ -1,0 +1,182 @@
+/*
+ * mhhb200.h -- C ABI of libmhhb200.so, the B200-native (sm_100a) dynamical core for MicroHH.
+ *
+ * This is the drop-in boundary for the hot path of one RK3 sub-step: every entry point
+ * replaces one member function of the reference's Advec / Diff / Pres / Boundary_cyclic /
+ * Timeloop classes (cited per function, paths relative to the reference tree).  A thin C++
+ * adapter (microhh_b200/host/mhh_adapters.hpp) forwards the class methods to
+ * these functions so `microhh init/run`, the .ini/.nc case files and the Field3d layout stay
+ * unchanged.
+ *
+ * Conventions
+ *  - Plain C: pointers and sizes only, no C++/torch types.
+ *  - Precision is a property of the context (MHH_F64 = default build, MHH_F32 = USESP build);
+ *    field pointers are `void*` to arrays of that type.
+ *  - Field arrays are DEVICE pointers in the reference's ghosted layout
+ *    ijk = i + j*icells + k*icells*jcells (include/grid.h:49-134); the caller owns them.
+ *    2-D companions (flux_bot, grad_bot, dudz_mo, ...) are DEVICE arrays of icells*jcells.
+ *  - Metric/base-state profiles passed at create / set_basestate time are HOST arrays of kcells.
+ *  - Every function returns 0 on success or a negative MHH_E_* code; mhh_last_error() gives the
+ *    message.  No exception crosses the ABI.
+ *  - Calls are asynchronous on the context's stream and ordered; mhh_sync() waits.
+ *    A context is not re-entrant; use one per GPU.
+ *  - There is NO CPU fallback: without a CUDA device every compute call fails with MHH_E_CUDA.
+ */
+#ifndef MHHB200_H
+#define MHHB200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#  define MHH_API __attribute__((visibility("default")))
+#else
+#  define MHH_API
+#endif
+
+#define MHH_F64 0
+#define MHH_F32 1
+
+#define MHH_OK          0
+#define MHH_E_INVALID  -1   /* bad argument / unsupported configuration */
+#define MHH_E_CUDA     -2   /* CUDA runtime error (message has the detail) */
+#define MHH_E_NOMEM    -3
+
+#define MHH_MAX_SCALARS 8
+
+/* Boundary_cyclic Edge (include/boundary_cyclic.h:33) */
+#define MHH_EDGE_EAST_WEST   0
+#define MHH_EDGE_NORTH_SOUTH 1
+#define MHH_EDGE_BOTH        2
+
+/* Boundary_type subset used for the vertical ghost cells (src/boundary.cxx:700-772) */
+#define MHH_BC_NONE     -1
+#define MHH_BC_DIRICHLET 0
+#define MHH_BC_NEUMANN   1   /* also Flux_type */
+
+typedef struct mhh_ctx mhh_ctx;
+
+/* POD copy of Grid_data<TF> (include/grid.h:49-134).  z..dzhi: HOST arrays, kcells entries,
+ * element type = the context's precision. */
+typedef struct mhh_grid_desc
+{
+    int itot, jtot, ktot;        /* global size */
+    int imax, jmax, kmax;        /* local block (== global for npx=npy=1) */
+    int igc, jgc, kgc;           /* ghost cells */
+    double xsize, ysize, zsize;
+    const void* z;
+    const void* zh;
+    const void* dz;
+    const void* dzh;
+    const void* dzi;
+    const void* dzhi;
+    int npx, npy;                /* process grid (src/master_parallel.cxx:103-153); 1,1 = single GPU */
+    int mpicoordx, mpicoordy;
+} mhh_grid_desc;
+
+/* Device pointers to the 3-D fields and their 2-D companions (Fields maps mp/mt/sp/st/sd,
+ * include/fields.h:134-143; Field3d companions include/field3d.h:49-78). */
+typedef struct mhh_fields
+{
+    void *u, *v, *w;             /* fields.mp */
+    void *ut, *vt, *wt;          /* fields.mt */
+    void *evisc;                 /* fields.sd["evisc"] */
+    void *p;                     /* fields.sd["p"] */
+    int   ns;                    /* number of prognostic scalars */
+    void *s[MHH_MAX_SCALARS];    /* fields.sp */
+    void *st[MHH_MAX_SCALARS];   /* fields.st */
+    double svisc[MHH_MAX_SCALARS];
+    double visc;
+    /* 2-D companions; may be NULL when the surface model is off */
+    void *u_fluxbot, *u_fluxtop, *v_fluxbot, *v_fluxtop;
+    void *s_fluxbot[MHH_MAX_SCALARS], *s_fluxtop[MHH_MAX_SCALARS];
+    /* Boundary_surface outputs consumed by Diff_smag2 (Boundary::get_dudz/dvdz/dbdz/z0m) */
+    void *dudz_mo, *dvdz_mo, *dbdz_mo, *z0m;
+    /* vertical ghost-cell inputs: value (Dirichlet) or gradient (Neumann/flux) at bottom/top */
+    void *u_bot, *u_gradbot, *u_top, *u_gradtop;
+    void *v_bot, *v_gradbot, *v_top, *v_gradtop;
+    void *s_bot[MHH_MAX_SCALARS], *s_gradbot[MHH_MAX_SCALARS], *s_top[MHH_MAX_SCALARS], *s_gradtop[MHH_MAX_SCALARS];
+} mhh_fields;
+
+/* Run-time switches of the path ([advec] [diff] [boundary] [thermo] of the .ini). */
+typedef struct mhh_params
+{
+    int    swadvec;              /* 25 = 2i5 (others: see mhh_advec_exec) */
+    int    swdiff;               /* 1 = smag2 */
+    int    swthermo;             /* 0 = off, 1 = dry (buoyancy from scalar 0 = th) */
+    int    surface_model;        /* Boundary switch != "default"  (Surface_model::Enabled) */
+    int    sw_mason;             /* [diff] swmason */
+    double cs, tPr;              /* [diff] cs, tPr */
+    int    mbcbot, mbctop;       /* MHH_BC_* for u,v */
+    int    sbcbot[MHH_MAX_SCALARS], sbctop[MHH_MAX_SCALARS];
+} mhh_params;
+
+/* ---- context ----------------------------------------------------------------------------- */
+MHH_API int  mhh_ctx_create(const mhh_grid_desc* grid, int dtype, int device, mhh_ctx** out);
+MHH_API void mhh_ctx_destroy(mhh_ctx* ctx);
+MHH_API const char* mhh_last_error(const mhh_ctx* ctx);
+MHH_API int  mhh_sync(mhh_ctx* ctx);
+/* Use an externally owned CUDA stream (cudaStream_t as void*); NULL = context's own stream. */
+MHH_API int  mhh_set_stream(mhh_ctx* ctx, void* cuda_stream);
+/* Fields::rhoref/rhorefh (include/fields.h:162-188) and Thermo_dry's thref/threfh; HOST arrays (kcells).
+ * thref/threfh may be NULL when swthermo == 0.  Also (re)builds the Pres_2 coefficient tables. */
+MHH_API int  mhh_set_basestate(mhh_ctx* ctx, const void* rhoref, const void* rhorefh, const void* thref, const void* threfh);
+/* number of kernel launches issued by this context so far (for bench.py's gpu_launches) */
+MHH_API long long mhh_launch_count(const mhh_ctx* ctx);
+/* Per-kernel device timing (CUDA events on the context's stream): start, run any calls, stop.
+ * `json` receives a context-owned string {"kernel": {"n": launches, "ms": total}, ...}. */
+MHH_API int mhh_profile_start(mhh_ctx* ctx);
+MHH_API int mhh_profile_stop(mhh_ctx* ctx, const char** json);
+/* bytes of device memory owned by the context (workspace, tables) */
+MHH_API long long mhh_workspace_bytes(const mhh_ctx* ctx);
+
+/* ---- Boundary_cyclic<TF>::exec / exec_2d  (src/boundary_cyclic.cxx:369-507) ---------------- */
+MHH_API int mhh_boundary_cyclic(mhh_ctx* ctx, void* fld, int edge);
+MHH_API int mhh_boundary_cyclic_2d(mhh_ctx* ctx, void* fld2d);
+
+/* ---- Boundary<TF>::set_ghost_cells, 2nd order, one field (src/boundary.cxx:700-772, 933-961) */
+MHH_API int mhh_boundary_ghost_cells_2nd(mhh_ctx* ctx, void* fld, int bcbot, const void* bot, const void* gradbot,
+                                 int bctop, const void* top, const void* gradtop);
+
+/* ---- Advec<TF>::exec / get_cfl  (Advec_2i5: src/advec_2i5.cxx:955-1063) -------------------- */
+MHH_API int mhh_advec_exec(mhh_ctx* ctx, int swadvec, const mhh_fields* f);
+MHH_API int mhh_advec_get_cfl(mhh_ctx* ctx, int swadvec, const mhh_fields* f, double dt, double* cfl);
+
+/* ---- Diff_smag2<TF>::exec_viscosity / exec / get_dn  (src/diff_smag2.cxx:312-356, 381-607) --
+ * n2: device N2 field from Thermo::get_thermo_field("N2"), or NULL to derive it from scalar 0
+ * (th) as Thermo_dry does (src/thermo_dry.cxx:66-78). */
+MHH_API int mhh_diff_smag2_exec_viscosity(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm, const void* n2);
+MHH_API int mhh_diff_smag2_exec(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm);
+MHH_API int mhh_diff_smag2_get_dn(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm, double dt, double* dn);
+
+/* ---- Thermo_dry<TF>::exec (buoyancy on wt) and get_thermo_field("N2")  (src/thermo_dry.cxx) -- */
+MHH_API int mhh_thermo_dry_exec(mhh_ctx* ctx, void* wt, const void* th);
+MHH_API int mhh_thermo_dry_n2(mhh_ctx* ctx, void* n2, const void* th);
+
+/* ---- Pres_2<TF>::exec / check_divergence  (src/pres_2.cxx:66-105) --------------------------- */
+MHH_API int mhh_pres_exec(mhh_ctx* ctx, int swpres, const mhh_fields* f, double sub_dt);
+MHH_API int mhh_pres_check_divergence(mhh_ctx* ctx, int swpres, const mhh_fields* f, double* divmax);
+/* Spectral pieces, exposed for tests / cuFFT comparison: forward x+y transform of a compact
+ * (kmax,jmax,imax) real device array into the context workspace and back. */
+MHH_API int mhh_pres_fft_roundtrip(mhh_ctx* ctx, const void* in_compact, void* out_compact, int solve);
+
+/* ---- Timeloop<TF>::exec, rk3 of one (field, tendency) pair  (src/timeloop.cxx:250-286) ------- */
+MHH_API int mhh_timeloop_rk3(mhh_ctx* ctx, void* a, void* at, int substep, double dt);
+
+/* ---- One whole RK3 sub-step of the dynamical core, fused (Model::exec, src/model.cxx:356-504):
+ * cyclic + vertical ghost cells -> eddy viscosity -> advection+diffusion(+buoyancy) tendencies ->
+ * pressure solve -> pressure correction fused with the RK3 update of u,v,w and the scalars. */
+MHH_API int mhh_dycore_substep(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm, int substep, double dt);
+/* Three sub-steps. */
+MHH_API int mhh_dycore_step(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm, double dt);
+/* End-to-end variant with HOST buffers (ghosted layout): copies u,v,w and the scalars to the
+ * device fields in `f`, zeroes nothing (tendencies in `f` are used as they are), runs `nsteps`
+ * full RK3 steps and copies u,v,w,scalars back.  Host pointers should be pinned. */
+MHH_API int mhh_dycore_step_host(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm, double dt, int nsteps,
+                         void* h_u, void* h_v, void* h_w, void* const* h_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MHHB200_H */

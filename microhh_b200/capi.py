@@ -1,0 +1,103 @@
+"""
+ctypes binding of libmhhb200.so (include/mhhb200.h).  This is the ONLY compute path of the
+package: if the CUDA extension is missing or no CUDA device is present, it raises -- there
+is no CPU fallback.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmhhb200.so")
+
+MHH_F64, MHH_F32 = 0, 1
+MHH_MAX_SCALARS = 8
+EDGE_EAST_WEST, EDGE_NORTH_SOUTH, EDGE_BOTH = 0, 1, 2
+BC_NONE, BC_DIRICHLET, BC_NEUMANN = -1, 0, 1
+
+_vp = C.c_void_p
+_SA = _vp * MHH_MAX_SCALARS
+
+
+class GridDesc(C.Structure):
+    _fields_ = [("itot", C.c_int), ("jtot", C.c_int), ("ktot", C.c_int),
+                ("imax", C.c_int), ("jmax", C.c_int), ("kmax", C.c_int),
+                ("igc", C.c_int), ("jgc", C.c_int), ("kgc", C.c_int),
+                ("xsize", C.c_double), ("ysize", C.c_double), ("zsize", C.c_double),
+                ("z", _vp), ("zh", _vp), ("dz", _vp), ("dzh", _vp), ("dzi", _vp), ("dzhi", _vp),
+                ("npx", C.c_int), ("npy", C.c_int), ("mpicoordx", C.c_int), ("mpicoordy", C.c_int)]
+
+
+class FieldsC(C.Structure):
+    _fields_ = [("u", _vp), ("v", _vp), ("w", _vp), ("ut", _vp), ("vt", _vp), ("wt", _vp),
+                ("evisc", _vp), ("p", _vp), ("ns", C.c_int),
+                ("s", _SA), ("st", _SA), ("svisc", C.c_double * MHH_MAX_SCALARS), ("visc", C.c_double),
+                ("u_fluxbot", _vp), ("u_fluxtop", _vp), ("v_fluxbot", _vp), ("v_fluxtop", _vp),
+                ("s_fluxbot", _SA), ("s_fluxtop", _SA),
+                ("dudz_mo", _vp), ("dvdz_mo", _vp), ("dbdz_mo", _vp), ("z0m", _vp),
+                ("u_bot", _vp), ("u_gradbot", _vp), ("u_top", _vp), ("u_gradtop", _vp),
+                ("v_bot", _vp), ("v_gradbot", _vp), ("v_top", _vp), ("v_gradtop", _vp),
+                ("s_bot", _SA), ("s_gradbot", _SA), ("s_top", _SA), ("s_gradtop", _SA)]
+
+
+class ParamsC(C.Structure):
+    _fields_ = [("swadvec", C.c_int), ("swdiff", C.c_int), ("swthermo", C.c_int),
+                ("surface_model", C.c_int), ("sw_mason", C.c_int),
+                ("cs", C.c_double), ("tPr", C.c_double),
+                ("mbcbot", C.c_int), ("mbctop", C.c_int),
+                ("sbcbot", C.c_int * MHH_MAX_SCALARS), ("sbctop", C.c_int * MHH_MAX_SCALARS)]
+
+
+# name -> (restype, argtypes); must list every symbol declared in include/mhhb200.h
+_PF, _PP = C.POINTER(FieldsC), C.POINTER(ParamsC)
+SIGNATURES = {
+    "mhh_ctx_create": (C.c_int, [C.POINTER(GridDesc), C.c_int, C.c_int, C.POINTER(_vp)]),
+    "mhh_ctx_destroy": (None, [_vp]),
+    "mhh_last_error": (C.c_char_p, [_vp]),
+    "mhh_sync": (C.c_int, [_vp]),
+    "mhh_set_stream": (C.c_int, [_vp, _vp]),
+    "mhh_set_basestate": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "mhh_launch_count": (C.c_longlong, [_vp]),
+    "mhh_workspace_bytes": (C.c_longlong, [_vp]),
+    "mhh_profile_start": (C.c_int, [_vp]),
+    "mhh_profile_stop": (C.c_int, [_vp, C.POINTER(C.c_char_p)]),
+    "mhh_boundary_cyclic": (C.c_int, [_vp, _vp, C.c_int]),
+    "mhh_boundary_cyclic_2d": (C.c_int, [_vp, _vp]),
+    "mhh_boundary_ghost_cells_2nd": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp]),
+    "mhh_advec_exec": (C.c_int, [_vp, C.c_int, _PF]),
+    "mhh_advec_get_cfl": (C.c_int, [_vp, C.c_int, _PF, C.c_double, C.POINTER(C.c_double)]),
+    "mhh_diff_smag2_exec_viscosity": (C.c_int, [_vp, _PF, _PP, _vp]),
+    "mhh_diff_smag2_exec": (C.c_int, [_vp, _PF, _PP]),
+    "mhh_diff_smag2_get_dn": (C.c_int, [_vp, _PF, _PP, C.c_double, C.POINTER(C.c_double)]),
+    "mhh_thermo_dry_exec": (C.c_int, [_vp, _vp, _vp]),
+    "mhh_thermo_dry_n2": (C.c_int, [_vp, _vp, _vp]),
+    "mhh_pres_exec": (C.c_int, [_vp, C.c_int, _PF, C.c_double]),
+    "mhh_pres_check_divergence": (C.c_int, [_vp, C.c_int, _PF, C.POINTER(C.c_double)]),
+    "mhh_pres_fft_roundtrip": (C.c_int, [_vp, _vp, _vp, C.c_int]),
+    "mhh_timeloop_rk3": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_double]),
+    "mhh_dycore_substep": (C.c_int, [_vp, _PF, _PP, C.c_int, C.c_double]),
+    "mhh_dycore_step": (C.c_int, [_vp, _PF, _PP, C.c_double]),
+    "mhh_dycore_step_host": (C.c_int, [_vp, _PF, _PP, C.c_double, C.c_int, _vp, _vp, _vp, C.POINTER(_vp)]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libmhhb200.so; raises if it has not been built (python __graft_entry__.py / make)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `make -C microhh_b200/csrc` "
+                "(or __graft_entry__.build()).  There is no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+class MhhError(RuntimeError):
+    pass

@@ -1,0 +1,857 @@
+// mhhb200 -- C ABI implementation (see include/mhhb200.h).  Host-side orchestration only:
+// argument checks, launch configuration, the per-context tables.  No CPU compute path exists.
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <new>
+
+#include "../../include/mhhb200.h"
+#include "common.cuh"
+#include "stencil_kernels.cuh"
+#include "poisson_kernels.cuh"
+
+using namespace mhh;
+
+struct mhh_ctx
+{
+    int dtype = MHH_F64;
+    int device = 0;
+    std::string err;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    long long launches = 0;
+    long long ws_bytes = 0;
+    int num_sms = 148;
+    // optional per-kernel timing: one event after every launch; a kernel's time is the gap to the
+    // previous event on the (in-order) stream
+    bool prof = false;
+    std::vector<std::pair<const char*, cudaEvent_t>> prof_events;
+    std::vector<cudaEvent_t> prof_pool;
+    std::string prof_json;
+    virtual ~mhh_ctx() {}
+};
+
+static void prof_mark(mhh_ctx* c, const char* name)
+{
+    if (!c->prof) return;
+    cudaEvent_t e;
+    if (!c->prof_pool.empty()) { e = c->prof_pool.back(); c->prof_pool.pop_back(); }
+    else if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, c->stream);
+    c->prof_events.emplace_back(name, e);
+}
+
+namespace {
+
+#define CUDA_TRY(ctx, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_); return MHH_E_CUDA; } } while (0)
+
+#define KCHECKN(ctx, name) do { (ctx)->launches++; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) { \
+    (ctx)->err = std::string("kernel launch ") + name + ": " + cudaGetErrorString(e_) + " at " + __FILE__ + ":" + std::to_string(__LINE__); \
+    return MHH_E_CUDA; } prof_mark(ctx, name); } while (0)
+
+FftPlan make_plan(int n, bool& ok)
+{
+    FftPlan p; p.n = n; p.nstages = 0;
+    int r = n;
+    ok = true;
+    const int cand[5] = {8, 4, 2, 3, 5};
+    while (r > 1)
+    {
+        bool found = false;
+        for (int c : cand)
+            if (r % c == 0) { p.radix[p.nstages++] = c; r /= c; found = true; break; }
+        if (!found || p.nstages >= 15) { ok = false; break; }
+    }
+    if (n == 1) { p.nstages = 0; }
+    return p;
+}
+
+template <typename TF>
+struct Ctx : mhh_ctx
+{
+    GridDev<TF> g{};
+    mhh_grid_desc desc{};
+    // device copies of the profiles
+    TF *d_prof = nullptr;          // 10 profiles x kcells
+    TF *d_mlen0 = nullptr;
+    // Pres_2
+    int nm = 0;
+    FftPlan plan_x{}, plan_y{};
+    cplx<TF> *tw_xh = nullptr, *tw_xf = nullptr, *tw_y = nullptr;
+    TF *d_bmati = nullptr, *d_bmatj = nullptr, *d_a = nullptr, *d_c = nullptr, *d_dz2rho = nullptr, *d_dz2 = nullptr;
+    TF *spec = nullptr;            // spectral workspace, (itot+2)*jtot*ktot
+    TF *fac = nullptr;             // tdma factors, nm*jtot*ktot
+    bool basestate_set = false;
+    double *d_red = nullptr;       // reduction scalar
+    double *h_red = nullptr;       // pinned
+    std::vector<TF> h_rhoref, h_rhorefh;
+    int rows_x = 1, mc_y = 4;
+    size_t smem_x = 0, smem_y = 0;
+
+    ~Ctx() override
+    {
+        cudaSetDevice(device);
+        cudaFree(d_prof); cudaFree(d_mlen0); cudaFree(tw_xh); cudaFree(tw_xf); cudaFree(tw_y);
+        cudaFree(d_bmati); cudaFree(d_bmatj); cudaFree(d_a); cudaFree(d_c); cudaFree(d_dz2rho); cudaFree(d_dz2);
+        cudaFree(spec); cudaFree(fac); cudaFree(d_red);
+        if (h_red) cudaFreeHost(h_red);
+        if (own_stream) cudaStreamDestroy(own_stream);
+    }
+
+    TdmaCoef<TF> coef() const { return {d_a, d_c, d_dz2rho, d_dz2, d_bmati, d_bmatj}; }
+
+    dim3 blk() const { return dim3(64, 4, 1); }
+    dim3 grd_interior() const { return dim3((g.imax + 63) / 64, (g.jmax + 3) / 4, g.kmax); }
+    dim3 grd_all() const { return dim3((g.icells + 63) / 64, (g.jcells + 3) / 4, g.kcells); }
+};
+
+template <typename TF>
+int twiddles(mhh_ctx* c, cplx<TF>** out, int n)
+{
+    std::vector<cplx<TF>> h((size_t)std::max(n, 1));
+    for (int t = 0; t < n; ++t)
+    {
+        // exact octant symmetries keep the table accurate to the last bit
+        const long double ang = -2.0L * 3.14159265358979323846264338327950288L * (long double)t / (long double)n;
+        h[t].x = (TF)cosl(ang);
+        h[t].y = (TF)sinl(ang);
+    }
+    CUDA_TRY(c, cudaMalloc(out, sizeof(cplx<TF>) * std::max(n, 1)));
+    CUDA_TRY(c, cudaMemcpy(*out, h.data(), sizeof(cplx<TF>) * std::max(n, 1), cudaMemcpyHostToDevice));
+    return MHH_OK;
+}
+
+template <typename TF>
+int create_impl(const mhh_grid_desc* d, int dtype, int device, mhh_ctx** out)
+{
+    Ctx<TF>* c = new (std::nothrow) Ctx<TF>();
+    if (!c) return MHH_E_NOMEM;
+    *out = c;
+    c->dtype = dtype; c->device = device; c->desc = *d;
+    CUDA_TRY(c, cudaSetDevice(device));
+    int nsm = 0;
+    CUDA_TRY(c, cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
+    c->num_sms = nsm;
+    CUDA_TRY(c, cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+
+    GridDev<TF>& g = c->g;
+    g.itot = d->itot; g.jtot = d->jtot; g.ktot = d->ktot;
+    g.imax = d->imax; g.jmax = d->jmax; g.kmax = d->kmax;
+    g.igc = d->igc; g.jgc = d->jgc; g.kgc = d->kgc;
+    g.icells = g.imax + 2 * g.igc; g.jcells = g.jmax + 2 * g.jgc; g.kcells = g.kmax + 2 * g.kgc;
+    g.istart = g.igc; g.iend = g.igc + g.imax;
+    g.jstart = g.jgc; g.jend = g.jgc + g.jmax;
+    g.kstart = g.kgc; g.kend = g.kgc + g.kmax;
+    g.ijcells = (long long)g.icells * g.jcells;
+    g.ncells = g.ijcells * g.kcells;
+    // src/grid.cxx:250-253: dx = xsize/itot in TF, dxi = 1/dx
+    g.dx = (TF)((TF)d->xsize / (TF)d->itot);
+    g.dy = (TF)((TF)d->ysize / (TF)d->jtot);
+    g.dxi = TF(1.) / g.dx;
+    g.dyi = TF(1.) / g.dy;
+    g.zsize = (TF)d->zsize;
+
+    if (d->npx != 1 || d->npy != 1)
+    { c->err = "this entry point is single-GPU (npx = npy = 1); use the distributed context for pencils"; return MHH_E_INVALID; }
+    if (g.imax != g.itot || g.jmax != g.jtot || g.kmax != g.ktot)
+    { c->err = "imax/jmax/kmax must equal itot/jtot/ktot for npx = npy = 1"; return MHH_E_INVALID; }
+    if (g.kmax < 6) { c->err = "ktot must be >= 6"; return MHH_E_INVALID; }
+    if (g.igc < 1 || g.kgc < 1 || g.jgc < 1) { c->err = "need at least one ghost cell"; return MHH_E_INVALID; }
+    if (g.itot % 2 != 0) { c->err = "itot must be even"; return MHH_E_INVALID; }
+
+    const int kc = g.kcells;
+    CUDA_TRY(c, cudaMalloc(&c->d_prof, sizeof(TF) * kc * 10));
+    CUDA_TRY(c, cudaMemset(c->d_prof, 0, sizeof(TF) * kc * 10));
+    const void* src[6] = {d->z, d->zh, d->dz, d->dzh, d->dzi, d->dzhi};
+    for (int n = 0; n < 6; ++n)
+    {
+        if (!src[n]) { c->err = "grid metric array is NULL"; return MHH_E_INVALID; }
+        CUDA_TRY(c, cudaMemcpy(c->d_prof + n * kc, src[n], sizeof(TF) * kc, cudaMemcpyHostToDevice));
+    }
+    g.z = c->d_prof; g.zh = c->d_prof + kc; g.dz = c->d_prof + 2 * kc; g.dzh = c->d_prof + 3 * kc;
+    g.dzi = c->d_prof + 4 * kc; g.dzhi = c->d_prof + 5 * kc;
+    g.rhoref = c->d_prof + 6 * kc; g.rhorefh = c->d_prof + 7 * kc;
+    g.thref = c->d_prof + 8 * kc; g.threfh = c->d_prof + 9 * kc;
+
+    CUDA_TRY(c, cudaMalloc(&c->d_red, sizeof(double)));
+    CUDA_TRY(c, cudaMallocHost(&c->h_red, sizeof(double)));
+
+    // ---- Pres_2 plans, twiddles, workspace ------------------------------------------------
+    c->nm = g.itot / 2 + 1;
+    bool okx = false, oky = false;
+    c->plan_x = make_plan(g.itot / 2, okx);
+    c->plan_y = make_plan(g.jtot, oky);
+    if (!okx || !oky) { c->err = "itot/2 and jtot must factor into 2, 3 and 5"; return MHH_E_INVALID; }
+    int rc;
+    if ((rc = twiddles<TF>(c, &c->tw_xh, g.itot / 2)) != MHH_OK) return rc;
+    if ((rc = twiddles<TF>(c, &c->tw_xf, g.itot)) != MHH_OK) return rc;
+    if ((rc = twiddles<TF>(c, &c->tw_y, g.jtot)) != MHH_OK) return rc;
+
+    const size_t nspec = (size_t)2 * c->nm * g.jtot * g.ktot;
+    const size_t nfac = (size_t)c->nm * g.jtot * g.ktot;
+    CUDA_TRY(c, cudaMalloc(&c->spec, sizeof(TF) * nspec));
+    CUDA_TRY(c, cudaMalloc(&c->fac, sizeof(TF) * nfac));
+    c->ws_bytes = (long long)(sizeof(TF) * (nspec + nfac));
+    CUDA_TRY(c, cudaMalloc(&c->d_bmati, sizeof(TF) * c->nm));
+    CUDA_TRY(c, cudaMalloc(&c->d_bmatj, sizeof(TF) * g.jtot));
+    CUDA_TRY(c, cudaMalloc(&c->d_a, sizeof(TF) * g.kmax));
+    CUDA_TRY(c, cudaMalloc(&c->d_c, sizeof(TF) * g.kmax));
+    CUDA_TRY(c, cudaMalloc(&c->d_dz2rho, sizeof(TF) * g.kmax));
+    CUDA_TRY(c, cudaMalloc(&c->d_dz2, sizeof(TF) * g.kmax));
+    CUDA_TRY(c, cudaMalloc(&c->d_mlen0, sizeof(TF) * kc));
+
+    // launch geometry of the FFT kernels
+    const int L = g.itot / 2;
+    c->rows_x = std::max(1, std::min(64, 2048 / std::max(L, 1)));
+    c->smem_x = (size_t)2 * c->rows_x * (L + 1) * sizeof(cplx<TF>);
+    int mc = std::max(4, std::min(16, 2048 / g.jtot));
+    if (sizeof(TF) == 4) mc *= 2;
+    while (mc > 1 && (size_t)2 * mc * (g.jtot + 1) * sizeof(cplx<TF>) > 200 * 1024) mc /= 2;
+    c->mc_y = mc;
+    c->smem_y = (size_t)2 * mc * (g.jtot + 1) * sizeof(cplx<TF>);
+    if (c->smem_x > 220 * 1024 || c->smem_y > 220 * 1024) { c->err = "grid too large for the shared-memory FFT"; return MHH_E_INVALID; }
+    CUDA_TRY(c, cudaFuncSetAttribute(fft_x_forward_kernel<TF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_x));
+    CUDA_TRY(c, cudaFuncSetAttribute(fft_x_forward_kernel<TF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_x));
+    CUDA_TRY(c, cudaFuncSetAttribute(fft_x_backward_kernel<TF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_x));
+    CUDA_TRY(c, cudaFuncSetAttribute(fft_y_kernel<TF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_y));
+    return MHH_OK;
+}
+
+template <typename TF>
+int set_basestate_impl(Ctx<TF>* c, const void* rhoref, const void* rhorefh, const void* thref, const void* threfh)
+{
+    GridDev<TF>& g = c->g;
+    const int kc = g.kcells;
+    if (!rhoref || !rhorefh) { c->err = "rhoref/rhorefh must not be NULL"; return MHH_E_INVALID; }
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaMemcpy(const_cast<TF*>(g.rhoref), rhoref, sizeof(TF) * kc, cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(const_cast<TF*>(g.rhorefh), rhorefh, sizeof(TF) * kc, cudaMemcpyHostToDevice));
+    if (thref) CUDA_TRY(c, cudaMemcpy(const_cast<TF*>(g.thref), thref, sizeof(TF) * kc, cudaMemcpyHostToDevice));
+    if (threfh) CUDA_TRY(c, cudaMemcpy(const_cast<TF*>(g.threfh), threfh, sizeof(TF) * kc, cudaMemcpyHostToDevice));
+    const TF* rr = static_cast<const TF*>(rhoref);
+    const TF* rh = static_cast<const TF*>(rhorefh);
+    c->h_rhoref.assign(rr, rr + kc); c->h_rhorefh.assign(rh, rh + kc);
+
+    // Pres_2::set_values (src/pres_2.cxx:124-153), in TF arithmetic like the reference
+    const mhh_grid_desc& d = c->desc;
+    const TF* dz = static_cast<const TF*>(d.dz);
+    const TF* dzhi = static_cast<const TF*>(d.dzhi);
+    const TF dxidxi = TF(1.) / (g.dx * g.dx), dyidyi = TF(1.) / (g.dy * g.dy);
+    const TF pi = std::acos(TF(-1.));
+    std::vector<TF> bmati(c->nm), bmatj(g.jtot), a(g.kmax), cc(g.kmax), dz2rho(g.kmax), dz2(g.kmax), mlen0(kc, TF(0));
+    for (int j = 0; j < g.jtot / 2 + 1; ++j)
+        bmatj[j] = TF(2.) * (std::cos(TF(2.) * pi * (TF)j / (TF)g.jtot) - TF(1.)) * dyidyi;
+    for (int j = g.jtot / 2 + 1; j < g.jtot; ++j)
+        bmatj[j] = bmatj[g.jtot - j];
+    for (int i = 0; i < g.itot / 2 + 1; ++i)
+        bmati[i] = TF(2.) * (std::cos(TF(2.) * pi * (TF)i / (TF)g.itot) - TF(1.)) * dxidxi;
+    for (int k = 0; k < g.kmax; ++k)
+    {
+        a[k] = dz[k + g.kgc] * rh[k + g.kgc] * dzhi[k + g.kgc];
+        cc[k] = dz[k + g.kgc] * rh[k + g.kgc + 1] * dzhi[k + g.kgc + 1];
+        dz2[k] = dz[k + g.kgc] * dz[k + g.kgc];
+        dz2rho[k] = dz2[k] * rr[k + g.kgc];
+    }
+    // Smagorinsky filter width per level: mlen0 = (dx*dy*dz)^(1/3) (cs applied at call time)
+    for (int k = 0; k < kc; ++k)
+        mlen0[k] = std::pow(g.dx * g.dy * dz[k], TF(1. / 3.));
+    CUDA_TRY(c, cudaMemcpy(c->d_bmati, bmati.data(), sizeof(TF) * c->nm, cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(c->d_bmatj, bmatj.data(), sizeof(TF) * g.jtot, cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(c->d_a, a.data(), sizeof(TF) * g.kmax, cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(c->d_c, cc.data(), sizeof(TF) * g.kmax, cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(c->d_dz2rho, dz2rho.data(), sizeof(TF) * g.kmax, cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(c->d_dz2, dz2.data(), sizeof(TF) * g.kmax, cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(c->d_mlen0, mlen0.data(), sizeof(TF) * kc, cudaMemcpyHostToDevice));
+
+    const long long ncol = (long long)c->nm * g.jtot;
+    tdma_setup_kernel<TF><<<(unsigned)((ncol + 127) / 128), 128, 0, c->stream>>>(c->fac, c->coef(), c->nm, g.jtot, g.kmax, 0, 0);
+    KCHECKN(c, "tdma_setup_kernel");
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->basestate_set = true;
+    return MHH_OK;
+}
+
+template <typename TF> inline TF* P(void* p) { return static_cast<TF*>(p); }
+template <typename TF> inline const TF* P(const void* p) { return static_cast<const TF*>(p); }
+
+#define NEED_BASE(c) do { if (!(c)->basestate_set) { (c)->err = "mhh_set_basestate has not been called"; return MHH_E_INVALID; } } while (0)
+#define NEED(c, ptr, what) do { if (!(ptr)) { (c)->err = std::string(what) + " is NULL"; return MHH_E_INVALID; } } while (0)
+
+template <typename TF>
+int cyclic_impl(Ctx<TF>* c, TF* fld, int edge, bool two_d)
+{
+    const GridDev<TF>& g = c->g;
+    NEED(c, fld, "field");
+    if (edge < 0 || edge > 2) { c->err = "bad edge"; return MHH_E_INVALID; }
+    const int nk = two_d ? 1 : g.kcells;
+    const int n0 = 2 * g.igc * g.jcells, n1 = 2 * g.jgc * g.icells;
+    const int nmax = std::max(n0, n1);
+    dim3 grid((nmax + 255) / 256, nk, 2);
+    cyclic_kernel<TF><<<grid, 256, 0, c->stream>>>(fld, g, edge, nk);
+    KCHECKN(c, "cyclic_kernel");
+    return MHH_OK;
+}
+
+template <typename TF>
+int ghost_impl(Ctx<TF>* c, TF* fld, int bcbot, const TF* bot, const TF* gradbot, int bctop, const TF* top, const TF* gradtop)
+{
+    const GridDev<TF>& g = c->g;
+    NEED(c, fld, "field");
+    if (bcbot == MHH_BC_DIRICHLET) NEED(c, bot, "bot");
+    if (bcbot == MHH_BC_NEUMANN) NEED(c, gradbot, "gradbot");
+    if (bctop == MHH_BC_DIRICHLET) NEED(c, top, "top");
+    if (bctop == MHH_BC_NEUMANN) NEED(c, gradtop, "gradtop");
+    dim3 b(64, 4), gr((g.icells + 63) / 64, (g.jcells + 3) / 4);
+    ghost_cells_2nd_kernel<TF><<<gr, b, 0, c->stream>>>(fld, g, bcbot, bot, gradbot, bctop, top, gradtop);
+    KCHECKN(c, "ghost_cells_2nd_kernel");
+    return MHH_OK;
+}
+
+template <typename TF>
+int evisc_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, const TF* n2)
+{
+    NEED_BASE(c);
+    const GridDev<TF>& g = c->g;
+    NEED(c, f->evisc, "evisc"); NEED(c, f->u, "u"); NEED(c, f->v, "v"); NEED(c, f->w, "w");
+    EviscArgs<TF> a{};
+    a.evisc = P<TF>(f->evisc); a.u = P<TF>(f->u); a.v = P<TF>(f->v); a.w = P<TF>(f->w);
+    a.n2 = n2; a.th = nullptr;
+    if (!n2)
+    {
+        if (f->ns < 1 || !f->s[0]) { c->err = "exec_viscosity: no N2 field and no scalar 0 (th) to derive it from"; return MHH_E_INVALID; }
+        a.th = P<TF>(f->s[0]);
+    }
+    a.n2mode = n2 ? 0 : 1;
+    a.surface = prm->surface_model; a.mason = prm->sw_mason;
+    a.cs = (TF)prm->cs; a.tPr = (TF)prm->tPr;
+    if (a.surface)
+    {
+        NEED(c, f->dudz_mo, "dudz_mo"); NEED(c, f->dvdz_mo, "dvdz_mo"); NEED(c, f->dbdz_mo, "dbdz_mo"); NEED(c, f->z0m, "z0m");
+        a.dudz = P<TF>(f->dudz_mo); a.dvdz = P<TF>(f->dvdz_mo); a.dbdz = P<TF>(f->dbdz_mo); a.z0m = P<TF>(f->z0m);
+    }
+    evisc_kernel<TF><<<c->grd_interior(), c->blk(), 0, c->stream>>>(a, g, c->d_mlen0);
+    KCHECKN(c, "evisc_kernel");
+    if (!a.surface)
+    {
+        dim3 b(64, 4), gr((g.icells + 63) / 64, (g.jcells + 3) / 4);
+        evisc_mirror_kernel<TF><<<gr, b, 0, c->stream>>>(a.evisc, g);
+        KCHECKN(c, "evisc_mirror_kernel");
+    }
+    return cyclic_impl<TF>(c, a.evisc, MHH_EDGE_BOTH, false);
+}
+template <typename TF>
+MomArgs<TF> mom_args(const mhh_fields* f)
+{
+    MomArgs<TF> a{};
+    a.ut = P<TF>(f->ut); a.vt = P<TF>(f->vt); a.wt = P<TF>(f->wt);
+    a.u = P<TF>(f->u); a.v = P<TF>(f->v); a.w = P<TF>(f->w);
+    a.evisc = P<TF>(f->evisc);
+    a.th = (f->ns > 0) ? P<TF>(f->s[0]) : nullptr;
+    a.u_fluxbot = P<TF>(f->u_fluxbot); a.u_fluxtop = P<TF>(f->u_fluxtop);
+    a.v_fluxbot = P<TF>(f->v_fluxbot); a.v_fluxtop = P<TF>(f->v_fluxtop);
+    a.visc = (TF)f->visc;
+    return a;
+}
+
+template <typename TF>
+ScalArgs<TF> scal_args(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, int n)
+{
+    const GridDev<TF>& g = c->g;
+    ScalArgs<TF> a{};
+    a.st = P<TF>(f->st[n]); a.s = P<TF>(f->s[n]);
+    a.u = P<TF>(f->u); a.v = P<TF>(f->v); a.w = P<TF>(f->w);
+    a.evisc = P<TF>(f->evisc);
+    a.fluxbot = P<TF>(f->s_fluxbot[n]); a.fluxtop = P<TF>(f->s_fluxtop[n]);
+    a.visc = (TF)f->svisc[n];
+    a.tPr = prm ? (TF)prm->tPr : TF(1);
+    // 1./(dx*dx) is formed in double in the reference and narrowed to TF (src/diff_smag2.cxx:445)
+    a.dxidxi = (TF)(1. / ((double)g.dx * (double)g.dx));
+    a.dyidyi = (TF)(1. / ((double)g.dy * (double)g.dy));
+    return a;
+}
+
+template <typename TF>
+int check_mom(Ctx<TF>* c, const mhh_fields* f, bool need_evisc, bool surface)
+{
+    NEED(c, f, "fields");
+    NEED(c, f->u, "u"); NEED(c, f->v, "v"); NEED(c, f->w, "w");
+    NEED(c, f->ut, "ut"); NEED(c, f->vt, "vt"); NEED(c, f->wt, "wt");
+    if (f->ns < 0 || f->ns > MHH_MAX_SCALARS) { c->err = "ns out of range"; return MHH_E_INVALID; }
+    for (int n = 0; n < f->ns; ++n) { NEED(c, f->s[n], "scalar"); NEED(c, f->st[n], "scalar tendency"); }
+    if (need_evisc) NEED(c, f->evisc, "evisc");
+    if (need_evisc && surface)
+    {
+        NEED(c, f->u_fluxbot, "u_fluxbot"); NEED(c, f->u_fluxtop, "u_fluxtop");
+        NEED(c, f->v_fluxbot, "v_fluxbot"); NEED(c, f->v_fluxtop, "v_fluxtop");
+        for (int n = 0; n < f->ns; ++n) { NEED(c, f->s_fluxbot[n], "s_fluxbot"); NEED(c, f->s_fluxtop[n], "s_fluxtop"); }
+    }
+    return MHH_OK;
+}
+
+// tendencies: adv / diff / buoyancy in any combination (templates keep the unused parts out)
+template <typename TF>
+int tend_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, bool adv, bool diff, bool buoy)
+{
+    NEED_BASE(c);
+    const GridDev<TF>& g = c->g;
+    const bool surface = diff && prm && prm->surface_model;
+    int rc = check_mom<TF>(c, f, diff, surface);
+    if (rc != MHH_OK) return rc;
+    if (adv && (g.igc < 3 || g.jgc < 3)) { c->err = "advec_2i5 needs igc, jgc >= 3"; return MHH_E_INVALID; }
+    if (buoy && (f->ns < 1)) { c->err = "buoyancy needs scalar 0 (th)"; return MHH_E_INVALID; }
+    const MomArgs<TF> a = mom_args<TF>(f);
+    dim3 gr = c->grd_interior(), b = c->blk();
+#define LAUNCH_MOM(A, D, S, B) tend_uvw_kernel<TF, A, D, S, B><<<gr, b, 0, c->stream>>>(a, g)
+    if (adv && diff && surface && buoy) LAUNCH_MOM(true, true, true, true);
+    else if (adv && diff && surface) LAUNCH_MOM(true, true, true, false);
+    else if (adv && diff && buoy) LAUNCH_MOM(true, true, false, true);
+    else if (adv && diff) LAUNCH_MOM(true, true, false, false);
+    else if (adv) LAUNCH_MOM(true, false, false, false);
+    else if (diff && surface) LAUNCH_MOM(false, true, true, false);
+    else if (diff) LAUNCH_MOM(false, true, false, false);
+    else { c->err = "tend_impl: nothing to do"; return MHH_E_INVALID; }
+#undef LAUNCH_MOM
+    KCHECKN(c, "tend_uvw_kernel");
+    for (int n = 0; n < f->ns; ++n)
+    {
+        const ScalArgs<TF> s = scal_args<TF>(c, f, prm, n);
+#define LAUNCH_S(A, D, S) tend_s_kernel<TF, A, D, S><<<gr, b, 0, c->stream>>>(s, g)
+        if (adv && diff && surface) LAUNCH_S(true, true, true);
+        else if (adv && diff) LAUNCH_S(true, true, false);
+        else if (adv) LAUNCH_S(true, false, false);
+        else if (diff && surface) LAUNCH_S(false, true, true);
+        else LAUNCH_S(false, true, false);
+#undef LAUNCH_S
+        KCHECKN(c, "tend_s_kernel");
+    }
+    return MHH_OK;
+}
+
+template <typename TF, int MODE>
+int reduce_impl(Ctx<TF>* c, const TF* u, const TF* v, const TF* w, TF p0, TF p1, TF p2, double* out)
+{
+    const GridDev<TF>& g = c->g;
+    CUDA_TRY(c, cudaMemsetAsync(c->d_red, 0, sizeof(double), c->stream));
+    reduce_kernel<TF, MODE><<<c->grd_interior(), c->blk(), 0, c->stream>>>(u, v, w, g, p0, p1, p2, c->d_red);
+    KCHECKN(c, "reduce_kernel");
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_red, c->d_red, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    *out = *c->h_red;
+    return MHH_OK;
+}
+
+// ---- Pres_2 ---------------------------------------------------------------------------------
+template <typename TF>
+int pres_spectral_solve(Ctx<TF>* c, bool do_solve)
+{
+    const GridDev<TF>& g = c->g;
+    const int grid_p = c->num_sms * 2;
+    if (g.jtot > 1)
+    {
+        fft_y_kernel<TF><<<grid_p, 256, c->smem_y, c->stream>>>(c->spec, c->nm, g.jtot, g.ktot, c->plan_y, c->tw_y, c->mc_y, 0);
+        KCHECKN(c, "fft_y_forward_kernel");
+    }
+    if (do_solve)
+    {
+        const long long ncol = (long long)c->nm * g.jtot;
+        tdma_solve_kernel<TF><<<(unsigned)((ncol + 127) / 128), 128, 0, c->stream>>>(c->spec, c->fac, c->coef(), c->nm, g.jtot, g.kmax, 0, 0);
+        KCHECKN(c, "tdma_solve_kernel");
+    }
+    if (g.jtot > 1)
+    {
+        fft_y_kernel<TF><<<grid_p, 256, c->smem_y, c->stream>>>(c->spec, c->nm, g.jtot, g.ktot, c->plan_y, c->tw_y, c->mc_y, 1);
+        KCHECKN(c, "fft_y_backward_kernel");
+    }
+    return MHH_OK;
+}
+
+template <typename TF>
+int pres_solve_impl(Ctx<TF>* c, const mhh_fields* f, double sub_dt)
+{
+    NEED_BASE(c);
+    const GridDev<TF>& g = c->g;
+    NEED(c, f->p, "p");
+    RhsSrc<TF> src{P<TF>(f->u), P<TF>(f->v), P<TF>(f->w), P<TF>(f->ut), P<TF>(f->vt), P<TF>(f->wt), (TF)(TF(1.) / sub_dt)};
+    const long long nrows = (long long)g.jtot * g.ktot;
+    const int grid_x = (int)std::min<long long>((nrows + c->rows_x - 1) / c->rows_x, (long long)c->num_sms * 4);
+    fft_x_forward_kernel<TF, true><<<grid_x, 256, c->smem_x, c->stream>>>(c->spec, src, g, c->plan_x, c->tw_xh, c->tw_xf, c->rows_x, nrows);
+    KCHECKN(c, "fft_x_forward_kernel");
+    int rc = pres_spectral_solve<TF>(c, true);
+    if (rc != MHH_OK) return rc;
+    const TF norm = TF(1.) / ((TF)g.itot * (TF)g.jtot);
+    fft_x_backward_kernel<TF><<<grid_x, 256, c->smem_x, c->stream>>>(c->spec, P<TF>(f->p), g, c->plan_x, c->tw_xh, c->tw_xf,
+            c->rows_x, nrows, norm, 1);
+    KCHECKN(c, "fft_x_backward_kernel");
+    if (g.jtot == 1)
+        return cyclic_impl<TF>(c, P<TF>(f->p), MHH_EDGE_NORTH_SOUTH, false);
+    return MHH_OK;
+}
+
+template <typename TF>
+int pres_exec_impl(Ctx<TF>* c, const mhh_fields* f, double sub_dt)
+{
+    int rc = check_mom<TF>(c, f, false, false);
+    if (rc != MHH_OK) return rc;
+    const GridDev<TF>& g = c->g;
+    // the reference fills the east ghost cells of ut and the north ghost cells of vt as a side effect
+    // (src/pres_2.cxx:180-181); keep that observable behaviour for the stand-alone entry point
+    if ((rc = cyclic_impl<TF>(c, P<TF>(f->ut), MHH_EDGE_EAST_WEST, false)) != MHH_OK) return rc;
+    if ((rc = cyclic_impl<TF>(c, P<TF>(f->vt), MHH_EDGE_NORTH_SOUTH, false)) != MHH_OK) return rc;
+    if ((rc = pres_solve_impl<TF>(c, f, sub_dt)) != MHH_OK) return rc;
+    PresArgs<TF> a{P<TF>(f->ut), P<TF>(f->vt), P<TF>(f->wt), P<TF>(f->u), P<TF>(f->v), P<TF>(f->w), P<TF>(f->p)};
+    pres_out_kernel<TF><<<c->grd_interior(), c->blk(), 0, c->stream>>>(a, g);
+    KCHECKN(c, "pres_out_kernel");
+    return MHH_OK;
+}
+
+template <typename TF>
+int rk3_impl(Ctx<TF>* c, TF* a, TF* at, int substep, double dt)
+{
+    const GridDev<TF>& g = c->g;
+    NEED(c, a, "field"); NEED(c, at, "tendency");
+    if (substep < 0 || substep > 2) { c->err = "substep must be 0..2"; return MHH_E_INVALID; }
+    const TF cA[3] = {TF(0.), TF(-5. / 9.), TF(-153. / 128.)};
+    const TF cB[3] = {TF(1. / 3.), TF(15. / 16.), TF(8. / 15.)};
+    const int nxt = (substep + 1) % 3;
+    rk3_kernel<TF><<<c->grd_all(), c->blk(), 0, c->stream>>>(a, at, cB[substep] * (TF)dt, cA[nxt], nxt == 0, g);
+    KCHECKN(c, "rk3_kernel");
+    return MHH_OK;
+}
+
+// One fused sub-step (Model::exec order, src/model.cxx:356-504, restricted to the hot path).
+template <typename TF>
+int substep_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, int substep, double dt)
+{
+    NEED_BASE(c);
+    NEED(c, prm, "params");
+    const GridDev<TF>& g = c->g;
+    if (prm->swadvec != 25 || prm->swdiff != 1) { c->err = "dycore_substep: only swadvec=2i5 (25) + swdiff=smag2 (1) are fused"; return MHH_E_INVALID; }
+    if (substep < 0 || substep > 2) { c->err = "substep must be 0..2"; return MHH_E_INVALID; }
+    int rc = check_mom<TF>(c, f, true, prm->surface_model != 0);
+    if (rc != MHH_OK) return rc;
+    NEED(c, f->p, "p");
+    // 1. boundary.set_prognostic_cyclic_bcs + set_ghost_cells
+    TF* mom[3] = {P<TF>(f->u), P<TF>(f->v), P<TF>(f->w)};
+    for (int n = 0; n < 3; ++n)
+        if ((rc = cyclic_impl<TF>(c, mom[n], MHH_EDGE_BOTH, false)) != MHH_OK) return rc;
+    for (int n = 0; n < f->ns; ++n)
+        if ((rc = cyclic_impl<TF>(c, P<TF>(f->s[n]), MHH_EDGE_BOTH, false)) != MHH_OK) return rc;
+    if ((rc = ghost_impl<TF>(c, P<TF>(f->u), prm->mbcbot, P<TF>(f->u_bot), P<TF>(f->u_gradbot), prm->mbctop, P<TF>(f->u_top), P<TF>(f->u_gradtop))) != MHH_OK) return rc;
+    if ((rc = ghost_impl<TF>(c, P<TF>(f->v), prm->mbcbot, P<TF>(f->v_bot), P<TF>(f->v_gradbot), prm->mbctop, P<TF>(f->v_top), P<TF>(f->v_gradtop))) != MHH_OK) return rc;
+    for (int n = 0; n < f->ns; ++n)
+        if ((rc = ghost_impl<TF>(c, P<TF>(f->s[n]), prm->sbcbot[n], P<TF>(f->s_bot[n]), P<TF>(f->s_gradbot[n]),
+                                 prm->sbctop[n], P<TF>(f->s_top[n]), P<TF>(f->s_gradtop[n]))) != MHH_OK) return rc;
+    // 2. diff.exec_viscosity
+    if ((rc = evisc_impl<TF>(c, f, prm, nullptr)) != MHH_OK) return rc;
+    // 3. thermo.exec + advec.exec + diff.exec, fused
+    if ((rc = tend_impl<TF>(c, f, prm, true, true, prm->swthermo == 1)) != MHH_OK) return rc;
+    // 4. pres.exec (solve), then pressure correction fused with timeloop.exec
+    const TF cA[3] = {TF(0.), TF(-5. / 9.), TF(-153. / 128.)};
+    const TF cB[3] = {TF(1. / 3.), TF(15. / 16.), TF(8. / 15.)};
+    const double cBd[3] = {1. / 3., 15. / 16., 8. / 15.};
+    const double sub_dt = cBd[substep] * dt;          // Timeloop::get_sub_time_step (double)
+    if ((rc = pres_solve_impl<TF>(c, f, sub_dt)) != MHH_OK) return rc;
+    const int nxt = (substep + 1) % 3;
+    PresArgs<TF> a{P<TF>(f->ut), P<TF>(f->vt), P<TF>(f->wt), P<TF>(f->u), P<TF>(f->v), P<TF>(f->w), P<TF>(f->p)};
+    pres_out_rk3_kernel<TF><<<c->grd_all(), c->blk(), 0, c->stream>>>(a, P<TF>(f->u), P<TF>(f->v), P<TF>(f->w),
+            cB[substep] * (TF)dt, cA[nxt], nxt == 0, g);
+    KCHECKN(c, "pres_out_rk3_kernel");
+    for (int n = 0; n < f->ns; ++n)
+        if ((rc = rk3_impl<TF>(c, P<TF>(f->s[n]), P<TF>(f->st[n]), substep, dt)) != MHH_OK) return rc;
+    return MHH_OK;
+}
+
+template <typename TF>
+int step_host_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, double dt, int nsteps,
+                   void* h_u, void* h_v, void* h_w, void* const* h_s)
+{
+    const GridDev<TF>& g = c->g;
+    const size_t bytes = sizeof(TF) * (size_t)g.ncells;
+    NEED(c, h_u, "h_u"); NEED(c, h_v, "h_v"); NEED(c, h_w, "h_w");
+    CUDA_TRY(c, cudaMemcpyAsync(f->u, h_u, bytes, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(f->v, h_v, bytes, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(f->w, h_w, bytes, cudaMemcpyHostToDevice, c->stream));
+    for (int n = 0; n < f->ns; ++n)
+    {
+        NEED(c, h_s[n], "h_s[n]");
+        CUDA_TRY(c, cudaMemcpyAsync(f->s[n], h_s[n], bytes, cudaMemcpyHostToDevice, c->stream));
+    }
+    for (int it = 0; it < nsteps; ++it)
+        for (int ss = 0; ss < 3; ++ss)
+        {
+            int rc = substep_impl<TF>(c, f, prm, ss, dt);
+            if (rc != MHH_OK) return rc;
+        }
+    CUDA_TRY(c, cudaMemcpyAsync(h_u, f->u, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(h_v, f->v, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(h_w, f->w, bytes, cudaMemcpyDeviceToHost, c->stream));
+    for (int n = 0; n < f->ns; ++n)
+        CUDA_TRY(c, cudaMemcpyAsync(h_s[n], f->s[n], bytes, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return MHH_OK;
+}
+
+template <typename TF>
+int fft_roundtrip_impl(Ctx<TF>* c, const TF* in, TF* out, int solve)
+{
+    NEED_BASE(c);
+    const GridDev<TF>& g = c->g;
+    NEED(c, in, "in"); NEED(c, out, "out");
+    // stage the compact input in the workspace rows (pitch 2*nm)
+    CUDA_TRY(c, cudaMemcpy2DAsync(c->spec, sizeof(TF) * 2 * c->nm, in, sizeof(TF) * g.itot, sizeof(TF) * g.itot,
+                                  (size_t)g.jtot * g.ktot, cudaMemcpyDeviceToDevice, c->stream));
+    const long long nrows = (long long)g.jtot * g.ktot;
+    const int grid_x = (int)std::min<long long>((nrows + c->rows_x - 1) / c->rows_x, (long long)c->num_sms * 4);
+    RhsSrc<TF> none{};
+    fft_x_forward_kernel<TF, false><<<grid_x, 256, c->smem_x, c->stream>>>(c->spec, none, g, c->plan_x, c->tw_xh, c->tw_xf, c->rows_x, nrows);
+    KCHECKN(c, "fft_x_forward_kernel");
+    int rc = pres_spectral_solve<TF>(c, solve != 0);
+    if (rc != MHH_OK) return rc;
+    // backward x into a temporary ghosted array is overkill here: use a private ghosted buffer
+    TF* tmp = nullptr;
+    CUDA_TRY(c, cudaMalloc(&tmp, sizeof(TF) * (size_t)g.ncells));
+    const TF norm = TF(1.) / ((TF)g.itot * (TF)g.jtot);
+    fft_x_backward_kernel<TF><<<grid_x, 256, c->smem_x, c->stream>>>(c->spec, tmp, g, c->plan_x, c->tw_xh, c->tw_xf, c->rows_x, nrows, norm, 0);
+    c->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess)
+        e = cudaMemcpy2DAsync(out, sizeof(TF) * g.itot,
+                              tmp + g.istart + (long long)g.jstart * g.icells + (long long)g.kstart * g.ijcells,
+                              sizeof(TF) * g.icells, sizeof(TF) * g.itot, g.jtot, cudaMemcpyDeviceToDevice, c->stream);
+    // cudaMemcpy2D handles one k-slab (rows are contiguous within a slab only); loop the slabs
+    for (int k = 1; k < g.ktot && e == cudaSuccess; ++k)
+        e = cudaMemcpy2DAsync(out + (size_t)k * g.itot * g.jtot, sizeof(TF) * g.itot,
+                              tmp + g.istart + (long long)g.jstart * g.icells + (long long)(g.kstart + k) * g.ijcells,
+                              sizeof(TF) * g.icells, sizeof(TF) * g.itot, g.jtot, cudaMemcpyDeviceToDevice, c->stream);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) { c->err = std::string("fft_roundtrip: ") + cudaGetErrorString(e); return MHH_E_CUDA; }
+    return MHH_OK;
+}
+
+} // namespace
+
+// ============================================================================================
+// C entry points
+// ============================================================================================
+#define DISPATCH(ctx, expr64, expr32) \
+    do { if (!(ctx)) return MHH_E_INVALID; \
+         cudaError_t e_ = cudaSetDevice((ctx)->device); \
+         if (e_ != cudaSuccess) { (ctx)->err = std::string("cudaSetDevice: ") + cudaGetErrorString(e_); return MHH_E_CUDA; } \
+         if ((ctx)->dtype == MHH_F64) { typedef double TF; Ctx<TF>* c = static_cast<Ctx<TF>*>(ctx); (void)c; return (expr64); } \
+         else { typedef float TF; Ctx<TF>* c = static_cast<Ctx<TF>*>(ctx); (void)c; return (expr32); } } while (0)
+#define DISPATCH1(ctx, expr) DISPATCH(ctx, expr, expr)
+
+extern "C" {
+
+int mhh_ctx_create(const mhh_grid_desc* grid, int dtype, int device, mhh_ctx** out)
+{
+    if (!grid || !out) return MHH_E_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev)
+    {
+        // no CPU fallback: a context cannot exist without a CUDA device
+        cudaGetLastError();
+        return MHH_E_CUDA;
+    }
+    int rc;
+    if (dtype == MHH_F64) rc = create_impl<double>(grid, dtype, device, out);
+    else if (dtype == MHH_F32) rc = create_impl<float>(grid, dtype, device, out);
+    else return MHH_E_INVALID;
+    return rc;   // on failure *out stays valid so that mhh_last_error() can be read; caller destroys it
+}
+
+void mhh_ctx_destroy(mhh_ctx* ctx) { delete ctx; }
+
+const char* mhh_last_error(const mhh_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context (no CUDA device?)"; }
+
+int mhh_sync(mhh_ctx* ctx)
+{
+    if (!ctx) return MHH_E_INVALID;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return MHH_OK;
+}
+
+int mhh_set_stream(mhh_ctx* ctx, void* s)
+{
+    if (!ctx) return MHH_E_INVALID;
+    ctx->stream = s ? static_cast<cudaStream_t>(s) : ctx->own_stream;
+    return MHH_OK;
+}
+
+long long mhh_launch_count(const mhh_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int mhh_profile_start(mhh_ctx* ctx)
+{
+    if (!ctx) return MHH_E_INVALID;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    for (auto& pe : ctx->prof_events) ctx->prof_pool.push_back(pe.second);
+    ctx->prof_events.clear();
+    ctx->prof = true;
+    prof_mark(ctx, "__start__");
+    return MHH_OK;
+}
+
+int mhh_profile_stop(mhh_ctx* ctx, const char** json)
+{
+    if (!ctx || !json) return MHH_E_INVALID;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->prof = false;
+    std::vector<std::string> names; std::vector<double> ms; std::vector<long long> cnt;
+    for (size_t n = 1; n < ctx->prof_events.size(); ++n)
+    {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, ctx->prof_events[n - 1].second, ctx->prof_events[n].second);
+        const std::string nm = ctx->prof_events[n].first;
+        size_t k = 0;
+        for (; k < names.size(); ++k) if (names[k] == nm) break;
+        if (k == names.size()) { names.push_back(nm); ms.push_back(0.); cnt.push_back(0); }
+        ms[k] += t; cnt[k] += 1;
+    }
+    std::string js = "{";
+    for (size_t k = 0; k < names.size(); ++k)
+    {
+        char buf[256];
+        snprintf(buf, sizeof(buf), "%s\"%s\": {\"n\": %lld, \"ms\": %.6f}", k ? ", " : "", names[k].c_str(), cnt[k], ms[k]);
+        js += buf;
+    }
+    js += "}";
+    ctx->prof_json = js;
+    *json = ctx->prof_json.c_str();
+    for (auto& pe : ctx->prof_events) ctx->prof_pool.push_back(pe.second);
+    ctx->prof_events.clear();
+    return MHH_OK;
+}
+long long mhh_workspace_bytes(const mhh_ctx* ctx) { return ctx ? ctx->ws_bytes : 0; }
+
+int mhh_set_basestate(mhh_ctx* ctx, const void* rhoref, const void* rhorefh, const void* thref, const void* threfh)
+{ DISPATCH1(ctx, set_basestate_impl<TF>(c, rhoref, rhorefh, thref, threfh)); }
+
+int mhh_boundary_cyclic(mhh_ctx* ctx, void* fld, int edge)
+{ DISPATCH1(ctx, cyclic_impl<TF>(c, P<TF>(fld), edge, false)); }
+
+int mhh_boundary_cyclic_2d(mhh_ctx* ctx, void* fld)
+{ DISPATCH1(ctx, cyclic_impl<TF>(c, P<TF>(fld), MHH_EDGE_BOTH, true)); }
+
+int mhh_boundary_ghost_cells_2nd(mhh_ctx* ctx, void* fld, int bcbot, const void* bot, const void* gradbot,
+                                 int bctop, const void* top, const void* gradtop)
+{ DISPATCH1(ctx, ghost_impl<TF>(c, P<TF>(fld), bcbot, P<TF>(bot), P<TF>(gradbot), bctop, P<TF>(top), P<TF>(gradtop))); }
+
+int mhh_advec_exec(mhh_ctx* ctx, int swadvec, const mhh_fields* f)
+{
+    if (ctx && swadvec != 25) { ctx->err = "advec_exec: only swadvec = 25 (2i5) is available"; return MHH_E_INVALID; }
+    DISPATCH1(ctx, tend_impl<TF>(c, f, nullptr, true, false, false));
+}
+
+int mhh_advec_get_cfl(mhh_ctx* ctx, int swadvec, const mhh_fields* f, double dt, double* cfl)
+{
+    if (!ctx || !f || !cfl) return MHH_E_INVALID;
+    if (swadvec != 25) { ctx->err = "advec_get_cfl: only swadvec = 25 (2i5) is available"; return MHH_E_INVALID; }
+    int rc;
+    if (ctx->dtype == MHH_F64) { typedef double TF; rc = reduce_impl<TF, 0>(static_cast<Ctx<TF>*>(ctx), P<TF>(f->u), P<TF>(f->v), P<TF>(f->w), 0, 0, 0, cfl); if (rc == MHH_OK) *cfl = *cfl * dt; }
+    else { typedef float TF; rc = reduce_impl<TF, 0>(static_cast<Ctx<TF>*>(ctx), P<TF>(f->u), P<TF>(f->v), P<TF>(f->w), 0, 0, 0, cfl); if (rc == MHH_OK) *cfl = (double)((float)*cfl * (float)dt); }
+    return rc;
+}
+
+int mhh_diff_smag2_exec_viscosity(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm, const void* n2)
+{
+    if (!f || !prm) return MHH_E_INVALID;
+    DISPATCH1(ctx, evisc_impl<TF>(c, f, prm, P<TF>(n2)));
+}
+
+int mhh_diff_smag2_exec(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm)
+{
+    if (!f || !prm) return MHH_E_INVALID;
+    DISPATCH1(ctx, tend_impl<TF>(c, f, prm, false, true, false));
+}
+
+int mhh_diff_smag2_get_dn(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm, double dt, double* dn)
+{
+    if (!ctx || !f || !prm || !dn) return MHH_E_INVALID;
+    int rc;
+    if (ctx->dtype == MHH_F64)
+    {
+        typedef double TF; Ctx<TF>* c = static_cast<Ctx<TF>*>(ctx);
+        const TF tprfac = TF(1) / std::min(TF(1.), (TF)prm->tPr);
+        rc = reduce_impl<TF, 1>(c, P<TF>(f->evisc), nullptr, nullptr, tprfac, (TF)(1. / ((double)c->g.dx * c->g.dx)), (TF)(1. / ((double)c->g.dy * c->g.dy)), dn);
+    }
+    else
+    {
+        typedef float TF; Ctx<TF>* c = static_cast<Ctx<TF>*>(ctx);
+        const TF tprfac = TF(1) / std::min(TF(1.), (TF)prm->tPr);
+        rc = reduce_impl<TF, 1>(c, P<TF>(f->evisc), nullptr, nullptr, tprfac, (TF)(1. / ((double)c->g.dx * c->g.dx)), (TF)(1. / ((double)c->g.dy * c->g.dy)), dn);
+    }
+    if (rc == MHH_OK) *dn = *dn * dt;
+    return rc;
+}
+
+int mhh_thermo_dry_exec(mhh_ctx* ctx, void* wt, const void* th)
+{
+    if (!ctx || !wt || !th) return MHH_E_INVALID;
+    DISPATCH1(ctx, ([&]() -> int {
+        NEED_BASE(c);
+        dim3 gr = c->grd_interior(); gr.z = c->g.kmax - 1;
+        buoyancy_kernel<TF><<<gr, c->blk(), 0, c->stream>>>(P<TF>(wt), P<TF>(th), c->g);
+        KCHECKN(c, "buoyancy_kernel"); return MHH_OK; })());
+}
+
+int mhh_thermo_dry_n2(mhh_ctx* ctx, void* n2, const void* th)
+{
+    if (!ctx || !n2 || !th) return MHH_E_INVALID;
+    DISPATCH1(ctx, ([&]() -> int {
+        NEED_BASE(c);
+        n2_kernel<TF><<<c->grd_interior(), c->blk(), 0, c->stream>>>(P<TF>(n2), P<TF>(th), c->g);
+        KCHECKN(c, "n2_kernel"); return MHH_OK; })());
+}
+
+int mhh_pres_exec(mhh_ctx* ctx, int swpres, const mhh_fields* f, double sub_dt)
+{
+    if (!f) return MHH_E_INVALID;
+    if (ctx && swpres != 2) { ctx->err = "pres_exec: only swpres = 2 is available"; return MHH_E_INVALID; }
+    DISPATCH1(ctx, pres_exec_impl<TF>(c, f, sub_dt));
+}
+
+int mhh_pres_check_divergence(mhh_ctx* ctx, int swpres, const mhh_fields* f, double* divmax)
+{
+    if (!ctx || !f || !divmax) return MHH_E_INVALID;
+    if (swpres != 2) { ctx->err = "pres_check_divergence: only swpres = 2 is available"; return MHH_E_INVALID; }
+    if (ctx->dtype == MHH_F64) { typedef double TF; Ctx<TF>* c = static_cast<Ctx<TF>*>(ctx); NEED_BASE(c); return reduce_impl<TF, 2>(c, P<TF>(f->u), P<TF>(f->v), P<TF>(f->w), 0, 0, 0, divmax); }
+    else { typedef float TF; Ctx<TF>* c = static_cast<Ctx<TF>*>(ctx); NEED_BASE(c); return reduce_impl<TF, 2>(c, P<TF>(f->u), P<TF>(f->v), P<TF>(f->w), 0, 0, 0, divmax); }
+}
+
+int mhh_pres_fft_roundtrip(mhh_ctx* ctx, const void* in_compact, void* out_compact, int solve)
+{ DISPATCH1(ctx, fft_roundtrip_impl<TF>(c, P<TF>(in_compact), P<TF>(out_compact), solve)); }
+
+int mhh_timeloop_rk3(mhh_ctx* ctx, void* a, void* at, int substep, double dt)
+{ DISPATCH1(ctx, rk3_impl<TF>(c, P<TF>(a), P<TF>(at), substep, dt)); }
+
+int mhh_dycore_substep(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm, int substep, double dt)
+{
+    if (!f) return MHH_E_INVALID;
+    DISPATCH1(ctx, substep_impl<TF>(c, f, prm, substep, dt));
+}
+
+int mhh_dycore_step(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm, double dt)
+{
+    for (int ss = 0; ss < 3; ++ss)
+    {
+        int rc = mhh_dycore_substep(ctx, f, prm, ss, dt);
+        if (rc != MHH_OK) return rc;
+    }
+    return MHH_OK;
+}
+
+int mhh_dycore_step_host(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm, double dt, int nsteps,
+                         void* h_u, void* h_v, void* h_w, void* const* h_s)
+{
+    if (!f || !prm) return MHH_E_INVALID;
+    DISPATCH1(ctx, step_host_impl<TF>(c, f, prm, dt, nsteps, h_u, h_v, h_w, h_s));
+}
+
+} // extern "C"

@@ -1,0 +1,93 @@
+// mhhb200 -- B200-native dynamical core for MicroHH's RK3 step.
+// Shared device-side definitions: grid descriptor, index helpers, finite-difference
+// operators (same formulas as reference include/finite_difference.h:33-158, restated).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+
+namespace mhh {
+
+constexpr int MAX_SCALARS = 8;
+
+// POD copy of the reference's Grid_data scalars (include/grid.h:49-134) plus device
+// pointers to the 1-D metric arrays (kcells entries each).
+template <typename TF>
+struct GridDev
+{
+    int itot, jtot, ktot;
+    int imax, jmax, kmax;
+    int igc, jgc, kgc;
+    int icells, jcells, kcells;
+    int istart, iend, jstart, jend, kstart, kend;
+    long long ijcells, ncells;
+    TF dx, dy, dxi, dyi;
+    TF zsize;
+    const TF* z;   const TF* zh;
+    const TF* dz;  const TF* dzh;
+    const TF* dzi; const TF* dzhi;
+    const TF* rhoref;  const TF* rhorefh;
+    const TF* thref;   const TF* threfh;
+};
+
+template <typename TF> __device__ __forceinline__ TF ld(const TF* __restrict__ p) { return __ldg(p); }
+
+// ---- Finite differences ----------------------------------------------------------------
+template <typename TF> __device__ __forceinline__ TF interp2(TF a, TF b) { return TF(0.5) * (a + b); }
+template <typename TF> __device__ __forceinline__ TF interp4_ws(TF a, TF b, TF c, TF d)
+{ return TF(7. / 12.) * (b + c) - TF(1. / 12.) * (a + d); }
+template <typename TF> __device__ __forceinline__ TF interp3_ws(TF a, TF b, TF c, TF d)
+{ return TF(3. / 12.) * (c - b) - TF(1. / 12.) * (d - a); }
+template <typename TF> __device__ __forceinline__ TF interp6_ws(TF a, TF b, TF c, TF d, TF e, TF f)
+{ return TF(37. / 60.) * (c + d) - TF(8. / 60.) * (b + e) + TF(1. / 60.) * (a + f); }
+template <typename TF> __device__ __forceinline__ TF interp5_ws(TF a, TF b, TF c, TF d, TF e, TF f)
+{ return TF(10. / 60.) * (d - c) - TF(5. / 60.) * (e - b) + TF(1. / 60.) * (f - a); }
+
+template <typename TF> __device__ __forceinline__ TF absf(TF a) { return a < TF(0) ? -a : a; }
+template <> __device__ __forceinline__ double absf<double>(double a) { return fabs(a); }
+template <> __device__ __forceinline__ float absf<float>(float a) { return fabsf(a); }
+template <typename TF> __device__ __forceinline__ TF sqrtf_(TF a);
+template <> __device__ __forceinline__ double sqrtf_<double>(double a) { return sqrt(a); }
+template <> __device__ __forceinline__ float sqrtf_<float>(float a) { return sqrtf(a); }
+template <typename TF> __device__ __forceinline__ TF pow2(TF a) { return a * a; }
+
+// Upwind-biased advective face fluxes of the 2i5 scheme:  vel*interp_even - |vel|*interp_odd.
+template <typename TF> __device__ __forceinline__ TF flux65(TF vel, TF a, TF b, TF c, TF d, TF e, TF f)
+{ return vel * interp6_ws(a, b, c, d, e, f) - absf(vel) * interp5_ws(a, b, c, d, e, f); }
+template <typename TF> __device__ __forceinline__ TF flux43(TF vel, TF a, TF b, TF c, TF d)
+{ return vel * interp4_ws(a, b, c, d) - absf(vel) * interp3_ws(a, b, c, d); }
+template <typename TF> __device__ __forceinline__ TF flux2(TF vel, TF a, TF b)
+{ return vel * interp2(a, b); }
+
+// Order of the vertical advective flux through level `f` counted on an axis whose first
+// interior level is `lo` and whose last is `hi` (faces: lo=kstart, hi=kend; centres for w:
+// lo=kstart-1 (virtual), see callers).  0: wall (zero flux), 2, 4 (4th/3rd), 6 (6th/5th).
+__device__ __forceinline__ int vorder(int f, int lo, int hi)
+{
+    const int d = min(f - lo, hi - f);
+    return d <= 0 ? 0 : (d == 1 ? 2 : (d == 2 ? 4 : 6));
+}
+
+// ---- atomic max for non-negative floating point values -----------------------------------
+__device__ __forceinline__ void atomic_max_nonneg(double* addr, double v)
+{ atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v)); }
+
+template <typename TF>
+__device__ __forceinline__ void block_max_to_global(TF v, double* out)
+{
+    __shared__ double red[32];
+    double d = (double)v;
+    for (int o = 16; o > 0; o >>= 1) d = fmax(d, __shfl_xor_sync(0xffffffffu, d, o));
+    const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+    const int nth = blockDim.x * blockDim.y * blockDim.z;
+    if ((tid & 31) == 0) red[tid >> 5] = d;
+    __syncthreads();
+    if (tid < 32)
+    {
+        d = tid < (nth + 31) / 32 ? red[tid] : 0.;
+        for (int o = 16; o > 0; o >>= 1) d = fmax(d, __shfl_xor_sync(0xffffffffu, d, o));
+        if (tid == 0) atomic_max_nonneg(out, d);
+    }
+}
+
+} // namespace mhh

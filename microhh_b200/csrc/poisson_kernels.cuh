@@ -1,0 +1,460 @@
+// mhhb200 -- Poisson solver kernels for Pres_2: shared-memory Stockham FFTs (mixed radix
+// 2/3/4/5/8) in x (real <-> half-spectrum) and y (complex), and the per-mode tridiagonal
+// solve in z.  cuFFT is NOT used here; it is only a comparator in the tests.
+//
+// Reference behaviour restated (never copied): FFT<TF>::exec_forward/backward (src/fft.cxx:338-452,
+// FFTW r2r R2HC/HC2R semantics), Pres_2::solve (src/pres_2.cxx:266-362), tdma (:202-263).
+//
+// Spectral layout (ours, internal): S[k][j][m] complex (interleaved re,im), m = 0..itot/2
+// (nm = itot/2+1 x-modes); after the y transform j is the y-mode l = 0..jtot-1.
+// The eigenvalue of slot (m,l) is bmati[m] + bmatj[l] exactly as in the reference's
+// half-complex layout, so the tridiagonal systems are the reference's systems.
+#pragma once
+#include "common.cuh"
+
+namespace mhh {
+
+template <typename TF> struct cplx { TF x, y; };
+template <typename TF> __device__ __forceinline__ cplx<TF> cmul(const cplx<TF> a, const cplx<TF> b)
+{ return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+template <typename TF> __device__ __forceinline__ cplx<TF> cadd(const cplx<TF> a, const cplx<TF> b) { return {a.x + b.x, a.y + b.y}; }
+template <typename TF> __device__ __forceinline__ cplx<TF> csub(const cplx<TF> a, const cplx<TF> b) { return {a.x - b.x, a.y - b.y}; }
+template <typename TF> __device__ __forceinline__ cplx<TF> cconj(const cplx<TF> a) { return {a.x, -a.y}; }
+// multiply by -i (forward rotation)
+template <typename TF> __device__ __forceinline__ cplx<TF> cmul_mi(const cplx<TF> a) { return {a.y, -a.x}; }
+
+struct FftPlan
+{
+    int n;            // complex transform length
+    int nstages;
+    int radix[16];
+};
+
+// One radix-R Stockham (decimation in frequency, autosort) butterfly.
+//   x: input (length n), y: output.  s = stride (product of previous radices), m = n_cur / R.
+//   tw: table of exp(-2 pi i t / n), t = 0..n-1 (full-length roots of unity).
+template <typename TF, int R>
+__device__ __forceinline__ void butterfly(const cplx<TF>* __restrict__ x, cplx<TF>* __restrict__ y,
+        const cplx<TF>* __restrict__ tw, const int n, const int s, const int m, const int p, const int q)
+{
+    cplx<TF> a[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) a[r] = x[q + s * (p + r * m)];
+
+    cplx<TF> b[R];
+    if (R == 2)
+    {
+        b[0] = cadd(a[0], a[1]);
+        b[1] = csub(a[0], a[1]);
+    }
+    else if (R == 4)
+    {
+        const cplx<TF> t0 = cadd(a[0], a[2]), t1 = csub(a[0], a[2]);
+        const cplx<TF> t2 = cadd(a[1], a[3]), t3 = cmul_mi(csub(a[1], a[3]));
+        b[0] = cadd(t0, t2); b[2] = csub(t0, t2);
+        b[1] = cadd(t1, t3); b[3] = csub(t1, t3);
+    }
+    else if (R == 8)
+    {
+        const TF h = TF(0.70710678118654752440);
+        // radix-2 x radix-4 decomposition
+        cplx<TF> e[4], o[4];
+        {
+            const cplx<TF> t0 = cadd(a[0], a[4]), t1 = csub(a[0], a[4]);
+            const cplx<TF> t2 = cadd(a[2], a[6]), t3 = cmul_mi(csub(a[2], a[6]));
+            e[0] = cadd(t0, t2); e[2] = csub(t0, t2); e[1] = cadd(t1, t3); e[3] = csub(t1, t3);
+        }
+        {
+            const cplx<TF> t0 = cadd(a[1], a[5]), t1 = csub(a[1], a[5]);
+            const cplx<TF> t2 = cadd(a[3], a[7]), t3 = cmul_mi(csub(a[3], a[7]));
+            o[0] = cadd(t0, t2); o[2] = csub(t0, t2); o[1] = cadd(t1, t3); o[3] = csub(t1, t3);
+        }
+        // twiddles w8^k: 1, (1-i)/sqrt2, -i, (-1-i)/sqrt2
+        const cplx<TF> o1 = {h * (o[1].x + o[1].y), h * (o[1].y - o[1].x)};
+        const cplx<TF> o2 = cmul_mi(o[2]);
+        const cplx<TF> o3 = {h * (o[3].y - o[3].x), -h * (o[3].x + o[3].y)};
+        b[0] = cadd(e[0], o[0]); b[4] = csub(e[0], o[0]);
+        b[1] = cadd(e[1], o1);   b[5] = csub(e[1], o1);
+        b[2] = cadd(e[2], o2);   b[6] = csub(e[2], o2);
+        b[3] = cadd(e[3], o3);   b[7] = csub(e[3], o3);
+    }
+    else if (R == 3)
+    {
+        const TF c = TF(-0.5), sn = TF(0.86602540378443864676);
+        const cplx<TF> t1 = cadd(a[1], a[2]);
+        const cplx<TF> t2 = {a[0].x + c * t1.x, a[0].y + c * t1.y};
+        const cplx<TF> d = csub(a[1], a[2]);
+        const cplx<TF> t3 = {sn * d.y, -sn * d.x};       // -i*sn*d
+        b[0] = cadd(a[0], t1);
+        b[1] = cadd(t2, t3);
+        b[2] = csub(t2, t3);
+    }
+    else if (R == 5)
+    {
+        const TF c1 = TF(0.30901699437494742410), c2 = TF(-0.80901699437494742410);
+        const TF s1 = TF(0.95105651629515357212), s2 = TF(0.58778525229247312917);
+        const cplx<TF> t1 = cadd(a[1], a[4]), t2 = cadd(a[2], a[3]);
+        const cplx<TF> d1 = csub(a[1], a[4]), d2 = csub(a[2], a[3]);
+        b[0] = {a[0].x + t1.x + t2.x, a[0].y + t1.y + t2.y};
+        const cplx<TF> m1 = {a[0].x + c1 * t1.x + c2 * t2.x, a[0].y + c1 * t1.y + c2 * t2.y};
+        const cplx<TF> m2 = {a[0].x + c2 * t1.x + c1 * t2.x, a[0].y + c2 * t1.y + c1 * t2.y};
+        // -i*(s1*d1 + s2*d2), -i*(s2*d1 - s1*d2)
+        const cplx<TF> n1 = {s1 * d1.y + s2 * d2.y, -(s1 * d1.x + s2 * d2.x)};
+        const cplx<TF> n2 = {s2 * d1.y - s1 * d2.y, -(s2 * d1.x - s1 * d2.x)};
+        b[1] = cadd(m1, n1); b[4] = csub(m1, n1);
+        b[2] = cadd(m2, n2); b[3] = csub(m2, n2);
+    }
+
+    // twiddle: w_{n_cur}^{p*r} = tw[(p*r*s) mod n]   (n = n_cur*s*...: s*m*R = n)
+    y[q + s * (R * p)] = b[0];
+#pragma unroll
+    for (int r = 1; r < R; ++r)
+    {
+        const int t = (p * r * s) % n;
+        y[q + s * (R * p + r)] = cmul(b[r], tw[t]);
+    }
+}
+
+// Complex forward FFT of `nseq` sequences of length plan.n held in shared memory.
+// seq stride = ld (complex elements).  Ping-pongs between buf0 and buf1; returns the buffer
+// holding the result (natural order).  All threads of the CTA must call.
+template <typename TF>
+__device__ cplx<TF>* smem_fft(cplx<TF>* buf0, cplx<TF>* buf1, const cplx<TF>* __restrict__ tw,
+        const FftPlan& plan, const int nseq, const int ld)
+{
+    const int n = plan.n;
+    const int tid = threadIdx.x;
+    const int nth = blockDim.x;
+    int s = 1;
+    int ncur = n;
+    cplx<TF>* x = buf0;
+    cplx<TF>* y = buf1;
+    for (int st = 0; st < plan.nstages; ++st)
+    {
+        const int R = plan.radix[st];
+        const int m = ncur / R;
+        const int nb = n / R;              // butterflies per sequence
+        for (int t = tid; t < nseq * nb; t += nth)
+        {
+            const int sq = t / nb;
+            const int b = t - sq * nb;
+            const int p = b / s;
+            const int q = b - p * s;
+            const cplx<TF>* xs = x + sq * ld;
+            cplx<TF>* ys = y + sq * ld;
+            switch (R)
+            {
+                case 8: butterfly<TF, 8>(xs, ys, tw, n, s, m, p, q); break;
+                case 4: butterfly<TF, 4>(xs, ys, tw, n, s, m, p, q); break;
+                case 2: butterfly<TF, 2>(xs, ys, tw, n, s, m, p, q); break;
+                case 3: butterfly<TF, 3>(xs, ys, tw, n, s, m, p, q); break;
+                default: butterfly<TF, 5>(xs, ys, tw, n, s, m, p, q); break;
+            }
+        }
+        __syncthreads();
+        cplx<TF>* tmp = x; x = y; y = tmp;
+        s *= R;
+        ncur = m;
+    }
+    return x;
+}
+
+// ------------------------------------------------------------------------------------------
+// x transform, forward: rows of itot reals -> nm = itot/2+1 complex modes (in place in `spec`,
+// row pitch 2*nm reals).  Real FFT through a half-length complex FFT.
+// RHS_FUSED: the row is not read from `spec` but computed on the fly as the pressure rhs
+// (Pres_2::input), so the divergence never makes a round trip through HBM.
+// One CTA handles ROWS rows at a time; grid-strides over all jtot*ktot rows.
+// ------------------------------------------------------------------------------------------
+template <typename TF>
+struct RhsSrc
+{
+    const TF* u; const TF* v; const TF* w; const TF* ut; const TF* vt; const TF* wt;
+    TF dti;
+};
+
+template <typename TF, bool RHS_FUSED>
+__global__ void fft_x_forward_kernel(TF* __restrict__ spec, const RhsSrc<TF> src, const GridDev<TF> g,
+        const FftPlan plan, const cplx<TF>* __restrict__ tw_half, const cplx<TF>* __restrict__ tw_full,
+        const int rows_per_cta, const long long nrows)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int L = plan.n;               // itot/2
+    const int N = 2 * L;
+    const int nm = L + 1;
+    const int ld = L + 1;               // padded sequence stride
+    cplx<TF>* buf0 = reinterpret_cast<cplx<TF>*>(smem_raw);
+    cplx<TF>* buf1 = buf0 + rows_per_cta * ld;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const long long jj = g.icells, kk = g.ijcells;
+
+    for (long long row0 = (long long)blockIdx.x * rows_per_cta; row0 < nrows; row0 += (long long)gridDim.x * rows_per_cta)
+    {
+        const int nr = (int)min((long long)rows_per_cta, nrows - row0);
+        // load: z[n] = x[2n] + i x[2n+1]
+        for (int t = tid; t < nr * N; t += nth)
+        {
+            const int r = t / N;
+            const int i = t - r * N;
+            const long long row = row0 + r;
+            TF val;
+            if (RHS_FUSED)
+            {
+                const int k = (int)(row / g.jtot) + g.kstart;
+                const int j = (int)(row % g.jtot) + g.jstart;
+                const long long ijk = (i + g.istart) + j * jj + k * kk;
+                const long long ie = (i + 1 == g.itot) ? ijk + 1 - g.itot : ijk + 1;
+                const long long jn = (j + 1 == g.jend) ? ijk + (1 - g.jtot) * jj : ijk + jj;
+                const TF dti = src.dti;
+                val = g.rhoref[k] * ((src.ut[ie] + src.u[ie] * dti) - (src.ut[ijk] + src.u[ijk] * dti)) * g.dxi
+                    + g.rhoref[k] * ((src.vt[jn] + src.v[jn] * dti) - (src.vt[ijk] + src.v[ijk] * dti)) * g.dyi
+                    + (g.rhorefh[k + 1] * (src.wt[ijk + kk] + src.w[ijk + kk] * dti)
+                     - g.rhorefh[k    ] * (src.wt[ijk     ] + src.w[ijk     ] * dti)) * g.dzi[k];
+            }
+            else
+                val = spec[row * (2 * nm) + i];
+            TF* dst = reinterpret_cast<TF*>(buf0 + r * ld);
+            dst[i] = val;
+        }
+        __syncthreads();
+        cplx<TF>* Z = smem_fft<TF>(buf0, buf1, tw_half, plan, nr, ld);
+        // post-process: X[m] = E[m] + W_N^m O[m]
+        for (int t = tid; t < nr * nm; t += nth)
+        {
+            const int r = t / nm;
+            const int m = t - r * nm;
+            const cplx<TF>* z = Z + r * ld;
+            const cplx<TF> zm = z[m == L ? 0 : m];
+            const cplx<TF> zc = cconj(z[(L - m) % L]);
+            const cplx<TF> e = {TF(0.5) * (zm.x + zc.x), TF(0.5) * (zm.y + zc.y)};
+            const cplx<TF> d = {TF(0.5) * (zm.x - zc.x), TF(0.5) * (zm.y - zc.y)};
+            const cplx<TF> o = cmul_mi(d);                  // (zm - zc)/(2i)
+            const cplx<TF> wN = tw_full[m];                  // exp(-2 pi i m / N)
+            const cplx<TF> X = cadd(e, cmul(wN, o));
+            cplx<TF>* out = reinterpret_cast<cplx<TF>*>(spec + (row0 + r) * (2 * nm));
+            out[m] = X;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// x transform, backward, fused with Pres_2::solve's unpack: half-spectrum rows -> real rows
+// scaled by `norm` = 1/(itot*jtot), written straight into the ghosted pressure array including
+// the periodic ghost cells in x and y and the zero-gradient bottom ghost level
+// (src/pres_2.cxx:339-361), so no separate copy / boundary_cyclic pass over p is needed.
+// ------------------------------------------------------------------------------------------
+template <typename TF>
+__global__ void fft_x_backward_kernel(const TF* __restrict__ spec, TF* __restrict__ p, const GridDev<TF> g,
+        const FftPlan plan, const cplx<TF>* __restrict__ tw_half, const cplx<TF>* __restrict__ tw_full,
+        const int rows_per_cta, const long long nrows, const TF norm, const int fill_y_ghosts)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int L = plan.n;
+    const int N = 2 * L;
+    const int nm = L + 1;
+    const int ld = L + 1;
+    cplx<TF>* buf0 = reinterpret_cast<cplx<TF>*>(smem_raw);
+    cplx<TF>* buf1 = buf0 + rows_per_cta * ld;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const long long jj = g.icells, kk = g.ijcells;
+
+    for (long long row0 = (long long)blockIdx.x * rows_per_cta; row0 < nrows; row0 += (long long)gridDim.x * rows_per_cta)
+    {
+        const int nr = (int)min((long long)rows_per_cta, nrows - row0);
+        // pre-process: Z'[m] = (X[m] + conj X[L-m]) + i e^{+2 pi i m/N} (X[m] - conj X[L-m]); store conj(Z') so the
+        // forward transform yields conj(inverse).
+        for (int t = tid; t < nr * L; t += nth)
+        {
+            const int r = t / L;
+            const int m = t - r * L;
+            const cplx<TF>* X = reinterpret_cast<const cplx<TF>*>(spec + (row0 + r) * (2 * nm));
+            const cplx<TF> xm = X[m];
+            const cplx<TF> xc = cconj(X[L - m]);
+            const cplx<TF> e = cadd(xm, xc);
+            const cplx<TF> d = csub(xm, xc);
+            const cplx<TF> wc = cconj(tw_full[m]);           // exp(+2 pi i m / N)
+            const cplx<TF> wd = cmul(wc, d);
+            const cplx<TF> z = {e.x - wd.y, e.y + wd.x};     // e + i*wd
+            buf0[r * ld + m] = cconj(z);
+        }
+        __syncthreads();
+        cplx<TF>* Z = smem_fft<TF>(buf0, buf1, tw_half, plan, nr, ld);
+        // store: x[2n] = Re(conj Z[n]) = Z[n].x, x[2n+1] = Im(conj Z[n]) = -Z[n].y
+        const int wtot = g.itot + 2 * g.igc;
+        for (int t = tid; t < nr * wtot; t += nth)
+        {
+            const int r = t / wtot;
+            const int ic = t - r * wtot;          // cell index in the ghosted row
+            int i = ic - g.igc;                   // interior index, wrapped
+            if (i < 0) i += g.itot; else if (i >= g.itot) i -= g.itot;
+            const cplx<TF> zz = Z[r * ld + (i >> 1)];
+            const TF val = ((i & 1) ? -zz.y : zz.x) * norm;
+            const long long row = row0 + r;
+            const int kq = (int)(row / g.jtot);
+            const int jq = (int)(row % g.jtot);
+            const int k = kq + g.kstart;
+            const int j = jq + g.jstart;
+            const long long base = ic + j * jj + k * kk;
+            p[base] = val;
+            if (kq == 0) p[base - kk] = val;
+            if (fill_y_ghosts)
+            {
+                if (jq < g.jgc)
+                {
+                    p[base + g.jtot * jj] = val;
+                    if (kq == 0) p[base + g.jtot * jj - kk] = val;
+                }
+                if (jq >= g.jtot - g.jgc)
+                {
+                    p[base - g.jtot * jj] = val;
+                    if (kq == 0) p[base - g.jtot * jj - kk] = val;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// y transform (complex, length jtot, stride = row pitch) on panels of MC consecutive x-modes.
+// inverse != 0 -> unnormalised inverse (conjugate trick).
+// ------------------------------------------------------------------------------------------
+template <typename TF>
+__global__ void fft_y_kernel(TF* __restrict__ spec, const int nm, const int jtot, const int ktot,
+        const FftPlan plan, const cplx<TF>* __restrict__ tw, const int MC, const int inverse)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int ld = jtot + 1;
+    cplx<TF>* buf0 = reinterpret_cast<cplx<TF>*>(smem_raw);
+    cplx<TF>* buf1 = buf0 + MC * ld;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int npanel_m = (nm + MC - 1) / MC;
+    const long long npanels = (long long)npanel_m * ktot;
+    cplx<TF>* S = reinterpret_cast<cplx<TF>*>(spec);
+
+    for (long long pnl = blockIdx.x; pnl < npanels; pnl += gridDim.x)
+    {
+        const int k = (int)(pnl / npanel_m);
+        const int m0 = (int)(pnl % npanel_m) * MC;
+        const int mc = min(MC, nm - m0);
+        cplx<TF>* base = S + (long long)k * jtot * nm + m0;
+        for (int t = tid; t < jtot * MC; t += nth)
+        {
+            const int j = t / MC;
+            const int c = t - j * MC;
+            if (c < mc)
+            {
+                cplx<TF> v = base[(long long)j * nm + c];
+                if (inverse) v.y = -v.y;
+                buf0[c * ld + j] = v;
+            }
+        }
+        __syncthreads();
+        cplx<TF>* Z = smem_fft<TF>(buf0, buf1, tw, plan, mc, ld);
+        for (int t = tid; t < jtot * MC; t += nth)
+        {
+            const int j = t / MC;
+            const int c = t - j * MC;
+            if (c < mc)
+            {
+                cplx<TF> v = Z[c * ld + j];
+                if (inverse) v.y = -v.y;
+                base[(long long)j * nm + c] = v;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Tridiagonal solve in z, one thread per (l, m) complex column (re and im share the factors).
+// The elimination factors depend only on the grid and the base state, so they are tabulated
+// once (`fac`, [k][l][m]) by tdma_setup_kernel and the sweeps carry no division chain.
+//   reference tdma:  work3d[k] = c[k-1]/w[k-1];  w[k] = b[k] - a[k]*work3d[k];
+//                    p[k] = (p[k] - a[k]*p[k-1]) / w[k];   back: p[k] -= work3d[k+1]*p[k+1]
+//   table: fac[k] = work3d[k] (k>=1), fac[0] unused;  winv[k] = 1/w[k] is rebuilt from b and fac.
+// ------------------------------------------------------------------------------------------
+template <typename TF>
+struct TdmaCoef
+{
+    const TF* a; const TF* c;        // kmax
+    const TF* dz2rho;                // kmax: dz^2 * rhoref
+    const TF* dz2;                   // kmax: dz^2
+    const TF* bmati; const TF* bmatj; // nm, jtot
+};
+
+template <typename TF>
+__device__ __forceinline__ TF tdma_b(const TdmaCoef<TF>& cf, const int k, const int kmax, const TF lam, const bool mode00)
+{
+    TF b = cf.dz2rho[k] * lam - (cf.a[k] + cf.c[k]);
+    if (k == 0) b += cf.a[0];
+    if (k == kmax - 1) b = mode00 ? b - cf.c[kmax - 1] : b + cf.c[kmax - 1];
+    return b;
+}
+
+template <typename TF>
+__global__ void tdma_setup_kernel(TF* __restrict__ fac, const TdmaCoef<TF> cf, const int nm, const int jtot, const int kmax,
+        const int m_off, const int l_off)
+{
+    const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long ncol = (long long)nm * jtot;
+    if (col >= ncol) return;
+    const int l = (int)(col / nm), m = (int)(col % nm);
+    const TF lam = cf.bmati[m + m_off] + cf.bmatj[l + l_off];
+    const bool mode00 = (m + m_off == 0) && (l + l_off == 0);
+    TF w = tdma_b(cf, 0, kmax, lam, mode00);
+    fac[col] = TF(0);
+    for (int k = 1; k < kmax; ++k)
+    {
+        const TF f = cf.c[k - 1] / w;
+        fac[col + k * ncol] = f;
+        w = tdma_b(cf, k, kmax, lam, mode00) - cf.a[k] * f;
+    }
+}
+
+template <typename TF>
+__global__ void __launch_bounds__(128) tdma_solve_kernel(TF* __restrict__ spec, const TF* __restrict__ fac, const TdmaCoef<TF> cf,
+        const int nm, const int jtot, const int kmax, const int m_off, const int l_off)
+{
+    const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long ncol = (long long)nm * jtot;
+    if (col >= ncol) return;
+    const int l = (int)(col / nm), m = (int)(col % nm);
+    const TF lam = cf.bmati[m + m_off] + cf.bmatj[l + l_off];
+    const bool mode00 = (m + m_off == 0) && (l + l_off == 0);
+    cplx<TF>* S = reinterpret_cast<cplx<TF>*>(spec) + col;
+
+    // forward sweep
+    cplx<TF> prev;
+    {
+        const TF w = tdma_b(cf, 0, kmax, lam, mode00);
+        cplx<TF> v = S[0];
+        const TF s = cf.dz2[0] / w;
+        prev = {v.x * s, v.y * s};
+        S[0] = prev;
+    }
+#pragma unroll 4
+    for (int k = 1; k < kmax; ++k)
+    {
+        const TF f = fac[col + k * ncol];
+        const TF ak = cf.a[k];
+        const TF w = tdma_b(cf, k, kmax, lam, mode00) - ak * f;
+        const TF winv = TF(1) / w;
+        const cplx<TF> v = S[k * ncol];
+        const TF d2 = cf.dz2[k];
+        prev = {(d2 * v.x - ak * prev.x) * winv, (d2 * v.y - ak * prev.y) * winv};
+        S[k * ncol] = prev;
+    }
+    // back substitution
+#pragma unroll 4
+    for (int k = kmax - 2; k >= 0; --k)
+    {
+        const TF f = fac[col + (k + 1) * ncol];
+        const cplx<TF> v = S[k * ncol];
+        prev = {v.x - f * prev.x, v.y - f * prev.y};
+        S[k * ncol] = prev;
+    }
+}
+
+} // namespace mhh

@@ -1,0 +1,268 @@
+"""
+Host-side mirror of the reference's operator interface for the hot path, over the C ABI.
+Names follow the reference: `Fields` (maps mp/mt/sp/st/sd of include/fields.h:134-143),
+`Boundary_cyclic.exec`, `Advec.exec/get_cfl`, `Diff.exec_viscosity/exec/get_dn`,
+`Pres.exec/check_divergence`, `Timeloop.exec` (include/advec.h:54-60, include/diff.h:45-62,
+include/pres.h:48-58, include/boundary_cyclic.h:42-50, include/timeloop.h:65).
+torch is used for device memory only.
+"""
+import ctypes as C
+import numpy as np
+import torch
+
+from . import capi
+from .capi import FieldsC, ParamsC, GridDesc, MhhError
+
+SWADVEC = {"2i5": 25, "2": 2, "4": 4}
+SWDIFF = {"smag2": 1, "2": 2, "4": 4}
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class Context:
+    """One mhh_ctx: grid + base state on one GPU."""
+
+    def __init__(self, gd, device=0):
+        if not torch.cuda.is_available():
+            raise MhhError("mhhb200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = capi.load()
+        self.gd = gd
+        self.device = device
+        self.torch_dtype = torch.float64 if gd.dtype == np.float64 else torch.float32
+        self._keep = [np.ascontiguousarray(getattr(gd, n)) for n in ("z", "zh", "dz", "dzh", "dzi", "dzhi")]
+        d = GridDesc(gd.itot, gd.jtot, gd.ktot, gd.imax, gd.jmax, gd.kmax, gd.igc, gd.jgc, gd.kgc,
+                     float(gd.xsize), float(gd.ysize), float(gd.zsize),
+                     *[a.ctypes.data_as(C.c_void_p) for a in self._keep],
+                     gd.npx, gd.npy, gd.mpicoordx, gd.mpicoordy)
+        h = C.c_void_p()
+        rc = self.lib.mhh_ctx_create(C.byref(d), capi.MHH_F64 if gd.dtype == np.float64 else capi.MHH_F32,
+                                     device, C.byref(h))
+        self.h = h
+        if rc != 0:
+            msg = self.lib.mhh_last_error(h).decode()
+            if h:
+                self.lib.mhh_ctx_destroy(h)
+            self.h = None
+            raise MhhError(f"mhh_ctx_create failed ({rc}): {msg}")
+        # run on torch's current stream so torch.cuda.Event timing sees the kernels
+        self.use_torch_stream()
+
+    def use_torch_stream(self):
+        s = torch.cuda.current_stream(self.device)
+        self.check(self.lib.mhh_set_stream(self.h, C.c_void_p(s.cuda_stream)))
+
+    def check(self, rc):
+        if rc != 0:
+            raise MhhError(f"mhhb200 error {rc}: {self.lib.mhh_last_error(self.h).decode()}")
+
+    def set_basestate(self, rhoref, rhorefh, thref=None, threfh=None):
+        arrs = [None if a is None else np.ascontiguousarray(a, dtype=self.gd.dtype) for a in (rhoref, rhorefh, thref, threfh)]
+        self.check(self.lib.mhh_set_basestate(self.h, *[None if a is None else a.ctypes.data_as(C.c_void_p) for a in arrs]))
+
+    def sync(self):
+        self.check(self.lib.mhh_sync(self.h))
+
+    @property
+    def launch_count(self):
+        return int(self.lib.mhh_launch_count(self.h))
+
+    def profile_start(self):
+        self.check(self.lib.mhh_profile_start(self.h))
+
+    def profile_stop(self):
+        import json
+        out = C.c_char_p()
+        self.check(self.lib.mhh_profile_stop(self.h, C.byref(out)))
+        return json.loads(out.value.decode())
+
+    @property
+    def workspace_bytes(self):
+        return int(self.lib.mhh_workspace_bytes(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mhh_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Fields:
+    """Device fields in the reference's ghosted layout, as torch tensors (kcells, jcells, icells)."""
+
+    def __init__(self, ctx, case=None, scalars=("th",), visc=1.e-5, svisc=1.e-5):
+        self.ctx = ctx
+        gd = ctx.gd
+        self.scalars = list(scalars)
+        dev = torch.device("cuda", ctx.device)
+        z3 = lambda: torch.zeros(gd.shape, dtype=ctx.torch_dtype, device=dev)
+        z2 = lambda: torch.zeros(gd.shape2d, dtype=ctx.torch_dtype, device=dev)
+        self.t = {}
+        for n in ["u", "v", "w", "ut", "vt", "wt", "evisc", "p"]:
+            self.t[n] = z3()
+        for s in self.scalars:
+            self.t[s] = z3(); self.t[s + "t"] = z3()
+        names2d = ["u_fluxbot", "u_fluxtop", "v_fluxbot", "v_fluxtop", "dudz_mo", "dvdz_mo", "dbdz_mo", "z0m",
+                   "u_bot", "u_gradbot", "u_top", "u_gradtop", "v_bot", "v_gradbot", "v_top", "v_gradtop"]
+        for s in self.scalars:
+            names2d += [f"{s}_fluxbot", f"{s}_fluxtop", f"{s}_bot", f"{s}_gradbot", f"{s}_top", f"{s}_gradtop"]
+        for n in names2d:
+            self.t[n] = z2()
+        self.visc = visc
+        self.svisc = svisc
+        if case is not None:
+            self.upload(case)
+        self._build()
+
+    def upload(self, case):
+        for n, t in self.t.items():
+            if n in case and isinstance(case[n], np.ndarray):
+                t.copy_(torch.from_numpy(np.ascontiguousarray(case[n])))
+
+    def download(self, names=None):
+        names = names or list(self.t.keys())
+        return {n: self.t[n].cpu().numpy() for n in names}
+
+    def __getitem__(self, n):
+        return self.t[n]
+
+    def _build(self):
+        c = FieldsC()
+        for n in ["u", "v", "w", "ut", "vt", "wt", "evisc", "p", "u_fluxbot", "u_fluxtop", "v_fluxbot", "v_fluxtop",
+                  "dudz_mo", "dvdz_mo", "dbdz_mo", "z0m", "u_bot", "u_gradbot", "u_top", "u_gradtop",
+                  "v_bot", "v_gradbot", "v_top", "v_gradtop"]:
+            setattr(c, n, _ptr(self.t[n]))
+        c.ns = len(self.scalars)
+        c.visc = self.visc
+        for i, s in enumerate(self.scalars):
+            c.s[i] = self.t[s].data_ptr(); c.st[i] = self.t[s + "t"].data_ptr()
+            c.svisc[i] = self.svisc
+            c.s_fluxbot[i] = self.t[f"{s}_fluxbot"].data_ptr(); c.s_fluxtop[i] = self.t[f"{s}_fluxtop"].data_ptr()
+            c.s_bot[i] = self.t[f"{s}_bot"].data_ptr(); c.s_gradbot[i] = self.t[f"{s}_gradbot"].data_ptr()
+            c.s_top[i] = self.t[f"{s}_top"].data_ptr(); c.s_gradtop[i] = self.t[f"{s}_gradtop"].data_ptr()
+        self.c = c
+
+
+def make_params(swadvec="2i5", swdiff="smag2", swthermo="dry", surface_model=True, sw_mason=True,
+                cs=0.23, tPr=1./3., mbcbot=capi.BC_NEUMANN, mbctop=capi.BC_NEUMANN,
+                sbcbot=capi.BC_NEUMANN, sbctop=capi.BC_NEUMANN, ns=1):
+    p = ParamsC()
+    p.swadvec = SWADVEC[swadvec]; p.swdiff = SWDIFF[swdiff]
+    p.swthermo = 1 if swthermo == "dry" else 0
+    p.surface_model = int(surface_model); p.sw_mason = int(sw_mason)
+    p.cs = cs; p.tPr = tPr
+    p.mbcbot = mbcbot; p.mbctop = mbctop
+    for i in range(capi.MHH_MAX_SCALARS):
+        p.sbcbot[i] = sbcbot; p.sbctop[i] = sbctop
+    return p
+
+
+class Boundary_cyclic:
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    def exec(self, fld, edge=capi.EDGE_BOTH):
+        self.ctx.check(self.ctx.lib.mhh_boundary_cyclic(self.ctx.h, _ptr(fld), edge))
+
+    def exec_2d(self, fld):
+        self.ctx.check(self.ctx.lib.mhh_boundary_cyclic_2d(self.ctx.h, _ptr(fld)))
+
+
+class Boundary:
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    def set_ghost_cells_field(self, fld, bcbot, bot, gradbot, bctop, top, gradtop):
+        self.ctx.check(self.ctx.lib.mhh_boundary_ghost_cells_2nd(
+            self.ctx.h, _ptr(fld), bcbot, _ptr(bot), _ptr(gradbot), bctop, _ptr(top), _ptr(gradtop)))
+
+
+class Advec:
+    def __init__(self, ctx, swadvec="2i5"):
+        self.ctx = ctx; self.sw = SWADVEC[swadvec]
+
+    def exec(self, fields):
+        self.ctx.check(self.ctx.lib.mhh_advec_exec(self.ctx.h, self.sw, C.byref(fields.c)))
+
+    def get_cfl(self, fields, dt):
+        out = C.c_double()
+        self.ctx.check(self.ctx.lib.mhh_advec_get_cfl(self.ctx.h, self.sw, C.byref(fields.c), dt, C.byref(out)))
+        return out.value
+
+
+class Diff:
+    def __init__(self, ctx, params):
+        self.ctx = ctx; self.prm = params
+
+    def exec_viscosity(self, fields, n2=None):
+        self.ctx.check(self.ctx.lib.mhh_diff_smag2_exec_viscosity(self.ctx.h, C.byref(fields.c), C.byref(self.prm), _ptr(n2)))
+
+    def exec(self, fields):
+        self.ctx.check(self.ctx.lib.mhh_diff_smag2_exec(self.ctx.h, C.byref(fields.c), C.byref(self.prm)))
+
+    def get_dn(self, fields, dt):
+        out = C.c_double()
+        self.ctx.check(self.ctx.lib.mhh_diff_smag2_get_dn(self.ctx.h, C.byref(fields.c), C.byref(self.prm), dt, C.byref(out)))
+        return out.value
+
+
+class Thermo_dry:
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    def exec(self, fields):
+        self.ctx.check(self.ctx.lib.mhh_thermo_dry_exec(self.ctx.h, _ptr(fields["wt"]), _ptr(fields[fields.scalars[0]])))
+
+    def get_thermo_field_N2(self, out, fields):
+        self.ctx.check(self.ctx.lib.mhh_thermo_dry_n2(self.ctx.h, _ptr(out), _ptr(fields[fields.scalars[0]])))
+
+
+class Pres:
+    def __init__(self, ctx, swpres=2):
+        self.ctx = ctx; self.sw = swpres
+
+    def exec(self, fields, sub_dt):
+        self.ctx.check(self.ctx.lib.mhh_pres_exec(self.ctx.h, self.sw, C.byref(fields.c), sub_dt))
+
+    def check_divergence(self, fields):
+        out = C.c_double()
+        self.ctx.check(self.ctx.lib.mhh_pres_check_divergence(self.ctx.h, self.sw, C.byref(fields.c), C.byref(out)))
+        return out.value
+
+    def fft_roundtrip(self, a_in, a_out, solve=False):
+        self.ctx.check(self.ctx.lib.mhh_pres_fft_roundtrip(self.ctx.h, _ptr(a_in), _ptr(a_out), int(solve)))
+
+
+class Timeloop:
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    def exec(self, fields, substep, dt):
+        names = ["u", "v", "w"] + fields.scalars
+        for n in names:
+            self.ctx.check(self.ctx.lib.mhh_timeloop_rk3(self.ctx.h, _ptr(fields[n]), _ptr(fields[n + "t"]), substep, dt))
+
+
+class Dycore:
+    """Fused sub-step / step drivers (Model::exec order restricted to the hot path)."""
+
+    def __init__(self, ctx, params):
+        self.ctx = ctx; self.prm = params
+
+    def substep(self, fields, substep, dt):
+        self.ctx.check(self.ctx.lib.mhh_dycore_substep(self.ctx.h, C.byref(fields.c), C.byref(self.prm), substep, dt))
+
+    def step(self, fields, dt):
+        self.ctx.check(self.ctx.lib.mhh_dycore_step(self.ctx.h, C.byref(fields.c), C.byref(self.prm), dt))
+
+    def step_host(self, fields, dt, nsteps, h_u, h_v, h_w, h_s):
+        arr = (C.c_void_p * len(h_s))(*[t.data_ptr() for t in h_s])
+        self.ctx.check(self.ctx.lib.mhh_dycore_step_host(
+            self.ctx.h, C.byref(fields.c), C.byref(self.prm), dt, nsteps,
+            C.c_void_p(h_u.data_ptr()), C.c_void_p(h_v.data_ptr()), C.c_void_p(h_w.data_ptr()), arr))

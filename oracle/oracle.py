@@ -831,3 +831,31 @@ def rk3(g, a, at, substep, dt):
 def rk3_subdt(dt, substep):
     """get_sub_time_step: double arithmetic (src/timeloop.cxx:338-342, 415-423)"""
     return RK3_CB[substep]*float(dt)
+
+
+# --------------------------------------------------------------------------------------
+# Same call surface as refbind.RefKernels, backed by the numpy restatement above
+# --------------------------------------------------------------------------------------
+class NumpyKernels:
+    def __init__(self, g):
+        self.g = g
+
+    def boundary_cyclic(self, a, edge=EDGE_BOTH): boundary_cyclic(self.g, a, edge)
+    def ghost_cells_bot_2nd(self, a, bc, abot, agradbot): ghost_cells_bot_2nd(self.g, a, bc, abot, agradbot)
+    def ghost_cells_top_2nd(self, a, bc, atop, agradtop): ghost_cells_top_2nd(self.g, a, bc, atop, agradtop)
+    def advec_2i5_u(self, ut, u, v, w, rhoref, rhorefh): advec_2i5_u(self.g, ut, u, v, w, rhoref, rhorefh)
+    def advec_2i5_v(self, vt, u, v, w, rhoref, rhorefh): advec_2i5_v(self.g, vt, u, v, w, rhoref, rhorefh)
+    def advec_2i5_w(self, wt, u, v, w, rhoref, rhorefh): advec_2i5_w(self.g, wt, u, v, w, rhoref, rhorefh)
+    def advec_2i5_s(self, st, s, u, v, w, rhoref, rhorefh): advec_2i5_s(self.g, st, s, u, v, w, rhoref, rhorefh)
+    def advec_2i5_cfl(self, u, v, w, dt): return float(advec_2i5_cfl(self.g, u, v, w, dt))
+    def diff_strain2(self, strain2, u, v, w, ugradbot, vgradbot, surface): diff_strain2(self.g, strain2, u, v, w, ugradbot, vgradbot, surface)
+    def diff_evisc(self, evisc, u, v, w, N2, bgradbot, z0m, cs, tPr, surface, mason=True): diff_evisc(self.g, evisc, N2, bgradbot, z0m, cs, tPr, surface, mason)
+    def diff_u(self, ut, u, v, w, evisc, fluxbot, fluxtop, rhoref, rhorefh, visc, surface): diff_u(self.g, ut, u, v, w, evisc, fluxbot, fluxtop, rhoref, rhorefh, visc, surface)
+    def diff_v(self, vt, u, v, w, evisc, fluxbot, fluxtop, rhoref, rhorefh, visc, surface): diff_v(self.g, vt, u, v, w, evisc, fluxbot, fluxtop, rhoref, rhorefh, visc, surface)
+    def diff_w(self, wt, u, v, w, evisc, rhoref, rhorefh, visc): diff_w(self.g, wt, u, v, w, evisc, rhoref, rhorefh, visc)
+    def diff_c(self, at, a, evisc, fluxbot, fluxtop, rhoref, rhorefh, tPr, visc, surface): diff_c(self.g, at, a, evisc, fluxbot, fluxtop, rhoref, rhorefh, tPr, visc, surface)
+    def diff_dnmul(self, evisc, tPr): return float(diff_dnmul(self.g, evisc, tPr))
+    def thermo_dry_N2(self, N2, th, thref): thermo_dry_N2(self.g, N2, th, thref)
+    def thermo_dry_buoyancy_tend_2nd(self, wt, th, threfh): thermo_dry_buoyancy_tend_2nd(self.g, wt, th, threfh)
+    def rk3(self, a, at, substep, dt): rk3(self.g, a, at, substep, dt)
+    tdma = None   # Pres2.tdma is used

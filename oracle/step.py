@@ -1,0 +1,85 @@
+"""
+TEST INFRASTRUCTURE ONLY -- one RK3 sub-step / step of the dynamical core in the reference's
+call order (Model<TF>::exec, reference src/model.cxx:356-504, restricted to the hot path):
+
+  boundary.set_prognostic_cyclic_bcs (:368) -> boundary.set_ghost_cells (:370) ->
+  diff.exec_viscosity (:376) -> thermo.exec (:388) -> advec.exec (:410) -> diff.exec (:414) ->
+  pres.exec (:435-437) -> timeloop.exec (:504)
+
+`K` supplies the kernels: oracle.NumpyKernels (the numpy restatement) or refbind.RefKernels
+(the reference's own compiled CPU kernels).  The member-function glue (Pres_2 input/solve/
+output, FFT) is always oracle.Pres2.
+"""
+import numpy as np
+from . import oracle as O
+
+
+def default_params(ns=1):
+    return dict(surface_model=True, sw_mason=True, cs=0.23, tPr=1./3., swthermo="dry",
+                mbcbot=O.BC_NEUMANN, mbctop=O.BC_NEUMANN, sbcbot=O.BC_NEUMANN, sbctop=O.BC_NEUMANN,
+                visc=1.e-5, svisc=1.e-5)
+
+
+def dycore_substep(g, K, c, prm, substep, dt, pres=None, timers=None):
+    """c: dict of numpy arrays as made by microhh_b200.synthetic.make_case (modified in place)."""
+    import time
+    t0 = time.perf_counter()
+    def lap(name):
+        nonlocal t0
+        if timers is not None:
+            t1 = time.perf_counter(); timers[name] = timers.get(name, 0.) + (t1 - t0); t0 = t1
+    scal = c["scalars"]
+    rr, rh = c["rhoref"], c["rhorefh"]
+    surface = prm["surface_model"]
+    for n in ["u", "v", "w"] + scal:
+        K.boundary_cyclic(c[n])
+    for n in ["u", "v"]:
+        K.ghost_cells_bot_2nd(c[n], prm["mbcbot"], c.get(n + "_bot"), c.get(n + "_gradbot"))
+        K.ghost_cells_top_2nd(c[n], prm["mbctop"], c.get(n + "_top"), c.get(n + "_gradtop"))
+    for s in scal:
+        K.ghost_cells_bot_2nd(c[s], prm["sbcbot"], c.get(s + "_bot"), c.get(s + "_gradbot"))
+        K.ghost_cells_top_2nd(c[s], prm["sbctop"], c.get(s + "_top"), c.get(s + "_gradtop"))
+    lap("boundary")
+    # exec_viscosity
+    K.diff_strain2(c["evisc"], c["u"], c["v"], c["w"], c["dudz_mo"], c["dvdz_mo"], surface)
+    N2 = np.zeros_like(c["evisc"])
+    K.thermo_dry_N2(N2, c[scal[0]], c["thref"])
+    K.diff_evisc(c["evisc"], c["u"], c["v"], c["w"], N2, c["dbdz_mo"], c["z0m"], prm["cs"], prm["tPr"], surface, prm["sw_mason"])
+    lap("evisc")
+    # thermo.exec
+    if prm["swthermo"] == "dry":
+        K.thermo_dry_buoyancy_tend_2nd(c["wt"], c[scal[0]], c["threfh"])
+    # advec.exec
+    K.advec_2i5_u(c["ut"], c["u"], c["v"], c["w"], rr, rh)
+    K.advec_2i5_v(c["vt"], c["u"], c["v"], c["w"], rr, rh)
+    K.advec_2i5_w(c["wt"], c["u"], c["v"], c["w"], rr, rh)
+    for s in scal:
+        K.advec_2i5_s(c[s + "t"], c[s], c["u"], c["v"], c["w"], rr, rh)
+    lap("advec")
+    # diff.exec
+    K.diff_u(c["ut"], c["u"], c["v"], c["w"], c["evisc"], c["u_fluxbot"], c["u_fluxtop"], rr, rh, prm["visc"], surface)
+    K.diff_v(c["vt"], c["u"], c["v"], c["w"], c["evisc"], c["v_fluxbot"], c["v_fluxtop"], rr, rh, prm["visc"], surface)
+    K.diff_w(c["wt"], c["u"], c["v"], c["w"], c["evisc"], rr, rh, prm["visc"])
+    for s in scal:
+        K.diff_c(c[s + "t"], c[s], c["evisc"], c[s + "_fluxbot"], c[s + "_fluxtop"], rr, rh, prm["tPr"], prm["svisc"], surface)
+    lap("diff")
+    # pres.exec(sub_dt)
+    if pres is None:
+        pres = O.Pres2(g, rr, rh)
+    tdma = None
+    if getattr(K, "tdma", None) is not None:
+        tdma = lambda p, b: K.tdma(pres.a.copy(), b, pres.c.copy(), p)
+    pres.exec(c["p"], c["u"], c["v"], c["w"], c["ut"], c["vt"], c["wt"], O.rk3_subdt(dt, substep), tdma)
+    lap("pres")
+    # timeloop.exec
+    for n in ["u", "v", "w"] + scal:
+        K.rk3(c[n], c[n + "t"], substep, dt)
+    lap("rk3")
+    return pres
+
+
+def dycore_step(g, K, c, prm, dt, timers=None):
+    pres = None
+    for ss in range(3):
+        pres = dycore_substep(g, K, c, prm, ss, dt, pres, timers)
+    return pres

@@ -1,0 +1,256 @@
+"""
+Parity tests proper: the CUDA path, called through the C ABI (libmhhb200.so), against the
+oracle on the same seeded inputs.  Tolerances are BASELINE.json's: relative L2 <= 1e-12 in
+fp64 and <= 1e-5 in fp32; copies (boundary_cyclic) are bit-exact.
+"""
+import copy
+import numpy as np
+import pytest
+
+from util import TOL, rel_l2, make_pair, interior, prepare_halos
+from oracle import oracle as O
+from oracle import step as ostep
+
+pytestmark = pytest.mark.gpu
+
+DTYPES = [np.float64, np.float32]
+SHAPES = [(32, 16, 12), (48, 40, 24), (20, 12, 8)]
+
+
+def gpu_setup(gd, case, ns=1):
+    import torch
+    from microhh_b200 import dycore as D
+    ctx = D.Context(gd, 0)
+    ctx.set_basestate(case["rhoref"], case["rhorefh"], case["thref"], case["threfh"])
+    f = D.Fields(ctx, case, scalars=case["scalars"])
+    prm = D.make_params(ns=ns)
+    return D, ctx, f, prm
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(16, 12, 8), (32, 1, 8)])
+@pytest.mark.parametrize("edge", [0, 1, 2])
+def test_boundary_cyclic_bitexact(dtype, shape, edge):
+    g, gd, case = make_pair(*shape, dtype)
+    rng = np.random.default_rng(5)
+    a = rng.standard_normal(gd.shape).astype(dtype)
+    case["u"] = a.copy()
+    D, ctx, f, prm = gpu_setup(gd, case)
+    D.Boundary_cyclic(ctx).exec(f["u"], edge)
+    O.boundary_cyclic(g, a, edge)
+    assert np.array_equal(f["u"].cpu().numpy(), a)
+    a2 = rng.standard_normal(gd.shape2d).astype(dtype)
+    f["z0m"].copy_(__import__("torch").from_numpy(a2))
+    D.Boundary_cyclic(ctx).exec_2d(f["z0m"])
+    O.boundary_cyclic_2d(g, a2)
+    assert np.array_equal(f["z0m"].cpu().numpy(), a2)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_ghost_cells(dtype):
+    g, gd, case = make_pair(16, 12, 8, dtype, stretched=True)
+    D, ctx, f, prm = gpu_setup(gd, case)
+    B = D.Boundary(ctx)
+    for bc in (0, 1):
+        a = case["u"].copy()
+        f["u"].copy_(__import__("torch").from_numpy(a))
+        B.set_ghost_cells_field(f["u"], bc, f["u_gradbot"], f["u_gradbot"], bc, f["u_gradtop"], f["u_gradtop"])
+        O.ghost_cells_bot_2nd(g, a, bc, case["u_gradbot"], case["u_gradbot"])
+        O.ghost_cells_top_2nd(g, a, bc, case["u_gradtop"], case["u_gradtop"])
+        assert rel_l2(f["u"].cpu().numpy(), a) <= TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("anel", [False, True])
+def test_advec_2i5(dtype, shape, anel):
+    g, gd, case = make_pair(*shape, dtype, stretched=True, anelastic=anel)
+    prepare_halos(g, case)
+    D, ctx, f, prm = gpu_setup(gd, case)
+    D.Advec(ctx, "2i5").exec(f)
+    rr, rh = case["rhoref"], case["rhorefh"]
+    ref = {n: g.field() for n in ("ut", "vt", "wt", "tht")}
+    O.advec_2i5_u(g, ref["ut"], case["u"], case["v"], case["w"], rr, rh)
+    O.advec_2i5_v(g, ref["vt"], case["u"], case["v"], case["w"], rr, rh)
+    O.advec_2i5_w(g, ref["wt"], case["u"], case["v"], case["w"], rr, rh)
+    O.advec_2i5_s(g, ref["tht"], case["th"], case["u"], case["v"], case["w"], rr, rh)
+    for n in ref:
+        assert rel_l2(f[n].cpu().numpy(), ref[n]) <= TOL[dtype], n
+    cfl = D.Advec(ctx, "2i5").get_cfl(f, 3.0)
+    assert abs(cfl - float(O.advec_2i5_cfl(g, case["u"], case["v"], case["w"], 3.0))) <= 10*TOL[dtype]*cfl
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("surface", [True, False])
+def test_diff_smag2(dtype, shape, surface):
+    g, gd, case = make_pair(*shape, dtype, stretched=True, anelastic=True)
+    prepare_halos(g, case)
+    D, ctx, f, _ = gpu_setup(gd, case)
+    prm = D.make_params(surface_model=surface)
+    diff = D.Diff(ctx, prm)
+    # exec_viscosity, N2 derived from th
+    diff.exec_viscosity(f)
+    ev = g.field(); N2 = g.field()
+    O.diff_strain2(g, ev, case["u"], case["v"], case["w"], case["dudz_mo"], case["dvdz_mo"], surface)
+    O.thermo_dry_N2(g, N2, case["th"], case["thref"])
+    O.diff_evisc(g, ev, N2, case["dbdz_mo"], case["z0m"], 0.23, 1./3., surface)
+    k0 = g.kstart - (0 if surface else 1); k1 = g.kend + (0 if surface else 1)
+    got = f["evisc"].cpu().numpy()
+    assert rel_l2(got[k0:k1], ev[k0:k1]) <= TOL[dtype]
+    # exec_viscosity with an externally supplied N2 field
+    import torch
+    n2_dev = torch.zeros_like(f["evisc"])
+    D.Thermo_dry(ctx).get_thermo_field_N2(n2_dev, f)
+    assert rel_l2(interior(g, n2_dev.cpu().numpy()), interior(g, N2)) <= TOL[dtype]
+    f["evisc"].zero_()
+    diff.exec_viscosity(f, n2_dev)
+    assert rel_l2(f["evisc"].cpu().numpy()[k0:k1], ev[k0:k1]) <= TOL[dtype]
+    # exec
+    f["evisc"].copy_(torch.from_numpy(ev))
+    diff.exec(f)
+    rr, rh = case["rhoref"], case["rhorefh"]
+    ref = {n: g.field() for n in ("ut", "vt", "wt", "tht")}
+    O.diff_u(g, ref["ut"], case["u"], case["v"], case["w"], ev, case["u_fluxbot"], case["u_fluxtop"], rr, rh, 1e-5, surface)
+    O.diff_v(g, ref["vt"], case["u"], case["v"], case["w"], ev, case["v_fluxbot"], case["v_fluxtop"], rr, rh, 1e-5, surface)
+    O.diff_w(g, ref["wt"], case["u"], case["v"], case["w"], ev, rr, rh, 1e-5)
+    O.diff_c(g, ref["tht"], case["th"], ev, case["th_fluxbot"], case["th_fluxtop"], rr, rh, 1./3., 1e-5, surface)
+    for n in ref:
+        assert rel_l2(f[n].cpu().numpy(), ref[n]) <= TOL[dtype], n
+    dn = diff.get_dn(f, 2.0)
+    assert abs(dn - 2.0*float(O.diff_dnmul(g, ev, 1./3.))) <= 10*TOL[dtype]*dn
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_thermo_dry_buoyancy(dtype):
+    g, gd, case = make_pair(32, 16, 12, dtype)
+    prepare_halos(g, case)
+    D, ctx, f, prm = gpu_setup(gd, case)
+    D.Thermo_dry(ctx).exec(f)
+    ref = g.field()
+    O.thermo_dry_buoyancy_tend_2nd(g, ref, case["th"], case["threfh"])
+    assert rel_l2(f["wt"].cpu().numpy(), ref) <= TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("substep", [0, 1, 2])
+def test_rk3(dtype, substep):
+    g, gd, case = make_pair(16, 12, 8, dtype)
+    rng = np.random.default_rng(3)
+    for n in ("u", "v", "w", "th"):
+        case[n + "t"] = rng.standard_normal(gd.shape).astype(dtype)
+    D, ctx, f, prm = gpu_setup(gd, case)
+    D.Timeloop(ctx).exec(f, substep, 6.0)
+    for n in ("u", "v", "w", "th"):
+        a, at = case[n].copy(), case[n + "t"].copy()
+        O.rk3(g, a, at, substep, 6.0)
+        assert rel_l2(f[n].cpu().numpy(), a) <= TOL[dtype]
+        assert rel_l2(f[n + "t"].cpu().numpy(), at) <= TOL[dtype] or np.abs(at).max() == 0
+        if substep == 2:
+            assert float(f[n + "t"].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(32, 16, 12), (48, 40, 24), (20, 12, 8), (96, 6, 8), (16, 1, 16)])
+def test_fft_roundtrip_and_solve(dtype, shape):
+    """x/y transforms round-trip to the identity; with the tridiagonal solve in between the result
+    equals the oracle's FFTW-semantics solve (r2hc -> tdma -> hc2r)."""
+    import torch
+    g, gd, case = make_pair(*shape, dtype, stretched=True, anelastic=True)
+    D, ctx, f, prm = gpu_setup(gd, case)
+    rng = np.random.default_rng(7)
+    rhs = rng.standard_normal((gd.kmax, gd.jmax, gd.imax)).astype(dtype)
+    a_in = torch.from_numpy(rhs).cuda(); a_out = torch.zeros_like(a_in)
+    pres = D.Pres(ctx)
+    pres.fft_roundtrip(a_in, a_out, solve=False)
+    assert rel_l2(a_out.cpu().numpy(), rhs) <= 20*TOL[dtype]
+    pres.fft_roundtrip(a_in, a_out, solve=True)
+    P = O.Pres2(g, case["rhoref"], case["rhorefh"])
+    p = g.field()
+    P.solve(rhs.copy(), p)
+    assert rel_l2(a_out.cpu().numpy(), interior(g, p)) <= 50*TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(32, 16, 12), (48, 40, 24)])
+@pytest.mark.parametrize("anel", [False, True])
+def test_pres_2_exec(dtype, shape, anel):
+    g, gd, case = make_pair(*shape, dtype, stretched=True, anelastic=anel)
+    prepare_halos(g, case)
+    rng = np.random.default_rng(11)
+    for n in ("ut", "vt", "wt"):
+        t = np.zeros(gd.shape, dtype)
+        interior(g, t)[...] = 0.01*rng.standard_normal((gd.kmax, gd.jmax, gd.imax))
+        case[n] = t
+    case["wt"][:g.kstart+1] = 0
+    D, ctx, f, prm = gpu_setup(gd, case)
+    sub_dt = 2.0
+    D.Pres(ctx).exec(f, sub_dt)
+    P = O.Pres2(g, case["rhoref"], case["rhorefh"])
+    ref = {n: case[n].copy() for n in ("ut", "vt", "wt")}
+    p = g.field()
+    P.exec(p, case["u"], case["v"], case["w"], ref["ut"], ref["vt"], ref["wt"], sub_dt)
+    ptol = 50*TOL[dtype]
+    got_p = f["p"].cpu().numpy()
+    assert rel_l2(got_p[g.kstart-1:g.kend], p[g.kstart-1:g.kend]) <= ptol
+    for n in ref:
+        assert rel_l2(interior(g, f[n].cpu().numpy()), interior(g, ref[n])) <= ptol, n
+    # post-pressure divergence of u + dt*ut at the reference's level (both ~ machine epsilon * scale)
+    un = {c: case[c] + sub_dt*f[c + "t"].cpu().numpy() for c in "uvw"}
+    uo = {c: case[c] + sub_dt*ref[c + "t"] for c in "uvw"}
+    for d_ in (un, uo):
+        for c in "uvw":
+            O.boundary_cyclic(g, d_[c])
+    div_gpu = P.divergence(un["u"], un["v"], un["w"]); div_ref = P.divergence(uo["u"], uo["v"], uo["w"])
+    scale = np.abs(interior(g, case["u"])).max()/float(g.dx)
+    eps = np.finfo(dtype).eps
+    assert div_gpu <= max(10*div_ref, 200*eps*scale)
+    # check_divergence entry point
+    import torch
+    for c in "uvw":
+        f[c].copy_(torch.from_numpy(un[c]))
+    assert abs(D.Pres(ctx).check_divergence(f) - div_gpu) <= 1e-3*div_gpu + 1e-30
+
+
+def run_steps(dtype, shape, nsteps, anel, stretched, ns=1):
+    g, gd, case = make_pair(*shape, dtype, stretched=stretched, anelastic=anel, ns=ns)
+    D, ctx, f, _ = gpu_setup(gd, case, ns)
+    prm = D.make_params(ns=ns)
+    dyc = D.Dycore(ctx, prm)
+    oprm = ostep.default_params()
+    K = O.NumpyKernels(g)
+    dt = 2.0
+    for _ in range(nsteps):
+        dyc.step(f, dt)
+        ostep.dycore_step(g, K, case, oprm, dt)
+    ctx.sync()
+    return g, case, f
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape,anel,stretched", [((32, 32, 32), False, False), ((48, 24, 16), True, True)])
+def test_full_rk3_step(dtype, shape, anel, stretched):
+    """One full RK3 step (3 sub-steps) of the fused path == the reference call order on the oracle:
+    relative L2 on u, v, w, th within BASELINE.json's tolerance."""
+    g, case, f = run_steps(dtype, shape, 1, anel, stretched)
+    for n in ("u", "v", "w", "th"):
+        assert rel_l2(interior(g, f[n].cpu().numpy()), interior(g, case[n])) <= TOL[dtype], n
+    for n in ("ut", "vt", "wt", "tht"):
+        assert float(f[n].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_two_steps_two_scalars(dtype):
+    g, case, f = run_steps(dtype, (32, 16, 16), 2, True, True, ns=2)
+    for n in ("u", "v", "w", "th", "s1"):
+        assert rel_l2(interior(g, f[n].cpu().numpy()), interior(g, case[n])) <= 5*TOL[dtype], n
+
+
+def test_errors_are_reported():
+    import ctypes as C
+    g, gd, case = make_pair(16, 12, 8, np.float64)
+    D, ctx, f, prm = gpu_setup(gd, case)
+    rc = ctx.lib.mhh_boundary_cyclic(ctx.h, None, 2)
+    assert rc == -1 and b"NULL" in ctx.lib.mhh_last_error(ctx.h)
+    with pytest.raises(D.MhhError):
+        D.Advec(ctx, "4").exec(f)
