@@ -117,7 +117,8 @@ MHH_API int  mhh_ctx_create(const mhh_grid_desc* grid, int dtype, int device, mh
 MHH_API void mhh_ctx_destroy(mhh_ctx* ctx);
 MHH_API const char* mhh_last_error(const mhh_ctx* ctx);
 MHH_API int  mhh_sync(mhh_ctx* ctx);
-/* Use an externally owned CUDA stream (cudaStream_t as void*); NULL = context's own stream. */
+/* Run on an externally owned CUDA stream (cudaStream_t as void*); NULL = the CUDA legacy default
+ * stream.  A new context runs on its own non-blocking stream until this is called. */
 MHH_API int  mhh_set_stream(mhh_ctx* ctx, void* cuda_stream);
 /* Fields::rhoref/rhorefh (include/fields.h:162-188) and Thermo_dry's thref/threfh; HOST arrays (kcells).
  * thref/threfh may be NULL when swthermo == 0.  Also (re)builds the Pres_2 coefficient tables. */

@@ -1,6 +1,9 @@
 // mhhb200 -- C ABI implementation (see include/mhhb200.h).  Host-side orchestration only:
 // argument checks, launch configuration, the per-context tables.  No CPU compute path exists.
 #include <cmath>
+#include <cstdlib>
+#include <cstdint>
+#include <initializer_list>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -10,6 +13,7 @@
 #include "common.cuh"
 #include "stencil_kernels.cuh"
 #include "poisson_kernels.cuh"
+#include "tile_kernels.cuh"
 
 using namespace mhh;
 
@@ -25,6 +29,7 @@ struct mhh_ctx
     int num_sms = 148;
     // optional per-kernel timing: one event after every launch; a kernel's time is the gap to the
     // previous event on the (in-order) stream
+    bool force_plain = false;   // MHH_FORCE_PLAIN=1: use the point-wise kernels everywhere (A/B comparisons)
     bool prof = false;
     std::vector<std::pair<const char*, cudaEvent_t>> prof_events;
     std::vector<cudaEvent_t> prof_pool;
@@ -130,6 +135,7 @@ int create_impl(const mhh_grid_desc* d, int dtype, int device, mhh_ctx** out)
     if (!c) return MHH_E_NOMEM;
     *out = c;
     c->dtype = dtype; c->device = device; c->desc = *d;
+    { const char* e = getenv("MHH_FORCE_PLAIN"); c->force_plain = e && e[0] == '1'; }
     CUDA_TRY(c, cudaSetDevice(device));
     int nsm = 0;
     CUDA_TRY(c, cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
@@ -391,6 +397,49 @@ int check_mom(Ctx<TF>* c, const mhh_fields* f, bool need_evisc, bool surface)
     return MHH_OK;
 }
 
+template <typename TF>
+int vec_width(const GridDev<TF>& g, std::initializer_list<const void*> ptrs)
+{
+    int v = 2;
+    if (g.icells % 2 != 0 || (g.igc - TILE_H) % 2 != 0 || (g.ijcells % 2) != 0) v = 1;
+    for (const void* p : ptrs)
+        if (p && (reinterpret_cast<uintptr_t>(p) % (2 * sizeof(TF))) != 0) v = 1;
+    return v;
+}
+
+inline int pick_kchunk(int ntiles_xy, int kmax, int num_sms)
+{
+    // enough CTAs to fill the machine twice, but chunks of at least 16 levels (warm-up level amortised)
+    int nz = (2 * num_sms + ntiles_xy - 1) / ntiles_xy;
+    nz = std::max(1, std::min(nz, std::max(1, kmax / 16)));
+    return (kmax + nz - 1) / nz;
+}
+
+// fused advection + diffusion (+ buoyancy) of u, v, w with the z-marching tile kernel
+template <typename TF>
+int mom_tile_launch(Ctx<TF>* c, const MomArgs<TF>& a, bool surface, bool buoy)
+{
+    const GridDev<TF>& g = c->g;
+    const int ntx = (g.imax + TILE_X - 1) / TILE_X, nty = (g.jmax + TILE_Y - 1) / TILE_Y;
+    MomTileArgs<TF> t{a, pick_kchunk(ntx * nty, g.kmax, c->num_sms)};
+    dim3 grid(ntx, nty, (g.kmax + t.kchunk - 1) / t.kchunk);
+    const size_t smem = mom_tile_smem(sizeof(TF));
+    const int vec = vec_width<TF>(g, {a.u, a.v, a.w, a.evisc});
+#define MT(S, B, V) do { \
+        static bool attr_done = false; \
+        if (!attr_done) { CUDA_TRY(c, cudaFuncSetAttribute(mom_tile_kernel<TF, S, B, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done = true; } \
+        mom_tile_kernel<TF, S, B, V><<<grid, TILE_THREADS, smem, c->stream>>>(t, g); } while (0)
+#define MT2(S, B) do { if (vec == 2) MT(S, B, 2); else MT(S, B, 1); } while (0)
+    if (surface && buoy) MT2(true, true);
+    else if (surface) MT2(true, false);
+    else if (buoy) MT2(false, true);
+    else MT2(false, false);
+#undef MT2
+#undef MT
+    KCHECKN(c, "mom_tile_kernel");
+    return MHH_OK;
+}
+
 // tendencies: adv / diff / buoyancy in any combination (templates keep the unused parts out)
 template <typename TF>
 int tend_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, bool adv, bool diff, bool buoy)
@@ -405,7 +454,12 @@ int tend_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, bool adv, 
     const MomArgs<TF> a = mom_args<TF>(f);
     dim3 gr = c->grd_interior(), b = c->blk();
 #define LAUNCH_MOM(A, D, S, B) tend_uvw_kernel<TF, A, D, S, B><<<gr, b, 0, c->stream>>>(a, g)
-    if (adv && diff && surface && buoy) LAUNCH_MOM(true, true, true, true);
+    const bool tiles = adv && diff && g.igc >= TILE_H && g.jgc >= TILE_H && !c->force_plain;
+    if (tiles)
+    {
+        if ((rc = mom_tile_launch<TF>(c, a, surface, buoy)) != MHH_OK) return rc;
+    }
+    else if (adv && diff && surface && buoy) LAUNCH_MOM(true, true, true, true);
     else if (adv && diff && surface) LAUNCH_MOM(true, true, true, false);
     else if (adv && diff && buoy) LAUNCH_MOM(true, true, false, true);
     else if (adv && diff) LAUNCH_MOM(true, true, false, false);
@@ -414,7 +468,7 @@ int tend_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, bool adv, 
     else if (diff) LAUNCH_MOM(false, true, false, false);
     else { c->err = "tend_impl: nothing to do"; return MHH_E_INVALID; }
 #undef LAUNCH_MOM
-    KCHECKN(c, "tend_uvw_kernel");
+    if (!tiles) KCHECKN(c, "tend_uvw_kernel");
     for (int n = 0; n < f->ns; ++n)
     {
         const ScalArgs<TF> s = scal_args<TF>(c, f, prm, n);
@@ -680,7 +734,7 @@ int mhh_sync(mhh_ctx* ctx)
 int mhh_set_stream(mhh_ctx* ctx, void* s)
 {
     if (!ctx) return MHH_E_INVALID;
-    ctx->stream = s ? static_cast<cudaStream_t>(s) : ctx->own_stream;
+    ctx->stream = static_cast<cudaStream_t>(s);   // NULL selects the CUDA legacy default stream
     return MHH_OK;
 }
 

@@ -51,7 +51,7 @@ class Context:
 
     def use_torch_stream(self):
         s = torch.cuda.current_stream(self.device)
-        self.check(self.lib.mhh_set_stream(self.h, C.c_void_p(s.cuda_stream)))
+        self.check(self.lib.mhh_set_stream(self.h, C.c_void_p(s.cuda_stream or None)))
 
     def check(self, rc):
         if rc != 0:

@@ -205,11 +205,9 @@ def test_pres_2_exec(dtype, shape, anel):
     scale = np.abs(interior(g, case["u"])).max()/float(g.dx)
     eps = np.finfo(dtype).eps
     assert div_gpu <= max(10*div_ref, 200*eps*scale)
-    # check_divergence entry point
-    import torch
-    for c in "uvw":
-        f[c].copy_(torch.from_numpy(un[c]))
-    assert abs(D.Pres(ctx).check_divergence(f) - div_gpu) <= 1e-3*div_gpu + 1e-30
+    # check_divergence entry point, on the (divergent) input velocities
+    div_in = float(P.divergence(case["u"], case["v"], case["w"]))
+    assert abs(D.Pres(ctx).check_divergence(f) - div_in) <= 100*TOL[dtype]*div_in
 
 
 def run_steps(dtype, shape, nsteps, anel, stretched, ns=1):
