@@ -317,6 +317,24 @@ int ghost_impl(Ctx<TF>* c, TF* fld, int bcbot, const TF* bot, const TF* gradbot,
 }
 
 template <typename TF>
+int vec_width(const GridDev<TF>& g, std::initializer_list<const void*> ptrs)
+{
+    int v = 2;
+    if (g.icells % 2 != 0 || (g.igc - TILE_H) % 2 != 0 || (g.ijcells % 2) != 0) v = 1;
+    for (const void* p : ptrs)
+        if (p && (reinterpret_cast<uintptr_t>(p) % (2 * sizeof(TF))) != 0) v = 1;
+    return v;
+}
+
+inline int pick_kchunk(int ntiles_xy, int kmax, int num_sms)
+{
+    // enough CTAs to fill the machine twice, but chunks of at least 16 levels (warm-up level amortised)
+    int nz = (2 * num_sms + ntiles_xy - 1) / ntiles_xy;
+    nz = std::max(1, std::min(nz, std::max(1, kmax / 16)));
+    return (kmax + nz - 1) / nz;
+}
+
+template <typename TF>
 int evisc_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, const TF* n2)
 {
     NEED_BASE(c);
@@ -338,8 +356,30 @@ int evisc_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, const TF*
         NEED(c, f->dudz_mo, "dudz_mo"); NEED(c, f->dvdz_mo, "dvdz_mo"); NEED(c, f->dbdz_mo, "dbdz_mo"); NEED(c, f->z0m, "z0m");
         a.dudz = P<TF>(f->dudz_mo); a.dvdz = P<TF>(f->dvdz_mo); a.dbdz = P<TF>(f->dbdz_mo); a.z0m = P<TF>(f->z0m);
     }
-    evisc_kernel<TF><<<c->grd_interior(), c->blk(), 0, c->stream>>>(a, g, c->d_mlen0);
-    KCHECKN(c, "evisc_kernel");
+    if (!c->force_plain)
+    {
+        const int ntx = (g.imax + TILE_X - 1) / TILE_X, nty = (g.jmax + TILE_Y - 1) / TILE_Y;
+        EviscTileArgs<TF> t{a, c->d_mlen0, pick_kchunk(ntx * nty, g.kmax, c->num_sms)};
+        dim3 grid(ntx, nty, (g.kmax + t.kchunk - 1) / t.kchunk);
+        const size_t smem = evisc_tile_smem(sizeof(TF), t.kchunk);
+        int vec = 2;
+        if (g.icells % 2 != 0 || (g.igc - EH) % 2 != 0 || (g.ijcells % 2) != 0) vec = 1;
+        for (const void* p : {(const void*)a.u, (const void*)a.v, (const void*)a.w})
+            if (reinterpret_cast<uintptr_t>(p) % (2 * sizeof(TF)) != 0) vec = 1;
+#define ET(S, V) do { \
+            static size_t attr_smem = 0; \
+            if (attr_smem < smem) { CUDA_TRY(c, cudaFuncSetAttribute(evisc_tile_kernel<TF, S, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; } \
+            evisc_tile_kernel<TF, S, V><<<grid, TILE_THREADS, smem, c->stream>>>(t, g); } while (0)
+        if (a.surface) { if (vec == 2) ET(true, 2); else ET(true, 1); }
+        else { if (vec == 2) ET(false, 2); else ET(false, 1); }
+#undef ET
+        KCHECKN(c, "evisc_tile_kernel");
+    }
+    else
+    {
+        evisc_kernel<TF><<<c->grd_interior(), c->blk(), 0, c->stream>>>(a, g, c->d_mlen0);
+        KCHECKN(c, "evisc_kernel");
+    }
     if (!a.surface)
     {
         dim3 b(64, 4), gr((g.icells + 63) / 64, (g.jcells + 3) / 4);
@@ -397,24 +437,6 @@ int check_mom(Ctx<TF>* c, const mhh_fields* f, bool need_evisc, bool surface)
     return MHH_OK;
 }
 
-template <typename TF>
-int vec_width(const GridDev<TF>& g, std::initializer_list<const void*> ptrs)
-{
-    int v = 2;
-    if (g.icells % 2 != 0 || (g.igc - TILE_H) % 2 != 0 || (g.ijcells % 2) != 0) v = 1;
-    for (const void* p : ptrs)
-        if (p && (reinterpret_cast<uintptr_t>(p) % (2 * sizeof(TF))) != 0) v = 1;
-    return v;
-}
-
-inline int pick_kchunk(int ntiles_xy, int kmax, int num_sms)
-{
-    // enough CTAs to fill the machine twice, but chunks of at least 16 levels (warm-up level amortised)
-    int nz = (2 * num_sms + ntiles_xy - 1) / ntiles_xy;
-    nz = std::max(1, std::min(nz, std::max(1, kmax / 16)));
-    return (kmax + nz - 1) / nz;
-}
-
 // fused advection + diffusion (+ buoyancy) of u, v, w with the z-marching tile kernel
 template <typename TF>
 int mom_tile_launch(Ctx<TF>* c, const MomArgs<TF>& a, bool surface, bool buoy)
@@ -423,11 +445,11 @@ int mom_tile_launch(Ctx<TF>* c, const MomArgs<TF>& a, bool surface, bool buoy)
     const int ntx = (g.imax + TILE_X - 1) / TILE_X, nty = (g.jmax + TILE_Y - 1) / TILE_Y;
     MomTileArgs<TF> t{a, pick_kchunk(ntx * nty, g.kmax, c->num_sms)};
     dim3 grid(ntx, nty, (g.kmax + t.kchunk - 1) / t.kchunk);
-    const size_t smem = mom_tile_smem(sizeof(TF));
+    const size_t smem = mom_tile_smem(sizeof(TF), t.kchunk);
     const int vec = vec_width<TF>(g, {a.u, a.v, a.w, a.evisc});
 #define MT(S, B, V) do { \
-        static bool attr_done = false; \
-        if (!attr_done) { CUDA_TRY(c, cudaFuncSetAttribute(mom_tile_kernel<TF, S, B, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done = true; } \
+        static size_t attr_smem = 0; \
+        if (attr_smem < smem) { CUDA_TRY(c, cudaFuncSetAttribute(mom_tile_kernel<TF, S, B, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; } \
         mom_tile_kernel<TF, S, B, V><<<grid, TILE_THREADS, smem, c->stream>>>(t, g); } while (0)
 #define MT2(S, B) do { if (vec == 2) MT(S, B, 2); else MT(S, B, 1); } while (0)
     if (surface && buoy) MT2(true, true);
@@ -437,6 +459,26 @@ int mom_tile_launch(Ctx<TF>* c, const MomArgs<TF>& a, bool surface, bool buoy)
 #undef MT2
 #undef MT
     KCHECKN(c, "mom_tile_kernel");
+    return MHH_OK;
+}
+
+template <typename TF>
+int scal_tile_launch(Ctx<TF>* c, const ScalArgs<TF>& a, bool surface)
+{
+    const GridDev<TF>& g = c->g;
+    const int ntx = (g.imax + TILE_X - 1) / TILE_X, nty = (g.jmax + TILE_Y - 1) / TILE_Y;
+    ScalTileArgs<TF> t{a, pick_kchunk(ntx * nty, g.kmax, c->num_sms)};
+    dim3 grid(ntx, nty, (g.kmax + t.kchunk - 1) / t.kchunk);
+    const size_t smem = scal_tile_smem(sizeof(TF), t.kchunk);
+    const int vec = vec_width<TF>(g, {a.s, a.evisc});
+#define ST(S, V) do { \
+        static size_t attr_smem = 0; \
+        if (attr_smem < smem) { CUDA_TRY(c, cudaFuncSetAttribute(scal_tile_kernel<TF, S, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; } \
+        scal_tile_kernel<TF, S, V><<<grid, TILE_THREADS, smem, c->stream>>>(t, g); } while (0)
+    if (surface) { if (vec == 2) ST(true, 2); else ST(true, 1); }
+    else { if (vec == 2) ST(false, 2); else ST(false, 1); }
+#undef ST
+    KCHECKN(c, "scal_tile_kernel");
     return MHH_OK;
 }
 
@@ -472,6 +514,11 @@ int tend_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, bool adv, 
     for (int n = 0; n < f->ns; ++n)
     {
         const ScalArgs<TF> s = scal_args<TF>(c, f, prm, n);
+        if (tiles)
+        {
+            if ((rc = scal_tile_launch<TF>(c, s, surface)) != MHH_OK) return rc;
+            continue;
+        }
 #define LAUNCH_S(A, D, S) tend_s_kernel<TF, A, D, S><<<gr, b, 0, c->stream>>>(s, g)
         if (adv && diff && surface) LAUNCH_S(true, true, true);
         else if (adv && diff) LAUNCH_S(true, true, false);
