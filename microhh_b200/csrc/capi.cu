@@ -29,6 +29,7 @@ struct mhh_ctx
     int num_sms = 148;
     // optional per-kernel timing: one event after every launch; a kernel's time is the gap to the
     // previous event on the (in-order) stream
+    int tile_y = 8;             // MHH_TILE_Y=8|16: tile height of the z-marching kernels
     bool force_plain = false;   // MHH_FORCE_PLAIN=1: use the point-wise kernels everywhere (A/B comparisons)
     bool prof = false;
     std::vector<std::pair<const char*, cudaEvent_t>> prof_events;
@@ -70,6 +71,14 @@ FftPlan make_plan(int n, bool& ok)
         if (!found || p.nstages >= 15) { ok = false; break; }
     }
     if (n == 1) { p.nstages = 0; }
+    auto lg2 = [](int v) { int l = 0; while ((1 << l) < v) ++l; return ((1 << l) == v) ? l : -1; };
+    int s = 1;
+    for (int st = 0; st < p.nstages; ++st)
+    {
+        p.log2s[st] = lg2(s);
+        p.log2nb[st] = lg2(n / p.radix[st]);
+        s *= p.radix[st];
+    }
     return p;
 }
 
@@ -136,6 +145,7 @@ int create_impl(const mhh_grid_desc* d, int dtype, int device, mhh_ctx** out)
     *out = c;
     c->dtype = dtype; c->device = device; c->desc = *d;
     { const char* e = getenv("MHH_FORCE_PLAIN"); c->force_plain = e && e[0] == '1'; }
+    { const char* e = getenv("MHH_TILE_Y"); if (e && atoi(e) == 16) c->tile_y = 16; else if (e && atoi(e) == 8) c->tile_y = 8; }
     CUDA_TRY(c, cudaSetDevice(device));
     int nsm = 0;
     CUDA_TRY(c, cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
@@ -214,6 +224,7 @@ int create_impl(const mhh_grid_desc* d, int dtype, int device, mhh_ctx** out)
     c->rows_x = std::max(1, std::min(64, 2048 / std::max(L, 1)));
     c->smem_x = (size_t)2 * c->rows_x * (L + 1) * sizeof(cplx<TF>);
     int mc = std::max(4, std::min(16, 2048 / g.jtot));
+    while (mc & (mc - 1)) mc &= (mc - 1);      // power of two (the kernel uses shifts)
     if (sizeof(TF) == 4) mc *= 2;
     while (mc > 1 && (size_t)2 * mc * (g.jtot + 1) * sizeof(cplx<TF>) > 200 * 1024) mc /= 2;
     c->mc_y = mc;
@@ -358,21 +369,24 @@ int evisc_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, const TF*
     }
     if (!c->force_plain)
     {
-        const int ntx = (g.imax + TILE_X - 1) / TILE_X, nty = (g.jmax + TILE_Y - 1) / TILE_Y;
+        const int ty = c->tile_y;
+        const int ntx = (g.imax + TILE_X - 1) / TILE_X, nty = (g.jmax + ty - 1) / ty;
         EviscTileArgs<TF> t{a, c->d_mlen0, pick_kchunk(ntx * nty, g.kmax, c->num_sms)};
         dim3 grid(ntx, nty, (g.kmax + t.kchunk - 1) / t.kchunk);
-        const size_t smem = evisc_tile_smem(sizeof(TF), t.kchunk);
+        const size_t smem = evisc_tile_smem(sizeof(TF), t.kchunk, ty);
         int vec = 2;
         if (g.icells % 2 != 0 || (g.igc - EH) % 2 != 0 || (g.ijcells % 2) != 0) vec = 1;
         for (const void* p : {(const void*)a.u, (const void*)a.v, (const void*)a.w})
             if (reinterpret_cast<uintptr_t>(p) % (2 * sizeof(TF)) != 0) vec = 1;
-#define ET(S, V) do { \
+#define ET3(S, V, Y) do { \
             static size_t attr_smem = 0; \
-            if (attr_smem < smem) { CUDA_TRY(c, cudaFuncSetAttribute(evisc_tile_kernel<TF, S, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; } \
-            evisc_tile_kernel<TF, S, V><<<grid, TILE_THREADS, smem, c->stream>>>(t, g); } while (0)
+            if (attr_smem < smem) { CUDA_TRY(c, cudaFuncSetAttribute(evisc_tile_kernel<TF, S, V, Y>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; } \
+            evisc_tile_kernel<TF, S, V, Y><<<grid, TILE_X * Y, smem, c->stream>>>(t, g); } while (0)
+#define ET(S, V) do { if (ty == 16) ET3(S, V, 16); else ET3(S, V, 8); } while (0)
         if (a.surface) { if (vec == 2) ET(true, 2); else ET(true, 1); }
         else { if (vec == 2) ET(false, 2); else ET(false, 1); }
 #undef ET
+#undef ET3
         KCHECKN(c, "evisc_tile_kernel");
     }
     else
@@ -442,16 +456,18 @@ template <typename TF>
 int mom_tile_launch(Ctx<TF>* c, const MomArgs<TF>& a, bool surface, bool buoy)
 {
     const GridDev<TF>& g = c->g;
-    const int ntx = (g.imax + TILE_X - 1) / TILE_X, nty = (g.jmax + TILE_Y - 1) / TILE_Y;
+    const int ty = c->tile_y;
+    const int ntx = (g.imax + TILE_X - 1) / TILE_X, nty = (g.jmax + ty - 1) / ty;
     MomTileArgs<TF> t{a, pick_kchunk(ntx * nty, g.kmax, c->num_sms)};
     dim3 grid(ntx, nty, (g.kmax + t.kchunk - 1) / t.kchunk);
-    const size_t smem = mom_tile_smem(sizeof(TF), t.kchunk);
+    const size_t smem = mom_tile_smem(sizeof(TF), t.kchunk, ty);
     const int vec = vec_width<TF>(g, {a.u, a.v, a.w, a.evisc});
-#define MT(S, B, V) do { \
+#define MT(S, B, V, Y) do { \
         static size_t attr_smem = 0; \
-        if (attr_smem < smem) { CUDA_TRY(c, cudaFuncSetAttribute(mom_tile_kernel<TF, S, B, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; } \
-        mom_tile_kernel<TF, S, B, V><<<grid, TILE_THREADS, smem, c->stream>>>(t, g); } while (0)
-#define MT2(S, B) do { if (vec == 2) MT(S, B, 2); else MT(S, B, 1); } while (0)
+        if (attr_smem < smem) { CUDA_TRY(c, cudaFuncSetAttribute(mom_tile_kernel<TF, S, B, V, Y>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; } \
+        mom_tile_kernel<TF, S, B, V, Y><<<grid, TILE_X * Y, smem, c->stream>>>(t, g); } while (0)
+#define MT2(S, B) do { if (vec == 2) { if (ty == 16) MT(S, B, 2, 16); else MT(S, B, 2, 8); } \
+                       else { if (ty == 16) MT(S, B, 1, 16); else MT(S, B, 1, 8); } } while (0)
     if (surface && buoy) MT2(true, true);
     else if (surface) MT2(true, false);
     else if (buoy) MT2(false, true);
@@ -466,18 +482,21 @@ template <typename TF>
 int scal_tile_launch(Ctx<TF>* c, const ScalArgs<TF>& a, bool surface)
 {
     const GridDev<TF>& g = c->g;
-    const int ntx = (g.imax + TILE_X - 1) / TILE_X, nty = (g.jmax + TILE_Y - 1) / TILE_Y;
+    const int ty = c->tile_y;
+    const int ntx = (g.imax + TILE_X - 1) / TILE_X, nty = (g.jmax + ty - 1) / ty;
     ScalTileArgs<TF> t{a, pick_kchunk(ntx * nty, g.kmax, c->num_sms)};
     dim3 grid(ntx, nty, (g.kmax + t.kchunk - 1) / t.kchunk);
-    const size_t smem = scal_tile_smem(sizeof(TF), t.kchunk);
+    const size_t smem = scal_tile_smem(sizeof(TF), t.kchunk, ty);
     const int vec = vec_width<TF>(g, {a.s, a.evisc});
-#define ST(S, V) do { \
+#define ST3(S, V, Y) do { \
         static size_t attr_smem = 0; \
-        if (attr_smem < smem) { CUDA_TRY(c, cudaFuncSetAttribute(scal_tile_kernel<TF, S, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; } \
-        scal_tile_kernel<TF, S, V><<<grid, TILE_THREADS, smem, c->stream>>>(t, g); } while (0)
+        if (attr_smem < smem) { CUDA_TRY(c, cudaFuncSetAttribute(scal_tile_kernel<TF, S, V, Y>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; } \
+        scal_tile_kernel<TF, S, V, Y><<<grid, TILE_X * Y, smem, c->stream>>>(t, g); } while (0)
+#define ST(S, V) do { if (ty == 16) ST3(S, V, 16); else ST3(S, V, 8); } while (0)
     if (surface) { if (vec == 2) ST(true, 2); else ST(true, 1); }
     else { if (vec == 2) ST(false, 2); else ST(false, 1); }
 #undef ST
+#undef ST3
     KCHECKN(c, "scal_tile_kernel");
     return MHH_OK;
 }

@@ -28,7 +28,16 @@ struct FftPlan
     int n;            // complex transform length
     int nstages;
     int radix[16];
+    int log2s[16];    // log2 of the stride entering stage st, or -1 when it is not a power of two
+    int log2nb[16];   // log2 of the butterflies per sequence (n / radix), or -1
 };
+
+// integer division / remainder by a value whose log2 is known (or -1 -> generic)
+__device__ __forceinline__ void divmod(const int x, const int d, const int lg, int& quo, int& rem)
+{
+    if (lg >= 0) { quo = x >> lg; rem = x & (d - 1); }
+    else { quo = x / d; rem = x - quo * d; }
+}
 
 // One radix-R Stockham (decimation in frequency, autosort) butterfly.
 //   x: input (length n), y: output.  s = stride (product of previous radices), m = n_cur / R.
@@ -105,13 +114,19 @@ __device__ __forceinline__ void butterfly(const cplx<TF>* __restrict__ x, cplx<T
         b[2] = cadd(m2, n2); b[3] = csub(m2, n2);
     }
 
-    // twiddle: w_{n_cur}^{p*r} = tw[(p*r*s) mod n]   (n = n_cur*s*...: s*m*R = n)
-    y[q + s * (R * p)] = b[0];
-#pragma unroll
-    for (int r = 1; r < R; ++r)
+    // twiddle: w_{n_cur}^{p*r} = tw[p*r*s]   (p < m = n_cur/R and n_cur*s = n, so p*r*s < n)
+    cplx<TF>* yo = y + q + s * (R * p);
+    yo[0] = b[0];
+    if (p == 0)
     {
-        const int t = (p * r * s) % n;
-        y[q + s * (R * p + r)] = cmul(b[r], tw[t]);
+#pragma unroll
+        for (int r = 1; r < R; ++r) yo[s * r] = b[r];
+    }
+    else
+    {
+        const int ps = p * s;
+#pragma unroll
+        for (int r = 1; r < R; ++r) yo[s * r] = cmul(b[r], tw[ps * r]);
     }
 }
 
@@ -134,12 +149,12 @@ __device__ cplx<TF>* smem_fft(cplx<TF>* buf0, cplx<TF>* buf1, const cplx<TF>* __
         const int R = plan.radix[st];
         const int m = ncur / R;
         const int nb = n / R;              // butterflies per sequence
+        const int lgs = plan.log2s[st], lgnb = plan.log2nb[st];
         for (int t = tid; t < nseq * nb; t += nth)
         {
-            const int sq = t / nb;
-            const int b = t - sq * nb;
-            const int p = b / s;
-            const int q = b - p * s;
+            int sq, b, p, q;
+            divmod(t, nb, lgnb, sq, b);
+            divmod(b, s, lgs, p, q);
             const cplx<TF>* xs = x + sq * ld;
             cplx<TF>* ys = y + sq * ld;
             switch (R)
@@ -185,54 +200,67 @@ __global__ void fft_x_forward_kernel(TF* __restrict__ spec, const RhsSrc<TF> src
     const int ld = L + 1;               // padded sequence stride
     cplx<TF>* buf0 = reinterpret_cast<cplx<TF>*>(smem_raw);
     cplx<TF>* buf1 = buf0 + rows_per_cta * ld;
-    const int tid = threadIdx.x, nth = blockDim.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const long long jj = g.icells, kk = g.ijcells;
 
     for (long long row0 = (long long)blockIdx.x * rows_per_cta; row0 < nrows; row0 += (long long)gridDim.x * rows_per_cta)
     {
         const int nr = (int)min((long long)rows_per_cta, nrows - row0);
-        // load: z[n] = x[2n] + i x[2n+1]
-        for (int t = tid; t < nr * N; t += nth)
+        // load: z[n] = x[2n] + i x[2n+1]; one warp per row so that the row decode is done once
+        const int nchN = (N + 31) >> 5;
+        for (int wi = warp; wi < nr * nchN; wi += nwarps)
         {
-            const int r = t / N;
-            const int i = t - r * N;
+            const int r = wi / nchN;
+            const int i0 = (wi - r * nchN) << 5;
             const long long row = row0 + r;
-            TF val;
+            TF* dst = reinterpret_cast<TF*>(buf0 + r * ld);
             if (RHS_FUSED)
             {
-                const int k = (int)(row / g.jtot) + g.kstart;
-                const int j = (int)(row % g.jtot) + g.jstart;
-                const long long ijk = (i + g.istart) + j * jj + k * kk;
-                const long long ie = (i + 1 == g.itot) ? ijk + 1 - g.itot : ijk + 1;
-                const long long jn = (j + 1 == g.jend) ? ijk + (1 - g.jtot) * jj : ijk + jj;
+                const int kq = (int)(row / g.jtot);
+                const int k = kq + g.kstart;
+                const int j = (int)(row - (long long)kq * g.jtot) + g.jstart;
+                const long long base = g.istart + j * jj + k * kk;
+                const long long jn_off = (j + 1 == g.jend) ? (1 - g.jtot) * jj : jj;
                 const TF dti = src.dti;
-                val = g.rhoref[k] * ((src.ut[ie] + src.u[ie] * dti) - (src.ut[ijk] + src.u[ijk] * dti)) * g.dxi
-                    + g.rhoref[k] * ((src.vt[jn] + src.v[jn] * dti) - (src.vt[ijk] + src.v[ijk] * dti)) * g.dyi
-                    + (g.rhorefh[k + 1] * (src.wt[ijk + kk] + src.w[ijk + kk] * dti)
-                     - g.rhorefh[k    ] * (src.wt[ijk     ] + src.w[ijk     ] * dti)) * g.dzi[k];
+                const TF rho = g.rhoref[k], rhoh0 = g.rhorefh[k], rhoh1 = g.rhorefh[k + 1], dzi = g.dzi[k];
+                const int i = i0 + lane;
+                if (i < N)
+                {
+                    const long long ijk = base + i;
+                    const long long ie = (i + 1 == N) ? ijk + 1 - N : ijk + 1;
+                    const long long jn = ijk + jn_off;
+                    dst[i] = rho * ((src.ut[ie] + src.u[ie] * dti) - (src.ut[ijk] + src.u[ijk] * dti)) * g.dxi
+                           + rho * ((src.vt[jn] + src.v[jn] * dti) - (src.vt[ijk] + src.v[ijk] * dti)) * g.dyi
+                           + (rhoh1 * (src.wt[ijk + kk] + src.w[ijk + kk] * dti)
+                            - rhoh0 * (src.wt[ijk     ] + src.w[ijk     ] * dti)) * dzi;
+                }
             }
             else
-                val = spec[row * (2 * nm) + i];
-            TF* dst = reinterpret_cast<TF*>(buf0 + r * ld);
-            dst[i] = val;
+            {
+                const TF* in = spec + row * (2 * nm);
+                const int i = i0 + lane;
+                if (i < N) dst[i] = in[i];
+            }
         }
         __syncthreads();
         cplx<TF>* Z = smem_fft<TF>(buf0, buf1, tw_half, plan, nr, ld);
         // post-process: X[m] = E[m] + W_N^m O[m]
-        for (int t = tid; t < nr * nm; t += nth)
+        const int nchM = (nm + 31) >> 5;
+        for (int wi = warp; wi < nr * nchM; wi += nwarps)
         {
-            const int r = t / nm;
-            const int m = t - r * nm;
+            const int r = wi / nchM;
+            const int m = ((wi - r * nchM) << 5) + lane;
             const cplx<TF>* z = Z + r * ld;
-            const cplx<TF> zm = z[m == L ? 0 : m];
-            const cplx<TF> zc = cconj(z[(L - m) % L]);
-            const cplx<TF> e = {TF(0.5) * (zm.x + zc.x), TF(0.5) * (zm.y + zc.y)};
-            const cplx<TF> d = {TF(0.5) * (zm.x - zc.x), TF(0.5) * (zm.y - zc.y)};
-            const cplx<TF> o = cmul_mi(d);                  // (zm - zc)/(2i)
-            const cplx<TF> wN = tw_full[m];                  // exp(-2 pi i m / N)
-            const cplx<TF> X = cadd(e, cmul(wN, o));
             cplx<TF>* out = reinterpret_cast<cplx<TF>*>(spec + (row0 + r) * (2 * nm));
-            out[m] = X;
+            if (m < nm)
+            {
+                const cplx<TF> zm = z[m == L ? 0 : m];
+                const cplx<TF> zc = cconj(z[m == 0 ? 0 : L - m]);
+                const cplx<TF> e = {TF(0.5) * (zm.x + zc.x), TF(0.5) * (zm.y + zc.y)};
+                const cplx<TF> d = {TF(0.5) * (zm.x - zc.x), TF(0.5) * (zm.y - zc.y)};
+                const cplx<TF> o = cmul_mi(d);                  // (zm - zc)/(2i)
+                out[m] = cadd(e, cmul(tw_full[m], o));           // tw_full[m] = exp(-2 pi i m / N)
+            }
         }
         __syncthreads();
     }
@@ -256,7 +284,7 @@ __global__ void fft_x_backward_kernel(const TF* __restrict__ spec, TF* __restric
     const int ld = L + 1;
     cplx<TF>* buf0 = reinterpret_cast<cplx<TF>*>(smem_raw);
     cplx<TF>* buf1 = buf0 + rows_per_cta * ld;
-    const int tid = threadIdx.x, nth = blockDim.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const long long jj = g.icells, kk = g.ijcells;
 
     for (long long row0 = (long long)blockIdx.x * rows_per_cta; row0 < nrows; row0 += (long long)gridDim.x * rows_per_cta)
@@ -264,48 +292,52 @@ __global__ void fft_x_backward_kernel(const TF* __restrict__ spec, TF* __restric
         const int nr = (int)min((long long)rows_per_cta, nrows - row0);
         // pre-process: Z'[m] = (X[m] + conj X[L-m]) + i e^{+2 pi i m/N} (X[m] - conj X[L-m]); store conj(Z') so the
         // forward transform yields conj(inverse).
-        for (int t = tid; t < nr * L; t += nth)
+        const int nchL = (L + 31) >> 5;
+        for (int wi = warp; wi < nr * nchL; wi += nwarps)
         {
-            const int r = t / L;
-            const int m = t - r * L;
+            const int r = wi / nchL;
+            const int m = ((wi - r * nchL) << 5) + lane;
             const cplx<TF>* X = reinterpret_cast<const cplx<TF>*>(spec + (row0 + r) * (2 * nm));
-            const cplx<TF> xm = X[m];
-            const cplx<TF> xc = cconj(X[L - m]);
-            const cplx<TF> e = cadd(xm, xc);
-            const cplx<TF> d = csub(xm, xc);
-            const cplx<TF> wc = cconj(tw_full[m]);           // exp(+2 pi i m / N)
-            const cplx<TF> wd = cmul(wc, d);
-            const cplx<TF> z = {e.x - wd.y, e.y + wd.x};     // e + i*wd
-            buf0[r * ld + m] = cconj(z);
+            if (m < L)
+            {
+                const cplx<TF> xm = X[m];
+                const cplx<TF> xc = cconj(X[L - m]);
+                const cplx<TF> e = cadd(xm, xc);
+                const cplx<TF> d = csub(xm, xc);
+                const cplx<TF> wd = cmul(cconj(tw_full[m]), d);  // exp(+2 pi i m / N) * d
+                buf0[r * ld + m] = {e.x - wd.y, -(e.y + wd.x)};   // conj(e + i*wd)
+            }
         }
         __syncthreads();
         cplx<TF>* Z = smem_fft<TF>(buf0, buf1, tw_half, plan, nr, ld);
         // store: x[2n] = Re(conj Z[n]) = Z[n].x, x[2n+1] = Im(conj Z[n]) = -Z[n].y
         const int wtot = g.itot + 2 * g.igc;
-        for (int t = tid; t < nr * wtot; t += nth)
+        const int nchW = (wtot + 31) >> 5;
+        for (int wi = warp; wi < nr * nchW; wi += nwarps)
         {
-            const int r = t / wtot;
-            const int ic = t - r * wtot;          // cell index in the ghosted row
-            int i = ic - g.igc;                   // interior index, wrapped
-            if (i < 0) i += g.itot; else if (i >= g.itot) i -= g.itot;
-            const cplx<TF> zz = Z[r * ld + (i >> 1)];
-            const TF val = ((i & 1) ? -zz.y : zz.x) * norm;
+            const int r = wi / nchW;
+            const int ic = ((wi - r * nchW) << 5) + lane;
             const long long row = row0 + r;
             const int kq = (int)(row / g.jtot);
-            const int jq = (int)(row % g.jtot);
-            const int k = kq + g.kstart;
-            const int j = jq + g.jstart;
-            const long long base = ic + j * jj + k * kk;
-            p[base] = val;
-            if (kq == 0) p[base - kk] = val;
-            if (fill_y_ghosts)
+            const int jq = (int)(row - (long long)kq * g.jtot);
+            const long long rowbase = (jq + g.jstart) * jj + (kq + g.kstart) * kk;
+            const bool ylo = fill_y_ghosts && jq < g.jgc, yhi = fill_y_ghosts && jq >= g.jtot - g.jgc;
+            const cplx<TF>* z = Z + r * ld;
+            if (ic < wtot)
             {
-                if (jq < g.jgc)
+                int i = ic - g.igc;                   // interior index, wrapped
+                if (i < 0) i += g.itot; else if (i >= g.itot) i -= g.itot;
+                const cplx<TF> zz = z[i >> 1];
+                const TF val = ((i & 1) ? -zz.y : zz.x) * norm;
+                const long long base = ic + rowbase;
+                p[base] = val;
+                if (kq == 0) p[base - kk] = val;
+                if (ylo)
                 {
                     p[base + g.jtot * jj] = val;
                     if (kq == 0) p[base + g.jtot * jj - kk] = val;
                 }
-                if (jq >= g.jtot - g.jgc)
+                if (yhi)
                 {
                     p[base - g.jtot * jj] = val;
                     if (kq == 0) p[base - g.jtot * jj - kk] = val;
@@ -330,6 +362,7 @@ __global__ void fft_y_kernel(TF* __restrict__ spec, const int nm, const int jtot
     cplx<TF>* buf1 = buf0 + MC * ld;
     const int tid = threadIdx.x, nth = blockDim.x;
     const int npanel_m = (nm + MC - 1) / MC;
+    const int lgMC = 31 - __clz(MC);          // MC is a power of two
     const long long npanels = (long long)npanel_m * ktot;
     cplx<TF>* S = reinterpret_cast<cplx<TF>*>(spec);
 
@@ -341,8 +374,8 @@ __global__ void fft_y_kernel(TF* __restrict__ spec, const int nm, const int jtot
         cplx<TF>* base = S + (long long)k * jtot * nm + m0;
         for (int t = tid; t < jtot * MC; t += nth)
         {
-            const int j = t / MC;
-            const int c = t - j * MC;
+            const int j = t >> lgMC;
+            const int c = t & (MC - 1);
             if (c < mc)
             {
                 cplx<TF> v = base[(long long)j * nm + c];
@@ -354,8 +387,8 @@ __global__ void fft_y_kernel(TF* __restrict__ spec, const int nm, const int jtot
         cplx<TF>* Z = smem_fft<TF>(buf0, buf1, tw, plan, mc, ld);
         for (int t = tid; t < jtot * MC; t += nth)
         {
-            const int j = t / MC;
-            const int c = t - j * MC;
+            const int j = t >> lgMC;
+            const int c = t & (MC - 1);
             if (c < mc)
             {
                 cplx<TF> v = Z[c * ld + j];

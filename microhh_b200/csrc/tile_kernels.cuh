@@ -15,13 +15,12 @@
 namespace mhh {
 
 constexpr int TILE_X = 32;
-constexpr int TILE_Y = 16;
-constexpr int TILE_H = 3;                         // halo of the staged planes
+constexpr int TILE_H = 3;                         // halo of the staged planes (advection stencils)
 constexpr int TILE_PX = TILE_X + 2 * TILE_H;      // 38
-constexpr int TILE_PY = TILE_Y + 2 * TILE_H;      // 22
-constexpr int TILE_PLANE = TILE_PX * TILE_PY;     // 836 elements
-constexpr int TILE_THREADS = TILE_X * TILE_Y;     // 512
 constexpr int RING = 3;
+// TY (tile height = warps per CTA) is a template parameter: 16 -> one 512-thread CTA per SM,
+// 8 -> two 256-thread CTAs per SM (fp64 kernels use ~128 registers per thread).
+constexpr int tile_plane(int ty, int h = TILE_H) { return (TILE_X + 2 * h) * (ty + 2 * h); }
 
 template <int BYTES>
 __device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc)
@@ -37,31 +36,43 @@ __device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-// Stage one horizontal plane (tile + halo) of `fld` at level `lev` into smem.
-// VEC = elements per cp.async (alignment guaranteed by the caller's dispatch).
-template <typename TF, int VEC, int H = TILE_H>
-__device__ __forceinline__ void stage_plane(TF* __restrict__ dst, const TF* __restrict__ fld, const int lev,
-        const int gi0, const int gj0, const GridDev<TF>& g)
+// Stages horizontal planes (tile + halo H) into shared memory with cp.async.  The per-thread
+// source/destination offsets are computed once; staging a plane is then NIT predicated copies.
+// VEC = elements per cp.async; the host dispatch guarantees that a vector never straddles the
+// end of a row (icells and the tile origin are multiples of VEC).
+template <typename TF, int VEC, int TY, int H>
+struct Stager
 {
-    if (lev < 0 || lev >= g.kcells) return;       // never consumed
-    const TF* src = fld + (long long)lev * g.ijcells;
-    constexpr int PX = TILE_X + 2 * H, PY = TILE_Y + 2 * H;
-    constexpr int NV = PX / VEC;                  // vectors per row
-    for (int t = threadIdx.x; t < NV * PY; t += TILE_THREADS)
+    static constexpr int PX = TILE_X + 2 * H, PY = TY + 2 * H;
+    static constexpr int NV = PX / VEC;
+    static constexpr int THREADS = TILE_X * TY;
+    static constexpr int NIT = (NV * PY + THREADS - 1) / THREADS;
+    int soff[NIT];
+    int goff[NIT];      // offset inside a horizontal plane, or -1
+
+    __device__ __forceinline__ void init(const int gi0, const int gj0, const GridDev<TF>& g)
     {
-        const int sy = t / NV;
-        const int sx = (t - sy * NV) * VEC;
-        const int gj = gj0 + sy;
-        const int gi = gi0 + sx;
-        if (gj < g.jcells && gi + VEC <= g.icells)
-            cp_async<VEC * (int)sizeof(TF)>(dst + sy * PX + sx, src + (long long)gj * g.icells + gi);
-        else if (gj < g.jcells)
+#pragma unroll
+        for (int it = 0; it < NIT; ++it)
         {
-            for (int v = 0; v < VEC; ++v)
-                if (gi + v < g.icells) dst[sy * PX + sx + v] = src[(long long)gj * g.icells + gi + v];
+            const int t = threadIdx.x + it * THREADS;
+            const int sy = t / NV;
+            const int sx = (t - sy * NV) * VEC;
+            const int gj = gj0 + sy, gi = gi0 + sx;
+            const bool ok = (t < NV * PY) && (gj < g.jcells) && (gi + VEC <= g.icells);
+            soff[it] = sy * PX + sx;
+            goff[it] = ok ? gj * g.icells + gi : -1;
         }
     }
-}
+    // src_plane = field pointer at the level to stage
+    __device__ __forceinline__ void stage(TF* __restrict__ dst, const TF* __restrict__ src_plane) const
+    {
+#pragma unroll
+        for (int it = 0; it < NIT; ++it)
+            if (goff[it] >= 0)
+                cp_async<VEC * (int)sizeof(TF)>(dst + soff[it], src_plane + goff[it]);
+    }
+};
 
 template <typename TF>
 __device__ __forceinline__ TF vflux_col(const int order, const TF vel, const TF c0, const TF c1, const TF c2,
@@ -81,14 +92,13 @@ struct MomTileArgs
     int kchunk;        // levels per CTA in z
 };
 
-template <typename TF, bool SURFACE, bool BUOY, int VEC>
-__global__ void __launch_bounds__(TILE_THREADS, 1) mom_tile_kernel(const MomTileArgs<TF> args, const GridDev<TF> g)
+template <typename TF, bool SURFACE, bool BUOY, int VEC, int TY>
+__global__ void __launch_bounds__(TILE_X * TY, 512 / (TILE_X * TY)) mom_tile_kernel(const MomTileArgs<TF> args, const GridDev<TF> g)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TF* sm = reinterpret_cast<TF*>(smem_raw);
+    constexpr int TILE_Y = TY, TILE_THREADS = TILE_X * TY, TILE_PLANE = tile_plane(TY);
     // layout: [field 0..3][ring][plane]   fields: 0 u, 1 v, 2 w, 3 evisc
-    auto plane = [&](int fld, int lev) -> TF* { return sm + ((fld * RING) + ((lev + RING) % RING)) * TILE_PLANE; };
-
     const MomArgs<TF>& a = args.m;
     const int tx = threadIdx.x % TILE_X, ty = threadIdx.x / TILE_X;
     const int i = g.istart + blockIdx.x * TILE_X + tx;
@@ -121,13 +131,20 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) mom_tile_kernel(const MomTile
         p_thh[t] = BUOY ? g.threfh[lev] : TF(1);
     }
 
-    // prologue: planes k0 = kc0-1 and k0+1
+    // prologue: planes k0 = kc0-1 and k0+1 into ring slots 0 and 1
+    Stager<TF, VEC, TY, TILE_H> stg;
+    stg.init(gi0, gj0, g);
+    const TF* pl_src[4];       // per field: pointer to the plane that is staged next
 #pragma unroll
-    for (int f = 0; f < 4; ++f) stage_plane<TF, VEC>(plane(f, k0), flds[f], k0, gi0, gj0, g);
+    for (int f = 0; f < 4; ++f)
+    {
+        pl_src[f] = flds[f] + (long long)k0 * kk;
+        stg.stage(sm + (f * RING + 0) * TILE_PLANE, pl_src[f]);
+        stg.stage(sm + (f * RING + 1) * TILE_PLANE, pl_src[f] + kk);
+        pl_src[f] += 2 * kk;
+    }
     cp_async_commit();
-#pragma unroll
-    for (int f = 0; f < 4; ++f) stage_plane<TF, VEC>(plane(f, k0 + 1), flds[f], k0 + 1, gi0, gj0, g);
-    cp_async_commit();
+    int s0 = 0;                // ring slot of plane k
 
     auto colload = [&](const TF* __restrict__ fld, int lev) -> TF {
         return (lev >= 0 && lev < g.kcells) ? fld[ij + (long long)lev * kk] : TF(0);
@@ -152,8 +169,13 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) mom_tile_kernel(const MomTile
         cp_async_wait<0>();          // planes k and k+1 have landed
         __syncthreads();             // ... for every thread; and everyone is done with plane k-1
         // stream in plane k+2 (into the slot of plane k-1) while level k is being computed
+        const int s1 = (s0 == RING - 1) ? 0 : s0 + 1;
+        const int s2 = (s1 == RING - 1) ? 0 : s1 + 1;
+        if (k + 2 < g.kcells)
+        {
 #pragma unroll
-        for (int f = 0; f < 4; ++f) stage_plane<TF, VEC>(plane(f, k + 2), flds[f], k + 2, gi0, gj0, g);
+            for (int f = 0; f < 4; ++f) { stg.stage(sm + (f * RING + s2) * TILE_PLANE, pl_src[f]); pl_src[f] += kk; }
+        }
         cp_async_commit();
         // global loads whose latency overlaps the arithmetic below: leading-edge column values for the
         // next step and the tendencies that are read-modify-written at the end of this step
@@ -171,13 +193,13 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) mom_tile_kernel(const MomTile
         if (st_uv) { ut_old = a.ut[o_k]; vt_old = a.vt[o_k]; }
         if (st_w) wt_old = a.wt[o_f];
 
-        const TF* __restrict__ U0 = plane(0, k) + sidx;
-        const TF* __restrict__ U1 = plane(0, k + 1) + sidx;
-        const TF* __restrict__ V0 = plane(1, k) + sidx;
-        const TF* __restrict__ V1 = plane(1, k + 1) + sidx;
-        const TF* __restrict__ W1 = plane(2, k + 1) + sidx;
-        const TF* __restrict__ E0 = plane(3, k) + sidx;
-        const TF* __restrict__ E1 = plane(3, k + 1) + sidx;
+        const TF* __restrict__ U0 = sm + (0 * RING + s0) * TILE_PLANE + sidx;
+        const TF* __restrict__ U1 = sm + (0 * RING + s1) * TILE_PLANE + sidx;
+        const TF* __restrict__ V0 = sm + (1 * RING + s0) * TILE_PLANE + sidx;
+        const TF* __restrict__ V1 = sm + (1 * RING + s1) * TILE_PLANE + sidx;
+        const TF* __restrict__ W1 = sm + (2 * RING + s1) * TILE_PLANE + sidx;
+        const TF* __restrict__ E0 = sm + (3 * RING + s0) * TILE_PLANE + sidx;
+        const TF* __restrict__ E1 = sm + (3 * RING + s1) * TILE_PLANE + sidx;
         constexpr int P = TILE_PX;
         const int pl = k - k0;                                  // profile slot of level k
         const TF rho_k = p_rho[pl], rhoh_f = p_rhoh[pl + 1];
@@ -279,11 +301,12 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) mom_tile_kernel(const MomTile
         for (int n = 0; n < 5; ++n) { uc[n] = uc[n + 1]; vc[n] = vc[n + 1]; wc[n] = wc[n + 1]; }
         uc[5] = u_new; vc[5] = v_new; wc[5] = w_new;
         thk = th1;
+        s0 = s1;
     }
     cp_async_wait<0>();
 }
 
-inline size_t mom_tile_smem(size_t elem, int kchunk) { return ((size_t)4 * RING * TILE_PLANE + (size_t)5 * (kchunk + 3)) * elem; }
+inline size_t mom_tile_smem(size_t elem, int kchunk, int ty) { return ((size_t)4 * RING * tile_plane(ty) + (size_t)5 * (kchunk + 3)) * elem; }
 
 
 // ------------------------------------------------------------------------------------------
@@ -298,13 +321,13 @@ struct ScalTileArgs
     int kchunk;
 };
 
-template <typename TF, bool SURFACE, int VEC>
-__global__ void __launch_bounds__(TILE_THREADS, 1) scal_tile_kernel(const ScalTileArgs<TF> args, const GridDev<TF> g)
+template <typename TF, bool SURFACE, int VEC, int TY>
+__global__ void __launch_bounds__(TILE_X * TY, 512 / (TILE_X * TY)) scal_tile_kernel(const ScalTileArgs<TF> args, const GridDev<TF> g)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TF* sm = reinterpret_cast<TF*>(smem_raw);
+    constexpr int TILE_Y = TY, TILE_THREADS = TILE_X * TY, TILE_PLANE = tile_plane(TY);
     constexpr int R2 = 2;
-    auto plane = [&](int fld, int lev) -> TF* { return sm + ((fld * R2) + ((lev + R2) % R2)) * TILE_PLANE; };
 
     const ScalArgs<TF>& a = args.s;
     const int tx = threadIdx.x % TILE_X, ty = threadIdx.x / TILE_X;
@@ -334,9 +357,14 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) scal_tile_kernel(const ScalTi
         p_rho[t] = g.rhoref[lev]; p_rhoh[t] = g.rhorefh[lev]; p_dzi[t] = g.dzi[lev]; p_dzhi[t] = g.dzhi[lev];
     }
 
-    stage_plane<TF, VEC>(plane(0, k0), a.s, k0, gi0, gj0, g);
-    stage_plane<TF, VEC>(plane(1, k0), a.evisc, k0, gi0, gj0, g);
+    Stager<TF, VEC, TY, TILE_H> stg;
+    stg.init(gi0, gj0, g);
+    const TF* src_s = a.s + (long long)k0 * kk;
+    const TF* src_e = a.evisc + (long long)k0 * kk;
+    stg.stage(sm + (0 * R2 + 0) * TILE_PLANE, src_s); src_s += kk;
+    stg.stage(sm + (1 * R2 + 0) * TILE_PLANE, src_e); src_e += kk;
     cp_async_commit();
+    int s0 = 0;
 
     auto colload = [&](const TF* __restrict__ fld, int lev) -> TF {
         return (lev >= 0 && lev < g.kcells) ? fld[ij + (long long)lev * kk] : TF(0);
@@ -350,8 +378,12 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) scal_tile_kernel(const ScalTi
     {
         cp_async_wait<0>();
         __syncthreads();
-        stage_plane<TF, VEC>(plane(0, k + 1), a.s, k + 1, gi0, gj0, g);
-        stage_plane<TF, VEC>(plane(1, k + 1), a.evisc, k + 1, gi0, gj0, g);
+        const int s1 = s0 ^ 1;
+        if (k + 1 < g.kcells)
+        {
+            stg.stage(sm + (0 * R2 + s1) * TILE_PLANE, src_s); src_s += kk;
+            stg.stage(sm + (1 * R2 + s1) * TILE_PLANE, src_e); src_e += kk;
+        }
         cp_async_commit();
 
         const bool store = (k >= kc0) && active;
@@ -366,8 +398,8 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) scal_tile_kernel(const ScalTi
             u0 = a.u[o_k]; u1 = a.u[o_k + 1]; v0 = a.v[o_k]; v1 = a.v[o_k + jj];
             st_old = a.st[o_k];
         }
-        const TF* __restrict__ S0 = plane(0, k) + sidx;
-        const TF* __restrict__ E0 = plane(1, k) + sidx;
+        const TF* __restrict__ S0 = sm + (0 * R2 + s0) * TILE_PLANE + sidx;
+        const TF* __restrict__ E0 = sm + (1 * R2 + s0) * TILE_PLANE + sidx;
         constexpr int P = TILE_PX;
         const int pl = k - k0;
         const TF rho_k = p_rho[pl], rhoh_f = p_rhoh[pl + 1], dzi_k = p_dzi[pl], dzhi_f = p_dzhi[pl + 1];
@@ -401,11 +433,12 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) scal_tile_kernel(const ScalTi
 #pragma unroll
         for (int n = 0; n < 5; ++n) sc[n] = sc[n + 1];
         sc[5] = s_new;
+        s0 = s1;
     }
     cp_async_wait<0>();
 }
 
-inline size_t scal_tile_smem(size_t elem, int kchunk) { return ((size_t)2 * 2 * TILE_PLANE + (size_t)4 * (kchunk + 3)) * elem; }
+inline size_t scal_tile_smem(size_t elem, int kchunk, int ty) { return ((size_t)2 * 2 * tile_plane(ty) + (size_t)4 * (kchunk + 3)) * elem; }
 
 
 // ------------------------------------------------------------------------------------------
@@ -415,8 +448,6 @@ inline size_t scal_tile_smem(size_t elem, int kchunk) { return ((size_t)2 * 2 * 
 // ------------------------------------------------------------------------------------------
 constexpr int EH = 1;
 constexpr int EPX = TILE_X + 2 * EH;      // 34
-constexpr int EPY = TILE_Y + 2 * EH;      // 18
-constexpr int EPLANE = EPX * EPY;
 
 template <typename TF>
 struct EviscTileArgs
@@ -426,13 +457,13 @@ struct EviscTileArgs
     int kchunk;
 };
 
-template <typename TF, bool SURFACE, int VEC>
-__global__ void __launch_bounds__(TILE_THREADS, 1) evisc_tile_kernel(const EviscTileArgs<TF> args, const GridDev<TF> g)
+template <typename TF, bool SURFACE, int VEC, int TY>
+__global__ void __launch_bounds__(TILE_X * TY, 512 / (TILE_X * TY)) evisc_tile_kernel(const EviscTileArgs<TF> args, const GridDev<TF> g)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TF* sm = reinterpret_cast<TF*>(smem_raw);
+    constexpr int TILE_Y = TY, TILE_THREADS = TILE_X * TY, EPLANE = tile_plane(TY, EH);
     // u: slots 0..2, v: 3..5, w: 6..8  (ring of 3 each)
-    auto plane = [&](int fld, int lev) -> TF* { return sm + ((fld * RING) + ((lev + RING) % RING)) * EPLANE; };
 
     const EviscArgs<TF>& a = args.e;
     const int tx = threadIdx.x % TILE_X, ty = threadIdx.x / TILE_X;
@@ -464,11 +495,19 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) evisc_tile_kernel(const Evisc
         p_gth[t] = (a.n2mode == 1) ? TF(GRAV) / g.thref[lev] : TF(0);
     }
     const TF* flds[3] = {a.u, a.v, a.w};
+    Stager<TF, VEC, TY, EH> stg;
+    stg.init(gi0, gj0, g);
+    const TF* pl_src[3];
 #pragma unroll
-    for (int f = 0; f < 3; ++f) stage_plane<TF, VEC, EH>(plane(f, k0), flds[f], k0, gi0, gj0, g);
-#pragma unroll
-    for (int f = 0; f < 3; ++f) stage_plane<TF, VEC, EH>(plane(f, k0 + 1), flds[f], k0 + 1, gi0, gj0, g);
+    for (int f = 0; f < 3; ++f)
+    {
+        pl_src[f] = flds[f] + (long long)k0 * kk;
+        stg.stage(sm + (f * RING + 0) * EPLANE, pl_src[f]);
+        stg.stage(sm + (f * RING + 1) * EPLANE, pl_src[f] + kk);
+        pl_src[f] += 2 * kk;
+    }
     cp_async_commit();
+    int s0 = 0;
 
     auto colload = [&](const TF* __restrict__ fld, int lev) -> TF {
         return (lev >= 0 && lev < g.kcells) ? fld[ij + (long long)lev * kk] : TF(0);
@@ -485,8 +524,13 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) evisc_tile_kernel(const Evisc
     {
         cp_async_wait<0>();
         __syncthreads();
+        const int s1 = (s0 == RING - 1) ? 0 : s0 + 1;
+        const int s2 = (s1 == RING - 1) ? 0 : s1 + 1;
+        if (k + 2 < g.kcells)
+        {
 #pragma unroll
-        for (int f = 0; f < 3; ++f) stage_plane<TF, VEC, EH>(plane(f, k + 2), flds[f], k + 2, gi0, gj0, g);
+            for (int f = 0; f < 3; ++f) { stg.stage(sm + (f * RING + s2) * EPLANE, pl_src[f]); pl_src[f] += kk; }
+        }
         cp_async_commit();
         const int f = k + 1;
         const bool store = (k >= kc0) && active;
@@ -495,12 +539,12 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) evisc_tile_kernel(const Evisc
         if (a.n2mode == 1) th_p = colload(a.th, k + 1);
         else if (store) n2v = a.n2[o_k];
 
-        const TF* __restrict__ U0 = plane(0, k) + sidx;
-        const TF* __restrict__ U1 = plane(0, f) + sidx;
-        const TF* __restrict__ V0 = plane(1, k) + sidx;
-        const TF* __restrict__ V1 = plane(1, f) + sidx;
-        const TF* __restrict__ W0 = plane(2, k) + sidx;
-        const TF* __restrict__ W1 = plane(2, f) + sidx;
+        const TF* __restrict__ U0 = sm + (0 * RING + s0) * EPLANE + sidx;
+        const TF* __restrict__ U1 = sm + (0 * RING + s1) * EPLANE + sidx;
+        const TF* __restrict__ V0 = sm + (1 * RING + s0) * EPLANE + sidx;
+        const TF* __restrict__ V1 = sm + (1 * RING + s1) * EPLANE + sidx;
+        const TF* __restrict__ W0 = sm + (2 * RING + s0) * EPLANE + sidx;
+        const TF* __restrict__ W1 = sm + (2 * RING + s1) * EPLANE + sidx;
         constexpr int P = EPX;
         const int pl = k - k0;
         const TF dzhi_f = p_dzhi[pl + 1];
@@ -551,10 +595,11 @@ __global__ void __launch_bounds__(TILE_THREADS, 1) evisc_tile_kernel(const Evisc
         }
         t0 = nt0; t1 = nt1; r0 = nr0; r1 = nr1; tw0 = wx0; tw1 = wx1; rw0 = wy0; rw1 = wy1;
         th_m = th_c; th_c = th_p;
+        s0 = s1;
     }
     cp_async_wait<0>();
 }
 
-inline size_t evisc_tile_smem(size_t elem, int kchunk) { return ((size_t)3 * RING * EPLANE + (size_t)5 * (kchunk + 3)) * elem; }
+inline size_t evisc_tile_smem(size_t elem, int kchunk, int ty) { return ((size_t)3 * RING * tile_plane(ty, EH) + (size_t)5 * (kchunk + 3)) * elem; }
 
 } // namespace mhh
