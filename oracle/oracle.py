@@ -393,6 +393,28 @@ def advec_2i5_cfl(g, u, v, w, dt):
 # --------------------------------------------------------------------------------------
 # Diff_smag2 (reference include/diff_kernels.h:34-511, src/diff_smag2.cxx:148-269)
 # --------------------------------------------------------------------------------------
+def _load_cport():
+    import ctypes, os
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build", "liboracle_c.so")
+    return ctypes.CDLL(p) if os.path.exists(p) else None
+
+_CPORT = _load_cport()
+
+def _libm_pow(x, y):
+    """std::pow(TF, TF) through the C library (oracle/cport/libm_vec.c), the libm the reference's CPU
+    build links; numpy's own SIMD pow is 1 ulp apart now and then.  Falls back to numpy when the
+    helper has not been built (make -C oracle cport): parity to ~1 ulp instead of bit-exact."""
+    import ctypes
+    x = np.ascontiguousarray(x)
+    if _CPORT is None or x.dtype not in (np.float64, np.float32):
+        return np.power(x, x.dtype.type(y))
+    out = np.empty_like(x)
+    if x.dtype == np.float64:
+        _CPORT.vpow_f64(x.ctypes.data_as(ctypes.c_void_p), ctypes.c_double(float(y)), out.ctypes.data_as(ctypes.c_void_p), ctypes.c_long(x.size))
+    else:
+        _CPORT.vpow_f32(x.ctypes.data_as(ctypes.c_void_p), ctypes.c_float(float(y)), out.ctypes.data_as(ctypes.c_void_p), ctypes.c_long(x.size))
+    return out
+
 DSMALL = 1.e-9   # Constants::dsmall (reference include/constants.h)
 KAPPA = 0.4      # Constants::kappa
 GRAV = 9.81      # Constants::grav
@@ -474,7 +496,7 @@ def diff_evisc(g, evisc, N2, bgradbot, z0m, cs, tPr, surface, mason=True):
     cs, tPr = TF(cs), TF(tPr)
     one_m = TF(1. - DSMALL)
     third = TF(1./3.)
-    mlen0_k = cs*np.power(g.dx*g.dy*g.dz, third).astype(TF)
+    mlen0_k = (cs*_libm_pow((g.dx*g.dy*g.dz).astype(TF), third)).astype(TF)
     ij = (slice(g.jstart, g.jend), slice(g.istart, g.iend))
     if not surface:
         k0, k1 = ks, ke
@@ -492,7 +514,7 @@ def diff_evisc(g, evisc, N2, bgradbot, z0m, cs, tPr, surface, mason=True):
             if not mason:
                 return m0 + np.zeros_like(_S(g, evisc, 0, 0, 0, k0, k1))
             zz = _K(g, g.z, 0, k0, k1) + z0m[ij][None, :, :]
-            return np.power(TF(1.)/(TF(1.)/np.power(m0, n_mason) + TF(1.)/(np.power(TF(KAPPA)*zz, n_mason))), TF(1.)/n_mason)
+            return _libm_pow(TF(1.)/(TF(1.)/_libm_pow(m0 + np.zeros_like(zz), n_mason) + TF(1.)/(_libm_pow(TF(KAPPA)*zz, n_mason))), TF(1.)/n_mason)
         # bottom (:216-239)
         k0, k1 = ks, ks+1
         ev = _S(g, evisc, 0, 0, 0, k0, k1)

@@ -1,0 +1,79 @@
+"""
+Generates tests/golden/*.npz: outputs of the REFERENCE's own CPU kernels (oracle/_ref/libmhh_ref.so,
+compiled from /root/reference by oracle/Makefile) for seeded synthetic inputs, in the reference's
+call order (oracle/step.py).  Run in the build container where /root/reference exists:
+
+    make -C oracle && python tests/make_golden.py
+
+The inputs are not stored: they are regenerated from (shape, dtype, seed, flags) by
+microhh_b200.synthetic.make_case, which is deterministic (numpy default_rng).  A checksum of the
+inputs is stored so that a drift of the generator is detected rather than silently compared.
+"""
+import copy
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE)); sys.path.insert(0, HERE)
+
+from util import make_pair, prepare_halos            # noqa: E402
+from oracle import oracle as O, step as ostep, refbind  # noqa: E402
+
+CASES = {
+    # name: (shape, dtype, anelastic, stretched, nsteps)
+    "step_16x12x8_f64": ((16, 12, 8), np.float64, False, False, 1),
+    "step_20x12x10_anel_stretched_f64": ((20, 12, 10), np.float64, True, True, 1),
+    "step_24x1x8_f64": ((24, 1, 8), np.float64, False, True, 1),
+    "step_16x12x8_f32": ((16, 12, 8), np.float32, False, False, 1),
+    "step_20x12x10_anel_stretched_f32": ((20, 12, 10), np.float32, True, True, 1),
+}
+DT = 2.0
+
+
+def input_digest(case):
+    h = hashlib.sha256()
+    for n in ("u", "v", "w", "th", "rhoref", "rhorefh", "dudz_mo", "dbdz_mo", "th_fluxbot"):
+        h.update(np.ascontiguousarray(case[n]).tobytes())
+    return h.hexdigest()
+
+
+def main():
+    assert refbind.available(), "build oracle/_ref first (make -C oracle)"
+    for name, (shape, dtype, anel, stretched, nsteps) in CASES.items():
+        g, gd, case = make_pair(*shape, dtype, stretched=stretched, anelastic=anel)
+        digest = input_digest(case)
+        out = {}
+        # single kernels on halo-filled inputs (tendencies start at zero)
+        ck = copy.deepcopy(case); prepare_halos(g, ck)
+        R = refbind.RefKernels(g)
+        rr, rh = ck["rhoref"], ck["rhorefh"]
+        R.advec_2i5_u(ck["ut"], ck["u"], ck["v"], ck["w"], rr, rh)
+        R.advec_2i5_v(ck["vt"], ck["u"], ck["v"], ck["w"], rr, rh)
+        R.advec_2i5_w(ck["wt"], ck["u"], ck["v"], ck["w"], rr, rh)
+        R.advec_2i5_s(ck["tht"], ck["th"], ck["u"], ck["v"], ck["w"], rr, rh)
+        for n in ("ut", "vt", "wt", "tht"):
+            out["advec_" + n] = ck[n].copy()
+        out["cfl"] = np.float64(R.advec_2i5_cfl(ck["u"], ck["v"], ck["w"], DT))
+        R.diff_strain2(ck["evisc"], ck["u"], ck["v"], ck["w"], ck["dudz_mo"], ck["dvdz_mo"], True)
+        n2 = np.zeros_like(ck["evisc"]); R.thermo_dry_N2(n2, ck["th"], ck["thref"])
+        R.diff_evisc(ck["evisc"], ck["u"], ck["v"], ck["w"], n2, ck["dbdz_mo"], ck["z0m"], 0.23, 1./3., True, True)
+        out["evisc"] = ck["evisc"].copy()
+        out["dn"] = np.float64(R.diff_dnmul(ck["evisc"], 1./3.)*DT)
+        # full RK3 step(s) in Model::exec order
+        cs = copy.deepcopy(case)
+        prm = ostep.default_params()
+        for _ in range(nsteps):
+            ostep.dycore_step(g, refbind.RefKernels(g), cs, prm, DT)
+        for n in ("u", "v", "w", "th", "p"):
+            out["step_" + n] = cs[n].copy()
+        np.savez_compressed(os.path.join(HERE, "golden", name + ".npz"), input_sha256=np.array(digest),
+                            shape=np.array(shape), anel=np.array(anel), stretched=np.array(stretched),
+                            nsteps=np.array(nsteps), dt=np.array(DT), **out)
+        print(name, digest[:12], {k: (v.shape if hasattr(v, "shape") else v) for k, v in list(out.items())[:3]})
+
+
+if __name__ == "__main__":
+    main()

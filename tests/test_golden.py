@@ -1,0 +1,104 @@
+"""
+Golden vectors (tests/golden/*.npz, made by tests/make_golden.py from the REFERENCE's own compiled
+CPU kernels).  CPU part: the numpy oracle reproduces them bit for bit and the FFT restatement obeys
+FFTW's documented R2HC/HC2R definition.  GPU part: the CUDA path through the C ABI matches them
+within BASELINE.json's tolerance (rel. L2 <= 1e-12 fp64 / 1e-5 fp32).
+"""
+import copy
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from util import TOL, rel_l2, make_pair, prepare_halos, interior
+from make_golden import input_digest
+from oracle import oracle as O, step as ostep
+
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz")))
+
+
+def load(path):
+    z = np.load(path)
+    dtype = np.float32 if path.endswith("_f32.npz") else np.float64
+    g, gd, case = make_pair(*[int(x) for x in z["shape"]], dtype, stretched=bool(z["stretched"]), anelastic=bool(z["anel"]))
+    assert input_digest(case) == str(z["input_sha256"]), "synthetic input generator drifted from the golden inputs"
+    return z, dtype, g, gd, case
+
+
+def test_golden_present():
+    assert len(GOLD) >= 5
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
+def test_oracle_reproduces_golden_bitexact(path):
+    z, dtype, g, gd, case = load(path)
+    K = O.NumpyKernels(g)
+    ck = copy.deepcopy(case); prepare_halos(g, ck)
+    rr, rh = ck["rhoref"], ck["rhorefh"]
+    K.advec_2i5_u(ck["ut"], ck["u"], ck["v"], ck["w"], rr, rh)
+    K.advec_2i5_v(ck["vt"], ck["u"], ck["v"], ck["w"], rr, rh)
+    K.advec_2i5_w(ck["wt"], ck["u"], ck["v"], ck["w"], rr, rh)
+    K.advec_2i5_s(ck["tht"], ck["th"], ck["u"], ck["v"], ck["w"], rr, rh)
+    for n in ("ut", "vt", "wt", "tht"):
+        assert np.array_equal(ck[n], z["advec_" + n]), n
+    assert K.advec_2i5_cfl(ck["u"], ck["v"], ck["w"], float(z["dt"])) == float(z["cfl"])
+    K.diff_strain2(ck["evisc"], ck["u"], ck["v"], ck["w"], ck["dudz_mo"], ck["dvdz_mo"], True)
+    n2 = np.zeros_like(ck["evisc"]); K.thermo_dry_N2(n2, ck["th"], ck["thref"])
+    K.diff_evisc(ck["evisc"], ck["u"], ck["v"], ck["w"], n2, ck["dbdz_mo"], ck["z0m"], 0.23, 1./3., True, True)
+    assert np.array_equal(ck["evisc"], z["evisc"])
+    cs = copy.deepcopy(case)
+    for _ in range(int(z["nsteps"])):
+        ostep.dycore_step(g, K, cs, ostep.default_params(), float(z["dt"]))
+    for n in ("u", "v", "w", "th", "p"):
+        assert np.array_equal(cs[n], z["step_" + n]), n
+
+
+@pytest.mark.parametrize("n", [2, 6, 8, 12, 20, 30])
+def test_fft_restatement_obeys_fftw_definition(n):
+    """FFTW r2r kinds used by the reference (src/fft.cxx:145-155): R2HC stores
+    [r0, r1, ..., r_{n/2}, i_{(n+1)/2-1}, ..., i_1] of X_k = sum_j x_j exp(-2 pi i j k / n); HC2R is its
+    unnormalised inverse (fftw3 manual, 'The Halfcomplex-format DFT')."""
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal((3, n))
+    j = np.arange(n)
+    X = np.array([[np.sum(row*np.exp(-2j*np.pi*j*k/n)) for k in range(n)] for row in x])
+    hc = O.r2hc(x.copy(), axis=1)
+    exp = np.zeros_like(x)
+    exp[:, :n//2 + 1] = X[:, :n//2 + 1].real
+    for k in range(1, (n + 1)//2):
+        exp[:, n - k] = X[:, k].imag
+    assert np.allclose(hc, exp, rtol=0, atol=1e-12*n)
+    back = O.hc2r(hc.copy(), axis=1)
+    assert np.allclose(back, n*x, rtol=0, atol=1e-12*n*n)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
+def test_cuda_matches_golden(path):
+    import torch
+    from microhh_b200 import dycore as D
+    z, dtype, g, gd, case = load(path)
+    ctx = D.Context(gd, 0)
+    ctx.set_basestate(case["rhoref"], case["rhorefh"], case["thref"], case["threfh"])
+    # single kernels on halo-filled inputs
+    ck = copy.deepcopy(case); prepare_halos(g, ck)
+    f = D.Fields(ctx, ck)
+    prm = D.make_params()
+    D.Advec(ctx).exec(f)
+    for n in ("ut", "vt", "wt", "tht"):
+        k0 = g.kstart + 1 if n == "wt" else g.kstart
+        assert rel_l2(interior(g, f[n].cpu().numpy(), k0), interior(g, z["advec_" + n], k0)) <= TOL[dtype], n
+    cfl = D.Advec(ctx).get_cfl(f, float(z["dt"]))
+    assert abs(cfl - float(z["cfl"])) <= 10*TOL[dtype]*float(z["cfl"])
+    D.Diff(ctx, prm).exec_viscosity(f)
+    assert rel_l2(f["evisc"].cpu().numpy(), z["evisc"]) <= 10*TOL[dtype]
+    dn = D.Diff(ctx, prm).get_dn(f, float(z["dt"]))
+    assert abs(dn - float(z["dn"])) <= 100*TOL[dtype]*float(z["dn"])
+    # full step
+    f2 = D.Fields(ctx, case)
+    for _ in range(int(z["nsteps"])):
+        D.Dycore(ctx, prm).step(f2, float(z["dt"]))
+    ctx.sync()
+    for n in ("u", "v", "w", "th"):
+        assert rel_l2(interior(g, f2[n].cpu().numpy()), interior(g, z["step_" + n])) <= TOL[dtype], n

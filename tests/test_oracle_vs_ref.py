@@ -1,0 +1,131 @@
+"""
+Pins the oracle (CPU, no GPU needed): the numpy restatement in oracle/oracle.py against the
+reference's own CPU kernels compiled from /root/reference into oracle/_ref/libmhh_ref.so
+(-O2 -ffp-contract=off).  Bit-exact for every kernel the harness reaches, and for a full RK3
+step assembled in the reference's call order.  Skipped (not failed) where oracle/_ref has not
+been built; the committed golden vectors (tests/golden/, test_golden.py) cover that case.
+"""
+import copy
+import numpy as np
+import pytest
+
+from util import make_pair, prepare_halos, interior
+from oracle import oracle as O
+from oracle import step as ostep
+from oracle import refbind
+
+pytestmark = pytest.mark.skipif(not refbind.available(), reason="oracle/_ref/libmhh_ref.so not built (make -C oracle)")
+
+DTYPES = [np.float64, np.float32]
+CASES = [((16, 12, 8), False, False), ((20, 12, 10), True, True), ((24, 1, 8), False, True)]
+
+
+def both(g):
+    return O.NumpyKernels(g), refbind.RefKernels(g)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape,anel,stretched", CASES)
+def test_kernels_bitexact(dtype, shape, anel, stretched):
+    g, gd, case = make_pair(*shape, dtype, stretched=stretched, anelastic=anel)
+    prepare_halos(g, case)
+    N, R = both(g)
+    rr, rh = case["rhoref"], case["rhorefh"]
+    rng = np.random.default_rng(11)
+
+    def pair(fn_name, out_names, *args_builder):
+        outs = []
+        for K in (N, R):
+            c = copy.deepcopy(case)
+            for n in out_names:
+                c[n] = rng_fill[n].copy()
+            args_builder[0](K, c)
+            outs.append([c[n] for n in out_names])
+        for a, b, n in zip(outs[0], outs[1], out_names):
+            assert np.array_equal(a, b), (fn_name, n, float(np.abs(a.astype(np.float64) - b).max()))
+
+    rng_fill = {n: rng.standard_normal(gd.shape).astype(dtype) for n in ("ut", "vt", "wt", "tht", "evisc")}
+
+    pair("advec_u", ["ut"], lambda K, c: K.advec_2i5_u(c["ut"], c["u"], c["v"], c["w"], rr, rh))
+    pair("advec_v", ["vt"], lambda K, c: K.advec_2i5_v(c["vt"], c["u"], c["v"], c["w"], rr, rh))
+    pair("advec_w", ["wt"], lambda K, c: K.advec_2i5_w(c["wt"], c["u"], c["v"], c["w"], rr, rh))
+    pair("advec_s", ["tht"], lambda K, c: K.advec_2i5_s(c["tht"], c["th"], c["u"], c["v"], c["w"], rr, rh))
+    pair("buoyancy", ["wt"], lambda K, c: K.thermo_dry_buoyancy_tend_2nd(c["wt"], c["th"], c["threfh"]))
+
+    for surface in (True, False):
+        # eddy viscosity chain: strain2 -> N2 -> evisc
+        ev = []
+        for K in (N, R):
+            c = copy.deepcopy(case)
+            c["evisc"] = np.zeros(gd.shape, dtype)
+            K.diff_strain2(c["evisc"], c["u"], c["v"], c["w"], c["dudz_mo"], c["dvdz_mo"], surface)
+            n2 = np.zeros(gd.shape, dtype)
+            K.thermo_dry_N2(n2, c["th"], c["thref"])
+            K.diff_evisc(c["evisc"], c["u"], c["v"], c["w"], n2, c["dbdz_mo"], c["z0m"], 0.23, 1./3., surface, True)
+            ev.append(c["evisc"])
+        assert np.array_equal(ev[0], ev[1]), ("evisc", surface)
+        case_e = copy.deepcopy(case); case_e["evisc"] = ev[1]
+        for nm, fn in (("diff_u", lambda K, c: K.diff_u(c["ut"], c["u"], c["v"], c["w"], c["evisc"], c["u_fluxbot"], c["u_fluxtop"], rr, rh, 1e-5, surface)),
+                       ("diff_v", lambda K, c: K.diff_v(c["vt"], c["u"], c["v"], c["w"], c["evisc"], c["v_fluxbot"], c["v_fluxtop"], rr, rh, 1e-5, surface)),
+                       ("diff_w", lambda K, c: K.diff_w(c["wt"], c["u"], c["v"], c["w"], c["evisc"], rr, rh, 1e-5)),
+                       ("diff_c", lambda K, c: K.diff_c(c["tht"], c["th"], c["evisc"], c["th_fluxbot"], c["th_fluxtop"], rr, rh, 1./3., 1e-5, surface))):
+            res = []
+            for K in (N, R):
+                c = copy.deepcopy(case_e)
+                for n in ("ut", "vt", "wt", "tht"):
+                    c[n] = rng_fill[n].copy()
+                fn(K, c)
+                res.append([c[n] for n in ("ut", "vt", "wt", "tht")])
+            for a, b in zip(*res):
+                assert np.array_equal(a, b), (nm, surface)
+        assert N.diff_dnmul(ev[0], 1./3.) == R.diff_dnmul(ev[1], 1./3.)
+    assert N.advec_2i5_cfl(case["u"], case["v"], case["w"], 2.0) == R.advec_2i5_cfl(case["u"], case["v"], case["w"], 2.0)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("edge", [0, 1, 2])
+@pytest.mark.parametrize("shape", [(16, 12, 8), (24, 1, 8)])
+def test_boundary_cyclic_bitexact(dtype, edge, shape):
+    g, gd, case = make_pair(*shape, dtype)
+    a = np.random.default_rng(3).standard_normal(gd.shape).astype(dtype)
+    b = a.copy()
+    N, R = both(g)
+    N.boundary_cyclic(a, edge); R.boundary_cyclic(b, edge)
+    assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("substep", [0, 1, 2])
+def test_rk3_and_tdma_bitexact(dtype, substep):
+    g, gd, case = make_pair(16, 12, 8, dtype, stretched=True, anelastic=True)
+    N, R = both(g)
+    rng = np.random.default_rng(4)
+    a0 = rng.standard_normal(gd.shape).astype(dtype); t0 = rng.standard_normal(gd.shape).astype(dtype)
+    a1, t1 = a0.copy(), t0.copy()
+    N.rk3(a0, t0, substep, 1.7); R.rk3(a1, t1, substep, 1.7)
+    assert np.array_equal(a0, a1) and np.array_equal(t0, t1)
+    # tridiagonal solve on the spectral right-hand side of this grid
+    P = O.Pres2(g, case["rhoref"], case["rhorefh"])
+    p = rng.standard_normal((g.kmax, g.jmax, g.imax)).astype(dtype)
+    pc0 = np.zeros(gd.shape, dtype); pc1 = np.zeros(gd.shape, dtype)
+    q0 = p.copy(); q1 = p.copy()
+    P.solve(q0, pc0)
+    P.solve(q1, pc1, tdma=lambda pp, b: R.tdma(P.a.copy(), b, P.c.copy(), pp))
+    assert np.array_equal(pc0, pc1)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape,anel,stretched", CASES)
+def test_full_rk3_step_bitexact(dtype, shape, anel, stretched):
+    """One full RK3 step in the reference's call order: numpy oracle == compiled reference kernels."""
+    g, gd, case = make_pair(*shape, dtype, stretched=stretched, anelastic=anel)
+    c0, c1 = copy.deepcopy(case), copy.deepcopy(case)
+    N, R = both(g)
+    prm = ostep.default_params()
+    ostep.dycore_step(g, N, c0, prm, 2.0)
+    ostep.dycore_step(g, R, c1, prm, 2.0)
+    for n in ("u", "v", "w", "th", "p", "evisc"):
+        assert np.array_equal(c0[n], c1[n]), n
+    # the step does something and stays finite
+    assert np.isfinite(interior(g, c0["u"])).all()
+    assert not np.array_equal(c0["u"], case["u"])
