@@ -14,6 +14,8 @@
 #include "stencil_kernels.cuh"
 #include "poisson_kernels.cuh"
 #include "tile_kernels.cuh"
+#include "tile2_kernels.cuh"
+#include <cudaTypedefs.h>
 
 using namespace mhh;
 
@@ -31,6 +33,8 @@ struct mhh_ctx
     // previous event on the (in-order) stream
     int tile_y = 8;             // MHH_TILE_Y=8|16: tile height of the z-marching kernels
     bool force_plain = false;   // MHH_FORCE_PLAIN=1: use the point-wise kernels everywhere (A/B comparisons)
+    bool no_tma = false;        // MHH_NO_TMA=1: keep the cp.async tile kernels (A/B comparisons)
+    int tile2_y = 6;            // MHH_TILE2_Y: rows (= warps) per CTA of the TMA tile kernels
     bool prof = false;
     std::vector<std::pair<const char*, cudaEvent_t>> prof_events;
     std::vector<cudaEvent_t> prof_pool;
@@ -145,6 +149,8 @@ int create_impl(const mhh_grid_desc* d, int dtype, int device, mhh_ctx** out)
     *out = c;
     c->dtype = dtype; c->device = device; c->desc = *d;
     { const char* e = getenv("MHH_FORCE_PLAIN"); c->force_plain = e && e[0] == '1'; }
+    { const char* e = getenv("MHH_NO_TMA"); c->no_tma = e && e[0] == '1'; }
+    { const char* e = getenv("MHH_TILE2_Y"); if (e) { int v = atoi(e); if (v == 4 || v == 6 || v == 8 || v == 12) c->tile2_y = v; } }
     { const char* e = getenv("MHH_TILE_Y"); if (e && atoi(e) == 16) c->tile_y = 16; else if (e && atoi(e) == 8) c->tile_y = 8; }
     CUDA_TRY(c, cudaSetDevice(device));
     int nsm = 0;
@@ -451,6 +457,61 @@ int check_mom(Ctx<TF>* c, const mhh_fields* f, bool need_evisc, bool surface)
     return MHH_OK;
 }
 
+// ---- TMA tensor maps (driver entry point fetched through the runtime; libcuda is not linked) ----
+inline PFN_cuTensorMapEncodeTiled tmap_encoder()
+{
+    static PFN_cuTensorMapEncodeTiled fn = nullptr;
+    if (!fn)
+    {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
+    }
+    return fn;
+}
+
+// 3-D map over a ghosted field (icells, jcells, kcells) with a box of (bx, by, 1) elements
+template <typename TF>
+bool make_field_tmap(CUtensorMap* m, const TF* fld, const GridDev<TF>& g, int bx, int by)
+{
+    PFN_cuTensorMapEncodeTiled enc = tmap_encoder();
+    if (!enc) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)g.icells, (cuuint64_t)g.jcells, (cuuint64_t)g.kcells};
+    const cuuint64_t strides[2] = {(cuuint64_t)g.icells * sizeof(TF), (cuuint64_t)g.ijcells * sizeof(TF)};
+    const cuuint32_t box[3] = {(cuuint32_t)bx, (cuuint32_t)by, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUtensorMapDataType dt = sizeof(TF) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    return enc(m, dt, 3, const_cast<TF*>(fld), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// TMA needs 16-byte aligned base pointers and row/plane pitches that are multiples of 16 bytes
+template <typename TF>
+bool tma_ok(const GridDev<TF>& g, std::initializer_list<const void*> ptrs)
+{
+    if (((size_t)g.icells * sizeof(TF)) % 16 != 0 || (g.imax % 2) != 0 || g.igc < 3 || g.jgc < 3) return false;
+    for (const void* p : ptrs)
+        if (!p || (reinterpret_cast<uintptr_t>(p) % 16) != 0) return false;
+    return tmap_encoder() != nullptr;
+}
+
+// z-chunk of the marching kernels: fill whole waves of resident CTAs, pay (warm-up levels)/kchunk per chunk
+inline int pick_kchunk_waves(int ntiles_xy, int kmax, int slots, int warm)
+{
+    int best_nz = 1; double best = -1.;
+    for (int nz = 1; nz <= std::max(1, kmax / 16); ++nz)
+    {
+        const int kchunk = (kmax + nz - 1) / nz;
+        const int nzz = (kmax + kchunk - 1) / kchunk;
+        const long long ctas = (long long)ntiles_xy * nzz;
+        const long long waves = (ctas + slots - 1) / slots;
+        const double eff = (double)ctas / (double)(waves * slots) * (double)kmax / (double)(nzz * (kchunk + warm));
+        if (eff > best * 1.02) { best = eff; best_nz = nz; }
+    }
+    return (kmax + best_nz - 1) / best_nz;
+}
+
 // fused advection + diffusion (+ buoyancy) of u, v, w with the z-marching tile kernel
 template <typename TF>
 int mom_tile_launch(Ctx<TF>* c, const MomArgs<TF>& a, bool surface, bool buoy)
@@ -475,6 +536,36 @@ int mom_tile_launch(Ctx<TF>* c, const MomArgs<TF>& a, bool surface, bool buoy)
 #undef MT2
 #undef MT
     KCHECKN(c, "mom_tile_kernel");
+    return MHH_OK;
+}
+
+// TMA-staged, two-columns-per-thread variant (tile2_kernels.cuh)
+template <typename TF>
+int mom2_launch(Ctx<TF>* c, const MomArgs<TF>& a, bool surface, bool buoy)
+{
+    const GridDev<TF>& g = c->g;
+    const int ty = c->tile2_y;
+    const int ntx = (g.imax + T2_W - 1) / T2_W, nty = (g.jmax + ty - 1) / ty;
+    const int per_sm = ty <= 8 ? 2 : 1;
+    Mom2Args<TF> t{a, pick_kchunk_waves(ntx * nty, g.kmax, c->num_sms * per_sm, 2)};
+    dim3 grid(ntx, nty, (g.kmax + t.kchunk - 1) / t.kchunk);
+    const size_t smem = mom2_smem(sizeof(TF), t.kchunk, ty);
+    CUtensorMap tu, tv, tw, te;
+    if (!make_field_tmap<TF>(&tu, a.u, g, T2_PX, ty + 2 * T2_H) || !make_field_tmap<TF>(&tv, a.v, g, T2_PX, ty + 2 * T2_H) ||
+        !make_field_tmap<TF>(&tw, a.w, g, T2_PX, ty + 2 * T2_H) || !make_field_tmap<TF>(&te, a.evisc, g, T2_PX, ty + 2 * T2_H))
+    { c->err = "cuTensorMapEncodeTiled failed"; return MHH_E_CUDA; }
+#define M2(S, B, Y) do { \
+        static size_t attr_smem = 0; \
+        if (attr_smem < smem) { CUDA_TRY(c, cudaFuncSetAttribute(mom2_kernel<TF, S, B, Y>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; } \
+        mom2_kernel<TF, S, B, Y><<<grid, 32 * Y, smem, c->stream>>>(tu, tv, tw, te, t, g); } while (0)
+#define M2Y(S, B) do { if (ty == 4) M2(S, B, 4); else if (ty == 8) M2(S, B, 8); else if (ty == 12) M2(S, B, 12); else M2(S, B, 6); } while (0)
+    if (surface && buoy) M2Y(true, true);
+    else if (surface) M2Y(true, false);
+    else if (buoy) M2Y(false, true);
+    else M2Y(false, false);
+#undef M2Y
+#undef M2
+    KCHECKN(c, "mom2_kernel");
     return MHH_OK;
 }
 
@@ -518,7 +609,10 @@ int tend_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, bool adv, 
     const bool tiles = adv && diff && g.igc >= TILE_H && g.jgc >= TILE_H && !c->force_plain;
     if (tiles)
     {
-        if ((rc = mom_tile_launch<TF>(c, a, surface, buoy)) != MHH_OK) return rc;
+        const bool tma = !c->no_tma && sizeof(TF) == 8 && tma_ok<TF>(g, {a.u, a.v, a.w, a.evisc});
+        if (tma) rc = mom2_launch<TF>(c, a, surface, buoy);
+        else rc = mom_tile_launch<TF>(c, a, surface, buoy);
+        if (rc != MHH_OK) return rc;
     }
     else if (adv && diff && surface && buoy) LAUNCH_MOM(true, true, true, true);
     else if (adv && diff && surface) LAUNCH_MOM(true, true, true, false);
