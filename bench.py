@@ -180,7 +180,7 @@ def run_ours(args):
     alg = {  # algorithmic array passes per launch, in units of N*B bytes
         "tend_uvw_kernel": 4 + 6, "tend_s_kernel": 5 + 2, "evisc_kernel": 5,
         # z-marching tile kernels: R u,v,w,evisc,th + RMW ut,vt,wt | R s,u,v,w,evisc + RMW st | R u,v,w,th + W evisc
-        "mom_tile_kernel": 5 + 6, "scal_tile_kernel": 5 + 2, "evisc_tile_kernel": 5,
+        "mom_tile_kernel": 5 + 6, "mom2_kernel": 5 + 6, "mom3_kernel": 5 + 6, "scal_tile_kernel": 5 + 2, "evisc_tile_kernel": 5,
         "fft_x_forward_kernel": 7, "fft_y_forward_kernel": 2, "fft_y_backward_kernel": 2,
         "tdma_solve_kernel": 2, "fft_x_backward_kernel": 2, "pres_out_rk3_kernel": 13, "rk3_kernel": 4,
     }

@@ -15,6 +15,7 @@
 #include "poisson_kernels.cuh"
 #include "tile_kernels.cuh"
 #include "tile2_kernels.cuh"
+#include "tile3_kernels.cuh"
 #include <cudaTypedefs.h>
 
 using namespace mhh;
@@ -34,7 +35,11 @@ struct mhh_ctx
     int tile_y = 8;             // MHH_TILE_Y=8|16: tile height of the z-marching kernels
     bool force_plain = false;   // MHH_FORCE_PLAIN=1: use the point-wise kernels everywhere (A/B comparisons)
     bool no_tma = false;        // MHH_NO_TMA=1: keep the cp.async tile kernels (A/B comparisons)
+    int tile3_y = 4;            // MHH_TILE3_Y: rows per CTA of the warp-specialised kernel (3*rows+1 warps)
     int tile2_y = 6;            // MHH_TILE2_Y: rows (= warps) per CTA of the TMA tile kernels
+    bool fuse_scalar = false;   // MHH_FUSE_SCALAR=1: scalar 0 as a fourth warp group of the momentum kernel
+    int mom_variant = 3;        // MHH_MOM=2|3: 2 = all components per thread, 3 = warp-specialised by component
+    int prefetch = 1;           // MHH_PREFETCH: L2 prefetch distance (levels) of the TMA tile kernels, 0 = off
     bool prof = false;
     std::vector<std::pair<const char*, cudaEvent_t>> prof_events;
     std::vector<cudaEvent_t> prof_pool;
@@ -151,6 +156,10 @@ int create_impl(const mhh_grid_desc* d, int dtype, int device, mhh_ctx** out)
     { const char* e = getenv("MHH_FORCE_PLAIN"); c->force_plain = e && e[0] == '1'; }
     { const char* e = getenv("MHH_NO_TMA"); c->no_tma = e && e[0] == '1'; }
     { const char* e = getenv("MHH_TILE2_Y"); if (e) { int v = atoi(e); if (v == 4 || v == 6 || v == 8 || v == 12) c->tile2_y = v; } }
+    { const char* e = getenv("MHH_FUSE_SCALAR"); c->fuse_scalar = e && e[0] == '1'; }
+    { const char* e = getenv("MHH_MOM"); if (e && atoi(e) == 2) c->mom_variant = 2; }
+    { const char* e = getenv("MHH_TILE3_Y"); if (e) { int v = atoi(e); if (v == 3 || v == 4 || v == 5) c->tile3_y = v; } }
+    { const char* e = getenv("MHH_PREFETCH"); if (e) c->prefetch = std::max(0, std::min(8, atoi(e))); }
     { const char* e = getenv("MHH_TILE_Y"); if (e && atoi(e) == 16) c->tile_y = 16; else if (e && atoi(e) == 8) c->tile_y = 8; }
     CUDA_TRY(c, cudaSetDevice(device));
     int nsm = 0;
@@ -473,7 +482,7 @@ inline PFN_cuTensorMapEncodeTiled tmap_encoder()
 
 // 3-D map over a ghosted field (icells, jcells, kcells) with a box of (bx, by, 1) elements
 template <typename TF>
-bool make_field_tmap(CUtensorMap* m, const TF* fld, const GridDev<TF>& g, int bx, int by)
+bool make_field_tmap(CUtensorMap* m, const void* fld, const GridDev<TF>& g, int bx, int by)
 {
     PFN_cuTensorMapEncodeTiled enc = tmap_encoder();
     if (!enc) return false;
@@ -482,7 +491,7 @@ bool make_field_tmap(CUtensorMap* m, const TF* fld, const GridDev<TF>& g, int bx
     const cuuint32_t box[3] = {(cuuint32_t)bx, (cuuint32_t)by, 1u};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
     const CUtensorMapDataType dt = sizeof(TF) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-    return enc(m, dt, 3, const_cast<TF*>(fld), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    return enc(m, dt, 3, const_cast<void*>(fld), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -547,17 +556,20 @@ int mom2_launch(Ctx<TF>* c, const MomArgs<TF>& a, bool surface, bool buoy)
     const int ty = c->tile2_y;
     const int ntx = (g.imax + T2_W - 1) / T2_W, nty = (g.jmax + ty - 1) / ty;
     const int per_sm = ty <= 8 ? 2 : 1;
-    Mom2Args<TF> t{a, pick_kchunk_waves(ntx * nty, g.kmax, c->num_sms * per_sm, 2)};
+    Mom2Args<TF> t{a, pick_kchunk_waves(ntx * nty, g.kmax, c->num_sms * per_sm, 2), c->prefetch};
     dim3 grid(ntx, nty, (g.kmax + t.kchunk - 1) / t.kchunk);
     const size_t smem = mom2_smem(sizeof(TF), t.kchunk, ty);
-    CUtensorMap tu, tv, tw, te;
-    if (!make_field_tmap<TF>(&tu, a.u, g, T2_PX, ty + 2 * T2_H) || !make_field_tmap<TF>(&tv, a.v, g, T2_PX, ty + 2 * T2_H) ||
-        !make_field_tmap<TF>(&tw, a.w, g, T2_PX, ty + 2 * T2_H) || !make_field_tmap<TF>(&te, a.evisc, g, T2_PX, ty + 2 * T2_H))
+    CUtensorMap tu, tv, tw, te, tut, tvt, twt, tth;
+    const int by = ty + 2 * T2_H;
+    if (!make_field_tmap<TF>(&tu, a.u, g, T2_PX, by) || !make_field_tmap<TF>(&tv, a.v, g, T2_PX, by) ||
+        !make_field_tmap<TF>(&tw, a.w, g, T2_PX, by) || !make_field_tmap<TF>(&te, a.evisc, g, T2_PX, by) ||
+        !make_field_tmap<TF>(&tut, a.ut, g, T2_W + 2, ty) || !make_field_tmap<TF>(&tvt, a.vt, g, T2_W + 2, ty) ||
+        !make_field_tmap<TF>(&twt, a.wt, g, T2_W + 2, ty) || !make_field_tmap<TF>(&tth, buoy ? (const void*)a.th : (const void*)a.u, g, T2_W + 2, ty))
     { c->err = "cuTensorMapEncodeTiled failed"; return MHH_E_CUDA; }
 #define M2(S, B, Y) do { \
         static size_t attr_smem = 0; \
         if (attr_smem < smem) { CUDA_TRY(c, cudaFuncSetAttribute(mom2_kernel<TF, S, B, Y>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; } \
-        mom2_kernel<TF, S, B, Y><<<grid, 32 * Y, smem, c->stream>>>(tu, tv, tw, te, t, g); } while (0)
+        mom2_kernel<TF, S, B, Y><<<grid, 32 * Y, smem, c->stream>>>(tu, tv, tw, te, tut, tvt, twt, tth, t, g); } while (0)
 #define M2Y(S, B) do { if (ty == 4) M2(S, B, 4); else if (ty == 8) M2(S, B, 8); else if (ty == 12) M2(S, B, 12); else M2(S, B, 6); } while (0)
     if (surface && buoy) M2Y(true, true);
     else if (surface) M2Y(true, false);
@@ -566,6 +578,53 @@ int mom2_launch(Ctx<TF>* c, const MomArgs<TF>& a, bool surface, bool buoy)
 #undef M2Y
 #undef M2
     KCHECKN(c, "mom2_kernel");
+    return MHH_OK;
+}
+
+// warp-specialised variant (tile3_kernels.cuh): one CTA of (3+nsc)*ty+1 warps per SM; the first scalar rides along
+template <typename TF>
+int mom3_launch(Ctx<TF>* c, const MomArgs<TF>& a, const ScalArgs<TF>* sc, bool surface, bool buoy)
+{
+    const GridDev<TF>& g = c->g;
+    const int ty = c->tile3_y;
+    const int nsc = sc ? 1 : 0;
+    const int ntx = (g.imax + T2_W - 1) / T2_W, nty = (g.jmax + ty - 1) / ty;
+    Tend3Args<TF> t{};
+    t.m = a; if (sc) t.sc = *sc;
+    t.kchunk = pick_kchunk_waves(ntx * nty, g.kmax, c->num_sms, 2);
+    t.prefetch = c->prefetch;
+    dim3 grid(ntx, nty, (g.kmax + t.kchunk - 1) / t.kchunk);
+    const size_t smem = mom3_smem(sizeof(TF), t.kchunk, ty, nsc);
+    CUtensorMap tu, tv, tw, te, ts, tut, tvt, twt, tst;
+    const int by = ty + 2 * T2_H;
+    if (!make_field_tmap<TF>(&tu, a.u, g, T2_PX, by) || !make_field_tmap<TF>(&tv, a.v, g, T2_PX, by) ||
+        !make_field_tmap<TF>(&tw, a.w, g, T2_PX, by) || !make_field_tmap<TF>(&te, a.evisc, g, T2_PX, by) ||
+        !make_field_tmap<TF>(&ts, sc ? (const void*)sc->s : (const void*)a.u, g, T2_PX, by) ||
+        !make_field_tmap<TF>(&tut, a.ut, g, T2_W + 2, ty) || !make_field_tmap<TF>(&tvt, a.vt, g, T2_W + 2, ty) ||
+        !make_field_tmap<TF>(&twt, a.wt, g, T2_W + 2, ty) || !make_field_tmap<TF>(&tst, sc ? (const void*)sc->st : (const void*)a.ut, g, T2_W + 2, ty))
+    { c->err = "cuTensorMapEncodeTiled failed"; return MHH_E_CUDA; }
+#define M3(S, B, N, Y) do { \
+        static size_t attr_smem = 0; \
+        if (attr_smem < smem) { CUDA_TRY(c, cudaFuncSetAttribute(mom3_kernel<TF, S, B, N, Y>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; } \
+        mom3_kernel<TF, S, B, N, Y><<<grid, 32 * (3 + N) * Y, smem, c->stream>>>(tu, tv, tw, te, ts, tut, tvt, twt, tst, t, g); } while (0)
+#define M3Y(S, B, N) do { if (ty == 3) M3(S, B, N, 3); else if (ty == 5) M3(S, B, N, 5); else M3(S, B, N, 4); } while (0)
+    if (nsc)
+    {
+        if (surface && buoy) M3Y(true, true, 1);
+        else if (surface) M3Y(true, false, 1);
+        else if (buoy) M3Y(false, true, 1);
+        else M3Y(false, false, 1);
+    }
+    else
+    {
+        if (surface && buoy) M3Y(true, true, 0);
+        else if (surface) M3Y(true, false, 0);
+        else if (buoy) M3Y(false, true, 0);
+        else M3Y(false, false, 0);
+    }
+#undef M3Y
+#undef M3
+    KCHECKN(c, "mom3_kernel");
     return MHH_OK;
 }
 
@@ -607,10 +666,22 @@ int tend_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, bool adv, 
     dim3 gr = c->grd_interior(), b = c->blk();
 #define LAUNCH_MOM(A, D, S, B) tend_uvw_kernel<TF, A, D, S, B><<<gr, b, 0, c->stream>>>(a, g)
     const bool tiles = adv && diff && g.igc >= TILE_H && g.jgc >= TILE_H && !c->force_plain;
+    int first_scalar = 0;       // scalars [0, first_scalar) were handled by the fused momentum kernel
     if (tiles)
     {
-        const bool tma = !c->no_tma && sizeof(TF) == 8 && tma_ok<TF>(g, {a.u, a.v, a.w, a.evisc});
-        if (tma) rc = mom2_launch<TF>(c, a, surface, buoy);
+        const bool tma = !c->no_tma && sizeof(TF) == 8 && tma_ok<TF>(g, {a.u, a.v, a.w, a.evisc, a.ut, a.vt, a.wt, buoy ? (const void*)a.th : (const void*)a.u});
+        if (tma && c->mom_variant == 3)
+        {
+            // scalar 0 rides along as the fourth warp group when its arrays qualify for TMA too
+            ScalArgs<TF> s0{};
+            // measured on B200 fp64 (512^3): fused 8.4 ms vs 4.3 + 2.9 ms separately -- these kernels are bound by the
+            // fp64 pipe and latency, not by HBM, so saving the scalar's re-read of u, v, w, evisc does not pay; opt-in.
+            bool fuse = f->ns > 0 && c->fuse_scalar;
+            if (fuse) { s0 = scal_args<TF>(c, f, prm, 0); fuse = tma_ok<TF>(g, {s0.s, s0.st}); }
+            rc = mom3_launch<TF>(c, a, fuse ? &s0 : nullptr, surface, buoy);
+            if (fuse) first_scalar = 1;
+        }
+        else if (tma) rc = mom2_launch<TF>(c, a, surface, buoy);
         else rc = mom_tile_launch<TF>(c, a, surface, buoy);
         if (rc != MHH_OK) return rc;
     }
@@ -624,7 +695,7 @@ int tend_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, bool adv, 
     else { c->err = "tend_impl: nothing to do"; return MHH_E_INVALID; }
 #undef LAUNCH_MOM
     if (!tiles) KCHECKN(c, "tend_uvw_kernel");
-    for (int n = 0; n < f->ns; ++n)
+    for (int n = first_scalar; n < f->ns; ++n)
     {
         const ScalArgs<TF> s = scal_args<TF>(c, f, prm, n);
         if (tiles)

@@ -38,8 +38,9 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
     unsigned ok;
     do
     {
-        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        // the suspend-time hint lets a waiting warp sleep instead of spinning in the issue slots of the working warps
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
     } while (!ok);
 }
 
@@ -48,6 +49,13 @@ __device__ __forceinline__ void tma_load_3d(unsigned smem_dst, const CUtensorMap
 {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
                  :: "r"(smem_dst), "l"(reinterpret_cast<unsigned long long>(tmap)), "r"(bar), "r"(x), "r"(y), "r"(z) : "memory");
+}
+
+// L2 prefetch of a box (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* tmap, int x, int y, int z)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];\n"
+                 :: "l"(reinterpret_cast<unsigned long long>(tmap)), "r"(x), "r"(y), "r"(z) : "memory");
 }
 
 template <typename TF> struct V2T;
@@ -71,6 +79,7 @@ struct Mom2Args
 {
     MomArgs<TF> m;
     int kchunk;
+    int prefetch;      // L2 prefetch distance in levels (0 = off)
 };
 
 // shared-memory layout: [0,128) mbarriers | planes [field][ring] | level profiles
@@ -81,6 +90,8 @@ template <typename TF, bool SURFACE, bool BUOY, int TY>
 __global__ void __launch_bounds__(32 * TY, (TY <= 8) ? 2 : 1)
 mom2_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_v,
             const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_e,
+            const __grid_constant__ CUtensorMap tm_ut, const __grid_constant__ CUtensorMap tm_vt,
+            const __grid_constant__ CUtensorMap tm_wt, const __grid_constant__ CUtensorMap tm_th,
             const Mom2Args<TF> args, const GridDev<TF> g)
 {
     typedef typename V2T<TF>::type V2;
@@ -176,7 +187,25 @@ mom2_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
         const int s1 = (s0 == T2_RING - 1) ? 0 : s0 + 1;
         const int s2 = (s1 == T2_RING - 1) ? 0 : s1 + 1;
         __syncthreads();                              // everyone is done with plane k-1 (slot s2)
-        if (threadIdx.x == 0 && k + 2 <= kc1) issue(s2, k + 2);   // only planes that will be consumed
+        if (threadIdx.x == 0)
+        {
+            if (k + 2 <= kc1) issue(s2, k + 2);   // only planes that will be consumed
+            // pull what the per-thread loads of the NEXT iterations touch into L2: the leading window levels of
+            // u, v, w (also the first DRAM touch of the planes staged three iterations later), the tendencies, th
+            if (args.prefetch)
+            {
+                const int pu = k + 1 + args.prefetch + 3;
+                if (pu < g.kcells) { tma_prefetch_3d(&tm_u, gi0, gj0, pu); tma_prefetch_3d(&tm_v, gi0, gj0, pu); }
+                if (pu + 1 < g.kcells) tma_prefetch_3d(&tm_w, gi0, gj0, pu + 1);
+                const int pt = k + args.prefetch;
+                if (pt + 1 <= kc1)
+                {
+                    tma_prefetch_3d(&tm_ut, gi0 + 2, gj0 + T2_H, pt); tma_prefetch_3d(&tm_vt, gi0 + 2, gj0 + T2_H, pt);
+                    tma_prefetch_3d(&tm_wt, gi0 + 2, gj0 + T2_H, pt + 1);
+                    if (BUOY) tma_prefetch_3d(&tm_th, gi0 + 2, gj0 + T2_H, pt + 1);
+                }
+            }
+        }
 
         const bool store = (k >= kc0);
         const int f = k + 1;

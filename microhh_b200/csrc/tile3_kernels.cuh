@@ -1,0 +1,488 @@
+// mhhb200 -- warp-specialised version of the TMA tile kernel for the fused momentum tendencies.
+//
+// Same tile geometry, shared-memory planes and arithmetic as mom2_kernel (tile2_kernels.cuh), but the
+// three velocity components are computed by three different groups of warps of the same CTA, all
+// reading the same TMA-staged planes:
+//     warps [0, TY)      u tendency   (row ty = warp)
+//     warps [TY, 2TY)    v tendency
+//     warps [2TY, 3TY)   w tendency (+ buoyancy)
+//     warps [3TY, 4TY)   first scalar (advec_s + diff_c), optional
+// A thread therefore carries the register window and the carried vertical flux of ONE component only
+// (about a third of the persistent registers), which lets 3x more warps be resident per tile; the
+// per-level block barrier is gone: a ring slot is filled by TMA (full mbarrier) and the LAST warp that
+// is done with a slot (shared-memory counter) re-issues the TMA for it, so nobody waits for a producer
+// and warps drift apart by up to RING-2 levels.  The warp count is kept a multiple of 4 (one register
+// file per SM sub-partition: a 17th warp would cut everybody's register budget from 128 to 96).
+#pragma once
+#include "tile2_kernels.cuh"
+
+namespace mhh {
+
+__device__ __forceinline__ void mbar_arrive(unsigned bar)
+{ asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory"); }
+
+constexpr int T3_RING = 4;
+
+inline size_t mom3_smem(size_t elem, int kchunk, int ty, int nsc)
+{ return 128 + ((size_t)(4 + nsc) * T3_RING * t2_plane(ty, (int)elem) + (size_t)8 * (kchunk + 3)) * elem + 128; }
+
+// the first prognostic scalar rides along as a fourth warp group (NSC = 1): advec_s + diff_c on the same planes
+template <typename TF>
+struct Tend3Args
+{
+    MomArgs<TF> m;
+    ScalArgs<TF> sc;
+    int kchunk;
+    int prefetch;
+};
+
+template <typename TF, bool SURFACE, bool BUOY, int NSC, int TY>
+__global__ void __launch_bounds__(32 * (3 + NSC) * TY, 1)
+mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_v,
+            const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_e,
+            const __grid_constant__ CUtensorMap tm_s,
+            const __grid_constant__ CUtensorMap tm_ut, const __grid_constant__ CUtensorMap tm_vt,
+            const __grid_constant__ CUtensorMap tm_wt, const __grid_constant__ CUtensorMap tm_st,
+            const Tend3Args<TF> args, const GridDev<TF> g)
+{
+    typedef typename V2T<TF>::type V2;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* sbase = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(sbase);     // full[RING], empty[RING]
+    TF* sm = reinterpret_cast<TF*>(sbase + 128);
+    constexpr int RING = T3_RING;
+    constexpr int PLANE = t2_plane(TY, (int)sizeof(TF)), P = T2_PX, NT = 32 * (3 + NSC) * TY, NCW = (3 + NSC) * TY;
+    constexpr int NF = 4 + NSC;
+    constexpr unsigned PLANE_BYTES = PLANE * sizeof(TF), BOX_BYTES = t2_box_bytes(TY, (int)sizeof(TF));
+
+    const MomArgs<TF>& a = args.m;
+    const int warp = threadIdx.x >> 5, tx = threadIdx.x & 31;
+    // NSC = 1: four groups, group = warp % 4.  Warps are dealt round-robin to the four SM sub-partitions, so each
+    // sub-partition then runs ONE component's loop and its instruction cache holds one code path instead of four
+    // (measured: 14 % of the stall samples were instruction fetches with group = warp / TY).
+    const int comp = NSC ? (warp & 3) : warp / TY, ty = NSC ? (warp >> 2) : warp - (warp / TY) * TY;
+    const int i = g.istart + blockIdx.x * T2_W + 2 * tx;
+    const int j = g.jstart + blockIdx.y * TY + ty;
+    const int gi0 = g.istart + blockIdx.x * T2_W - T2_HL;
+    const int gj0 = g.jstart + blockIdx.y * TY - T2_H;
+    const bool active = (i + 1 < g.iend) && (j < g.jend);
+    const int ks = g.kstart, ke = g.kend;
+    const int kc0 = ks + blockIdx.z * args.kchunk;
+    const int kc1 = min(ke, kc0 + args.kchunk);
+    const long long jj = g.icells, kk = g.ijcells;
+    const int ic = min(i, g.iend - 2), jc = min(j, g.jend - 1);
+    const long long ij = ic + jc * jj;
+    const int sidx = (ty + T2_H) * P + T2_HL + 2 * tx;
+    const TF dxi = g.dxi, dyi = g.dyi, visc = a.visc;
+    const TF q = TF(0.25);
+
+    const int k0 = kc0 - 1;
+    TF* prof = sm + NF * RING * PLANE;
+    const int nlev = args.kchunk + 3;
+    TF* p_rho = prof; TF* p_rhoh = prof + nlev; TF* p_rdzi = prof + 2 * nlev; TF* p_rdzhi = prof + 3 * nlev;
+    TF* p_dzhi = prof + 4 * nlev; TF* p_gth = prof + 5 * nlev; TF* p_thh = prof + 6 * nlev; TF* p_dzi = prof + 7 * nlev;
+    for (int t = threadIdx.x; t < nlev; t += NT)
+    {
+        const int lev = min(max(k0 + t, 0), g.kcells - 1);
+        const TF rho = g.rhoref[lev], rhoh = g.rhorefh[lev];
+        p_rho[t] = rho; p_rhoh[t] = rhoh;
+        p_rdzi[t] = g.dzi[lev] / rho;
+        p_rdzhi[t] = g.dzhi[lev] / rhoh;
+        p_dzhi[t] = g.dzhi[lev];
+        p_gth[t] = BUOY ? TF(GRAV) / g.threfh[lev] : TF(0);
+        p_thh[t] = BUOY ? g.threfh[lev] : TF(0);
+        p_dzi[t] = g.dzi[lev];
+    }
+    const unsigned full0 = smem_u32(bars);
+    int* cnt = reinterpret_cast<int*>(sbase + 64);      // per ring slot: consumer warps that are done with it
+    const unsigned pl0 = smem_u32(sm);
+    // TMA loads of level `lev` into ring slot `slot` (+ L2 prefetch of what the per-thread loads touch a little later)
+    auto issue = [&](int slot, int lev) {
+        const unsigned bar = full0 + 8 * slot;
+        mbar_expect_tx(bar, NF * BOX_BYTES);
+        tma_load_3d(pl0 + (0 * RING + slot) * PLANE_BYTES, &tm_u, bar, gi0, gj0, lev);
+        tma_load_3d(pl0 + (1 * RING + slot) * PLANE_BYTES, &tm_v, bar, gi0, gj0, lev);
+        tma_load_3d(pl0 + (2 * RING + slot) * PLANE_BYTES, &tm_w, bar, gi0, gj0, lev);
+        tma_load_3d(pl0 + (3 * RING + slot) * PLANE_BYTES, &tm_e, bar, gi0, gj0, lev);
+        if (NSC) tma_load_3d(pl0 + (4 * RING + slot) * PLANE_BYTES, &tm_s, bar, gi0, gj0, lev);
+        if (args.prefetch)
+        {
+            const int pu = lev + 1 + args.prefetch;           // leading window levels (first DRAM touch of later planes)
+            if (pu < g.kcells) { tma_prefetch_3d(&tm_u, gi0, gj0, pu); tma_prefetch_3d(&tm_v, gi0, gj0, pu); if (NSC) tma_prefetch_3d(&tm_s, gi0, gj0, pu); }
+            if (pu + 1 < g.kcells) tma_prefetch_3d(&tm_w, gi0, gj0, pu + 1);
+            const int pt = lev - 2 + args.prefetch;           // tendencies that are read-modify-written soon
+            if (pt >= kc0 && pt < kc1)
+            {
+                tma_prefetch_3d(&tm_ut, gi0 + 2, gj0 + T2_H, pt); tma_prefetch_3d(&tm_vt, gi0 + 2, gj0 + T2_H, pt);
+                tma_prefetch_3d(&tm_wt, gi0 + 2, gj0 + T2_H, pt + 1);
+                if (NSC) tma_prefetch_3d(&tm_st, gi0 + 2, gj0 + T2_H, pt);
+            }
+        }
+    };
+    if (threadIdx.x == 0)
+    {
+        for (int s = 0; s < RING; ++s) { mbar_init(full0 + 8 * s, 1); cnt[s] = 0; }
+        mbar_fence_init();
+    }
+    __syncthreads();            // the only block-wide barrier
+    if (threadIdx.x == 0)
+        for (int n = 0; n < RING && k0 + n <= kc1; ++n) issue(n, k0 + n);
+
+    // ================================================================== consumer warps
+    auto colload = [&](const TF* __restrict__ fld, int lev, int c) -> TF {
+        return (lev >= 0 && lev < g.kcells) ? fld[ij + c + (long long)lev * kk] : TF(0);
+    };
+    auto LD2 = [](const TF* p) -> V2 { return *reinterpret_cast<const V2*>(p); };
+    auto row10 = [&](const TF* p, TF (&x)[12]) {
+#pragma unroll
+        for (int n = 0; n < 6; ++n) { const V2 t = LD2(p + 2 * n - 5); x[2 * n] = t.x; x[2 * n + 1] = t.y; } };
+    auto row6 = [&](const TF* p, TF (&x)[8]) {
+#pragma unroll
+        for (int n = 0; n < 4; ++n) { const V2 t = LD2(p + 2 * n - 3); x[2 * n] = t.x; x[2 * n + 1] = t.y; } };
+    auto row4 = [&](const TF* p, TF (&x)[6]) {
+#pragma unroll
+        for (int n = 0; n < 3; ++n) { const V2 t = LD2(p + 2 * n - 1); x[2 * n] = t.x; x[2 * n + 1] = t.y; } };
+    // row3: x[-1..2] -> array index n+1: two aligned vector loads (shared-memory bandwidth co-limits this kernel)
+    auto row3 = [&](const TF* p, TF (&x)[4]) {
+        const V2 t0 = LD2(p - 1), t1 = LD2(p + 1); x[0] = t0.x; x[1] = t0.y; x[2] = t1.x; x[3] = t1.y; };
+    auto col7 = [&](const TF* p, TF (&y)[7][2]) {
+#pragma unroll
+        for (int d = -3; d <= 3; ++d) { y[d + 3][0] = p[d * P]; y[d + 3][1] = p[d * P + 1]; } };
+    auto pair = [&](const TF* p, TF (&x)[2]) { x[0] = p[0]; x[1] = p[1]; };
+    auto psum = [&](const TF (&e)[4], TF (&sum)[3]) {
+#pragma unroll
+        for (int m = 0; m < 3; ++m) sum[m] = e[m] + e[m + 1]; };
+    auto plane = [&](int fld, int slot) -> const TF* { return sm + (fld * RING + slot) * PLANE + sidx; };
+    // wait for plane (k+1), hand back the slots of planes k and k+1
+    auto acquire = [&](int k, int& s0, int& s1) {
+        const int n = k - k0;
+        s0 = n % RING; s1 = (n + 1) % RING;
+        if (n == 0) mbar_wait(full0, 0);
+        mbar_wait(full0 + 8 * s1, ((n + 1) / RING) & 1);
+    };
+    // done with plane k (slot s0): the LAST warp to get here refills the slot with plane k+RING -- nobody waits
+    auto release = [&](int k, int s0) {
+        __syncwarp();
+        if (tx == 0)
+        {
+            // No fence here: every value read from the slot has been consumed by arithmetic that precedes this point,
+            // and a __threadfence_block() would also wait for the global stores just issued (measured: +28 % kernel time).
+            unsigned prev;
+            asm volatile("atom.shared.add.u32 %0, [%1], 1;\n" : "=r"(prev) : "r"(smem_u32(&cnt[s0])) : "memory");
+            if (prev == NCW - 1)
+            {
+                cnt[s0] = 0;
+                if (k + RING <= kc1) issue(s0, k + RING);
+            }
+        }
+    };
+
+#define X10(a, n) a[(n) + 5]
+#define X6(a, n) a[(n) + 1]
+#define X4(a, n) a[(n) + 1]
+    if (comp == 0)
+    {
+        // ------------------------------------------------------------------ u
+        TF ua[2], ub[2], uc[2], ud[2], gu[2] = {0, 0};
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+        { ua[c] = colload(a.u, k0 - 2, c); ub[c] = colload(a.u, k0 - 1, c); uc[c] = colload(a.u, k0 + 2, c); ud[c] = colload(a.u, k0 + 3, c); }
+        for (int k = k0; k < kc1; ++k)
+        {
+            const int f = k + 1, pl = k - k0;
+            const bool st = (k >= kc0) && active;
+            const long long o_k = ij + (long long)k * kk;
+            const TF un0 = colload(a.u, k + 4, 0), un1 = colload(a.u, k + 4, 1);
+            TF old0 = 0, old1 = 0;
+            if (st) { old0 = a.ut[o_k]; old1 = a.ut[o_k + 1]; }
+            const TF rhoh_f = p_rhoh[pl + 1], rdzi_k = p_rdzi[pl], dzhi_f = p_dzhi[pl + 1];
+            const int of = vorder(f, ks, ke);
+            int s0, s1;
+            acquire(k, s0, s1);
+            const TF* __restrict__ U0 = plane(0, s0); const TF* __restrict__ U1 = plane(0, s1);
+            const TF* __restrict__ V0 = plane(1, s0); const TF* __restrict__ W1 = plane(2, s1);
+            const TF* __restrict__ E0 = plane(3, s0); const TF* __restrict__ E1 = plane(3, s1);
+            TF ux[12], w6[4], e0[4], e1[4], s0r[3], s1r[3], U1R[2];
+            row10(U0, ux); row3(W1, w6); row3(E0, e0); row3(E1, e1); pair(U1, U1R);
+            psum(e0, s0r); psum(e1, s1r);
+            TF fx[3], dx_[3];
+#pragma unroll
+            for (int m = 0; m < 3; ++m)
+            {
+                fx[m] = flux65(interp2(X10(ux, m - 1), X10(ux, m)), X10(ux, m - 3), X10(ux, m - 2), X10(ux, m - 1), X10(ux, m), X10(ux, m + 1), X10(ux, m + 2));
+                dx_[m] = (X6(e0, m - 1) + visc) * (X10(ux, m) - X10(ux, m - 1)) * dxi;
+            }
+            TF gt[2];
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+            {
+                const TF uk = X10(ux, c), uk1 = U1R[c];
+                const TF ft_a = rhoh_f * vflux_col<TF>(of, interp2(X6(w6, c - 1), X6(w6, c)), ua[c], ub[c], uk, uk1, uc[c], ud[c]);
+                TF ft_d;
+                if (SURFACE && f == ks) ft_d = -rhoh_f * a.u_fluxbot[ij + c];
+                else if (SURFACE && f == ke) ft_d = -rhoh_f * a.u_fluxtop[ij + c];
+                else
+                {
+                    const TF evisct = q * (s0r[c] + s1r[c]) + visc;
+                    ft_d = rhoh_f * evisct * ((uk1 - uk) * dzhi_f + (X6(w6, c) - X6(w6, c - 1)) * dxi);
+                }
+                gt[c] = ft_d - ft_a;
+            }
+            if (st)
+            {
+                TF uy[7][2], v6[4], vp6[4], em[4], ep[4], s0m[3], s0p[3];
+                col7(U0, uy); row3(V0, v6); row3(V0 + P, vp6); row3(E0 - P, em); row3(E0 + P, ep);
+                psum(em, s0m); psum(ep, s0p);
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+                {
+                    const TF fn = flux65(interp2(X6(vp6, c - 1), X6(vp6, c)), uy[1][c], uy[2][c], uy[3][c], uy[4][c], uy[5][c], uy[6][c]);
+                    const TF fs = flux65(interp2(X6(v6, c - 1), X6(v6, c)), uy[0][c], uy[1][c], uy[2][c], uy[3][c], uy[4][c], uy[5][c]);
+                    const TF eviscn = q * (s0r[c] + s0p[c]) + visc;
+                    const TF eviscs = q * (s0m[c] + s0r[c]) + visc;
+                    const TF d = (dx_[c + 1] - dx_[c]) * TF(2.) * dxi
+                               + (eviscn * ((uy[4][c] - uy[3][c]) * dyi + (X6(vp6, c) - X6(vp6, c - 1)) * dxi)
+                                - eviscs * ((uy[3][c] - uy[2][c]) * dyi + (X6(v6, c) - X6(v6, c - 1)) * dxi)) * dyi;
+                    const TF tu = -(fx[c + 1] - fx[c]) * dxi - (fn - fs) * dyi + d + (gt[c] - gu[c]) * rdzi_k;
+                    a.ut[o_k + c] = (c == 0 ? old0 : old1) + tu;
+                }
+            }
+            release(k, s0);
+            gu[0] = gt[0]; gu[1] = gt[1];
+            ua[0] = ub[0]; ua[1] = ub[1]; ub[0] = X10(ux, 0); ub[1] = X10(ux, 1);
+            uc[0] = ud[0]; uc[1] = ud[1]; ud[0] = un0; ud[1] = un1;
+        }
+    }
+    else if (comp == 1)
+    {
+        // ------------------------------------------------------------------ v
+        TF va[2], vb[2], vc[2], vd[2], gv[2] = {0, 0};
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+        { va[c] = colload(a.v, k0 - 2, c); vb[c] = colload(a.v, k0 - 1, c); vc[c] = colload(a.v, k0 + 2, c); vd[c] = colload(a.v, k0 + 3, c); }
+        for (int k = k0; k < kc1; ++k)
+        {
+            const int f = k + 1, pl = k - k0;
+            const bool st = (k >= kc0) && active;
+            const long long o_k = ij + (long long)k * kk;
+            const TF vn0 = colload(a.v, k + 4, 0), vn1 = colload(a.v, k + 4, 1);
+            TF old0 = 0, old1 = 0;
+            if (st) { old0 = a.vt[o_k]; old1 = a.vt[o_k + 1]; }
+            const TF rhoh_f = p_rhoh[pl + 1], rdzi_k = p_rdzi[pl], dzhi_f = p_dzhi[pl + 1];
+            const int of = vorder(f, ks, ke);
+            int s0, s1;
+            acquire(k, s0, s1);
+            const TF* __restrict__ U0 = plane(0, s0);
+            const TF* __restrict__ V0 = plane(1, s0); const TF* __restrict__ V1 = plane(1, s1);
+            const TF* __restrict__ W1 = plane(2, s1);
+            const TF* __restrict__ E0 = plane(3, s0); const TF* __restrict__ E1 = plane(3, s1);
+            TF vx[12], e0[4], em[4], V1R[2], W1R[2], W1M[2], E1R[2], E1M[2];
+            row10(V0, vx); row3(E0, e0); row3(E0 - P, em);
+            pair(V1, V1R); pair(W1, W1R); pair(W1 - P, W1M); pair(E1, E1R); pair(E1 - P, E1M);
+            TF gt[2];
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+            {
+                const TF vk = X10(vx, c), vk1 = V1R[c];
+                const TF ft_a = rhoh_f * vflux_col<TF>(of, interp2(W1M[c], W1R[c]), va[c], vb[c], vk, vk1, vc[c], vd[c]);
+                TF ft_d;
+                if (SURFACE && f == ks) ft_d = -rhoh_f * a.v_fluxbot[ij + c];
+                else if (SURFACE && f == ke) ft_d = -rhoh_f * a.v_fluxtop[ij + c];
+                else
+                {
+                    const TF evisct = q * ((X6(em, c) + X6(e0, c)) + (E1M[c] + E1R[c])) + visc;
+                    ft_d = rhoh_f * evisct * ((vk1 - vk) * dzhi_f + (W1R[c] - W1M[c]) * dyi);
+                }
+                gt[c] = ft_d - ft_a;
+            }
+            if (st)
+            {
+                TF u4[4], um4[4], vy[7][2], s0r[3], s0m[3];
+                row3(U0, u4); row3(U0 - P, um4); col7(V0, vy);
+                psum(e0, s0r); psum(em, s0m);
+                TF fx[3], dx_[3];
+#pragma unroll
+                for (int m = 0; m < 3; ++m)
+                {
+                    fx[m] = flux65(interp2(X4(um4, m), X4(u4, m)), X10(vx, m - 3), X10(vx, m - 2), X10(vx, m - 1), X10(vx, m), X10(vx, m + 1), X10(vx, m + 2));
+                    const TF eviscc = q * (s0m[m] + s0r[m]) + visc;
+                    dx_[m] = eviscc * ((X10(vx, m) - X10(vx, m - 1)) * dxi + (X4(u4, m) - X4(um4, m)) * dyi);
+                }
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+                {
+                    const TF fn = flux65(interp2(vy[3][c], vy[4][c]), vy[1][c], vy[2][c], vy[3][c], vy[4][c], vy[5][c], vy[6][c]);
+                    const TF fs = flux65(interp2(vy[2][c], vy[3][c]), vy[0][c], vy[1][c], vy[2][c], vy[3][c], vy[4][c], vy[5][c]);
+                    const TF d = (dx_[c + 1] - dx_[c]) * dxi
+                               + ((X6(e0, c) + visc) * (vy[4][c] - vy[3][c]) * dyi - (X6(em, c) + visc) * (vy[3][c] - vy[2][c]) * dyi) * TF(2.) * dyi;
+                    const TF tv = -(fx[c + 1] - fx[c]) * dxi - (fn - fs) * dyi + d + (gt[c] - gv[c]) * rdzi_k;
+                    a.vt[o_k + c] = (c == 0 ? old0 : old1) + tv;
+                }
+            }
+            release(k, s0);
+            gv[0] = gt[0]; gv[1] = gt[1];
+            va[0] = vb[0]; va[1] = vb[1]; vb[0] = X10(vx, 0); vb[1] = X10(vx, 1);
+            vc[0] = vd[0]; vc[1] = vd[1]; vd[0] = vn0; vd[1] = vn1;
+        }
+    }
+    else if (NSC == 1 && comp == 3)
+    {
+        // ------------------------------------------------------------------ scalar 0 (advec_s + diff_c)
+        const ScalArgs<TF>& sa_ = args.sc;
+        const TF h = TF(0.5), tPr_i = TF(1) / sa_.tPr, svisc = sa_.visc;
+        TF sa[2], sb[2], sc[2], sd[2], gs[2] = {0, 0};
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+        { sa[c] = colload(sa_.s, k0 - 2, c); sb[c] = colload(sa_.s, k0 - 1, c); sc[c] = colload(sa_.s, k0 + 2, c); sd[c] = colload(sa_.s, k0 + 3, c); }
+        for (int k = k0; k < kc1; ++k)
+        {
+            const int f = k + 1, pl = k - k0;
+            const bool st = (k >= kc0) && active;
+            const long long o_k = ij + (long long)k * kk;
+            const TF sn0 = colload(sa_.s, k + 4, 0), sn1 = colload(sa_.s, k + 4, 1);
+            TF old0 = 0, old1 = 0;
+            if (st) { old0 = sa_.st[o_k]; old1 = sa_.st[o_k + 1]; }
+            const TF rhoh_f = p_rhoh[pl + 1], rdzi_k = p_rdzi[pl], dzhi_f = p_dzhi[pl + 1];
+            const int of = vorder(f, ks, ke);
+            int s0, s1;
+            acquire(k, s0, s1);
+            const TF* __restrict__ U0 = plane(0, s0); const TF* __restrict__ V0 = plane(1, s0);
+            const TF* __restrict__ W1 = plane(2, s1);
+            const TF* __restrict__ E0 = plane(3, s0); const TF* __restrict__ E1 = plane(3, s1);
+            const TF* __restrict__ S0 = plane(4, s0); const TF* __restrict__ S1 = plane(4, s1);
+            TF sx[12], S1R[2], W1R[2], E1R[2], e0[4];
+            row10(S0, sx); pair(S1, S1R); pair(W1, W1R); pair(E1, E1R); row3(E0, e0);
+            TF gt[2];
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+            {
+                const TF sk = X10(sx, c), sk1 = S1R[c];
+                const TF ft_a = rhoh_f * vflux_col<TF>(of, W1R[c], sa[c], sb[c], sk, sk1, sc[c], sd[c]);
+                TF ft_d;
+                if (SURFACE && f == ks) ft_d = -rhoh_f * sa_.fluxbot[ij + c];
+                else if (SURFACE && f == ke) ft_d = -rhoh_f * sa_.fluxtop[ij + c];
+                else
+                {
+                    const TF evisct = h * (X6(e0, c) + E1R[c]) * tPr_i + svisc;
+                    ft_d = rhoh_f * evisct * (sk1 - sk) * dzhi_f;
+                }
+                gt[c] = ft_d - ft_a;
+            }
+            if (st)
+            {
+                TF u4[4], sy[7][2], V0R[2], V0P[2], EM0[2], EP0[2];
+                row3(U0, u4); col7(S0, sy); pair(V0, V0R); pair(V0 + P, V0P); pair(E0 - P, EM0); pair(E0 + P, EP0);
+                TF fx[3], dx_[3];
+#pragma unroll
+                for (int m = 0; m < 3; ++m)
+                {
+                    fx[m] = flux65(X4(u4, m), X10(sx, m - 3), X10(sx, m - 2), X10(sx, m - 1), X10(sx, m), X10(sx, m + 1), X10(sx, m + 2));
+                    const TF eviscx = h * (X6(e0, m - 1) + X6(e0, m)) * tPr_i + svisc;
+                    dx_[m] = eviscx * (X10(sx, m) - X10(sx, m - 1));
+                }
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+                {
+                    const TF fn = flux65(V0P[c], sy[1][c], sy[2][c], sy[3][c], sy[4][c], sy[5][c], sy[6][c]);
+                    const TF fs = flux65(V0R[c], sy[0][c], sy[1][c], sy[2][c], sy[3][c], sy[4][c], sy[5][c]);
+                    const TF eviscn = h * (X6(e0, c) + EP0[c]) * tPr_i + svisc;
+                    const TF eviscs = h * (EM0[c] + X6(e0, c)) * tPr_i + svisc;
+                    const TF d = (dx_[c + 1] - dx_[c]) * sa_.dxidxi
+                               + (eviscn * (sy[4][c] - sy[3][c]) - eviscs * (sy[3][c] - sy[2][c])) * sa_.dyidyi;
+                    const TF ts = -(fx[c + 1] - fx[c]) * dxi - (fn - fs) * dyi + d + (gt[c] - gs[c]) * rdzi_k;
+                    sa_.st[o_k + c] = (c == 0 ? old0 : old1) + ts;
+                }
+            }
+            release(k, s0);
+            gs[0] = gt[0]; gs[1] = gt[1];
+            sa[0] = sb[0]; sa[1] = sb[1]; sb[0] = X10(sx, 0); sb[1] = X10(sx, 1);
+            sc[0] = sd[0]; sc[1] = sd[1]; sd[0] = sn0; sd[1] = sn1;
+        }
+    }
+    else
+    {
+        // ------------------------------------------------------------------ w at face f = k+1 (+ buoyancy)
+        TF wa[2], wb[2], we[2], wc[2], wd[2], gw[2] = {0, 0}, thc[2] = {TF(0), TF(0)};
+        if (BUOY && !NSC) { thc[0] = colload(a.th, k0, 0); thc[1] = colload(a.th, k0, 1); }
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+        {
+            wa[c] = colload(a.w, k0 - 1, c); wb[c] = colload(a.w, k0, c); we[c] = colload(a.w, k0 + 2, c);
+            wc[c] = colload(a.w, k0 + 3, c); wd[c] = colload(a.w, k0 + 4, c);
+        }
+        for (int k = k0; k < kc1; ++k)
+        {
+            const int f = k + 1, pl = k - k0;
+            const bool st = (k >= kc0) && active && f < ke;
+            const long long o_f = ij + (long long)f * kk;
+            const TF wn0 = colload(a.w, k + 5, 0), wn1 = colload(a.w, k + 5, 1);
+            TF thn0 = TF(0), thn1 = TF(0);          // th[k+1] straight from global when the scalar is not staged (issued early)
+            if (BUOY && !NSC) { thn0 = colload(a.th, k + 1, 0); thn1 = colload(a.th, k + 1, 1); }
+            TF old0 = 0, old1 = 0;
+            if (st) { old0 = a.wt[o_f]; old1 = a.wt[o_f + 1]; }
+            const int oc = vorder(f, ks - 1, ke);
+            const TF rho_c = p_rho[pl + 1], dzi_c = p_dzi[pl + 1], rdzhi_f = p_rdzhi[pl + 1], dzhi_f = p_dzhi[pl + 1];
+            int s0, s1;
+            acquire(k, s0, s1);
+            const TF* __restrict__ U0 = plane(0, s0); const TF* __restrict__ U1 = plane(0, s1);
+            const TF* __restrict__ V0 = plane(1, s0); const TF* __restrict__ V1 = plane(1, s1);
+            const TF* __restrict__ W1 = plane(2, s1);
+            const TF* __restrict__ E0 = plane(3, s0); const TF* __restrict__ E1 = plane(3, s1);
+            TF wx[12], E1R[2], thk[2] = {TF(0), TF(0)}, th1[2] = {TF(0), TF(0)};
+            row10(W1, wx); pair(E1, E1R);
+            if (BUOY && NSC) { pair(plane(4, s0), thk); pair(plane(4, s1), th1); }       // th rides in the scalar planes
+            else if (BUOY) { thk[0] = thc[0]; thk[1] = thc[1]; th1[0] = thn0; th1[1] = thn1; thc[0] = thn0; thc[1] = thn1; }
+            TF gt[2];
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+            {
+                const TF wf = X10(wx, c);
+                const TF ft_a = rho_c * vflux_col<TF>(oc, interp2(wf, we[c]), wa[c], wb[c], wf, we[c], wc[c], wd[c]);
+                const TF ft_d = rho_c * (E1R[c] + visc) * (we[c] - wf) * dzi_c;
+                gt[c] = TF(2.) * ft_d - ft_a;
+            }
+            if (st)
+            {
+                TF u4[4], u14[4], e0[4], e16[4], s0r[3], s1r[3];
+                row3(U0, u4); row3(U1, u14); row3(E0, e0); row3(E1, e16);
+                psum(e0, s0r); psum(e16, s1r);
+                TF fx[3], dx_[3];
+#pragma unroll
+                for (int m = 0; m < 3; ++m)
+                {
+                    fx[m] = flux65(interp2(X4(u4, m), X4(u14, m)), X10(wx, m - 3), X10(wx, m - 2), X10(wx, m - 1), X10(wx, m), X10(wx, m + 1), X10(wx, m + 2));
+                    const TF eviscx = q * (s0r[m] + s1r[m]) + visc;
+                    dx_[m] = eviscx * ((X10(wx, m) - X10(wx, m - 1)) * dxi + (X4(u14, m) - X4(u4, m)) * dzhi_f);
+                }
+                TF wy[7][2], V0R[2], V0P[2], V1R[2], V1P[2], EM0[2], EP0[2], EM1[2], EP1[2];
+                col7(W1, wy);
+                pair(V0, V0R); pair(V0 + P, V0P); pair(V1, V1R); pair(V1 + P, V1P);
+                pair(E0 - P, EM0); pair(E0 + P, EP0); pair(E1 - P, EM1); pair(E1 + P, EP1);
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+                {
+                    const TF fn = flux65(interp2(V0P[c], V1P[c]), wy[1][c], wy[2][c], wy[3][c], wy[4][c], wy[5][c], wy[6][c]);
+                    const TF fs = flux65(interp2(V0R[c], V1R[c]), wy[0][c], wy[1][c], wy[2][c], wy[3][c], wy[4][c], wy[5][c]);
+                    const TF eviscn = q * ((X6(e0, c) + X6(e16, c)) + (EP0[c] + EP1[c])) + visc;
+                    const TF eviscs = q * ((EM0[c] + X6(e0, c)) + (EM1[c] + X6(e16, c))) + visc;
+                    TF tw = -(fx[c + 1] - fx[c]) * dxi - (fn - fs) * dyi
+                          + (dx_[c + 1] - dx_[c]) * dxi
+                          + (eviscn * ((wy[4][c] - wy[3][c]) * dyi + (V1P[c] - V0P[c]) * dzhi_f)
+                           - eviscs * ((wy[3][c] - wy[2][c]) * dyi + (V1R[c] - V0R[c]) * dzhi_f)) * dyi
+                          + (gt[c] - gw[c]) * rdzhi_f;
+                    if (BUOY) tw += p_gth[pl + 1] * (interp2(thk[c], th1[c]) - p_thh[pl + 1]);
+                    a.wt[o_f + c] = (c == 0 ? old0 : old1) + tw;
+                }
+            }
+            release(k, s0);
+            gw[0] = gt[0]; gw[1] = gt[1];
+            wa[0] = wb[0]; wa[1] = wb[1]; wb[0] = X10(wx, 0); wb[1] = X10(wx, 1);
+            we[0] = wc[0]; we[1] = wc[1]; wc[0] = wd[0]; wc[1] = wd[1]; wd[0] = wn0; wd[1] = wn1;
+        }
+    }
+#undef X10
+#undef X6
+#undef X4
+}
+
+} // namespace mhh
