@@ -35,9 +35,9 @@ struct mhh_ctx
     int tile_y = 8;             // MHH_TILE_Y=8|16: tile height of the z-marching kernels
     bool force_plain = false;   // MHH_FORCE_PLAIN=1: use the point-wise kernels everywhere (A/B comparisons)
     bool no_tma = false;        // MHH_NO_TMA=1: keep the cp.async tile kernels (A/B comparisons)
-    int tile3_y = 4;            // MHH_TILE3_Y: rows per CTA of the warp-specialised kernel (3*rows+1 warps)
+    int tile3_y = 0;            // MHH_TILE3_Y: rows per CTA of the warp-specialised kernel; 0 = 3 rows with the scalar group (13 warps), 4 without
     int tile2_y = 6;            // MHH_TILE2_Y: rows (= warps) per CTA of the TMA tile kernels
-    bool fuse_scalar = false;   // MHH_FUSE_SCALAR=1: scalar 0 as a fourth warp group of the momentum kernel
+    bool fuse_scalar = true;    // MHH_FUSE_SCALAR=0: keep scalar 0 out of the momentum kernel (A/B comparisons)
     int mom_variant = 3;        // MHH_MOM=2|3: 2 = all components per thread, 3 = warp-specialised by component
     int prefetch = 1;           // MHH_PREFETCH: L2 prefetch distance (levels) of the TMA tile kernels, 0 = off
     bool prof = false;
@@ -156,7 +156,7 @@ int create_impl(const mhh_grid_desc* d, int dtype, int device, mhh_ctx** out)
     { const char* e = getenv("MHH_FORCE_PLAIN"); c->force_plain = e && e[0] == '1'; }
     { const char* e = getenv("MHH_NO_TMA"); c->no_tma = e && e[0] == '1'; }
     { const char* e = getenv("MHH_TILE2_Y"); if (e) { int v = atoi(e); if (v == 4 || v == 6 || v == 8 || v == 12) c->tile2_y = v; } }
-    { const char* e = getenv("MHH_FUSE_SCALAR"); c->fuse_scalar = e && e[0] == '1'; }
+    { const char* e = getenv("MHH_FUSE_SCALAR"); if (e) c->fuse_scalar = e[0] == '1'; }
     { const char* e = getenv("MHH_MOM"); if (e && atoi(e) == 2) c->mom_variant = 2; }
     { const char* e = getenv("MHH_TILE3_Y"); if (e) { int v = atoi(e); if (v == 3 || v == 4 || v == 5) c->tile3_y = v; } }
     { const char* e = getenv("MHH_PREFETCH"); if (e) c->prefetch = std::max(0, std::min(8, atoi(e))); }
@@ -586,8 +586,8 @@ template <typename TF>
 int mom3_launch(Ctx<TF>* c, const MomArgs<TF>& a, const ScalArgs<TF>* sc, bool surface, bool buoy)
 {
     const GridDev<TF>& g = c->g;
-    const int ty = c->tile3_y;
     const int nsc = sc ? 1 : 0;
+    const int ty = c->tile3_y ? c->tile3_y : (nsc ? 3 : 4);
     const int ntx = (g.imax + T2_W - 1) / T2_W, nty = (g.jmax + ty - 1) / ty;
     Tend3Args<TF> t{};
     t.m = a; if (sc) t.sc = *sc;
@@ -606,7 +606,7 @@ int mom3_launch(Ctx<TF>* c, const MomArgs<TF>& a, const ScalArgs<TF>* sc, bool s
 #define M3(S, B, N, Y) do { \
         static size_t attr_smem = 0; \
         if (attr_smem < smem) { CUDA_TRY(c, cudaFuncSetAttribute(mom3_kernel<TF, S, B, N, Y>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; } \
-        mom3_kernel<TF, S, B, N, Y><<<grid, 32 * (3 + N) * Y, smem, c->stream>>>(tu, tv, tw, te, ts, tut, tvt, twt, tst, t, g); } while (0)
+        mom3_kernel<TF, S, B, N, Y><<<grid, 32 * ((3 + N) * Y + 1), smem, c->stream>>>(tu, tv, tw, te, ts, tut, tvt, twt, tst, t, g); } while (0)
 #define M3Y(S, B, N) do { if (ty == 3) M3(S, B, N, 3); else if (ty == 5) M3(S, B, N, 5); else M3(S, B, N, 4); } while (0)
     if (nsc)
     {
@@ -674,8 +674,7 @@ int tend_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, bool adv, 
         {
             // scalar 0 rides along as the fourth warp group when its arrays qualify for TMA too
             ScalArgs<TF> s0{};
-            // measured on B200 fp64 (512^3): fused 8.4 ms vs 4.3 + 2.9 ms separately -- these kernels are bound by the
-            // fp64 pipe and latency, not by HBM, so saving the scalar's re-read of u, v, w, evisc does not pay; opt-in.
+            // measured on B200 fp64 (512^3): 5.8 ms fused (3 rows, 13 warps) vs 4.3 + 2.9 ms as two kernels
             bool fuse = f->ns > 0 && c->fuse_scalar;
             if (fuse) { s0 = scal_args<TF>(c, f, prm, 0); fuse = tma_ok<TF>(g, {s0.s, s0.st}); }
             rc = mom3_launch<TF>(c, a, fuse ? &s0 : nullptr, surface, buoy);

@@ -7,12 +7,13 @@
 //     warps [TY, 2TY)    v tendency
 //     warps [2TY, 3TY)   w tendency (+ buoyancy)
 //     warps [3TY, 4TY)   first scalar (advec_s + diff_c), optional
+//     last warp          producer: one lane issues the TMA loads / L2 prefetches
 // A thread therefore carries the register window and the carried vertical flux of ONE component only
 // (about a third of the persistent registers), which lets 3x more warps be resident per tile; the
-// per-level block barrier is gone: a ring slot is filled by TMA (full mbarrier) and the LAST warp that
-// is done with a slot (shared-memory counter) re-issues the TMA for it, so nobody waits for a producer
-// and warps drift apart by up to RING-2 levels.  The warp count is kept a multiple of 4 (one register
-// file per SM sub-partition: a 17th warp would cut everybody's register budget from 128 to 96).
+// per-level block barrier is replaced by full/empty mbarriers per ring slot, so warps drift apart by up
+// to RING-2 levels instead of all waiting for the slowest one.  One extra warp is the TMA producer.
+// (Registers are allocated per SM sub-partition: with 17 warps one sub-partition holds 5 and everybody's
+// budget drops from 128 to 96 registers, so warp counts of 4n+1 are avoided where registers are tight.)
 #pragma once
 #include "tile2_kernels.cuh"
 
@@ -37,7 +38,7 @@ struct Tend3Args
 };
 
 template <typename TF, bool SURFACE, bool BUOY, int NSC, int TY>
-__global__ void __launch_bounds__(32 * (3 + NSC) * TY, 1)
+__global__ void __launch_bounds__(32 * ((3 + NSC) * TY + 1), 1)
 mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_v,
             const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_e,
             const __grid_constant__ CUtensorMap tm_s,
@@ -51,7 +52,7 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(sbase);     // full[RING], empty[RING]
     TF* sm = reinterpret_cast<TF*>(sbase + 128);
     constexpr int RING = T3_RING;
-    constexpr int PLANE = t2_plane(TY, (int)sizeof(TF)), P = T2_PX, NT = 32 * (3 + NSC) * TY, NCW = (3 + NSC) * TY;
+    constexpr int PLANE = t2_plane(TY, (int)sizeof(TF)), P = T2_PX, NT = 32 * ((3 + NSC) * TY + 1), NCW = (3 + NSC) * TY;
     constexpr int NF = 4 + NSC;
     constexpr unsigned PLANE_BYTES = PLANE * sizeof(TF), BOX_BYTES = t2_box_bytes(TY, (int)sizeof(TF));
 
@@ -93,40 +94,51 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
         p_thh[t] = BUOY ? g.threfh[lev] : TF(0);
         p_dzi[t] = g.dzi[lev];
     }
-    const unsigned full0 = smem_u32(bars);
-    int* cnt = reinterpret_cast<int*>(sbase + 64);      // per ring slot: consumer warps that are done with it
+    const unsigned full0 = smem_u32(bars), empty0 = full0 + 8 * RING;
     const unsigned pl0 = smem_u32(sm);
-    // TMA loads of level `lev` into ring slot `slot` (+ L2 prefetch of what the per-thread loads touch a little later)
-    auto issue = [&](int slot, int lev) {
-        const unsigned bar = full0 + 8 * slot;
-        mbar_expect_tx(bar, NF * BOX_BYTES);
-        tma_load_3d(pl0 + (0 * RING + slot) * PLANE_BYTES, &tm_u, bar, gi0, gj0, lev);
-        tma_load_3d(pl0 + (1 * RING + slot) * PLANE_BYTES, &tm_v, bar, gi0, gj0, lev);
-        tma_load_3d(pl0 + (2 * RING + slot) * PLANE_BYTES, &tm_w, bar, gi0, gj0, lev);
-        tma_load_3d(pl0 + (3 * RING + slot) * PLANE_BYTES, &tm_e, bar, gi0, gj0, lev);
-        if (NSC) tma_load_3d(pl0 + (4 * RING + slot) * PLANE_BYTES, &tm_s, bar, gi0, gj0, lev);
-        if (args.prefetch)
-        {
-            const int pu = lev + 1 + args.prefetch;           // leading window levels (first DRAM touch of later planes)
-            if (pu < g.kcells) { tma_prefetch_3d(&tm_u, gi0, gj0, pu); tma_prefetch_3d(&tm_v, gi0, gj0, pu); if (NSC) tma_prefetch_3d(&tm_s, gi0, gj0, pu); }
-            if (pu + 1 < g.kcells) tma_prefetch_3d(&tm_w, gi0, gj0, pu + 1);
-            const int pt = lev - 2 + args.prefetch;           // tendencies that are read-modify-written soon
-            if (pt >= kc0 && pt < kc1)
-            {
-                tma_prefetch_3d(&tm_ut, gi0 + 2, gj0 + T2_H, pt); tma_prefetch_3d(&tm_vt, gi0 + 2, gj0 + T2_H, pt);
-                tma_prefetch_3d(&tm_wt, gi0 + 2, gj0 + T2_H, pt + 1);
-                if (NSC) tma_prefetch_3d(&tm_st, gi0 + 2, gj0 + T2_H, pt);
-            }
-        }
-    };
     if (threadIdx.x == 0)
     {
-        for (int s = 0; s < RING; ++s) { mbar_init(full0 + 8 * s, 1); cnt[s] = 0; }
+        for (int s = 0; s < RING; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, NCW); }
         mbar_fence_init();
     }
-    __syncthreads();            // the only block-wide barrier
-    if (threadIdx.x == 0)
-        for (int n = 0; n < RING && k0 + n <= kc1; ++n) issue(n, k0 + n);
+    __syncthreads();            // the only block-wide barrier: roles split below
+
+    // ================================================================== producer warp
+    // A dedicated warp keeps the TMA issue (a dozen slow uniform-datapath instructions per level) off the critical
+    // path of the compute warps: letting the last warp that releases a slot refill it cost +25 % kernel time.
+    if (warp == NCW)
+    {
+        if (tx == 0)
+        {
+            for (int lev = k0; lev <= kc1; ++lev)
+            {
+                const int n = lev - k0, slot = n % RING, use = n / RING;
+                if (use > 0) mbar_wait(empty0 + 8 * slot, (use - 1) & 1);       // every consumer warp released the slot
+                const unsigned bar = full0 + 8 * slot;
+                mbar_expect_tx(bar, NF * BOX_BYTES);
+                tma_load_3d(pl0 + (0 * RING + slot) * PLANE_BYTES, &tm_u, bar, gi0, gj0, lev);
+                tma_load_3d(pl0 + (1 * RING + slot) * PLANE_BYTES, &tm_v, bar, gi0, gj0, lev);
+                tma_load_3d(pl0 + (2 * RING + slot) * PLANE_BYTES, &tm_w, bar, gi0, gj0, lev);
+                tma_load_3d(pl0 + (3 * RING + slot) * PLANE_BYTES, &tm_e, bar, gi0, gj0, lev);
+                if (NSC) tma_load_3d(pl0 + (4 * RING + slot) * PLANE_BYTES, &tm_s, bar, gi0, gj0, lev);
+                if (args.prefetch)
+                {
+                    // what the consumers' per-thread loads touch a little later: leading window levels, tendencies
+                    const int pu = lev + 2 + args.prefetch;
+                    if (pu < g.kcells) { tma_prefetch_3d(&tm_u, gi0, gj0, pu); tma_prefetch_3d(&tm_v, gi0, gj0, pu); if (NSC) tma_prefetch_3d(&tm_s, gi0, gj0, pu); }
+                    if (pu + 1 < g.kcells) tma_prefetch_3d(&tm_w, gi0, gj0, pu + 1);
+                    const int pt = lev + args.prefetch - 1;
+                    if (pt >= kc0 && pt < kc1)
+                    {
+                        tma_prefetch_3d(&tm_ut, gi0 + 2, gj0 + T2_H, pt); tma_prefetch_3d(&tm_vt, gi0 + 2, gj0 + T2_H, pt);
+                        tma_prefetch_3d(&tm_wt, gi0 + 2, gj0 + T2_H, pt + 1);
+                        if (NSC) tma_prefetch_3d(&tm_st, gi0 + 2, gj0 + T2_H, pt);
+                    }
+                }
+            }
+        }
+        return;
+    }
 
     // ================================================================== consumer warps
     auto colload = [&](const TF* __restrict__ fld, int lev, int c) -> TF {
@@ -160,22 +172,7 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
         if (n == 0) mbar_wait(full0, 0);
         mbar_wait(full0 + 8 * s1, ((n + 1) / RING) & 1);
     };
-    // done with plane k (slot s0): the LAST warp to get here refills the slot with plane k+RING -- nobody waits
-    auto release = [&](int k, int s0) {
-        __syncwarp();
-        if (tx == 0)
-        {
-            // No fence here: every value read from the slot has been consumed by arithmetic that precedes this point,
-            // and a __threadfence_block() would also wait for the global stores just issued (measured: +28 % kernel time).
-            unsigned prev;
-            asm volatile("atom.shared.add.u32 %0, [%1], 1;\n" : "=r"(prev) : "r"(smem_u32(&cnt[s0])) : "memory");
-            if (prev == NCW - 1)
-            {
-                cnt[s0] = 0;
-                if (k + RING <= kc1) issue(s0, k + RING);
-            }
-        }
-    };
+    auto release = [&](int k, int s0) { (void)k; __syncwarp(); if (tx == 0) mbar_arrive(empty0 + 8 * s0); };
 
 #define X10(a, n) a[(n) + 5]
 #define X6(a, n) a[(n) + 1]
