@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "stencil_kernels.cuh"
 #include "poisson_kernels.cuh"
+#include "fft_warp.cuh"
 #include "tile_kernels.cuh"
 #include "tile2_kernels.cuh"
 #include "tile3_kernels.cuh"
@@ -111,6 +112,7 @@ struct Ctx : mhh_ctx
     double *h_red = nullptr;       // pinned
     std::vector<TF> h_rhoref, h_rhorefh;
     int rows_x = 1, mc_y = 4;
+    bool wfft_x = false, wfft_y = false;   // warp-per-sequence FFT kernels (power-of-two lengths)
     size_t smem_x = 0, smem_y = 0;
 
     ~Ctx() override
@@ -144,6 +146,75 @@ int twiddles(mhh_ctx* c, cplx<TF>** out, int n)
     CUDA_TRY(c, cudaMalloc(out, sizeof(cplx<TF>) * std::max(n, 1)));
     CUDA_TRY(c, cudaMemcpy(*out, h.data(), sizeof(cplx<TF>) * std::max(n, 1), cudaMemcpyHostToDevice));
     return MHH_OK;
+}
+
+// ---- warp-per-sequence FFT dispatch (fft_warp.cuh) -------------------------------------------
+#define WFFT_X_CASES(X) X(16) X(32) X(64) X(128) X(256) X(512) X(1024)
+#define WFFT_Y_CASES(X) X(8) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048)
+
+template <typename TF>
+int wfft_x_attrs(mhh_ctx* c, int L)
+{
+    switch (L)
+    {
+#define X(N) case N: \
+        CUDA_TRY(c, cudaFuncSetAttribute(wfft_x_forward_kernel<TF, N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wfft_smem<TF, N>())); \
+        CUDA_TRY(c, cudaFuncSetAttribute(wfft_x_forward_kernel<TF, N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wfft_smem<TF, N>())); \
+        CUDA_TRY(c, cudaFuncSetAttribute(wfft_x_backward_kernel<TF, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wfft_smem<TF, N>())); break;
+        WFFT_X_CASES(X)
+#undef X
+        default: c->err = "wfft_x: unsupported length"; return MHH_E_INVALID;
+    }
+    return MHH_OK;
+}
+
+template <typename TF>
+int wfft_y_attrs(mhh_ctx* c, int J)
+{
+    switch (J)
+    {
+#define X(N) case N: CUDA_TRY(c, cudaFuncSetAttribute(wfft_y_kernel<TF, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wfft_smem<TF, N>())); break;
+        WFFT_Y_CASES(X)
+#undef X
+        default: c->err = "wfft_y: unsupported length"; return MHH_E_INVALID;
+    }
+    return MHH_OK;
+}
+
+template <typename TF>
+void wfft_x_forward_launch(int L, bool fused, int grid, cudaStream_t st, TF* spec, const RhsSrc<TF>& src, const GridDev<TF>& g,
+                           const cplx<TF>* twh, const cplx<TF>* twf, long long nrows)
+{
+    switch (L)
+    {
+#define X(N) case N: if (fused) wfft_x_forward_kernel<TF, N, true><<<grid, 32 * WFFT_WARPS, wfft_smem<TF, N>(), st>>>(spec, src, g, twh, twf, nrows); \
+                     else wfft_x_forward_kernel<TF, N, false><<<grid, 32 * WFFT_WARPS, wfft_smem<TF, N>(), st>>>(spec, src, g, twh, twf, nrows); break;
+        WFFT_X_CASES(X)
+#undef X
+    }
+}
+
+template <typename TF>
+void wfft_x_backward_launch(int L, int grid, cudaStream_t st, const TF* spec, TF* p, const GridDev<TF>& g,
+                            const cplx<TF>* twh, const cplx<TF>* twf, long long nrows, TF norm, int fill)
+{
+    switch (L)
+    {
+#define X(N) case N: wfft_x_backward_kernel<TF, N><<<grid, 32 * WFFT_WARPS, wfft_smem<TF, N>(), st>>>(spec, p, g, twh, twf, nrows, norm, fill); break;
+        WFFT_X_CASES(X)
+#undef X
+    }
+}
+
+template <typename TF>
+void wfft_y_launch(int J, int grid, cudaStream_t st, TF* spec, int nm, int ktot, const cplx<TF>* tw, int inverse)
+{
+    switch (J)
+    {
+#define X(N) case N: wfft_y_kernel<TF, N><<<grid, 32 * WFFT_WARPS, wfft_smem<TF, N>(), st>>>(spec, nm, ktot, tw, inverse); break;
+        WFFT_Y_CASES(X)
+#undef X
+    }
 }
 
 template <typename TF>
@@ -249,6 +320,14 @@ int create_impl(const mhh_grid_desc* d, int dtype, int device, mhh_ctx** out)
     CUDA_TRY(c, cudaFuncSetAttribute(fft_x_forward_kernel<TF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_x));
     CUDA_TRY(c, cudaFuncSetAttribute(fft_x_backward_kernel<TF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_x));
     CUDA_TRY(c, cudaFuncSetAttribute(fft_y_kernel<TF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_y));
+    // warp-per-sequence kernels for power-of-two lengths (MHH_NO_WFFT=1 keeps the generic block kernels)
+    const bool no_wfft = getenv("MHH_NO_WFFT") && getenv("MHH_NO_WFFT")[0] == '1';
+    auto pow2_in = [](int v, int lo, int hi) { return v >= lo && v <= hi && (v & (v - 1)) == 0; };
+    c->wfft_x = !no_wfft && pow2_in(L, 16, 1024);
+    c->wfft_y = !no_wfft && pow2_in(g.jtot, 8, 2048);
+    int rc2;
+    if (c->wfft_x && (rc2 = wfft_x_attrs<TF>(c, L)) != MHH_OK) return rc2;
+    if (c->wfft_y && (rc2 = wfft_y_attrs<TF>(c, g.jtot)) != MHH_OK) return rc2;
     return MHH_OK;
 }
 
@@ -733,9 +812,12 @@ int pres_spectral_solve(Ctx<TF>* c, bool do_solve)
 {
     const GridDev<TF>& g = c->g;
     const int grid_p = c->num_sms * 2;
+    const long long ypanels = (long long)((c->nm + WFFT_WARPS - 1) / WFFT_WARPS) * g.ktot;
+    const int grid_wy = (int)std::min<long long>(ypanels, (long long)c->num_sms * 8);
     if (g.jtot > 1)
     {
-        fft_y_kernel<TF><<<grid_p, 256, c->smem_y, c->stream>>>(c->spec, c->nm, g.jtot, g.ktot, c->plan_y, c->tw_y, c->mc_y, 0);
+        if (c->wfft_y) wfft_y_launch<TF>(g.jtot, grid_wy, c->stream, c->spec, c->nm, g.ktot, c->tw_y, 0);
+        else fft_y_kernel<TF><<<grid_p, 256, c->smem_y, c->stream>>>(c->spec, c->nm, g.jtot, g.ktot, c->plan_y, c->tw_y, c->mc_y, 0);
         KCHECKN(c, "fft_y_forward_kernel");
     }
     if (do_solve)
@@ -746,7 +828,8 @@ int pres_spectral_solve(Ctx<TF>* c, bool do_solve)
     }
     if (g.jtot > 1)
     {
-        fft_y_kernel<TF><<<grid_p, 256, c->smem_y, c->stream>>>(c->spec, c->nm, g.jtot, g.ktot, c->plan_y, c->tw_y, c->mc_y, 1);
+        if (c->wfft_y) wfft_y_launch<TF>(g.jtot, grid_wy, c->stream, c->spec, c->nm, g.ktot, c->tw_y, 1);
+        else fft_y_kernel<TF><<<grid_p, 256, c->smem_y, c->stream>>>(c->spec, c->nm, g.jtot, g.ktot, c->plan_y, c->tw_y, c->mc_y, 1);
         KCHECKN(c, "fft_y_backward_kernel");
     }
     return MHH_OK;
@@ -761,12 +844,15 @@ int pres_solve_impl(Ctx<TF>* c, const mhh_fields* f, double sub_dt)
     RhsSrc<TF> src{P<TF>(f->u), P<TF>(f->v), P<TF>(f->w), P<TF>(f->ut), P<TF>(f->vt), P<TF>(f->wt), (TF)(TF(1.) / sub_dt)};
     const long long nrows = (long long)g.jtot * g.ktot;
     const int grid_x = (int)std::min<long long>((nrows + c->rows_x - 1) / c->rows_x, (long long)c->num_sms * 4);
-    fft_x_forward_kernel<TF, true><<<grid_x, 256, c->smem_x, c->stream>>>(c->spec, src, g, c->plan_x, c->tw_xh, c->tw_xf, c->rows_x, nrows);
+    const int grid_wx = (int)std::min<long long>((nrows + WFFT_WARPS - 1) / WFFT_WARPS, (long long)c->num_sms * 8);
+    if (c->wfft_x) wfft_x_forward_launch<TF>(g.itot / 2, true, grid_wx, c->stream, c->spec, src, g, c->tw_xh, c->tw_xf, nrows);
+    else fft_x_forward_kernel<TF, true><<<grid_x, 256, c->smem_x, c->stream>>>(c->spec, src, g, c->plan_x, c->tw_xh, c->tw_xf, c->rows_x, nrows);
     KCHECKN(c, "fft_x_forward_kernel");
     int rc = pres_spectral_solve<TF>(c, true);
     if (rc != MHH_OK) return rc;
     const TF norm = TF(1.) / ((TF)g.itot * (TF)g.jtot);
-    fft_x_backward_kernel<TF><<<grid_x, 256, c->smem_x, c->stream>>>(c->spec, P<TF>(f->p), g, c->plan_x, c->tw_xh, c->tw_xf,
+    if (c->wfft_x) wfft_x_backward_launch<TF>(g.itot / 2, grid_wx, c->stream, c->spec, P<TF>(f->p), g, c->tw_xh, c->tw_xf, nrows, norm, 1);
+    else fft_x_backward_kernel<TF><<<grid_x, 256, c->smem_x, c->stream>>>(c->spec, P<TF>(f->p), g, c->plan_x, c->tw_xh, c->tw_xf,
             c->rows_x, nrows, norm, 1);
     KCHECKN(c, "fft_x_backward_kernel");
     if (g.jtot == 1)
@@ -890,7 +976,9 @@ int fft_roundtrip_impl(Ctx<TF>* c, const TF* in, TF* out, int solve)
     const long long nrows = (long long)g.jtot * g.ktot;
     const int grid_x = (int)std::min<long long>((nrows + c->rows_x - 1) / c->rows_x, (long long)c->num_sms * 4);
     RhsSrc<TF> none{};
-    fft_x_forward_kernel<TF, false><<<grid_x, 256, c->smem_x, c->stream>>>(c->spec, none, g, c->plan_x, c->tw_xh, c->tw_xf, c->rows_x, nrows);
+    const int grid_wx = (int)std::min<long long>((nrows + WFFT_WARPS - 1) / WFFT_WARPS, (long long)c->num_sms * 8);
+    if (c->wfft_x) wfft_x_forward_launch<TF>(g.itot / 2, false, grid_wx, c->stream, c->spec, none, g, c->tw_xh, c->tw_xf, nrows);
+    else fft_x_forward_kernel<TF, false><<<grid_x, 256, c->smem_x, c->stream>>>(c->spec, none, g, c->plan_x, c->tw_xh, c->tw_xf, c->rows_x, nrows);
     KCHECKN(c, "fft_x_forward_kernel");
     int rc = pres_spectral_solve<TF>(c, solve != 0);
     if (rc != MHH_OK) return rc;
@@ -898,7 +986,8 @@ int fft_roundtrip_impl(Ctx<TF>* c, const TF* in, TF* out, int solve)
     TF* tmp = nullptr;
     CUDA_TRY(c, cudaMalloc(&tmp, sizeof(TF) * (size_t)g.ncells));
     const TF norm = TF(1.) / ((TF)g.itot * (TF)g.jtot);
-    fft_x_backward_kernel<TF><<<grid_x, 256, c->smem_x, c->stream>>>(c->spec, tmp, g, c->plan_x, c->tw_xh, c->tw_xf, c->rows_x, nrows, norm, 0);
+    if (c->wfft_x) wfft_x_backward_launch<TF>(g.itot / 2, grid_wx, c->stream, c->spec, tmp, g, c->tw_xh, c->tw_xf, nrows, norm, 0);
+    else fft_x_backward_kernel<TF><<<grid_x, 256, c->smem_x, c->stream>>>(c->spec, tmp, g, c->plan_x, c->tw_xh, c->tw_xf, c->rows_x, nrows, norm, 0);
     c->launches++;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess)
