@@ -98,17 +98,21 @@ def run_ours(args):
     itot, jtot, ktot = parse_workload(args.workload)
     S = 1
 
-    # replicas: each rank owns an independent LES domain of the named shape (weak scaling; the
-    # slab-decomposed single-domain path is the multi-GPU context)
-    gd = GridData(itot, jtot, ktot, 25.*itot, 25.*jtot, 25.*ktot, 3, 3, 1, dtype)
-    case = make_case(gd, seed=2 + rank, noise=0.01)
+    # ONE domain decomposed into y slabs over the ranks (npx = 1, npy = world).  Weak scaling: the per-GPU block
+    # keeps the named size, the horizontal domain grows (y doubles first, then x): 1: i x j, 2: i x 2j, 4: 2i x 2j,
+    # 8: 2i x 4j -- every rank owns itot_g x (jtot_g / world) x ktot = the named number of points.
+    fx = {1: 1, 2: 1, 4: 2, 8: 2}.get(world, 1)
+    fy = world // fx
+    itot_g, jtot_g = itot*fx, jtot*fy
+    gd = GridData(itot_g, jtot_g, ktot, 25.*itot_g, 25.*jtot_g, 25.*ktot, 3, 3, 1, dtype, npy=world, mpicoordy=rank)
+    case = make_case(gd, seed=2, noise=0.01)
     ctx = D.Context(gd, local_rank)
     ctx.set_basestate(case["rhoref"], case["rhorefh"], case["thref"], case["threfh"])
     f = D.Fields(ctx, case)
     prm = D.make_params()
     dyc = D.Dycore(ctx, prm)
     dt = args.dt
-    npts = gd.npoints
+    npts = gd.npoints // world        # per GPU
 
     def barrier():
         if world > 1:
@@ -180,7 +184,8 @@ def run_ours(args):
     alg = {  # algorithmic array passes per launch, in units of N*B bytes
         "tend_uvw_kernel": 4 + 6, "tend_s_kernel": 5 + 2, "evisc_kernel": 5,
         # z-marching tile kernels: R u,v,w,evisc,th + RMW ut,vt,wt | R s,u,v,w,evisc + RMW st | R u,v,w,th + W evisc
-        "mom_tile_kernel": 5 + 6, "mom2_kernel": 5 + 6, "mom3_kernel": 5 + 6, "scal_tile_kernel": 5 + 2, "evisc_tile_kernel": 5,
+        # mom3 carries scalar 0 as a fourth warp group: R u,v,w,evisc,th + RMW ut,vt,wt,tht
+        "mom_tile_kernel": 5 + 6, "mom2_kernel": 5 + 6, "mom3_kernel": 5 + 8, "scal_tile_kernel": 5 + 2, "evisc_tile_kernel": 5,
         "fft_x_forward_kernel": 7, "fft_y_forward_kernel": 2, "fft_y_backward_kernel": 2,
         "tdma_solve_kernel": 2, "fft_x_backward_kernel": 2, "pres_out_rk3_kernel": 13, "rk3_kernel": 4,
     }
@@ -199,7 +204,7 @@ def run_ours(args):
              "frac_of_hbm": step_alg_bytes/(ms_per_step*1e-3)/1e9/peaks["hbm_gbs"]}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         try:
             cpu = cpu_baseline(dtype, args.cpu_sample, dt)
         except Exception as ex:   # the baseline is a report, never a reason to lose the GPU number
@@ -209,7 +214,8 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": f"drycblles-shaped LES {itot}x{jtot}x{ktot} per GPU, advec_2i5+diff_smag2+pres_2+thermo_dry, S=1",
-                       "parallelism": "replicas only" if world > 1 else "single GPU",
+                       "global_grid": f"{itot_g}x{jtot_g}x{ktot}",
+                       "parallelism": f"one domain in {world} y-slabs (npx=1, npy={world}): NCCL halo rows + all-to-all transposes" if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (each field >> 126 MB)", "dt": dt},
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "whole_step_roofline": whole, "cpu_baseline": cpu,

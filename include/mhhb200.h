@@ -71,7 +71,7 @@ typedef struct mhh_grid_desc
     const void* dzh;
     const void* dzi;
     const void* dzhi;
-    int npx, npy;                /* process grid (src/master_parallel.cxx:103-153); 1,1 = single GPU */
+    int npx, npy;                /* process grid (src/master_parallel.cxx:103-153); 1,1 = single GPU; npx must be 1 (y slabs) */
     int mpicoordx, mpicoordy;
 } mhh_grid_desc;
 
@@ -131,6 +131,39 @@ MHH_API int mhh_profile_start(mhh_ctx* ctx);
 MHH_API int mhh_profile_stop(mhh_ctx* ctx, const char** json);
 /* bytes of device memory owned by the context (workspace, tables) */
 MHH_API long long mhh_workspace_bytes(const mhh_ctx* ctx);
+
+/* ---- multi-GPU: y-slab decomposition (npx = 1, npy = P ranks, one context / process per GPU) -----
+ * The reference cannot combine MPI and CUDA (CMakeLists.txt:50-52); its CPU-MPI code is the semantic
+ * model: the process grid of Master (src/master_parallel.cxx:103-153; here mpicoordy = rank),
+ * Boundary_cyclic's neighbour exchange (src/boundary_cyclic.cxx:115-176), Transpose::exec_xy/exec_yx
+ * (src/transpose.cxx:117-271) inside FFT::exec_forward/backward (src/fft.cxx:455-587) and the
+ * MPI_Allreduce(MAX) of cfl / dn / divergence (src/master_parallel.cxx:270-290).
+ * A context created with npy > 1 owns the slab jmax = jtot/npy; once mhh_comm_init() has connected
+ * the ranks, EVERY hot-path call below is collective over the slab ranks (NCCL semantics) and does
+ * its own north/south ghost-row exchange, all-to-all transposes and reductions on the context's
+ * stream.  NCCL is bound at run time (dlopen of libnccl.so.2); single-GPU use needs no NCCL.
+ * Bootstrap: rank 0 calls mhh_comm_get_unique_id, the host broadcasts the bytes (MPI_Bcast in
+ * MicroHH's Master, torch.distributed in the tests), every rank calls mhh_comm_init. */
+#define MHH_COMM_ID_BYTES 128
+MHH_API int mhh_comm_get_unique_id(void* id, int nbytes);
+MHH_API int mhh_comm_init(mhh_ctx* ctx, const void* id, int nbytes);
+
+/* Spectral workspace layout of the slab decomposition (pure host functions, no GPU needed): which
+ * x-modes a rank owns after the forward transpose and where element (row, mode) / (k, j, mode) lives
+ * in the x-side / y-side buffers (complex-element index).  Exposed so that the host-side tests can
+ * replay the all-to-all with any transport (world_size-2 gloo tests on CPU). */
+typedef struct mhh_slab_info
+{
+    int nm;                  /* x-modes in total: itot/2 + 1 */
+    int mcl, m_off;          /* modes owned by this rank: [m_off, m_off + mcl) */
+    int jmax;                /* rows of the slab per level */
+    long long rows;          /* jmax*ktot */
+    long long xside_elems;   /* complex elements of the x-side buffer: nm*rows */
+    long long yside_elems;   /* complex elements of the y-side buffer: mcl*jtot*ktot */
+} mhh_slab_info;
+MHH_API int mhh_slab_layout(int itot, int jtot, int ktot, int npy, int rank, mhh_slab_info* out);
+MHH_API long long mhh_slab_xindex(int itot, int jtot, int ktot, int npy, int rank, long long row, int m);
+MHH_API long long mhh_slab_yindex(int itot, int jtot, int ktot, int npy, int rank, int k, int j, int ml);
 
 /* ---- Boundary_cyclic<TF>::exec / exec_2d  (src/boundary_cyclic.cxx:369-507) ---------------- */
 MHH_API int mhh_boundary_cyclic(mhh_ctx* ctx, void* fld, int edge);

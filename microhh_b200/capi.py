@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libmhhb200.so")
 
 MHH_F64, MHH_F32 = 0, 1
 MHH_MAX_SCALARS = 8
+MHH_COMM_ID_BYTES = 128
 EDGE_EAST_WEST, EDGE_NORTH_SOUTH, EDGE_BOTH = 0, 1, 2
 BC_NONE, BC_DIRICHLET, BC_NEUMANN = -1, 0, 1
 
@@ -39,6 +40,11 @@ class FieldsC(C.Structure):
                 ("s_bot", _SA), ("s_gradbot", _SA), ("s_top", _SA), ("s_gradtop", _SA)]
 
 
+class SlabInfo(C.Structure):
+    _fields_ = [("nm", C.c_int), ("mcl", C.c_int), ("m_off", C.c_int), ("jmax", C.c_int),
+                ("rows", C.c_longlong), ("xside_elems", C.c_longlong), ("yside_elems", C.c_longlong)]
+
+
 class ParamsC(C.Structure):
     _fields_ = [("swadvec", C.c_int), ("swdiff", C.c_int), ("swthermo", C.c_int),
                 ("surface_model", C.c_int), ("sw_mason", C.c_int),
@@ -60,6 +66,11 @@ SIGNATURES = {
     "mhh_workspace_bytes": (C.c_longlong, [_vp]),
     "mhh_profile_start": (C.c_int, [_vp]),
     "mhh_profile_stop": (C.c_int, [_vp, C.POINTER(C.c_char_p)]),
+    "mhh_comm_get_unique_id": (C.c_int, [_vp, C.c_int]),
+    "mhh_comm_init": (C.c_int, [_vp, _vp, C.c_int]),
+    "mhh_slab_layout": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(SlabInfo)]),
+    "mhh_slab_xindex": (C.c_longlong, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_int]),
+    "mhh_slab_yindex": (C.c_longlong, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "mhh_boundary_cyclic": (C.c_int, [_vp, _vp, C.c_int]),
     "mhh_boundary_cyclic_2d": (C.c_int, [_vp, _vp]),
     "mhh_boundary_ghost_cells_2nd": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp]),

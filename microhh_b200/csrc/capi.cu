@@ -17,7 +17,10 @@
 #include "tile_kernels.cuh"
 #include "tile2_kernels.cuh"
 #include "tile3_kernels.cuh"
+#include "slab_kernels.cuh"
 #include <cudaTypedefs.h>
+#include <dlfcn.h>
+#include <nccl.h>
 
 using namespace mhh;
 
@@ -45,8 +48,52 @@ struct mhh_ctx
     std::vector<std::pair<const char*, cudaEvent_t>> prof_events;
     std::vector<cudaEvent_t> prof_pool;
     std::string prof_json;
+    // y-slab decomposition (npx = 1, npy = nranks): NCCL communicator over the slab ranks
+    int nranks = 1, rank = 0;
+    ncclComm_t comm = nullptr;
     virtual ~mhh_ctx() {}
 };
+
+// ---- NCCL, bound at run time (dlopen) so that single-GPU users need no NCCL at all; inside a torch
+// process this resolves to the libnccl.so.2 torch has already loaded.
+struct NcclApi
+{
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static NcclApi* nccl_api(std::string& err)
+{
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried)
+    {
+        tried = true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) { api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (api.handle) break; }
+        if (api.handle)
+        {
+#define NCCL_SYM(field, sym) api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.handle, sym))
+            NCCL_SYM(GetUniqueId, "ncclGetUniqueId"); NCCL_SYM(CommInitRank, "ncclCommInitRank");
+            NCCL_SYM(CommDestroy, "ncclCommDestroy"); NCCL_SYM(Send, "ncclSend"); NCCL_SYM(Recv, "ncclRecv");
+            NCCL_SYM(AllReduce, "ncclAllReduce"); NCCL_SYM(GroupStart, "ncclGroupStart"); NCCL_SYM(GroupEnd, "ncclGroupEnd");
+            NCCL_SYM(GetErrorString, "ncclGetErrorString");
+#undef NCCL_SYM
+            if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.Send || !api.Recv || !api.AllReduce ||
+                !api.GroupStart || !api.GroupEnd || !api.GetErrorString) { dlclose(api.handle); api.handle = nullptr; }
+        }
+    }
+    if (!api.handle) { err = "NCCL (libnccl.so.2) could not be loaded"; return nullptr; }
+    return &api;
+}
 
 static void prof_mark(mhh_ctx* c, const char* name)
 {
@@ -62,6 +109,9 @@ namespace {
 
 #define CUDA_TRY(ctx, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
     (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_); return MHH_E_CUDA; } } while (0)
+
+#define NCCL_TRY(ctx, api, call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) { \
+    (ctx)->err = std::string(#call) + ": " + (api)->GetErrorString(r_); return MHH_E_CUDA; } } while (0)
 
 #define KCHECKN(ctx, name) do { (ctx)->launches++; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) { \
     (ctx)->err = std::string("kernel launch ") + name + ": " + cudaGetErrorString(e_) + " at " + __FILE__ + ":" + std::to_string(__LINE__); \
@@ -105,8 +155,12 @@ struct Ctx : mhh_ctx
     FftPlan plan_x{}, plan_y{};
     cplx<TF> *tw_xh = nullptr, *tw_xf = nullptr, *tw_y = nullptr;
     TF *d_bmati = nullptr, *d_bmatj = nullptr, *d_a = nullptr, *d_c = nullptr, *d_dz2rho = nullptr, *d_dz2 = nullptr;
-    TF *spec = nullptr;            // spectral workspace, (itot+2)*jtot*ktot
-    TF *fac = nullptr;             // tdma factors, nm*jtot*ktot
+    TF *spec = nullptr;            // spectral workspace, x side: nm*jmax*ktot complex
+    TF *specT = nullptr;           // y side: mcl*jtot*ktot complex (== spec on a single GPU)
+    TF *fac = nullptr;             // tdma factors, mcl*jtot*ktot
+    SpecLayout lay{};
+    TF *halo = nullptr;            // 4 staging buffers (send south/north, recv north/south) of halo_cap elements
+    size_t halo_cap = 0;
     bool basestate_set = false;
     double *d_red = nullptr;       // reduction scalar
     double *h_red = nullptr;       // pinned
@@ -120,7 +174,9 @@ struct Ctx : mhh_ctx
         cudaSetDevice(device);
         cudaFree(d_prof); cudaFree(d_mlen0); cudaFree(tw_xh); cudaFree(tw_xf); cudaFree(tw_y);
         cudaFree(d_bmati); cudaFree(d_bmatj); cudaFree(d_a); cudaFree(d_c); cudaFree(d_dz2rho); cudaFree(d_dz2);
-        cudaFree(spec); cudaFree(fac); cudaFree(d_red);
+        if (specT != spec) cudaFree(specT);
+        cudaFree(spec); cudaFree(fac); cudaFree(d_red); cudaFree(halo);
+        if (comm) { std::string e; NcclApi* api = nccl_api(e); if (api) api->CommDestroy(comm); }
         if (h_red) cudaFreeHost(h_red);
         if (own_stream) cudaStreamDestroy(own_stream);
     }
@@ -182,36 +238,36 @@ int wfft_y_attrs(mhh_ctx* c, int J)
 }
 
 template <typename TF>
-void wfft_x_forward_launch(int L, bool fused, int grid, cudaStream_t st, TF* spec, const RhsSrc<TF>& src, const GridDev<TF>& g,
+void wfft_x_forward_launch(int L, bool fused, int grid, cudaStream_t st, TF* spec, const RhsSrc<TF>& src, const GridDev<TF>& g, const SpecLayout& lay,
                            const cplx<TF>* twh, const cplx<TF>* twf, long long nrows)
 {
     switch (L)
     {
-#define X(N) case N: if (fused) wfft_x_forward_kernel<TF, N, true><<<grid, 32 * WFFT_WARPS, wfft_smem<TF, N>(), st>>>(spec, src, g, twh, twf, nrows); \
-                     else wfft_x_forward_kernel<TF, N, false><<<grid, 32 * WFFT_WARPS, wfft_smem<TF, N>(), st>>>(spec, src, g, twh, twf, nrows); break;
+#define X(N) case N: if (fused) wfft_x_forward_kernel<TF, N, true><<<grid, 32 * WFFT_WARPS, wfft_smem<TF, N>(), st>>>(spec, src, g, lay, twh, twf, nrows); \
+                     else wfft_x_forward_kernel<TF, N, false><<<grid, 32 * WFFT_WARPS, wfft_smem<TF, N>(), st>>>(spec, src, g, lay, twh, twf, nrows); break;
         WFFT_X_CASES(X)
 #undef X
     }
 }
 
 template <typename TF>
-void wfft_x_backward_launch(int L, int grid, cudaStream_t st, const TF* spec, TF* p, const GridDev<TF>& g,
+void wfft_x_backward_launch(int L, int grid, cudaStream_t st, const TF* spec, TF* p, const GridDev<TF>& g, const SpecLayout& lay,
                             const cplx<TF>* twh, const cplx<TF>* twf, long long nrows, TF norm, int fill)
 {
     switch (L)
     {
-#define X(N) case N: wfft_x_backward_kernel<TF, N><<<grid, 32 * WFFT_WARPS, wfft_smem<TF, N>(), st>>>(spec, p, g, twh, twf, nrows, norm, fill); break;
+#define X(N) case N: wfft_x_backward_kernel<TF, N><<<grid, 32 * WFFT_WARPS, wfft_smem<TF, N>(), st>>>(spec, p, g, lay, twh, twf, nrows, norm, fill); break;
         WFFT_X_CASES(X)
 #undef X
     }
 }
 
 template <typename TF>
-void wfft_y_launch(int J, int grid, cudaStream_t st, TF* spec, int nm, int ktot, const cplx<TF>* tw, int inverse)
+void wfft_y_launch(int J, int grid, cudaStream_t st, TF* spec, const SpecLayout& lay, int nm, int ktot, const cplx<TF>* tw, int inverse)
 {
     switch (J)
     {
-#define X(N) case N: wfft_y_kernel<TF, N><<<grid, 32 * WFFT_WARPS, wfft_smem<TF, N>(), st>>>(spec, nm, ktot, tw, inverse); break;
+#define X(N) case N: wfft_y_kernel<TF, N><<<grid, 32 * WFFT_WARPS, wfft_smem<TF, N>(), st>>>(spec, lay, nm, ktot, tw, inverse); break;
         WFFT_Y_CASES(X)
 #undef X
     }
@@ -256,10 +312,16 @@ int create_impl(const mhh_grid_desc* d, int dtype, int device, mhh_ctx** out)
     g.dyi = TF(1.) / g.dy;
     g.zsize = (TF)d->zsize;
 
-    if (d->npx != 1 || d->npy != 1)
-    { c->err = "this entry point is single-GPU (npx = npy = 1); use the distributed context for pencils"; return MHH_E_INVALID; }
-    if (g.imax != g.itot || g.jmax != g.jtot || g.kmax != g.ktot)
-    { c->err = "imax/jmax/kmax must equal itot/jtot/ktot for npx = npy = 1"; return MHH_E_INVALID; }
+    // y slabs: x and z are never split (one all-to-all pair per Poisson solve instead of the pencil layout's three)
+    const int P = d->npy;
+    if (d->npx != 1 || P < 1)
+    { c->err = "the decomposition is y slabs: npx must be 1 and npy >= 1"; return MHH_E_INVALID; }
+    if (g.jtot % P != 0 || g.imax != g.itot || g.jmax != g.jtot / P || g.kmax != g.ktot)
+    { c->err = "need imax = itot, jmax = jtot/npy, kmax = ktot"; return MHH_E_INVALID; }
+    if (d->mpicoordx != 0 || d->mpicoordy < 0 || d->mpicoordy >= P) { c->err = "mpicoordy out of range"; return MHH_E_INVALID; }
+    if (P > 1 && (g.jmax < g.jgc || g.itot / 2 + 1 < P)) { c->err = "slab too thin for this many ranks"; return MHH_E_INVALID; }
+    c->nranks = P; c->rank = d->mpicoordy;
+    c->lay = make_spec_layout(g.itot, g.jtot, g.ktot, P, c->rank);
     if (g.kmax < 6) { c->err = "ktot must be >= 6"; return MHH_E_INVALID; }
     if (g.igc < 1 || g.kgc < 1 || g.jgc < 1) { c->err = "need at least one ghost cell"; return MHH_E_INVALID; }
     if (g.itot % 2 != 0) { c->err = "itot must be even"; return MHH_E_INVALID; }
@@ -292,11 +354,13 @@ int create_impl(const mhh_grid_desc* d, int dtype, int device, mhh_ctx** out)
     if ((rc = twiddles<TF>(c, &c->tw_xf, g.itot)) != MHH_OK) return rc;
     if ((rc = twiddles<TF>(c, &c->tw_y, g.jtot)) != MHH_OK) return rc;
 
-    const size_t nspec = (size_t)2 * c->nm * g.jtot * g.ktot;
-    const size_t nfac = (size_t)c->nm * g.jtot * g.ktot;
+    const size_t nspec = (size_t)2 * c->nm * g.jmax * g.ktot;
+    const size_t nspecT = (size_t)2 * c->lay.mcl * g.jtot * g.ktot;
+    const size_t nfac = (size_t)c->lay.mcl * g.jtot * g.ktot;
     CUDA_TRY(c, cudaMalloc(&c->spec, sizeof(TF) * nspec));
+    if (P > 1) CUDA_TRY(c, cudaMalloc(&c->specT, sizeof(TF) * nspecT)); else c->specT = c->spec;
     CUDA_TRY(c, cudaMalloc(&c->fac, sizeof(TF) * nfac));
-    c->ws_bytes = (long long)(sizeof(TF) * (nspec + nfac));
+    c->ws_bytes = (long long)(sizeof(TF) * (nspec + (P > 1 ? nspecT : 0) + nfac));
     CUDA_TRY(c, cudaMalloc(&c->d_bmati, sizeof(TF) * c->nm));
     CUDA_TRY(c, cudaMalloc(&c->d_bmatj, sizeof(TF) * g.jtot));
     CUDA_TRY(c, cudaMalloc(&c->d_a, sizeof(TF) * g.kmax));
@@ -377,8 +441,8 @@ int set_basestate_impl(Ctx<TF>* c, const void* rhoref, const void* rhorefh, cons
     CUDA_TRY(c, cudaMemcpy(c->d_dz2, dz2.data(), sizeof(TF) * g.kmax, cudaMemcpyHostToDevice));
     CUDA_TRY(c, cudaMemcpy(c->d_mlen0, mlen0.data(), sizeof(TF) * kc, cudaMemcpyHostToDevice));
 
-    const long long ncol = (long long)c->nm * g.jtot;
-    tdma_setup_kernel<TF><<<(unsigned)((ncol + 127) / 128), 128, 0, c->stream>>>(c->fac, c->coef(), c->nm, g.jtot, g.kmax, 0, 0);
+    const long long ncol = (long long)c->lay.mcl * g.jtot;
+    tdma_setup_kernel<TF><<<(unsigned)((ncol + 127) / 128), 128, 0, c->stream>>>(c->fac, c->coef(), c->lay.mcl, g.jtot, g.kmax, c->lay.m_off, 0);
     KCHECKN(c, "tdma_setup_kernel");
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     c->basestate_set = true;
@@ -391,8 +455,74 @@ template <typename TF> inline const TF* P(const void* p) { return static_cast<co
 #define NEED_BASE(c) do { if (!(c)->basestate_set) { (c)->err = "mhh_set_basestate has not been called"; return MHH_E_INVALID; } } while (0)
 #define NEED(c, ptr, what) do { if (!(ptr)) { (c)->err = std::string(what) + " is NULL"; return MHH_E_INVALID; } } while (0)
 
+// north/south ghost rows of a batch of fields from the slab neighbours (periodic in y across ranks)
+template <typename TF>
+int exchange_ns(Ctx<TF>* c, TF* const* flds, int nf, int w, int nk)
+{
+    const GridDev<TF>& g0 = c->g;
+    if (nf < 1 || nf > HALO_MAX_FIELDS || w < 1 || w > g0.jgc) { c->err = "exchange_ns: bad batch"; return MHH_E_INVALID; }
+    if (!c->comm) { c->err = "slab context without communicator: call mhh_comm_init first"; return MHH_E_INVALID; }
+    NcclApi* api = nccl_api(c->err);
+    if (!api) return MHH_E_CUDA;
+    GridDev<TF> g = g0;
+    g.kcells = nk;                                  // 2-D companions: one level
+    const size_t per = (size_t)w * g.icells * nk;
+    const size_t need = per * nf;
+    if (c->halo_cap < need)
+    {
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        cudaFree(c->halo); c->halo = nullptr; c->halo_cap = 0;
+        CUDA_TRY(c, cudaMalloc(&c->halo, sizeof(TF) * need * 4));
+        c->halo_cap = need;
+    }
+    TF* sendS = c->halo; TF* sendN = c->halo + c->halo_cap; TF* recvN = c->halo + 2 * c->halo_cap; TF* recvS = c->halo + 3 * c->halo_cap;
+    HaloFields<TF> h{}; h.nf = nf;
+    for (int n = 0; n < nf; ++n) { NEED(c, flds[n], "field"); h.f[n] = flds[n]; }
+    const int grid = (int)std::min<size_t>((need + 255) / 256, (size_t)c->num_sms * 8);
+    halo_pack_kernel<TF><<<grid, 256, 0, c->stream>>>(h, g, w, sendS, sendN);
+    KCHECKN(c, "halo_pack_kernel");
+    const int south = (c->rank + c->nranks - 1) % c->nranks, north = (c->rank + 1) % c->nranks;
+    const size_t bytes = need * sizeof(TF);
+    NCCL_TRY(c, api, api->GroupStart());
+    NCCL_TRY(c, api, api->Send(sendS, bytes, ncclChar, south, c->comm, c->stream));
+    NCCL_TRY(c, api, api->Send(sendN, bytes, ncclChar, north, c->comm, c->stream));
+    NCCL_TRY(c, api, api->Recv(recvN, bytes, ncclChar, north, c->comm, c->stream));
+    NCCL_TRY(c, api, api->Recv(recvS, bytes, ncclChar, south, c->comm, c->stream));
+    NCCL_TRY(c, api, api->GroupEnd());
+    prof_mark(c, "halo_sendrecv_nccl");
+    halo_unpack_kernel<TF><<<grid, 256, 0, c->stream>>>(h, g, w, recvN, recvS);
+    KCHECKN(c, "halo_unpack_kernel");
+    return MHH_OK;
+}
+
+template <typename TF>
+int cyclic_local(Ctx<TF>* c, TF* fld, int edge, bool two_d);
+
+// Boundary_cyclic::exec on one field: local periodic copies, plus the neighbour exchange for y slabs
 template <typename TF>
 int cyclic_impl(Ctx<TF>* c, TF* fld, int edge, bool two_d)
+{
+    if (c->nranks == 1) return cyclic_local<TF>(c, fld, edge, two_d);
+    if (edge < 0 || edge > 2) { c->err = "bad edge"; return MHH_E_INVALID; }
+    int rc;
+    if (edge != MHH_EDGE_NORTH_SOUTH && (rc = cyclic_local<TF>(c, fld, MHH_EDGE_EAST_WEST, two_d)) != MHH_OK) return rc;
+    if (edge == MHH_EDGE_EAST_WEST) return MHH_OK;
+    return exchange_ns<TF>(c, &fld, 1, c->g.jgc, two_d ? 1 : c->g.kcells);
+}
+
+// a batch of fields: one message per direction for all of them
+template <typename TF>
+int cyclic_fields(Ctx<TF>* c, TF* const* flds, int nf)
+{
+    int rc;
+    for (int n = 0; n < nf; ++n)
+        if ((rc = cyclic_local<TF>(c, flds[n], c->nranks == 1 ? MHH_EDGE_BOTH : MHH_EDGE_EAST_WEST, false)) != MHH_OK) return rc;
+    if (c->nranks == 1) return MHH_OK;
+    return exchange_ns<TF>(c, flds, nf, c->g.jgc, c->g.kcells);
+}
+
+template <typename TF>
+int cyclic_local(Ctx<TF>* c, TF* fld, int edge, bool two_d)
 {
     const GridDev<TF>& g = c->g;
     NEED(c, fld, "field");
@@ -800,6 +930,13 @@ int reduce_impl(Ctx<TF>* c, const TF* u, const TF* v, const TF* w, TF p0, TF p1,
     CUDA_TRY(c, cudaMemsetAsync(c->d_red, 0, sizeof(double), c->stream));
     reduce_kernel<TF, MODE><<<c->grd_interior(), c->blk(), 0, c->stream>>>(u, v, w, g, p0, p1, p2, c->d_red);
     KCHECKN(c, "reduce_kernel");
+    if (c->nranks > 1)
+    {
+        if (!c->comm) { c->err = "slab context without communicator: call mhh_comm_init first"; return MHH_E_INVALID; }
+        NcclApi* api = nccl_api(c->err);
+        if (!api) return MHH_E_CUDA;
+        NCCL_TRY(c, api, api->AllReduce(c->d_red, c->d_red, 1, ncclFloat64, ncclMax, c->comm, c->stream));
+    }
     CUDA_TRY(c, cudaMemcpyAsync(c->h_red, c->d_red, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     *out = *c->h_red;
@@ -807,32 +944,76 @@ int reduce_impl(Ctx<TF>* c, const TF* u, const TF* v, const TF* w, TF p0, TF p1,
 }
 
 // ---- Pres_2 ---------------------------------------------------------------------------------
+// The slab all-to-all (reference semantics: Transpose::exec_xy / exec_yx, src/transpose.cxx:117-271).  Block d of the
+// x-side buffer IS the message for rank d and block s of the y-side buffer IS the message from rank s (SpecLayout), so
+// there is no pack/unpack pass: grouped ncclSend/ncclRecv straight out of / into the workspaces.
+template <typename TF>
+int slab_all_to_all(Ctx<TF>* c, bool forward)
+{
+    if (c->nranks == 1) return MHH_OK;
+    if (!c->comm) { c->err = "slab context without communicator: call mhh_comm_init first"; return MHH_E_INVALID; }
+    NcclApi* api = nccl_api(c->err);
+    if (!api) return MHH_E_CUDA;
+    const SpecLayout& l = c->lay;
+    cplx<TF>* X = reinterpret_cast<cplx<TF>*>(c->spec);
+    cplx<TF>* Y = reinterpret_cast<cplx<TF>*>(c->specT);
+    const size_t ybytes = sizeof(cplx<TF>) * (size_t)l.mcl * l.rows;      // every message on the y side has this size
+    NCCL_TRY(c, api, api->GroupStart());
+    for (int step = 1; step < l.P; ++step)
+    {
+        const int to = (l.rank + step) % l.P, from = (l.rank + l.P - step) % l.P;
+        cplx<TF>* xb_to = X + (size_t)l.offset(to) * l.rows;
+        cplx<TF>* xb_from = X + (size_t)l.offset(from) * l.rows;
+        const size_t xbytes_to = sizeof(cplx<TF>) * (size_t)l.count(to) * l.rows;
+        const size_t xbytes_from = sizeof(cplx<TF>) * (size_t)l.count(from) * l.rows;
+        if (forward)
+        {
+            NCCL_TRY(c, api, api->Send(xb_to, xbytes_to, ncclChar, to, c->comm, c->stream));
+            NCCL_TRY(c, api, api->Recv(Y + (size_t)from * l.mcl * l.rows, ybytes, ncclChar, from, c->comm, c->stream));
+        }
+        else
+        {
+            NCCL_TRY(c, api, api->Send(Y + (size_t)to * l.mcl * l.rows, ybytes, ncclChar, to, c->comm, c->stream));
+            NCCL_TRY(c, api, api->Recv(xb_from, xbytes_from, ncclChar, from, c->comm, c->stream));
+        }
+    }
+    NCCL_TRY(c, api, api->GroupEnd());
+    cplx<TF>* xs = X + (size_t)l.offset(l.rank) * l.rows;
+    cplx<TF>* ys = Y + (size_t)l.rank * l.mcl * l.rows;
+    CUDA_TRY(c, cudaMemcpyAsync(forward ? ys : xs, forward ? xs : ys, ybytes, cudaMemcpyDeviceToDevice, c->stream));
+    prof_mark(c, forward ? "all_to_all_xy_nccl" : "all_to_all_yx_nccl");
+    return MHH_OK;
+}
+
 template <typename TF>
 int pres_spectral_solve(Ctx<TF>* c, bool do_solve)
 {
     const GridDev<TF>& g = c->g;
+    const int mcl = c->lay.mcl;
+    int rc;
+    if ((rc = slab_all_to_all<TF>(c, true)) != MHH_OK) return rc;
     const int grid_p = c->num_sms * 2;
-    const long long ypanels = (long long)((c->nm + WFFT_WARPS - 1) / WFFT_WARPS) * g.ktot;
-    const int grid_wy = (int)std::min<long long>(ypanels, (long long)c->num_sms * 8);
+    const long long ypanels = (long long)((mcl + WFFT_WARPS - 1) / WFFT_WARPS) * g.ktot;
+    const int grid_wy = (int)std::max<long long>(1, std::min<long long>(ypanels, (long long)c->num_sms * 8));
     if (g.jtot > 1)
     {
-        if (c->wfft_y) wfft_y_launch<TF>(g.jtot, grid_wy, c->stream, c->spec, c->nm, g.ktot, c->tw_y, 0);
-        else fft_y_kernel<TF><<<grid_p, 256, c->smem_y, c->stream>>>(c->spec, c->nm, g.jtot, g.ktot, c->plan_y, c->tw_y, c->mc_y, 0);
+        if (c->wfft_y) wfft_y_launch<TF>(g.jtot, grid_wy, c->stream, c->specT, c->lay, mcl, g.ktot, c->tw_y, 0);
+        else fft_y_kernel<TF><<<grid_p, 256, c->smem_y, c->stream>>>(c->specT, c->lay, mcl, g.jtot, g.ktot, c->plan_y, c->tw_y, c->mc_y, 0);
         KCHECKN(c, "fft_y_forward_kernel");
     }
     if (do_solve)
     {
-        const long long ncol = (long long)c->nm * g.jtot;
-        tdma_solve_kernel<TF><<<(unsigned)((ncol + 127) / 128), 128, 0, c->stream>>>(c->spec, c->fac, c->coef(), c->nm, g.jtot, g.kmax, 0, 0);
+        const long long ncol = (long long)mcl * g.jtot;
+        tdma_solve_kernel<TF><<<(unsigned)((ncol + 127) / 128), 128, 0, c->stream>>>(c->specT, c->fac, c->coef(), c->lay, mcl, g.jtot, g.kmax, c->lay.m_off, 0);
         KCHECKN(c, "tdma_solve_kernel");
     }
     if (g.jtot > 1)
     {
-        if (c->wfft_y) wfft_y_launch<TF>(g.jtot, grid_wy, c->stream, c->spec, c->nm, g.ktot, c->tw_y, 1);
-        else fft_y_kernel<TF><<<grid_p, 256, c->smem_y, c->stream>>>(c->spec, c->nm, g.jtot, g.ktot, c->plan_y, c->tw_y, c->mc_y, 1);
+        if (c->wfft_y) wfft_y_launch<TF>(g.jtot, grid_wy, c->stream, c->specT, c->lay, mcl, g.ktot, c->tw_y, 1);
+        else fft_y_kernel<TF><<<grid_p, 256, c->smem_y, c->stream>>>(c->specT, c->lay, mcl, g.jtot, g.ktot, c->plan_y, c->tw_y, c->mc_y, 1);
         KCHECKN(c, "fft_y_backward_kernel");
     }
-    return MHH_OK;
+    return slab_all_to_all<TF>(c, false);
 }
 
 template <typename TF>
@@ -841,20 +1022,34 @@ int pres_solve_impl(Ctx<TF>* c, const mhh_fields* f, double sub_dt)
     NEED_BASE(c);
     const GridDev<TF>& g = c->g;
     NEED(c, f->p, "p");
-    RhsSrc<TF> src{P<TF>(f->u), P<TF>(f->v), P<TF>(f->w), P<TF>(f->ut), P<TF>(f->vt), P<TF>(f->wt), (TF)(TF(1.) / sub_dt)};
-    const long long nrows = (long long)g.jtot * g.ktot;
+    const bool slab = c->nranks > 1;
+    if (slab)
+    {
+        // the divergence needs vt one row beyond the slab (src/pres_2.cxx:181 exchanges vt north-south)
+        TF* vt = P<TF>(f->vt);
+        int rc0 = exchange_ns<TF>(c, &vt, 1, 1, g.kcells);
+        if (rc0 != MHH_OK) return rc0;
+    }
+    RhsSrc<TF> src{P<TF>(f->u), P<TF>(f->v), P<TF>(f->w), P<TF>(f->ut), P<TF>(f->vt), P<TF>(f->wt), (TF)(TF(1.) / sub_dt), slab ? 0 : 1};
+    const long long nrows = (long long)g.jmax * g.ktot;
     const int grid_x = (int)std::min<long long>((nrows + c->rows_x - 1) / c->rows_x, (long long)c->num_sms * 4);
     const int grid_wx = (int)std::min<long long>((nrows + WFFT_WARPS - 1) / WFFT_WARPS, (long long)c->num_sms * 8);
-    if (c->wfft_x) wfft_x_forward_launch<TF>(g.itot / 2, true, grid_wx, c->stream, c->spec, src, g, c->tw_xh, c->tw_xf, nrows);
-    else fft_x_forward_kernel<TF, true><<<grid_x, 256, c->smem_x, c->stream>>>(c->spec, src, g, c->plan_x, c->tw_xh, c->tw_xf, c->rows_x, nrows);
+    if (c->wfft_x) wfft_x_forward_launch<TF>(g.itot / 2, true, grid_wx, c->stream, c->spec, src, g, c->lay, c->tw_xh, c->tw_xf, nrows);
+    else fft_x_forward_kernel<TF, true><<<grid_x, 256, c->smem_x, c->stream>>>(c->spec, src, g, c->lay, c->plan_x, c->tw_xh, c->tw_xf, c->rows_x, nrows);
     KCHECKN(c, "fft_x_forward_kernel");
     int rc = pres_spectral_solve<TF>(c, true);
     if (rc != MHH_OK) return rc;
     const TF norm = TF(1.) / ((TF)g.itot * (TF)g.jtot);
-    if (c->wfft_x) wfft_x_backward_launch<TF>(g.itot / 2, grid_wx, c->stream, c->spec, P<TF>(f->p), g, c->tw_xh, c->tw_xf, nrows, norm, 1);
-    else fft_x_backward_kernel<TF><<<grid_x, 256, c->smem_x, c->stream>>>(c->spec, P<TF>(f->p), g, c->plan_x, c->tw_xh, c->tw_xf,
-            c->rows_x, nrows, norm, 1);
+    const int fill = slab ? 0 : 1;          // slabs get their north/south ghost rows of p from the neighbours below
+    if (c->wfft_x) wfft_x_backward_launch<TF>(g.itot / 2, grid_wx, c->stream, c->spec, P<TF>(f->p), g, c->lay, c->tw_xh, c->tw_xf, nrows, norm, fill);
+    else fft_x_backward_kernel<TF><<<grid_x, 256, c->smem_x, c->stream>>>(c->spec, P<TF>(f->p), g, c->lay, c->plan_x, c->tw_xh, c->tw_xf,
+            c->rows_x, nrows, norm, fill);
     KCHECKN(c, "fft_x_backward_kernel");
+    if (slab)
+    {
+        TF* pp = P<TF>(f->p);
+        return exchange_ns<TF>(c, &pp, 1, g.jgc, g.kcells);
+    }
     if (g.jtot == 1)
         return cyclic_impl<TF>(c, P<TF>(f->p), MHH_EDGE_NORTH_SOUTH, false);
     return MHH_OK;
@@ -904,11 +1099,9 @@ int substep_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, int sub
     if (rc != MHH_OK) return rc;
     NEED(c, f->p, "p");
     // 1. boundary.set_prognostic_cyclic_bcs + set_ghost_cells
-    TF* mom[3] = {P<TF>(f->u), P<TF>(f->v), P<TF>(f->w)};
-    for (int n = 0; n < 3; ++n)
-        if ((rc = cyclic_impl<TF>(c, mom[n], MHH_EDGE_BOTH, false)) != MHH_OK) return rc;
-    for (int n = 0; n < f->ns; ++n)
-        if ((rc = cyclic_impl<TF>(c, P<TF>(f->s[n]), MHH_EDGE_BOTH, false)) != MHH_OK) return rc;
+    TF* prog[3 + MHH_MAX_SCALARS] = {P<TF>(f->u), P<TF>(f->v), P<TF>(f->w)};
+    for (int n = 0; n < f->ns; ++n) prog[3 + n] = P<TF>(f->s[n]);
+    if ((rc = cyclic_fields<TF>(c, prog, 3 + f->ns)) != MHH_OK) return rc;
     if ((rc = ghost_impl<TF>(c, P<TF>(f->u), prm->mbcbot, P<TF>(f->u_bot), P<TF>(f->u_gradbot), prm->mbctop, P<TF>(f->u_top), P<TF>(f->u_gradtop))) != MHH_OK) return rc;
     if ((rc = ghost_impl<TF>(c, P<TF>(f->v), prm->mbcbot, P<TF>(f->v_bot), P<TF>(f->v_gradbot), prm->mbctop, P<TF>(f->v_top), P<TF>(f->v_gradtop))) != MHH_OK) return rc;
     for (int n = 0; n < f->ns; ++n)
@@ -970,6 +1163,7 @@ int fft_roundtrip_impl(Ctx<TF>* c, const TF* in, TF* out, int solve)
     NEED_BASE(c);
     const GridDev<TF>& g = c->g;
     NEED(c, in, "in"); NEED(c, out, "out");
+    if (c->nranks > 1) { c->err = "pres_fft_roundtrip is a single-GPU test entry point"; return MHH_E_INVALID; }
     // stage the compact input in the workspace rows (pitch 2*nm)
     CUDA_TRY(c, cudaMemcpy2DAsync(c->spec, sizeof(TF) * 2 * c->nm, in, sizeof(TF) * g.itot, sizeof(TF) * g.itot,
                                   (size_t)g.jtot * g.ktot, cudaMemcpyDeviceToDevice, c->stream));
@@ -977,8 +1171,8 @@ int fft_roundtrip_impl(Ctx<TF>* c, const TF* in, TF* out, int solve)
     const int grid_x = (int)std::min<long long>((nrows + c->rows_x - 1) / c->rows_x, (long long)c->num_sms * 4);
     RhsSrc<TF> none{};
     const int grid_wx = (int)std::min<long long>((nrows + WFFT_WARPS - 1) / WFFT_WARPS, (long long)c->num_sms * 8);
-    if (c->wfft_x) wfft_x_forward_launch<TF>(g.itot / 2, false, grid_wx, c->stream, c->spec, none, g, c->tw_xh, c->tw_xf, nrows);
-    else fft_x_forward_kernel<TF, false><<<grid_x, 256, c->smem_x, c->stream>>>(c->spec, none, g, c->plan_x, c->tw_xh, c->tw_xf, c->rows_x, nrows);
+    if (c->wfft_x) wfft_x_forward_launch<TF>(g.itot / 2, false, grid_wx, c->stream, c->spec, none, g, c->lay, c->tw_xh, c->tw_xf, nrows);
+    else fft_x_forward_kernel<TF, false><<<grid_x, 256, c->smem_x, c->stream>>>(c->spec, none, g, c->lay, c->plan_x, c->tw_xh, c->tw_xf, c->rows_x, nrows);
     KCHECKN(c, "fft_x_forward_kernel");
     int rc = pres_spectral_solve<TF>(c, solve != 0);
     if (rc != MHH_OK) return rc;
@@ -986,8 +1180,8 @@ int fft_roundtrip_impl(Ctx<TF>* c, const TF* in, TF* out, int solve)
     TF* tmp = nullptr;
     CUDA_TRY(c, cudaMalloc(&tmp, sizeof(TF) * (size_t)g.ncells));
     const TF norm = TF(1.) / ((TF)g.itot * (TF)g.jtot);
-    if (c->wfft_x) wfft_x_backward_launch<TF>(g.itot / 2, grid_wx, c->stream, c->spec, tmp, g, c->tw_xh, c->tw_xf, nrows, norm, 0);
-    else fft_x_backward_kernel<TF><<<grid_x, 256, c->smem_x, c->stream>>>(c->spec, tmp, g, c->plan_x, c->tw_xh, c->tw_xf, c->rows_x, nrows, norm, 0);
+    if (c->wfft_x) wfft_x_backward_launch<TF>(g.itot / 2, grid_wx, c->stream, c->spec, tmp, g, c->lay, c->tw_xh, c->tw_xf, nrows, norm, 0);
+    else fft_x_backward_kernel<TF><<<grid_x, 256, c->smem_x, c->stream>>>(c->spec, tmp, g, c->lay, c->plan_x, c->tw_xh, c->tw_xf, c->rows_x, nrows, norm, 0);
     c->launches++;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess)
@@ -1058,6 +1252,61 @@ int mhh_set_stream(mhh_ctx* ctx, void* s)
 }
 
 long long mhh_launch_count(const mhh_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int mhh_comm_get_unique_id(void* id, int nbytes)
+{
+    if (!id || nbytes < (int)sizeof(ncclUniqueId)) return MHH_E_INVALID;
+    std::string err;
+    NcclApi* api = nccl_api(err);
+    if (!api) return MHH_E_CUDA;
+    ncclUniqueId u;
+    if (api->GetUniqueId(&u) != ncclSuccess) return MHH_E_CUDA;
+    memset(id, 0, (size_t)nbytes);
+    memcpy(id, &u, sizeof(u));
+    return MHH_OK;
+}
+
+int mhh_comm_init(mhh_ctx* ctx, const void* id, int nbytes)
+{
+    if (!ctx) return MHH_E_INVALID;
+    if (!id || nbytes < (int)sizeof(ncclUniqueId)) { ctx->err = "comm_init: bad unique id"; return MHH_E_INVALID; }
+    if (ctx->comm) { ctx->err = "comm_init: communicator already set"; return MHH_E_INVALID; }
+    if (ctx->nranks == 1) return MHH_OK;              // nothing to connect
+    NcclApi* api = nccl_api(ctx->err);
+    if (!api) return MHH_E_CUDA;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    ncclUniqueId u;
+    memcpy(&u, id, sizeof(u));
+    NCCL_TRY(ctx, api, api->CommInitRank(&ctx->comm, ctx->nranks, u, ctx->rank));
+    return MHH_OK;
+}
+
+int mhh_slab_layout(int itot, int jtot, int ktot, int npy, int rank, mhh_slab_info* out)
+{
+    if (!out || npy < 1 || rank < 0 || rank >= npy || itot < 2 || jtot < 1 || ktot < 1 || jtot % npy != 0 || itot / 2 + 1 < npy) return MHH_E_INVALID;
+    const SpecLayout l = make_spec_layout(itot, jtot, ktot, npy, rank);
+    out->nm = l.nm; out->mcl = l.mcl; out->m_off = l.m_off; out->jmax = l.jmax;
+    out->rows = l.rows;
+    out->xside_elems = (long long)l.nm * l.rows;
+    out->yside_elems = (long long)l.mcl * jtot * ktot;
+    return MHH_OK;
+}
+
+long long mhh_slab_xindex(int itot, int jtot, int ktot, int npy, int rank, long long row, int m)
+{
+    if (npy < 1 || rank < 0 || rank >= npy || jtot % npy != 0 || itot / 2 + 1 < npy) return -1;
+    const SpecLayout l = make_spec_layout(itot, jtot, ktot, npy, rank);
+    if (row < 0 || row >= l.rows || m < 0 || m >= l.nm) return -1;
+    return l.xidx(row, m);
+}
+
+long long mhh_slab_yindex(int itot, int jtot, int ktot, int npy, int rank, int k, int j, int ml)
+{
+    if (npy < 1 || rank < 0 || rank >= npy || jtot % npy != 0 || itot / 2 + 1 < npy) return -1;
+    const SpecLayout l = make_spec_layout(itot, jtot, ktot, npy, rank);
+    if (k < 0 || k >= ktot || j < 0 || j >= jtot || ml < 0 || ml >= l.mcl) return -1;
+    return l.yidx(k, j, ml);
+}
 
 int mhh_profile_start(mhh_ctx* ctx)
 {

@@ -132,7 +132,7 @@ template <typename TF, int L> constexpr size_t wfft_smem() { return (size_t)WFFT
 // x forward, fused with Pres_2::input: one warp per (j,k) row of itot = 2L reals.
 // ------------------------------------------------------------------------------------------
 template <typename TF, int L, bool RHS_FUSED>
-__global__ void __launch_bounds__(32 * WFFT_WARPS) wfft_x_forward_kernel(TF* __restrict__ spec, const RhsSrc<TF> src, const GridDev<TF> g,
+__global__ void __launch_bounds__(32 * WFFT_WARPS) wfft_x_forward_kernel(TF* __restrict__ spec, const RhsSrc<TF> src, const GridDev<TF> g, const SpecLayout lay,
         const cplx<TF>* __restrict__ tw_half, const cplx<TF>* __restrict__ tw_full, const long long nrows)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -146,11 +146,11 @@ __global__ void __launch_bounds__(32 * WFFT_WARPS) wfft_x_forward_kernel(TF* __r
     {
         if (RHS_FUSED)
         {
-            const int kq = (int)(r / g.jtot);
+            const int kq = (int)(r / g.jmax);
             const int k = kq + g.kstart;
-            const int j = (int)(r - (long long)kq * g.jtot) + g.jstart;
+            const int j = (int)(r - (long long)kq * g.jmax) + g.jstart;
             const long long base = g.istart + j * jj + k * kk;
-            const long long jn_off = (j + 1 == g.jend) ? (1 - g.jtot) * jj : jj;
+            const long long jn_off = (src.ywrap && j + 1 == g.jend) ? (1 - g.jmax) * jj : jj;
             const TF rho = g.rhoref[k], rhoh0 = g.rhorefh[k], rhoh1 = g.rhorefh[k + 1], dzi = g.dzi[k];
 #pragma unroll 2
             for (int n = lane; n < L; n += 32)
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(32 * WFFT_WARPS) wfft_x_forward_kernel(TF* __r
         __syncwarp();
         wfft<TF, L>(row, tw_half, lane);
         // real-FFT post-processing: X[m] = E[m] + W_N^m O[m], m = 0..L
-        cplx<TF>* out = reinterpret_cast<cplx<TF>*>(spec + r * (2 * nm));
+        cplx<TF>* out = reinterpret_cast<cplx<TF>*>(spec) + (lay.P == 1 ? r * nm : 0);
 #pragma unroll
         for (int m = lane; m < nm; m += 32)
         {
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(32 * WFFT_WARPS) wfft_x_forward_kernel(TF* __r
             const cplx<TF> zc = cconj(row[fpad(digitrev<L>(m == 0 ? 0 : L - m))]);
             const cplx<TF> e = {TF(0.5) * (zm.x + zc.x), TF(0.5) * (zm.y + zc.y)};
             const cplx<TF> d = {TF(0.5) * (zm.x - zc.x), TF(0.5) * (zm.y - zc.y)};
-            out[m] = cadd(e, cmul(tw_full[m], cmul_mi(d)));
+            out[lay.P == 1 ? (long long)m : lay.xidx(r, m)] = cadd(e, cmul(tw_full[m], cmul_mi(d)));
         }
         __syncwarp();
     }
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(32 * WFFT_WARPS) wfft_x_forward_kernel(TF* __r
 // x backward fused with Pres_2::solve's unpack (ghost cells in x, y and the bottom level).
 // ------------------------------------------------------------------------------------------
 template <typename TF, int L>
-__global__ void __launch_bounds__(32 * WFFT_WARPS) wfft_x_backward_kernel(const TF* __restrict__ spec, TF* __restrict__ p, const GridDev<TF> g,
+__global__ void __launch_bounds__(32 * WFFT_WARPS) wfft_x_backward_kernel(const TF* __restrict__ spec, TF* __restrict__ p, const GridDev<TF> g, const SpecLayout lay,
         const cplx<TF>* __restrict__ tw_half, const cplx<TF>* __restrict__ tw_full, const long long nrows, const TF norm, const int fill_y_ghosts)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -209,12 +209,12 @@ __global__ void __launch_bounds__(32 * WFFT_WARPS) wfft_x_backward_kernel(const 
     {
         // Z'[m] = (X[m] + conj X[L-m]) + i e^{+2 pi i m/N} (X[m] - conj X[L-m]); conj(Z') goes in so that the forward
         // transform yields conj(inverse)
-        const cplx<TF>* X = reinterpret_cast<const cplx<TF>*>(spec + r * (2 * nm));
+        const cplx<TF>* X = reinterpret_cast<const cplx<TF>*>(spec) + (lay.P == 1 ? r * nm : 0);
 #pragma unroll
         for (int m = lane; m < L; m += 32)
         {
-            const cplx<TF> xm = X[m];
-            const cplx<TF> xc = cconj(X[L - m]);
+            const cplx<TF> xm = X[lay.P == 1 ? (long long)m : lay.xidx(r, m)];
+            const cplx<TF> xc = cconj(X[lay.P == 1 ? (long long)(L - m) : lay.xidx(r, L - m)]);
             const cplx<TF> e = cadd(xm, xc);
             const cplx<TF> d = csub(xm, xc);
             const cplx<TF> wd = cmul(cconj(tw_full[m]), d);
@@ -222,10 +222,10 @@ __global__ void __launch_bounds__(32 * WFFT_WARPS) wfft_x_backward_kernel(const 
         }
         __syncwarp();
         wfft<TF, L>(row, tw_half, lane);
-        const int kq = (int)(r / g.jtot);
-        const int jq = (int)(r - (long long)kq * g.jtot);
+        const int kq = (int)(r / g.jmax);
+        const int jq = (int)(r - (long long)kq * g.jmax);
         const long long rowbase = (jq + g.jstart) * jj + (kq + g.kstart) * kk;
-        const bool ylo = fill_y_ghosts && jq < g.jgc, yhi = fill_y_ghosts && jq >= g.jtot - g.jgc;
+        const bool ylo = fill_y_ghosts && jq < g.jgc, yhi = fill_y_ghosts && jq >= g.jmax - g.jgc;
         const int wtot = g.itot + 2 * g.igc;
         for (int ic = lane; ic < wtot; ic += 32)
         {
@@ -236,8 +236,8 @@ __global__ void __launch_bounds__(32 * WFFT_WARPS) wfft_x_backward_kernel(const 
             const long long o = ic + rowbase;
             p[o] = val;
             if (kq == 0) p[o - kk] = val;
-            if (ylo) { p[o + g.jtot * jj] = val; if (kq == 0) p[o + g.jtot * jj - kk] = val; }
-            if (yhi) { p[o - g.jtot * jj] = val; if (kq == 0) p[o - g.jtot * jj - kk] = val; }
+            if (ylo) { p[o + g.jmax * jj] = val; if (kq == 0) p[o + g.jmax * jj - kk] = val; }
+            if (yhi) { p[o - g.jmax * jj] = val; if (kq == 0) p[o - g.jmax * jj - kk] = val; }
         }
         __syncwarp();
     }
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(32 * WFFT_WARPS) wfft_x_backward_kernel(const 
 // bytes per y in fp64) of one level, each warp transforms one mode, the panel goes back in place.
 // ------------------------------------------------------------------------------------------
 template <typename TF, int J>
-__global__ void __launch_bounds__(32 * WFFT_WARPS) wfft_y_kernel(TF* __restrict__ spec, const int nm, const int ktot,
+__global__ void __launch_bounds__(32 * WFFT_WARPS) wfft_y_kernel(TF* __restrict__ spec, const SpecLayout lay, const int nm, const int ktot,
         const cplx<TF>* __restrict__ tw, const int inverse)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -265,13 +265,14 @@ __global__ void __launch_bounds__(32 * WFFT_WARPS) wfft_y_kernel(TF* __restrict_
         const int k = (int)(pnl / npanel_m);
         const int m0 = (int)(pnl - (long long)k * npanel_m) * MC;
         const int mc = min(MC, nm - m0);
-        cplx<TF>* base = S + (long long)k * J * nm + m0;
+        cplx<TF>* base = S + (long long)k * J * nm + m0;      // P == 1 addressing; slabs go through lay.yidx
+        const bool one = lay.P == 1;
         if (c < mc)
         {
 #pragma unroll 4
             for (int j = j0; j < J; j += NT / MC)
             {
-                cplx<TF> v = base[(long long)j * nm + c];
+                cplx<TF> v = one ? base[(long long)j * nm + c] : S[lay.yidx(k, j, m0 + c)];
                 if (inverse) v.y = -v.y;
                 sm[c * RS + fpad(j)] = v;
             }
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(32 * WFFT_WARPS) wfft_y_kernel(TF* __restrict_
             {
                 cplx<TF> v = sm[c * RS + fpad(digitrev<J>(j))];
                 if (inverse) v.y = -v.y;
-                base[(long long)j * nm + c] = v;
+                if (one) base[(long long)j * nm + c] = v; else S[lay.yidx(k, j, m0 + c)] = v;
             }
         }
         __syncthreads();

@@ -32,6 +32,67 @@ struct FftPlan
     int log2nb[16];   // log2 of the butterflies per sequence (n / radix), or -1
 };
 
+// ------------------------------------------------------------------------------------------
+// Spectral workspace layout, single GPU and y-slab decomposition (npx = 1, npy = P).
+//   x side (after the x transform): rank-local rows r = jl + k*jmax, all nm x-modes, stored as P
+//     blocks -- block d holds the modes owned by rank d, [r][m - m_off(d)] -- so that block d IS the
+//     all-to-all message for rank d (no pack pass).
+//   y side (after the all-to-all): this rank's mcl modes for ALL jtot rows, stored as P blocks --
+//     block s is the message received from rank s, [k*jmax + jl][ml] -- so the y transform and the
+//     tridiagonal solve read the receive buffer directly (no unpack pass).
+//   Modes are dealt out evenly: base = nm / P each, the first nm % P ranks get one more.
+//   P = 1 degenerates to S[k][j][m] with pitch nm (one buffer, no exchange).
+// Semantic model: reference src/transpose.cxx:117-271 (exec_xy / exec_yx) + src/fft.cxx:455-587.
+// ------------------------------------------------------------------------------------------
+struct SpecLayout
+{
+    int P;        // ranks along y
+    int rank;
+    int nm;       // x-modes in total (itot/2 + 1)
+    int base, rem;
+    int jmax, jtot, ktot;
+    int mcl;      // modes owned by this rank
+    int m_off;    // first owned mode
+    long long rows;   // jmax*ktot
+
+    __host__ __device__ int count(const int d) const { return base + (d < rem ? 1 : 0); }
+    __host__ __device__ int offset(const int d) const { return d * base + (d < rem ? d : rem); }
+    __host__ __device__ int owner(const int m) const
+    {
+        const int cut = rem * (base + 1);
+        return m < cut ? m / (base + 1) : rem + (m - cut) / base;
+    }
+    // x side: complex index of (row r, mode m)
+    __host__ __device__ long long xidx(const long long r, const int m) const
+    {
+        if (P == 1) return r * nm + m;
+        const int d = owner(m);
+        const int o = offset(d);
+        return (long long)o * rows + r * count(d) + (m - o);
+    }
+    // y side: complex index of (level k, global row j, local mode ml)
+    __host__ __device__ long long yidx(const int k, const int j, const int ml) const
+    {
+        if (P == 1) return ((long long)k * jtot + j) * nm + ml;
+        const int s = j / jmax;
+        const int jl = j - s * jmax;
+        return (long long)s * mcl * rows + ((long long)k * jmax + jl) * mcl + ml;
+    }
+    // y side: a column (fixed j, ml) advances by this many complex elements per level
+    __host__ __device__ long long ykstride() const { return (long long)jmax * mcl; }
+};
+
+inline SpecLayout make_spec_layout(int itot, int jtot, int ktot, int P, int rank)
+{
+    SpecLayout s{};
+    s.P = P; s.rank = rank; s.nm = itot / 2 + 1;
+    s.base = s.nm / P; s.rem = s.nm % P;
+    s.jmax = jtot / P; s.jtot = jtot; s.ktot = ktot;
+    s.mcl = s.count(rank); s.m_off = s.offset(rank);
+    s.rows = (long long)s.jmax * ktot;
+    return s;
+}
+
 // integer division / remainder by a value whose log2 is known (or -1 -> generic)
 __device__ __forceinline__ void divmod(const int x, const int d, const int lg, int& quo, int& rem)
 {
@@ -186,10 +247,11 @@ struct RhsSrc
 {
     const TF* u; const TF* v; const TF* w; const TF* ut; const TF* vt; const TF* wt;
     TF dti;
+    int ywrap;      // 1: the block is periodic in y by itself (single GPU); 0: read the exchanged north ghost row of vt / v
 };
 
 template <typename TF, bool RHS_FUSED>
-__global__ void fft_x_forward_kernel(TF* __restrict__ spec, const RhsSrc<TF> src, const GridDev<TF> g,
+__global__ void fft_x_forward_kernel(TF* __restrict__ spec, const RhsSrc<TF> src, const GridDev<TF> g, const SpecLayout lay,
         const FftPlan plan, const cplx<TF>* __restrict__ tw_half, const cplx<TF>* __restrict__ tw_full,
         const int rows_per_cta, const long long nrows)
 {
@@ -216,11 +278,11 @@ __global__ void fft_x_forward_kernel(TF* __restrict__ spec, const RhsSrc<TF> src
             TF* dst = reinterpret_cast<TF*>(buf0 + r * ld);
             if (RHS_FUSED)
             {
-                const int kq = (int)(row / g.jtot);
+                const int kq = (int)(row / g.jmax);
                 const int k = kq + g.kstart;
-                const int j = (int)(row - (long long)kq * g.jtot) + g.jstart;
+                const int j = (int)(row - (long long)kq * g.jmax) + g.jstart;
                 const long long base = g.istart + j * jj + k * kk;
-                const long long jn_off = (j + 1 == g.jend) ? (1 - g.jtot) * jj : jj;
+                const long long jn_off = (src.ywrap && j + 1 == g.jend) ? (1 - g.jmax) * jj : jj;
                 const TF dti = src.dti;
                 const TF rho = g.rhoref[k], rhoh0 = g.rhorefh[k], rhoh1 = g.rhorefh[k + 1], dzi = g.dzi[k];
                 const int i = i0 + lane;
@@ -251,7 +313,7 @@ __global__ void fft_x_forward_kernel(TF* __restrict__ spec, const RhsSrc<TF> src
             const int r = wi / nchM;
             const int m = ((wi - r * nchM) << 5) + lane;
             const cplx<TF>* z = Z + r * ld;
-            cplx<TF>* out = reinterpret_cast<cplx<TF>*>(spec + (row0 + r) * (2 * nm));
+            cplx<TF>* out = reinterpret_cast<cplx<TF>*>(spec);
             if (m < nm)
             {
                 const cplx<TF> zm = z[m == L ? 0 : m];
@@ -259,7 +321,7 @@ __global__ void fft_x_forward_kernel(TF* __restrict__ spec, const RhsSrc<TF> src
                 const cplx<TF> e = {TF(0.5) * (zm.x + zc.x), TF(0.5) * (zm.y + zc.y)};
                 const cplx<TF> d = {TF(0.5) * (zm.x - zc.x), TF(0.5) * (zm.y - zc.y)};
                 const cplx<TF> o = cmul_mi(d);                  // (zm - zc)/(2i)
-                out[m] = cadd(e, cmul(tw_full[m], o));           // tw_full[m] = exp(-2 pi i m / N)
+                out[lay.xidx(row0 + r, m)] = cadd(e, cmul(tw_full[m], o));           // tw_full[m] = exp(-2 pi i m / N)
             }
         }
         __syncthreads();
@@ -273,7 +335,7 @@ __global__ void fft_x_forward_kernel(TF* __restrict__ spec, const RhsSrc<TF> src
 // (src/pres_2.cxx:339-361), so no separate copy / boundary_cyclic pass over p is needed.
 // ------------------------------------------------------------------------------------------
 template <typename TF>
-__global__ void fft_x_backward_kernel(const TF* __restrict__ spec, TF* __restrict__ p, const GridDev<TF> g,
+__global__ void fft_x_backward_kernel(const TF* __restrict__ spec, TF* __restrict__ p, const GridDev<TF> g, const SpecLayout lay,
         const FftPlan plan, const cplx<TF>* __restrict__ tw_half, const cplx<TF>* __restrict__ tw_full,
         const int rows_per_cta, const long long nrows, const TF norm, const int fill_y_ghosts)
 {
@@ -297,11 +359,11 @@ __global__ void fft_x_backward_kernel(const TF* __restrict__ spec, TF* __restric
         {
             const int r = wi / nchL;
             const int m = ((wi - r * nchL) << 5) + lane;
-            const cplx<TF>* X = reinterpret_cast<const cplx<TF>*>(spec + (row0 + r) * (2 * nm));
+            const cplx<TF>* X = reinterpret_cast<const cplx<TF>*>(spec);
             if (m < L)
             {
-                const cplx<TF> xm = X[m];
-                const cplx<TF> xc = cconj(X[L - m]);
+                const cplx<TF> xm = X[lay.xidx(row0 + r, m)];
+                const cplx<TF> xc = cconj(X[lay.xidx(row0 + r, L - m)]);
                 const cplx<TF> e = cadd(xm, xc);
                 const cplx<TF> d = csub(xm, xc);
                 const cplx<TF> wd = cmul(cconj(tw_full[m]), d);  // exp(+2 pi i m / N) * d
@@ -318,10 +380,10 @@ __global__ void fft_x_backward_kernel(const TF* __restrict__ spec, TF* __restric
             const int r = wi / nchW;
             const int ic = ((wi - r * nchW) << 5) + lane;
             const long long row = row0 + r;
-            const int kq = (int)(row / g.jtot);
-            const int jq = (int)(row - (long long)kq * g.jtot);
+            const int kq = (int)(row / g.jmax);
+            const int jq = (int)(row - (long long)kq * g.jmax);
             const long long rowbase = (jq + g.jstart) * jj + (kq + g.kstart) * kk;
-            const bool ylo = fill_y_ghosts && jq < g.jgc, yhi = fill_y_ghosts && jq >= g.jtot - g.jgc;
+            const bool ylo = fill_y_ghosts && jq < g.jgc, yhi = fill_y_ghosts && jq >= g.jmax - g.jgc;
             const cplx<TF>* z = Z + r * ld;
             if (ic < wtot)
             {
@@ -334,13 +396,13 @@ __global__ void fft_x_backward_kernel(const TF* __restrict__ spec, TF* __restric
                 if (kq == 0) p[base - kk] = val;
                 if (ylo)
                 {
-                    p[base + g.jtot * jj] = val;
-                    if (kq == 0) p[base + g.jtot * jj - kk] = val;
+                    p[base + g.jmax * jj] = val;
+                    if (kq == 0) p[base + g.jmax * jj - kk] = val;
                 }
                 if (yhi)
                 {
-                    p[base - g.jtot * jj] = val;
-                    if (kq == 0) p[base - g.jtot * jj - kk] = val;
+                    p[base - g.jmax * jj] = val;
+                    if (kq == 0) p[base - g.jmax * jj - kk] = val;
                 }
             }
         }
@@ -353,7 +415,7 @@ __global__ void fft_x_backward_kernel(const TF* __restrict__ spec, TF* __restric
 // inverse != 0 -> unnormalised inverse (conjugate trick).
 // ------------------------------------------------------------------------------------------
 template <typename TF>
-__global__ void fft_y_kernel(TF* __restrict__ spec, const int nm, const int jtot, const int ktot,
+__global__ void fft_y_kernel(TF* __restrict__ spec, const SpecLayout lay, const int nm, const int jtot, const int ktot,
         const FftPlan plan, const cplx<TF>* __restrict__ tw, const int MC, const int inverse)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -371,14 +433,13 @@ __global__ void fft_y_kernel(TF* __restrict__ spec, const int nm, const int jtot
         const int k = (int)(pnl / npanel_m);
         const int m0 = (int)(pnl % npanel_m) * MC;
         const int mc = min(MC, nm - m0);
-        cplx<TF>* base = S + (long long)k * jtot * nm + m0;
         for (int t = tid; t < jtot * MC; t += nth)
         {
             const int j = t >> lgMC;
             const int c = t & (MC - 1);
             if (c < mc)
             {
-                cplx<TF> v = base[(long long)j * nm + c];
+                cplx<TF> v = S[lay.yidx(k, j, m0 + c)];
                 if (inverse) v.y = -v.y;
                 buf0[c * ld + j] = v;
             }
@@ -393,7 +454,7 @@ __global__ void fft_y_kernel(TF* __restrict__ spec, const int nm, const int jtot
             {
                 cplx<TF> v = Z[c * ld + j];
                 if (inverse) v.y = -v.y;
-                base[(long long)j * nm + c] = v;
+                S[lay.yidx(k, j, m0 + c)] = v;
             }
         }
         __syncthreads();
@@ -448,7 +509,7 @@ __global__ void tdma_setup_kernel(TF* __restrict__ fac, const TdmaCoef<TF> cf, c
 
 template <typename TF>
 __global__ void __launch_bounds__(128) tdma_solve_kernel(TF* __restrict__ spec, const TF* __restrict__ fac, const TdmaCoef<TF> cf,
-        const int nm, const int jtot, const int kmax, const int m_off, const int l_off)
+        const SpecLayout lay, const int nm, const int jtot, const int kmax, const int m_off, const int l_off)
 {
     const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long ncol = (long long)nm * jtot;
@@ -456,7 +517,8 @@ __global__ void __launch_bounds__(128) tdma_solve_kernel(TF* __restrict__ spec, 
     const int l = (int)(col / nm), m = (int)(col % nm);
     const TF lam = cf.bmati[m + m_off] + cf.bmatj[l + l_off];
     const bool mode00 = (m + m_off == 0) && (l + l_off == 0);
-    cplx<TF>* S = reinterpret_cast<cplx<TF>*>(spec) + col;
+    cplx<TF>* S = reinterpret_cast<cplx<TF>*>(spec) + lay.yidx(0, l, m);
+    const long long ks = lay.ykstride();
 
     // forward sweep
     cplx<TF> prev;
@@ -474,19 +536,19 @@ __global__ void __launch_bounds__(128) tdma_solve_kernel(TF* __restrict__ spec, 
         const TF ak = cf.a[k];
         const TF w = tdma_b(cf, k, kmax, lam, mode00) - ak * f;
         const TF winv = TF(1) / w;
-        const cplx<TF> v = S[k * ncol];
+        const cplx<TF> v = S[k * ks];
         const TF d2 = cf.dz2[k];
         prev = {(d2 * v.x - ak * prev.x) * winv, (d2 * v.y - ak * prev.y) * winv};
-        S[k * ncol] = prev;
+        S[k * ks] = prev;
     }
     // back substitution
 #pragma unroll 4
     for (int k = kmax - 2; k >= 0; --k)
     {
         const TF f = fac[col + (k + 1) * ncol];
-        const cplx<TF> v = S[k * ncol];
+        const cplx<TF> v = S[k * ks];
         prev = {v.x - f * prev.x, v.y - f * prev.y};
-        S[k * ncol] = prev;
+        S[k * ks] = prev;
     }
 }
 

@@ -48,6 +48,24 @@ class Context:
             raise MhhError(f"mhh_ctx_create failed ({rc}): {msg}")
         # run on torch's current stream so torch.cuda.Event timing sees the kernels
         self.use_torch_stream()
+        if gd.npy > 1:
+            self.comm_init()
+
+    def comm_init(self):
+        """Connect the y-slab ranks (one process per GPU): rank 0 makes the NCCL unique id, torch.distributed
+        broadcasts the bytes (MicroHH's Master would use MPI_Bcast), every rank joins."""
+        import torch.distributed as dist
+        if not dist.is_initialized() or dist.get_world_size() != self.gd.npy or dist.get_rank() != self.gd.mpicoordy:
+            raise MhhError("slab context needs torch.distributed initialised with world_size = npy and rank = mpicoordy")
+        n = capi.MHH_COMM_ID_BYTES
+        buf = (C.c_ubyte * n)()
+        if dist.get_rank() == 0:
+            self.check(self.lib.mhh_comm_get_unique_id(buf, n))
+        dev = torch.device("cuda", self.device) if dist.get_backend() == "nccl" else torch.device("cpu")
+        t = torch.tensor(list(buf), dtype=torch.uint8, device=dev)
+        dist.broadcast(t, src=0)
+        buf = (C.c_ubyte * n)(*t.cpu().tolist())
+        self.check(self.lib.mhh_comm_init(self.h, buf, n))
 
     def use_torch_stream(self):
         s = torch.cuda.current_stream(self.device)

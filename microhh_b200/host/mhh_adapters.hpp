@@ -1,0 +1,310 @@
+// mhh_adapters.hpp -- drop-in adapters between MicroHH's scheme classes and libmhhb200's C ABI.
+//
+// This header is compiled INSIDE the MicroHH source tree (it includes MicroHH's own headers; none of
+// them is copied here).  Each adapter derives from the reference's abstract scheme class, keeps the
+// reference's constructor / virtual signatures, and forwards the device work to the C entry points
+// of include/mhhb200.h.  The factories (src/advec.cxx:54-98, src/diff.cxx:56-92, src/pres.cxx:67-86)
+// return these classes for the same .ini switches, so `microhh init/run`, the .ini/.nc case files and
+// the Field3d ghost-cell layout stay unchanged.  See INTEGRATION.md for the three factory edits.
+//
+//   reference class (interface)                     adapter                      C ABI
+//   Advec<TF>        include/advec.h:45-71          Advec_2i5_b200<TF>           mhh_advec_exec / mhh_advec_get_cfl
+//   Diff<TF>         include/diff.h:38-71           Diff_smag2_b200<TF>          mhh_diff_smag2_exec_viscosity / _exec / _get_dn
+//   Pres<TF>         include/pres.h:41-92           Pres_2_b200<TF>              mhh_pres_exec / mhh_pres_check_divergence
+//   Boundary_cyclic  include/boundary_cyclic.h:35   Boundary_cyclic_b200<TF>     mhh_boundary_cyclic / _2d
+//   Timeloop::exec   include/timeloop.h:65          timeloop_exec_b200()         mhh_timeloop_rk3
+//   Model::exec loop src/model.cxx:356-504          dycore_substep_b200()        mhh_dycore_substep (fused fast path)
+//
+// Errors: the C ABI never throws; MHH_CHECK rethrows as std::runtime_error, which main() already
+// turns into "message + exit code 1" (main/microhh.cxx:59-68).
+#pragma once
+
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "mhhb200.h"
+
+#include "master.h"
+#include "grid.h"
+#include "fields.h"
+#include "advec.h"
+#include "diff.h"
+#include "pres.h"
+#include "boundary.h"
+#include "boundary_cyclic.h"
+#include "thermo.h"
+#include "stats.h"
+#include "constants.h"
+
+namespace mhhb200
+{
+    inline void check(mhh_ctx* ctx, const int rc, const char* what)
+    {
+        if (rc != MHH_OK)
+            throw std::runtime_error(std::string("mhhb200: ") + what + ": " + mhh_last_error(ctx));
+    }
+    #define MHH_CHECK(ctx, call) ::mhhb200::check((ctx), (call), #call)
+
+    template<typename TF> constexpr int dtype_of() { return sizeof(TF) == 8 ? MHH_F64 : MHH_F32; }
+
+    // One context per process (= per GPU), shared by all adapters of a Model.  Created after Grid::create
+    // and Fields::create, because the metric arrays and the base state are inputs.
+    template<typename TF>
+    class Context
+    {
+        public:
+            Context(Master& master, Grid<TF>& grid, Fields<TF>& fields, const int device=0)
+            {
+                const Grid_data<TF>& gd = grid.get_grid_data();
+                const MPI_data& md = master.get_MPI_data();
+                mhh_grid_desc d{};
+                d.itot = gd.itot; d.jtot = gd.jtot; d.ktot = gd.ktot;
+                d.imax = gd.imax; d.jmax = gd.jmax; d.kmax = gd.kmax;
+                d.igc = gd.igc; d.jgc = gd.jgc; d.kgc = gd.kgc;
+                d.xsize = gd.xsize; d.ysize = gd.ysize; d.zsize = gd.zsize;
+                d.z = gd.z.data(); d.zh = gd.zh.data(); d.dz = gd.dz.data(); d.dzh = gd.dzh.data();
+                d.dzi = gd.dzi.data(); d.dzhi = gd.dzhi.data();
+                d.npx = md.npx; d.npy = md.npy; d.mpicoordx = md.mpicoordx; d.mpicoordy = md.mpicoordy;
+                const int rc = mhh_ctx_create(&d, dtype_of<TF>(), device, &ctx);
+                if (rc != MHH_OK)
+                {
+                    const std::string msg = mhh_last_error(ctx);
+                    mhh_ctx_destroy(ctx);
+                    throw std::runtime_error("mhhb200: mhh_ctx_create: " + msg);
+                }
+                // MicroHH drives everything on the legacy default stream
+                MHH_CHECK(ctx, mhh_set_stream(ctx, nullptr));
+                MHH_CHECK(ctx, mhh_set_basestate(ctx, fields.rhoref.data(), fields.rhorefh.data(), nullptr, nullptr));
+
+                #ifdef USEMPI
+                // y slabs: rank 0 makes the NCCL id, MPI broadcasts it (Master owns the communicator)
+                if (md.npy > 1)
+                {
+                    unsigned char id[MHH_COMM_ID_BYTES] = {};
+                    if (md.mpiid == 0) MHH_CHECK(ctx, mhh_comm_get_unique_id(id, MHH_COMM_ID_BYTES));
+                    master.broadcast(reinterpret_cast<char*>(id), MHH_COMM_ID_BYTES);
+                    MHH_CHECK(ctx, mhh_comm_init(ctx, id, MHH_COMM_ID_BYTES));
+                }
+                #endif
+            }
+            ~Context() { mhh_ctx_destroy(ctx); }
+            Context(const Context&) = delete;
+            Context& operator=(const Context&) = delete;
+
+            // Thermo_dry's reference profiles are only known after Thermo::create
+            void set_thermo_basestate(Fields<TF>& fields, const std::vector<TF>& thref, const std::vector<TF>& threfh)
+            { MHH_CHECK(ctx, mhh_set_basestate(ctx, fields.rhoref.data(), fields.rhorefh.data(), thref.data(), threfh.data())); }
+
+            mhh_ctx* ctx = nullptr;
+    };
+
+    // Device pointers of the Fields maps in the C ABI's POD (borrowed per call, never owned).
+    template<typename TF>
+    mhh_fields fields_view(Fields<TF>& fields, Boundary<TF>* boundary=nullptr)
+    {
+        mhh_fields f{};
+        f.u = fields.mp.at("u")->fld_g;   f.v = fields.mp.at("v")->fld_g;   f.w = fields.mp.at("w")->fld_g;
+        f.ut = fields.mt.at("u")->fld_g;  f.vt = fields.mt.at("v")->fld_g;  f.wt = fields.mt.at("w")->fld_g;
+        if (fields.sd.count("evisc")) f.evisc = fields.sd.at("evisc")->fld_g;
+        if (fields.sd.count("p"))     f.p = fields.sd.at("p")->fld_g;
+        f.visc = fields.visc;
+        f.u_fluxbot = fields.mp.at("u")->flux_bot_g; f.u_fluxtop = fields.mp.at("u")->flux_top_g;
+        f.v_fluxbot = fields.mp.at("v")->flux_bot_g; f.v_fluxtop = fields.mp.at("v")->flux_top_g;
+        f.u_bot = fields.mp.at("u")->fld_bot_g; f.u_gradbot = fields.mp.at("u")->grad_bot_g;
+        f.u_top = fields.mp.at("u")->fld_top_g; f.u_gradtop = fields.mp.at("u")->grad_top_g;
+        f.v_bot = fields.mp.at("v")->fld_bot_g; f.v_gradbot = fields.mp.at("v")->grad_bot_g;
+        f.v_top = fields.mp.at("v")->fld_top_g; f.v_gradtop = fields.mp.at("v")->grad_top_g;
+        int n = 0;
+        // the thermodynamic scalar must be scalar 0 (buoyancy / N2 source): std::map order puts "th" / "thl" after
+        // e.g. "qt", so it is moved to the front explicitly
+        std::vector<std::string> names;
+        for (auto& it : fields.sp) names.push_back(it.first);
+        for (const char* thname : {"th", "thl"})
+            for (size_t i = 0; i < names.size(); ++i)
+                if (names[i] == thname) { std::swap(names[0], names[i]); }
+        for (const std::string& name : names)
+        {
+            if (n == MHH_MAX_SCALARS) throw std::runtime_error("mhhb200: more than MHH_MAX_SCALARS prognostic scalars");
+            auto& s = fields.sp.at(name);
+            f.s[n] = s->fld_g; f.st[n] = fields.st.at(name)->fld_g; f.svisc[n] = s->visc;
+            f.s_fluxbot[n] = s->flux_bot_g; f.s_fluxtop[n] = s->flux_top_g;
+            f.s_bot[n] = s->fld_bot_g; f.s_gradbot[n] = s->grad_bot_g;
+            f.s_top[n] = s->fld_top_g; f.s_gradtop[n] = s->grad_top_g;
+            ++n;
+        }
+        f.ns = n;
+        if (boundary && boundary->get_switch() != "default")
+        {
+            f.dudz_mo = boundary->get_dudz_g(); f.dvdz_mo = boundary->get_dvdz_g();
+            f.dbdz_mo = boundary->get_dbdz_g(); f.z0m = boundary->get_z0m_g();
+        }
+        return f;
+    }
+
+    // ---- Advec_2i5 (src/advec_2i5.cxx:955-1063) -------------------------------------------------
+    template<typename TF>
+    class Advec_2i5_b200 : public Advec<TF>
+    {
+        public:
+            Advec_2i5_b200(Master& m, Grid<TF>& g, Fields<TF>& f, Input& in, std::shared_ptr<Context<TF>> c) :
+                Advec<TF>(m, g, f, in), c(std::move(c))
+            { g.set_minimum_ghost_cells(3, 3, 1); }     // src/advec_2i5.cxx:42-45
+
+            void create(Stats<TF>&) override {}
+            void exec(Stats<TF>&) override
+            {
+                const mhh_fields f = fields_view(this->fields);
+                MHH_CHECK(c->ctx, mhh_advec_exec(c->ctx, 25, &f));
+            }
+            double get_cfl(double dt) override
+            {
+                const mhh_fields f = fields_view(this->fields);
+                double cfl = 0.;
+                MHH_CHECK(c->ctx, mhh_advec_get_cfl(c->ctx, 25, &f, dt, &cfl));
+                return cfl;
+            }
+            unsigned long get_time_limit(unsigned long idt, double dt) override
+            {
+                // src/advec_2i5.cxx:984-992
+                double cfl = get_cfl(dt);
+                cfl = std::max(this->cflmin, cfl);
+                return idt * this->cflmax / cfl;
+            }
+            void get_advec_flux(Field3d<TF>&, const Field3d<TF>&) override
+            { throw std::runtime_error("mhhb200: get_advec_flux is a statistics path (out of scope)"); }
+            Advection_type get_switch() const override { return Advection_type::Advec_2i5; }
+
+        private:
+            std::shared_ptr<Context<TF>> c;
+    };
+
+    // ---- Diff_smag2 (src/diff_smag2.cxx:312-607) ------------------------------------------------
+    template<typename TF>
+    class Diff_smag2_b200 : public Diff<TF>
+    {
+        public:
+            Diff_smag2_b200(Master& m, Grid<TF>& g, Fields<TF>& f, Boundary<TF>& b, Input& in, std::shared_ptr<Context<TF>> c) :
+                Diff<TF>(m, g, f, b, in), c(std::move(c))
+            {
+                // same .ini keys as src/diff_smag2.cxx:275-290
+                dnmax = in.get_item<double>("diff", "dnmax", "", 0.4);
+                prm.cs = in.get_item<TF>("diff", "cs", "", 0.23);
+                prm.tPr = in.get_item<TF>("diff", "tPr", "", 1./3.);
+                prm.sw_mason = in.get_item<bool>("diff", "swmason", "", true);
+                this->tPr = prm.tPr;
+                prm.swadvec = 25; prm.swdiff = 1;
+                f.init_diagnostic_field("evisc", "Eddy viscosity", "m2 s-1", "thermo", g.get_grid_data().sloc);
+            }
+            Diffusion_type get_switch() const override { return Diffusion_type::Diff_smag2; }
+            void init() override {}
+            void create(Stats<TF>&, const bool) override {}
+            void exec_viscosity(Stats<TF>&, Thermo<TF>& thermo) override
+            {
+                prm.surface_model = this->boundary.get_switch() != "default";
+                prm.swthermo = thermo.get_switch() == Thermo_type::Dry ? 1 : 0;
+                const mhh_fields f = fields_view(this->fields, &this->boundary);
+                if (prm.swthermo == 1)
+                    MHH_CHECK(c->ctx, mhh_diff_smag2_exec_viscosity(c->ctx, &f, &prm, nullptr));   // N2 derived from th
+                else
+                {
+                    auto n2 = this->fields.get_tmp_g();
+                    thermo.get_thermo_field_g(*n2, "N2", false);
+                    const int rc = mhh_diff_smag2_exec_viscosity(c->ctx, &f, &prm, n2->fld_g);
+                    this->fields.release_tmp_g(n2);
+                    MHH_CHECK(c->ctx, rc);
+                }
+            }
+            void exec(Stats<TF>&) override
+            {
+                const mhh_fields f = fields_view(this->fields, &this->boundary);
+                MHH_CHECK(c->ctx, mhh_diff_smag2_exec(c->ctx, &f, &prm));
+            }
+            void exec_stats(Stats<TF>&, Thermo<TF>&) override {}
+            void diff_flux(Field3d<TF>&, const Field3d<TF>&) override
+            { throw std::runtime_error("mhhb200: diff_flux is a statistics path (out of scope)"); }
+            double get_dn(double dt) override
+            {
+                const mhh_fields f = fields_view(this->fields);
+                double dn = 0.;
+                MHH_CHECK(c->ctx, mhh_diff_smag2_get_dn(c->ctx, &f, &prm, dt, &dn));
+                return dn;
+            }
+            unsigned long get_time_limit(unsigned long idt, double dt) override
+            {
+                // src/diff_smag2.cxx:312-331
+                double dn = get_dn(dt);
+                dn = std::max(Constants::dsmall, dn);
+                return idt * dnmax / dn;
+            }
+            void prepare_device(Boundary<TF>&) override {}
+            void clear_device() override {}
+
+        private:
+            std::shared_ptr<Context<TF>> c;
+            mhh_params prm{};
+            double dnmax;
+    };
+
+    // ---- Pres_2 (src/pres_2.cxx:66-105) ---------------------------------------------------------
+    template<typename TF>
+    class Pres_2_b200 : public Pres<TF>
+    {
+        public:
+            Pres_2_b200(Master& m, Grid<TF>& g, Fields<TF>& f, FFT<TF>& fft, Input& in, std::shared_ptr<Context<TF>> c) :
+                Pres<TF>(m, g, f, fft, in), c(std::move(c)) {}
+            void init() override {}
+            void set_values() override {}       // the tables are built by mhh_set_basestate
+            void create(Stats<TF>&) override {}
+            void exec(double sub_dt, Stats<TF>&) override
+            {
+                const mhh_fields f = fields_view(this->fields);
+                MHH_CHECK(c->ctx, mhh_pres_exec(c->ctx, 2, &f, sub_dt));
+            }
+            TF check_divergence() override
+            {
+                const mhh_fields f = fields_view(this->fields);
+                double div = 0.;
+                MHH_CHECK(c->ctx, mhh_pres_check_divergence(c->ctx, 2, &f, &div));
+                return static_cast<TF>(div);
+            }
+            void prepare_device() override {}
+            void clear_device() override {}
+
+        private:
+            std::shared_ptr<Context<TF>> c;
+    };
+
+    // ---- Boundary_cyclic::exec_g / exec_2d_g (src/boundary_cyclic.cu:98-128) --------------------
+    template<typename TF>
+    struct Boundary_cyclic_b200
+    {
+        std::shared_ptr<Context<TF>> c;
+        void exec_g(TF* fld, Edge edge=Edge::Both_edges)
+        {
+            const int e = edge == Edge::East_west_edge ? MHH_EDGE_EAST_WEST : edge == Edge::North_south_edge ? MHH_EDGE_NORTH_SOUTH : MHH_EDGE_BOTH;
+            MHH_CHECK(c->ctx, mhh_boundary_cyclic(c->ctx, fld, e));
+        }
+        void exec_2d_g(TF* fld) { MHH_CHECK(c->ctx, mhh_boundary_cyclic_2d(c->ctx, fld)); }
+    };
+
+    // ---- Timeloop::exec (src/timeloop.cu:82-112): rk3 of every prognostic (field, tendency) pair ---
+    template<typename TF>
+    void timeloop_exec_b200(Context<TF>& c, Fields<TF>& fields, const int substep, const double dt)
+    {
+        for (auto& it : fields.at)
+            MHH_CHECK(c.ctx, mhh_timeloop_rk3(c.ctx, fields.ap.at(it.first)->fld_g, it.second->fld_g, substep, dt));
+    }
+
+    // ---- fused sub-step: replaces the boundary -> diff.exec_viscosity -> thermo/advec/diff.exec ->
+    // pres.exec -> timeloop.exec sequence of Model::exec (src/model.cxx:356-504) by ONE call when the
+    // case uses swadvec=2i5, swdiff=smag2, swpres=2 and thermo_dry (or no thermo).
+    template<typename TF>
+    void dycore_substep_b200(Context<TF>& c, Fields<TF>& fields, Boundary<TF>& boundary, const mhh_params& prm,
+                             const int substep, const double dt)
+    {
+        const mhh_fields f = fields_view(fields, &boundary);
+        MHH_CHECK(c.ctx, mhh_dycore_substep(c.ctx, &f, &prm, substep, dt));
+    }
+}

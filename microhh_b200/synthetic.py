@@ -13,8 +13,12 @@ def make_case(gd, seed=2, anelastic=False, noise=0.05, ns=1):
     kc, jc, ic = gd.shape
     x = (np.arange(ic) - gd.igc + 0.5)*float(gd.dx)
     xh = (np.arange(ic) - gd.igc)*float(gd.dx)
-    y = (np.arange(jc) - gd.jgc + 0.5)*float(gd.dy)
-    yh = (np.arange(jc) - gd.jgc)*float(gd.dy)
+    # a y slab (npy > 1) sees its own stretch of the global coordinate; the noise is seeded per rank
+    joff = gd.mpicoordy*gd.jmax
+    if gd.npy > 1:
+        rng = np.random.default_rng(seed + 7919*gd.mpicoordy)
+    y = (np.arange(jc) - gd.jgc + 0.5 + joff)*float(gd.dy)
+    yh = (np.arange(jc) - gd.jgc + joff)*float(gd.dy)
     z = gd.z.astype(np.float64); zh = gd.zh.astype(np.float64)
     Lx, Ly, Lz = float(gd.xsize), float(gd.ysize), float(gd.zsize)
     twopi = 2.*np.pi
@@ -74,4 +78,20 @@ def make_case(gd, seed=2, anelastic=False, noise=0.05, ns=1):
         out[name + "t"] = np.zeros(gd.shape, TF)
     out["evisc"] = np.zeros(gd.shape, TF)
     out["p"] = np.zeros(gd.shape, TF)
+    return out
+
+
+def slab_of(case, gd_global, gd_local):
+    """The y slab of rank `gd_local.mpicoordy` cut out of a global case (ghost rows included: local row jl is
+    global row mpicoordy*jmax + jl of the ghosted global array).  1-D profiles and names are shared."""
+    r = gd_local.mpicoordy
+    j0, j1 = r*gd_local.jmax, r*gd_local.jmax + gd_local.jcells
+    out = {}
+    for k, a in case.items():
+        if isinstance(a, np.ndarray) and a.ndim == 3 and a.shape == gd_global.shape:
+            out[k] = np.ascontiguousarray(a[:, j0:j1, :])
+        elif isinstance(a, np.ndarray) and a.ndim == 2 and a.shape == gd_global.shape2d:
+            out[k] = np.ascontiguousarray(a[j0:j1, :])
+        else:
+            out[k] = a
     return out

@@ -1,0 +1,39 @@
+"""The C++ adapter classes (microhh_b200/host/mhh_adapters.hpp) must compile against the reference's own
+headers: every adapter template is explicitly instantiated with g++ -fsyntax-only.  Needs /root/reference
+(this container); skipped on the GPU box."""
+import os
+import subprocess
+import tempfile
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+
+SRC = r'''
+#include "microhh_b200/host/mhh_adapters.hpp"
+#include "input.h"
+template class mhhb200::Context<double>;
+template class mhhb200::Context<float>;
+template class mhhb200::Advec_2i5_b200<double>;
+template class mhhb200::Diff_smag2_b200<double>;
+template class mhhb200::Pres_2_b200<float>;
+template struct mhhb200::Boundary_cyclic_b200<double>;
+template void mhhb200::timeloop_exec_b200<double>(mhhb200::Context<double>&, Fields<double>&, int, double);
+template void mhhb200::dycore_substep_b200<float>(mhhb200::Context<float>&, Fields<float>&, Boundary<float>&, const mhh_params&, int, double);
+'''
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "include")), reason="reference tree not mounted")
+def test_adapters_instantiate_against_reference_headers():
+    with tempfile.NamedTemporaryFile("w", suffix=".cpp", delete=False) as fh:
+        fh.write(SRC)
+        path = fh.name
+    try:
+        cmd = ["g++", "-std=c++20", "-fsyntax-only", "-DUSECUDA", "-DRESTRICTKEYWORD=__restrict__", "-w",
+               f"-I{ROOT}", f"-I{ROOT}/include", f"-I{ROOT}/oracle/ref/shim", f"-I{REF}/include",
+               "-I/usr/local/cuda/include", path]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-3000:]
+    finally:
+        os.unlink(path)

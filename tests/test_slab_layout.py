@@ -1,0 +1,165 @@
+"""
+Host-side tests of the y-slab decomposition (no GPU): the spectral workspace layout exported by the
+C ABI (mhh_slab_layout / mhh_slab_xindex / mhh_slab_yindex) and a world_size-2 gloo replay of the
+distributed Poisson solve (x transform on the slab -> all-to-all -> y transform + tridiagonal solve
+on the owned x-modes -> all-to-all back -> inverse x transform) that must reproduce the oracle's
+single-domain Pres_2 solve.  The CUDA kernels use exactly these index functions (SpecLayout).
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from microhh_b200 import capi
+
+
+def slab_info(lib, itot, jtot, ktot, P, r):
+    s = capi.SlabInfo()
+    assert lib.mhh_slab_layout(itot, jtot, ktot, P, r, C.byref(s)) == 0
+    return s
+
+
+@pytest.mark.parametrize("shape,P", [((16, 8, 6), 2), ((32, 12, 5), 4), ((20, 9, 4), 3), ((16, 8, 4), 1), ((1024, 2048, 2), 8)])
+def test_layout_is_a_bijection_and_blocks_are_messages(shape, P):
+    lib = capi.load()
+    itot, jtot, ktot = shape
+    infos = [slab_info(lib, itot, jtot, ktot, P, r) for r in range(P)]
+    nm = itot//2 + 1
+    assert sum(s.mcl for s in infos) == nm
+    assert [s.m_off for s in infos] == list(np.cumsum([0] + [s.mcl for s in infos[:-1]]))
+    assert max(s.mcl for s in infos) - min(s.mcl for s in infos) <= 1          # even deal
+    if itot > 64:
+        return
+    for r in range(P):
+        s = infos[r]
+        seen = np.zeros(s.xside_elems, bool)
+        for row in range(s.rows):
+            for m in range(nm):
+                e = lib.mhh_slab_xindex(itot, jtot, ktot, P, r, row, m)
+                assert 0 <= e < s.xside_elems and not seen[e]
+                seen[e] = True
+                # block d of the x side == message to rank d == block r of rank d's y side, same offset inside
+                d = next(q for q in range(P) if infos[q].m_off <= m < infos[q].m_off + infos[q].mcl)
+                k, jl = divmod(row, s.jmax)
+                ey = lib.mhh_slab_yindex(itot, jtot, ktot, P, d, k, r*s.jmax + jl, m - infos[d].m_off)
+                assert e - infos[d].m_off*s.rows == ey - r*infos[d].mcl*s.rows
+        assert seen.all()
+        seen_y = np.zeros(s.yside_elems, bool)
+        for k in range(ktot):
+            for j in range(jtot):
+                for ml in range(s.mcl):
+                    e = lib.mhh_slab_yindex(itot, jtot, ktot, P, r, k, j, ml)
+                    assert 0 <= e < s.yside_elems and not seen_y[e]
+                    seen_y[e] = True
+        assert seen_y.all()
+    assert lib.mhh_slab_xindex(itot, jtot, ktot, P, 0, infos[0].rows, 0) == -1
+    assert lib.mhh_slab_layout(itot, jtot + 1, ktot, 2, 0, C.byref(capi.SlabInfo())) != 0 or (jtot + 1) % 2 == 0
+
+
+def _slab_worker(rank, world, port, shape, out_q):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import oracle as O
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lib = capi.load()
+        itot, jtot, ktot = shape
+        g = O.Grid(itot, jtot, ktot, 100., 80., 60., 3, 3, 1, np.float64,
+                   z=np.cumsum(np.linspace(0.7, 1.3, ktot))*60./np.linspace(0.7, 1.3, ktot).sum() - 0.3)
+        rho = np.exp(-g.z/8000.); rhoh = np.exp(-g.zh/8000.)
+        pres = O.Pres2(g, rho, rhoh)
+        rhs = np.random.default_rng(5).standard_normal((ktot, jtot, itot))
+        rhs -= rhs.mean()
+        infos = [slab_info(lib, itot, jtot, ktot, world, r) for r in range(world)]
+        me = infos[rank]; nm = me.nm; jmax = me.jmax; rows = me.rows
+
+        # ---- x side: transform my rows, write them through the layout --------------------------
+        loc = rhs[:, rank*jmax:(rank+1)*jmax, :]
+        X = np.fft.rfft(loc, axis=2)                                      # (k, jl, m)
+        xbuf = np.zeros(me.xside_elems, np.complex128)
+        xi = np.empty((ktot, jmax, nm), np.int64)
+        for k in range(ktot):
+            for jl in range(jmax):
+                for m in range(nm):
+                    xi[k, jl, m] = lib.mhh_slab_xindex(itot, jtot, ktot, world, rank, k*jmax + jl, m)
+        xbuf[xi] = X
+
+        def exchange(src, forward):
+            ysz = me.mcl*rows
+            dst = np.zeros(me.yside_elems if forward else me.xside_elems, np.complex128)
+            reqs = []; recv = {}
+            for peer in range(world):
+                xs = slice(infos[peer].m_off*rows, (infos[peer].m_off + infos[peer].mcl)*rows)   # my x block for `peer`
+                ys = slice(peer*ysz, (peer+1)*ysz)                                               # my y block from `peer`
+                s_out = src[xs] if forward else src[ys]
+                d_sl = ys if forward else xs
+                if peer == rank:
+                    dst[d_sl] = s_out
+                    continue
+                t_out = torch.from_numpy(np.ascontiguousarray(s_out).view(np.float64).copy())
+                t_in = torch.empty(2*(d_sl.stop - d_sl.start), dtype=torch.float64)
+                recv[peer] = (d_sl, t_in)
+                reqs.append(dist.isend(t_out, peer)); reqs.append(dist.irecv(t_in, peer))
+            for q in reqs:
+                q.wait()
+            for peer, (d_sl, t_in) in recv.items():
+                dst[d_sl] = t_in.numpy().view(np.complex128)
+            return dst
+
+        ybuf = exchange(xbuf, True)
+        # ---- y side: gather (k, j, ml) through the layout ---------------------------------------
+        yi = np.empty((ktot, jtot, me.mcl), np.int64)
+        for k in range(ktot):
+            for j in range(jtot):
+                for ml in range(me.mcl):
+                    yi[k, j, ml] = lib.mhh_slab_yindex(itot, jtot, ktot, world, rank, k, j, ml)
+        S = np.fft.fft(ybuf[yi], axis=1)                                  # (k, l, ml)
+        # Pres_2::solve matrix (src/pres_2.cxx:292-324) for my modes, complex right-hand side
+        kg = g.kgc
+        dz = g.dz[kg:kg+ktot][:, None, None]; rr = rho[kg:kg+ktot][:, None, None]
+        lam = pres.bmatj[None, :, None] + pres.bmati[None, None, me.m_off:me.m_off + me.mcl]
+        b = dz*dz*rr*lam - (pres.a + pres.c)[:, None, None]
+        b[0] += pres.a[0]
+        top = np.full((jtot, me.mcl), pres.c[ktot-1])
+        if me.m_off == 0:
+            top[0, 0] = -pres.c[ktot-1]
+        b[ktot-1] += top
+        S = dz*dz*S
+        re, im = np.ascontiguousarray(S.real), np.ascontiguousarray(S.imag)
+        pres.tdma(re, b.copy()); pres.tdma(im, b.copy())
+        S = np.fft.ifft(re + 1j*im, axis=1)                               # includes 1/jtot
+        ybuf[yi] = S
+        xbuf = exchange(ybuf, False)
+        p_loc = np.fft.irfft(xbuf[xi], n=itot, axis=2)                    # includes 1/itot
+
+        p = g.field()
+        pres.solve(rhs.copy(), p)
+        ref = p[g.kstart:g.kend, g.jstart:g.jend, g.istart:g.iend][:, rank*jmax:(rank+1)*jmax, :]
+        err = np.sqrt(((p_loc - ref)**2).sum()/(ref**2).sum())
+        out_q.put((rank, float(err)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shape", [(16, 8, 6), (20, 12, 5)])
+def test_gloo_world2_slab_solve_matches_single_domain(shape):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_slab_worker, args=(r, 2, port, shape, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = []
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    while not q.empty():
+        res.append(q.get())
+    assert len(res) == 2
+    for rank, err in res:
+        assert err <= 1e-12, (rank, err)
