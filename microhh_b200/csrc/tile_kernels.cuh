@@ -447,6 +447,7 @@ inline size_t scal_tile_smem(size_t elem, int kchunk, int ty) { return ((size_t)
 // terms of the top face are carried to the next level.
 // ------------------------------------------------------------------------------------------
 constexpr int EH = 1;
+constexpr int ERING = 4;                  // planes in flight per field: levels k, k+1 in use, k+2 and k+3 on their way
 constexpr int EPX = TILE_X + 2 * EH;      // 34
 
 template <typename TF>
@@ -463,7 +464,7 @@ __global__ void __launch_bounds__(TILE_X * TY, 512 / (TILE_X * TY)) evisc_tile_k
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TF* sm = reinterpret_cast<TF*>(smem_raw);
     constexpr int TILE_Y = TY, TILE_THREADS = TILE_X * TY, EPLANE = tile_plane(TY, EH);
-    // u: slots 0..2, v: 3..5, w: 6..8  (ring of 3 each)
+    // u: slots 0..3, v: 4..7, w: 8..11  (ring of ERING each)
 
     const EviscArgs<TF>& a = args.e;
     const int tx = threadIdx.x % TILE_X, ty = threadIdx.x / TILE_X;
@@ -483,6 +484,7 @@ __global__ void __launch_bounds__(TILE_X * TY, 512 / (TILE_X * TY)) evisc_tile_k
     const TF e8 = TF(0.125);
 
     const int k0 = kc0 - 1;
+    constexpr int RING = ERING;
     TF* prof = sm + 3 * RING * EPLANE;
     const int nlev = args.kchunk + 3;
     TF* p_dzi = prof; TF* p_dzhi = prof + nlev; TF* p_m0 = prof + 2 * nlev; TF* p_z = prof + 3 * nlev; TF* p_gth = prof + 4 * nlev;
@@ -507,13 +509,21 @@ __global__ void __launch_bounds__(TILE_X * TY, 512 / (TILE_X * TY)) evisc_tile_k
         pl_src[f] += 2 * kk;
     }
     cp_async_commit();
+    if (k0 + 2 < g.kcells)
+    {
+#pragma unroll
+        for (int f = 0; f < 3; ++f) { stg.stage(sm + (f * RING + 2) * EPLANE, pl_src[f]); pl_src[f] += kk; }
+    }
+    cp_async_commit();
     int s0 = 0;
 
     auto colload = [&](const TF* __restrict__ fld, int lev) -> TF {
         return (lev >= 0 && lev < g.kcells) ? fld[ij + (long long)lev * kk] : TF(0);
     };
-    TF th_m = 0, th_c = 0;
-    if (a.n2mode == 1) { th_m = colload(a.th, k0 - 1); th_c = colload(a.th, k0); }
+    // th column window: level k+2 is requested one iteration before it is needed, so the load latency is off the
+    // critical path (ncu: 29 % of the stall samples sat on the consumer of the same-iteration load)
+    TF th_m = 0, th_c = 0, th_p = 0;
+    if (a.n2mode == 1) { th_m = colload(a.th, k0 - 1); th_c = colload(a.th, k0); th_p = colload(a.th, k0 + 1); }
     TF z0 = TF(0), dudz_b = 0, dvdz_b = 0, dbdz_b = 0;
     if (SURFACE) { z0 = a.z0m[ij]; if (kc0 == ks) { dudz_b = a.dudz[ij]; dvdz_b = a.dvdz[ij]; dbdz_b = a.dbdz[ij]; } }
 
@@ -522,21 +532,21 @@ __global__ void __launch_bounds__(TILE_X * TY, 512 / (TILE_X * TY)) evisc_tile_k
 
     for (int k = k0; k < kc1; ++k)
     {
-        cp_async_wait<0>();
+        cp_async_wait<1>();          // everything but the newest group (level k+2) has landed: planes k and k+1 are ready
         __syncthreads();
-        const int s1 = (s0 == RING - 1) ? 0 : s0 + 1;
-        const int s2 = (s1 == RING - 1) ? 0 : s1 + 1;
-        if (k + 2 < g.kcells)
+        const int s1 = (s0 + 1) & (RING - 1);
+        const int s3 = (s0 + 3) & (RING - 1);          // held level k-1, which every thread finished with before the barrier
+        if (k + 3 < g.kcells)
         {
 #pragma unroll
-            for (int f = 0; f < 3; ++f) { stg.stage(sm + (f * RING + s2) * EPLANE, pl_src[f]); pl_src[f] += kk; }
+            for (int f = 0; f < 3; ++f) { stg.stage(sm + (f * RING + s3) * EPLANE, pl_src[f]); pl_src[f] += kk; }
         }
         cp_async_commit();
         const int f = k + 1;
         const bool store = (k >= kc0) && active;
         const long long o_k = ij + (long long)k * kk;
-        TF th_p = 0, n2v = 0;
-        if (a.n2mode == 1) th_p = colload(a.th, k + 1);
+        TF th_n = 0, n2v = 0;
+        if (a.n2mode == 1) th_n = colload(a.th, k + 2);
         else if (store) n2v = a.n2[o_k];
 
         const TF* __restrict__ U0 = sm + (0 * RING + s0) * EPLANE + sidx;
@@ -582,7 +592,7 @@ __global__ void __launch_bounds__(TILE_X * TY, 512 / (TILE_X * TY)) evisc_tile_k
             if (bottom_mo) n2 = dbdz_b;
             else if (a.n2mode == 1) n2 = p_gth[pl] * TF(0.5) * (th_p - th_m) * p_dzi[pl];
             else n2 = n2v;
-            TF rit = n2 / s2 / a.tPr;
+            TF rit = n2 / (s2 * a.tPr);
             rit = rit < TF(1. - DSMALL) ? rit : TF(1. - DSMALL);
             TF m2 = p_m0[pl];
             if (SURFACE && a.mason)
@@ -591,15 +601,15 @@ __global__ void __launch_bounds__(TILE_X * TY, 512 / (TILE_X * TY)) evisc_tile_k
                 const TF t2 = t * t;
                 m2 = m2 * t2 / (m2 + t2);       // == 1/(1/mlen0^2 + 1/(kappa (z+z0))^2)
             }
-            a.evisc[o_k] = m2 * sqrtf_(s2) * sqrtf_(TF(1.) - rit);
+            a.evisc[o_k] = m2 * sqrtf_(s2 * (TF(1.) - rit));
         }
         t0 = nt0; t1 = nt1; r0 = nr0; r1 = nr1; tw0 = wx0; tw1 = wx1; rw0 = wy0; rw1 = wy1;
-        th_m = th_c; th_c = th_p;
+        th_m = th_c; th_c = th_p; th_p = th_n;
         s0 = s1;
     }
     cp_async_wait<0>();
 }
 
-inline size_t evisc_tile_smem(size_t elem, int kchunk, int ty) { return ((size_t)3 * RING * tile_plane(ty, EH) + (size_t)5 * (kchunk + 3)) * elem; }
+inline size_t evisc_tile_smem(size_t elem, int kchunk, int ty) { return ((size_t)3 * ERING * tile_plane(ty, EH) + (size_t)5 * (kchunk + 3)) * elem; }
 
 } // namespace mhh
