@@ -98,12 +98,12 @@ def run_ours(args):
     itot, jtot, ktot = parse_workload(args.workload)
     S = 1
 
-    # ONE domain decomposed into y slabs over the ranks (npx = 1, npy = world).  Weak scaling: the per-GPU block
-    # keeps the named size, the horizontal domain grows (y doubles first, then x): 1: i x j, 2: i x 2j, 4: 2i x 2j,
-    # 8: 2i x 4j -- every rank owns itot_g x (jtot_g / world) x ktot = the named number of points.
-    fx = {1: 1, 2: 1, 4: 2, 8: 2}.get(world, 1)
-    fy = world // fx
-    itot_g, jtot_g = itot*fx, jtot*fy
+    # ONE domain decomposed into y slabs over the ranks (npx = 1, npy = world).  Weak scaling: every GPU keeps the
+    # named number of points while the domain doubles per doubling of the ranks (y, then x, then z):
+    # 1: 512^3, 2: 512x1024x512, 4: 1024x1024x512, 8: 1024^3 -- BASELINE.json's 1024^3 fp64 grid on 8 B200s.
+    fx, fy, fz = {1: (1, 1, 1), 2: (1, 2, 1), 4: (2, 2, 1), 8: (2, 2, 2)}.get(world, (1, world, 1))
+    itot_g, jtot_g, ktot_l = itot*fx, jtot*fy, ktot
+    ktot = ktot*fz
     gd = GridData(itot_g, jtot_g, ktot, 25.*itot_g, 25.*jtot_g, 25.*ktot, 3, 3, 1, dtype, npy=world, mpicoordy=rank)
     case = make_case(gd, seed=2, noise=0.01)
     ctx = D.Context(gd, local_rank)
@@ -213,7 +213,7 @@ def run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": f"drycblles-shaped LES {itot}x{jtot}x{ktot} per GPU, advec_2i5+diff_smag2+pres_2+thermo_dry, S=1",
+            "config": {"workload": f"drycblles-shaped LES {itot}x{jtot}x{ktot_l} points per GPU, advec_2i5+diff_smag2+pres_2+thermo_dry, S=1",
                        "global_grid": f"{itot_g}x{jtot_g}x{ktot}",
                        "parallelism": f"one domain in {world} y-slabs (npx=1, npy={world}): NCCL halo rows + all-to-all transposes" if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (each field >> 126 MB)", "dt": dt},
@@ -289,7 +289,7 @@ def run_reference(args):
             "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3*it*jt*kt*cpu["cores"]/cpu["value"] if cpu["value"] else None,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": f"drycblles-shaped LES {itot}x{jtot}x{ktot} per GPU, advec_2i5+diff_smag2+pres_2+thermo_dry, S=1",
+            "config": {"workload": f"drycblles-shaped LES {itot}x{jtot}x{ktot} points per GPU, advec_2i5+diff_smag2+pres_2+thermo_dry, S=1",
                        "note": "CPU arm times a bounded sample of the same workload: " + cpu["sample"]},
             "cpu_baseline": cpu,
             "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

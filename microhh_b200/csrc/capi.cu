@@ -43,6 +43,7 @@ struct mhh_ctx
     int tile2_y = 6;            // MHH_TILE2_Y: rows (= warps) per CTA of the TMA tile kernels
     bool fuse_scalar = true;    // MHH_FUSE_SCALAR=0: keep scalar 0 out of the momentum kernel (A/B comparisons)
     int mom_variant = 3;        // MHH_MOM=2|3: 2 = all components per thread, 3 = warp-specialised by component
+    int evisc_mb = 4;           // MHH_EVISC_MB=2|3|4 (measured 512^3 fp64: 2.72 | 2.51 | 2.11 ms): resident CTAs per SM the eddy-viscosity kernel is compiled for (register cap)
     int prefetch = 1;           // MHH_PREFETCH: L2 prefetch distance (levels) of the TMA tile kernels, 0 = off
     bool prof = false;
     std::vector<std::pair<const char*, cudaEvent_t>> prof_events;
@@ -286,6 +287,7 @@ int create_impl(const mhh_grid_desc* d, int dtype, int device, mhh_ctx** out)
     { const char* e = getenv("MHH_FUSE_SCALAR"); if (e) c->fuse_scalar = e[0] == '1'; }
     { const char* e = getenv("MHH_MOM"); if (e && atoi(e) == 2) c->mom_variant = 2; }
     { const char* e = getenv("MHH_TILE3_Y"); if (e) { int v = atoi(e); if (v == 3 || v == 4 || v == 5) c->tile3_y = v; } }
+    { const char* e = getenv("MHH_EVISC_MB"); if (e) c->evisc_mb = atoi(e); }
     { const char* e = getenv("MHH_PREFETCH"); if (e) c->prefetch = std::max(0, std::min(8, atoi(e))); }
     { const char* e = getenv("MHH_TILE_Y"); if (e && atoi(e) == 16) c->tile_y = 16; else if (e && atoi(e) == 8) c->tile_y = 8; }
     CUDA_TRY(c, cudaSetDevice(device));
@@ -387,8 +389,10 @@ int create_impl(const mhh_grid_desc* d, int dtype, int device, mhh_ctx** out)
     // warp-per-sequence kernels for power-of-two lengths (MHH_NO_WFFT=1 keeps the generic block kernels)
     const bool no_wfft = getenv("MHH_NO_WFFT") && getenv("MHH_NO_WFFT")[0] == '1';
     auto pow2_in = [](int v, int lo, int hi) { return v >= lo && v <= hi && (v & (v - 1)) == 0; };
-    c->wfft_x = !no_wfft && pow2_in(L, 16, 1024);
-    c->wfft_y = !no_wfft && pow2_in(g.jtot, 8, 2048);
+    // one warp-private padded row per warp must fit the 227 KB of shared memory (fp64: up to 1024 points, fp32: 2048)
+    auto wfft_fits = [](int n) { return (size_t)WFFT_WARPS * (size_t)(fpad(n - 1) + 2) * sizeof(cplx<TF>) <= (size_t)227 * 1024; };
+    c->wfft_x = !no_wfft && pow2_in(L, 16, 1024) && wfft_fits(L);
+    c->wfft_y = !no_wfft && pow2_in(g.jtot, 8, 2048) && wfft_fits(g.jtot);
     int rc2;
     if (c->wfft_x && (rc2 = wfft_x_attrs<TF>(c, L)) != MHH_OK) return rc2;
     if (c->wfft_y && (rc2 = wfft_y_attrs<TF>(c, g.jtot)) != MHH_OK) return rc2;
@@ -561,6 +565,8 @@ int vec_width(const GridDev<TF>& g, std::initializer_list<const void*> ptrs)
     return v;
 }
 
+inline int pick_kchunk_waves(int ntiles_xy, int kmax, int slots, int warm);
+
 inline int pick_kchunk(int ntiles_xy, int kmax, int num_sms)
 {
     // enough CTAs to fill the machine twice, but chunks of at least 16 levels (warm-up level amortised)
@@ -595,22 +601,25 @@ int evisc_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, const TF*
     {
         const int ty = c->tile_y;
         const int ntx = (g.imax + TILE_X - 1) / TILE_X, nty = (g.jmax + ty - 1) / ty;
-        EviscTileArgs<TF> t{a, c->d_mlen0, pick_kchunk(ntx * nty, g.kmax, c->num_sms)};
+        const int mb = (ty == 16) ? 1 : (c->evisc_mb == 3 || c->evisc_mb == 4 ? c->evisc_mb : 2);
+        EviscTileArgs<TF> t{a, c->d_mlen0, pick_kchunk_waves(ntx * nty, g.kmax, c->num_sms * mb, 1)};
         dim3 grid(ntx, nty, (g.kmax + t.kchunk - 1) / t.kchunk);
         const size_t smem = evisc_tile_smem(sizeof(TF), t.kchunk, ty);
         int vec = 2;
         if (g.icells % 2 != 0 || (g.igc - EH) % 2 != 0 || (g.ijcells % 2) != 0) vec = 1;
         for (const void* p : {(const void*)a.u, (const void*)a.v, (const void*)a.w})
             if (reinterpret_cast<uintptr_t>(p) % (2 * sizeof(TF)) != 0) vec = 1;
-#define ET3(S, V, Y) do { \
+#define ET4(S, V, Y, MB) do { \
             static size_t attr_smem = 0; \
-            if (attr_smem < smem) { CUDA_TRY(c, cudaFuncSetAttribute(evisc_tile_kernel<TF, S, V, Y>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; } \
-            evisc_tile_kernel<TF, S, V, Y><<<grid, TILE_X * Y, smem, c->stream>>>(t, g); } while (0)
-#define ET(S, V) do { if (ty == 16) ET3(S, V, 16); else ET3(S, V, 8); } while (0)
+            if (attr_smem < smem) { CUDA_TRY(c, cudaFuncSetAttribute(evisc_tile_kernel<TF, S, V, Y, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; } \
+            evisc_tile_kernel<TF, S, V, Y, MB><<<grid, TILE_X * Y, smem, c->stream>>>(t, g); } while (0)
+#define ET3(S, V, Y) do { if (c->evisc_mb == 3) ET4(S, V, Y, 3); else if (c->evisc_mb == 4) ET4(S, V, Y, 4); else ET4(S, V, Y, 512 / (TILE_X * Y)); } while (0)
+#define ET(S, V) do { if (ty == 16) ET4(S, V, 16, 1); else ET3(S, V, 8); } while (0)
         if (a.surface) { if (vec == 2) ET(true, 2); else ET(true, 1); }
         else { if (vec == 2) ET(false, 2); else ET(false, 1); }
 #undef ET
 #undef ET3
+#undef ET4
         KCHECKN(c, "evisc_tile_kernel");
     }
     else

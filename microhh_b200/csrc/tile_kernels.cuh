@@ -458,8 +458,8 @@ struct EviscTileArgs
     int kchunk;
 };
 
-template <typename TF, bool SURFACE, int VEC, int TY>
-__global__ void __launch_bounds__(TILE_X * TY, 512 / (TILE_X * TY)) evisc_tile_kernel(const EviscTileArgs<TF> args, const GridDev<TF> g)
+template <typename TF, bool SURFACE, int VEC, int TY, int MB = 512 / (TILE_X * TY)>
+__global__ void __launch_bounds__(TILE_X * TY, MB) evisc_tile_kernel(const EviscTileArgs<TF> args, const GridDev<TF> g)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TF* sm = reinterpret_cast<TF*>(smem_raw);
