@@ -102,8 +102,8 @@ typedef struct mhh_fields
 /* Run-time switches of the path ([advec] [diff] [boundary] [thermo] of the .ini). */
 typedef struct mhh_params
 {
-    int    swadvec;              /* 25 = 2i5 (others: see mhh_advec_exec) */
-    int    swdiff;               /* 1 = smag2 */
+    int    swadvec;              /* 25 = 2i5, 2 = 2 */
+    int    swdiff;               /* 1 = smag2, 2 = 2 */
     int    swthermo;             /* 0 = off, 1 = dry (buoyancy from scalar 0 = th) */
     int    surface_model;        /* Boundary switch != "default"  (Surface_model::Enabled) */
     int    sw_mason;             /* [diff] swmason */
@@ -173,7 +173,8 @@ MHH_API int mhh_boundary_cyclic_2d(mhh_ctx* ctx, void* fld2d);
 MHH_API int mhh_boundary_ghost_cells_2nd(mhh_ctx* ctx, void* fld, int bcbot, const void* bot, const void* gradbot,
                                  int bctop, const void* top, const void* gradtop);
 
-/* ---- Advec<TF>::exec / get_cfl  (Advec_2i5: src/advec_2i5.cxx:955-1063) -------------------- */
+/* ---- Advec<TF>::exec / get_cfl  (swadvec = 25: Advec_2i5, src/advec_2i5.cxx:955-1063;
+ *      swadvec = 2: Advec_2, src/advec_2.cxx:288-345) ------------------------------------------ */
 MHH_API int mhh_advec_exec(mhh_ctx* ctx, int swadvec, const mhh_fields* f);
 MHH_API int mhh_advec_get_cfl(mhh_ctx* ctx, int swadvec, const mhh_fields* f, double dt, double* cfl);
 
@@ -183,6 +184,10 @@ MHH_API int mhh_advec_get_cfl(mhh_ctx* ctx, int swadvec, const mhh_fields* f, do
 MHH_API int mhh_diff_smag2_exec_viscosity(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm, const void* n2);
 MHH_API int mhh_diff_smag2_exec(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm);
 MHH_API int mhh_diff_smag2_get_dn(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm, double dt, double* dn);
+
+/* ---- Diff_2<TF>::exec / get_dn  (src/diff_2.cxx:133-190): nu * laplacian on u, v, w and every scalar ---- */
+MHH_API int mhh_diff_2_exec(mhh_ctx* ctx, const mhh_fields* f);
+MHH_API int mhh_diff_2_get_dn(mhh_ctx* ctx, const mhh_fields* f, double dt, double* dn);
 
 /* ---- Thermo_dry<TF>::exec (buoyancy on wt) and get_thermo_field("N2")  (src/thermo_dry.cxx) -- */
 MHH_API int mhh_thermo_dry_exec(mhh_ctx* ctx, void* wt, const void* th);

@@ -79,6 +79,8 @@ SIGNATURES = {
     "mhh_diff_smag2_exec_viscosity": (C.c_int, [_vp, _PF, _PP, _vp]),
     "mhh_diff_smag2_exec": (C.c_int, [_vp, _PF, _PP]),
     "mhh_diff_smag2_get_dn": (C.c_int, [_vp, _PF, _PP, C.c_double, C.POINTER(C.c_double)]),
+    "mhh_diff_2_exec": (C.c_int, [_vp, _PF]),
+    "mhh_diff_2_get_dn": (C.c_int, [_vp, _PF, C.c_double, C.POINTER(C.c_double)]),
     "mhh_thermo_dry_exec": (C.c_int, [_vp, _vp, _vp]),
     "mhh_thermo_dry_n2": (C.c_int, [_vp, _vp, _vp]),
     "mhh_pres_exec": (C.c_int, [_vp, C.c_int, _PF, C.c_double]),

@@ -18,6 +18,7 @@
 #include "tile2_kernels.cuh"
 #include "tile3_kernels.cuh"
 #include "slab_kernels.cuh"
+#include "order2_kernels.cuh"
 #include <cudaTypedefs.h>
 #include <dlfcn.h>
 #include <nccl.h>
@@ -165,7 +166,7 @@ struct Ctx : mhh_ctx
     bool basestate_set = false;
     double *d_red = nullptr;       // reduction scalar
     double *h_red = nullptr;       // pinned
-    std::vector<TF> h_rhoref, h_rhorefh;
+    std::vector<TF> h_rhoref, h_rhorefh, h_dz;
     int rows_x = 1, mc_y = 4;
     bool wfft_x = false, wfft_y = false;   // warp-per-sequence FFT kernels (power-of-two lengths)
     size_t smem_x = 0, smem_y = 0;
@@ -337,6 +338,7 @@ int create_impl(const mhh_grid_desc* d, int dtype, int device, mhh_ctx** out)
         if (!src[n]) { c->err = "grid metric array is NULL"; return MHH_E_INVALID; }
         CUDA_TRY(c, cudaMemcpy(c->d_prof + n * kc, src[n], sizeof(TF) * kc, cudaMemcpyHostToDevice));
     }
+    c->h_dz.assign(static_cast<const TF*>(d->dz), static_cast<const TF*>(d->dz) + kc);
     g.z = c->d_prof; g.zh = c->d_prof + kc; g.dz = c->d_prof + 2 * kc; g.dzh = c->d_prof + 3 * kc;
     g.dzi = c->d_prof + 4 * kc; g.dzhi = c->d_prof + 5 * kc;
     g.rhoref = c->d_prof + 6 * kc; g.rhorefh = c->d_prof + 7 * kc;
@@ -932,6 +934,67 @@ int tend_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, bool adv, 
     return MHH_OK;
 }
 
+// Advec_2 / Diff_2 / thermo_dry buoyancy in any combination (order2_kernels.cuh)
+template <typename TF>
+int o2_impl(Ctx<TF>* c, const mhh_fields* f, bool adv, bool diff, bool buoy)
+{
+    NEED_BASE(c);
+    const GridDev<TF>& g = c->g;
+    int rc = check_mom<TF>(c, f, false, false);
+    if (rc != MHH_OK) return rc;
+    if (buoy && f->ns < 1) { c->err = "buoyancy needs scalar 0 (th)"; return MHH_E_INVALID; }
+    if (!adv && !diff && !buoy) { c->err = "o2_impl: nothing to do"; return MHH_E_INVALID; }
+    O2Args<TF> a{};
+    a.ut = P<TF>(f->ut); a.vt = P<TF>(f->vt); a.wt = P<TF>(f->wt);
+    a.u = P<TF>(f->u); a.v = P<TF>(f->v); a.w = P<TF>(f->w);
+    a.th = f->ns > 0 ? P<TF>(f->s[0]) : nullptr;
+    a.visc = (TF)f->visc;
+    // `const double dxidxi = 1/(dx*dx);` (src/diff_2.cxx:44-45): the division itself is done in TF, then widened
+    a.dxidxi = (double)(TF(1) / (g.dx * g.dx)); a.dyidyi = (double)(TF(1) / (g.dy * g.dy));
+    dim3 gr = c->grd_interior(), b = c->blk();
+#define O2(A, D, B) o2_uvw_kernel<TF, A, D, B><<<gr, b, 0, c->stream>>>(a, g)
+    if (adv && diff && buoy) O2(true, true, true);
+    else if (adv && diff) O2(true, true, false);
+    else if (adv && buoy) O2(true, false, true);
+    else if (adv) O2(true, false, false);
+    else if (diff && buoy) O2(false, true, true);
+    else if (diff) O2(false, true, false);
+    else O2(false, false, true);
+#undef O2
+    KCHECKN(c, "o2_uvw_kernel");
+    if (!adv && !diff) return MHH_OK;
+    for (int n = 0; n < f->ns; ++n)
+    {
+        O2ScalArgs<TF> s{P<TF>(f->st[n]), P<TF>(f->s[n]), a.u, a.v, a.w, (TF)f->svisc[n], a.dxidxi, a.dyidyi};
+        if (adv && diff) o2_s_kernel<TF, true, true><<<gr, b, 0, c->stream>>>(s, g);
+        else if (adv) o2_s_kernel<TF, true, false><<<gr, b, 0, c->stream>>>(s, g);
+        else o2_s_kernel<TF, false, true><<<gr, b, 0, c->stream>>>(s, g);
+        KCHECKN(c, "o2_s_kernel");
+    }
+    return MHH_OK;
+}
+
+template <typename TF>
+int o2_cfl_impl(Ctx<TF>* c, const mhh_fields* f, double* out)
+{
+    const GridDev<TF>& g = c->g;
+    NEED(c, f->u, "u"); NEED(c, f->v, "v"); NEED(c, f->w, "w");
+    CUDA_TRY(c, cudaMemsetAsync(c->d_red, 0, sizeof(double), c->stream));
+    o2_cfl_kernel<TF><<<c->grd_interior(), c->blk(), 0, c->stream>>>(P<TF>(f->u), P<TF>(f->v), P<TF>(f->w), g, c->d_red);
+    KCHECKN(c, "o2_cfl_kernel");
+    if (c->nranks > 1)
+    {
+        if (!c->comm) { c->err = "slab context without communicator: call mhh_comm_init first"; return MHH_E_INVALID; }
+        NcclApi* api = nccl_api(c->err);
+        if (!api) return MHH_E_CUDA;
+        NCCL_TRY(c, api, api->AllReduce(c->d_red, c->d_red, 1, ncclFloat64, ncclMax, c->comm, c->stream));
+    }
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_red, c->d_red, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    *out = *c->h_red;
+    return MHH_OK;
+}
+
 template <typename TF, int MODE>
 int reduce_impl(Ctx<TF>* c, const TF* u, const TF* v, const TF* w, TF p0, TF p1, TF p2, double* out)
 {
@@ -1102,9 +1165,11 @@ int substep_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, int sub
     NEED_BASE(c);
     NEED(c, prm, "params");
     const GridDev<TF>& g = c->g;
-    if (prm->swadvec != 25 || prm->swdiff != 1) { c->err = "dycore_substep: only swadvec=2i5 (25) + swdiff=smag2 (1) are fused"; return MHH_E_INVALID; }
+    if ((prm->swadvec != 25 && prm->swadvec != 2) || (prm->swdiff != 1 && prm->swdiff != 2))
+    { c->err = "dycore_substep: swadvec must be 2i5 (25) or 2, swdiff smag2 (1) or 2"; return MHH_E_INVALID; }
     if (substep < 0 || substep > 2) { c->err = "substep must be 0..2"; return MHH_E_INVALID; }
-    int rc = check_mom<TF>(c, f, true, prm->surface_model != 0);
+    const bool smag = prm->swdiff == 1, adv5 = prm->swadvec == 25, buoy = prm->swthermo == 1;
+    int rc = check_mom<TF>(c, f, smag, smag && prm->surface_model != 0);
     if (rc != MHH_OK) return rc;
     NEED(c, f->p, "p");
     // 1. boundary.set_prognostic_cyclic_bcs + set_ghost_cells
@@ -1117,9 +1182,22 @@ int substep_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, int sub
         if ((rc = ghost_impl<TF>(c, P<TF>(f->s[n]), prm->sbcbot[n], P<TF>(f->s_bot[n]), P<TF>(f->s_gradbot[n]),
                                  prm->sbctop[n], P<TF>(f->s_top[n]), P<TF>(f->s_gradtop[n]))) != MHH_OK) return rc;
     // 2. diff.exec_viscosity
-    if ((rc = evisc_impl<TF>(c, f, prm, nullptr)) != MHH_OK) return rc;
-    // 3. thermo.exec + advec.exec + diff.exec, fused
-    if ((rc = tend_impl<TF>(c, f, prm, true, true, prm->swthermo == 1)) != MHH_OK) return rc;
+    if (smag && (rc = evisc_impl<TF>(c, f, prm, nullptr)) != MHH_OK) return rc;
+    // 3. thermo.exec + advec.exec + diff.exec: one fused kernel per scheme family
+    if (adv5 && smag) rc = tend_impl<TF>(c, f, prm, true, true, buoy);                       // 2i5 + smag2 (+ buoyancy)
+    else if (!adv5 && !smag) rc = o2_impl<TF>(c, f, true, true, buoy);                       // 2 + 2 (+ buoyancy)
+    else if (!adv5)                                                                          // 2 + smag2 (drycblles as shipped)
+    {
+        if ((rc = o2_impl<TF>(c, f, true, false, buoy)) != MHH_OK) return rc;
+        rc = tend_impl<TF>(c, f, prm, false, true, false);
+    }
+    else                                                                                     // 2i5 + 2
+    {
+        if (buoy && (rc = o2_impl<TF>(c, f, false, false, true)) != MHH_OK) return rc;
+        if ((rc = tend_impl<TF>(c, f, prm, true, false, false)) != MHH_OK) return rc;
+        rc = o2_impl<TF>(c, f, false, true, false);
+    }
+    if (rc != MHH_OK) return rc;
     // 4. pres.exec (solve), then pressure correction fused with timeloop.exec
     const TF cA[3] = {TF(0.), TF(-5. / 9.), TF(-153. / 128.)};
     const TF cB[3] = {TF(1. / 3.), TF(15. / 16.), TF(8. / 15.)};
@@ -1376,15 +1454,47 @@ int mhh_boundary_ghost_cells_2nd(mhh_ctx* ctx, void* fld, int bcbot, const void*
 
 int mhh_advec_exec(mhh_ctx* ctx, int swadvec, const mhh_fields* f)
 {
-    if (ctx && swadvec != 25) { ctx->err = "advec_exec: only swadvec = 25 (2i5) is available"; return MHH_E_INVALID; }
+    if (ctx && swadvec != 25 && swadvec != 2) { ctx->err = "advec_exec: swadvec must be 25 (2i5) or 2"; return MHH_E_INVALID; }
+    if (swadvec == 2) DISPATCH1(ctx, o2_impl<TF>(c, f, true, false, false));
     DISPATCH1(ctx, tend_impl<TF>(c, f, nullptr, true, false, false));
+}
+
+int mhh_diff_2_exec(mhh_ctx* ctx, const mhh_fields* f)
+{
+    if (!f) return MHH_E_INVALID;
+    DISPATCH1(ctx, o2_impl<TF>(c, f, false, true, false));
+}
+
+int mhh_diff_2_get_dn(mhh_ctx* ctx, const mhh_fields* f, double dt, double* dn)
+{
+    if (!ctx || !f || !dn) return MHH_E_INVALID;
+    if (f->ns < 0 || f->ns > MHH_MAX_SCALARS) { ctx->err = "ns out of range"; return MHH_E_INVALID; }
+    // Diff_2::create + get_dn (src/diff_2.cxx:133-152): host arithmetic on the grid metrics, no field pass
+    DISPATCH1(ctx, ([&]() -> int {
+        double viscmax = (double)(TF)f->visc;
+        for (int n = 0; n < f->ns; ++n) viscmax = std::max(viscmax, (double)(TF)f->svisc[n]);
+        const GridDev<TF>& g = c->g;
+        double dnmul = 0.;
+        for (int k = g.kstart; k < g.kend; ++k)
+        {
+            const TF dzk = c->h_dz[k];
+            dnmul = std::max(dnmul, std::abs((double)(TF)viscmax * (1. / (double)(g.dx * g.dx) + 1. / (double)(g.dy * g.dy) + 1. / (double)(dzk * dzk))));
+        }
+        *dn = dnmul * dt;
+        return MHH_OK; })());
 }
 
 int mhh_advec_get_cfl(mhh_ctx* ctx, int swadvec, const mhh_fields* f, double dt, double* cfl)
 {
     if (!ctx || !f || !cfl) return MHH_E_INVALID;
-    if (swadvec != 25) { ctx->err = "advec_get_cfl: only swadvec = 25 (2i5) is available"; return MHH_E_INVALID; }
+    if (swadvec != 25 && swadvec != 2) { ctx->err = "advec_get_cfl: swadvec must be 25 (2i5) or 2"; return MHH_E_INVALID; }
     int rc;
+    if (swadvec == 2)
+    {
+        if (ctx->dtype == MHH_F64) { rc = o2_cfl_impl<double>(static_cast<Ctx<double>*>(ctx), f, cfl); if (rc == MHH_OK) *cfl = *cfl * dt; }
+        else { rc = o2_cfl_impl<float>(static_cast<Ctx<float>*>(ctx), f, cfl); if (rc == MHH_OK) *cfl = (double)((float)*cfl * (float)dt); }
+        return rc;
+    }
     if (ctx->dtype == MHH_F64) { typedef double TF; rc = reduce_impl<TF, 0>(static_cast<Ctx<TF>*>(ctx), P<TF>(f->u), P<TF>(f->v), P<TF>(f->w), 0, 0, 0, cfl); if (rc == MHH_OK) *cfl = *cfl * dt; }
     else { typedef float TF; rc = reduce_impl<TF, 0>(static_cast<Ctx<TF>*>(ctx), P<TF>(f->u), P<TF>(f->v), P<TF>(f->w), 0, 0, 0, cfl); if (rc == MHH_OK) *cfl = (double)((float)*cfl * (float)dt); }
     return rc;

@@ -230,6 +230,21 @@ class Diff:
         return out.value
 
 
+class Diff_2:
+    """Diff_2<TF> (src/diff_2.cxx): constant-viscosity diffusion of u, v, w and all scalars."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    def exec(self, fields):
+        self.ctx.check(self.ctx.lib.mhh_diff_2_exec(self.ctx.h, C.byref(fields.c)))
+
+    def get_dn(self, fields, dt):
+        out = C.c_double()
+        self.ctx.check(self.ctx.lib.mhh_diff_2_get_dn(self.ctx.h, C.byref(fields.c), dt, C.byref(out)))
+        return out.value
+
+
 class Thermo_dry:
     def __init__(self, ctx):
         self.ctx = ctx

@@ -391,6 +391,117 @@ def advec_2i5_cfl(g, u, v, w, dt):
 
 
 # --------------------------------------------------------------------------------------
+# Advec_2 (reference src/advec_2.cxx:48-202): plain 2nd-order flux form, +-1 stencil
+# --------------------------------------------------------------------------------------
+def advec_2_u(g, ut, u, v, w, rhoref, rhorefh):
+    """src/advec_2.cxx:78-107"""
+    TF = g.TF
+    dxi, dyi = TF(1.)/g.dx, TF(1.)/g.dy
+    U = lambda dk=0, dj=0, di=0: _S(g, u, dk, dj, di)
+    V = lambda dk=0, dj=0, di=0: _S(g, v, dk, dj, di)
+    W = lambda dk=0, dj=0, di=0: _S(g, w, dk, dj, di)
+    _S(g, ut)[...] += (
+        - ( interp2(U(), U(0,0,1)) * interp2(U(), U(0,0,1))
+          - interp2(U(0,0,-1), U()) * interp2(U(0,0,-1), U()) ) * dxi
+        - ( interp2(V(0,1,-1), V(0,1,0)) * interp2(U(), U(0,1,0))
+          - interp2(V(0,0,-1), V()) * interp2(U(0,-1,0), U()) ) * dyi
+        - ( _K(g, rhorefh, 1) * interp2(W(1,0,-1), W(1,0,0)) * interp2(U(), U(1,0,0))
+          - _K(g, rhorefh, 0) * interp2(W(0,0,-1), W()) * interp2(U(-1,0,0), U()) ) / _K(g, rhoref) * _K(g, g.dzi) )
+
+
+def advec_2_v(g, vt, u, v, w, rhoref, rhorefh):
+    """src/advec_2.cxx:109-138"""
+    TF = g.TF
+    dxi, dyi = TF(1.)/g.dx, TF(1.)/g.dy
+    U = lambda dk=0, dj=0, di=0: _S(g, u, dk, dj, di)
+    V = lambda dk=0, dj=0, di=0: _S(g, v, dk, dj, di)
+    W = lambda dk=0, dj=0, di=0: _S(g, w, dk, dj, di)
+    _S(g, vt)[...] += (
+        - ( interp2(U(0,-1,1), U(0,0,1)) * interp2(V(), V(0,0,1))
+          - interp2(U(0,-1,0), U()) * interp2(V(0,0,-1), V()) ) * dxi
+        - ( interp2(V(), V(0,1,0)) * interp2(V(), V(0,1,0))
+          - interp2(V(0,-1,0), V()) * interp2(V(0,-1,0), V()) ) * dyi
+        - ( _K(g, rhorefh, 1) * interp2(W(1,-1,0), W(1,0,0)) * interp2(V(), V(1,0,0))
+          - _K(g, rhorefh, 0) * interp2(W(0,-1,0), W()) * interp2(V(-1,0,0), V()) ) / _K(g, rhoref) * _K(g, g.dzi) )
+
+
+def advec_2_w(g, wt, u, v, w, rhoref, rhorefh):
+    """src/advec_2.cxx:140-169 (k = kstart+1 .. kend-1)"""
+    TF = g.TF
+    dxi, dyi = TF(1.)/g.dx, TF(1.)/g.dy
+    k0, k1 = g.kstart+1, g.kend
+    U = lambda dk=0, dj=0, di=0: _S(g, u, dk, dj, di, k0, k1)
+    V = lambda dk=0, dj=0, di=0: _S(g, v, dk, dj, di, k0, k1)
+    W = lambda dk=0, dj=0, di=0: _S(g, w, dk, dj, di, k0, k1)
+    _S(g, wt, 0, 0, 0, k0, k1)[...] += (
+        - ( interp2(U(-1,0,1), U(0,0,1)) * interp2(W(), W(0,0,1))
+          - interp2(U(-1,0,0), U()) * interp2(W(0,0,-1), W()) ) * dxi
+        - ( interp2(V(-1,1,0), V(0,1,0)) * interp2(W(), W(0,1,0))
+          - interp2(V(-1,0,0), V()) * interp2(W(0,-1,0), W()) ) * dyi
+        - ( _K(g, rhoref, 0, k0, k1) * interp2(W(), W(1,0,0)) * interp2(W(), W(1,0,0))
+          - _K(g, rhoref, -1, k0, k1) * interp2(W(-1,0,0), W()) * interp2(W(-1,0,0), W()) ) / _K(g, rhorefh, 0, k0, k1) * _K(g, g.dzhi, 0, k0, k1) )
+
+
+def advec_2_s(g, st, s, u, v, w, rhoref, rhorefh):
+    """src/advec_2.cxx:171-202"""
+    TF = g.TF
+    dxi, dyi = TF(1.)/g.dx, TF(1.)/g.dy
+    S = lambda dk=0, dj=0, di=0: _S(g, s, dk, dj, di)
+    _S(g, st)[...] += (
+        - ( _S(g, u, 0, 0, 1) * interp2(S(), S(0,0,1))
+          - _S(g, u) * interp2(S(0,0,-1), S()) ) * dxi
+        - ( _S(g, v, 0, 1, 0) * interp2(S(), S(0,1,0))
+          - _S(g, v) * interp2(S(0,-1,0), S()) ) * dyi
+        - ( _K(g, rhorefh, 1) * _S(g, w, 1) * interp2(S(), S(1,0,0))
+          - _K(g, rhorefh, 0) * _S(g, w) * interp2(S(-1,0,0), S()) ) / _K(g, rhoref) * _K(g, g.dzi) )
+
+
+def advec_2_cfl(g, u, v, w, dt):
+    """src/advec_2.cxx:50-76 (returns cfl*dt in TF)"""
+    TF = g.TF
+    dxi, dyi = TF(1.)/g.dx, TF(1.)/g.dy
+    c = (np.abs(interp2(_S(g, u), _S(g, u, 0, 0, 1)))*dxi + np.abs(interp2(_S(g, v), _S(g, v, 0, 1, 0)))*dyi
+         + np.abs(interp2(_S(g, w), _S(g, w, 1)))*_K(g, g.dzi))
+    return TF(TF(c.max())*TF(dt))
+
+
+# --------------------------------------------------------------------------------------
+# Diff_2 (reference src/diff_2.cxx:38-86, dnmul :139-152).  dxidxi / dyidyi are `double` even in the
+# single-precision build (:44-45), so the SP sum is formed in double and narrowed by the `+=`.
+# --------------------------------------------------------------------------------------
+def _diff_2(g, at, a, visc, k0, dz_up, dz_dn, dz_c):
+    TF = g.TF
+    k1 = g.kend
+    # `const double dxidxi = 1/(dx*dx);` -- int 1 over a TF product: the DIVISION is done in TF, the result widened
+    dxidxi = np.float64(TF(1.)/TF(g.dx*g.dx))
+    dyidyi = np.float64(TF(1.)/TF(g.dy*g.dy))
+    A = lambda dk=0, dj=0, di=0: _S(g, a, dk, dj, di, k0, k1)
+    lap = ( ( (A(0,0,1) - A()) - (A() - A(0,0,-1)) ) * dxidxi
+          + ( (A(0,1,0) - A()) - (A() - A(0,-1,0)) ) * dyidyi
+          + ( (A(1,0,0) - A()) * dz_up - (A() - A(-1,0,0)) * dz_dn ) * dz_c )
+    tgt = _S(g, at, 0, 0, 0, k0, k1)
+    tgt[...] = (tgt + TF(visc) * lap).astype(TF)
+
+
+def diff_2_c(g, at, a, visc):
+    """src/diff_2.cxx:38-61"""
+    _diff_2(g, at, a, visc, g.kstart, _K(g, g.dzhi, 1), _K(g, g.dzhi, 0), _K(g, g.dzi))
+
+
+def diff_2_w(g, wt, w, visc):
+    """src/diff_2.cxx:63-86 (k = kstart+1 .. kend-1)"""
+    k0, k1 = g.kstart+1, g.kend
+    _diff_2(g, wt, w, visc, k0, _K(g, g.dzi, 0, k0, k1), _K(g, g.dzi, -1, k0, k1), _K(g, g.dzhi, 0, k0, k1))
+
+
+def diff_2_dnmul(g, viscmax):
+    """src/diff_2.cxx:139-152: max_k |viscmax (1/dx^2 + 1/dy^2 + 1/dz[k]^2)| (host side, once)"""
+    TF = g.TF
+    dz = g.dz[g.kstart:g.kend]
+    return float(np.max(np.abs(TF(viscmax) * (1./np.float64(g.dx*g.dx) + 1./np.float64(g.dy*g.dy) + 1./(dz*dz).astype(np.float64)))))
+
+
+# --------------------------------------------------------------------------------------
 # Diff_smag2 (reference include/diff_kernels.h:34-511, src/diff_smag2.cxx:148-269)
 # --------------------------------------------------------------------------------------
 def _load_cport():
@@ -870,6 +981,13 @@ class NumpyKernels:
     def advec_2i5_w(self, wt, u, v, w, rhoref, rhorefh): advec_2i5_w(self.g, wt, u, v, w, rhoref, rhorefh)
     def advec_2i5_s(self, st, s, u, v, w, rhoref, rhorefh): advec_2i5_s(self.g, st, s, u, v, w, rhoref, rhorefh)
     def advec_2i5_cfl(self, u, v, w, dt): return float(advec_2i5_cfl(self.g, u, v, w, dt))
+    def advec_2_u(self, ut, u, v, w, rhoref, rhorefh): advec_2_u(self.g, ut, u, v, w, rhoref, rhorefh)
+    def advec_2_v(self, vt, u, v, w, rhoref, rhorefh): advec_2_v(self.g, vt, u, v, w, rhoref, rhorefh)
+    def advec_2_w(self, wt, u, v, w, rhoref, rhorefh): advec_2_w(self.g, wt, u, v, w, rhoref, rhorefh)
+    def advec_2_s(self, st, s, u, v, w, rhoref, rhorefh): advec_2_s(self.g, st, s, u, v, w, rhoref, rhorefh)
+    def advec_2_cfl(self, u, v, w, dt): return float(advec_2_cfl(self.g, u, v, w, dt))
+    def diff_2_c(self, at, a, visc): diff_2_c(self.g, at, a, visc)
+    def diff_2_w(self, wt, w, visc): diff_2_w(self.g, wt, w, visc)
     def diff_strain2(self, strain2, u, v, w, ugradbot, vgradbot, surface): diff_strain2(self.g, strain2, u, v, w, ugradbot, vgradbot, surface)
     def diff_evisc(self, evisc, u, v, w, N2, bgradbot, z0m, cs, tPr, surface, mason=True): diff_evisc(self.g, evisc, N2, bgradbot, z0m, cs, tPr, surface, mason)
     def diff_u(self, ut, u, v, w, evisc, fluxbot, fluxtop, rhoref, rhorefh, visc, surface): diff_u(self.g, ut, u, v, w, evisc, fluxbot, fluxtop, rhoref, rhorefh, visc, surface)

@@ -76,6 +76,30 @@ class RefKernels:
         g = self.g
         return self._call("ref_advec_2i5_cfl", u, v, w, g.dzi, g.dx, g.dy, float(dt), restype=C.c_double)
 
+    # --- advec_2
+    def advec_2_u(self, ut, u, v, w, rhoref, rhorefh):
+        g = self.g; self._call("ref_advec_2_u", ut, u, v, w, g.dzi, g.dx, g.dy, rhoref, rhorefh)
+
+    def advec_2_v(self, vt, u, v, w, rhoref, rhorefh):
+        g = self.g; self._call("ref_advec_2_v", vt, u, v, w, g.dzi, g.dx, g.dy, rhoref, rhorefh)
+
+    def advec_2_w(self, wt, u, v, w, rhoref, rhorefh):
+        g = self.g; self._call("ref_advec_2_w", wt, u, v, w, g.dzhi, g.dx, g.dy, rhoref, rhorefh)
+
+    def advec_2_s(self, st, s, u, v, w, rhoref, rhorefh):
+        g = self.g; self._call("ref_advec_2_s", st, s, u, v, w, g.dzi, g.dx, g.dy, rhoref, rhorefh)
+
+    def advec_2_cfl(self, u, v, w, dt):
+        g = self.g
+        return self._call("ref_advec_2_cfl", u, v, w, g.dzi, g.dx, g.dy, float(dt), restype=C.c_double)
+
+    # --- diff_2
+    def diff_2_c(self, at, a, visc):
+        g = self.g; self._call("ref_diff_2_c", at, a, float(visc), g.dx, g.dy, g.dzi, g.dzhi)
+
+    def diff_2_w(self, wt, w, visc):
+        g = self.g; self._call("ref_diff_2_w", wt, w, float(visc), g.dx, g.dy, g.dzi, g.dzhi)
+
     # --- diff_smag2
     def diff_strain2(self, strain2, u, v, w, ugradbot, vgradbot, surface):
         g = self.g; TF = g.TF

@@ -15,7 +15,7 @@ from . import oracle as O
 
 
 def default_params(ns=1):
-    return dict(surface_model=True, sw_mason=True, cs=0.23, tPr=1./3., swthermo="dry",
+    return dict(swadvec="2i5", swdiff="smag2", surface_model=True, sw_mason=True, cs=0.23, tPr=1./3., swthermo="dry",
                 mbcbot=O.BC_NEUMANN, mbctop=O.BC_NEUMANN, sbcbot=O.BC_NEUMANN, sbctop=O.BC_NEUMANN,
                 visc=1.e-5, svisc=1.e-5)
 
@@ -40,29 +40,48 @@ def dycore_substep(g, K, c, prm, substep, dt, pres=None, timers=None):
         K.ghost_cells_bot_2nd(c[s], prm["sbcbot"], c.get(s + "_bot"), c.get(s + "_gradbot"))
         K.ghost_cells_top_2nd(c[s], prm["sbctop"], c.get(s + "_top"), c.get(s + "_gradtop"))
     lap("boundary")
-    # exec_viscosity
-    K.diff_strain2(c["evisc"], c["u"], c["v"], c["w"], c["dudz_mo"], c["dvdz_mo"], surface)
-    N2 = np.zeros_like(c["evisc"])
-    K.thermo_dry_N2(N2, c[scal[0]], c["thref"])
-    K.diff_evisc(c["evisc"], c["u"], c["v"], c["w"], N2, c["dbdz_mo"], c["z0m"], prm["cs"], prm["tPr"], surface, prm["sw_mason"])
+    swadvec, swdiff = prm.get("swadvec", "2i5"), prm.get("swdiff", "smag2")
+    # exec_viscosity (Diff_smag2 only; Diff_2::exec_viscosity is empty)
+    if swdiff == "smag2":
+        K.diff_strain2(c["evisc"], c["u"], c["v"], c["w"], c["dudz_mo"], c["dvdz_mo"], surface)
+        N2 = np.zeros_like(c["evisc"])
+        K.thermo_dry_N2(N2, c[scal[0]], c["thref"])
+        K.diff_evisc(c["evisc"], c["u"], c["v"], c["w"], N2, c["dbdz_mo"], c["z0m"], prm["cs"], prm["tPr"], surface, prm["sw_mason"])
     lap("evisc")
     # thermo.exec
     if prm["swthermo"] == "dry":
         K.thermo_dry_buoyancy_tend_2nd(c["wt"], c[scal[0]], c["threfh"])
-    # advec.exec
-    K.advec_2i5_u(c["ut"], c["u"], c["v"], c["w"], rr, rh)
-    K.advec_2i5_v(c["vt"], c["u"], c["v"], c["w"], rr, rh)
-    K.advec_2i5_w(c["wt"], c["u"], c["v"], c["w"], rr, rh)
+    # advec.exec (Advec_2i5::exec src/advec_2i5.cxx:1017-1063, Advec_2::exec src/advec_2.cxx:311-345)
+    A = {"2i5": (K.advec_2i5_u, K.advec_2i5_v, K.advec_2i5_w, K.advec_2i5_s),
+         "2": (getattr(K, "advec_2_u", None), getattr(K, "advec_2_v", None), getattr(K, "advec_2_w", None), getattr(K, "advec_2_s", None))}[swadvec]
+    A[0](c["ut"], c["u"], c["v"], c["w"], rr, rh)
+    A[1](c["vt"], c["u"], c["v"], c["w"], rr, rh)
+    A[2](c["wt"], c["u"], c["v"], c["w"], rr, rh)
     for s in scal:
-        K.advec_2i5_s(c[s + "t"], c[s], c["u"], c["v"], c["w"], rr, rh)
+        A[3](c[s + "t"], c[s], c["u"], c["v"], c["w"], rr, rh)
     lap("advec")
     # diff.exec
+    if swdiff == "2":
+        # Diff_2::exec (src/diff_2.cxx:163-190)
+        K.diff_2_c(c["ut"], c["u"], prm["visc"])
+        K.diff_2_c(c["vt"], c["v"], prm["visc"])
+        K.diff_2_w(c["wt"], c["w"], prm["visc"])
+        for s in scal:
+            K.diff_2_c(c[s + "t"], c[s], prm["svisc"])
+        lap("diff")
+        return _pres_and_rk3(g, K, c, prm, substep, dt, pres, lap)
     K.diff_u(c["ut"], c["u"], c["v"], c["w"], c["evisc"], c["u_fluxbot"], c["u_fluxtop"], rr, rh, prm["visc"], surface)
     K.diff_v(c["vt"], c["u"], c["v"], c["w"], c["evisc"], c["v_fluxbot"], c["v_fluxtop"], rr, rh, prm["visc"], surface)
     K.diff_w(c["wt"], c["u"], c["v"], c["w"], c["evisc"], rr, rh, prm["visc"])
     for s in scal:
         K.diff_c(c[s + "t"], c[s], c["evisc"], c[s + "_fluxbot"], c[s + "_fluxtop"], rr, rh, prm["tPr"], prm["svisc"], surface)
     lap("diff")
+    return _pres_and_rk3(g, K, c, prm, substep, dt, pres, lap)
+
+
+def _pres_and_rk3(g, K, c, prm, substep, dt, pres, lap):
+    scal = c["scalars"]
+    rr, rh = c["rhoref"], c["rhorefh"]
     # pres.exec(sub_dt)
     if pres is None:
         pres = O.Pres2(g, rr, rh)

@@ -31,6 +31,7 @@ CASES = {
     "step_20x12x10_anel_stretched_f32": ((20, 12, 10), np.float32, True, True, 1),
 }
 DT = 2.0
+VISC2, SVISC2 = 0.5, 0.7          # viscosities of the Diff_2 vectors (large enough to matter in one step)
 
 
 def input_digest(case):
@@ -62,6 +63,26 @@ def main():
         R.diff_evisc(ck["evisc"], ck["u"], ck["v"], ck["w"], n2, ck["dbdz_mo"], ck["z0m"], 0.23, 1./3., True, True)
         out["evisc"] = ck["evisc"].copy()
         out["dn"] = np.float64(R.diff_dnmul(ck["evisc"], 1./3.)*DT)
+        # Advec_2 / Diff_2 single kernels (tendencies start at zero again)
+        c2 = copy.deepcopy(case); prepare_halos(g, c2)
+        R.advec_2_u(c2["ut"], c2["u"], c2["v"], c2["w"], rr, rh)
+        R.advec_2_v(c2["vt"], c2["u"], c2["v"], c2["w"], rr, rh)
+        R.advec_2_w(c2["wt"], c2["u"], c2["v"], c2["w"], rr, rh)
+        R.advec_2_s(c2["tht"], c2["th"], c2["u"], c2["v"], c2["w"], rr, rh)
+        for n in ("ut", "vt", "wt", "tht"):
+            out["advec2_" + n] = c2[n].copy()
+        out["cfl2"] = np.float64(R.advec_2_cfl(c2["u"], c2["v"], c2["w"], DT))
+        c3 = copy.deepcopy(case); prepare_halos(g, c3)
+        R.diff_2_c(c3["ut"], c3["u"], VISC2); R.diff_2_c(c3["vt"], c3["v"], VISC2); R.diff_2_w(c3["wt"], c3["w"], VISC2)
+        R.diff_2_c(c3["tht"], c3["th"], SVISC2)
+        for n in ("ut", "vt", "wt", "tht"):
+            out["diff2_" + n] = c3[n].copy()
+        # full RK3 step with the plain 2nd-order schemes (swadvec=2, swdiff=2)
+        c4 = copy.deepcopy(case)
+        prm2 = ostep.default_params(); prm2.update(swadvec="2", swdiff="2", visc=VISC2, svisc=SVISC2)
+        ostep.dycore_step(g, refbind.RefKernels(g), c4, prm2, DT)
+        for n in ("u", "v", "w", "th"):
+            out["step22_" + n] = c4[n].copy()
         # full RK3 step(s) in Model::exec order
         cs = copy.deepcopy(case)
         prm = ostep.default_params()

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 from util import TOL, rel_l2, make_pair, prepare_halos, interior
-from make_golden import input_digest
+from make_golden import VISC2, SVISC2, input_digest
 from oracle import oracle as O, step as ostep
 
 GOLD = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz")))
@@ -52,6 +52,25 @@ def test_oracle_reproduces_golden_bitexact(path):
         ostep.dycore_step(g, K, cs, ostep.default_params(), float(z["dt"]))
     for n in ("u", "v", "w", "th", "p"):
         assert np.array_equal(cs[n], z["step_" + n]), n
+    # Advec_2 / Diff_2 vectors
+    c2 = copy.deepcopy(case); prepare_halos(g, c2)
+    K.advec_2_u(c2["ut"], c2["u"], c2["v"], c2["w"], rr, rh)
+    K.advec_2_v(c2["vt"], c2["u"], c2["v"], c2["w"], rr, rh)
+    K.advec_2_w(c2["wt"], c2["u"], c2["v"], c2["w"], rr, rh)
+    K.advec_2_s(c2["tht"], c2["th"], c2["u"], c2["v"], c2["w"], rr, rh)
+    for n in ("ut", "vt", "wt", "tht"):
+        assert np.array_equal(c2[n], z["advec2_" + n]), n
+    assert K.advec_2_cfl(c2["u"], c2["v"], c2["w"], float(z["dt"])) == float(z["cfl2"])
+    c3 = copy.deepcopy(case); prepare_halos(g, c3)
+    K.diff_2_c(c3["ut"], c3["u"], VISC2); K.diff_2_c(c3["vt"], c3["v"], VISC2); K.diff_2_w(c3["wt"], c3["w"], VISC2)
+    K.diff_2_c(c3["tht"], c3["th"], SVISC2)
+    for n in ("ut", "vt", "wt", "tht"):
+        assert np.array_equal(c3[n], z["diff2_" + n]), n
+    c4 = copy.deepcopy(case)
+    prm2 = ostep.default_params(); prm2.update(swadvec="2", swdiff="2", visc=VISC2, svisc=SVISC2)
+    ostep.dycore_step(g, K, c4, prm2, float(z["dt"]))
+    for n in ("u", "v", "w", "th"):
+        assert np.array_equal(c4[n], z["step22_" + n]), n
 
 
 @pytest.mark.parametrize("n", [2, 6, 8, 12, 20, 30])
@@ -95,6 +114,24 @@ def test_cuda_matches_golden(path):
     assert rel_l2(f["evisc"].cpu().numpy(), z["evisc"]) <= 10*TOL[dtype]
     dn = D.Diff(ctx, prm).get_dn(f, float(z["dt"]))
     assert abs(dn - float(z["dn"])) <= 100*TOL[dtype]*float(z["dn"])
+    # Advec_2 / Diff_2 kernels and the (2, 2) full step
+    f3 = D.Fields(ctx, ck)
+    D.Advec(ctx, "2").exec(f3)
+    for n in ("ut", "vt", "wt", "tht"):
+        k0 = g.kstart + 1 if n == "wt" else g.kstart
+        assert rel_l2(interior(g, f3[n].cpu().numpy(), k0), interior(g, z["advec2_" + n], k0)) <= TOL[dtype], n
+    cfl2 = D.Advec(ctx, "2").get_cfl(f3, float(z["dt"]))
+    assert abs(cfl2 - float(z["cfl2"])) <= 10*TOL[dtype]*float(z["cfl2"])
+    f4 = D.Fields(ctx, ck, visc=VISC2, svisc=SVISC2)
+    D.Diff_2(ctx).exec(f4)
+    for n in ("ut", "vt", "wt", "tht"):
+        k0 = g.kstart + 1 if n == "wt" else g.kstart
+        assert rel_l2(interior(g, f4[n].cpu().numpy(), k0), interior(g, z["diff2_" + n], k0)) <= TOL[dtype], n
+    f5 = D.Fields(ctx, case, visc=VISC2, svisc=SVISC2)
+    D.Dycore(ctx, D.make_params(swadvec="2", swdiff="2")).step(f5, float(z["dt"]))
+    ctx.sync()
+    for n in ("u", "v", "w", "th"):
+        assert rel_l2(interior(g, f5[n].cpu().numpy()), interior(g, z["step22_" + n])) <= TOL[dtype], n
     # full step
     f2 = D.Fields(ctx, case)
     for _ in range(int(z["nsteps"])):

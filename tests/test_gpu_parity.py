@@ -122,6 +122,54 @@ def test_diff_smag2(dtype, shape, surface):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("anel", [False, True])
+def test_advec_2_and_diff_2(dtype, shape, anel):
+    """Advec_2 (src/advec_2.cxx) and Diff_2 (src/diff_2.cxx) kernels, cfl and dn against the oracle."""
+    g, gd, case = make_pair(*shape, dtype, stretched=True, anelastic=anel)
+    prepare_halos(g, case)
+    D, ctx, f, prm = gpu_setup(gd, case)
+    D.Advec(ctx, "2").exec(f)
+    rr, rh = case["rhoref"], case["rhorefh"]
+    ref = {n: g.field() for n in ("ut", "vt", "wt", "tht")}
+    O.advec_2_u(g, ref["ut"], case["u"], case["v"], case["w"], rr, rh)
+    O.advec_2_v(g, ref["vt"], case["u"], case["v"], case["w"], rr, rh)
+    O.advec_2_w(g, ref["wt"], case["u"], case["v"], case["w"], rr, rh)
+    O.advec_2_s(g, ref["tht"], case["th"], case["u"], case["v"], case["w"], rr, rh)
+    for n in ref:
+        assert rel_l2(f[n].cpu().numpy(), ref[n]) <= TOL[dtype], n
+    cfl = D.Advec(ctx, "2").get_cfl(f, 3.0)
+    assert abs(cfl - float(O.advec_2_cfl(g, case["u"], case["v"], case["w"], 3.0))) <= 10*TOL[dtype]*cfl
+    # Diff_2 on top of the advection tendencies (the kernels accumulate)
+    f.visc, f.svisc = 0.5, 0.7
+    f._build()
+    D.Diff_2(ctx).exec(f)
+    O.diff_2_c(g, ref["ut"], case["u"], 0.5); O.diff_2_c(g, ref["vt"], case["v"], 0.5)
+    O.diff_2_w(g, ref["wt"], case["w"], 0.5); O.diff_2_c(g, ref["tht"], case["th"], 0.7)
+    for n in ref:
+        assert rel_l2(f[n].cpu().numpy(), ref[n]) <= TOL[dtype], n
+    dn = D.Diff_2(ctx).get_dn(f, 2.0)
+    assert abs(dn - 2.0*O.diff_2_dnmul(g, 0.7)) <= 10*TOL[dtype]*dn
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("swadvec,swdiff", [("2", "2"), ("2", "smag2"), ("2i5", "2")])
+def test_full_rk3_step_scheme_combinations(dtype, swadvec, swdiff):
+    """Full RK3 step with Advec_2 / Diff_2 in every combination with the LES schemes."""
+    g, gd, case = make_pair(32, 24, 16, dtype, stretched=True, anelastic=True)
+    D, ctx, f, _ = gpu_setup(gd, case)
+    f.visc, f.svisc = 0.5, 0.7
+    f._build()
+    prm = D.make_params(swadvec=swadvec, swdiff=swdiff)
+    oprm = ostep.default_params(); oprm.update(swadvec=swadvec, swdiff=swdiff, visc=0.5, svisc=0.7)
+    D.Dycore(ctx, prm).step(f, 2.0)
+    ostep.dycore_step(g, O.NumpyKernels(g), case, oprm, 2.0)
+    ctx.sync()
+    for n in ("u", "v", "w", "th"):
+        assert rel_l2(interior(g, f[n].cpu().numpy()), interior(g, case[n])) <= TOL[dtype], n
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 def test_thermo_dry_buoyancy(dtype):
     g, gd, case = make_pair(32, 16, 12, dtype)
     prepare_halos(g, case)

@@ -50,6 +50,15 @@ def test_kernels_bitexact(dtype, shape, anel, stretched):
     pair("advec_v", ["vt"], lambda K, c: K.advec_2i5_v(c["vt"], c["u"], c["v"], c["w"], rr, rh))
     pair("advec_w", ["wt"], lambda K, c: K.advec_2i5_w(c["wt"], c["u"], c["v"], c["w"], rr, rh))
     pair("advec_s", ["tht"], lambda K, c: K.advec_2i5_s(c["tht"], c["th"], c["u"], c["v"], c["w"], rr, rh))
+    # Advec_2 / Diff_2 (reference src/advec_2.cxx, src/diff_2.cxx)
+    pair("advec_2_u", ["ut"], lambda K, c: K.advec_2_u(c["ut"], c["u"], c["v"], c["w"], rr, rh))
+    pair("advec_2_v", ["vt"], lambda K, c: K.advec_2_v(c["vt"], c["u"], c["v"], c["w"], rr, rh))
+    pair("advec_2_w", ["wt"], lambda K, c: K.advec_2_w(c["wt"], c["u"], c["v"], c["w"], rr, rh))
+    pair("advec_2_s", ["tht"], lambda K, c: K.advec_2_s(c["tht"], c["th"], c["u"], c["v"], c["w"], rr, rh))
+    pair("diff_2_c", ["ut"], lambda K, c: K.diff_2_c(c["ut"], c["u"], 0.7))
+    pair("diff_2_c_s", ["tht"], lambda K, c: K.diff_2_c(c["tht"], c["th"], 1.3))
+    pair("diff_2_w", ["wt"], lambda K, c: K.diff_2_w(c["wt"], c["w"], 0.7))
+    assert N.advec_2_cfl(case["u"], case["v"], case["w"], 2.0) == R.advec_2_cfl(case["u"], case["v"], case["w"], 2.0)
     pair("buoyancy", ["wt"], lambda K, c: K.thermo_dry_buoyancy_tend_2nd(c["wt"], c["th"], c["threfh"]))
 
     for surface in (True, False):
@@ -112,6 +121,21 @@ def test_rk3_and_tdma_bitexact(dtype, substep):
     P.solve(q0, pc0)
     P.solve(q1, pc1, tdma=lambda pp, b: R.tdma(P.a.copy(), b, P.c.copy(), pp))
     assert np.array_equal(pc0, pc1)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("swadvec,swdiff", [("2", "2"), ("2", "smag2"), ("2i5", "2")])
+def test_full_rk3_step_scheme_combinations_bitexact(dtype, swadvec, swdiff):
+    """Advec_2 / Diff_2 in every combination with the LES schemes ("2" + "smag2" is drycblles as shipped)."""
+    g, gd, case = make_pair(20, 12, 10, dtype, stretched=True, anelastic=True)
+    c0, c1 = copy.deepcopy(case), copy.deepcopy(case)
+    N, R = both(g)
+    prm = ostep.default_params(); prm.update(swadvec=swadvec, swdiff=swdiff, visc=0.5, svisc=0.7)
+    ostep.dycore_step(g, N, c0, prm, 2.0)
+    ostep.dycore_step(g, R, c1, prm, 2.0)
+    for n in ("u", "v", "w", "th", "p"):
+        assert np.array_equal(c0[n], c1[n]), n
+    assert np.isfinite(interior(g, c0["u"])).all()
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
