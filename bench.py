@@ -24,6 +24,9 @@ if ROOT not in sys.path:
 
 import numpy as np
 
+# NCCL prints its version banner to stdout when NCCL_DEBUG is VERSION/WARN; keep stdout for the ONE JSON line
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 METRIC = "grid-point RK3 steps/s"
 UNIT = "grid-point-steps/s"
 

@@ -24,7 +24,7 @@ import numpy as np
 # Grid (reference src/grid.cxx:141-170 sizes, :245-304 metrics for swspatialorder=2)
 # --------------------------------------------------------------------------------------
 class Grid:
-    def __init__(self, itot, jtot, ktot, xsize, ysize, zsize, igc, jgc, kgc, dtype=np.float64, z=None):
+    def __init__(self, itot, jtot, ktot, xsize, ysize, zsize, igc, jgc, kgc, dtype=np.float64, z=None, order=2):
         TF = np.dtype(dtype).type
         self.TF = TF
         self.itot, self.jtot, self.ktot = itot, jtot, ktot
@@ -50,7 +50,59 @@ class Grid:
             dz = zsize / ktot
             z = np.linspace(0.5*dz, zsize - 0.5*dz, ktot)
         self.z[ks:ke] = np.asarray(z, TF)
-        self._calculate_2nd()
+        self.order = order
+        if order == 4:
+            assert kgc >= 3 and igc >= 3, "swspatialorder=4 uses three ghost cells (src/grid.cxx:87-92)"
+            self._calculate_4th()
+        else:
+            self._calculate_2nd()
+
+    def _calculate_4th(self):
+        """src/grid.cxx:306-375.  Literals like `2.` / `(1./3.)` are double in the reference, so those lines are
+        evaluated in double and narrowed on assignment; `ci0<TF>*z[..]` lines stay in TF."""
+        TF = self.TF
+        D = np.float64
+        ks, ke, kc = self.kstart, self.kend, self.kcells
+        z, zh, dz, dzh, dzi, dzhi = self.z, self.zh, self.dz, self.dzh, self.dzi, self.dzhi
+        self.dzi4 = np.zeros(kc, TF); self.dzhi4 = np.zeros(kc, TF)
+        dzi4, dzhi4 = self.dzi4, self.dzhi4
+        dhuge = 1e30
+        z[ks-1] = TF(-2.*D(z[ks]) + (1./3.)*D(z[ks+1]))
+        z[ks-2] = TF(-9.*D(z[ks]) + 2.*D(z[ks+1]))
+        z[ke] = TF((8./3.)*D(self.zsize) - 2.*D(z[ke-1]) + (1./3.)*D(z[ke-2]))
+        z[ke+1] = TF(8.*D(self.zsize) - 9.*D(z[ke-1]) + 2.*D(z[ke-2]))
+        z[ks-3] = TF(dhuge); z[ke+2] = TF(dhuge)
+        ci = [TF(c) for c in CI]; bi = [TF(c) for c in BI]; ti = [TF(c) for c in TI]
+        cg = [TF(c) for c in CG]; bg = [TF(c) for c in BG]; tg = [TF(c) for c in TG]
+        w4 = lambda c, a, k0: c[0]*a[k0] + c[1]*a[k0+1] + c[2]*a[k0+2] + c[3]*a[k0+3]
+        zh[ks] = TF(0.)
+        for k in range(ks+1, ke):
+            zh[k] = w4(ci, z, k-2)
+        zh[ke] = self.zsize
+        zh[ks-1] = w4(bi, z, ks-2)
+        zh[ke+1] = w4(ti, z, ke-2)
+        with np.errstate(over="ignore", invalid="ignore"):
+            for k in range(1, kc):
+                dzh[k] = z[k] - z[k-1]
+                dzhi[k] = TF(1./D(dzh[k]))
+            dzh[ks-3] = dzh[ks+3]; dzhi[ks-3] = dzhi[ks+3]
+            for k in range(1, kc-1):
+                dz[k] = zh[k+1] - zh[k]
+                dzi[k] = TF(1./D(dz[k])) if dz[k] != 0 else TF(np.inf)
+        dz[ks-3] = dz[ks+2]; dzi[ks-3] = dzi[ks+2]
+        dz[ke+2] = dz[ke-3]; dzi[ke+2] = dzi[ke-3]
+        for k in range(ks, ke):
+            dzi4[k] = TF(1./D(w4(cg, zh, k-1)))
+            dzhi4[k] = TF(1./D(w4(cg, z, k-2)))
+        dzhi4[ke] = TF(1./D(w4(cg, z, ke-2)))
+        dzi4[ks-1] = TF(1./D(w4(bg, zh, ks-1)))
+        dzhi4[ks-1] = TF(1./D(w4(bg, z, ks-2)))
+        dzi4[ke] = TF(1./D(w4(tg, zh, ke-2)))
+        dzhi4[ke+1] = TF(1./D(w4(tg, z, ke-2)))
+        self.dzhi4bot = TF(1./D(w4(bg, z, ks-1)))
+        self.dzhi4top = TF(1./D(w4(tg, z, ke-3)))
+        for k in (ks-2, ks-3, ke+1, ke+2):
+            dzi4[k] = TF(dhuge)
 
     def _calculate_2nd(self):
         """src/grid.cxx:274-304"""
@@ -98,6 +150,14 @@ def _K(g, v, dk=0, k0=None, k1=None):
 # --------------------------------------------------------------------------------------
 # Finite-difference helpers (reference include/finite_difference.h:33-158)
 # --------------------------------------------------------------------------------------
+# 4th-order weights (include/finite_difference.h:58-93)
+CI = (-1./16., 9./16., 9./16., -1./16.)
+BI = (5./16., 15./16., -5./16., 1./16.)
+TI = (1./16., -5./16., 15./16., 5./16.)
+CG = (1./24., -27./24., 27./24., -1./24.)
+BG = (-23./24., 21./24., 3./24., -1./24.)
+TG = (1./24., -3./24., -21./24., 23./24.)
+CDG = (-1460./576., 783./576., -54./576., 1./576.)
 def interp2(a, b):
     return a.dtype.type(0.5)*(a + b)
 
@@ -499,6 +559,156 @@ def diff_2_dnmul(g, viscmax):
     TF = g.TF
     dz = g.dz[g.kstart:g.kend]
     return float(np.max(np.abs(TF(viscmax) * (1./np.float64(g.dx*g.dx) + 1./np.float64(g.dy*g.dy) + 1./(dz*dz).astype(np.float64)))))
+
+
+# --------------------------------------------------------------------------------------
+# Advec_4 (reference src/advec_4.cxx:50-487): 4th-order divergence (cg weights) of products of 4th-order
+# interpolations (ci weights); the outermost vertical flux of the first / last row uses the one-sided
+# bi / ti interpolation of the advected quantity.  Every direction is its own `-=` statement in the
+# reference, so every direction is rounded into the tendency separately here as well.
+# --------------------------------------------------------------------------------------
+def _w4(c, a, b, cc, d, TF):
+    """c0*a + c1*b + c2*c + c3*d, left to right, in TF"""
+    return TF(c[0])*a + TF(c[1])*b + TF(c[2])*cc + TF(c[3])*d
+
+
+def _advec4_rows(g, lo):
+    """(k0, k1, bottom?, top?) row groups of a tendency whose first row is `lo`"""
+    return ((lo, lo+1, True, False), (lo+1, g.kend-1, False, False), (g.kend-1, g.kend, False, True))
+
+
+def _advec4_generic(g, at, q, vel_x, vel_y, vel_z, dzx, lo):
+    """at -= d(vel_x q)/dx; at -= d(vel_y q)/dy (3-D only); at -= d(vel_z q)/dz.
+    vel_d(m, k0, k1): advecting velocity at flux point m = 0..3 of direction d; q interpolated along d."""
+    TF = g.TF
+    dxi, dyi = TF(1.)/g.dx, TF(1.)/g.dy
+    dim3 = g.jtot > 1
+    for (k0, k1, bot, top) in _advec4_rows(g, lo):
+        if k1 <= k0:
+            continue
+        Q = lambda dk=0, dj=0, di=0: _S(g, q, dk, dj, di, k0, k1)
+        tgt = _S(g, at, 0, 0, 0, k0, k1)
+        def div(vel, qi):
+            return ( TF(CG[0])*(vel(0, k0, k1)*qi(0)) + TF(CG[1])*(vel(1, k0, k1)*qi(1))
+                   + TF(CG[2])*(vel(2, k0, k1)*qi(2)) + TF(CG[3])*(vel(3, k0, k1)*qi(3)) )
+        tgt[...] -= div(vel_x, lambda m: _w4(CI, Q(0, 0, m-3), Q(0, 0, m-2), Q(0, 0, m-1), Q(0, 0, m), TF)) * dxi
+        if dim3:
+            tgt[...] -= div(vel_y, lambda m: _w4(CI, Q(0, m-3), Q(0, m-2), Q(0, m-1), Q(0, m), TF)) * dyi
+        def qz(m):
+            if bot and m == 0:
+                return _w4(BI, Q(-2), Q(-1), Q(0), Q(1), TF)
+            if top and m == 3:
+                return _w4(TI, Q(-1), Q(0), Q(1), Q(2), TF)
+            return _w4(CI, Q(m-3), Q(m-2), Q(m-1), Q(m), TF)
+        tgt[...] -= div(vel_z, qz) * _K(g, dzx, 0, k0, k1)
+
+
+def advec_4_u(g, ut, u, v, w):
+    """src/advec_4.cxx:88-186"""
+    TF = g.TF
+    I = lambda a, b, c, d: _w4(CI, a, b, c, d, TF)
+    U = lambda k0, k1, dk=0, dj=0, di=0: _S(g, u, dk, dj, di, k0, k1)
+    V = lambda k0, k1, dk=0, dj=0, di=0: _S(g, v, dk, dj, di, k0, k1)
+    W = lambda k0, k1, dk=0, dj=0, di=0: _S(g, w, dk, dj, di, k0, k1)
+    vx = lambda m, k0, k1: I(U(k0, k1, 0, 0, m-3), U(k0, k1, 0, 0, m-2), U(k0, k1, 0, 0, m-1), U(k0, k1, 0, 0, m))
+    vy = lambda m, k0, k1: I(V(k0, k1, 0, m-1, -2), V(k0, k1, 0, m-1, -1), V(k0, k1, 0, m-1, 0), V(k0, k1, 0, m-1, 1))
+    vz = lambda m, k0, k1: I(W(k0, k1, m-1, 0, -2), W(k0, k1, m-1, 0, -1), W(k0, k1, m-1, 0, 0), W(k0, k1, m-1, 0, 1))
+    _advec4_generic(g, ut, u, vx, vy, vz, g.dzi4, g.kstart)
+
+
+def advec_4_v(g, vt, u, v, w):
+    """src/advec_4.cxx:188-286"""
+    TF = g.TF
+    I = lambda a, b, c, d: _w4(CI, a, b, c, d, TF)
+    U = lambda k0, k1, dk=0, dj=0, di=0: _S(g, u, dk, dj, di, k0, k1)
+    V = lambda k0, k1, dk=0, dj=0, di=0: _S(g, v, dk, dj, di, k0, k1)
+    W = lambda k0, k1, dk=0, dj=0, di=0: _S(g, w, dk, dj, di, k0, k1)
+    vx = lambda m, k0, k1: I(U(k0, k1, 0, -2, m-1), U(k0, k1, 0, -1, m-1), U(k0, k1, 0, 0, m-1), U(k0, k1, 0, 1, m-1))
+    vy = lambda m, k0, k1: I(V(k0, k1, 0, m-3), V(k0, k1, 0, m-2), V(k0, k1, 0, m-1), V(k0, k1, 0, m))
+    vz = lambda m, k0, k1: I(W(k0, k1, m-1, -2), W(k0, k1, m-1, -1), W(k0, k1, m-1, 0), W(k0, k1, m-1, 1))
+    _advec4_generic(g, vt, v, vx, vy, vz, g.dzi4, g.kstart)
+
+
+def advec_4_w(g, wt, u, v, w):
+    """src/advec_4.cxx:288-386 (rows kstart+1 .. kend-1; both factors of the outermost vertical flux one-sided)"""
+    TF = g.TF
+    I = lambda a, b, c, d: _w4(CI, a, b, c, d, TF)
+    U = lambda k0, k1, dk=0, dj=0, di=0: _S(g, u, dk, dj, di, k0, k1)
+    V = lambda k0, k1, dk=0, dj=0, di=0: _S(g, v, dk, dj, di, k0, k1)
+    W = lambda k0, k1, dk=0, dj=0, di=0: _S(g, w, dk, dj, di, k0, k1)
+    vx = lambda m, k0, k1: I(U(k0, k1, -2, 0, m-1), U(k0, k1, -1, 0, m-1), U(k0, k1, 0, 0, m-1), U(k0, k1, 1, 0, m-1))
+    vy = lambda m, k0, k1: I(V(k0, k1, -2, m-1), V(k0, k1, -1, m-1), V(k0, k1, 0, m-1), V(k0, k1, 1, m-1))
+    lo = g.kstart+1
+    def vz(m, k0, k1):
+        if k0 == lo and m == 0:
+            return _w4(BI, W(k0, k1, -2), W(k0, k1, -1), W(k0, k1, 0), W(k0, k1, 1), TF)
+        if k1 == g.kend and m == 3:
+            return _w4(TI, W(k0, k1, -1), W(k0, k1, 0), W(k0, k1, 1), W(k0, k1, 2), TF)
+        return I(W(k0, k1, m-3), W(k0, k1, m-2), W(k0, k1, m-1), W(k0, k1, m))
+    _advec4_generic(g, wt, w, vx, vy, vz, g.dzhi4, lo)
+
+
+def advec_4_s(g, st, s, u, v, w):
+    """src/advec_4.cxx:388-486 (face velocities used directly)"""
+    vx = lambda m, k0, k1: _S(g, u, 0, 0, m-1, k0, k1)
+    vy = lambda m, k0, k1: _S(g, v, 0, m-1, 0, k0, k1)
+    vz = lambda m, k0, k1: _S(g, w, m-1, 0, 0, k0, k1)
+    _advec4_generic(g, st, s, vx, vy, vz, g.dzi4, g.kstart)
+
+
+def advec_4_cfl(g, u, v, w, dt):
+    """src/advec_4.cxx:50-86: interp4c(a,b,c,d) = ci0*(a+d) + ci1*(b+c)"""
+    TF = g.TF
+    dxi, dyi = TF(1.)/g.dx, TF(1.)/g.dy
+    i4c = lambda a, b, c, d: TF(CI[0])*(a+d) + TF(CI[1])*(b+c)
+    c = ( np.abs(i4c(_S(g, u, 0, 0, -1), _S(g, u), _S(g, u, 0, 0, 1), _S(g, u, 0, 0, 2)))*dxi
+        + np.abs(i4c(_S(g, v, 0, -1), _S(g, v), _S(g, v, 0, 1), _S(g, v, 0, 2)))*dyi
+        + np.abs(i4c(_S(g, w, -1), _S(g, w), _S(g, w, 1), _S(g, w, 2)))*_K(g, g.dzi) )
+    return TF(TF(c.max())*TF(dt))
+
+
+# --------------------------------------------------------------------------------------
+# Diff_4 (reference src/diff_4.cxx:40-175): nu * (7-point cdg laplacian in x, y; div(grad) with cg weights and
+# one-sided bg / tg gradients at the walls in z).  Three separate `+=` statements per point.
+# --------------------------------------------------------------------------------------
+def _diff4(g, at, a, visc, lo, dz_in, dz_out, dxidxi, dyidyi, in_off):
+    TF = g.TF
+    visc = TF(visc)
+    dim3 = g.jtot > 1
+    cdg = [TF(c) for c in CDG]
+    for (k0, k1, bot, top) in _advec4_rows(g, lo):
+        if k1 <= k0:
+            continue
+        A = lambda dk=0, dj=0, di=0: _S(g, a, dk, dj, di, k0, k1)
+        tgt = _S(g, at, 0, 0, 0, k0, k1)
+        tgt[...] += visc * (cdg[3]*A(0, 0, -3) + cdg[2]*A(0, 0, -2) + cdg[1]*A(0, 0, -1) + cdg[0]*A()
+                            + cdg[1]*A(0, 0, 1) + cdg[2]*A(0, 0, 2) + cdg[3]*A(0, 0, 3)) * dxidxi
+        if dim3:
+            tgt[...] += visc * (cdg[3]*A(0, -3) + cdg[2]*A(0, -2) + cdg[1]*A(0, -1) + cdg[0]*A()
+                                + cdg[1]*A(0, 1) + cdg[2]*A(0, 2) + cdg[3]*A(0, 3)) * dyidyi
+        def grad(m):
+            if bot and m == 0:
+                return _w4(BG, A(-2), A(-1), A(0), A(1), TF)
+            if top and m == 3:
+                return _w4(TG, A(-1), A(0), A(1), A(2), TF)
+            return _w4(CG, A(m-3), A(m-2), A(m-1), A(m), TF)
+        Kin = lambda m: _K(g, dz_in, m - 1 + in_off, k0, k1)
+        tgt[...] += visc * ( TF(CG[0])*grad(0)*Kin(0) + TF(CG[1])*grad(1)*Kin(1)
+                           + TF(CG[2])*grad(2)*Kin(2) + TF(CG[3])*grad(3)*Kin(3) ) * _K(g, dz_out, 0, k0, k1)
+
+
+def diff_4_c(g, at, a, visc):
+    """src/diff_4.cxx:40-105 (`dxidxi = 1./(dx*dx)`: double division narrowed to TF)"""
+    TF = g.TF
+    _diff4(g, at, a, visc, g.kstart, g.dzhi4, g.dzi4,
+           TF(1./np.float64(g.dx*g.dx)), TF(1./np.float64(g.dy*g.dy)), 0)
+
+
+def diff_4_w(g, wt, w, visc):
+    """src/diff_4.cxx:107-175 (`dxidxi = 1/(dx*dx)`: TF division; inner metric dzi4[k-2..k+1], outer dzhi4[k])"""
+    TF = g.TF
+    _diff4(g, wt, w, visc, g.kstart+1, g.dzi4, g.dzhi4,
+           TF(1.)/TF(g.dx*g.dx), TF(1.)/TF(g.dy*g.dy), -1)
 
 
 # --------------------------------------------------------------------------------------
@@ -987,6 +1197,13 @@ class NumpyKernels:
     def advec_2_s(self, st, s, u, v, w, rhoref, rhorefh): advec_2_s(self.g, st, s, u, v, w, rhoref, rhorefh)
     def advec_2_cfl(self, u, v, w, dt): return float(advec_2_cfl(self.g, u, v, w, dt))
     def diff_2_c(self, at, a, visc): diff_2_c(self.g, at, a, visc)
+    def advec_4_u(self, ut, u, v, w): advec_4_u(self.g, ut, u, v, w)
+    def advec_4_v(self, vt, u, v, w): advec_4_v(self.g, vt, u, v, w)
+    def advec_4_w(self, wt, u, v, w): advec_4_w(self.g, wt, u, v, w)
+    def advec_4_s(self, st, s, u, v, w): advec_4_s(self.g, st, s, u, v, w)
+    def advec_4_cfl(self, u, v, w, dt): return float(advec_4_cfl(self.g, u, v, w, dt))
+    def diff_4_c(self, at, a, visc): diff_4_c(self.g, at, a, visc)
+    def diff_4_w(self, wt, w, visc): diff_4_w(self.g, wt, w, visc)
     def diff_2_w(self, wt, w, visc): diff_2_w(self.g, wt, w, visc)
     def diff_strain2(self, strain2, u, v, w, ugradbot, vgradbot, surface): diff_strain2(self.g, strain2, u, v, w, ugradbot, vgradbot, surface)
     def diff_evisc(self, evisc, u, v, w, N2, bgradbot, z0m, cs, tPr, surface, mason=True): diff_evisc(self.g, evisc, N2, bgradbot, z0m, cs, tPr, surface, mason)

@@ -100,6 +100,29 @@ class RefKernels:
     def diff_2_w(self, wt, w, visc):
         g = self.g; self._call("ref_diff_2_w", wt, w, float(visc), g.dx, g.dy, g.dzi, g.dzhi)
 
+    # --- advec_4 / diff_4 (grid built with order=4)
+    def advec_4_u(self, ut, u, v, w):
+        g = self.g; self._call("ref_advec_4_u", ut, u, v, w, g.dzi4, g.dx, g.dy)
+
+    def advec_4_v(self, vt, u, v, w):
+        g = self.g; self._call("ref_advec_4_v", vt, u, v, w, g.dzi4, g.dx, g.dy)
+
+    def advec_4_w(self, wt, u, v, w):
+        g = self.g; self._call("ref_advec_4_w", wt, u, v, w, g.dzhi4, g.dx, g.dy)
+
+    def advec_4_s(self, st, s, u, v, w):
+        g = self.g; self._call("ref_advec_4_s", st, s, u, v, w, g.dzi4, g.dx, g.dy)
+
+    def advec_4_cfl(self, u, v, w, dt):
+        g = self.g
+        return self._call("ref_advec_4_cfl", u, v, w, g.dzi, g.dx, g.dy, float(dt), restype=C.c_double)
+
+    def diff_4_c(self, at, a, visc):
+        g = self.g; self._call("ref_diff_4_c", at, a, float(visc), g.dx, g.dy, g.dzi4, g.dzhi4)
+
+    def diff_4_w(self, wt, w, visc):
+        g = self.g; self._call("ref_diff_4_w", wt, w, float(visc), g.dx, g.dy, g.dzi4, g.dzhi4)
+
     # --- diff_smag2
     def diff_strain2(self, strain2, u, v, w, ugradbot, vgradbot, surface):
         g = self.g; TF = g.TF
