@@ -25,7 +25,10 @@ if ROOT not in sys.path:
 import numpy as np
 
 # NCCL prints its version banner to stdout when NCCL_DEBUG is VERSION/WARN; keep stdout for the ONE JSON line
+# (NCCL honours NCCL_DEBUG_FILE only above the VERSION level)
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 METRIC = "grid-point RK3 steps/s"
 UNIT = "grid-point-steps/s"

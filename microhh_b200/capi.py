@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libmhhb200.so")
 MHH_F64, MHH_F32 = 0, 1
 MHH_MAX_SCALARS = 8
 MHH_COMM_ID_BYTES = 128
+MHH_IPC_BYTES = 128
 EDGE_EAST_WEST, EDGE_NORTH_SOUTH, EDGE_BOTH = 0, 1, 2
 BC_NONE, BC_DIRICHLET, BC_NEUMANN = -1, 0, 1
 
@@ -68,6 +69,8 @@ SIGNATURES = {
     "mhh_profile_stop": (C.c_int, [_vp, C.POINTER(C.c_char_p)]),
     "mhh_comm_get_unique_id": (C.c_int, [_vp, C.c_int]),
     "mhh_comm_init": (C.c_int, [_vp, _vp, C.c_int]),
+    "mhh_comm_get_ipc_handles": (C.c_int, [_vp, _vp, C.c_int]),
+    "mhh_comm_open_peers": (C.c_int, [_vp, _vp, C.c_int]),
     "mhh_slab_layout": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(SlabInfo)]),
     "mhh_slab_xindex": (C.c_longlong, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_int]),
     "mhh_slab_yindex": (C.c_longlong, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),

@@ -161,6 +161,8 @@ struct Ctx : mhh_ctx
     TF *specT = nullptr;           // y side: mcl*jtot*ktot complex (== spec on a single GPU)
     TF *fac = nullptr;             // tdma factors, mcl*jtot*ktot
     SpecLayout lay{};
+    PeerPtrs<TF> peers{};          // IPC-mapped workspaces of all slab ranks (peers.on: fused transposes)
+    int *d_barrier = nullptr;      // dummy word for the all-reduce that closes a fused transpose
     TF *halo = nullptr;            // 4 staging buffers (send south/north, recv north/south) of halo_cap elements
     size_t halo_cap = 0;
     bool basestate_set = false;
@@ -176,6 +178,9 @@ struct Ctx : mhh_ctx
         cudaSetDevice(device);
         cudaFree(d_prof); cudaFree(d_mlen0); cudaFree(tw_xh); cudaFree(tw_xf); cudaFree(tw_y);
         cudaFree(d_bmati); cudaFree(d_bmatj); cudaFree(d_a); cudaFree(d_c); cudaFree(d_dz2rho); cudaFree(d_dz2);
+        for (int r = 0; r < MAX_SLAB_RANKS; ++r)
+            if (peers.on && r != rank) { if (peers.x[r]) cudaIpcCloseMemHandle(peers.x[r]); if (peers.y[r]) cudaIpcCloseMemHandle(peers.y[r]); }
+        cudaFree(d_barrier);
         if (specT != spec) cudaFree(specT);
         cudaFree(spec); cudaFree(fac); cudaFree(d_red); cudaFree(halo);
         if (comm) { std::string e; NcclApi* api = nccl_api(e); if (api) api->CommDestroy(comm); }
@@ -240,13 +245,13 @@ int wfft_y_attrs(mhh_ctx* c, int J)
 }
 
 template <typename TF>
-void wfft_x_forward_launch(int L, bool fused, int grid, cudaStream_t st, TF* spec, const RhsSrc<TF>& src, const GridDev<TF>& g, const SpecLayout& lay,
+void wfft_x_forward_launch(int L, bool fused, int grid, cudaStream_t st, TF* spec, const RhsSrc<TF>& src, const GridDev<TF>& g, const SpecLayout& lay, const PeerPtrs<TF>& pp,
                            const cplx<TF>* twh, const cplx<TF>* twf, long long nrows)
 {
     switch (L)
     {
-#define X(N) case N: if (fused) wfft_x_forward_kernel<TF, N, true><<<grid, 32 * WFFT_WARPS, wfft_smem<TF, N>(), st>>>(spec, src, g, lay, twh, twf, nrows); \
-                     else wfft_x_forward_kernel<TF, N, false><<<grid, 32 * WFFT_WARPS, wfft_smem<TF, N>(), st>>>(spec, src, g, lay, twh, twf, nrows); break;
+#define X(N) case N: if (fused) wfft_x_forward_kernel<TF, N, true><<<grid, 32 * WFFT_WARPS, wfft_smem<TF, N>(), st>>>(spec, src, g, lay, pp, twh, twf, nrows); \
+                     else wfft_x_forward_kernel<TF, N, false><<<grid, 32 * WFFT_WARPS, wfft_smem<TF, N>(), st>>>(spec, src, g, lay, pp, twh, twf, nrows); break;
         WFFT_X_CASES(X)
 #undef X
     }
@@ -265,11 +270,11 @@ void wfft_x_backward_launch(int L, int grid, cudaStream_t st, const TF* spec, TF
 }
 
 template <typename TF>
-void wfft_y_launch(int J, int grid, cudaStream_t st, TF* spec, const SpecLayout& lay, int nm, int ktot, const cplx<TF>* tw, int inverse)
+void wfft_y_launch(int J, int grid, cudaStream_t st, TF* spec, const SpecLayout& lay, const PeerPtrs<TF>& pp, int nm, int ktot, const cplx<TF>* tw, int inverse)
 {
     switch (J)
     {
-#define X(N) case N: wfft_y_kernel<TF, N><<<grid, 32 * WFFT_WARPS, wfft_smem<TF, N>(), st>>>(spec, lay, nm, ktot, tw, inverse); break;
+#define X(N) case N: wfft_y_kernel<TF, N><<<grid, 32 * WFFT_WARPS, wfft_smem<TF, N>(), st>>>(spec, lay, pp, nm, ktot, tw, inverse); break;
         WFFT_Y_CASES(X)
 #undef X
     }
@@ -344,6 +349,8 @@ int create_impl(const mhh_grid_desc* d, int dtype, int device, mhh_ctx** out)
     g.rhoref = c->d_prof + 6 * kc; g.rhorefh = c->d_prof + 7 * kc;
     g.thref = c->d_prof + 8 * kc; g.threfh = c->d_prof + 9 * kc;
 
+    CUDA_TRY(c, cudaMalloc(&c->d_barrier, sizeof(int)));
+    CUDA_TRY(c, cudaMemset(c->d_barrier, 0, sizeof(int)));
     CUDA_TRY(c, cudaMalloc(&c->d_red, sizeof(double)));
     CUDA_TRY(c, cudaMallocHost(&c->h_red, sizeof(double)));
 
@@ -1019,6 +1026,18 @@ int reduce_impl(Ctx<TF>* c, const TF* u, const TF* v, const TF* w, TF p0, TF p1,
 // The slab all-to-all (reference semantics: Transpose::exec_xy / exec_yx, src/transpose.cxx:117-271).  Block d of the
 // x-side buffer IS the message for rank d and block s of the y-side buffer IS the message from rank s (SpecLayout), so
 // there is no pack/unpack pass: grouped ncclSend/ncclRecv straight out of / into the workspaces.
+// All ranks have finished the kernels enqueued before this point once the all-reduce completes (it cannot finish
+// before every rank has contributed, and every rank contributes in stream order after its own kernels).
+template <typename TF>
+int slab_barrier(Ctx<TF>* c, const char* name)
+{
+    NcclApi* api = nccl_api(c->err);
+    if (!api) return MHH_E_CUDA;
+    NCCL_TRY(c, api, api->AllReduce(c->d_barrier, c->d_barrier, 1, ncclInt32, ncclMax, c->comm, c->stream));
+    prof_mark(c, name);
+    return MHH_OK;
+}
+
 template <typename TF>
 int slab_all_to_all(Ctx<TF>* c, bool forward)
 {
@@ -1063,14 +1082,15 @@ int pres_spectral_solve(Ctx<TF>* c, bool do_solve)
     const GridDev<TF>& g = c->g;
     const int mcl = c->lay.mcl;
     int rc;
-    if ((rc = slab_all_to_all<TF>(c, true)) != MHH_OK) return rc;
+    // fused transposes: the x transform already stored into the owners' y-side buffers; one all-reduce is the barrier
+    if ((rc = c->peers.on ? slab_barrier<TF>(c, "transpose_xy_barrier") : slab_all_to_all<TF>(c, true)) != MHH_OK) return rc;
     const int grid_p = c->num_sms * 2;
     const long long ypanels = (long long)((mcl + WFFT_WARPS - 1) / WFFT_WARPS) * g.ktot;
     const int grid_wy = (int)std::max<long long>(1, std::min<long long>(ypanels, (long long)c->num_sms * 8));
     if (g.jtot > 1)
     {
-        if (c->wfft_y) wfft_y_launch<TF>(g.jtot, grid_wy, c->stream, c->specT, c->lay, mcl, g.ktot, c->tw_y, 0);
-        else fft_y_kernel<TF><<<grid_p, 256, c->smem_y, c->stream>>>(c->specT, c->lay, mcl, g.jtot, g.ktot, c->plan_y, c->tw_y, c->mc_y, 0);
+        if (c->wfft_y) wfft_y_launch<TF>(g.jtot, grid_wy, c->stream, c->specT, c->lay, c->peers, mcl, g.ktot, c->tw_y, 0);
+        else fft_y_kernel<TF><<<grid_p, 256, c->smem_y, c->stream>>>(c->specT, c->lay, c->peers, mcl, g.jtot, g.ktot, c->plan_y, c->tw_y, c->mc_y, 0);
         KCHECKN(c, "fft_y_forward_kernel");
     }
     if (do_solve)
@@ -1081,11 +1101,12 @@ int pres_spectral_solve(Ctx<TF>* c, bool do_solve)
     }
     if (g.jtot > 1)
     {
-        if (c->wfft_y) wfft_y_launch<TF>(g.jtot, grid_wy, c->stream, c->specT, c->lay, mcl, g.ktot, c->tw_y, 1);
-        else fft_y_kernel<TF><<<grid_p, 256, c->smem_y, c->stream>>>(c->specT, c->lay, mcl, g.jtot, g.ktot, c->plan_y, c->tw_y, c->mc_y, 1);
+        if (c->wfft_y) wfft_y_launch<TF>(g.jtot, grid_wy, c->stream, c->specT, c->lay, c->peers, mcl, g.ktot, c->tw_y, 1);
+        else fft_y_kernel<TF><<<grid_p, 256, c->smem_y, c->stream>>>(c->specT, c->lay, c->peers, mcl, g.jtot, g.ktot, c->plan_y, c->tw_y, c->mc_y, 1);
         KCHECKN(c, "fft_y_backward_kernel");
     }
-    return slab_all_to_all<TF>(c, false);
+    else if (c->peers.on) { c->err = "fused transposes need jtot > 1"; return MHH_E_INVALID; }
+    return c->peers.on ? slab_barrier<TF>(c, "transpose_yx_barrier") : slab_all_to_all<TF>(c, false);
 }
 
 template <typename TF>
@@ -1106,8 +1127,8 @@ int pres_solve_impl(Ctx<TF>* c, const mhh_fields* f, double sub_dt)
     const long long nrows = (long long)g.jmax * g.ktot;
     const int grid_x = (int)std::min<long long>((nrows + c->rows_x - 1) / c->rows_x, (long long)c->num_sms * 4);
     const int grid_wx = (int)std::min<long long>((nrows + WFFT_WARPS - 1) / WFFT_WARPS, (long long)c->num_sms * 8);
-    if (c->wfft_x) wfft_x_forward_launch<TF>(g.itot / 2, true, grid_wx, c->stream, c->spec, src, g, c->lay, c->tw_xh, c->tw_xf, nrows);
-    else fft_x_forward_kernel<TF, true><<<grid_x, 256, c->smem_x, c->stream>>>(c->spec, src, g, c->lay, c->plan_x, c->tw_xh, c->tw_xf, c->rows_x, nrows);
+    if (c->wfft_x) wfft_x_forward_launch<TF>(g.itot / 2, true, grid_wx, c->stream, c->spec, src, g, c->lay, c->peers, c->tw_xh, c->tw_xf, nrows);
+    else fft_x_forward_kernel<TF, true><<<grid_x, 256, c->smem_x, c->stream>>>(c->spec, src, g, c->lay, c->peers, c->plan_x, c->tw_xh, c->tw_xf, c->rows_x, nrows);
     KCHECKN(c, "fft_x_forward_kernel");
     int rc = pres_spectral_solve<TF>(c, true);
     if (rc != MHH_OK) return rc;
@@ -1258,8 +1279,8 @@ int fft_roundtrip_impl(Ctx<TF>* c, const TF* in, TF* out, int solve)
     const int grid_x = (int)std::min<long long>((nrows + c->rows_x - 1) / c->rows_x, (long long)c->num_sms * 4);
     RhsSrc<TF> none{};
     const int grid_wx = (int)std::min<long long>((nrows + WFFT_WARPS - 1) / WFFT_WARPS, (long long)c->num_sms * 8);
-    if (c->wfft_x) wfft_x_forward_launch<TF>(g.itot / 2, false, grid_wx, c->stream, c->spec, none, g, c->lay, c->tw_xh, c->tw_xf, nrows);
-    else fft_x_forward_kernel<TF, false><<<grid_x, 256, c->smem_x, c->stream>>>(c->spec, none, g, c->lay, c->plan_x, c->tw_xh, c->tw_xf, c->rows_x, nrows);
+    if (c->wfft_x) wfft_x_forward_launch<TF>(g.itot / 2, false, grid_wx, c->stream, c->spec, none, g, c->lay, c->peers, c->tw_xh, c->tw_xf, nrows);
+    else fft_x_forward_kernel<TF, false><<<grid_x, 256, c->smem_x, c->stream>>>(c->spec, none, g, c->lay, c->peers, c->plan_x, c->tw_xh, c->tw_xf, c->rows_x, nrows);
     KCHECKN(c, "fft_x_forward_kernel");
     int rc = pres_spectral_solve<TF>(c, solve != 0);
     if (rc != MHH_OK) return rc;
@@ -1366,6 +1387,45 @@ int mhh_comm_init(mhh_ctx* ctx, const void* id, int nbytes)
     memcpy(&u, id, sizeof(u));
     NCCL_TRY(ctx, api, api->CommInitRank(&ctx->comm, ctx->nranks, u, ctx->rank));
     return MHH_OK;
+}
+
+int mhh_comm_get_ipc_handles(mhh_ctx* ctx, void* out, int nbytes)
+{
+    if (!ctx) return MHH_E_INVALID;
+    if (!out || nbytes < MHH_IPC_BYTES) { ctx->err = "get_ipc_handles: buffer too small"; return MHH_E_INVALID; }
+    DISPATCH1(ctx, ([&]() -> int {
+        cudaIpcMemHandle_t h[2];
+        static_assert(2 * sizeof(cudaIpcMemHandle_t) == MHH_IPC_BYTES, "handle size");
+        CUDA_TRY(c, cudaIpcGetMemHandle(&h[0], c->spec));
+        CUDA_TRY(c, cudaIpcGetMemHandle(&h[1], c->specT));
+        memcpy(out, h, sizeof(h));
+        return MHH_OK; })());
+}
+
+int mhh_comm_open_peers(mhh_ctx* ctx, const void* all, int nbytes)
+{
+    if (!ctx) return MHH_E_INVALID;
+    if (!all || nbytes < ctx->nranks * MHH_IPC_BYTES) { ctx->err = "open_peers: need nranks * MHH_IPC_BYTES bytes"; return MHH_E_INVALID; }
+    if (ctx->nranks == 1) return MHH_OK;
+    if (ctx->nranks > MAX_SLAB_RANKS) { ctx->err = "open_peers: too many ranks"; return MHH_E_INVALID; }
+    if (!ctx->comm) { ctx->err = "open_peers: call mhh_comm_init first"; return MHH_E_INVALID; }
+    { const char* e = getenv("MHH_NO_PEER"); if (e && e[0] == '1') return MHH_OK; }       // keep the NCCL all-to-all (A/B comparisons)
+    DISPATCH1(ctx, ([&]() -> int {
+        if (c->peers.on) { c->err = "open_peers: already open"; return MHH_E_INVALID; }
+        if (c->g.jtot == 1) return MHH_OK;
+        const cudaIpcMemHandle_t* h = static_cast<const cudaIpcMemHandle_t*>(all);
+        PeerPtrs<TF> pp{};
+        for (int r = 0; r < c->nranks; ++r)
+        {
+            if (r == c->rank) { pp.x[r] = c->spec; pp.y[r] = c->specT; continue; }
+            void *px = nullptr, *py = nullptr;
+            CUDA_TRY(c, cudaIpcOpenMemHandle(&px, h[2 * r], cudaIpcMemLazyEnablePeerAccess));
+            CUDA_TRY(c, cudaIpcOpenMemHandle(&py, h[2 * r + 1], cudaIpcMemLazyEnablePeerAccess));
+            pp.x[r] = static_cast<TF*>(px); pp.y[r] = static_cast<TF*>(py);
+        }
+        pp.on = 1;
+        c->peers = pp;
+        return MHH_OK; })());
 }
 
 int mhh_slab_layout(int itot, int jtot, int ktot, int npy, int rank, mhh_slab_info* out)

@@ -132,7 +132,7 @@ template <typename TF, int L> constexpr size_t wfft_smem() { return (size_t)WFFT
 // x forward, fused with Pres_2::input: one warp per (j,k) row of itot = 2L reals.
 // ------------------------------------------------------------------------------------------
 template <typename TF, int L, bool RHS_FUSED>
-__global__ void __launch_bounds__(32 * WFFT_WARPS) wfft_x_forward_kernel(TF* __restrict__ spec, const RhsSrc<TF> src, const GridDev<TF> g, const SpecLayout lay,
+__global__ void __launch_bounds__(32 * WFFT_WARPS) wfft_x_forward_kernel(TF* __restrict__ spec, const RhsSrc<TF> src, const GridDev<TF> g, const SpecLayout lay, const PeerPtrs<TF> pp,
         const cplx<TF>* __restrict__ tw_half, const cplx<TF>* __restrict__ tw_full, const long long nrows)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -186,10 +186,13 @@ __global__ void __launch_bounds__(32 * WFFT_WARPS) wfft_x_forward_kernel(TF* __r
             const cplx<TF> zc = cconj(row[fpad(digitrev<L>(m == 0 ? 0 : L - m))]);
             const cplx<TF> e = {TF(0.5) * (zm.x + zc.x), TF(0.5) * (zm.y + zc.y)};
             const cplx<TF> d = {TF(0.5) * (zm.x - zc.x), TF(0.5) * (zm.y - zc.y)};
-            out[lay.P == 1 ? (long long)m : lay.xidx(r, m)] = cadd(e, cmul(tw_full[m], cmul_mi(d)));
+            const cplx<TF> X = cadd(e, cmul(tw_full[m], cmul_mi(d)));
+            if (pp.on) *peer_y_slot<TF>(pp, lay, r, m) = X;                  // straight into the owner's y-side buffer (NVLink store)
+            else out[lay.P == 1 ? (long long)m : lay.xidx(r, m)] = X;
         }
         __syncwarp();
     }
+    if (pp.on) __threadfence_system();          // peer stores are performed before the kernel counts as finished
 }
 
 // ------------------------------------------------------------------------------------------
@@ -248,7 +251,7 @@ __global__ void __launch_bounds__(32 * WFFT_WARPS) wfft_x_backward_kernel(const 
 // bytes per y in fp64) of one level, each warp transforms one mode, the panel goes back in place.
 // ------------------------------------------------------------------------------------------
 template <typename TF, int J>
-__global__ void __launch_bounds__(32 * WFFT_WARPS) wfft_y_kernel(TF* __restrict__ spec, const SpecLayout lay, const int nm, const int ktot,
+__global__ void __launch_bounds__(32 * WFFT_WARPS) wfft_y_kernel(TF* __restrict__ spec, const SpecLayout lay, const PeerPtrs<TF> pp, const int nm, const int ktot,
         const cplx<TF>* __restrict__ tw, const int inverse)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -287,11 +290,14 @@ __global__ void __launch_bounds__(32 * WFFT_WARPS) wfft_y_kernel(TF* __restrict_
             {
                 cplx<TF> v = sm[c * RS + fpad(digitrev<J>(j))];
                 if (inverse) v.y = -v.y;
-                if (one) base[(long long)j * nm + c] = v; else S[lay.yidx(k, j, m0 + c)] = v;
+                if (one) base[(long long)j * nm + c] = v;
+                else if (pp.on && inverse) *peer_x_slot<TF>(pp, lay, k, j, m0 + c) = v;       // straight into the row owner's x-side buffer
+                else S[lay.yidx(k, j, m0 + c)] = v;
             }
         }
         __syncthreads();
     }
+    if (pp.on && inverse) __threadfence_system();
 }
 
 } // namespace mhh

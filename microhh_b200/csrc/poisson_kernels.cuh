@@ -93,6 +93,37 @@ inline SpecLayout make_spec_layout(int itot, int jtot, int ktot, int P, int rank
     return s;
 }
 
+// Peer-mapped spectral workspaces of all slab ranks (CUDA IPC over NVLink/NVSwitch).  When `on`, the x transform stores
+// its modes straight into the y-side buffer of the rank that owns them and the inverse y transform stores straight into
+// the x-side buffer of the rank that owns the row: the all-to-all IS the store phase of the FFT kernels (no separate
+// transpose pass, no staging), followed by one tiny all-reduce as a barrier.
+constexpr int MAX_SLAB_RANKS = 16;
+template <typename TF>
+struct PeerPtrs
+{
+    int on;
+    TF* x[MAX_SLAB_RANKS];      // x-side buffers (complex, as TF pairs)
+    TF* y[MAX_SLAB_RANKS];      // y-side buffers
+};
+
+// complex element address of (local row r, mode m) in the y-side buffer of the mode's owner
+template <typename TF>
+__device__ __forceinline__ cplx<TF>* peer_y_slot(const PeerPtrs<TF>& pp, const SpecLayout& lay, const long long r, const int m)
+{
+    const int d = lay.owner(m);
+    const int cnt = lay.count(d);
+    return reinterpret_cast<cplx<TF>*>(pp.y[d]) + ((long long)lay.rank * cnt + 0) * lay.rows + r * cnt + (m - lay.offset(d));
+}
+
+// complex element address of (level k, global row j, local mode ml) in the x-side buffer of the row's owner
+template <typename TF>
+__device__ __forceinline__ cplx<TF>* peer_x_slot(const PeerPtrs<TF>& pp, const SpecLayout& lay, const int k, const int j, const int ml)
+{
+    const int s = j / lay.jmax;
+    const int jl = j - s * lay.jmax;
+    return reinterpret_cast<cplx<TF>*>(pp.x[s]) + (long long)lay.m_off * lay.rows + ((long long)k * lay.jmax + jl) * lay.mcl + ml;
+}
+
 // integer division / remainder by a value whose log2 is known (or -1 -> generic)
 __device__ __forceinline__ void divmod(const int x, const int d, const int lg, int& quo, int& rem)
 {
@@ -251,7 +282,7 @@ struct RhsSrc
 };
 
 template <typename TF, bool RHS_FUSED>
-__global__ void fft_x_forward_kernel(TF* __restrict__ spec, const RhsSrc<TF> src, const GridDev<TF> g, const SpecLayout lay,
+__global__ void fft_x_forward_kernel(TF* __restrict__ spec, const RhsSrc<TF> src, const GridDev<TF> g, const SpecLayout lay, const PeerPtrs<TF> pp,
         const FftPlan plan, const cplx<TF>* __restrict__ tw_half, const cplx<TF>* __restrict__ tw_full,
         const int rows_per_cta, const long long nrows)
 {
@@ -321,11 +352,13 @@ __global__ void fft_x_forward_kernel(TF* __restrict__ spec, const RhsSrc<TF> src
                 const cplx<TF> e = {TF(0.5) * (zm.x + zc.x), TF(0.5) * (zm.y + zc.y)};
                 const cplx<TF> d = {TF(0.5) * (zm.x - zc.x), TF(0.5) * (zm.y - zc.y)};
                 const cplx<TF> o = cmul_mi(d);                  // (zm - zc)/(2i)
-                out[lay.xidx(row0 + r, m)] = cadd(e, cmul(tw_full[m], o));           // tw_full[m] = exp(-2 pi i m / N)
+                const cplx<TF> X = cadd(e, cmul(tw_full[m], o));           // tw_full[m] = exp(-2 pi i m / N)
+                if (pp.on) *peer_y_slot<TF>(pp, lay, row0 + r, m) = X; else out[lay.xidx(row0 + r, m)] = X;
             }
         }
         __syncthreads();
     }
+    if (pp.on) __threadfence_system();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -415,7 +448,7 @@ __global__ void fft_x_backward_kernel(const TF* __restrict__ spec, TF* __restric
 // inverse != 0 -> unnormalised inverse (conjugate trick).
 // ------------------------------------------------------------------------------------------
 template <typename TF>
-__global__ void fft_y_kernel(TF* __restrict__ spec, const SpecLayout lay, const int nm, const int jtot, const int ktot,
+__global__ void fft_y_kernel(TF* __restrict__ spec, const SpecLayout lay, const PeerPtrs<TF> pp, const int nm, const int jtot, const int ktot,
         const FftPlan plan, const cplx<TF>* __restrict__ tw, const int MC, const int inverse)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -454,11 +487,12 @@ __global__ void fft_y_kernel(TF* __restrict__ spec, const SpecLayout lay, const 
             {
                 cplx<TF> v = Z[c * ld + j];
                 if (inverse) v.y = -v.y;
-                S[lay.yidx(k, j, m0 + c)] = v;
+                if (pp.on && inverse) *peer_x_slot<TF>(pp, lay, k, j, m0 + c) = v; else S[lay.yidx(k, j, m0 + c)] = v;
             }
         }
         __syncthreads();
     }
+    if (pp.on && inverse) __threadfence_system();
 }
 
 // ------------------------------------------------------------------------------------------

@@ -66,6 +66,16 @@ class Context:
         dist.broadcast(t, src=0)
         buf = (C.c_ubyte * n)(*t.cpu().tolist())
         self.check(self.lib.mhh_comm_init(self.h, buf, n))
+        # fused transposes: exchange the CUDA IPC handles of the spectral workspaces and map the peers' buffers
+        if dist.get_backend() == "nccl":
+            m = capi.MHH_IPC_BYTES
+            hb = (C.c_ubyte * m)()
+            self.check(self.lib.mhh_comm_get_ipc_handles(self.h, hb, m))
+            mine = torch.tensor(list(hb), dtype=torch.uint8, device=dev)
+            allh = [torch.empty_like(mine) for _ in range(self.gd.npy)]
+            dist.all_gather(allh, mine)
+            flat = torch.cat(allh).cpu().tolist()
+            self.check(self.lib.mhh_comm_open_peers(self.h, (C.c_ubyte * len(flat))(*flat), len(flat)))
 
     def use_torch_stream(self):
         s = torch.cuda.current_stream(self.device)
