@@ -151,9 +151,10 @@ MHH_API int mhh_comm_init(mhh_ctx* ctx, const void* id, int nbytes);
  * two spectral workspaces, the host all-gathers them in rank order (MPI_Allgather / torch.distributed.all_gather),
  * every rank opens its peers'.  From then on the x transform stores its modes straight into the owning rank's y-side
  * workspace and the inverse y transform stores straight into the row owner's x-side workspace -- the all-to-all is the
- * store phase of the FFT kernels; one 4-byte all-reduce closes each transpose.  Without these calls (or with
- * MHH_NO_PEER=1) the transposes are grouped ncclSend/ncclRecv. */
-#define MHH_IPC_BYTES 128
+ * store phase of the FFT kernels; one 4-byte all-reduce closes each transpose.  The ghost-row exchange likewise pushes
+ * its strips straight into the neighbours' receive buffers.  Without these calls (or with MHH_NO_PEER=1) both use
+ * grouped ncclSend/ncclRecv. */
+#define MHH_IPC_BYTES 192
 MHH_API int mhh_comm_get_ipc_handles(mhh_ctx* ctx, void* out, int nbytes);
 MHH_API int mhh_comm_open_peers(mhh_ctx* ctx, const void* all_handles, int nbytes);
 

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libmhhb200.so")
 MHH_F64, MHH_F32 = 0, 1
 MHH_MAX_SCALARS = 8
 MHH_COMM_ID_BYTES = 128
-MHH_IPC_BYTES = 128
+MHH_IPC_BYTES = 192
 EDGE_EAST_WEST, EDGE_NORTH_SOUTH, EDGE_BOTH = 0, 1, 2
 BC_NONE, BC_DIRICHLET, BC_NEUMANN = -1, 0, 1
 

@@ -163,6 +163,12 @@ struct Ctx : mhh_ctx
     SpecLayout lay{};
     PeerPtrs<TF> peers{};          // IPC-mapped workspaces of all slab ranks (peers.on: fused transposes)
     int *d_barrier = nullptr;      // dummy word for the all-reduce that closes a fused transpose
+    // peer halos: two alternating sets of (from north, from south) receive buffers, exported over CUDA IPC; the
+    // neighbours' sets are mapped in peer_halo_{south,north}
+    TF *phalo = nullptr;           // own: [set][dir] x phalo_cap elements
+    size_t phalo_cap = 0;
+    TF *phalo_south = nullptr, *phalo_north = nullptr;     // base of the south / north neighbour's phalo
+    unsigned phalo_count = 0;
     TF *halo = nullptr;            // 4 staging buffers (send south/north, recv north/south) of halo_cap elements
     size_t halo_cap = 0;
     bool basestate_set = false;
@@ -180,6 +186,9 @@ struct Ctx : mhh_ctx
         cudaFree(d_bmati); cudaFree(d_bmatj); cudaFree(d_a); cudaFree(d_c); cudaFree(d_dz2rho); cudaFree(d_dz2);
         for (int r = 0; r < MAX_SLAB_RANKS; ++r)
             if (peers.on && r != rank) { if (peers.x[r]) cudaIpcCloseMemHandle(peers.x[r]); if (peers.y[r]) cudaIpcCloseMemHandle(peers.y[r]); }
+        if (phalo_south && phalo_south != phalo) cudaIpcCloseMemHandle(phalo_south);
+        if (phalo_north && phalo_north != phalo && phalo_north != phalo_south) cudaIpcCloseMemHandle(phalo_north);
+        cudaFree(phalo);
         cudaFree(d_barrier);
         if (specT != spec) cudaFree(specT);
         cudaFree(spec); cudaFree(fac); cudaFree(d_red); cudaFree(halo);
@@ -365,7 +374,9 @@ int create_impl(const mhh_grid_desc* d, int dtype, int device, mhh_ctx** out)
     if ((rc = twiddles<TF>(c, &c->tw_xf, g.itot)) != MHH_OK) return rc;
     if ((rc = twiddles<TF>(c, &c->tw_y, g.jtot)) != MHH_OK) return rc;
 
-    const size_t nspec = (size_t)2 * c->nm * g.jmax * g.ktot;
+    // x side: room for the 8-mode-panel layout of the fused peer transposes (a few per cent of padding when P > 1)
+    SpecLayout tiled = c->lay; tiled.xtiled = 1;
+    const size_t nspec = (size_t)2 * std::max<long long>((long long)c->nm * g.jmax * g.ktot, P > 1 ? tiled.xside_elems() : 0);
     const size_t nspecT = (size_t)2 * c->lay.mcl * g.jtot * g.ktot;
     const size_t nfac = (size_t)c->lay.mcl * g.jtot * g.ktot;
     CUDA_TRY(c, cudaMalloc(&c->spec, sizeof(TF) * nspec));
@@ -468,6 +479,9 @@ template <typename TF> inline const TF* P(const void* p) { return static_cast<co
 #define NEED_BASE(c) do { if (!(c)->basestate_set) { (c)->err = "mhh_set_basestate has not been called"; return MHH_E_INVALID; } } while (0)
 #define NEED(c, ptr, what) do { if (!(ptr)) { (c)->err = std::string(what) + " is NULL"; return MHH_E_INVALID; } } while (0)
 
+template <typename TF>
+int slab_barrier(Ctx<TF>* c, const char* name);
+
 // north/south ghost rows of a batch of fields from the slab neighbours (periodic in y across ranks)
 template <typename TF>
 int exchange_ns(Ctx<TF>* c, TF* const* flds, int nf, int w, int nk)
@@ -481,6 +495,22 @@ int exchange_ns(Ctx<TF>* c, TF* const* flds, int nf, int w, int nk)
     g.kcells = nk;                                  // 2-D companions: one level
     const size_t per = (size_t)w * g.icells * nk;
     const size_t need = per * nf;
+    if (c->phalo_south && need <= c->phalo_cap)
+    {
+        // peer halos: push the strips into the neighbours' receive buffers, barrier, unpack the own ones.  Two buffer sets
+        // alternate so that a neighbour that is still unpacking exchange n is never overwritten by exchange n+1.
+        HaloFields<TF> h{}; h.nf = nf;
+        for (int n = 0; n < nf; ++n) { NEED(c, flds[n], "field"); h.f[n] = flds[n]; }
+        const size_t set = (size_t)(c->phalo_count++ & 1u) * 2 * c->phalo_cap;
+        const int grid = (int)std::min<size_t>((need + 255) / 256, (size_t)c->num_sms * 8);
+        halo_push_kernel<TF><<<grid, 256, 0, c->stream>>>(h, g, w, c->phalo_south + set, c->phalo_north + set + c->phalo_cap);
+        KCHECKN(c, "halo_push_kernel");
+        int rcb = slab_barrier<TF>(c, "halo_barrier");
+        if (rcb != MHH_OK) return rcb;
+        halo_unpack_kernel<TF><<<grid, 256, 0, c->stream>>>(h, g, w, c->phalo + set, c->phalo + set + c->phalo_cap);
+        KCHECKN(c, "halo_unpack_kernel");
+        return MHH_OK;
+    }
     if (c->halo_cap < need)
     {
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
@@ -1394,10 +1424,19 @@ int mhh_comm_get_ipc_handles(mhh_ctx* ctx, void* out, int nbytes)
     if (!ctx) return MHH_E_INVALID;
     if (!out || nbytes < MHH_IPC_BYTES) { ctx->err = "get_ipc_handles: buffer too small"; return MHH_E_INVALID; }
     DISPATCH1(ctx, ([&]() -> int {
-        cudaIpcMemHandle_t h[2];
-        static_assert(2 * sizeof(cudaIpcMemHandle_t) == MHH_IPC_BYTES, "handle size");
+        cudaIpcMemHandle_t h[3];
+        static_assert(3 * sizeof(cudaIpcMemHandle_t) == MHH_IPC_BYTES, "handle size");
+        if (!c->phalo)
+        {
+            // receive buffers for the peer halos: up to 8 fields of jgc rows, two directions, two alternating sets
+            const GridDev<TF>& g = c->g;
+            c->phalo_cap = (size_t)8 * g.jgc * g.icells * g.kcells;
+            CUDA_TRY(c, cudaMalloc(&c->phalo, sizeof(TF) * c->phalo_cap * 4));
+            c->ws_bytes += (long long)(sizeof(TF) * c->phalo_cap * 4);
+        }
         CUDA_TRY(c, cudaIpcGetMemHandle(&h[0], c->spec));
         CUDA_TRY(c, cudaIpcGetMemHandle(&h[1], c->specT));
+        CUDA_TRY(c, cudaIpcGetMemHandle(&h[2], c->phalo));
         memcpy(out, h, sizeof(h));
         return MHH_OK; })());
 }
@@ -1419,12 +1458,22 @@ int mhh_comm_open_peers(mhh_ctx* ctx, const void* all, int nbytes)
         {
             if (r == c->rank) { pp.x[r] = c->spec; pp.y[r] = c->specT; continue; }
             void *px = nullptr, *py = nullptr;
-            CUDA_TRY(c, cudaIpcOpenMemHandle(&px, h[2 * r], cudaIpcMemLazyEnablePeerAccess));
-            CUDA_TRY(c, cudaIpcOpenMemHandle(&py, h[2 * r + 1], cudaIpcMemLazyEnablePeerAccess));
+            CUDA_TRY(c, cudaIpcOpenMemHandle(&px, h[3 * r], cudaIpcMemLazyEnablePeerAccess));
+            CUDA_TRY(c, cudaIpcOpenMemHandle(&py, h[3 * r + 1], cudaIpcMemLazyEnablePeerAccess));
             pp.x[r] = static_cast<TF*>(px); pp.y[r] = static_cast<TF*>(py);
+        }
+        if (c->phalo && !(getenv("MHH_NO_PEER_HALO") && getenv("MHH_NO_PEER_HALO")[0] == '1'))
+        {
+            const int south = (c->rank + c->nranks - 1) % c->nranks, north = (c->rank + 1) % c->nranks;
+            void *ps = nullptr, *pn = nullptr;
+            CUDA_TRY(c, cudaIpcOpenMemHandle(&ps, h[3 * south + 2], cudaIpcMemLazyEnablePeerAccess));
+            if (north == south) pn = ps;
+            else CUDA_TRY(c, cudaIpcOpenMemHandle(&pn, h[3 * north + 2], cudaIpcMemLazyEnablePeerAccess));
+            c->phalo_south = static_cast<TF*>(ps); c->phalo_north = static_cast<TF*>(pn);
         }
         pp.on = 1;
         c->peers = pp;
+        c->lay.xtiled = 1;
         return MHH_OK; })());
 }
 

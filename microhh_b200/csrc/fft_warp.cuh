@@ -213,11 +213,12 @@ __global__ void __launch_bounds__(32 * WFFT_WARPS) wfft_x_backward_kernel(const 
         // Z'[m] = (X[m] + conj X[L-m]) + i e^{+2 pi i m/N} (X[m] - conj X[L-m]); conj(Z') goes in so that the forward
         // transform yields conj(inverse)
         const cplx<TF>* X = reinterpret_cast<const cplx<TF>*>(spec) + (lay.P == 1 ? r * nm : 0);
+        const int kq0 = (int)(r / g.jmax), jq0 = (int)(r - (long long)kq0 * g.jmax);
 #pragma unroll
         for (int m = lane; m < L; m += 32)
         {
-            const cplx<TF> xm = X[lay.P == 1 ? (long long)m : lay.xidx(r, m)];
-            const cplx<TF> xc = cconj(X[lay.P == 1 ? (long long)(L - m) : lay.xidx(r, L - m)]);
+            const cplx<TF> xm = X[lay.P == 1 ? (long long)m : lay.xidx_kj(kq0, jq0, m)];
+            const cplx<TF> xc = cconj(X[lay.P == 1 ? (long long)(L - m) : lay.xidx_kj(kq0, jq0, L - m)]);
             const cplx<TF> e = cadd(xm, xc);
             const cplx<TF> d = csub(xm, xc);
             const cplx<TF> wd = cmul(cconj(tw_full[m]), d);

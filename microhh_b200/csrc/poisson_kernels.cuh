@@ -54,6 +54,8 @@ struct SpecLayout
     int mcl;      // modes owned by this rank
     int m_off;    // first owned mode
     long long rows;   // jmax*ktot
+    int xtiled;       // x side in 8-mode panels (fused peer transposes): block d = [k][panel][jl][8], so that the inverse y
+                      // transform's panel stores are long contiguous runs in the row owner's memory (NVLink-friendly)
 
     __host__ __device__ int count(const int d) const { return base + (d < rem ? 1 : 0); }
     __host__ __device__ int offset(const int d) const { return d * base + (d < rem ? d : rem); }
@@ -62,14 +64,29 @@ struct SpecLayout
         const int cut = rem * (base + 1);
         return m < cut ? m / (base + 1) : rem + (m - cut) / base;
     }
-    // x side: complex index of (row r, mode m)
-    __host__ __device__ long long xidx(const long long r, const int m) const
+    __host__ __device__ int pcnt(const int d) const { return (count(d) + 7) >> 3; }       // 8-mode panels of block d
+    __host__ __device__ long long xoff_tiled(const int d) const
     {
+        const int lo = (base + 7) >> 3, hi = (base + 8) >> 3;
+        return 8 * rows * ((long long)d * lo + (long long)(d < rem ? d : rem) * (hi - lo));
+    }
+    // x side: complex index of (level k, local row jl, mode m)
+    __host__ __device__ long long xidx_kj(const int k, const int jl, const int m) const
+    {
+        const long long r = (long long)k * jmax + jl;
         if (P == 1) return r * nm + m;
         const int d = owner(m);
         const int o = offset(d);
-        return (long long)o * rows + r * count(d) + (m - o);
+        if (!xtiled) return (long long)o * rows + r * count(d) + (m - o);
+        const int ml = m - o;
+        return xoff_tiled(d) + (((long long)k * pcnt(d) + (ml >> 3)) * jmax + jl) * 8 + (ml & 7);
     }
+    __host__ __device__ long long xidx(const long long r, const int m) const
+    {
+        const int k = (int)(r / jmax);
+        return xidx_kj(k, (int)(r - (long long)k * jmax), m);
+    }
+    __host__ __device__ long long xside_elems() const { return xtiled ? xoff_tiled(P) : (long long)nm * rows; }
     // y side: complex index of (level k, global row j, local mode ml)
     __host__ __device__ long long yidx(const int k, const int j, const int ml) const
     {
@@ -121,7 +138,9 @@ __device__ __forceinline__ cplx<TF>* peer_x_slot(const PeerPtrs<TF>& pp, const S
 {
     const int s = j / lay.jmax;
     const int jl = j - s * lay.jmax;
-    return reinterpret_cast<cplx<TF>*>(pp.x[s]) + (long long)lay.m_off * lay.rows + ((long long)k * lay.jmax + jl) * lay.mcl + ml;
+    // block `rank` of the (tiled) x side of rank s: [k][panel][jl][8]
+    return reinterpret_cast<cplx<TF>*>(pp.x[s]) + lay.xoff_tiled(lay.rank)
+           + (((long long)k * lay.pcnt(lay.rank) + (ml >> 3)) * lay.jmax + jl) * 8 + (ml & 7);
 }
 
 // integer division / remainder by a value whose log2 is known (or -1 -> generic)

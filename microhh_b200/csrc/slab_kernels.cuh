@@ -65,4 +65,28 @@ __global__ void __launch_bounds__(256) halo_unpack_kernel(const HaloFields<TF> h
     }
 }
 
+// Peer-memory variant of the pack: the strips are stored straight into the neighbours' receive buffers over NVLink
+// (dstN = the SOUTH neighbour's "from north" buffer gets my first rows, dstS = the NORTH neighbour's "from south" buffer
+// gets my last rows); no send staging, no NCCL transfer.
+template <typename TF>
+__global__ void __launch_bounds__(256) halo_push_kernel(const HaloFields<TF> h, const GridDev<TF> g, const int w,
+        TF* __restrict__ south_recvN, TF* __restrict__ north_recvS)
+{
+    const long long per = (long long)w * g.icells * g.kcells;
+    const long long n = per * h.nf;
+    const int rowlen = w * g.icells;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+    {
+        const int f = (int)(e / per);
+        const long long r = e - f * per;
+        const int k = (int)(r / rowlen);
+        const int r2 = (int)(r - (long long)k * rowlen);
+        const TF* __restrict__ a = h.f[f];
+        const long long lev = (long long)k * g.ijcells;
+        south_recvN[e] = a[lev + (long long)g.jstart * g.icells + r2];
+        north_recvS[e] = a[lev + (long long)(g.jend - w) * g.icells + r2];
+    }
+    __threadfence_system();
+}
+
 } // namespace mhh
