@@ -73,6 +73,9 @@ typedef struct mhh_grid_desc
     const void* dzhi;
     int npx, npy;                /* process grid (src/master_parallel.cxx:103-153); 1,1 = single GPU; npx must be 1 (y slabs) */
     int mpicoordx, mpicoordy;
+    /* 4th-order grid only (swspatialorder = 4, src/grid.cxx:306-375): HOST arrays of kcells, else NULL */
+    const void* dzi4;
+    const void* dzhi4;
 } mhh_grid_desc;
 
 /* Device pointers to the 3-D fields and their 2-D companions (Fields maps mp/mt/sp/st/sd,
@@ -184,7 +187,7 @@ MHH_API int mhh_boundary_ghost_cells_2nd(mhh_ctx* ctx, void* fld, int bcbot, con
                                  int bctop, const void* top, const void* gradtop);
 
 /* ---- Advec<TF>::exec / get_cfl  (swadvec = 25: Advec_2i5, src/advec_2i5.cxx:955-1063;
- *      swadvec = 2: Advec_2, src/advec_2.cxx:288-345) ------------------------------------------ */
+ *      swadvec = 2: Advec_2, src/advec_2.cxx:288-345; swadvec = 4: Advec_4, src/advec_4.cxx:573-684) */
 MHH_API int mhh_advec_exec(mhh_ctx* ctx, int swadvec, const mhh_fields* f);
 MHH_API int mhh_advec_get_cfl(mhh_ctx* ctx, int swadvec, const mhh_fields* f, double dt, double* cfl);
 
@@ -198,6 +201,9 @@ MHH_API int mhh_diff_smag2_get_dn(mhh_ctx* ctx, const mhh_fields* f, const mhh_p
 /* ---- Diff_2<TF>::exec / get_dn  (src/diff_2.cxx:133-190): nu * laplacian on u, v, w and every scalar ---- */
 MHH_API int mhh_diff_2_exec(mhh_ctx* ctx, const mhh_fields* f);
 MHH_API int mhh_diff_2_get_dn(mhh_ctx* ctx, const mhh_fields* f, double dt, double* dn);
+/* ---- Diff_4<TF>::exec (src/diff_4.cxx:255-310; get_dn is Diff_2's formula, :226-245 -> mhh_diff_2_get_dn).  Needs a
+ * 4th-order grid.  Advec_4 is mhh_advec_exec / mhh_advec_get_cfl with swadvec = 4 (src/advec_4.cxx:573-684). */
+MHH_API int mhh_diff_4_exec(mhh_ctx* ctx, const mhh_fields* f);
 
 /* ---- Thermo_dry<TF>::exec (buoyancy on wt) and get_thermo_field("N2")  (src/thermo_dry.cxx) -- */
 MHH_API int mhh_thermo_dry_exec(mhh_ctx* ctx, void* wt, const void* th);

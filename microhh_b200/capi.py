@@ -26,7 +26,8 @@ class GridDesc(C.Structure):
                 ("igc", C.c_int), ("jgc", C.c_int), ("kgc", C.c_int),
                 ("xsize", C.c_double), ("ysize", C.c_double), ("zsize", C.c_double),
                 ("z", _vp), ("zh", _vp), ("dz", _vp), ("dzh", _vp), ("dzi", _vp), ("dzhi", _vp),
-                ("npx", C.c_int), ("npy", C.c_int), ("mpicoordx", C.c_int), ("mpicoordy", C.c_int)]
+                ("npx", C.c_int), ("npy", C.c_int), ("mpicoordx", C.c_int), ("mpicoordy", C.c_int),
+                ("dzi4", _vp), ("dzhi4", _vp)]
 
 
 class FieldsC(C.Structure):
@@ -83,6 +84,7 @@ SIGNATURES = {
     "mhh_diff_smag2_exec": (C.c_int, [_vp, _PF, _PP]),
     "mhh_diff_smag2_get_dn": (C.c_int, [_vp, _PF, _PP, C.c_double, C.POINTER(C.c_double)]),
     "mhh_diff_2_exec": (C.c_int, [_vp, _PF]),
+    "mhh_diff_4_exec": (C.c_int, [_vp, _PF]),
     "mhh_diff_2_get_dn": (C.c_int, [_vp, _PF, C.c_double, C.POINTER(C.c_double)]),
     "mhh_thermo_dry_exec": (C.c_int, [_vp, _vp, _vp]),
     "mhh_thermo_dry_n2": (C.c_int, [_vp, _vp, _vp]),

@@ -19,6 +19,7 @@
 #include "tile3_kernels.cuh"
 #include "slab_kernels.cuh"
 #include "order2_kernels.cuh"
+#include "order4_kernels.cuh"
 #include <cudaTypedefs.h>
 #include <dlfcn.h>
 #include <nccl.h>
@@ -150,7 +151,7 @@ struct Ctx : mhh_ctx
     GridDev<TF> g{};
     mhh_grid_desc desc{};
     // device copies of the profiles
-    TF *d_prof = nullptr;          // 10 profiles x kcells
+    TF *d_prof = nullptr;          // 12 profiles x kcells
     TF *d_mlen0 = nullptr;
     // Pres_2
     int nm = 0;
@@ -344,8 +345,8 @@ int create_impl(const mhh_grid_desc* d, int dtype, int device, mhh_ctx** out)
     if (g.itot % 2 != 0) { c->err = "itot must be even"; return MHH_E_INVALID; }
 
     const int kc = g.kcells;
-    CUDA_TRY(c, cudaMalloc(&c->d_prof, sizeof(TF) * kc * 10));
-    CUDA_TRY(c, cudaMemset(c->d_prof, 0, sizeof(TF) * kc * 10));
+    CUDA_TRY(c, cudaMalloc(&c->d_prof, sizeof(TF) * kc * 12));
+    CUDA_TRY(c, cudaMemset(c->d_prof, 0, sizeof(TF) * kc * 12));
     const void* src[6] = {d->z, d->zh, d->dz, d->dzh, d->dzi, d->dzhi};
     for (int n = 0; n < 6; ++n)
     {
@@ -357,6 +358,15 @@ int create_impl(const mhh_grid_desc* d, int dtype, int device, mhh_ctx** out)
     g.dzi = c->d_prof + 4 * kc; g.dzhi = c->d_prof + 5 * kc;
     g.rhoref = c->d_prof + 6 * kc; g.rhorefh = c->d_prof + 7 * kc;
     g.thref = c->d_prof + 8 * kc; g.threfh = c->d_prof + 9 * kc;
+    g.dzi4 = nullptr; g.dzhi4 = nullptr;
+    if (d->dzi4 && d->dzhi4)
+    {
+        // 4th-order grid (src/grid.cxx:306-375): three ghost cells everywhere
+        if (g.igc < 3 || g.jgc < 3 || g.kgc < 3) { c->err = "a 4th-order grid needs igc, jgc, kgc >= 3"; return MHH_E_INVALID; }
+        CUDA_TRY(c, cudaMemcpy(c->d_prof + 10 * kc, d->dzi4, sizeof(TF) * kc, cudaMemcpyHostToDevice));
+        CUDA_TRY(c, cudaMemcpy(c->d_prof + 11 * kc, d->dzhi4, sizeof(TF) * kc, cudaMemcpyHostToDevice));
+        g.dzi4 = c->d_prof + 10 * kc; g.dzhi4 = c->d_prof + 11 * kc;
+    }
 
     CUDA_TRY(c, cudaMalloc(&c->d_barrier, sizeof(int)));
     CUDA_TRY(c, cudaMemset(c->d_barrier, 0, sizeof(int)));
@@ -1011,14 +1021,55 @@ int o2_impl(Ctx<TF>* c, const mhh_fields* f, bool adv, bool diff, bool buoy)
     return MHH_OK;
 }
 
+// Advec_4 / Diff_4 in any combination (order4_kernels.cuh)
 template <typename TF>
-int o2_cfl_impl(Ctx<TF>* c, const mhh_fields* f, double* out)
+int o4_impl(Ctx<TF>* c, const mhh_fields* f, bool adv, bool diff)
+{
+    const GridDev<TF>& g = c->g;
+    if (!g.dzi4) { c->err = "4th-order schemes need a 4th-order grid (dzi4 / dzhi4 in mhh_grid_desc, three ghost cells)"; return MHH_E_INVALID; }
+    if (g.kmax < 4) { c->err = "4th-order schemes need ktot >= 4"; return MHH_E_INVALID; }
+    int rc = check_mom<TF>(c, f, false, false);
+    if (rc != MHH_OK) return rc;
+    O4Args<TF> a{};
+    a.ut = P<TF>(f->ut); a.vt = P<TF>(f->vt); a.wt = P<TF>(f->wt);
+    a.u = P<TF>(f->u); a.v = P<TF>(f->v); a.w = P<TF>(f->w);
+    a.visc = (TF)f->visc;
+    a.dxidxi_c = (TF)(1. / (double)(g.dx * g.dx)); a.dyidyi_c = (TF)(1. / (double)(g.dy * g.dy));
+    a.dxidxi_w = TF(1) / (g.dx * g.dx); a.dyidyi_w = TF(1) / (g.dy * g.dy);
+    const bool dim3 = g.jtot > 1;
+    {
+        ::dim3 gr = c->grd_interior(), b = c->blk();
+#define O4(A, D, T) o4_uvw_kernel<TF, A, D, T><<<gr, b, 0, c->stream>>>(a, g)
+        if (adv && diff) { if (dim3) O4(true, true, true); else O4(true, true, false); }
+        else if (adv) { if (dim3) O4(true, false, true); else O4(true, false, false); }
+        else if (diff) { if (dim3) O4(false, true, true); else O4(false, true, false); }
+        else { c->err = "o4_impl: nothing to do"; return MHH_E_INVALID; }
+#undef O4
+        KCHECKN(c, "o4_uvw_kernel");
+        for (int n = 0; n < f->ns; ++n)
+        {
+            O4ScalArgs<TF> s{P<TF>(f->st[n]), P<TF>(f->s[n]), a.u, a.v, a.w, (TF)f->svisc[n], a.dxidxi_c, a.dyidyi_c};
+#define O4S(A, D, T) o4_s_kernel<TF, A, D, T><<<gr, b, 0, c->stream>>>(s, g)
+            if (adv && diff) { if (dim3) O4S(true, true, true); else O4S(true, true, false); }
+            else if (adv) { if (dim3) O4S(true, false, true); else O4S(true, false, false); }
+            else { if (dim3) O4S(false, true, true); else O4S(false, true, false); }
+#undef O4S
+            KCHECKN(c, "o4_s_kernel");
+        }
+    }
+    return MHH_OK;
+}
+
+template <typename TF>
+int o2_cfl_impl(Ctx<TF>* c, const mhh_fields* f, double* out, int order = 2)
 {
     const GridDev<TF>& g = c->g;
     NEED(c, f->u, "u"); NEED(c, f->v, "v"); NEED(c, f->w, "w");
     CUDA_TRY(c, cudaMemsetAsync(c->d_red, 0, sizeof(double), c->stream));
-    o2_cfl_kernel<TF><<<c->grd_interior(), c->blk(), 0, c->stream>>>(P<TF>(f->u), P<TF>(f->v), P<TF>(f->w), g, c->d_red);
-    KCHECKN(c, "o2_cfl_kernel");
+    if (order == 4) o4_cfl_kernel<TF><<<c->grd_interior(), c->blk(), 0, c->stream>>>(P<TF>(f->u), P<TF>(f->v), P<TF>(f->w), g, c->d_red);
+    else o2_cfl_kernel<TF><<<c->grd_interior(), c->blk(), 0, c->stream>>>(P<TF>(f->u), P<TF>(f->v), P<TF>(f->w), g, c->d_red);
+    const char* cfl_name = order == 4 ? "o4_cfl_kernel" : "o2_cfl_kernel";
+    KCHECKN(c, cfl_name);
     if (c->nranks > 1)
     {
         if (!c->comm) { c->err = "slab context without communicator: call mhh_comm_init first"; return MHH_E_INVALID; }
@@ -1563,8 +1614,9 @@ int mhh_boundary_ghost_cells_2nd(mhh_ctx* ctx, void* fld, int bcbot, const void*
 
 int mhh_advec_exec(mhh_ctx* ctx, int swadvec, const mhh_fields* f)
 {
-    if (ctx && swadvec != 25 && swadvec != 2) { ctx->err = "advec_exec: swadvec must be 25 (2i5) or 2"; return MHH_E_INVALID; }
+    if (ctx && swadvec != 25 && swadvec != 2 && swadvec != 4) { ctx->err = "advec_exec: swadvec must be 25 (2i5), 2 or 4"; return MHH_E_INVALID; }
     if (swadvec == 2) DISPATCH1(ctx, o2_impl<TF>(c, f, true, false, false));
+    if (swadvec == 4) DISPATCH1(ctx, o4_impl<TF>(c, f, true, false));
     DISPATCH1(ctx, tend_impl<TF>(c, f, nullptr, true, false, false));
 }
 
@@ -1572,6 +1624,12 @@ int mhh_diff_2_exec(mhh_ctx* ctx, const mhh_fields* f)
 {
     if (!f) return MHH_E_INVALID;
     DISPATCH1(ctx, o2_impl<TF>(c, f, false, true, false));
+}
+
+int mhh_diff_4_exec(mhh_ctx* ctx, const mhh_fields* f)
+{
+    if (!f) return MHH_E_INVALID;
+    DISPATCH1(ctx, o4_impl<TF>(c, f, false, true));
 }
 
 int mhh_diff_2_get_dn(mhh_ctx* ctx, const mhh_fields* f, double dt, double* dn)
@@ -1596,12 +1654,12 @@ int mhh_diff_2_get_dn(mhh_ctx* ctx, const mhh_fields* f, double dt, double* dn)
 int mhh_advec_get_cfl(mhh_ctx* ctx, int swadvec, const mhh_fields* f, double dt, double* cfl)
 {
     if (!ctx || !f || !cfl) return MHH_E_INVALID;
-    if (swadvec != 25 && swadvec != 2) { ctx->err = "advec_get_cfl: swadvec must be 25 (2i5) or 2"; return MHH_E_INVALID; }
+    if (swadvec != 25 && swadvec != 2 && swadvec != 4) { ctx->err = "advec_get_cfl: swadvec must be 25 (2i5), 2 or 4"; return MHH_E_INVALID; }
     int rc;
-    if (swadvec == 2)
+    if (swadvec == 2 || swadvec == 4)
     {
-        if (ctx->dtype == MHH_F64) { rc = o2_cfl_impl<double>(static_cast<Ctx<double>*>(ctx), f, cfl); if (rc == MHH_OK) *cfl = *cfl * dt; }
-        else { rc = o2_cfl_impl<float>(static_cast<Ctx<float>*>(ctx), f, cfl); if (rc == MHH_OK) *cfl = (double)((float)*cfl * (float)dt); }
+        if (ctx->dtype == MHH_F64) { rc = o2_cfl_impl<double>(static_cast<Ctx<double>*>(ctx), f, cfl, swadvec); if (rc == MHH_OK) *cfl = *cfl * dt; }
+        else { rc = o2_cfl_impl<float>(static_cast<Ctx<float>*>(ctx), f, cfl, swadvec); if (rc == MHH_OK) *cfl = (double)((float)*cfl * (float)dt); }
         return rc;
     }
     if (ctx->dtype == MHH_F64) { typedef double TF; rc = reduce_impl<TF, 0>(static_cast<Ctx<TF>*>(ctx), P<TF>(f->u), P<TF>(f->v), P<TF>(f->w), 0, 0, 0, cfl); if (rc == MHH_OK) *cfl = *cfl * dt; }

@@ -28,6 +28,7 @@ struct GridDev
     const TF* dzi; const TF* dzhi;
     const TF* rhoref;  const TF* rhorefh;
     const TF* thref;   const TF* threfh;
+    const TF* dzi4;    const TF* dzhi4;     // 4th-order metrics (NULL on a 2nd-order grid)
 };
 
 template <typename TF> __device__ __forceinline__ TF ld(const TF* __restrict__ p) { return __ldg(p); }

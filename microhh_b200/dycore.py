@@ -32,10 +32,12 @@ class Context:
         self.device = device
         self.torch_dtype = torch.float64 if gd.dtype == np.float64 else torch.float32
         self._keep = [np.ascontiguousarray(getattr(gd, n)) for n in ("z", "zh", "dz", "dzh", "dzi", "dzhi")]
+        self._keep4 = [np.ascontiguousarray(getattr(gd, n)) for n in ("dzi4", "dzhi4")] if getattr(gd, "order", 2) == 4 else [None, None]
         d = GridDesc(gd.itot, gd.jtot, gd.ktot, gd.imax, gd.jmax, gd.kmax, gd.igc, gd.jgc, gd.kgc,
                      float(gd.xsize), float(gd.ysize), float(gd.zsize),
                      *[a.ctypes.data_as(C.c_void_p) for a in self._keep],
-                     gd.npx, gd.npy, gd.mpicoordx, gd.mpicoordy)
+                     gd.npx, gd.npy, gd.mpicoordx, gd.mpicoordy,
+                     *[None if a is None else a.ctypes.data_as(C.c_void_p) for a in self._keep4])
         h = C.c_void_p()
         rc = self.lib.mhh_ctx_create(C.byref(d), capi.MHH_F64 if gd.dtype == np.float64 else capi.MHH_F32,
                                      device, C.byref(h))
@@ -253,6 +255,16 @@ class Diff_2:
         out = C.c_double()
         self.ctx.check(self.ctx.lib.mhh_diff_2_get_dn(self.ctx.h, C.byref(fields.c), dt, C.byref(out)))
         return out.value
+
+
+class Diff_4:
+    """Diff_4<TF> (src/diff_4.cxx): 4th-order constant-viscosity diffusion (needs a 4th-order grid)."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    def exec(self, fields):
+        self.ctx.check(self.ctx.lib.mhh_diff_4_exec(self.ctx.h, C.byref(fields.c)))
 
 
 class Thermo_dry:

@@ -170,6 +170,46 @@ def test_full_rk3_step_scheme_combinations(dtype, swadvec, swdiff):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(32, 16, 12), (24, 1, 8), (20, 12, 6)])
+@pytest.mark.parametrize("stretched", [False, True])
+def test_advec_4_and_diff_4(dtype, shape, stretched):
+    """Advec_4 (src/advec_4.cxx) and Diff_4 (src/diff_4.cxx) on a 4th-order grid, 3-D and 2-D (jtot = 1)."""
+    import torch
+    from util import stretched_z
+    from microhh_b200 import dycore as D
+    from microhh_b200.grid import GridData
+    it, jt, kt = shape
+    z = stretched_z(kt, 3200.) if stretched else None
+    g = O.Grid(it, jt, kt, 3200., 3200., 3200., 3, 3, 3, dtype, z=z, order=4)
+    gd = GridData(it, jt, kt, 3200., 3200., 3200., 3, 3, 3, dtype, z=z, order=4)
+    rng = np.random.default_rng(3)
+    fld = lambda: rng.standard_normal(gd.shape).astype(dtype)
+    case = dict(u=fld(), v=fld(), w=fld(), th=fld(), ut=fld(), vt=fld(), wt=fld(), tht=fld())
+    ctx = D.Context(gd, 0)
+    ones = np.ones(gd.kcells, dtype)
+    ctx.set_basestate(ones, ones, 300*ones, 300*ones)
+    f = D.Fields(ctx, case, visc=0.7, svisc=1.3)
+    D.Advec(ctx, "4").exec(f)
+    ref = {n: case[n].copy() for n in ("ut", "vt", "wt", "tht")}
+    O.advec_4_u(g, ref["ut"], case["u"], case["v"], case["w"]); O.advec_4_v(g, ref["vt"], case["u"], case["v"], case["w"])
+    O.advec_4_w(g, ref["wt"], case["u"], case["v"], case["w"]); O.advec_4_s(g, ref["tht"], case["th"], case["u"], case["v"], case["w"])
+    for n in ref:
+        assert rel_l2(f[n].cpu().numpy(), ref[n]) <= TOL[dtype], n
+    cfl = D.Advec(ctx, "4").get_cfl(f, 3.0)
+    assert abs(cfl - float(O.advec_4_cfl(g, case["u"], case["v"], case["w"], 3.0))) <= 10*TOL[dtype]*cfl
+    D.Diff_4(ctx).exec(f)
+    O.diff_4_c(g, ref["ut"], case["u"], 0.7); O.diff_4_c(g, ref["vt"], case["v"], 0.7)
+    O.diff_4_w(g, ref["wt"], case["w"], 0.7); O.diff_4_c(g, ref["tht"], case["th"], 1.3)
+    for n in ref:
+        assert rel_l2(f[n].cpu().numpy(), ref[n]) <= TOL[dtype], n
+    # a 2nd-order grid refuses the 4th-order schemes loudly
+    g2, gd2, case2 = make_pair(16, 12, 8, dtype)
+    D2, ctx2, f2, _ = gpu_setup(gd2, case2)
+    with pytest.raises(D.MhhError):
+        D.Advec(ctx2, "4").exec(f2)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 def test_thermo_dry_buoyancy(dtype):
     g, gd, case = make_pair(32, 16, 12, dtype)
     prepare_halos(g, case)
@@ -299,4 +339,4 @@ def test_errors_are_reported():
     rc = ctx.lib.mhh_boundary_cyclic(ctx.h, None, 2)
     assert rc == -1 and b"NULL" in ctx.lib.mhh_last_error(ctx.h)
     with pytest.raises(D.MhhError):
-        D.Advec(ctx, "4").exec(f)
+        D.Advec(ctx, "4").exec(f)          # 4th-order scheme on a 2nd-order grid
