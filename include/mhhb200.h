@@ -209,7 +209,8 @@ MHH_API int mhh_diff_4_exec(mhh_ctx* ctx, const mhh_fields* f);
 MHH_API int mhh_thermo_dry_exec(mhh_ctx* ctx, void* wt, const void* th);
 MHH_API int mhh_thermo_dry_n2(mhh_ctx* ctx, void* n2, const void* th);
 
-/* ---- Pres_2<TF>::exec / check_divergence  (src/pres_2.cxx:66-105) --------------------------- */
+/* ---- Pres<TF>::exec / check_divergence: swpres = 2 -> Pres_2 (src/pres_2.cxx:66-105);
+ *      swpres = 4 -> Pres_4 (src/pres_4.cxx:76-156; 7-band solve per mode; needs a 4th-order grid; single GPU) -- */
 MHH_API int mhh_pres_exec(mhh_ctx* ctx, int swpres, const mhh_fields* f, double sub_dt);
 MHH_API int mhh_pres_check_divergence(mhh_ctx* ctx, int swpres, const mhh_fields* f, double* divmax);
 /* Spectral pieces, exposed for tests / cuFFT comparison: forward x+y transform of a compact

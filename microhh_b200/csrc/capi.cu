@@ -20,6 +20,7 @@
 #include "slab_kernels.cuh"
 #include "order2_kernels.cuh"
 #include "order4_kernels.cuh"
+#include "pres4_kernels.cuh"
 #include <cudaTypedefs.h>
 #include <dlfcn.h>
 #include <nccl.h>
@@ -161,6 +162,9 @@ struct Ctx : mhh_ctx
     TF *spec = nullptr;            // spectral workspace, x side: nm*jmax*ktot complex
     TF *specT = nullptr;           // y side: mcl*jtot*ktot complex (== spec on a single GPU)
     TF *fac = nullptr;             // tdma factors, mcl*jtot*ktot
+    // Pres_4: band coefficients (7 x kmax), 4th-order modified wavenumbers, LU factors of every mode (7 x (kmax+4) x ncol)
+    TF *d_m7 = nullptr, *d_bmati4 = nullptr, *d_bmatj4 = nullptr, *lu4 = nullptr;
+    std::vector<TF> h_dzi4, h_dzhi4;
     SpecLayout lay{};
     PeerPtrs<TF> peers{};          // IPC-mapped workspaces of all slab ranks (peers.on: fused transposes)
     int *d_barrier = nullptr;      // dummy word for the all-reduce that closes a fused transpose
@@ -191,6 +195,7 @@ struct Ctx : mhh_ctx
         if (phalo_north && phalo_north != phalo && phalo_north != phalo_south) cudaIpcCloseMemHandle(phalo_north);
         cudaFree(phalo);
         cudaFree(d_barrier);
+        cudaFree(d_m7); cudaFree(d_bmati4); cudaFree(d_bmatj4); cudaFree(lu4);
         if (specT != spec) cudaFree(specT);
         cudaFree(spec); cudaFree(fac); cudaFree(d_red); cudaFree(halo);
         if (comm) { std::string e; NcclApi* api = nccl_api(e); if (api) api->CommDestroy(comm); }
@@ -366,6 +371,8 @@ int create_impl(const mhh_grid_desc* d, int dtype, int device, mhh_ctx** out)
         CUDA_TRY(c, cudaMemcpy(c->d_prof + 10 * kc, d->dzi4, sizeof(TF) * kc, cudaMemcpyHostToDevice));
         CUDA_TRY(c, cudaMemcpy(c->d_prof + 11 * kc, d->dzhi4, sizeof(TF) * kc, cudaMemcpyHostToDevice));
         g.dzi4 = c->d_prof + 10 * kc; g.dzhi4 = c->d_prof + 11 * kc;
+        c->h_dzi4.assign(static_cast<const TF*>(d->dzi4), static_cast<const TF*>(d->dzi4) + kc);
+        c->h_dzhi4.assign(static_cast<const TF*>(d->dzhi4), static_cast<const TF*>(d->dzhi4) + kc);
     }
 
     CUDA_TRY(c, cudaMalloc(&c->d_barrier, sizeof(int)));
@@ -1260,6 +1267,160 @@ int rk3_impl(Ctx<TF>* c, TF* a, TF* at, int substep, double dt)
     return MHH_OK;
 }
 
+// ---- Pres_4 ---------------------------------------------------------------------------------
+// Pres_4::set_values (src/pres_4.cxx:178-252) + the LU factors of every mode; done at the first call
+template <typename TF>
+int pres4_prepare(Ctx<TF>* c)
+{
+    if (c->lu4) return MHH_OK;
+    const GridDev<TF>& g = c->g;
+    if (!g.dzi4) { c->err = "Pres_4 needs a 4th-order grid (dzi4 / dzhi4 in mhh_grid_desc, three ghost cells)"; return MHH_E_INVALID; }
+    if (c->nranks > 1) { c->err = "Pres_4 is single-GPU in this version"; return MHH_E_INVALID; }
+    if (g.kmax < 4) { c->err = "Pres_4 needs ktot >= 4"; return MHH_E_INVALID; }
+    const int kmax = g.kmax, ks = g.kstart;
+    const TF dxidxi = (TF)(1. / (double)(g.dx * g.dx)), dyidyi = (TF)(1. / (double)(g.dy * g.dy));
+    const double pi = (double)(TF)std::acos(-1.);
+    auto wave = [&](int q, int n, TF fac) {
+        return (TF)((2. * (1. / 576.) * std::cos(6. * pi * (double)q / (double)n) - 2. * (54. / 576.) * std::cos(4. * pi * (double)q / (double)n)
+                   + 2. * (783. / 576.) * std::cos(2. * pi * (double)q / (double)n) - (1460. / 576.)) * (double)fac); };
+    std::vector<TF> bi(c->nm), bj(g.jtot), m((size_t)7 * kmax);
+    for (int i = 0; i < c->nm; ++i) bi[i] = wave(i, g.itot, dxidxi);
+    for (int j = 0; j < g.jtot / 2 + 1; ++j) bj[j] = wave(j, g.jtot, dyidyi);
+    for (int j = g.jtot / 2 + 1; j < g.jtot; ++j) bj[j] = bj[g.jtot - j];
+    const std::vector<TF>& H = c->h_dzhi4; const std::vector<TF>& Z = c->h_dzi4;
+    auto h = [&](int k) { return (double)H[k]; };
+    const double f = 1. / 576.;
+    auto M = [&](int n, int k) -> TF& { return m[(size_t)n * kmax + k]; };
+    for (int k = 0; k < kmax; ++k)
+    {
+        const int kc = ks + k;
+        const double z = (double)Z[kc];
+        if (k == 0)
+        {
+            M(0, k) = 0.;
+            M(1, k) = (TF)(f * (-27. * h(kc)) * z);
+            M(2, k) = (TF)(f * (-1. * h(kc + 1) + 729. * h(kc) + 27. * h(kc + 1)) * z);
+            M(3, k) = (TF)(f * (27. * h(kc + 1) - 729. * h(kc) - 729. * h(kc + 1) - 1. * h(kc + 2)) * z);
+            M(4, k) = (TF)(f * (-27. * h(kc + 1) + 27. * h(kc) + 729. * h(kc + 1) + 27. * h(kc + 2)) * z);
+            M(5, k) = (TF)(f * (1. * h(kc + 1) - 27. * h(kc + 1) - 27. * h(kc + 2)) * z);
+            M(6, k) = (TF)(f * (1. * h(kc + 2)) * z);
+        }
+        else if (k < kmax - 1)
+        {
+            M(0, k) = (TF)(f * (1. * h(kc - 1)) * z);
+            M(1, k) = (TF)(f * (-27. * h(kc - 1) - 27. * h(kc)) * z);
+            M(2, k) = (TF)(f * (27. * h(kc - 1) + 729. * h(kc) + 27. * h(kc + 1)) * z);
+            M(3, k) = (TF)(f * (-1. * h(kc - 1) - 729. * h(kc) - 729. * h(kc + 1) - 1. * h(kc + 2)) * z);
+            M(4, k) = (TF)(f * (27. * h(kc) + 729. * h(kc + 1) + 27. * h(kc + 2)) * z);
+            M(5, k) = (TF)(f * (-27. * h(kc + 1) - 27. * h(kc + 2)) * z);
+            M(6, k) = (TF)(f * (1. * h(kc + 2)) * z);
+        }
+        else
+        {
+            M(0, k) = (TF)(f * (1. * h(kc - 1)) * z);
+            M(1, k) = (TF)(f * (-27. * h(kc - 1) - 27. * h(kc) + 1. * h(kc)) * z);
+            M(2, k) = (TF)(f * (27. * h(kc - 1) + 729. * h(kc) + 27. * h(kc + 1) - 27. * h(kc)) * z);
+            M(3, k) = (TF)(f * (-1. * h(kc - 1) - 729. * h(kc) - 729. * h(kc + 1) + 27. * h(kc)) * z);
+            M(4, k) = (TF)(f * (27. * h(kc) + 729. * h(kc + 1) - 1. * h(kc)) * z);
+            M(5, k) = (TF)(f * (-27. * h(kc + 1)) * z);
+            M(6, k) = 0.;
+        }
+    }
+    const long long ncol = (long long)c->nm * g.jtot;
+    CUDA_TRY(c, cudaMalloc(&c->d_m7, sizeof(TF) * m.size()));
+    CUDA_TRY(c, cudaMalloc(&c->d_bmati4, sizeof(TF) * bi.size()));
+    CUDA_TRY(c, cudaMalloc(&c->d_bmatj4, sizeof(TF) * bj.size()));
+    CUDA_TRY(c, cudaMemcpy(c->d_m7, m.data(), sizeof(TF) * m.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(c->d_bmati4, bi.data(), sizeof(TF) * bi.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(c->d_bmatj4, bj.data(), sizeof(TF) * bj.size(), cudaMemcpyHostToDevice));
+    const size_t nlu = (size_t)7 * (kmax + 4) * ncol;
+    CUDA_TRY(c, cudaMalloc(&c->lu4, sizeof(TF) * nlu));
+    c->ws_bytes += (long long)(sizeof(TF) * nlu);
+    HdmaCoef<TF> cf{c->d_m7, c->d_bmati4, c->d_bmatj4};
+    hdma_setup_kernel<TF><<<(unsigned)((ncol + 127) / 128), 128, 0, c->stream>>>(c->lu4, cf, c->nm, g.jtot, kmax);
+    KCHECKN(c, "hdma_setup_kernel");
+    return MHH_OK;
+}
+
+// Pres_4::exec (src/pres_4.cxx:76-144): input -> transforms + 7-band solve -> ghost cells -> output
+template <typename TF>
+int pres4_exec_impl(Ctx<TF>* c, const mhh_fields* f, double sub_dt)
+{
+    int rc = check_mom<TF>(c, f, false, false);
+    if (rc != MHH_OK) return rc;
+    NEED(c, f->p, "p");
+    if ((rc = pres4_prepare<TF>(c)) != MHH_OK) return rc;
+    const GridDev<TF>& g = c->g;
+    const bool dim3 = g.jtot > 1;
+    // cyclic ghosts of the tendencies and the mirrored wt over the walls are side effects of Pres_4::input
+    if ((rc = cyclic_impl<TF>(c, P<TF>(f->ut), MHH_EDGE_EAST_WEST, false)) != MHH_OK) return rc;
+    if (dim3 && (rc = cyclic_impl<TF>(c, P<TF>(f->vt), MHH_EDGE_NORTH_SOUTH, false)) != MHH_OK) return rc;
+    {
+        ::dim3 b2(64, 4), g2((g.imax + 63) / 64, (g.jmax + 3) / 4);
+        pres4_wtbc_kernel<TF><<<g2, b2, 0, c->stream>>>(P<TF>(f->wt), g);
+        KCHECKN(c, "pres4_wtbc_kernel");
+    }
+    const TF dti = (TF)(1. / sub_dt);
+    const long long pitch = 2 * c->nm;
+    if (dim3) pres4_in_kernel<TF, true><<<c->grd_interior(), c->blk(), 0, c->stream>>>(P<TF>(f->u), P<TF>(f->v), P<TF>(f->w), P<TF>(f->ut), P<TF>(f->vt), P<TF>(f->wt), c->spec, pitch, dti, g);
+    else pres4_in_kernel<TF, false><<<c->grd_interior(), c->blk(), 0, c->stream>>>(P<TF>(f->u), P<TF>(f->v), P<TF>(f->w), P<TF>(f->ut), P<TF>(f->vt), P<TF>(f->wt), c->spec, pitch, dti, g);
+    KCHECKN(c, "pres4_in_kernel");
+    const long long nrows = (long long)g.jmax * g.ktot;
+    const int grid_x = (int)std::min<long long>((nrows + c->rows_x - 1) / c->rows_x, (long long)c->num_sms * 4);
+    const int grid_wx = (int)std::min<long long>((nrows + WFFT_WARPS - 1) / WFFT_WARPS, (long long)c->num_sms * 8);
+    RhsSrc<TF> none{};
+    if (c->wfft_x) wfft_x_forward_launch<TF>(g.itot / 2, false, grid_wx, c->stream, c->spec, none, g, c->lay, c->peers, c->tw_xh, c->tw_xf, nrows);
+    else fft_x_forward_kernel<TF, false><<<grid_x, 256, c->smem_x, c->stream>>>(c->spec, none, g, c->lay, c->peers, c->plan_x, c->tw_xh, c->tw_xf, c->rows_x, nrows);
+    KCHECKN(c, "fft_x_forward_kernel");
+    const int grid_p = c->num_sms * 2;
+    const long long ypanels = (long long)((c->nm + WFFT_WARPS - 1) / WFFT_WARPS) * g.ktot;
+    const int grid_wy = (int)std::max<long long>(1, std::min<long long>(ypanels, (long long)c->num_sms * 8));
+    if (dim3)
+    {
+        if (c->wfft_y) wfft_y_launch<TF>(g.jtot, grid_wy, c->stream, c->spec, c->lay, c->peers, c->nm, g.ktot, c->tw_y, 0);
+        else fft_y_kernel<TF><<<grid_p, 256, c->smem_y, c->stream>>>(c->spec, c->lay, c->peers, c->nm, g.jtot, g.ktot, c->plan_y, c->tw_y, c->mc_y, 0);
+        KCHECKN(c, "fft_y_forward_kernel");
+    }
+    const long long ncol = (long long)c->nm * g.jtot;
+    hdma_solve_kernel<TF><<<(unsigned)((ncol + 127) / 128), 128, 0, c->stream>>>(c->spec, c->lu4, c->nm, g.jtot, g.kmax);
+    KCHECKN(c, "hdma_solve_kernel");
+    if (dim3)
+    {
+        if (c->wfft_y) wfft_y_launch<TF>(g.jtot, grid_wy, c->stream, c->spec, c->lay, c->peers, c->nm, g.ktot, c->tw_y, 1);
+        else fft_y_kernel<TF><<<grid_p, 256, c->smem_y, c->stream>>>(c->spec, c->lay, c->peers, c->nm, g.jtot, g.ktot, c->plan_y, c->tw_y, c->mc_y, 1);
+        KCHECKN(c, "fft_y_backward_kernel");
+    }
+    const TF norm = TF(1.) / ((TF)g.itot * (TF)g.jtot);
+    if (c->wfft_x) wfft_x_backward_launch<TF>(g.itot / 2, grid_wx, c->stream, c->spec, P<TF>(f->p), g, c->lay, c->tw_xh, c->tw_xf, nrows, norm, 1);
+    else fft_x_backward_kernel<TF><<<grid_x, 256, c->smem_x, c->stream>>>(c->spec, P<TF>(f->p), g, c->lay, c->plan_x, c->tw_xh, c->tw_xf, c->rows_x, nrows, norm, 1);
+    KCHECKN(c, "fft_x_backward_kernel");
+    if (!dim3 && (rc = cyclic_impl<TF>(c, P<TF>(f->p), MHH_EDGE_NORTH_SOUTH, false)) != MHH_OK) return rc;
+    {
+        ::dim3 b2(64, 4), g2((g.icells + 63) / 64, (g.jcells + 3) / 4);
+        pres4_ghost_kernel<TF><<<g2, b2, 0, c->stream>>>(P<TF>(f->p), g);
+        KCHECKN(c, "pres4_ghost_kernel");
+    }
+    if (dim3) pres4_out_kernel<TF, true><<<c->grd_interior(), c->blk(), 0, c->stream>>>(P<TF>(f->ut), P<TF>(f->vt), P<TF>(f->wt), P<TF>(f->p), g);
+    else pres4_out_kernel<TF, false><<<c->grd_interior(), c->blk(), 0, c->stream>>>(P<TF>(f->ut), P<TF>(f->vt), P<TF>(f->wt), P<TF>(f->p), g);
+    KCHECKN(c, "pres4_out_kernel");
+    return MHH_OK;
+}
+
+template <typename TF>
+int pres4_div_impl(Ctx<TF>* c, const mhh_fields* f, double* out)
+{
+    const GridDev<TF>& g = c->g;
+    if (!g.dzi4) { c->err = "Pres_4 needs a 4th-order grid"; return MHH_E_INVALID; }
+    NEED(c, f->u, "u"); NEED(c, f->v, "v"); NEED(c, f->w, "w");
+    CUDA_TRY(c, cudaMemsetAsync(c->d_red, 0, sizeof(double), c->stream));
+    pres4_div_kernel<TF><<<c->grd_interior(), c->blk(), 0, c->stream>>>(P<TF>(f->u), P<TF>(f->v), P<TF>(f->w), g, c->d_red);
+    KCHECKN(c, "pres4_div_kernel");
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_red, c->d_red, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    *out = *c->h_red;
+    return MHH_OK;
+}
+
 // One fused sub-step (Model::exec order, src/model.cxx:356-504, restricted to the hot path).
 template <typename TF>
 int substep_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, int substep, double dt)
@@ -1721,14 +1882,20 @@ int mhh_thermo_dry_n2(mhh_ctx* ctx, void* n2, const void* th)
 int mhh_pres_exec(mhh_ctx* ctx, int swpres, const mhh_fields* f, double sub_dt)
 {
     if (!f) return MHH_E_INVALID;
-    if (ctx && swpres != 2) { ctx->err = "pres_exec: only swpres = 2 is available"; return MHH_E_INVALID; }
+    if (ctx && swpres != 2 && swpres != 4) { ctx->err = "pres_exec: swpres must be 2 or 4"; return MHH_E_INVALID; }
+    if (swpres == 4) DISPATCH1(ctx, pres4_exec_impl<TF>(c, f, sub_dt));
     DISPATCH1(ctx, pres_exec_impl<TF>(c, f, sub_dt));
 }
 
 int mhh_pres_check_divergence(mhh_ctx* ctx, int swpres, const mhh_fields* f, double* divmax)
 {
     if (!ctx || !f || !divmax) return MHH_E_INVALID;
-    if (swpres != 2) { ctx->err = "pres_check_divergence: only swpres = 2 is available"; return MHH_E_INVALID; }
+    if (swpres != 2 && swpres != 4) { ctx->err = "pres_check_divergence: swpres must be 2 or 4"; return MHH_E_INVALID; }
+    if (swpres == 4)
+    {
+        if (ctx->dtype == MHH_F64) return pres4_div_impl<double>(static_cast<Ctx<double>*>(ctx), f, divmax);
+        return pres4_div_impl<float>(static_cast<Ctx<float>*>(ctx), f, divmax);
+    }
     if (ctx->dtype == MHH_F64) { typedef double TF; Ctx<TF>* c = static_cast<Ctx<TF>*>(ctx); NEED_BASE(c); return reduce_impl<TF, 2>(c, P<TF>(f->u), P<TF>(f->v), P<TF>(f->w), 0, 0, 0, divmax); }
     else { typedef float TF; Ctx<TF>* c = static_cast<Ctx<TF>*>(ctx); NEED_BASE(c); return reduce_impl<TF, 2>(c, P<TF>(f->u), P<TF>(f->v), P<TF>(f->w), 0, 0, 0, divmax); }
 }

@@ -1157,6 +1157,195 @@ class Pres2:
 
 
 # --------------------------------------------------------------------------------------
+# Pres_4 (reference src/pres_4.cxx:178-767): 4th-order divergence / gradient (cg weights), 4-term cosine modified
+# wavenumbers, a 7-band system of kmax+4 rows per horizontal mode (two boundary rows at either end) solved by
+# banded LU without pivoting (`hdma`).  Member functions of the reference class (need live Grid/Fields objects), so
+# restated here; PARITY UNPINNED against reference output -- pinned by the defining property instead: after
+# `output` the 4th-order divergence of u + dt*ut vanishes to rounding (tests/test_pres4_oracle.py).
+# --------------------------------------------------------------------------------------
+class Pres4:
+    def __init__(self, g):
+        """set_values: src/pres_4.cxx:178-252"""
+        assert g.order == 4
+        TF = g.TF; D = np.float64
+        self.g = g
+        dxidxi = TF(1./D(g.dx*g.dx)); dyidyi = TF(1./D(g.dy*g.dy))
+        pi = D(TF(np.arccos(-1.)))          # `const TF pi = std::acos(-1.)`, then used in double expressions
+        def bmat(n, fac):
+            b = np.zeros(n, TF)
+            for q in range(n//2 + 1):
+                b[q] = TF(( 2.*(1./576.)*np.cos(6.*pi*D(q)/D(n)) - 2.*(54./576.)*np.cos(4.*pi*D(q)/D(n))
+                          + 2.*(783./576.)*np.cos(2.*pi*D(q)/D(n)) - (1460./576.) ) * D(fac))
+            for q in range(n//2 + 1, n):
+                b[q] = b[n-q]
+            return b
+        self.bmati = bmat(g.itot, dxidxi); self.bmatj = bmat(g.jtot, dyidyi)
+        kmax, ks = g.kmax, g.kstart
+        h = g.dzhi4.astype(D); c = g.dzi4.astype(D)
+        m = np.zeros((7, kmax), D)
+        f = 1./576.
+        k, kc = 0, ks
+        m[0, k] = 0.
+        m[1, k] = f*(-27.*h[kc])*c[kc]
+        m[2, k] = f*(-1.*h[kc+1] + 729.*h[kc] + 27.*h[kc+1])*c[kc]
+        m[3, k] = f*(27.*h[kc+1] - 729.*h[kc] - 729.*h[kc+1] - 1.*h[kc+2])*c[kc]
+        m[4, k] = f*(-27.*h[kc+1] + 27.*h[kc] + 729.*h[kc+1] + 27.*h[kc+2])*c[kc]
+        m[5, k] = f*(1.*h[kc+1] - 27.*h[kc+1] - 27.*h[kc+2])*c[kc]
+        m[6, k] = f*(1.*h[kc+2])*c[kc]
+        for k in range(1, kmax-1):
+            kc = ks + k
+            m[0, k] = f*(1.*h[kc-1])*c[kc]
+            m[1, k] = f*(-27.*h[kc-1] - 27.*h[kc])*c[kc]
+            m[2, k] = f*(27.*h[kc-1] + 729.*h[kc] + 27.*h[kc+1])*c[kc]
+            m[3, k] = f*(-1.*h[kc-1] - 729.*h[kc] - 729.*h[kc+1] - 1.*h[kc+2])*c[kc]
+            m[4, k] = f*(27.*h[kc] + 729.*h[kc+1] + 27.*h[kc+2])*c[kc]
+            m[5, k] = f*(-27.*h[kc+1] - 27.*h[kc+2])*c[kc]
+            m[6, k] = f*(1.*h[kc+2])*c[kc]
+        k = kmax-1; kc = ks + k
+        m[0, k] = f*(1.*h[kc-1])*c[kc]
+        m[1, k] = f*(-27.*h[kc-1] - 27.*h[kc] + 1.*h[kc])*c[kc]
+        m[2, k] = f*(27.*h[kc-1] + 729.*h[kc] + 27.*h[kc+1] - 27.*h[kc])*c[kc]
+        m[3, k] = f*(-1.*h[kc-1] - 729.*h[kc] - 729.*h[kc+1] + 27.*h[kc])*c[kc]
+        m[4, k] = f*(27.*h[kc] + 729.*h[kc+1] - 1.*h[kc])*c[kc]
+        m[5, k] = f*(-27.*h[kc+1])*c[kc]
+        m[6, k] = 0.
+        self.m = m.astype(TF)          # m1..m7 are std::vector<TF>: narrowed on assignment
+
+    def input(self, u, v, w, ut, vt, wt, dt):
+        """src/pres_4.cxx:254-317 (fills the ut/vt cyclic ghosts and the wt wall ghosts as a side effect)"""
+        g = self.g; TF = g.TF
+        dxi, dyi = TF(1./np.float64(g.dx)), TF(1./np.float64(g.dy))
+        dti = TF(1./dt)
+        dim3 = g.jtot > 1
+        boundary_cyclic(g, ut, EDGE_EW)
+        if dim3:
+            boundary_cyclic(g, vt, EDGE_NS)
+        js, je, i0, i1, ks, ke = g.jstart, g.jend, g.istart, g.iend, g.kstart, g.kend
+        wt[ks-1, js:je, i0:i1] = -wt[ks+1, js:je, i0:i1]
+        wt[ke+1, js:je, i0:i1] = -wt[ke-1, js:je, i0:i1]
+        cg = [TF(x) for x in CG]
+        T = lambda a, at, dk=0, dj=0, di=0: _S(g, at, dk, dj, di) + _S(g, a, dk, dj, di)*dti
+        p = (cg[0]*T(u, ut, 0, 0, -1) + cg[1]*T(u, ut) + cg[2]*T(u, ut, 0, 0, 1) + cg[3]*T(u, ut, 0, 0, 2)) * dxi
+        if dim3:
+            p = p + (cg[0]*T(v, vt, 0, -1) + cg[1]*T(v, vt) + cg[2]*T(v, vt, 0, 1) + cg[3]*T(v, vt, 0, 2)) * dyi
+        p = p + (cg[0]*T(w, wt, -1) + cg[1]*T(w, wt) + cg[2]*T(w, wt, 1) + cg[3]*T(w, wt, 2)) * _K(g, g.dzi4)
+        return np.ascontiguousarray(p.astype(TF))
+
+    def hdma(self, m1, m2, m3, m4, m5, m6, m7, p):
+        """src/pres_4.cxx:573-730: banded LU + forward/backward substitution; arrays are (kmax+4, ...) and modified in place"""
+        TF = self.g.TF; one = TF(1.)
+        kmax = self.g.kmax
+        m1[0] = one; m2[0] = one; m3[0] = one/m4[0]; m4[0] = one
+        m5[0] = m5[0]*m3[0]; m6[0] = m6[0]*m3[0]; m7[0] = m7[0]*m3[0]
+        k = 1
+        m1[k] = one; m2[k] = one
+        m3[k] = m3[k]/m4[k-1]
+        m4[k] = m4[k] - m3[k]*m5[k-1]
+        m5[k] = m5[k] - m3[k]*m6[k-1]
+        m6[k] = m6[k] - m3[k]*m7[k-1]
+        k = 2
+        m1[k] = one
+        m2[k] = m2[k]/m4[k-2]
+        m3[k] = (m3[k] - m2[k]*m5[k-2])/m4[k-1]
+        m4[k] = m4[k] - m3[k]*m5[k-1] - m2[k]*m6[k-2]
+        m5[k] = m5[k] - m3[k]*m6[k-1] - m2[k]*m7[k-2]
+        m6[k] = m6[k] - m3[k]*m7[k-1]
+        def lower(k):
+            m1[k] = m1[k]/m4[k-3]
+            m2[k] = (m2[k] - m1[k]*m5[k-3])/m4[k-2]
+            m3[k] = (m3[k] - m2[k]*m5[k-2] - m1[k]*m6[k-3])/m4[k-1]
+            m4[k] = m4[k] - m3[k]*m5[k-1] - m2[k]*m6[k-2] - m1[k]*m7[k-3]
+        for k in range(3, kmax+2):
+            lower(k)
+            m5[k] = m5[k] - m3[k]*m6[k-1] - m2[k]*m7[k-2]
+            m6[k] = m6[k] - m3[k]*m7[k-1]
+        m7[kmax+1] = one
+        k = kmax+2
+        lower(k)
+        m5[k] = m5[k] - m3[k]*m6[k-1] - m2[k]*m7[k-2]
+        m6[k] = one; m7[k] = one
+        k = kmax+3
+        lower(k)
+        m5[k] = one; m6[k] = one; m7[k] = one
+        # L y = p
+        p[0] = p[0]*m3[0]
+        p[1] = p[1] - p[0]*m3[1]
+        p[2] = p[2] - p[1]*m3[2] - p[0]*m2[2]
+        for k in range(3, kmax+4):
+            p[k] = p[k] - p[k-1]*m3[k] - p[k-2]*m2[k] - p[k-3]*m1[k]
+        # U x = y
+        k = kmax+3
+        p[k] = p[k]/m4[k]
+        p[k-1] = (p[k-1] - p[k]*m5[k-1])/m4[k-1]
+        p[k-2] = (p[k-2] - p[k-1]*m5[k-2] - p[k]*m6[k-2])/m4[k-2]
+        for k in range(kmax, -1, -1):
+            p[k] = (p[k] - p[k+1]*m5[k] - p[k+2]*m6[k] - p[k+3]*m7[k])/m4[k]
+
+    def solve(self, pc, p):
+        """src/pres_4.cxx:319-529.  pc: compact rhs (kmax, jmax, imax); p: ghosted output."""
+        g = self.g; TF = g.TF
+        kmax = g.kmax
+        pc = r2hc(pc, axis=2)
+        if g.jtot > 1:
+            pc = r2hc(pc, axis=1)
+        shp = (kmax+4, g.jtot, g.itot)
+        M = [np.zeros(shp, TF) for _ in range(7)]
+        pt = np.zeros(shp, TF)
+        # rows 0, 1: zero gradient at the bottom
+        M[3][0] = 1.; M[6][0] = -1.
+        M[3][1] = 1.; M[4][1] = -1.
+        for n in range(7):
+            M[n][2:kmax+2] = self.m[n][:, None, None]
+        M[3][2:kmax+2] = M[3][2:kmax+2] + self.bmati[None, None, :] + self.bmatj[None, :, None]
+        pt[2:kmax+2] = pc
+        # top rows: dp/dz = 0, except mode (0,0) which fixes the level of p
+        M[2][kmax+2] = -1.; M[3][kmax+2] = 1.
+        M[0][kmax+3] = -1.; M[3][kmax+3] = 1.
+        M[0][kmax+2, 0, 0] = 0.; M[1][kmax+2, 0, 0] = TF(-1/3.); M[2][kmax+2, 0, 0] = 2.; M[3][kmax+2, 0, 0] = 1.
+        M[0][kmax+3, 0, 0] = -2.; M[1][kmax+3, 0, 0] = 9.; M[2][kmax+3, 0, 0] = 0.; M[3][kmax+3, 0, 0] = 1.
+        self.hdma(*M, pt)
+        pc = np.ascontiguousarray(pt[2:kmax+2])
+        if g.jtot > 1:
+            pc = hc2r(pc, axis=1) / TF(g.jtot)
+        pc = hc2r(pc, axis=2) / TF(g.itot)
+        _S(g, p)[...] = pc
+        ks, ke = g.kstart, g.kend
+        I = (slice(g.jstart, g.jend), slice(g.istart, g.iend))
+        p[ks-1][I] = p[ks][I]; p[ks-2][I] = p[ks+1][I]
+        p[ke][I] = p[ke-1][I]; p[ke+1][I] = p[ke-2][I]
+        boundary_cyclic(g, p)
+
+    def output(self, ut, vt, wt, p):
+        """src/pres_4.cxx:531-571"""
+        g = self.g; TF = g.TF
+        dxi, dyi = TF(1./np.float64(g.dx)), TF(1./np.float64(g.dy))
+        cg = [TF(x) for x in CG]
+        P = lambda dk=0, dj=0, di=0, k0=None, k1=None: _S(g, p, dk, dj, di, k0, k1)
+        _S(g, ut)[...] -= (cg[0]*P(0, 0, -2) + cg[1]*P(0, 0, -1) + cg[2]*P() + cg[3]*P(0, 0, 1)) * dxi
+        if g.jtot > 1:
+            _S(g, vt)[...] -= (cg[0]*P(0, -2) + cg[1]*P(0, -1) + cg[2]*P() + cg[3]*P(0, 1)) * dyi
+        k0, k1 = g.kstart+1, g.kend
+        _S(g, wt, 0, 0, 0, k0, k1)[...] -= (cg[0]*P(-2, 0, 0, k0, k1) + cg[1]*P(-1, 0, 0, k0, k1) + cg[2]*P(0, 0, 0, k0, k1)
+                                            + cg[3]*P(1, 0, 0, k0, k1)) * _K(g, g.dzhi4, 0, k0, k1)
+
+    def exec(self, p, u, v, w, ut, vt, wt, dt):
+        """src/pres_4.cxx:76-144"""
+        pc = self.input(u, v, w, ut, vt, wt, dt)
+        self.solve(pc, p)
+        self.output(ut, vt, wt, p)
+
+    def divergence(self, u, v, w):
+        """src/pres_4.cxx:732-767"""
+        g = self.g; TF = g.TF
+        dxi, dyi = TF(1./np.float64(g.dx)), TF(1./np.float64(g.dy))
+        cg = [TF(x) for x in CG]
+        div = ( (cg[0]*_S(g, u, 0, 0, -1) + cg[1]*_S(g, u) + cg[2]*_S(g, u, 0, 0, 1) + cg[3]*_S(g, u, 0, 0, 2)) * dxi
+              + (cg[0]*_S(g, v, 0, -1) + cg[1]*_S(g, v) + cg[2]*_S(g, v, 0, 1) + cg[3]*_S(g, v, 0, 2)) * dyi
+              + (cg[0]*_S(g, w, -1) + cg[1]*_S(g, w) + cg[2]*_S(g, w, 1) + cg[3]*_S(g, w, 2)) * _K(g, g.dzi4) )
+        return TF(np.abs(div).max())
+
+
+# --------------------------------------------------------------------------------------
 # Timeloop rk3 (reference src/timeloop.cxx:250-286, 415-423)
 # --------------------------------------------------------------------------------------
 RK3_CA = (0., -5./9., -153./128.)

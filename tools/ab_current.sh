@@ -1,3 +1,2 @@
-source tools/gpu_ab.sh
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
-tail -15 gpurun_out/pytest_gpu.log
+tail -30 gpurun_out/pytest_gpu.log
