@@ -105,8 +105,8 @@ typedef struct mhh_fields
 /* Run-time switches of the path ([advec] [diff] [boundary] [thermo] of the .ini). */
 typedef struct mhh_params
 {
-    int    swadvec;              /* 25 = 2i5, 2 = 2 */
-    int    swdiff;               /* 1 = smag2, 2 = 2 */
+    int    swadvec;              /* 25 = 2i5, 2 = 2, 4 = 4 */
+    int    swdiff;               /* 1 = smag2, 2 = 2, 4 = 4 (the 4th-order configuration: 4 + 4 + pres_4 on a 4th-order grid) */
     int    swthermo;             /* 0 = off, 1 = dry (buoyancy from scalar 0 = th) */
     int    surface_model;        /* Boundary switch != "default"  (Surface_model::Enabled) */
     int    sw_mason;             /* [diff] swmason */
@@ -185,6 +185,12 @@ MHH_API int mhh_boundary_cyclic_2d(mhh_ctx* ctx, void* fld2d);
 /* ---- Boundary<TF>::set_ghost_cells, 2nd order, one field (src/boundary.cxx:700-772, 933-961) */
 MHH_API int mhh_boundary_ghost_cells_2nd(mhh_ctx* ctx, void* fld, int bcbot, const void* bot, const void* gradbot,
                                  int bctop, const void* top, const void* gradtop);
+
+/* ---- 4th-order grids: Boundary<TF>::set_ghost_cells, one field (src/boundary.cxx:776-848, 963-991), and
+ *      Boundary<TF>::set_ghost_cells_w (src/boundary.cxx:850-922, 999-1021; conservation != 0: Conservation_type) ---- */
+MHH_API int mhh_boundary_ghost_cells_4th(mhh_ctx* ctx, void* fld, int bcbot, const void* bot, const void* gradbot,
+                                 int bctop, const void* top, const void* gradtop);
+MHH_API int mhh_boundary_ghost_cells_w_4th(mhh_ctx* ctx, void* w, int conservation);
 
 /* ---- Advec<TF>::exec / get_cfl  (swadvec = 25: Advec_2i5, src/advec_2i5.cxx:955-1063;
  *      swadvec = 2: Advec_2, src/advec_2.cxx:288-345; swadvec = 4: Advec_4, src/advec_4.cxx:573-684) */

@@ -78,6 +78,8 @@ SIGNATURES = {
     "mhh_boundary_cyclic": (C.c_int, [_vp, _vp, C.c_int]),
     "mhh_boundary_cyclic_2d": (C.c_int, [_vp, _vp]),
     "mhh_boundary_ghost_cells_2nd": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp]),
+    "mhh_boundary_ghost_cells_4th": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp]),
+    "mhh_boundary_ghost_cells_w_4th": (C.c_int, [_vp, _vp, C.c_int]),
     "mhh_advec_exec": (C.c_int, [_vp, C.c_int, _PF]),
     "mhh_advec_get_cfl": (C.c_int, [_vp, C.c_int, _PF, C.c_double, C.POINTER(C.c_double)]),
     "mhh_diff_smag2_exec_viscosity": (C.c_int, [_vp, _PF, _PP, _vp]),

@@ -164,7 +164,7 @@ struct Ctx : mhh_ctx
     TF *fac = nullptr;             // tdma factors, mcl*jtot*ktot
     // Pres_4: band coefficients (7 x kmax), 4th-order modified wavenumbers, LU factors of every mode (7 x (kmax+4) x ncol)
     TF *d_m7 = nullptr, *d_bmati4 = nullptr, *d_bmatj4 = nullptr, *lu4 = nullptr;
-    std::vector<TF> h_dzi4, h_dzhi4;
+    std::vector<TF> h_dzi4, h_dzhi4, h_z;
     SpecLayout lay{};
     PeerPtrs<TF> peers{};          // IPC-mapped workspaces of all slab ranks (peers.on: fused transposes)
     int *d_barrier = nullptr;      // dummy word for the all-reduce that closes a fused transpose
@@ -359,6 +359,7 @@ int create_impl(const mhh_grid_desc* d, int dtype, int device, mhh_ctx** out)
         CUDA_TRY(c, cudaMemcpy(c->d_prof + n * kc, src[n], sizeof(TF) * kc, cudaMemcpyHostToDevice));
     }
     c->h_dz.assign(static_cast<const TF*>(d->dz), static_cast<const TF*>(d->dz) + kc);
+    c->h_z.assign(static_cast<const TF*>(d->z), static_cast<const TF*>(d->z) + kc);
     g.z = c->d_prof; g.zh = c->d_prof + kc; g.dz = c->d_prof + 2 * kc; g.dzh = c->d_prof + 3 * kc;
     g.dzi = c->d_prof + 4 * kc; g.dzhi = c->d_prof + 5 * kc;
     g.rhoref = c->d_prof + 6 * kc; g.rhorefh = c->d_prof + 7 * kc;
@@ -1421,6 +1422,77 @@ int pres4_div_impl(Ctx<TF>* c, const mhh_fields* f, double* out)
     return MHH_OK;
 }
 
+// Boundary::set_ghost_cells, 4th order, one field (src/boundary.cxx:776-848, 963-991)
+template <typename TF>
+int ghost4_impl(Ctx<TF>* c, TF* fld, int bcbot, const TF* bot, const TF* gradbot, int bctop, const TF* top, const TF* gradtop)
+{
+    const GridDev<TF>& g = c->g;
+    NEED(c, fld, "field");
+    if (!g.dzi4) { c->err = "4th-order ghost cells need a 4th-order grid"; return MHH_E_INVALID; }
+    if (bcbot == MHH_BC_DIRICHLET) NEED(c, bot, "bot");
+    if (bcbot == MHH_BC_NEUMANN) NEED(c, gradbot, "gradbot");
+    if (bctop == MHH_BC_DIRICHLET) NEED(c, top, "top");
+    if (bctop == MHH_BC_NEUMANN) NEED(c, gradtop, "gradtop");
+    // grad4(a,b,c,d) = -cg0*(d-a) - cg1*(c-b) (include/finite_difference.h:127-131) of the z levels around the walls
+    const std::vector<TF>& z = c->h_z;
+    auto grad4 = [](TF a, TF b, TF cc, TF d) { return -W4<TF>::cg0 * (d - a) - W4<TF>::cg1 * (cc - b); };
+    const TF gb = grad4(z[g.kstart - 2], z[g.kstart - 1], z[g.kstart], z[g.kstart + 1]);
+    const TF gt = grad4(z[g.kend - 2], z[g.kend - 1], z[g.kend], z[g.kend + 1]);
+    dim3 b(64, 4), gr((g.icells + 63) / 64, (g.jcells + 3) / 4);
+    ghost_cells_4th_kernel<TF><<<gr, b, 0, c->stream>>>(fld, g, bcbot, bot, gradbot, bctop, top, gradtop, gb, gt);
+    KCHECKN(c, "ghost_cells_4th_kernel");
+    return MHH_OK;
+}
+
+template <typename TF>
+int ghost4w_impl(Ctx<TF>* c, TF* w, int conservation)
+{
+    const GridDev<TF>& g = c->g;
+    NEED(c, w, "w");
+    if (!g.dzi4) { c->err = "4th-order ghost cells need a 4th-order grid"; return MHH_E_INVALID; }
+    dim3 b(64, 4), gr((g.icells + 63) / 64, (g.jcells + 3) / 4);
+    ghost_cells_w_4th_kernel<TF><<<gr, b, 0, c->stream>>>(w, g, conservation);
+    KCHECKN(c, "ghost_cells_w_4th_kernel");
+    return MHH_OK;
+}
+
+// The 4th-order DNS sub-step (swspatialorder = 4: advec_4 + diff_4 + pres_4, no thermo), Model::exec order
+// (src/model.cxx:368-437, 504): cyclic -> ghost cells (w normal) -> w conservation -> advec -> w normal -> diff ->
+// w conservation -> pres -> w normal -> rk3.  advec_4 and diff_4 stay two launches: they see different w ghost cells
+// (conservation vs normal type).
+template <typename TF>
+int substep_o4_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, int substep, double dt)
+{
+    const GridDev<TF>& g = c->g;
+    if (c->nranks > 1) { c->err = "the 4th-order sub-step is single-GPU in this version"; return MHH_E_INVALID; }
+    if (prm->swthermo != 0) { c->err = "the 4th-order sub-step has no thermo coupling (swthermo = 0)"; return MHH_E_INVALID; }
+    int rc = check_mom<TF>(c, f, false, false);
+    if (rc != MHH_OK) return rc;
+    NEED(c, f->p, "p");
+    TF* prog[3 + MHH_MAX_SCALARS] = {P<TF>(f->u), P<TF>(f->v), P<TF>(f->w)};
+    for (int n = 0; n < f->ns; ++n) prog[3 + n] = P<TF>(f->s[n]);
+    if ((rc = cyclic_fields<TF>(c, prog, 3 + f->ns)) != MHH_OK) return rc;
+    if ((rc = ghost4_impl<TF>(c, P<TF>(f->u), prm->mbcbot, P<TF>(f->u_bot), P<TF>(f->u_gradbot), prm->mbctop, P<TF>(f->u_top), P<TF>(f->u_gradtop))) != MHH_OK) return rc;
+    if ((rc = ghost4_impl<TF>(c, P<TF>(f->v), prm->mbcbot, P<TF>(f->v_bot), P<TF>(f->v_gradbot), prm->mbctop, P<TF>(f->v_top), P<TF>(f->v_gradtop))) != MHH_OK) return rc;
+    for (int n = 0; n < f->ns; ++n)
+        if ((rc = ghost4_impl<TF>(c, P<TF>(f->s[n]), prm->sbcbot[n], P<TF>(f->s_bot[n]), P<TF>(f->s_gradbot[n]),
+                                  prm->sbctop[n], P<TF>(f->s_top[n]), P<TF>(f->s_gradtop[n]))) != MHH_OK) return rc;
+    if ((rc = ghost4w_impl<TF>(c, P<TF>(f->w), 1)) != MHH_OK) return rc;        // (the normal-type fill right before is overwritten)
+    if ((rc = o4_impl<TF>(c, f, true, false)) != MHH_OK) return rc;
+    if ((rc = ghost4w_impl<TF>(c, P<TF>(f->w), 0)) != MHH_OK) return rc;
+    if ((rc = o4_impl<TF>(c, f, false, true)) != MHH_OK) return rc;
+    if ((rc = ghost4w_impl<TF>(c, P<TF>(f->w), 1)) != MHH_OK) return rc;
+    const double cBd[3] = {1. / 3., 15. / 16., 8. / 15.};
+    if ((rc = pres4_exec_impl<TF>(c, f, cBd[substep] * dt)) != MHH_OK) return rc;
+    if ((rc = ghost4w_impl<TF>(c, P<TF>(f->w), 0)) != MHH_OK) return rc;
+    TF* tend[3 + MHH_MAX_SCALARS] = {P<TF>(f->ut), P<TF>(f->vt), P<TF>(f->wt)};
+    for (int n = 0; n < f->ns; ++n) tend[3 + n] = P<TF>(f->st[n]);
+    for (int n = 0; n < 3 + f->ns; ++n)
+        if ((rc = rk3_impl<TF>(c, prog[n], tend[n], substep, dt)) != MHH_OK) return rc;
+    (void)g;
+    return MHH_OK;
+}
+
 // One fused sub-step (Model::exec order, src/model.cxx:356-504, restricted to the hot path).
 template <typename TF>
 int substep_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, int substep, double dt)
@@ -1428,9 +1500,14 @@ int substep_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, int sub
     NEED_BASE(c);
     NEED(c, prm, "params");
     const GridDev<TF>& g = c->g;
-    if ((prm->swadvec != 25 && prm->swadvec != 2) || (prm->swdiff != 1 && prm->swdiff != 2))
-    { c->err = "dycore_substep: swadvec must be 2i5 (25) or 2, swdiff smag2 (1) or 2"; return MHH_E_INVALID; }
     if (substep < 0 || substep > 2) { c->err = "substep must be 0..2"; return MHH_E_INVALID; }
+    if (prm->swadvec == 4 || prm->swdiff == 4)
+    {
+        if (prm->swadvec != 4 || prm->swdiff != 4) { c->err = "dycore_substep: the 4th-order configuration is swadvec = 4 with swdiff = 4 (and pres_4)"; return MHH_E_INVALID; }
+        return substep_o4_impl<TF>(c, f, prm, substep, dt);
+    }
+    if ((prm->swadvec != 25 && prm->swadvec != 2) || (prm->swdiff != 1 && prm->swdiff != 2))
+    { c->err = "dycore_substep: swadvec must be 2i5 (25), 2 or 4, swdiff smag2 (1), 2 or 4"; return MHH_E_INVALID; }
     const bool smag = prm->swdiff == 1, adv5 = prm->swadvec == 25, buoy = prm->swthermo == 1;
     int rc = check_mom<TF>(c, f, smag, smag && prm->surface_model != 0);
     if (rc != MHH_OK) return rc;
@@ -1772,6 +1849,13 @@ int mhh_boundary_cyclic_2d(mhh_ctx* ctx, void* fld)
 int mhh_boundary_ghost_cells_2nd(mhh_ctx* ctx, void* fld, int bcbot, const void* bot, const void* gradbot,
                                  int bctop, const void* top, const void* gradtop)
 { DISPATCH1(ctx, ghost_impl<TF>(c, P<TF>(fld), bcbot, P<TF>(bot), P<TF>(gradbot), bctop, P<TF>(top), P<TF>(gradtop))); }
+
+int mhh_boundary_ghost_cells_4th(mhh_ctx* ctx, void* fld, int bcbot, const void* bot, const void* gradbot,
+                                 int bctop, const void* top, const void* gradtop)
+{ DISPATCH1(ctx, ghost4_impl<TF>(c, P<TF>(fld), bcbot, P<TF>(bot), P<TF>(gradbot), bctop, P<TF>(top), P<TF>(gradtop))); }
+
+int mhh_boundary_ghost_cells_w_4th(mhh_ctx* ctx, void* w, int conservation)
+{ DISPATCH1(ctx, ghost4w_impl<TF>(c, P<TF>(w), conservation)); }
 
 int mhh_advec_exec(mhh_ctx* ctx, int swadvec, const mhh_fields* f)
 {

@@ -189,6 +189,61 @@ __global__ void __launch_bounds__(256) o4_s_kernel(const O4ScalArgs<TF> a, const
     a.st[ijk] = st;
 }
 
+// 4th-order vertical ghost cells of a cell-centred field (src/boundary.cxx:776-848): two levels at either wall from the
+// wall value (Dirichlet) or the wall gradient (Neumann / flux).  gb / gt = grad4 of the z levels around the wall.
+template <typename TF>
+__global__ void ghost_cells_4th_kernel(TF* __restrict__ a, const GridDev<TF> g,
+        const int bcbot, const TF* __restrict__ bot, const TF* __restrict__ gradbot,
+        const int bctop, const TF* __restrict__ top, const TF* __restrict__ gradtop, const TF gb, const TF gt)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= g.icells || j >= g.jcells) return;
+    const long long ij = i + (long long)j * g.icells, kk = g.ijcells;
+    const long long kb = ij + g.kstart * kk, kt = ij + (g.kend - 1) * kk;
+    if (bcbot == 0)
+    {
+        a[kb - kk] = TF(8. / 3.) * bot[ij] - TF(2.) * a[kb] + TF(1. / 3.) * a[kb + kk];
+        a[kb - 2 * kk] = TF(8.) * bot[ij] - TF(9.) * a[kb] + TF(2.) * a[kb + kk];
+    }
+    else if (bcbot == 1)
+    {
+        a[kb - kk] = TF(-1.) * gb * gradbot[ij] + a[kb];
+        a[kb - 2 * kk] = TF(-3.) * gb * gradbot[ij] + a[kb + kk];
+    }
+    if (bctop == 0)
+    {
+        a[kt + kk] = TF(8. / 3.) * top[ij] - TF(2.) * a[kt] + TF(1. / 3.) * a[kt - kk];
+        a[kt + 2 * kk] = TF(8.) * top[ij] - TF(9.) * a[kt] + TF(2.) * a[kt - kk];
+    }
+    else if (bctop == 1)
+    {
+        a[kt + kk] = TF(1.) * gt * gradtop[ij] + a[kt];
+        a[kt + 2 * kk] = TF(3.) * gt * gradtop[ij] + a[kt - kk];
+    }
+}
+
+// no-penetration ghost cells of w (src/boundary.cxx:850-922): conservation type (two mirrored levels) or normal type
+template <typename TF>
+__global__ void ghost_cells_w_4th_kernel(TF* __restrict__ w, const GridDev<TF> g, const int conservation)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= g.icells || j >= g.jcells) return;
+    const long long ij = i + (long long)j * g.icells, kk = g.ijcells;
+    const long long kb = ij + g.kstart * kk, kt = ij + g.kend * kk;
+    if (conservation)
+    {
+        w[kb - kk] = -w[kb + kk]; w[kb - 2 * kk] = -w[kb + 2 * kk];
+        w[kt + kk] = -w[kt - kk]; w[kt + 2 * kk] = -w[kt - 2 * kk];
+    }
+    else
+    {
+        w[kb - kk] = TF(-6.) * w[kb + kk] + TF(4.) * w[kb + 2 * kk] - w[kb + 3 * kk];
+        w[kt + kk] = TF(-6.) * w[kt - kk] + TF(4.) * w[kt - 2 * kk] - w[kt - 3 * kk];
+    }
+}
+
 // Advec_4 calc_cfl (src/advec_4.cxx:50-86): interp4c(a,b,c,d) = ci0*(a+d) + ci1*(b+c)
 template <typename TF>
 __global__ void __launch_bounds__(256) o4_cfl_kernel(const TF* __restrict__ u, const TF* __restrict__ v, const TF* __restrict__ w,

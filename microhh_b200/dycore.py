@@ -213,6 +213,20 @@ class Boundary:
             self.ctx.h, _ptr(fld), bcbot, _ptr(bot), _ptr(gradbot), bctop, _ptr(top), _ptr(gradtop)))
 
 
+class Boundary_4th:
+    """Boundary<TF>::set_ghost_cells / set_ghost_cells_w on a 4th-order grid (src/boundary.cxx:776-922)."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    def set_ghost_cells_field(self, fld, bcbot, bot, gradbot, bctop, top, gradtop):
+        self.ctx.check(self.ctx.lib.mhh_boundary_ghost_cells_4th(
+            self.ctx.h, _ptr(fld), bcbot, _ptr(bot), _ptr(gradbot), bctop, _ptr(top), _ptr(gradtop)))
+
+    def set_ghost_cells_w(self, w, conservation):
+        self.ctx.check(self.ctx.lib.mhh_boundary_ghost_cells_w_4th(self.ctx.h, _ptr(w), int(bool(conservation))))
+
+
 class Advec:
     def __init__(self, ctx, swadvec="2i5"):
         self.ctx = ctx; self.sw = SWADVEC[swadvec]

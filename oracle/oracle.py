@@ -230,6 +230,48 @@ def ghost_cells_top_2nd(g, a, bc, atop, agradtop):
 
 
 # --------------------------------------------------------------------------------------
+# 4th-order vertical ghost cells (reference src/boundary.cxx:776-922): two ghost levels from the wall value
+# (Dirichlet) or the wall gradient (Neumann / flux); w: no-penetration, "normal" (one level, 3rd-order extrapolation of
+# the zero-divergence condition) and "conservation" (two levels mirrored with a sign flip) types.
+# --------------------------------------------------------------------------------------
+def _grad4(a, b, c, d, TF):
+    """include/finite_difference.h:127-131: -cg0*(d-a) - cg1*(c-b)"""
+    return -TF(CG[0])*(d - a) - TF(CG[1])*(c - b)
+
+
+def ghost_cells_bot_4th(g, a, bc, abot, agradbot):
+    TF = g.TF; ks = g.kstart
+    if bc == BC_DIRICHLET:
+        a[ks-1] = TF(8./3.)*abot - TF(2.)*a[ks] + TF(1./3.)*a[ks+1]
+        a[ks-2] = TF(8.)*abot - TF(9.)*a[ks] + TF(2.)*a[ks+1]
+    elif bc == BC_NEUMANN:
+        gr = _grad4(g.z[ks-2], g.z[ks-1], g.z[ks], g.z[ks+1], TF)
+        a[ks-1] = TF(-1.)*gr*agradbot + a[ks]
+        a[ks-2] = TF(-3.)*gr*agradbot + a[ks+1]
+
+
+def ghost_cells_top_4th(g, a, bc, atop, agradtop):
+    TF = g.TF; ke = g.kend
+    if bc == BC_DIRICHLET:
+        a[ke] = TF(8./3.)*atop - TF(2.)*a[ke-1] + TF(1./3.)*a[ke-2]
+        a[ke+1] = TF(8.)*atop - TF(9.)*a[ke-1] + TF(2.)*a[ke-2]
+    elif bc == BC_NEUMANN:
+        gr = _grad4(g.z[ke-2], g.z[ke-1], g.z[ke], g.z[ke+1], TF)
+        a[ke] = TF(1.)*gr*agradtop + a[ke-1]
+        a[ke+1] = TF(3.)*gr*agradtop + a[ke-2]
+
+
+def ghost_cells_w_4th(g, w, conservation):
+    TF = g.TF; ks, ke = g.kstart, g.kend
+    if conservation:
+        w[ks-1] = -w[ks+1]; w[ks-2] = -w[ks+2]
+        w[ke+1] = -w[ke-1]; w[ke+2] = -w[ke-2]
+    else:
+        w[ks-1] = TF(-6.)*w[ks+1] + TF(4.)*w[ks+2] - w[ks+3]
+        w[ke+1] = TF(-6.)*w[ke-1] + TF(4.)*w[ke-2] - w[ke-3]
+
+
+# --------------------------------------------------------------------------------------
 # Advec_2i5 (reference src/advec_2i5.cxx:151-728)
 # --------------------------------------------------------------------------------------
 def _advec_2i5_vertical(g, at, a, wface, rho_f, rho_c, dzx, lo, hi):
@@ -1375,6 +1417,9 @@ class NumpyKernels:
     def boundary_cyclic(self, a, edge=EDGE_BOTH): boundary_cyclic(self.g, a, edge)
     def ghost_cells_bot_2nd(self, a, bc, abot, agradbot): ghost_cells_bot_2nd(self.g, a, bc, abot, agradbot)
     def ghost_cells_top_2nd(self, a, bc, atop, agradtop): ghost_cells_top_2nd(self.g, a, bc, atop, agradtop)
+    def ghost_cells_bot_4th(self, a, bc, abot, agradbot): ghost_cells_bot_4th(self.g, a, bc, abot, agradbot)
+    def ghost_cells_top_4th(self, a, bc, atop, agradtop): ghost_cells_top_4th(self.g, a, bc, atop, agradtop)
+    def ghost_cells_w_4th(self, w, conservation): ghost_cells_w_4th(self.g, w, conservation)
     def advec_2i5_u(self, ut, u, v, w, rhoref, rhorefh): advec_2i5_u(self.g, ut, u, v, w, rhoref, rhorefh)
     def advec_2i5_v(self, vt, u, v, w, rhoref, rhorefh): advec_2i5_v(self.g, vt, u, v, w, rhoref, rhorefh)
     def advec_2i5_w(self, wt, u, v, w, rhoref, rhorefh): advec_2i5_w(self.g, wt, u, v, w, rhoref, rhorefh)

@@ -59,6 +59,15 @@ class RefKernels:
     def ghost_cells_top_2nd(self, a, bc, atop, agradtop):
         self._call("ref_ghost_cells_top_2nd", a, self.g.dzh, bc, atop, agradtop)
 
+    def ghost_cells_bot_4th(self, a, bc, abot, agradbot):
+        self._call("ref_ghost_cells_bot_4th", a, self.g.z, bc, abot, agradbot)
+
+    def ghost_cells_top_4th(self, a, bc, atop, agradtop):
+        self._call("ref_ghost_cells_top_4th", a, self.g.z, bc, atop, agradtop)
+
+    def ghost_cells_w_4th(self, w, conservation):
+        self._call("ref_ghost_cells_w_4th", w, int(bool(conservation)))
+
     # --- advec_2i5
     def advec_2i5_u(self, ut, u, v, w, rhoref, rhorefh):
         g = self.g; self._call("ref_advec_2i5_u", ut, u, v, w, g.dzi, g.dx, g.dy, rhoref, rhorefh)

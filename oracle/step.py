@@ -97,8 +97,47 @@ def _pres_and_rk3(g, K, c, prm, substep, dt, pres, lap):
     return pres
 
 
+def dycore_substep_o4(g, K, c, prm, substep, dt, pres=None):
+    """The 4th-order DNS configuration (swspatialorder=4: advec_4 + diff_4 + pres_4, no thermo), same call order of
+    Model<TF>::exec (src/model.cxx:368-437): cyclic -> 4th-order ghost cells (w: normal type) -> w conservation type ->
+    advec -> w normal -> diff -> w conservation -> pres -> w normal -> rk3."""
+    scal = c["scalars"]
+    for n in ["u", "v", "w"] + scal:
+        K.boundary_cyclic(c[n])
+    for n in ["u", "v"]:
+        K.ghost_cells_bot_4th(c[n], prm["mbcbot"], c.get(n + "_bot"), c.get(n + "_gradbot"))
+        K.ghost_cells_top_4th(c[n], prm["mbctop"], c.get(n + "_top"), c.get(n + "_gradtop"))
+    K.ghost_cells_w_4th(c["w"], False)
+    for s in scal:
+        K.ghost_cells_bot_4th(c[s], prm["sbcbot"], c.get(s + "_bot"), c.get(s + "_gradbot"))
+        K.ghost_cells_top_4th(c[s], prm["sbctop"], c.get(s + "_top"), c.get(s + "_gradtop"))
+    K.ghost_cells_w_4th(c["w"], True)
+    K.advec_4_u(c["ut"], c["u"], c["v"], c["w"])
+    K.advec_4_v(c["vt"], c["u"], c["v"], c["w"])
+    K.advec_4_w(c["wt"], c["u"], c["v"], c["w"])
+    for s in scal:
+        K.advec_4_s(c[s + "t"], c[s], c["u"], c["v"], c["w"])
+    K.ghost_cells_w_4th(c["w"], False)
+    K.diff_4_c(c["ut"], c["u"], prm["visc"])
+    K.diff_4_c(c["vt"], c["v"], prm["visc"])
+    K.diff_4_w(c["wt"], c["w"], prm["visc"])
+    for s in scal:
+        K.diff_4_c(c[s + "t"], c[s], prm["svisc"])
+    K.ghost_cells_w_4th(c["w"], True)
+    if pres is None:
+        pres = O.Pres4(g)
+    pres.exec(c["p"], c["u"], c["v"], c["w"], c["ut"], c["vt"], c["wt"], O.rk3_subdt(dt, substep))
+    K.ghost_cells_w_4th(c["w"], False)
+    for n in ["u", "v", "w"] + scal:
+        K.rk3(c[n], c[n + "t"], substep, dt)
+    return pres
+
+
 def dycore_step(g, K, c, prm, dt, timers=None):
     pres = None
     for ss in range(3):
-        pres = dycore_substep(g, K, c, prm, ss, dt, pres, timers)
+        if prm.get("swadvec") == "4":
+            pres = dycore_substep_o4(g, K, c, prm, ss, dt, pres)
+        else:
+            pres = dycore_substep(g, K, c, prm, ss, dt, pres, timers)
     return pres

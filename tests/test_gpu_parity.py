@@ -269,6 +269,51 @@ def test_pres_4_exec(dtype, shape, stretched):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape,mbc", [((32, 24, 16), 0), ((24, 1, 12), 0), ((32, 16, 12), 1)])
+def test_full_rk3_step_order4(dtype, shape, mbc):
+    """The 4th-order DNS configuration (moser180 / taylorgreen style: advec_4 + diff_4 + pres_4, 4th-order ghost cells,
+    no thermo): one full RK3 step == the oracle in the reference's call order; no-slip (Dirichlet) and free-slip walls."""
+    from util import stretched_z
+    from microhh_b200 import dycore as D, capi
+    from microhh_b200.grid import GridData
+    from microhh_b200.synthetic import make_case
+    it, jt, kt = shape
+    z = stretched_z(kt, 2.)
+    g = O.Grid(it, jt, kt, 6., 4., 2., 3, 3, 3, dtype, z=z, order=4)
+    gd = GridData(it, jt, kt, 6., 4., 2., 3, 3, 3, dtype, z=z, order=4)
+    case = make_case(gd, seed=5, noise=0.02)
+    ks, ke = g.kstart, g.kend
+    case["w"][:ks+1] = 0; case["w"][ke:] = 0
+    case["th"] = (1. + 0.1*case["u"]).astype(dtype)            # a passive scalar with sane ghost values
+    if jt == 1:
+        case["v"][:] = 0
+    for n in ("u", "v"):
+        case[n + "_bot"] = np.zeros(gd.shape2d, dtype); case[n + "_top"] = np.zeros(gd.shape2d, dtype)
+        case[n + "_gradbot"] = np.zeros(gd.shape2d, dtype); case[n + "_gradtop"] = np.zeros(gd.shape2d, dtype)
+    case["th_gradbot"] = np.zeros(gd.shape2d, dtype); case["th_gradtop"] = np.zeros(gd.shape2d, dtype)
+    ctx = D.Context(gd, 0)
+    ones = np.ones(gd.kcells, dtype)
+    ctx.set_basestate(ones, ones, 300*ones, 300*ones)
+    visc = 1e-3
+    f = D.Fields(ctx, case, visc=visc, svisc=visc)
+    prm = D.make_params(swadvec="4", swdiff="4", swthermo=None, surface_model=False, mbcbot=mbc, mbctop=mbc)
+    oprm = ostep.default_params(); oprm.update(swadvec="4", swdiff="4", visc=visc, svisc=visc, mbcbot=mbc, mbctop=mbc)
+    dt = 0.01
+    D.Dycore(ctx, prm).step(f, dt)
+    ostep.dycore_step(g, O.NumpyKernels(g), case, oprm, dt)
+    ctx.sync()
+    names = ("u", "w", "th") if jt == 1 else ("u", "v", "w", "th")
+    for n in names:
+        assert rel_l2(interior(g, f[n].cpu().numpy()), interior(g, case[n])) <= 20*TOL[dtype], n
+    un = {c: f[c].cpu().numpy().copy() for c in "uvw"}
+    for c in "uvw":
+        O.boundary_cyclic(g, un[c])
+    O.ghost_cells_w_4th(g, un["w"], True)
+    scale = float(np.abs(interior(g, case["u"])).max())/float(g.dx)
+    assert float(O.Pres4(g).divergence(un["u"], un["v"], un["w"])) <= (1e-10 if dtype == np.float64 else 5e-3)*scale
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 def test_thermo_dry_buoyancy(dtype):
     g, gd, case = make_pair(32, 16, 12, dtype)
     prepare_halos(g, case)

@@ -151,6 +151,58 @@ def test_order4_kernels_bitexact(dtype, shape, stretched):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(16, 12, 10), (24, 1, 8)])
+def test_full_rk3_step_order4_bitexact(dtype, shape):
+    """4th-order DNS step (advec_4 + diff_4 + pres_4 + 4th-order ghost cells) in Model::exec order: numpy kernels ==
+    compiled reference kernels (the Pres_4 member-function glue is the oracle's restatement in both)."""
+    from util import stretched_z
+    from microhh_b200.grid import GridData
+    from microhh_b200.synthetic import make_case
+    it, jt, kt = shape
+    z = stretched_z(kt, 2.)
+    g = O.Grid(it, jt, kt, 6., 4., 2., 3, 3, 3, dtype, z=z, order=4)
+    gd = GridData(it, jt, kt, 6., 4., 2., 3, 3, 3, dtype, z=z, order=4)
+    case = make_case(gd, seed=5, noise=0.02)
+    ks, ke = g.kstart, g.kend
+    case["w"][:ks+1] = 0; case["w"][ke:] = 0
+    case["th"] = (1. + 0.1*case["u"]).astype(dtype)
+    for n in ("u", "v"):
+        for sfx in ("_bot", "_top", "_gradbot", "_gradtop"):
+            case[n + sfx] = np.zeros(gd.shape2d, dtype)
+    case["th_gradbot"] = np.zeros(gd.shape2d, dtype); case["th_gradtop"] = np.zeros(gd.shape2d, dtype)
+    prm = ostep.default_params(); prm.update(swadvec="4", swdiff="4", visc=1e-3, svisc=1e-3, mbcbot=0, mbctop=0)
+    c0, c1 = copy.deepcopy(case), copy.deepcopy(case)
+    N, R = both(g)
+    ostep.dycore_step(g, N, c0, prm, 0.01)
+    ostep.dycore_step(g, R, c1, prm, 0.01)
+    for n in ("u", "v", "w", "th", "p"):
+        assert np.array_equal(interior(g, c0[n]), interior(g, c1[n])), n
+    assert np.isfinite(interior(g, c0["u"])).all() and not np.array_equal(c0["u"], case["u"])
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("bc", [0, 1])
+def test_order4_ghost_cells_bitexact(dtype, bc):
+    """4th-order vertical ghost cells (src/boundary.cxx:776-922): numpy oracle == compiled reference."""
+    from util import stretched_z
+    rng = np.random.default_rng(8)
+    g = O.Grid(12, 10, 8, 3200., 3200., 3200., 3, 3, 3, dtype, z=stretched_z(8, 3200.), order=4)
+    N, R = both(g)
+    a0 = rng.standard_normal((g.kcells, g.jcells, g.icells)).astype(dtype)
+    two = lambda: rng.standard_normal((g.jcells, g.icells)).astype(dtype)
+    bot, gbot, top, gtop = two(), two(), two(), two()
+    out = []
+    for K in (N, R):
+        a = a0.copy(); w1 = a0.copy(); w2 = a0.copy()
+        K.ghost_cells_bot_4th(a, bc, bot, gbot); K.ghost_cells_top_4th(a, bc, top, gtop)
+        K.ghost_cells_w_4th(w1, False); K.ghost_cells_w_4th(w2, True)
+        out.append((a, w1, w2))
+    for x, y in zip(*out):
+        assert np.array_equal(x, y)
+    assert not np.array_equal(out[0][0], a0)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("swadvec,swdiff", [("2", "2"), ("2", "smag2"), ("2i5", "2")])
 def test_full_rk3_step_scheme_combinations_bitexact(dtype, swadvec, swdiff):
     """Advec_2 / Diff_2 in every combination with the LES schemes ("2" + "smag2" is drycblles as shipped)."""
