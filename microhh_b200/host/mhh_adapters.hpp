@@ -8,9 +8,10 @@
 // the Field3d ghost-cell layout stay unchanged.  See INTEGRATION.md for the three factory edits.
 //
 //   reference class (interface)                     adapter                      C ABI
-//   Advec<TF>        include/advec.h:45-71          Advec_2i5_b200<TF>           mhh_advec_exec / mhh_advec_get_cfl
+//   Advec<TF>        include/advec.h:45-71          Advec_{2i5,2,4}_b200<TF>     mhh_advec_exec / mhh_advec_get_cfl
 //   Diff<TF>         include/diff.h:38-71           Diff_smag2_b200<TF>          mhh_diff_smag2_exec_viscosity / _exec / _get_dn
-//   Pres<TF>         include/pres.h:41-92           Pres_2_b200<TF>              mhh_pres_exec / mhh_pres_check_divergence
+//                                                   Diff_{2,4}_b200<TF>          mhh_diff_2_exec / mhh_diff_4_exec / mhh_diff_2_get_dn
+//   Pres<TF>         include/pres.h:41-92           Pres_{2,4}_b200<TF>          mhh_pres_exec / mhh_pres_check_divergence
 //   Boundary_cyclic  include/boundary_cyclic.h:35   Boundary_cyclic_b200<TF>     mhh_boundary_cyclic / _2d
 //   Timeloop::exec   include/timeloop.h:65          timeloop_exec_b200()         mhh_timeloop_rk3
 //   Model::exec loop src/model.cxx:356-504          dycore_substep_b200()        mhh_dycore_substep (fused fast path)
@@ -67,6 +68,7 @@ namespace mhhb200
                 d.z = gd.z.data(); d.zh = gd.zh.data(); d.dz = gd.dz.data(); d.dzh = gd.dzh.data();
                 d.dzi = gd.dzi.data(); d.dzhi = gd.dzhi.data();
                 d.npx = md.npx; d.npy = md.npy; d.mpicoordx = md.mpicoordx; d.mpicoordy = md.mpicoordy;
+                if (grid.get_spatial_order() == Grid_order::Fourth) { d.dzi4 = gd.dzi4.data(); d.dzhi4 = gd.dzhi4.data(); }
                 const int rc = mhh_ctx_create(&d, dtype_of<TF>(), device, &ctx);
                 if (rc != MHH_OK)
                 {
@@ -86,6 +88,11 @@ namespace mhhb200
                     if (md.mpiid == 0) MHH_CHECK(ctx, mhh_comm_get_unique_id(id, MHH_COMM_ID_BYTES));
                     master.broadcast(reinterpret_cast<char*>(id), MHH_COMM_ID_BYTES);
                     MHH_CHECK(ctx, mhh_comm_init(ctx, id, MHH_COMM_ID_BYTES));
+                    // fused transposes / ghost rows over NVLink peer memory: all-gather the CUDA IPC handles in rank order
+                    std::vector<unsigned char> mine(MHH_IPC_BYTES), all((size_t)MHH_IPC_BYTES * md.nprocs);
+                    MHH_CHECK(ctx, mhh_comm_get_ipc_handles(ctx, mine.data(), MHH_IPC_BYTES));
+                    MPI_Allgather(mine.data(), MHH_IPC_BYTES, MPI_BYTE, all.data(), MHH_IPC_BYTES, MPI_BYTE, md.commxy);
+                    MHH_CHECK(ctx, mhh_comm_open_peers(ctx, all.data(), (int)all.size()));
                 }
                 #endif
             }
@@ -143,26 +150,33 @@ namespace mhhb200
         return f;
     }
 
-    // ---- Advec_2i5 (src/advec_2i5.cxx:955-1063) -------------------------------------------------
-    template<typename TF>
-    class Advec_2i5_b200 : public Advec<TF>
+    // ---- Advec_2i5 (src/advec_2i5.cxx:955-1063), Advec_2 (src/advec_2.cxx:288-345), Advec_4 (src/advec_4.cxx:573-684):
+    // SW = the C ABI's swadvec code (25, 2, 4)
+    template<typename TF, int SW, Advection_type TYPE>
+    class Advec_b200 : public Advec<TF>
     {
         public:
-            Advec_2i5_b200(Master& m, Grid<TF>& g, Fields<TF>& f, Input& in, std::shared_ptr<Context<TF>> c) :
+            Advec_b200(Master& m, Grid<TF>& g, Fields<TF>& f, Input& in, std::shared_ptr<Context<TF>> c) :
                 Advec<TF>(m, g, f, in), c(std::move(c))
-            { g.set_minimum_ghost_cells(3, 3, 1); }     // src/advec_2i5.cxx:42-45
+            {
+                // ghost cells as the reference constructors ask for them (src/advec_2i5.cxx:42-45, src/advec_2.cxx:40-43,
+                // src/advec_4.cxx:41-48)
+                if (SW == 25) g.set_minimum_ghost_cells(3, 3, 1);
+                else if (SW == 2) g.set_minimum_ghost_cells(1, 1, 1);
+                else g.set_minimum_ghost_cells(3, 3, 3);
+            }
 
             void create(Stats<TF>&) override {}
             void exec(Stats<TF>&) override
             {
                 const mhh_fields f = fields_view(this->fields);
-                MHH_CHECK(c->ctx, mhh_advec_exec(c->ctx, 25, &f));
+                MHH_CHECK(c->ctx, mhh_advec_exec(c->ctx, SW, &f));
             }
             double get_cfl(double dt) override
             {
                 const mhh_fields f = fields_view(this->fields);
                 double cfl = 0.;
-                MHH_CHECK(c->ctx, mhh_advec_get_cfl(c->ctx, 25, &f, dt, &cfl));
+                MHH_CHECK(c->ctx, mhh_advec_get_cfl(c->ctx, SW, &f, dt, &cfl));
                 return cfl;
             }
             unsigned long get_time_limit(unsigned long idt, double dt) override
@@ -174,11 +188,14 @@ namespace mhhb200
             }
             void get_advec_flux(Field3d<TF>&, const Field3d<TF>&) override
             { throw std::runtime_error("mhhb200: get_advec_flux is a statistics path (out of scope)"); }
-            Advection_type get_switch() const override { return Advection_type::Advec_2i5; }
+            Advection_type get_switch() const override { return TYPE; }
 
         private:
             std::shared_ptr<Context<TF>> c;
     };
+    template<typename TF> using Advec_2i5_b200 = Advec_b200<TF, 25, Advection_type::Advec_2i5>;
+    template<typename TF> using Advec_2_b200   = Advec_b200<TF, 2,  Advection_type::Advec_2>;
+    template<typename TF> using Advec_4_b200   = Advec_b200<TF, 4,  Advection_type::Advec_4>;
 
     // ---- Diff_smag2 (src/diff_smag2.cxx:312-607) ------------------------------------------------
     template<typename TF>
@@ -247,12 +264,51 @@ namespace mhhb200
             double dnmax;
     };
 
-    // ---- Pres_2 (src/pres_2.cxx:66-105) ---------------------------------------------------------
-    template<typename TF>
-    class Pres_2_b200 : public Pres<TF>
+    // ---- Diff_2 (src/diff_2.cxx:120-190) and Diff_4 (src/diff_4.cxx:200-310): ORDER = 2 | 4 --------------------
+    template<typename TF, int ORDER>
+    class Diff_const_b200 : public Diff<TF>
     {
         public:
-            Pres_2_b200(Master& m, Grid<TF>& g, Fields<TF>& f, FFT<TF>& fft, Input& in, std::shared_ptr<Context<TF>> c) :
+            Diff_const_b200(Master& m, Grid<TF>& g, Fields<TF>& f, Boundary<TF>& b, Input& in, std::shared_ptr<Context<TF>> c) :
+                Diff<TF>(m, g, f, b, in), c(std::move(c))
+            { dnmax = in.get_item<double>("diff", "dnmax", "", 0.4); }
+            Diffusion_type get_switch() const override { return ORDER == 2 ? Diffusion_type::Diff_2 : Diffusion_type::Diff_4; }
+            void init() override {}
+            void create(Stats<TF>&, const bool) override {}
+            void exec_viscosity(Stats<TF>&, Thermo<TF>&) override {}
+            void exec(Stats<TF>&) override
+            {
+                const mhh_fields f = fields_view(this->fields);
+                MHH_CHECK(c->ctx, ORDER == 2 ? mhh_diff_2_exec(c->ctx, &f) : mhh_diff_4_exec(c->ctx, &f));
+            }
+            void exec_stats(Stats<TF>&, Thermo<TF>&) override {}
+            void diff_flux(Field3d<TF>&, const Field3d<TF>&) override
+            { throw std::runtime_error("mhhb200: diff_flux is a statistics path (out of scope)"); }
+            double get_dn(double dt) override
+            {
+                const mhh_fields f = fields_view(this->fields);
+                double dn = 0.;
+                MHH_CHECK(c->ctx, mhh_diff_2_get_dn(c->ctx, &f, dt, &dn));     // Diff_4 uses the same formula (src/diff_4.cxx:226-245)
+                return dn;
+            }
+            unsigned long get_time_limit(unsigned long idt, double dt) override
+            { return idt * dnmax / std::max(Constants::dsmall, get_dn(dt)); }         // src/diff_2.cxx:127-136
+            void prepare_device(Boundary<TF>&) override {}
+            void clear_device() override {}
+
+        private:
+            std::shared_ptr<Context<TF>> c;
+            double dnmax;
+    };
+    template<typename TF> using Diff_2_b200 = Diff_const_b200<TF, 2>;
+    template<typename TF> using Diff_4_b200 = Diff_const_b200<TF, 4>;
+
+    // ---- Pres_2 (src/pres_2.cxx:66-105) and Pres_4 (src/pres_4.cxx:76-156): SW = swpres (2 | 4) -------------------
+    template<typename TF, int SW>
+    class Pres_b200 : public Pres<TF>
+    {
+        public:
+            Pres_b200(Master& m, Grid<TF>& g, Fields<TF>& f, FFT<TF>& fft, Input& in, std::shared_ptr<Context<TF>> c) :
                 Pres<TF>(m, g, f, fft, in), c(std::move(c)) {}
             void init() override {}
             void set_values() override {}       // the tables are built by mhh_set_basestate
@@ -260,13 +316,13 @@ namespace mhhb200
             void exec(double sub_dt, Stats<TF>&) override
             {
                 const mhh_fields f = fields_view(this->fields);
-                MHH_CHECK(c->ctx, mhh_pres_exec(c->ctx, 2, &f, sub_dt));
+                MHH_CHECK(c->ctx, mhh_pres_exec(c->ctx, SW, &f, sub_dt));
             }
             TF check_divergence() override
             {
                 const mhh_fields f = fields_view(this->fields);
                 double div = 0.;
-                MHH_CHECK(c->ctx, mhh_pres_check_divergence(c->ctx, 2, &f, &div));
+                MHH_CHECK(c->ctx, mhh_pres_check_divergence(c->ctx, SW, &f, &div));
                 return static_cast<TF>(div);
             }
             void prepare_device() override {}
@@ -275,6 +331,8 @@ namespace mhhb200
         private:
             std::shared_ptr<Context<TF>> c;
     };
+    template<typename TF> using Pres_2_b200 = Pres_b200<TF, 2>;
+    template<typename TF> using Pres_4_b200 = Pres_b200<TF, 4>;
 
     // ---- Boundary_cyclic::exec_g / exec_2d_g (src/boundary_cyclic.cu:98-128) --------------------
     template<typename TF>

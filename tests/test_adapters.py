@@ -15,9 +15,14 @@ SRC = r'''
 #include "input.h"
 template class mhhb200::Context<double>;
 template class mhhb200::Context<float>;
-template class mhhb200::Advec_2i5_b200<double>;
+template class mhhb200::Advec_b200<double, 25, Advection_type::Advec_2i5>;
+template class mhhb200::Advec_b200<float, 2, Advection_type::Advec_2>;
+template class mhhb200::Advec_b200<double, 4, Advection_type::Advec_4>;
 template class mhhb200::Diff_smag2_b200<double>;
-template class mhhb200::Pres_2_b200<float>;
+template class mhhb200::Diff_const_b200<double, 2>;
+template class mhhb200::Diff_const_b200<float, 4>;
+template class mhhb200::Pres_b200<float, 2>;
+template class mhhb200::Pres_b200<double, 4>;
 template struct mhhb200::Boundary_cyclic_b200<double>;
 template void mhhb200::timeloop_exec_b200<double>(mhhb200::Context<double>&, Fields<double>&, int, double);
 template void mhhb200::dycore_substep_b200<float>(mhhb200::Context<float>&, Fields<float>&, Boundary<float>&, const mhh_params&, int, double);
