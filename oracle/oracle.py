@@ -11,8 +11,12 @@ results are bit-identical to the reference's own CPU kernels compiled with
 `-ffp-contract=off` (`oracle/_ref/libmhh_ref.so`; checked in tests/test_oracle_vs_ref.py
 and pinned by the golden vectors in tests/golden/).
 
-Parity status: PINNED for advec_2i5 / diff_smag2 / thermo_dry / boundary / rk3 / tdma
-against the reference's own compiled kernels (bit-exact).  The FFT (FFTW3, a system
+Parity status: PINNED for advec_2i5 / advec_2 / advec_4 / diff_smag2 / diff_2 / diff_4 / thermo_dry /
+boundary (cyclic, 2nd- and 4th-order vertical ghost cells) / rk3 / tdma against the reference's own
+compiled kernels (bit-exact).  "Parity unpinned" (class-member code of the reference that needs live
+Grid/Fields objects, restated and pinned by properties instead): Pres_2 / Pres_4 glue (input, matrix
+build, hdma, output; property = the corrected velocity is divergence-free to rounding) and the
+4th-order grid metrics (property = exact for a uniform grid).  The FFT (FFTW3, a system
 package that is not vendored in the reference; call sites reference src/fft.cxx:145-155,
 338-452) is restated from its published definition with numpy.fft (pocketfft):
 "parity unpinned" at the FFTW boundary, pinned instead by the DFT definition and by the
