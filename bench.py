@@ -195,6 +195,9 @@ def run_ours(args):
         "fft_x_forward_kernel": 7, "fft_y_forward_kernel": 2, "fft_y_backward_kernel": 2,
         "tdma_solve_kernel": 2, "fft_x_backward_kernel": 2, "pres_out_rk3_kernel": 13, "rk3_kernel": 4,
     }
+    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this very workload
+    # (profiles/r01/ncu_full_mom3_evisc_raw.csv: dram__bytes_read.sum + dram__bytes_write.sum); null for other workloads
+    ncu_traffic = {("mom3_kernel", "f64", "512x512x512"): 10.547e9 + 4.303e9}
     roofline = None
     if top[0] is not None:
         name, st = top
@@ -202,7 +205,9 @@ def run_ours(args):
         passes = alg.get(name, 0)
         achieved = passes*npts*B/(per_launch_ms*1e-3)/1e9
         roofline = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": achieved/peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                    "frac": achieved/peaks["hbm_gbs"],
+                    "traffic": ncu_traffic.get((name, args.dtype, f"{itot}x{jtot}x{ktot_l}")) if world == 1 else None,
+                    "traffic_unit": "bytes per launch (ncu, profiles/r01)", "peak_source": peak_src,
                     "share_of_step": st["ms"]/ms, "algorithmic_passes": passes}
     step_alg_bytes = 3*algorithmic_bytes_per_point_substep(S, B)*npts
     whole = {"algorithmic_bytes_per_step": step_alg_bytes,

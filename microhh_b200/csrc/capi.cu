@@ -667,7 +667,7 @@ int evisc_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, const TF*
         for (const void* p : {(const void*)a.u, (const void*)a.v, (const void*)a.w})
             if (reinterpret_cast<uintptr_t>(p) % (2 * sizeof(TF)) != 0) vec = 1;
 #define ET4(S, V, Y, MB) do { \
-            static size_t attr_smem = 0; \
+            static size_t attr_smem_dev[64] = {0}; size_t& attr_smem = attr_smem_dev[c->device & 63];   /* the attribute is per device */ \
             if (attr_smem < smem) { CUDA_TRY(c, cudaFuncSetAttribute(evisc_tile_kernel<TF, S, V, Y, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; } \
             evisc_tile_kernel<TF, S, V, Y, MB><<<grid, TILE_X * Y, smem, c->stream>>>(t, g); } while (0)
 #define ET3(S, V, Y) do { if (c->evisc_mb == 3) ET4(S, V, Y, 3); else if (c->evisc_mb == 4) ET4(S, V, Y, 4); else ET4(S, V, Y, 512 / (TILE_X * Y)); } while (0)
@@ -808,7 +808,7 @@ int mom_tile_launch(Ctx<TF>* c, const MomArgs<TF>& a, bool surface, bool buoy)
     const size_t smem = mom_tile_smem(sizeof(TF), t.kchunk, ty);
     const int vec = vec_width<TF>(g, {a.u, a.v, a.w, a.evisc});
 #define MT(S, B, V, Y) do { \
-        static size_t attr_smem = 0; \
+        static size_t attr_smem_dev[64] = {0}; size_t& attr_smem = attr_smem_dev[c->device & 63];   /* the attribute is per device */ \
         if (attr_smem < smem) { CUDA_TRY(c, cudaFuncSetAttribute(mom_tile_kernel<TF, S, B, V, Y>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; } \
         mom_tile_kernel<TF, S, B, V, Y><<<grid, TILE_X * Y, smem, c->stream>>>(t, g); } while (0)
 #define MT2(S, B) do { if (vec == 2) { if (ty == 16) MT(S, B, 2, 16); else MT(S, B, 2, 8); } \
@@ -842,7 +842,7 @@ int mom2_launch(Ctx<TF>* c, const MomArgs<TF>& a, bool surface, bool buoy)
         !make_field_tmap<TF>(&twt, a.wt, g, T2_W + 2, ty) || !make_field_tmap<TF>(&tth, buoy ? (const void*)a.th : (const void*)a.u, g, T2_W + 2, ty))
     { c->err = "cuTensorMapEncodeTiled failed"; return MHH_E_CUDA; }
 #define M2(S, B, Y) do { \
-        static size_t attr_smem = 0; \
+        static size_t attr_smem_dev[64] = {0}; size_t& attr_smem = attr_smem_dev[c->device & 63];   /* the attribute is per device */ \
         if (attr_smem < smem) { CUDA_TRY(c, cudaFuncSetAttribute(mom2_kernel<TF, S, B, Y>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; } \
         mom2_kernel<TF, S, B, Y><<<grid, 32 * Y, smem, c->stream>>>(tu, tv, tw, te, tut, tvt, twt, tth, t, g); } while (0)
 #define M2Y(S, B) do { if (ty == 4) M2(S, B, 4); else if (ty == 8) M2(S, B, 8); else if (ty == 12) M2(S, B, 12); else M2(S, B, 6); } while (0)
@@ -879,7 +879,7 @@ int mom3_launch(Ctx<TF>* c, const MomArgs<TF>& a, const ScalArgs<TF>* sc, bool s
         !make_field_tmap<TF>(&twt, a.wt, g, T2_W + 2, ty) || !make_field_tmap<TF>(&tst, sc ? (const void*)sc->st : (const void*)a.ut, g, T2_W + 2, ty))
     { c->err = "cuTensorMapEncodeTiled failed"; return MHH_E_CUDA; }
 #define M3(S, B, N, Y) do { \
-        static size_t attr_smem = 0; \
+        static size_t attr_smem_dev[64] = {0}; size_t& attr_smem = attr_smem_dev[c->device & 63];   /* the attribute is per device */ \
         if (attr_smem < smem) { CUDA_TRY(c, cudaFuncSetAttribute(mom3_kernel<TF, S, B, N, Y>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; } \
         mom3_kernel<TF, S, B, N, Y><<<grid, 32 * ((3 + N) * Y + 1), smem, c->stream>>>(tu, tv, tw, te, ts, tut, tvt, twt, tst, t, g); } while (0)
 #define M3Y(S, B, N) do { if (ty == 3) M3(S, B, N, 3); else if (ty == 5) M3(S, B, N, 5); else M3(S, B, N, 4); } while (0)
@@ -914,7 +914,7 @@ int scal_tile_launch(Ctx<TF>* c, const ScalArgs<TF>& a, bool surface)
     const size_t smem = scal_tile_smem(sizeof(TF), t.kchunk, ty);
     const int vec = vec_width<TF>(g, {a.s, a.evisc});
 #define ST3(S, V, Y) do { \
-        static size_t attr_smem = 0; \
+        static size_t attr_smem_dev[64] = {0}; size_t& attr_smem = attr_smem_dev[c->device & 63];   /* the attribute is per device */ \
         if (attr_smem < smem) { CUDA_TRY(c, cudaFuncSetAttribute(scal_tile_kernel<TF, S, V, Y>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; } \
         scal_tile_kernel<TF, S, V, Y><<<grid, TILE_X * Y, smem, c->stream>>>(t, g); } while (0)
 #define ST(S, V) do { if (ty == 16) ST3(S, V, 16); else ST3(S, V, 8); } while (0)
