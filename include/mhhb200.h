@@ -160,6 +160,9 @@ MHH_API int mhh_comm_init(mhh_ctx* ctx, const void* id, int nbytes);
 #define MHH_IPC_BYTES 192
 MHH_API int mhh_comm_get_ipc_handles(mhh_ctx* ctx, void* out, int nbytes);
 MHH_API int mhh_comm_open_peers(mhh_ctx* ctx, const void* all_handles, int nbytes);
+/* Drop the peer mappings again and use NCCL transport (e.g. when mapping failed on some rank: the host decides
+ * collectively and every rank calls this). */
+MHH_API int mhh_comm_disable_peers(mhh_ctx* ctx);
 
 /* Spectral workspace layout of the slab decomposition (pure host functions, no GPU needed): which
  * x-modes a rank owns after the forward transpose and where element (row, mode) / (k, j, mode) lives

@@ -1738,6 +1738,7 @@ int mhh_comm_open_peers(mhh_ctx* ctx, const void* all, int nbytes)
     if (ctx->nranks > MAX_SLAB_RANKS) { ctx->err = "open_peers: too many ranks"; return MHH_E_INVALID; }
     if (!ctx->comm) { ctx->err = "open_peers: call mhh_comm_init first"; return MHH_E_INVALID; }
     { const char* e = getenv("MHH_NO_PEER"); if (e && e[0] == '1') return MHH_OK; }       // keep the NCCL all-to-all (A/B comparisons)
+    { const char* e = getenv("MHH_FAIL_PEER_RANK"); if (e && atoi(e) == ctx->rank) { ctx->err = "open_peers: failure injected by MHH_FAIL_PEER_RANK (test knob)"; return MHH_E_CUDA; } }
     DISPATCH1(ctx, ([&]() -> int {
         if (c->peers.on) { c->err = "open_peers: already open"; return MHH_E_INVALID; }
         if (c->g.jtot == 1) return MHH_OK;
@@ -1763,6 +1764,27 @@ int mhh_comm_open_peers(mhh_ctx* ctx, const void* all, int nbytes)
         pp.on = 1;
         c->peers = pp;
         c->lay.xtiled = 1;
+        return MHH_OK; })());
+}
+
+int mhh_comm_disable_peers(mhh_ctx* ctx)
+{
+    if (!ctx) return MHH_E_INVALID;
+    // back to grouped ncclSend/ncclRecv for transposes and ghost rows (collective decision of the host: every rank calls it)
+    DISPATCH1(ctx, ([&]() -> int {
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        for (int r = 0; r < MAX_SLAB_RANKS; ++r)
+            if (c->peers.on && r != c->rank)
+            {
+                if (c->peers.x[r]) cudaIpcCloseMemHandle(c->peers.x[r]);
+                if (c->peers.y[r]) cudaIpcCloseMemHandle(c->peers.y[r]);
+            }
+        c->peers = PeerPtrs<TF>{};
+        c->lay.xtiled = 0;
+        if (c->phalo_south && c->phalo_south != c->phalo) cudaIpcCloseMemHandle(c->phalo_south);
+        if (c->phalo_north && c->phalo_north != c->phalo && c->phalo_north != c->phalo_south) cudaIpcCloseMemHandle(c->phalo_north);
+        c->phalo_south = nullptr; c->phalo_north = nullptr;
+        cudaGetLastError();
         return MHH_OK; })());
 }
 

@@ -77,7 +77,15 @@ class Context:
             allh = [torch.empty_like(mine) for _ in range(self.gd.npy)]
             dist.all_gather(allh, mine)
             flat = torch.cat(allh).cpu().tolist()
-            self.check(self.lib.mhh_comm_open_peers(self.h, (C.c_ubyte * len(flat))(*flat), len(flat)))
+            rc = self.lib.mhh_comm_open_peers(self.h, (C.c_ubyte * len(flat))(*flat), len(flat))
+            # the transport is a collective property: if the mapping failed anywhere, every rank goes back to NCCL
+            ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                import warnings
+                warnings.warn("mhhb200: CUDA IPC peer mapping unavailable (%s); using NCCL transposes and halos"
+                              % self.lib.mhh_last_error(self.h).decode())
+                self.check(self.lib.mhh_comm_disable_peers(self.h))
 
     def use_torch_stream(self):
         s = torch.cuda.current_stream(self.device)
