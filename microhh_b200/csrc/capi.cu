@@ -1463,7 +1463,6 @@ int ghost4w_impl(Ctx<TF>* c, TF* w, int conservation)
 template <typename TF>
 int substep_o4_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, int substep, double dt)
 {
-    const GridDev<TF>& g = c->g;
     if (c->nranks > 1) { c->err = "the 4th-order sub-step is single-GPU in this version"; return MHH_E_INVALID; }
     if (prm->swthermo != 0) { c->err = "the 4th-order sub-step has no thermo coupling (swthermo = 0)"; return MHH_E_INVALID; }
     int rc = check_mom<TF>(c, f, false, false);
@@ -1489,7 +1488,6 @@ int substep_o4_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, int 
     for (int n = 0; n < f->ns; ++n) tend[3 + n] = P<TF>(f->st[n]);
     for (int n = 0; n < 3 + f->ns; ++n)
         if ((rc = rk3_impl<TF>(c, prog[n], tend[n], substep, dt)) != MHH_OK) return rc;
-    (void)g;
     return MHH_OK;
 }
 

@@ -393,8 +393,6 @@ __global__ void fft_x_backward_kernel(const TF* __restrict__ spec, TF* __restric
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int L = plan.n;
-    const int N = 2 * L;
-    const int nm = L + 1;
     const int ld = L + 1;
     cplx<TF>* buf0 = reinterpret_cast<cplx<TF>*>(smem_raw);
     cplx<TF>* buf1 = buf0 + rows_per_cta * ld;

@@ -65,7 +65,6 @@ __global__ void hdma_setup_kernel(TF* __restrict__ lu, const HdmaCoef<TF> cf, co
     if (col >= ncol) return;
     const int l = (int)(col / nm), mx = (int)(col % nm);
     const bool mode00 = (l == 0 && mx == 0);
-    const TF lam = cf.bmati[mx] + cf.bmatj[l];
     const int nr = kmax + 4;
     const long long rs = ncol;                          // row stride
     const long long bs = (long long)nr * ncol;          // band stride
@@ -94,7 +93,6 @@ __global__ void hdma_setup_kernel(TF* __restrict__ lu, const HdmaCoef<TF> cf, co
         }
         for (int n = 0; n < 7; ++n) A(n, r) = b[n];
     }
-    (void)lam;
     const TF one = TF(1.);
     // LU without pivoting, the reference's statement order
     A(0, 0) = one; A(1, 0) = one; A(2, 0) = one / A(3, 0); A(3, 0) = one;

@@ -542,7 +542,6 @@ __global__ void __launch_bounds__(TILE_X * TY, MB) evisc_tile_kernel(const Evisc
             for (int f = 0; f < 3; ++f) { stg.stage(sm + (f * RING + s3) * EPLANE, pl_src[f]); pl_src[f] += kk; }
         }
         cp_async_commit();
-        const int f = k + 1;
         const bool store = (k >= kc0) && active;
         const long long o_k = ij + (long long)k * kk;
         TF th_n = 0, n2v = 0;

@@ -41,8 +41,80 @@ def input_digest(case):
     return h.hexdigest()
 
 
+# 4th-order DNS configuration (advec_4 + diff_4 + pres_4 + 4th-order ghost cells) on a 4th-order grid
+CASES4 = {
+    "step4_16x12x10_f64": ((16, 12, 10), np.float64, 0),
+    "step4_24x1x8_f64": ((24, 1, 8), np.float64, 0),
+    "step4_20x12x8_freeslip_f32": ((20, 12, 8), np.float32, 1),
+}
+VISC4, DT4 = 1e-3, 0.01
+
+
+def make_case4(shape, dtype):
+    """Inputs of the 4th-order vectors: a synthetic.make_case field set on a stretched 4th-order grid, w = 0 at the walls,
+    a passive scalar, zero wall values / gradients."""
+    from util import stretched_z
+    from microhh_b200.grid import GridData
+    from microhh_b200.synthetic import make_case
+    it, jt, kt = shape
+    z = stretched_z(kt, 2.)
+    g = O.Grid(it, jt, kt, 6., 4., 2., 3, 3, 3, dtype, z=z, order=4)
+    gd = GridData(it, jt, kt, 6., 4., 2., 3, 3, 3, dtype, z=z, order=4)
+    case = make_case(gd, seed=5, noise=0.02)
+    case["w"][:g.kstart+1] = 0; case["w"][g.kend:] = 0
+    case["th"] = (1. + 0.1*case["u"]).astype(dtype)
+    if jt == 1:
+        case["v"][:] = 0
+    for n in ("u", "v"):
+        for sfx in ("_bot", "_top", "_gradbot", "_gradtop"):
+            case[n + sfx] = np.zeros(gd.shape2d, dtype)
+    case["th_gradbot"] = np.zeros(gd.shape2d, dtype); case["th_gradtop"] = np.zeros(gd.shape2d, dtype)
+    return g, gd, case
+
+
+def params4(mbc):
+    prm = ostep.default_params()
+    prm.update(swadvec="4", swdiff="4", visc=VISC4, svisc=VISC4, mbcbot=mbc, mbctop=mbc)
+    return prm
+
+
+def main4():
+    for name, (shape, dtype, mbc) in CASES4.items():
+        g, gd, case = make_case4(shape, dtype)
+        digest = input_digest4(case)
+        R = refbind.RefKernels(g)
+        out = {}
+        ck = copy.deepcopy(case)
+        for n in ("u", "v", "w", "th"):
+            R.boundary_cyclic(ck[n])
+        R.advec_4_u(ck["ut"], ck["u"], ck["v"], ck["w"]); R.advec_4_v(ck["vt"], ck["u"], ck["v"], ck["w"])
+        R.advec_4_w(ck["wt"], ck["u"], ck["v"], ck["w"]); R.advec_4_s(ck["tht"], ck["th"], ck["u"], ck["v"], ck["w"])
+        for n in ("ut", "vt", "wt", "tht"):
+            out["advec4_" + n] = ck[n].copy()
+        out["cfl4"] = np.float64(R.advec_4_cfl(ck["u"], ck["v"], ck["w"], DT))
+        R.diff_4_c(ck["ut"], ck["u"], VISC4); R.diff_4_c(ck["vt"], ck["v"], VISC4); R.diff_4_w(ck["wt"], ck["w"], VISC4)
+        R.diff_4_c(ck["tht"], ck["th"], VISC4)
+        for n in ("ut", "vt", "wt", "tht"):
+            out["advdiff4_" + n] = ck[n].copy()
+        cs = copy.deepcopy(case)
+        ostep.dycore_step(g, refbind.RefKernels(g), cs, params4(mbc), DT4)
+        for n in ("u", "v", "w", "th", "p"):
+            out["step_" + n] = cs[n].copy()
+        np.savez_compressed(os.path.join(HERE, "golden", name + ".npz"), input_sha256=np.array(digest), shape=np.array(shape),
+                            mbc=np.array(mbc), dt=np.array(DT4), **out)
+        print(name, digest[:12])
+
+
+def input_digest4(case):
+    h = hashlib.sha256()
+    for n in ("u", "v", "w", "th"):
+        h.update(np.ascontiguousarray(case[n]).tobytes())
+    return h.hexdigest()
+
+
 def main():
     assert refbind.available(), "build oracle/_ref first (make -C oracle)"
+    main4()
     for name, (shape, dtype, anel, stretched, nsteps) in CASES.items():
         g, gd, case = make_pair(*shape, dtype, stretched=stretched, anelastic=anel)
         digest = input_digest(case)

@@ -12,10 +12,11 @@ import numpy as np
 import pytest
 
 from util import TOL, rel_l2, make_pair, prepare_halos, interior
-from make_golden import VISC2, SVISC2, input_digest
+from make_golden import VISC2, SVISC2, input_digest, make_case4, params4, input_digest4, VISC4, DT
 from oracle import oracle as O, step as ostep
 
-GOLD = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz")))
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "step_*.npz")))
+GOLD4 = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "step4_*.npz")))
 
 
 def load(path):
@@ -139,3 +140,74 @@ def test_cuda_matches_golden(path):
     ctx.sync()
     for n in ("u", "v", "w", "th"):
         assert rel_l2(interior(g, f2[n].cpu().numpy()), interior(g, z["step_" + n])) <= TOL[dtype], n
+
+
+# ---- 4th-order DNS configuration (advec_4 + diff_4 + pres_4 + 4th-order ghost cells) -----------------------------
+def load4(path):
+    z = np.load(path)
+    dtype = np.float32 if path.endswith("_f32.npz") else np.float64
+    g, gd, case = make_case4(tuple(int(x) for x in z["shape"]), dtype)
+    assert input_digest4(case) == str(z["input_sha256"]), "synthetic input generator drifted from the golden inputs"
+    return z, dtype, g, gd, case
+
+
+def test_golden4_present():
+    assert len(GOLD4) >= 3
+
+
+@pytest.mark.parametrize("path", GOLD4, ids=[os.path.basename(p)[:-4] for p in GOLD4])
+def test_oracle_reproduces_golden4_bitexact(path):
+    z, dtype, g, gd, case = load4(path)
+    K = O.NumpyKernels(g)
+    ck = copy.deepcopy(case)
+    for n in ("u", "v", "w", "th"):
+        K.boundary_cyclic(ck[n])
+    K.advec_4_u(ck["ut"], ck["u"], ck["v"], ck["w"]); K.advec_4_v(ck["vt"], ck["u"], ck["v"], ck["w"])
+    K.advec_4_w(ck["wt"], ck["u"], ck["v"], ck["w"]); K.advec_4_s(ck["tht"], ck["th"], ck["u"], ck["v"], ck["w"])
+    for n in ("ut", "vt", "wt", "tht"):
+        assert np.array_equal(ck[n], z["advec4_" + n]), n
+    assert K.advec_4_cfl(ck["u"], ck["v"], ck["w"], DT) == float(z["cfl4"])
+    K.diff_4_c(ck["ut"], ck["u"], VISC4); K.diff_4_c(ck["vt"], ck["v"], VISC4); K.diff_4_w(ck["wt"], ck["w"], VISC4)
+    K.diff_4_c(ck["tht"], ck["th"], VISC4)
+    for n in ("ut", "vt", "wt", "tht"):
+        assert np.array_equal(ck[n], z["advdiff4_" + n]), n
+    cs = copy.deepcopy(case)
+    ostep.dycore_step(g, K, cs, params4(int(z["mbc"])), float(z["dt"]))
+    for n in ("u", "v", "w", "th", "p"):
+        assert np.array_equal(interior(g, cs[n]), interior(g, z["step_" + n])), n
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", GOLD4, ids=[os.path.basename(p)[:-4] for p in GOLD4])
+def test_cuda_matches_golden4(path):
+    from microhh_b200 import dycore as D
+    z, dtype, g, gd, case = load4(path)
+    ctx = D.Context(gd, 0)
+    ones = np.ones(gd.kcells, dtype)
+    ctx.set_basestate(ones, ones, 300*ones, 300*ones)
+    ck = copy.deepcopy(case)
+    for n in ("u", "v", "w", "th"):
+        O.boundary_cyclic(g, ck[n])
+    f = D.Fields(ctx, ck, visc=VISC4, svisc=VISC4)
+    D.Advec(ctx, "4").exec(f)
+    two_d = g.jtot == 1
+    for n in ("ut", "vt", "wt", "tht"):
+        if two_d and n == "vt":
+            continue
+        k0 = g.kstart + 1 if n == "wt" else g.kstart
+        assert rel_l2(interior(g, f[n].cpu().numpy(), k0), interior(g, z["advec4_" + n], k0)) <= TOL[dtype], n
+    cfl = D.Advec(ctx, "4").get_cfl(f, DT)
+    assert abs(cfl - float(z["cfl4"])) <= 10*TOL[dtype]*float(z["cfl4"])
+    D.Diff_4(ctx).exec(f)
+    for n in ("ut", "vt", "wt", "tht"):
+        if two_d and n == "vt":
+            continue
+        k0 = g.kstart + 1 if n == "wt" else g.kstart
+        assert rel_l2(interior(g, f[n].cpu().numpy(), k0), interior(g, z["advdiff4_" + n], k0)) <= TOL[dtype], n
+    mbc = int(z["mbc"])
+    f2 = D.Fields(ctx, case, visc=VISC4, svisc=VISC4)
+    prm = D.make_params(swadvec="4", swdiff="4", swthermo=None, surface_model=False, mbcbot=mbc, mbctop=mbc)
+    D.Dycore(ctx, prm).step(f2, float(z["dt"]))
+    ctx.sync()
+    for n in (("u", "w", "th") if two_d else ("u", "v", "w", "th")):
+        assert rel_l2(interior(g, f2[n].cpu().numpy()), interior(g, z["step_" + n])) <= 20*TOL[dtype], n
