@@ -163,3 +163,54 @@ def test_gloo_world2_slab_solve_matches_single_domain(shape):
     assert len(res) == 2
     for rank, err in res:
         assert err <= 1e-12, (rank, err)
+
+
+def _halo_worker(rank, world, port, out_q):
+    """Replays the slab ghost-row exchange (east-west local copy, then the first/last jgc interior rows over the full ghosted
+    width to the south/north neighbour) with gloo and compares with the single-domain cyclic fill."""
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import oracle as O
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        itot, jtot, ktot, gc = 12, 8*world, 5, 3
+        g = O.Grid(itot, jtot, ktot, 1., 1., 1., gc, gc, 1, np.float64)
+        a = np.random.default_rng(3).standard_normal((g.kcells, g.jcells, g.icells))
+        ref = a.copy()
+        O.boundary_cyclic(g, ref)
+        jmax = jtot//world
+        gl = O.Grid(itot, jmax, ktot, 1., 1., 1., gc, gc, 1, np.float64)          # the slab as a local grid
+        loc = np.ascontiguousarray(a[:, rank*jmax:rank*jmax + gl.jcells, :])     # ghost rows hold stale data
+        O.boundary_cyclic(gl, loc, O.EDGE_EW)                                    # east-west: local periodic copy
+        south, north = (rank - 1) % world, (rank + 1) % world
+        send_s = torch.from_numpy(np.ascontiguousarray(loc[:, gl.jstart:gl.jstart+gc, :]))      # -> south's north ghosts
+        send_n = torch.from_numpy(np.ascontiguousarray(loc[:, gl.jend-gc:gl.jend, :]))          # -> north's south ghosts
+        recv_n = torch.empty_like(send_s); recv_s = torch.empty_like(send_n)
+        reqs = [dist.isend(send_s, south, tag=1), dist.isend(send_n, north, tag=2),
+                dist.irecv(recv_n, north, tag=1), dist.irecv(recv_s, south, tag=2)]
+        for q in reqs:
+            q.wait()
+        loc[:, gl.jend:gl.jend+gc, :] = recv_n.numpy()
+        loc[:, 0:gc, :] = recv_s.numpy()
+        want = ref[:, rank*jmax:rank*jmax + gl.jcells, :]
+        out_q.put((rank, bool(np.array_equal(loc, want))))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gloo_slab_halo_exchange_equals_global_cyclic_fill(world):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_halo_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    res = [q.get() for _ in range(world)]
+    assert all(ok for _, ok in res), res
