@@ -100,6 +100,9 @@ typedef struct mhh_fields
     void *u_bot, *u_gradbot, *u_top, *u_gradtop;
     void *v_bot, *v_gradbot, *v_top, *v_gradtop;
     void *s_bot[MHH_MAX_SCALARS], *s_gradbot[MHH_MAX_SCALARS], *s_top[MHH_MAX_SCALARS], *s_gradtop[MHH_MAX_SCALARS];
+    /* != 0: the scalar is in [advec] fluxlimit_list -> Advec_2i5 advects it with the Koren (1993) flux limiter
+     * (include/advec_monotonic.h:98-202, src/advec_2i5.cxx:1046-1056) */
+    int   s_fluxlimit[MHH_MAX_SCALARS];
 } mhh_fields;
 
 /* Run-time switches of the path ([advec] [diff] [boundary] [thermo] of the .ini). */

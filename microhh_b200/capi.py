@@ -39,7 +39,8 @@ class FieldsC(C.Structure):
                 ("dudz_mo", _vp), ("dvdz_mo", _vp), ("dbdz_mo", _vp), ("z0m", _vp),
                 ("u_bot", _vp), ("u_gradbot", _vp), ("u_top", _vp), ("u_gradtop", _vp),
                 ("v_bot", _vp), ("v_gradbot", _vp), ("v_top", _vp), ("v_gradtop", _vp),
-                ("s_bot", _SA), ("s_gradbot", _SA), ("s_top", _SA), ("s_gradtop", _SA)]
+                ("s_bot", _SA), ("s_gradbot", _SA), ("s_top", _SA), ("s_gradtop", _SA),
+                ("s_fluxlimit", C.c_int * MHH_MAX_SCALARS)]
 
 
 class SlabInfo(C.Structure):

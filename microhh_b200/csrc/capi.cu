@@ -950,7 +950,7 @@ int tend_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, bool adv, 
             // scalar 0 rides along as the fourth warp group when its arrays qualify for TMA too
             ScalArgs<TF> s0{};
             // measured on B200 fp64 (512^3): 5.8 ms fused (3 rows, 13 warps) vs 4.3 + 2.9 ms as two kernels
-            bool fuse = f->ns > 0 && c->fuse_scalar;
+            bool fuse = f->ns > 0 && c->fuse_scalar && !f->s_fluxlimit[0];
             if (fuse) { s0 = scal_args<TF>(c, f, prm, 0); fuse = tma_ok<TF>(g, {s0.s, s0.st}); }
             rc = mom3_launch<TF>(c, a, fuse ? &s0 : nullptr, surface, buoy);
             if (fuse) first_scalar = 1;
@@ -972,6 +972,19 @@ int tend_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, bool adv, 
     for (int n = first_scalar; n < f->ns; ++n)
     {
         const ScalArgs<TF> s = scal_args<TF>(c, f, prm, n);
+        if (adv && f->s_fluxlimit[n])
+        {
+            // `fluxlimit_list` scalar (src/advec_2i5.cxx:1046-1056): Koren-limited advection, then the diffusion alone
+            advec_s_lim_kernel<TF><<<gr, b, 0, c->stream>>>(s.st, s.s, s.u, s.v, s.w, g);
+            KCHECKN(c, "advec_s_lim_kernel");
+            if (diff)
+            {
+                if (surface) tend_s_kernel<TF, false, true, true><<<gr, b, 0, c->stream>>>(s, g);
+                else tend_s_kernel<TF, false, true, false><<<gr, b, 0, c->stream>>>(s, g);
+                KCHECKN(c, "tend_s_kernel");
+            }
+            continue;
+        }
         if (tiles)
         {
             if ((rc = scal_tile_launch<TF>(c, s, surface)) != MHH_OK) return rc;

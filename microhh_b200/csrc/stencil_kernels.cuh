@@ -460,6 +460,65 @@ __global__ void __launch_bounds__(256) tend_s_kernel(const ScalArgs<TF> a, const
     a.st[ijk] += ts;
 }
 
+// ------------------------------------------------------------------------------------------
+// Flux-limited scalar advection (Koren 1993; reference include/advec_monotonic.h:28-202), used by Advec_2i5 for the
+// scalars of `fluxlimit_list` (src/advec_2i5.cxx:1046-1056).  VARIANT 0: flux_lim, 1: flux_lim_bot (first-order upwind
+// from below), 2: flux_lim_top (first-order upwind from above).  Faces kstart and kend carry no flux.
+// ------------------------------------------------------------------------------------------
+template <typename TF> __device__ __forceinline__ TF lim_eps();
+template <> __device__ __forceinline__ double lim_eps<double>() { return 2.220446049250313e-16; }
+template <> __device__ __forceinline__ float lim_eps<float>() { return 1.1920929e-07f; }
+template <typename TF> __device__ __forceinline__ TF maxf_(TF a, TF b) { return a > b ? a : b; }
+template <typename TF> __device__ __forceinline__ TF minf_(TF a, TF b) { return a < b ? a : b; }
+
+template <typename TF>
+__device__ __forceinline__ TF lim_branch(const TF vel, const TF a2, const TF a1, const TF b1)
+{
+    // vel*(a1 + phi/2 (a1 - a2)), phi = max(0, min(two_r, (1 + two_r)/3, 2)), two_r = 2 (b1 - a1) / guarded(a1 - a2)
+    const TF d = a1 - a2;
+    const TF mag = maxf_(absf(d), lim_eps<TF>());
+    const TF denom = (d < TF(0) || (d == TF(0) && signbit(d))) ? -mag : mag;          // copysign(1, d) * max(|d|, eps)
+    const TF two_r = TF(2.) * (b1 - a1) / denom;
+    const TF phi = maxf_(TF(0.), minf_(two_r, minf_(TF(1. / 3.) * (TF(1.) + two_r), TF(2.))));
+    return vel * (a1 + TF(0.5) * phi * (a1 - a2));
+}
+
+template <typename TF, int VARIANT>
+__device__ __forceinline__ TF flux_lim(const TF vel, const TF sm2, const TF sm1, const TF sp1, const TF sp2)
+{
+    if (vel >= TF(0.)) return VARIANT == 1 ? vel * sm1 : lim_branch<TF>(vel, sm2, sm1, sp1);
+    return VARIANT == 2 ? vel * sp1 : lim_branch<TF>(vel, sp2, sp1, sm1);
+}
+
+template <typename TF>
+__global__ void __launch_bounds__(256) advec_s_lim_kernel(TF* __restrict__ st, const TF* __restrict__ s,
+        const TF* __restrict__ u, const TF* __restrict__ v, const TF* __restrict__ w, const GridDev<TF> g)
+{
+    const int i = g.istart + blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = g.jstart + blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = g.kstart + blockIdx.z;
+    if (i >= g.iend || j >= g.jend) return;
+    const long long jj = g.icells, kk = g.ijcells;
+    const long long ijk = i + j * jj + k * kk;
+    const int ks = g.kstart, ke = g.kend;
+    const TF hx = (flux_lim<TF, 0>(u[ijk + 1], s[ijk - 1], s[ijk], s[ijk + 1], s[ijk + 2])
+                 - flux_lim<TF, 0>(u[ijk], s[ijk - 2], s[ijk - 1], s[ijk], s[ijk + 1])) * g.dxi;
+    const TF hy = (flux_lim<TF, 0>(v[ijk + jj], s[ijk - jj], s[ijk], s[ijk + jj], s[ijk + 2 * jj])
+                 - flux_lim<TF, 0>(v[ijk], s[ijk - 2 * jj], s[ijk - jj], s[ijk], s[ijk + jj])) * g.dyi;
+    // vertical face fluxes: face f lies below level f; variants next to the walls
+    auto face = [&](const int f, const long long o) -> TF {       // o = index of the cell above the face
+        const TF wv = w[o];
+        if (f == ks + 1) return flux_lim<TF, 1>(wv, s[o - 2 * kk], s[o - kk], s[o], s[o + kk]);
+        if (f == ke - 1) return flux_lim<TF, 2>(wv, s[o - 2 * kk], s[o - kk], s[o], s[o + kk]);
+        return flux_lim<TF, 0>(wv, s[o - 2 * kk], s[o - kk], s[o], s[o + kk]);
+    };
+    TF vert;
+    if (k == ks) vert = g.rhorefh[k + 1] * face(k + 1, ijk + kk);
+    else if (k == ke - 1) vert = -(g.rhorefh[k] * face(k, ijk));
+    else vert = g.rhorefh[k + 1] * face(k + 1, ijk + kk) - g.rhorefh[k] * face(k, ijk);
+    st[ijk] += -hx - hy - vert / g.rhoref[k] * g.dzi[k];
+}
+
 // thermo_dry buoyancy tendency on w (src/thermo_dry.cxx:165-179)
 template <typename TF>
 __global__ void buoyancy_kernel(TF* __restrict__ wt, const TF* __restrict__ th, const GridDev<TF> g)

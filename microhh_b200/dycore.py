@@ -134,8 +134,9 @@ class Context:
 class Fields:
     """Device fields in the reference's ghosted layout, as torch tensors (kcells, jcells, icells)."""
 
-    def __init__(self, ctx, case=None, scalars=("th",), visc=1.e-5, svisc=1.e-5):
+    def __init__(self, ctx, case=None, scalars=("th",), visc=1.e-5, svisc=1.e-5, fluxlimit_list=()):
         self.ctx = ctx
+        self.fluxlimit_list = tuple(fluxlimit_list)        # [advec] fluxlimit_list of the .ini
         gd = ctx.gd
         self.scalars = list(scalars)
         dev = torch.device("cuda", ctx.device)
@@ -181,6 +182,7 @@ class Fields:
         for i, s in enumerate(self.scalars):
             c.s[i] = self.t[s].data_ptr(); c.st[i] = self.t[s + "t"].data_ptr()
             c.svisc[i] = self.svisc
+            c.s_fluxlimit[i] = 1 if s in self.fluxlimit_list else 0
             c.s_fluxbot[i] = self.t[f"{s}_fluxbot"].data_ptr(); c.s_fluxtop[i] = self.t[f"{s}_fluxtop"].data_ptr()
             c.s_bot[i] = self.t[f"{s}_bot"].data_ptr(); c.s_gradbot[i] = self.t[f"{s}_gradbot"].data_ptr()
             c.s_top[i] = self.t[f"{s}_top"].data_ptr(); c.s_gradtop[i] = self.t[f"{s}_gradtop"].data_ptr()

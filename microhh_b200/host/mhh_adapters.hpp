@@ -109,7 +109,7 @@ namespace mhhb200
 
     // Device pointers of the Fields maps in the C ABI's POD (borrowed per call, never owned).
     template<typename TF>
-    mhh_fields fields_view(Fields<TF>& fields, Boundary<TF>* boundary=nullptr)
+    mhh_fields fields_view(Fields<TF>& fields, Boundary<TF>* boundary=nullptr, const std::vector<std::string>* fluxlimit_list=nullptr)
     {
         mhh_fields f{};
         f.u = fields.mp.at("u")->fld_g;   f.v = fields.mp.at("v")->fld_g;   f.w = fields.mp.at("w")->fld_g;
@@ -139,6 +139,8 @@ namespace mhhb200
             f.s_fluxbot[n] = s->flux_bot_g; f.s_fluxtop[n] = s->flux_top_g;
             f.s_bot[n] = s->fld_bot_g; f.s_gradbot[n] = s->grad_bot_g;
             f.s_top[n] = s->fld_top_g; f.s_gradtop[n] = s->grad_top_g;
+            if (fluxlimit_list)
+                for (const std::string& lim : *fluxlimit_list) if (lim == name) f.s_fluxlimit[n] = 1;
             ++n;
         }
         f.ns = n;
@@ -161,7 +163,8 @@ namespace mhhb200
             {
                 // ghost cells as the reference constructors ask for them (src/advec_2i5.cxx:42-45, src/advec_2.cxx:40-43,
                 // src/advec_4.cxx:41-48)
-                if (SW == 25) g.set_minimum_ghost_cells(3, 3, 1);
+                if (SW == 25) fluxlimit_list = in.get_list<std::string>("advec", "fluxlimit_list", "", std::vector<std::string>());   // src/advec_2i5.cxx:39-40
+                if (SW == 25) g.set_minimum_ghost_cells(3, 3, fluxlimit_list.empty() ? 1 : 2);                                        // :42-46
                 else if (SW == 2) g.set_minimum_ghost_cells(1, 1, 1);
                 else g.set_minimum_ghost_cells(3, 3, 3);
             }
@@ -169,7 +172,7 @@ namespace mhhb200
             void create(Stats<TF>&) override {}
             void exec(Stats<TF>&) override
             {
-                const mhh_fields f = fields_view(this->fields);
+                const mhh_fields f = fields_view(this->fields, static_cast<Boundary<TF>*>(nullptr), &fluxlimit_list);
                 MHH_CHECK(c->ctx, mhh_advec_exec(c->ctx, SW, &f));
             }
             double get_cfl(double dt) override
@@ -192,6 +195,7 @@ namespace mhhb200
 
         private:
             std::shared_ptr<Context<TF>> c;
+            std::vector<std::string> fluxlimit_list;
     };
     template<typename TF> using Advec_2i5_b200 = Advec_b200<TF, 25, Advection_type::Advec_2i5>;
     template<typename TF> using Advec_2_b200   = Advec_b200<TF, 2,  Advection_type::Advec_2>;

@@ -403,6 +403,54 @@ def advec_2i5_s(g, st, s, u, v, w, rhoref, rhorefh):
     # bit-identical to the "- ( rhorefh[k]*abs(w)*interp3 )" form of advec_u/v used above.
 
 
+# --------------------------------------------------------------------------------------
+# Flux-limited scalar advection (reference include/advec_monotonic.h:28-202): Koren (1993) limiter, used by Advec_2i5 for
+# the scalars in `fluxlimit_list` (src/advec_2i5.cxx:1046-1056).  Faces kstart / kend carry no flux; the first / last
+# interior face falls back to first-order upwind on its wall side (flux_lim_bot / flux_lim_top).
+# --------------------------------------------------------------------------------------
+def _flux_lim(u, sm2, sm1, sp1, sp2, variant=0):
+    """variant 0: flux_lim, 1: flux_lim_bot (u >= 0 -> u*sm1), 2: flux_lim_top (u < 0 -> u*sp1)"""
+    TF = u.dtype.type
+    eps = np.finfo(TF).eps
+    def limited(a2, a1, b1):
+        # u*(a1 + 0.5*phi*(a1 - a2)), phi from two_r = 2*(b1 - a1)/denom
+        d = a1 - a2
+        denom = (np.copysign(1., d) * np.maximum(np.abs(d), eps)).astype(TF)
+        two_r = TF(2.)*(b1 - a1)/denom
+        phi = np.maximum(TF(0.), np.minimum(two_r, np.minimum(TF(1./3.)*(TF(1.) + two_r), TF(2.))))
+        return u*(a1 + TF(0.5)*phi*(a1 - a2))
+    pos = u*sm1 if variant == 1 else limited(sm2, sm1, sp1)
+    neg = u*sp1 if variant == 2 else limited(sp2, sp1, sm1)
+    return np.where(u >= TF(0.), pos, neg)
+
+
+def advec_s_lim(g, st, s, u, v, w, rhoref, rhorefh):
+    """include/advec_monotonic.h:98-202"""
+    TF = g.TF
+    dxi, dyi = TF(1.)/g.dx, TF(1.)/g.dy
+    ks, ke = g.kstart, g.kend
+    def horiz(k0, k1):
+        S = lambda dj=0, di=0: _S(g, s, 0, dj, di, k0, k1)
+        U = lambda di=0: _S(g, u, 0, 0, di, k0, k1)
+        V = lambda dj=0: _S(g, v, 0, dj, 0, k0, k1)
+        return ( - ( _flux_lim(U(1), S(0, -1), S(), S(0, 1), S(0, 2)) - _flux_lim(U(0), S(0, -2), S(0, -1), S(), S(0, 1)) ) * dxi
+                 - ( _flux_lim(V(1), S(-1), S(), S(1), S(2)) - _flux_lim(V(0), S(-2), S(-1), S(), S(1)) ) * dyi )
+    def vface(k0, k1, up, variant):
+        # flux through the upper (up=1) or lower (up=0) face of rows k0..k1
+        Sk = lambda dk: _S(g, s, dk, 0, 0, k0, k1)
+        return _K(g, rhorefh, up, k0, k1) * _flux_lim(_S(g, w, up, 0, 0, k0, k1), Sk(up-2), Sk(up-1), Sk(up), Sk(up+1), variant)
+    def add(k0, k1, top, bot):
+        if k1 <= k0:
+            return
+        vert = (top - bot) if (top is not None and bot is not None) else (top if bot is None else -bot)
+        _S(g, st, 0, 0, 0, k0, k1)[...] += horiz(k0, k1) - (vert) / _K(g, rhoref, 0, k0, k1) * _K(g, g.dzi, 0, k0, k1)
+    add(ks+2, ke-2, vface(ks+2, ke-2, 1, 0), vface(ks+2, ke-2, 0, 0))
+    add(ks, ks+1, vface(ks, ks+1, 1, 1), None)
+    add(ks+1, ks+2, vface(ks+1, ks+2, 1, 0), vface(ks+1, ks+2, 0, 1))
+    add(ke-2, ke-1, vface(ke-2, ke-1, 1, 2), vface(ke-2, ke-1, 0, 0))
+    add(ke-1, ke, None, vface(ke-1, ke, 0, 2))
+
+
 def advec_2i5_w(g, wt, u, v, w, rhoref, rhorefh):
     """src/advec_2i5.cxx:453-579"""
     TF = g.TF
@@ -1429,6 +1477,7 @@ class NumpyKernels:
     def advec_2i5_w(self, wt, u, v, w, rhoref, rhorefh): advec_2i5_w(self.g, wt, u, v, w, rhoref, rhorefh)
     def advec_2i5_s(self, st, s, u, v, w, rhoref, rhorefh): advec_2i5_s(self.g, st, s, u, v, w, rhoref, rhorefh)
     def advec_2i5_cfl(self, u, v, w, dt): return float(advec_2i5_cfl(self.g, u, v, w, dt))
+    def advec_s_lim(self, st, s, u, v, w, rhoref, rhorefh): advec_s_lim(self.g, st, s, u, v, w, rhoref, rhorefh)
     def advec_2_u(self, ut, u, v, w, rhoref, rhorefh): advec_2_u(self.g, ut, u, v, w, rhoref, rhorefh)
     def advec_2_v(self, vt, u, v, w, rhoref, rhorefh): advec_2_v(self.g, vt, u, v, w, rhoref, rhorefh)
     def advec_2_w(self, wt, u, v, w, rhoref, rhorefh): advec_2_w(self.g, wt, u, v, w, rhoref, rhorefh)

@@ -81,6 +81,9 @@ class RefKernels:
     def advec_2i5_s(self, st, s, u, v, w, rhoref, rhorefh):
         g = self.g; self._call("ref_advec_2i5_s", st, s, u, v, w, g.dzi, g.dx, g.dy, rhoref, rhorefh)
 
+    def advec_s_lim(self, st, s, u, v, w, rhoref, rhorefh):
+        g = self.g; self._call("ref_advec_s_lim", st, s, u, v, w, g.dzi, g.dx, g.dy, rhoref, rhorefh)
+
     def advec_2i5_cfl(self, u, v, w, dt):
         g = self.g
         return self._call("ref_advec_2i5_cfl", u, v, w, g.dzi, g.dx, g.dy, float(dt), restype=C.c_double)

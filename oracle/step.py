@@ -58,7 +58,10 @@ def dycore_substep(g, K, c, prm, substep, dt, pres=None, timers=None):
     A[1](c["vt"], c["u"], c["v"], c["w"], rr, rh)
     A[2](c["wt"], c["u"], c["v"], c["w"], rr, rh)
     for s in scal:
-        A[3](c[s + "t"], c[s], c["u"], c["v"], c["w"], rr, rh)
+        if swadvec == "2i5" and s in prm.get("fluxlimit_list", ()):
+            K.advec_s_lim(c[s + "t"], c[s], c["u"], c["v"], c["w"], rr, rh)      # src/advec_2i5.cxx:1046-1056
+        else:
+            A[3](c[s + "t"], c[s], c["u"], c["v"], c["w"], rr, rh)
     lap("advec")
     # diff.exec
     if swdiff == "2":

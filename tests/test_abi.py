@@ -42,7 +42,7 @@ def test_struct_sizes_match_header_layout():
     from microhh_b200 import capi
     assert C.sizeof(capi.GridDesc) == 9*4 + 4 + 3*8 + 6*8 + 4*4 + 2*8    # 9 ints (+pad), 3 doubles, 6 pointers, 4 ints, 2 pointers
     n = capi.MHH_MAX_SCALARS
-    assert C.sizeof(capi.FieldsC) == 8*8 + 8 + 2*n*8 + n*8 + 8 + 4*8 + 2*n*8 + 4*8 + 8*8 + 4*n*8
+    assert C.sizeof(capi.FieldsC) == 8*8 + 8 + 2*n*8 + n*8 + 8 + 4*8 + 2*n*8 + 4*8 + 8*8 + 4*n*8 + n*4
     assert C.sizeof(capi.ParamsC) == 5*4 + 4 + 2*8 + 2*4 + 2*n*4
 
 

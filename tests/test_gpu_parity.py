@@ -314,6 +314,36 @@ def test_full_rk3_step_order4(dtype, shape, mbc):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(32, 16, 12), (20, 12, 8), (16, 1, 16)])
+def test_advec_s_lim_and_fluxlimit_step(dtype, shape):
+    """Koren-limited scalar advection (include/advec_monotonic.h:98-202) for a scalar in fluxlimit_list: the kernel through
+    Advec::exec, and a full RK3 step in which the limited scalar bypasses the fused tendency kernel."""
+    g, gd, case = make_pair(*shape, dtype, stretched=True, anelastic=True, ns=2)
+    rng = np.random.default_rng(9)
+    case["s1"] = (case["s1"] + 0.5*rng.standard_normal(gd.shape)).astype(dtype)          # rough enough for every limiter branch
+    halo = copy.deepcopy(case); prepare_halos(g, halo)
+    from microhh_b200 import dycore as D
+    ctx = D.Context(gd, 0)
+    ctx.set_basestate(case["rhoref"], case["rhorefh"], case["thref"], case["threfh"])
+    f = D.Fields(ctx, halo, scalars=case["scalars"], fluxlimit_list=("s1",))
+    D.Advec(ctx, "2i5").exec(f)
+    rr, rh = case["rhoref"], case["rhorefh"]
+    ref = {n: g.field() for n in ("tht", "s1t")}
+    O.advec_2i5_s(g, ref["tht"], halo["th"], halo["u"], halo["v"], halo["w"], rr, rh)
+    O.advec_s_lim(g, ref["s1t"], halo["s1"], halo["u"], halo["v"], halo["w"], rr, rh)
+    for n in ref:
+        assert rel_l2(f[n].cpu().numpy(), ref[n]) <= TOL[dtype], n
+    # full step: th fused in the momentum kernel, s1 limited
+    f2 = D.Fields(ctx, case, scalars=case["scalars"], fluxlimit_list=("s1",))
+    D.Dycore(ctx, D.make_params(ns=2)).step(f2, 2.0)
+    oprm = ostep.default_params(); oprm.update(fluxlimit_list=("s1",))
+    ostep.dycore_step(g, O.NumpyKernels(g), case, oprm, 2.0)
+    ctx.sync()
+    for n in ("u", "v", "w", "th", "s1"):
+        assert rel_l2(interior(g, f2[n].cpu().numpy()), interior(g, case[n])) <= 5*TOL[dtype], n
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 def test_thermo_dry_buoyancy(dtype):
     g, gd, case = make_pair(32, 16, 12, dtype)
     prepare_halos(g, case)

@@ -50,6 +50,10 @@ def test_kernels_bitexact(dtype, shape, anel, stretched):
     pair("advec_v", ["vt"], lambda K, c: K.advec_2i5_v(c["vt"], c["u"], c["v"], c["w"], rr, rh))
     pair("advec_w", ["wt"], lambda K, c: K.advec_2i5_w(c["wt"], c["u"], c["v"], c["w"], rr, rh))
     pair("advec_s", ["tht"], lambda K, c: K.advec_2i5_s(c["tht"], c["th"], c["u"], c["v"], c["w"], rr, rh))
+    pair("advec_s_lim", ["tht"], lambda K, c: K.advec_s_lim(c["tht"], c["th"], c["u"], c["v"], c["w"], rr, rh))
+    rough = np.random.default_rng(5).standard_normal(gd.shape).astype(dtype)       # every branch of the limiter
+    rough[:, ::3, ::2] = rough[:, 1::3, ::2][:, :rough[:, ::3, ::2].shape[1]] if shape[1] > 3 else 0.   # and exact ties (denominator guard)
+    pair("advec_s_lim_rough", ["tht"], lambda K, c: K.advec_s_lim(c["tht"], rough, c["u"], c["v"], c["w"], rr, rh))
     # Advec_2 / Diff_2 (reference src/advec_2.cxx, src/diff_2.cxx)
     pair("advec_2_u", ["ut"], lambda K, c: K.advec_2_u(c["ut"], c["u"], c["v"], c["w"], rr, rh))
     pair("advec_2_v", ["vt"], lambda K, c: K.advec_2_v(c["vt"], c["u"], c["v"], c["w"], rr, rh))
@@ -148,6 +152,22 @@ def test_order4_kernels_bitexact(dtype, shape, stretched):
         assert np.array_equal(res[0][0][n], res[1][0][n]), (n, float(np.abs(res[0][0][n].astype(np.float64) - res[1][0][n]).max()))
         assert not np.array_equal(res[0][0][n], t0[n])
     assert res[0][1] == res[1][1]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_full_rk3_step_fluxlimit_bitexact(dtype):
+    """LES step with the second scalar in [advec] fluxlimit_list (Koren-limited advection, src/advec_2i5.cxx:1046-1056)."""
+    g, gd, case = make_pair(20, 12, 10, dtype, stretched=True, anelastic=True, ns=2)
+    c0, c1 = copy.deepcopy(case), copy.deepcopy(case)
+    N, R = both(g)
+    prm = ostep.default_params(); prm.update(fluxlimit_list=("s1",))
+    ostep.dycore_step(g, N, c0, prm, 2.0)
+    ostep.dycore_step(g, R, c1, prm, 2.0)
+    for n in ("u", "v", "w", "th", "s1"):
+        assert np.array_equal(c0[n], c1[n]), n
+    c2 = copy.deepcopy(case)
+    ostep.dycore_step(g, N, c2, ostep.default_params(), 2.0)
+    assert not np.array_equal(c0["s1"], c2["s1"])          # the limiter does change the scalar
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
