@@ -641,7 +641,9 @@ int evisc_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, const TF*
     EviscArgs<TF> a{};
     a.evisc = P<TF>(f->evisc); a.u = P<TF>(f->u); a.v = P<TF>(f->v); a.w = P<TF>(f->w);
     a.n2 = n2; a.th = nullptr;
-    if (!n2)
+    // Thermo_type::Disabled (src/diff_smag2.cxx:507-545): no stability correction, calc_evisc_neutral
+    const bool neutral = !n2 && prm->swthermo == 0;
+    if (!n2 && !neutral)
     {
         if (f->ns < 1 || !f->s[0]) { c->err = "exec_viscosity: no N2 field and no scalar 0 (th) to derive it from"; return MHH_E_INVALID; }
         a.th = P<TF>(f->s[0]);
@@ -651,10 +653,16 @@ int evisc_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, const TF*
     a.cs = (TF)prm->cs; a.tPr = (TF)prm->tPr;
     if (a.surface)
     {
-        NEED(c, f->dudz_mo, "dudz_mo"); NEED(c, f->dvdz_mo, "dvdz_mo"); NEED(c, f->dbdz_mo, "dbdz_mo"); NEED(c, f->z0m, "z0m");
+        NEED(c, f->dudz_mo, "dudz_mo"); NEED(c, f->dvdz_mo, "dvdz_mo"); NEED(c, f->z0m, "z0m");
+        if (!neutral) NEED(c, f->dbdz_mo, "dbdz_mo");
         a.dudz = P<TF>(f->dudz_mo); a.dvdz = P<TF>(f->dvdz_mo); a.dbdz = P<TF>(f->dbdz_mo); a.z0m = P<TF>(f->z0m);
     }
-    if (!c->force_plain)
+    if (neutral)
+    {
+        evisc_neutral_kernel<TF><<<c->grd_interior(), c->blk(), 0, c->stream>>>(a, g, c->d_mlen0, (TF)f->visc);
+        KCHECKN(c, "evisc_neutral_kernel");
+    }
+    else if (!c->force_plain)
     {
         const int ty = c->tile_y;
         const int ntx = (g.imax + TILE_X - 1) / TILE_X, nty = (g.jmax + ty - 1) / ty;

@@ -205,6 +205,44 @@ __global__ void evisc_kernel(const EviscArgs<TF> a, const GridDev<TF> g, const T
     a.evisc[ijk] = m2 * sqrtf_(s2) * sqrtf_(TF(1.) - rit);
 }
 
+// Neutral eddy viscosity (no thermo; reference calc_evisc_neutral, src/diff_smag2.cxx:47-146): K = mlen^2 sqrt(S^2).
+// Surface model: Mason wall correction with n = 1, mlen = 1 / (1/mlen0 + 1/(kappa (z + z0m))).  Resolved walls: van Driest
+// damping, mlen = fac * mlen0 with fac = min over both walls of 1 - exp(-(distance * u_tau) / (26 nu)),
+// u_tau = |nu dU/dz at the wall|^(1/2).
+template <typename TF> __device__ __forceinline__ TF expf_(TF a);
+template <> __device__ __forceinline__ double expf_<double>(double a) { return exp(a); }
+template <> __device__ __forceinline__ float expf_<float>(float a) { return expf(a); }
+
+template <typename TF>
+__global__ void evisc_neutral_kernel(const EviscArgs<TF> a, const GridDev<TF> g, const TF* __restrict__ mlen0, const TF visc)
+{
+    const int i = g.istart + blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = g.jstart + blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = g.kstart + blockIdx.z;
+    if (i >= g.iend || j >= g.jend) return;
+    const long long jj = g.icells, kk = g.ijcells;
+    const long long ij = i + j * jj;
+    const long long ijk = ij + k * kk;
+    const bool bottom_mo = a.surface && (k == g.kstart);
+    const TF s2 = strain2_point<TF>(a.u, a.v, a.w, ijk, 1, jj, kk, g.dxi, g.dyi, g.dzi[k], g.dzhi[k], g.dzhi[k + 1],
+                                    bottom_mo, bottom_mo ? a.dudz[ij] : TF(0), bottom_mo ? a.dvdz[ij] : TF(0));
+    const TF ml0 = a.cs * mlen0[k];
+    TF mlen;
+    if (a.surface)
+        mlen = a.mason ? TF(1.) / (TF(1.) / ml0 + TF(1.) / (TF(KAPPA) * (g.z[k] + a.z0m[ij]))) : ml0;
+    else
+    {
+        const long long ib = ij + g.kstart * kk, it = ij + g.kend * kk;
+        const TF tb = pow2(visc * (a.u[ib] - a.u[ib - kk]) * g.dzhi[g.kstart]) + pow2(visc * (a.v[ib] - a.v[ib - kk]) * g.dzhi[g.kstart]);
+        const TF tt = pow2(visc * (a.u[it] - a.u[it - kk]) * g.dzhi[g.kend]) + pow2(visc * (a.v[it] - a.v[it - kk]) * g.dzhi[g.kend]);
+        const TF utau_b = sqrtf_(sqrtf_(tb)), utau_t = sqrtf_(sqrtf_(tt));          // pow(x, 1/4)
+        const TF fac_b = TF(1.) - expf_<TF>(-(g.z[k] * utau_b) / (TF(26.) * visc));
+        const TF fac_t = TF(1.) - expf_<TF>(-((g.zsize - g.z[k]) * utau_t) / (TF(26.) * visc));
+        mlen = (fac_b < fac_t ? fac_b : fac_t) * ml0;
+    }
+    a.evisc[ijk] = mlen * mlen * sqrtf_(s2);
+}
+
 // Resolved-wall variant: mirror evisc over bottom and top walls (src/diff_smag2.cxx:195-207).
 template <typename TF>
 __global__ void evisc_mirror_kernel(TF* __restrict__ evisc, const GridDev<TF> g)

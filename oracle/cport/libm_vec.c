@@ -6,3 +6,6 @@
 #define EXPORT __attribute__((visibility("default")))
 EXPORT void vpow_f64(const double* x, double y, double* out, long n) { for (long i = 0; i < n; ++i) out[i] = pow(x[i], y); }
 EXPORT void vpow_f32(const float* x, float y, float* out, long n) { for (long i = 0; i < n; ++i) out[i] = powf(x[i], y); }
+/* std::exp for calc_evisc_neutral's van Driest damping (reference src/diff_smag2.cxx:99-100) */
+EXPORT void vexp_f64(const double* x, double* out, long n) { for (long i = 0; i < n; ++i) out[i] = exp(x[i]); }
+EXPORT void vexp_f32(const float* x, float* out, long n) { for (long i = 0; i < n; ++i) out[i] = expf(x[i]); }

@@ -834,6 +834,18 @@ DSMALL = 1.e-9   # Constants::dsmall (reference include/constants.h)
 KAPPA = 0.4      # Constants::kappa
 GRAV = 9.81      # Constants::grav
 
+def _libm_exp(x):
+    """std::exp(TF) through the C library (see _libm_pow)"""
+    import ctypes
+    x = np.ascontiguousarray(x)
+    if _CPORT is None or not hasattr(_CPORT, "vexp_f64") or x.dtype not in (np.float64, np.float32):
+        return np.exp(x)
+    out = np.empty_like(x)
+    fn = _CPORT.vexp_f64 if x.dtype == np.float64 else _CPORT.vexp_f32
+    fn(x.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p), ctypes.c_long(x.size))
+    return out
+
+
 def _pow2(a):
     return a*a
 
@@ -942,6 +954,42 @@ def diff_evisc(g, evisc, N2, bgradbot, z0m, cs, tPr, surface, mason=True):
         rit = _S(g, N2, 0, 0, 0, k0, k1) / ev / tPr
         rit = np.minimum(rit, one_m)
         ev[...] = _pow2(mlen_of(k0, k1)) * np.sqrt(ev) * np.sqrt(TF(1.) - rit)
+    boundary_cyclic(g, evisc)
+
+
+def diff_evisc_neutral(g, evisc, u, v, w, z0m, cs, visc, surface, mason=True):
+    """src/diff_smag2.cxx:47-146: no stability correction (swthermo=0).  `evisc` holds strain2 on entry.  Surface model:
+    Mason wall correction with n = 1; resolved walls: van Driest damping from the wall shear of either wall, then the
+    mirror over the walls; ends with the cyclic fill."""
+    TF = g.TF
+    ks, ke = g.kstart, g.kend
+    third = TF(1./3.)
+    mlen0_k = (TF(cs)*_libm_pow((g.dx*g.dy*g.dz).astype(TF), third)).astype(TF)
+    ij = (slice(g.jstart, g.jend), slice(g.istart, g.iend))
+    ev = _S(g, evisc)
+    if not surface:
+        visc = TF(visc); A = TF(26.)
+        def u_tau(kw):
+            du = visc*(u[kw][ij] - u[kw-1][ij])*g.dzhi[kw]
+            dv = visc*(v[kw][ij] - v[kw-1][ij])*g.dzhi[kw]
+            return _libm_pow((_pow2(du) + _pow2(dv)).astype(TF), TF(0.25))
+        ut_bot, ut_top = u_tau(ks)[None, :, :], u_tau(ke)[None, :, :]
+        zk = _K(g, g.z)
+        fac_bot = TF(1.) - _libm_exp((-(zk*ut_bot) / (A*visc)).astype(TF))
+        fac_top = TF(1.) - _libm_exp((-((g.zsize - zk)*ut_top) / (A*visc)).astype(TF))
+        fac = np.minimum(fac_bot, fac_top)
+        ev[...] = _pow2(fac * _K(g, mlen0_k)) * np.sqrt(ev)
+        evisc[ks-1] = evisc[ks]
+        evisc[ke] = evisc[ke-1]
+    else:
+        if mason:
+            one = TF(1.)      # n_mason = 1: pow(x, 1) is exact, kept for the reference's expression structure
+            zz = (_K(g, g.z) + z0m[ij][None, :, :]).astype(TF)
+            m0 = _K(g, mlen0_k) + np.zeros_like(zz)
+            mlen = _libm_pow(one/(one/_libm_pow(m0, one) + one/(_libm_pow(TF(KAPPA)*zz, one))), one/one)
+        else:
+            mlen = _K(g, mlen0_k)
+        ev[...] = _pow2(mlen) * np.sqrt(ev)
     boundary_cyclic(g, evisc)
 
 
@@ -1494,6 +1542,7 @@ class NumpyKernels:
     def diff_2_w(self, wt, w, visc): diff_2_w(self.g, wt, w, visc)
     def diff_strain2(self, strain2, u, v, w, ugradbot, vgradbot, surface): diff_strain2(self.g, strain2, u, v, w, ugradbot, vgradbot, surface)
     def diff_evisc(self, evisc, u, v, w, N2, bgradbot, z0m, cs, tPr, surface, mason=True): diff_evisc(self.g, evisc, N2, bgradbot, z0m, cs, tPr, surface, mason)
+    def diff_evisc_neutral(self, evisc, u, v, w, z0m, cs, visc, surface, mason=True): diff_evisc_neutral(self.g, evisc, u, v, w, z0m, cs, visc, surface, mason)
     def diff_u(self, ut, u, v, w, evisc, fluxbot, fluxtop, rhoref, rhorefh, visc, surface): diff_u(self.g, ut, u, v, w, evisc, fluxbot, fluxtop, rhoref, rhorefh, visc, surface)
     def diff_v(self, vt, u, v, w, evisc, fluxbot, fluxtop, rhoref, rhorefh, visc, surface): diff_v(self.g, vt, u, v, w, evisc, fluxbot, fluxtop, rhoref, rhorefh, visc, surface)
     def diff_w(self, wt, u, v, w, evisc, rhoref, rhorefh, visc): diff_w(self.g, wt, u, v, w, evisc, rhoref, rhorefh, visc)

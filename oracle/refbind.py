@@ -146,6 +146,11 @@ class RefKernels:
         self._call("ref_diff_evisc", evisc, u, v, w, N2, bgradbot, g.z, g.dz, g.dzi, z0m, g.dx, g.dy,
                    float(cs), float(tPr), int(surface), int(mason))
 
+    def diff_evisc_neutral(self, evisc, u, v, w, z0m, cs, visc, surface, mason=True):
+        g = self.g
+        self._call("ref_diff_evisc_neutral", evisc, u, v, w, None, None, g.z, g.dz, g.dzhi, z0m, g.dx, g.dy, g.zsize,
+                   float(cs), float(visc), int(surface), int(mason))
+
     def diff_u(self, ut, u, v, w, evisc, fluxbot, fluxtop, rhoref, rhorefh, visc, surface):
         g = self.g; TF = g.TF
         self._call("ref_diff_u", ut, u, v, w, g.dzi, g.dzhi, TF(1./float(g.dx)), TF(1./float(g.dy)), evisc,

@@ -44,9 +44,13 @@ def dycore_substep(g, K, c, prm, substep, dt, pres=None, timers=None):
     # exec_viscosity (Diff_smag2 only; Diff_2::exec_viscosity is empty)
     if swdiff == "smag2":
         K.diff_strain2(c["evisc"], c["u"], c["v"], c["w"], c["dudz_mo"], c["dvdz_mo"], surface)
-        N2 = np.zeros_like(c["evisc"])
-        K.thermo_dry_N2(N2, c[scal[0]], c["thref"])
-        K.diff_evisc(c["evisc"], c["u"], c["v"], c["w"], N2, c["dbdz_mo"], c["z0m"], prm["cs"], prm["tPr"], surface, prm["sw_mason"])
+        if prm["swthermo"] == "dry":
+            N2 = np.zeros_like(c["evisc"])
+            K.thermo_dry_N2(N2, c[scal[0]], c["thref"])
+            K.diff_evisc(c["evisc"], c["u"], c["v"], c["w"], N2, c["dbdz_mo"], c["z0m"], prm["cs"], prm["tPr"], surface, prm["sw_mason"])
+        else:
+            # Thermo_type::Disabled (src/diff_smag2.cxx:507-545)
+            K.diff_evisc_neutral(c["evisc"], c["u"], c["v"], c["w"], c["z0m"], prm["cs"], prm["visc"], surface, prm["sw_mason"])
     lap("evisc")
     # thermo.exec
     if prm["swthermo"] == "dry":

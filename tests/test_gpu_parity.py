@@ -344,6 +344,36 @@ def test_advec_s_lim_and_fluxlimit_step(dtype, shape):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("surface,mason", [(True, True), (True, False), (False, True)])
+def test_evisc_neutral_and_neutral_step(dtype, surface, mason):
+    """Thermo_type::Disabled: calc_evisc_neutral (src/diff_smag2.cxx:47-146; Mason n = 1 with the surface model, van Driest
+    damping over resolved walls) and a full RK3 step without buoyancy."""
+    g, gd, case = make_pair(32, 24, 16, dtype, stretched=True, anelastic=True)
+    halo = copy.deepcopy(case); prepare_halos(g, halo)
+    from microhh_b200 import dycore as D
+    ctx = D.Context(gd, 0)
+    ctx.set_basestate(case["rhoref"], case["rhorefh"], case["thref"], case["threfh"])
+    visc = 1e-2
+    f = D.Fields(ctx, halo, visc=visc, svisc=visc)
+    prm = D.make_params(swthermo=None, surface_model=surface, sw_mason=mason)
+    D.Diff(ctx, prm).exec_viscosity(f)
+    ev = g.field()
+    O.diff_strain2(g, ev, halo["u"], halo["v"], halo["w"], halo["dudz_mo"], halo["dvdz_mo"], surface)
+    O.diff_evisc_neutral(g, ev, halo["u"], halo["v"], halo["w"], halo["z0m"], 0.23, visc, surface, mason)
+    k0 = g.kstart - (0 if surface else 1); k1 = g.kend + (0 if surface else 1)
+    assert rel_l2(f["evisc"].cpu().numpy()[k0:k1], ev[k0:k1]) <= 10*TOL[dtype]
+    if not surface:
+        return
+    f2 = D.Fields(ctx, case, visc=visc, svisc=visc)
+    D.Dycore(ctx, prm).step(f2, 2.0)
+    oprm = ostep.default_params(); oprm.update(swthermo=None, surface_model=surface, sw_mason=mason, visc=visc, svisc=visc)
+    ostep.dycore_step(g, O.NumpyKernels(g), case, oprm, 2.0)
+    ctx.sync()
+    for n in ("u", "v", "w", "th"):
+        assert rel_l2(interior(g, f2[n].cpu().numpy()), interior(g, case[n])) <= 5*TOL[dtype], n
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 def test_thermo_dry_buoyancy(dtype):
     g, gd, case = make_pair(32, 16, 12, dtype)
     prepare_halos(g, case)

@@ -77,6 +77,17 @@ def test_kernels_bitexact(dtype, shape, anel, stretched):
             K.diff_evisc(c["evisc"], c["u"], c["v"], c["w"], n2, c["dbdz_mo"], c["z0m"], 0.23, 1./3., surface, True)
             ev.append(c["evisc"])
         assert np.array_equal(ev[0], ev[1]), ("evisc", surface)
+        # neutral variant (no thermo): Mason with n = 1 (surface model) / van Driest damping (resolved walls)
+        for mason in (True, False):
+            evn = []
+            for K in (N, R):
+                c = copy.deepcopy(case)
+                c["evisc"] = np.zeros(gd.shape, dtype)
+                K.diff_strain2(c["evisc"], c["u"], c["v"], c["w"], c["dudz_mo"], c["dvdz_mo"], surface)
+                K.diff_evisc_neutral(c["evisc"], c["u"], c["v"], c["w"], c["z0m"], 0.23, 1e-2, surface, mason)
+                evn.append(c["evisc"])
+            assert np.array_equal(evn[0], evn[1]), ("evisc_neutral", surface, mason)
+            assert not np.array_equal(evn[0], ev[0])
         case_e = copy.deepcopy(case); case_e["evisc"] = ev[1]
         for nm, fn in (("diff_u", lambda K, c: K.diff_u(c["ut"], c["u"], c["v"], c["w"], c["evisc"], c["u_fluxbot"], c["u_fluxtop"], rr, rh, 1e-5, surface)),
                        ("diff_v", lambda K, c: K.diff_v(c["vt"], c["u"], c["v"], c["w"], c["evisc"], c["v_fluxbot"], c["v_fluxtop"], rr, rh, 1e-5, surface)),
@@ -152,6 +163,20 @@ def test_order4_kernels_bitexact(dtype, shape, stretched):
         assert np.array_equal(res[0][0][n], res[1][0][n]), (n, float(np.abs(res[0][0][n].astype(np.float64) - res[1][0][n]).max()))
         assert not np.array_equal(res[0][0][n], t0[n])
     assert res[0][1] == res[1][1]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("surface", [True, False])
+def test_full_rk3_step_neutral_bitexact(dtype, surface):
+    """LES step without thermo (swthermo=0): calc_evisc_neutral, no buoyancy."""
+    g, gd, case = make_pair(20, 12, 10, dtype, stretched=True, anelastic=True)
+    c0, c1 = copy.deepcopy(case), copy.deepcopy(case)
+    N, R = both(g)
+    prm = ostep.default_params(); prm.update(swthermo=None, surface_model=surface, visc=1e-2)
+    ostep.dycore_step(g, N, c0, prm, 2.0)
+    ostep.dycore_step(g, R, c1, prm, 2.0)
+    for n in ("u", "v", "w", "th", "evisc"):
+        assert np.array_equal(c0[n], c1[n]), n
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
