@@ -72,3 +72,36 @@ def test_product_does_not_import_oracle():
                 txt = open(os.path.join(dirpath, fn)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), fn
                 assert "oracle/" not in txt, fn
+
+
+def test_header_is_plain_c_and_links():
+    """include/mhhb200.h is the FFI boundary: it must compile as C99 (no C++ / torch types) and a C program calling the
+    GPU-free entry points must link against the library and run (slab layout query; a context cannot be created without a
+    CUDA device and must say so)."""
+    import subprocess
+    import tempfile
+    from microhh_b200 import capi
+    capi.load()
+    src = r"""
+#include <stdio.h>
+#include "mhhb200.h"
+int main(void)
+{
+    mhh_slab_info s;
+    if (mhh_slab_layout(1024, 1024, 1024, 8, 3, &s) != MHH_OK) return 1;
+    if (s.nm != 513 || s.jmax != 128 || s.mcl != 64 || s.m_off != 65 + 2*64) return 2;
+    if (mhh_slab_layout(1024, 1000, 8, 7, 0, &s) == MHH_OK) return 3;      /* jtot not divisible */
+    printf("%d %d %d\n", s.nm, s.mcl, s.m_off);
+    return 0;
+}
+"""
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "t.c"); exe = os.path.join(d, "t")
+        with open(c, "w") as fh:
+            fh.write(src)
+        libdir = os.path.dirname(capi.LIB_PATH)
+        r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", f"-I{ROOT}/include", c, "-o", exe,
+                            f"-L{libdir}", "-lmhhb200", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        r = subprocess.run([exe], capture_output=True, text=True)
+        assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
