@@ -226,7 +226,9 @@ def run_ours(args):
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": f"drycblles-shaped LES {itot}x{jtot}x{ktot_l} points per GPU, advec_2i5+diff_smag2+pres_2+thermo_dry, S=1",
                        "global_grid": f"{itot_g}x{jtot_g}x{ktot}",
-                       "parallelism": f"one domain in {world} y-slabs (npx=1, npy={world}): NCCL halo rows + all-to-all transposes" if world > 1 else "single GPU",
+                       "parallelism": (f"one domain in {world} y-slabs (npx=1, npy={world}); transposes and ghost rows: "
+                                       + ("stores of the FFT / pack kernels straight into peer memory over NVLink (CUDA IPC), 4-byte NCCL all-reduce as barrier"
+                                          if ctx.transport == "peer" else "grouped ncclSend/ncclRecv")) if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (each field >> 126 MB)", "dt": dt},
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "whole_step_roofline": whole, "cpu_baseline": cpu,

@@ -166,6 +166,8 @@ MHH_API int mhh_comm_open_peers(mhh_ctx* ctx, const void* all_handles, int nbyte
 /* Drop the peer mappings again and use NCCL transport (e.g. when mapping failed on some rank: the host decides
  * collectively and every rank calls this). */
 MHH_API int mhh_comm_disable_peers(mhh_ctx* ctx);
+/* 0 = single GPU / not connected, 1 = NCCL send/recv transposes and halos, 2 = fused NVLink peer stores */
+MHH_API int mhh_comm_transport(const mhh_ctx* ctx);
 
 /* Spectral workspace layout of the slab decomposition (pure host functions, no GPU needed): which
  * x-modes a rank owns after the forward transpose and where element (row, mode) / (k, j, mode) lives

@@ -74,6 +74,7 @@ SIGNATURES = {
     "mhh_comm_get_ipc_handles": (C.c_int, [_vp, _vp, C.c_int]),
     "mhh_comm_open_peers": (C.c_int, [_vp, _vp, C.c_int]),
     "mhh_comm_disable_peers": (C.c_int, [_vp]),
+    "mhh_comm_transport": (C.c_int, [_vp]),
     "mhh_slab_layout": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(SlabInfo)]),
     "mhh_slab_xindex": (C.c_longlong, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_int]),
     "mhh_slab_yindex": (C.c_longlong, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),

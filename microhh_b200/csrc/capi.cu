@@ -1786,6 +1786,13 @@ int mhh_comm_open_peers(mhh_ctx* ctx, const void* all, int nbytes)
         return MHH_OK; })());
 }
 
+int mhh_comm_transport(const mhh_ctx* ctx)
+{
+    if (!ctx || ctx->nranks == 1 || !ctx->comm) return 0;
+    if (ctx->dtype == MHH_F64) return static_cast<const Ctx<double>*>(ctx)->peers.on ? 2 : 1;
+    return static_cast<const Ctx<float>*>(ctx)->peers.on ? 2 : 1;
+}
+
 int mhh_comm_disable_peers(mhh_ctx* ctx)
 {
     if (!ctx) return MHH_E_INVALID;

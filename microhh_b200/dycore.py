@@ -116,6 +116,11 @@ class Context:
         return json.loads(out.value.decode())
 
     @property
+    def transport(self):
+        """'single', 'nccl' (grouped send/recv transposes and halos) or 'peer' (fused NVLink peer stores)"""
+        return ("single", "nccl", "peer")[int(self.lib.mhh_comm_transport(self.h))]
+
+    @property
     def workspace_bytes(self):
         return int(self.lib.mhh_workspace_bytes(self.h))
 
