@@ -1,0 +1,71 @@
+"""`.ini` case files stay unchanged: microhh_b200.case reads the reference's shipped cases with the reference's defaults
+(needs /root/reference; skipped on the GPU box) and maps them onto the hot path's switches."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from microhh_b200 import capi
+from microhh_b200.case import CaseConfig, read_ini
+
+REF = "/root/reference/cases"
+pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted")
+
+
+def case(name):
+    return CaseConfig.from_file(os.path.join(REF, name, name + ".ini"))
+
+
+def test_every_shipped_case_parses():
+    inis = [p for p in glob.glob(os.path.join(REF, "*", "*.ini"))
+            if os.path.basename(p)[:-4] == os.path.basename(os.path.dirname(p))]
+    assert len(inis) >= 20
+    for p in inis:
+        c = CaseConfig.from_file(p)
+        assert c.itot > 0 and c.ktot > 0 and c.order in ("2", "4")
+        assert isinstance(c.unsupported(), list)
+
+
+def test_drycblles_as_shipped():
+    """the shipped file has swadvec=2 (2i5 is a test permutation), smag2, thermo dry, surface model."""
+    c = case("drycblles")
+    assert (c.itot, c.jtot, c.ktot) == (128, 128, 128) and c.order == "2"
+    assert (c.swadvec, c.swdiff, c.swpres, c.swthermo) == ("2", "smag2", "2", "dry")
+    assert c.unsupported() == [] and c.scalars == ["th"]
+    p = c.make_params()
+    assert (p.swadvec, p.swdiff, p.swthermo, p.surface_model) == (2, 1, 1, 1)
+    assert (p.mbcbot, p.mbctop) == (capi.BC_DIRICHLET, capi.BC_NEUMANN)       # noslip / freeslip
+    assert p.sbcbot[0] == capi.BC_NEUMANN and p.sbctop[0] == capi.BC_NEUMANN    # flux / neumann
+    assert abs(c.dnmax - 0.3) < 1e-12 and abs(c.cflmax - 1.2) < 1e-12 and c.visc == 1e-5
+    gd = c.grid_data()
+    assert (gd.igc, gd.jgc, gd.kgc) == (1, 1, 1) and gd.icells == 130
+    c.ini["advec"]["swadvec"] = "2i5"                                            # the reference's test permutation
+    c2 = CaseConfig(c.ini)
+    assert c2.ghost_cells() == (3, 3, 1) and c2.make_params().swadvec == 25
+
+
+def test_defaults_follow_the_grid_order():
+    tg = case("taylorgreen")       # no [advec]/[diff]/[pres] switches: defaults = swspatialorder
+    assert (tg.order, tg.swadvec, tg.swdiff, tg.swpres, tg.swthermo) == ("2", "2", "2", "2", "0")
+    assert tg.jtot == 1 and tg.unsupported() == []
+    m5 = case("moser590")
+    assert (m5.order, m5.swadvec, m5.swdiff, m5.swpres) == ("4", "4", "4", "4") and m5.unsupported() == []
+    assert m5.ghost_cells() == (3, 3, 3) and m5.grid_data().order == 4
+    assert m5.make_params().swadvec == 4
+
+
+def test_out_of_path_switches_are_named():
+    assert case("moser180").unsupported() == ["swadvec=4m"]
+    assert "swthermo=moist" in case("bomex").unsupported()
+    assert "swthermo=buoy" in case("weakscaling").unsupported()
+    with pytest.raises(ValueError):
+        case("bomex").make_params()
+    assert case("andren1994").unsupported() == []                                # neutral LES: calc_evisc_neutral
+
+
+def test_ini_syntax(tmp_path):
+    p = tmp_path / "x.ini"
+    p.write_text("[grid]\nitot=8 # comment\n\n# full-line comment\njtot = 4\n[fields]\nrndamp[th]=0.1\n")
+    ini = read_ini(str(p))
+    assert ini["grid"] == {"itot": "8", "jtot": "4"} and ini["fields"]["rndamp[th]"] == "0.1"
