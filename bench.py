@@ -151,6 +151,20 @@ def run_ours(args):
     if rank == 0:
         sampler.stop_flag.set(); sampler.join(timeout=2)
     finite = bool(torch.isfinite(f["u"]).all().item())
+    # size-independent property at the full size: after the pressure correction the velocity is divergence-free to
+    # rounding (Pres_2::check_divergence on the cyclic-filled fields; relative to |u|max/dx)
+    post_div = None
+    try:
+        bc = D.Boundary_cyclic(ctx)
+        for n in ("u", "v", "w"):
+            bc.exec(f[n])
+        div = D.Pres(ctx).check_divergence(f)
+        umax = torch.tensor([float(f["u"].abs().max())], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(umax, op=dist.ReduceOp.MAX)
+        post_div = {"max_abs_divergence": div, "relative_to_umax_over_dx": div/(float(umax.item())/float(gd.dx))}
+    except Exception as ex:      # a diagnostic must never cost the bench line
+        post_div = {"error": str(ex)[:200]}
 
     # ---- end to end through the C ABI with HOST (pinned) buffers ------------------------------
     e2e = None
@@ -233,7 +247,7 @@ def run_ours(args):
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "whole_step_roofline": whole, "cpu_baseline": cpu,
             "kernels_ms_per_step": {k: v["ms"]/args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
-            "finite": finite}
+            "finite": finite, "post_step_divergence": post_div}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
