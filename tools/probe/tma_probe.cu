@@ -33,6 +33,9 @@ int main(int argc, char** argv)
 {
     int ic = atoi(argv[1]), jc = atoi(argv[2]), kc = atoi(argv[3]), bx = atoi(argv[4]), by = atoi(argv[5]);
     int x = atoi(argv[6]), y = atoi(argv[7]), z = atoi(argv[8]);
+    // optional 9th argument: element stride along x (2 = every other column: the even/odd de-interleaved planes planned
+    // for mom3, DESIGN.md "next steps"); the box then delivers ceil(bx / sx) elements per row
+    const int sx = argc > 9 ? atoi(argv[9]) : 1;
     void* p; cudaDriverEntryPointQueryResult q;
     cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
     auto enc = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
@@ -44,26 +47,27 @@ int main(int argc, char** argv)
     CUtensorMap tm;
     cuuint64_t dims[3] = {(cuuint64_t)ic, (cuuint64_t)jc, (cuuint64_t)kc};
     cuuint64_t str[2] = {(cuuint64_t)ic * 8, (cuuint64_t)ic * jc * 8};
-    cuuint32_t box[3] = {(cuuint32_t)bx, (cuuint32_t)by, 1}, es[3] = {1, 1, 1};
+    cuuint32_t box[3] = {(cuuint32_t)bx, (cuuint32_t)by, 1}, es[3] = {(cuuint32_t)sx, 1, 1};
+    const int nx = (bx + sx - 1) / sx;          // elements per row that land in shared memory
     CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, d, dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     printf("encode rc=%d  dims %d %d %d box %d %d at %d %d %d\n", (int)r, ic, jc, kc, bx, by, x, y, z);
     if (r != CUDA_SUCCESS) return 0;
-    size_t smem = 128 + (size_t)bx * by * 8;
+    size_t smem = 128 + (size_t)nx * by * 8;
     cudaFuncSetAttribute(probe<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    probe<0><<<1, 128, smem>>>(tm, o, bx * by, x, y, z);
+    probe<0><<<1, 128, smem>>>(tm, o, nx * by, x, y, z);
     cudaError_t e = cudaDeviceSynchronize();
     printf("  run: %s\n", cudaGetErrorString(e));
     if (e != cudaSuccess) return 0;
     std::vector<double> ho((size_t)bx * by);
     cudaMemcpy(ho.data(), o, ho.size() * 8, cudaMemcpyDeviceToHost);
     int bad = 0;
-    for (int jj = 0; jj < by; ++jj) for (int ii = 0; ii < bx; ++ii)
+    for (int jj = 0; jj < by; ++jj) for (int ii = 0; ii < nx; ++ii)
     {
-        int gi = x + ii, gj = y + jj;
+        int gi = x + ii * sx, gj = y + jj;
         double exp = (gi >= 0 && gi < ic && gj >= 0 && gj < jc && z >= 0 && z < kc) ? h[(size_t)gi + (size_t)gj * ic + (size_t)z * ic * jc] : 0.;
-        if (ho[(size_t)jj * bx + ii] != exp) ++bad;
+        if (ho[(size_t)jj * nx + ii] != exp) ++bad;
     }
-    printf("  mismatches: %d of %d\n", bad, bx * by);
+    printf("  mismatches: %d of %d (element stride %d)\n", bad, nx * by, sx);
     return 0;
 }
