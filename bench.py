@@ -68,7 +68,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append(parts)
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.02)
 
     def summary(self):
         if not self.samples:
