@@ -184,6 +184,9 @@ typedef struct mhh_slab_info
 } mhh_slab_info;
 MHH_API int mhh_slab_layout(int itot, int jtot, int ktot, int npy, int rank, mhh_slab_info* out);
 MHH_API long long mhh_slab_xindex(int itot, int jtot, int ktot, int npy, int rank, long long row, int m);
+/* x-side index in the 8-mode-panel layout used with the fused peer transposes (block d = [k][panel][jl][8]); *total
+ * receives the padded size of the x-side buffer in complex elements */
+MHH_API long long mhh_slab_xindex_tiled(int itot, int jtot, int ktot, int npy, int rank, long long row, int m, long long* total);
 MHH_API long long mhh_slab_yindex(int itot, int jtot, int ktot, int npy, int rank, int k, int j, int ml);
 
 /* ---- Boundary_cyclic<TF>::exec / exec_2d  (src/boundary_cyclic.cxx:369-507) ---------------- */

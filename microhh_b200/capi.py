@@ -77,6 +77,7 @@ SIGNATURES = {
     "mhh_comm_transport": (C.c_int, [_vp]),
     "mhh_slab_layout": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(SlabInfo)]),
     "mhh_slab_xindex": (C.c_longlong, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_int]),
+    "mhh_slab_xindex_tiled": (C.c_longlong, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_int, C.POINTER(C.c_longlong)]),
     "mhh_slab_yindex": (C.c_longlong, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "mhh_boundary_cyclic": (C.c_int, [_vp, _vp, C.c_int]),
     "mhh_boundary_cyclic_2d": (C.c_int, [_vp, _vp]),

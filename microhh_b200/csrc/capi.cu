@@ -1833,6 +1833,16 @@ long long mhh_slab_xindex(int itot, int jtot, int ktot, int npy, int rank, long 
     return l.xidx(row, m);
 }
 
+long long mhh_slab_xindex_tiled(int itot, int jtot, int ktot, int npy, int rank, long long row, int m, long long* total)
+{
+    if (npy < 1 || rank < 0 || rank >= npy || jtot % npy != 0 || itot / 2 + 1 < npy) return -1;
+    SpecLayout l = make_spec_layout(itot, jtot, ktot, npy, rank);
+    l.xtiled = 1;
+    if (total) *total = l.xside_elems();
+    if (row < 0 || row >= l.rows || m < 0 || m >= l.nm) return -1;
+    return l.xidx(row, m);
+}
+
 long long mhh_slab_yindex(int itot, int jtot, int ktot, int npy, int rank, int k, int j, int ml)
 {
     if (npy < 1 || rank < 0 || rank >= npy || jtot % npy != 0 || itot / 2 + 1 < npy) return -1;

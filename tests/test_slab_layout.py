@@ -214,3 +214,35 @@ def test_gloo_slab_halo_exchange_equals_global_cyclic_fill(world):
         assert p.exitcode == 0
     res = [q.get() for _ in range(world)]
     assert all(ok for _, ok in res), res
+
+
+@pytest.mark.parametrize("shape,P", [((16, 8, 3), 2), ((40, 12, 2), 4), ((36, 9, 2), 3)])
+def test_panel_tiled_x_side_is_injective_and_panel_contiguous(shape, P):
+    """The 8-mode-panel x-side layout of the fused peer transposes: injective into the padded buffer, the 8 modes of a panel
+    contiguous, consecutive local rows of a panel 8 elements apart (what makes the inverse y transform's remote stores long
+    contiguous runs), and every rank agrees on where block d starts."""
+    lib = capi.load()
+    itot, jtot, ktot = shape
+    nm = itot//2 + 1
+    infos = [slab_info(lib, itot, jtot, ktot, P, r) for r in range(P)]
+    for r in range(P):
+        s = infos[r]
+        tot = C.c_longlong()
+        idx = np.empty((s.rows, nm), np.int64)
+        for row in range(s.rows):
+            for m in range(nm):
+                idx[row, m] = lib.mhh_slab_xindex_tiled(itot, jtot, ktot, P, r, row, m, C.byref(tot))
+        assert idx.min() >= 0 and idx.max() < tot.value and len(np.unique(idx)) == idx.size
+        assert tot.value >= nm*s.rows and tot.value <= (nm + 8*P)*s.rows              # padding: < one panel per block
+        for d in range(P):
+            m0, cnt = infos[d].m_off, infos[d].mcl
+            for ml in range(cnt - 1):
+                if (ml & 7) != 7:
+                    assert np.all(idx[:, m0 + ml + 1] - idx[:, m0 + ml] == 1)          # inside a panel: contiguous modes
+            jmax = s.jmax
+            for k in range(ktot):
+                rows = np.arange(k*jmax, (k + 1)*jmax)
+                assert np.all(np.diff(idx[rows, m0]) == 8)                              # consecutive rows: next 128-byte line
+        if r > 0:
+            first = [lib.mhh_slab_xindex_tiled(itot, jtot, ktot, P, q, 0, infos[1].m_off, None) for q in (0, r)]
+            assert first[0] == first[1]
