@@ -241,6 +241,19 @@ MHH_API int mhh_timeloop_rk3(mhh_ctx* ctx, void* a, void* at, int substep, doubl
  * cyclic + vertical ghost cells -> eddy viscosity -> advection+diffusion(+buoyancy) tendencies ->
  * pressure solve -> pressure correction fused with the RK3 update of u,v,w and the scalars. */
 MHH_API int mhh_dycore_substep(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm, int substep, double dt);
+/* The same sub-step in stages, for a host that keeps running its own surface model (Boundary_surface::exec) at the point
+ * where Model::exec runs it (src/model.cxx:375-401: exec_viscosity -> thermo.exec -> boundary.exec -> set_ghost_cells ->
+ * advec.exec ...):
+ *   mhh_dycore_substep_pre        boundary.set_prognostic_cyclic_bcs + set_ghost_cells + diff.exec_viscosity
+ *   (host: boundary->exec updates dudz_mo / fluxbot / gradbot ...)
+ *   mhh_dycore_set_ghost_cells    boundary.set_ghost_cells of u, v and the scalars again (src/model.cxx:401)
+ *   mhh_dycore_substep_post       thermo.exec + advec.exec + diff.exec (fused), pres.exec, timeloop.exec
+ * mhh_dycore_substep == pre + post (the 2-D companions are then the caller's values for the whole sub-step).
+ * mhh_dycore_tendencies is the fused tendency stage of `post` alone (tests, profiling). LES configurations only. */
+MHH_API int mhh_dycore_substep_pre(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm);
+MHH_API int mhh_dycore_set_ghost_cells(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm);
+MHH_API int mhh_dycore_tendencies(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm);
+MHH_API int mhh_dycore_substep_post(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm, int substep, double dt);
 /* Three sub-steps. */
 MHH_API int mhh_dycore_step(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm, double dt);
 /* End-to-end variant with HOST buffers (ghosted layout): copies u,v,w and the scalars to the

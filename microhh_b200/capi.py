@@ -99,6 +99,10 @@ SIGNATURES = {
     "mhh_pres_fft_roundtrip": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "mhh_timeloop_rk3": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_double]),
     "mhh_dycore_substep": (C.c_int, [_vp, _PF, _PP, C.c_int, C.c_double]),
+    "mhh_dycore_substep_pre": (C.c_int, [_vp, _PF, _PP]),
+    "mhh_dycore_set_ghost_cells": (C.c_int, [_vp, _PF, _PP]),
+    "mhh_dycore_tendencies": (C.c_int, [_vp, _PF, _PP]),
+    "mhh_dycore_substep_post": (C.c_int, [_vp, _PF, _PP, C.c_int, C.c_double]),
     "mhh_dycore_step": (C.c_int, [_vp, _PF, _PP, C.c_double]),
     "mhh_dycore_step_host": (C.c_int, [_vp, _PF, _PP, C.c_double, C.c_int, _vp, _vp, _vp, C.POINTER(_vp)]),
 }

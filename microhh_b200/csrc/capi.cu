@@ -17,6 +17,7 @@
 #include "tile_kernels.cuh"
 #include "tile2_kernels.cuh"
 #include "tile3_kernels.cuh"
+#include "tile4_kernels.cuh"
 #include "slab_kernels.cuh"
 #include "order2_kernels.cuh"
 #include "order4_kernels.cuh"
@@ -45,7 +46,8 @@ struct mhh_ctx
     int tile3_y = 0;            // MHH_TILE3_Y: rows per CTA of the warp-specialised kernel; 0 = 3 rows with the scalar group (13 warps), 4 without
     int tile2_y = 6;            // MHH_TILE2_Y: rows (= warps) per CTA of the TMA tile kernels
     bool fuse_scalar = true;    // MHH_FUSE_SCALAR=0: keep scalar 0 out of the momentum kernel (A/B comparisons)
-    int mom_variant = 3;        // MHH_MOM=2|3: 2 = all components per thread, 3 = warp-specialised by component
+    int mom_variant = 4;        // MHH_MOM=2|3|4: 2 = all components per thread, 3 = warp-specialised by component, 4 = 3 with 2 x 2 register blocks (default)
+    int tile4_w = 3;            // MHH_TILE4_W=2|3: warps per component of mom4 (rows per CTA = 2x)
     int evisc_mb = 4;           // MHH_EVISC_MB=2|3|4 (measured 512^3 fp64: 2.72 | 2.51 | 2.11 ms): resident CTAs per SM the eddy-viscosity kernel is compiled for (register cap)
     int prefetch = 1;           // MHH_PREFETCH: L2 prefetch distance (levels) of the TMA tile kernels, 0 = off
     bool prof = false;
@@ -306,7 +308,8 @@ int create_impl(const mhh_grid_desc* d, int dtype, int device, mhh_ctx** out)
     { const char* e = getenv("MHH_NO_TMA"); c->no_tma = e && e[0] == '1'; }
     { const char* e = getenv("MHH_TILE2_Y"); if (e) { int v = atoi(e); if (v == 4 || v == 6 || v == 8 || v == 12) c->tile2_y = v; } }
     { const char* e = getenv("MHH_FUSE_SCALAR"); if (e) c->fuse_scalar = e[0] == '1'; }
-    { const char* e = getenv("MHH_MOM"); if (e && atoi(e) == 2) c->mom_variant = 2; }
+    { const char* e = getenv("MHH_MOM"); if (e && (atoi(e) == 2 || atoi(e) == 3)) c->mom_variant = atoi(e); }
+    { const char* e = getenv("MHH_TILE4_W"); if (e && (atoi(e) == 2 || atoi(e) == 3)) c->tile4_w = atoi(e); }
     { const char* e = getenv("MHH_TILE3_Y"); if (e) { int v = atoi(e); if (v == 3 || v == 4 || v == 5) c->tile3_y = v; } }
     { const char* e = getenv("MHH_EVISC_MB"); if (e) c->evisc_mb = atoi(e); }
     { const char* e = getenv("MHH_PREFETCH"); if (e) c->prefetch = std::max(0, std::min(8, atoi(e))); }
@@ -911,6 +914,54 @@ int mom3_launch(Ctx<TF>* c, const MomArgs<TF>& a, const ScalArgs<TF>* sc, bool s
     return MHH_OK;
 }
 
+// 2 x 2 register-blocked warp-specialised variant (tile4_kernels.cuh); fp64 and fp32
+template <typename TF>
+int mom4_launch(Ctx<TF>* c, const MomArgs<TF>& a, const ScalArgs<TF>* sc, bool surface, bool buoy)
+{
+    const GridDev<TF>& g = c->g;
+    const int nsc = sc ? 1 : 0;
+    const int tyw = c->tile4_w;
+    const int rows = 2 * tyw;
+    const int ntx = (g.imax + T4_W - 1) / T4_W, nty = (g.jmax + rows - 1) / rows;
+    Tend3Args<TF> t{};
+    t.m = a; if (sc) t.sc = *sc;
+    t.kchunk = pick_kchunk_waves(ntx * nty, g.kmax, c->num_sms, 2);
+    t.prefetch = c->prefetch;
+    dim3 grid(ntx, nty, (g.kmax + t.kchunk - 1) / t.kchunk);
+    const size_t smem = mom4_smem(sizeof(TF), t.kchunk, tyw, nsc);
+    CUtensorMap tu, tv, tw, te, ts, tut, tvt, twt, tst;
+    const int by = t4_rows(tyw);
+    if (!make_field_tmap<TF>(&tu, a.u, g, T4_PX, by) || !make_field_tmap<TF>(&tv, a.v, g, T4_PX, by) ||
+        !make_field_tmap<TF>(&tw, a.w, g, T4_PX, by) || !make_field_tmap<TF>(&te, a.evisc, g, T4_PX, by) ||
+        !make_field_tmap<TF>(&ts, sc ? (const void*)sc->s : (const void*)a.u, g, T4_PX, by) ||
+        !make_field_tmap<TF>(&tut, a.ut, g, T4_W + 4, rows) || !make_field_tmap<TF>(&tvt, a.vt, g, T4_W + 4, rows) ||
+        !make_field_tmap<TF>(&twt, a.wt, g, T4_W + 4, rows) || !make_field_tmap<TF>(&tst, sc ? (const void*)sc->st : (const void*)a.ut, g, T4_W + 4, rows))
+    { c->err = "cuTensorMapEncodeTiled failed"; return MHH_E_CUDA; }
+#define M4(S, B, N, W) do { \
+        static size_t attr_smem_dev[64] = {0}; size_t& attr_smem = attr_smem_dev[c->device & 63];   /* the attribute is per device */ \
+        if (attr_smem < smem) { CUDA_TRY(c, cudaFuncSetAttribute(mom4_kernel<TF, S, B, N, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; } \
+        mom4_kernel<TF, S, B, N, W><<<grid, 32 * ((3 + N) * W + 1), smem, c->stream>>>(tu, tv, tw, te, ts, tut, tvt, twt, tst, t, g); } while (0)
+#define M4W(S, B, N) do { if (tyw == 2) M4(S, B, N, 2); else M4(S, B, N, 3); } while (0)
+    if (nsc)
+    {
+        if (surface && buoy) M4W(true, true, 1);
+        else if (surface) M4W(true, false, 1);
+        else if (buoy) M4W(false, true, 1);
+        else M4W(false, false, 1);
+    }
+    else
+    {
+        if (surface && buoy) M4W(true, true, 0);
+        else if (surface) M4W(true, false, 0);
+        else if (buoy) M4W(false, true, 0);
+        else M4W(false, false, 0);
+    }
+#undef M4W
+#undef M4
+    KCHECKN(c, "mom4_kernel");
+    return MHH_OK;
+}
+
 template <typename TF>
 int scal_tile_launch(Ctx<TF>* c, const ScalArgs<TF>& a, bool surface)
 {
@@ -952,8 +1003,18 @@ int tend_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, bool adv, 
     int first_scalar = 0;       // scalars [0, first_scalar) were handled by the fused momentum kernel
     if (tiles)
     {
-        const bool tma = !c->no_tma && sizeof(TF) == 8 && tma_ok<TF>(g, {a.u, a.v, a.w, a.evisc, a.ut, a.vt, a.wt, buoy ? (const void*)a.th : (const void*)a.u});
-        if (tma && c->mom_variant == 3)
+        const bool tma_any = !c->no_tma && tma_ok<TF>(g, {a.u, a.v, a.w, a.evisc, a.ut, a.vt, a.wt, buoy ? (const void*)a.th : (const void*)a.u});
+        const bool tma = tma_any && sizeof(TF) == 8;          // mom2 / mom3 are fp64-only (odd-aligned 8-byte pairs)
+        if (tma_any && c->mom_variant == 4)
+        {
+            // fp64 and fp32 (USESP: needs a row pitch that is a multiple of 16 bytes, i.e. icells % 4 == 0 -- igc = 4)
+            ScalArgs<TF> s0{};
+            bool fuse = f->ns > 0 && c->fuse_scalar && !f->s_fluxlimit[0];
+            if (fuse) { s0 = scal_args<TF>(c, f, prm, 0); fuse = tma_ok<TF>(g, {s0.s, s0.st}); }
+            rc = mom4_launch<TF>(c, a, fuse ? &s0 : nullptr, surface, buoy);
+            if (fuse) first_scalar = 1;
+        }
+        else if (tma && c->mom_variant == 3)
         {
             // scalar 0 rides along as the fourth warp group when its arrays qualify for TMA too
             ScalArgs<TF> s0{};
@@ -1512,37 +1573,72 @@ int substep_o4_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, int 
     return MHH_OK;
 }
 
-// One fused sub-step (Model::exec order, src/model.cxx:356-504, restricted to the hot path).
+// One fused sub-step (Model::exec order, src/model.cxx:356-504, restricted to the hot path), in three stages so that a host
+// that keeps its own surface model can run it where the reference does (src/model.cxx:375-401: exec_viscosity ->
+// thermo.exec -> boundary.exec + set_ghost_cells -> advec.exec ...):
+//   pre  : boundary.set_prognostic_cyclic_bcs + set_ghost_cells, diff.exec_viscosity
+//   ghost: boundary.set_ghost_cells again (after the host's boundary.exec changed the 2-D companions)
+//   post : thermo.exec + advec.exec + diff.exec (fused), pres.exec, timeloop.exec
 template <typename TF>
-int substep_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, int substep, double dt)
+int substep_check(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, bool& o4)
 {
     NEED_BASE(c);
     NEED(c, prm, "params");
-    const GridDev<TF>& g = c->g;
-    if (substep < 0 || substep > 2) { c->err = "substep must be 0..2"; return MHH_E_INVALID; }
+    o4 = false;
     if (prm->swadvec == 4 || prm->swdiff == 4)
     {
         if (prm->swadvec != 4 || prm->swdiff != 4) { c->err = "dycore_substep: the 4th-order configuration is swadvec = 4 with swdiff = 4 (and pres_4)"; return MHH_E_INVALID; }
-        return substep_o4_impl<TF>(c, f, prm, substep, dt);
+        o4 = true;
+        return MHH_OK;
     }
     if ((prm->swadvec != 25 && prm->swadvec != 2) || (prm->swdiff != 1 && prm->swdiff != 2))
     { c->err = "dycore_substep: swadvec must be 2i5 (25), 2 or 4, swdiff smag2 (1), 2 or 4"; return MHH_E_INVALID; }
-    const bool smag = prm->swdiff == 1, adv5 = prm->swadvec == 25, buoy = prm->swthermo == 1;
+    const bool smag = prm->swdiff == 1;
     int rc = check_mom<TF>(c, f, smag, smag && prm->surface_model != 0);
     if (rc != MHH_OK) return rc;
     NEED(c, f->p, "p");
-    // 1. boundary.set_prognostic_cyclic_bcs + set_ghost_cells
-    TF* prog[3 + MHH_MAX_SCALARS] = {P<TF>(f->u), P<TF>(f->v), P<TF>(f->w)};
-    for (int n = 0; n < f->ns; ++n) prog[3 + n] = P<TF>(f->s[n]);
-    if ((rc = cyclic_fields<TF>(c, prog, 3 + f->ns)) != MHH_OK) return rc;
+    return MHH_OK;
+}
+
+// Boundary::set_ghost_cells of u, v and the scalars (2nd order)
+template <typename TF>
+int ghost_all_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm)
+{
+    int rc;
     if ((rc = ghost_impl<TF>(c, P<TF>(f->u), prm->mbcbot, P<TF>(f->u_bot), P<TF>(f->u_gradbot), prm->mbctop, P<TF>(f->u_top), P<TF>(f->u_gradtop))) != MHH_OK) return rc;
     if ((rc = ghost_impl<TF>(c, P<TF>(f->v), prm->mbcbot, P<TF>(f->v_bot), P<TF>(f->v_gradbot), prm->mbctop, P<TF>(f->v_top), P<TF>(f->v_gradtop))) != MHH_OK) return rc;
     for (int n = 0; n < f->ns; ++n)
         if ((rc = ghost_impl<TF>(c, P<TF>(f->s[n]), prm->sbcbot[n], P<TF>(f->s_bot[n]), P<TF>(f->s_gradbot[n]),
                                  prm->sbctop[n], P<TF>(f->s_top[n]), P<TF>(f->s_gradtop[n]))) != MHH_OK) return rc;
+    return MHH_OK;
+}
+
+template <typename TF>
+int substep_pre_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm)
+{
+    bool o4;
+    int rc = substep_check<TF>(c, f, prm, o4);
+    if (rc != MHH_OK) return rc;
+    if (o4) { c->err = "dycore_substep_pre/post: the 4th-order configuration has no surface model; use mhh_dycore_substep"; return MHH_E_INVALID; }
+    // 1. boundary.set_prognostic_cyclic_bcs + set_ghost_cells
+    TF* prog[3 + MHH_MAX_SCALARS] = {P<TF>(f->u), P<TF>(f->v), P<TF>(f->w)};
+    for (int n = 0; n < f->ns; ++n) prog[3 + n] = P<TF>(f->s[n]);
+    if ((rc = cyclic_fields<TF>(c, prog, 3 + f->ns)) != MHH_OK) return rc;
+    if ((rc = ghost_all_impl<TF>(c, f, prm)) != MHH_OK) return rc;
     // 2. diff.exec_viscosity
-    if (smag && (rc = evisc_impl<TF>(c, f, prm, nullptr)) != MHH_OK) return rc;
-    // 3. thermo.exec + advec.exec + diff.exec: one fused kernel per scheme family
+    if (prm->swdiff == 1 && (rc = evisc_impl<TF>(c, f, prm, nullptr)) != MHH_OK) return rc;
+    return MHH_OK;
+}
+
+// 3. thermo.exec + advec.exec + diff.exec: one fused kernel per scheme family
+template <typename TF>
+int tendencies_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm)
+{
+    bool o4;
+    int rc = substep_check<TF>(c, f, prm, o4);
+    if (rc != MHH_OK) return rc;
+    if (o4) { c->err = "dycore_tendencies: use mhh_advec_exec / mhh_diff_4_exec on a 4th-order grid (they see different w ghost cells)"; return MHH_E_INVALID; }
+    const bool smag = prm->swdiff == 1, adv5 = prm->swadvec == 25, buoy = prm->swthermo == 1;
     if (adv5 && smag) rc = tend_impl<TF>(c, f, prm, true, true, buoy);                       // 2i5 + smag2 (+ buoyancy)
     else if (!adv5 && !smag) rc = o2_impl<TF>(c, f, true, true, buoy);                       // 2 + 2 (+ buoyancy)
     else if (!adv5)                                                                          // 2 + smag2 (drycblles as shipped)
@@ -1556,6 +1652,15 @@ int substep_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, int sub
         if ((rc = tend_impl<TF>(c, f, prm, true, false, false)) != MHH_OK) return rc;
         rc = o2_impl<TF>(c, f, false, true, false);
     }
+    return rc;
+}
+
+template <typename TF>
+int substep_post_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, int substep, double dt)
+{
+    const GridDev<TF>& g = c->g;
+    if (substep < 0 || substep > 2) { c->err = "substep must be 0..2"; return MHH_E_INVALID; }
+    int rc = tendencies_impl<TF>(c, f, prm);
     if (rc != MHH_OK) return rc;
     // 4. pres.exec (solve), then pressure correction fused with timeloop.exec
     const TF cA[3] = {TF(0.), TF(-5. / 9.), TF(-153. / 128.)};
@@ -1571,6 +1676,18 @@ int substep_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, int sub
     for (int n = 0; n < f->ns; ++n)
         if ((rc = rk3_impl<TF>(c, P<TF>(f->s[n]), P<TF>(f->st[n]), substep, dt)) != MHH_OK) return rc;
     return MHH_OK;
+}
+
+template <typename TF>
+int substep_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, int substep, double dt)
+{
+    bool o4;
+    int rc = substep_check<TF>(c, f, prm, o4);
+    if (rc != MHH_OK) return rc;
+    if (substep < 0 || substep > 2) { c->err = "substep must be 0..2"; return MHH_E_INVALID; }
+    if (o4) return substep_o4_impl<TF>(c, f, prm, substep, dt);
+    if ((rc = substep_pre_impl<TF>(c, f, prm)) != MHH_OK) return rc;
+    return substep_post_impl<TF>(c, f, prm, substep, dt);
 }
 
 template <typename TF>
@@ -2052,6 +2169,30 @@ int mhh_dycore_substep(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm,
 {
     if (!f) return MHH_E_INVALID;
     DISPATCH1(ctx, substep_impl<TF>(c, f, prm, substep, dt));
+}
+
+int mhh_dycore_substep_pre(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm)
+{
+    if (!f) return MHH_E_INVALID;
+    DISPATCH1(ctx, substep_pre_impl<TF>(c, f, prm));
+}
+
+int mhh_dycore_set_ghost_cells(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm)
+{
+    if (!f || !prm) return MHH_E_INVALID;
+    DISPATCH1(ctx, ghost_all_impl<TF>(c, f, prm));
+}
+
+int mhh_dycore_tendencies(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm)
+{
+    if (!f) return MHH_E_INVALID;
+    DISPATCH1(ctx, tendencies_impl<TF>(c, f, prm));
+}
+
+int mhh_dycore_substep_post(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm, int substep, double dt)
+{
+    if (!f) return MHH_E_INVALID;
+    DISPATCH1(ctx, substep_post_impl<TF>(c, f, prm, substep, dt));
 }
 
 int mhh_dycore_step(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm, double dt)

@@ -342,6 +342,18 @@ class Dycore:
     def substep(self, fields, substep, dt):
         self.ctx.check(self.ctx.lib.mhh_dycore_substep(self.ctx.h, C.byref(fields.c), C.byref(self.prm), substep, dt))
 
+    def substep_pre(self, fields):
+        self.ctx.check(self.ctx.lib.mhh_dycore_substep_pre(self.ctx.h, C.byref(fields.c), C.byref(self.prm)))
+
+    def set_ghost_cells(self, fields):
+        self.ctx.check(self.ctx.lib.mhh_dycore_set_ghost_cells(self.ctx.h, C.byref(fields.c), C.byref(self.prm)))
+
+    def tendencies(self, fields):
+        self.ctx.check(self.ctx.lib.mhh_dycore_tendencies(self.ctx.h, C.byref(fields.c), C.byref(self.prm)))
+
+    def substep_post(self, fields, substep, dt):
+        self.ctx.check(self.ctx.lib.mhh_dycore_substep_post(self.ctx.h, C.byref(fields.c), C.byref(self.prm), substep, dt))
+
     def step(self, fields, dt):
         self.ctx.check(self.ctx.lib.mhh_dycore_step(self.ctx.h, C.byref(fields.c), C.byref(self.prm), dt))
 

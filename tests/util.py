@@ -22,10 +22,12 @@ def stretched_z(ktot, zsize):
     return 0.5*(zh[1:] + zh[:-1])
 
 
-def make_pair(itot, jtot, ktot, dtype, stretched=False, anelastic=False, ns=1, seed=2, sizes=(3200., 3200., 3200.)):
+def make_pair(itot, jtot, ktot, dtype, stretched=False, anelastic=False, ns=1, seed=2, sizes=(3200., 3200., 3200.), igc=3):
+    """igc = 4 is what the USESP adapters request (Grid::set_minimum_ghost_cells): the fp32 row pitch is then a multiple
+    of 16 bytes and the TMA-staged kernels apply."""
     z = stretched_z(ktot, sizes[2]) if stretched else None
-    g = O.Grid(itot, jtot, ktot, *sizes, 3, 3, 1, dtype, z=z)
-    gd = GridData(itot, jtot, ktot, *sizes, 3, 3, 1, dtype, z=z)
+    g = O.Grid(itot, jtot, ktot, *sizes, igc, 3, 1, dtype, z=z)
+    gd = GridData(itot, jtot, ktot, *sizes, igc, 3, 1, dtype, z=z)
     case = make_case(gd, seed=seed, anelastic=anelastic, ns=ns)
     return g, gd, case
 
