@@ -110,7 +110,9 @@ def run_ours(args):
     fx, fy, fz = {1: (1, 1, 1), 2: (1, 2, 1), 4: (2, 2, 1), 8: (2, 2, 2)}.get(world, (1, world, 1))
     itot_g, jtot_g, ktot_l = itot*fx, jtot*fy, ktot
     ktot = ktot*fz
-    gd = GridData(itot_g, jtot_g, ktot, 25.*itot_g, 25.*jtot_g, 25.*ktot, 3, 3, 1, dtype, npy=world, mpicoordy=rank)
+    # USESP: the adapters ask Grid for igc = 4 (set_minimum_ghost_cells), which makes the fp32 row pitch a multiple of 16 B
+    igc = args.igc if args.igc else (3 if dtype == np.float64 else 4)
+    gd = GridData(itot_g, jtot_g, ktot, 25.*itot_g, 25.*jtot_g, 25.*ktot, igc, 3, 1, dtype, npy=world, mpicoordy=rank)
     case = make_case(gd, seed=2, noise=0.01)
     ctx = D.Context(gd, local_rank)
     ctx.set_basestate(case["rhoref"], case["rhorefh"], case["thref"], case["threfh"])
@@ -333,6 +335,7 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("MHH_BENCH_WORKLOAD", "512x512x512"))
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--dt", type=float, default=1.0)
+    ap.add_argument("--igc", type=int, default=0, help="x ghost cells (0 = 3 for fp64, 4 for fp32)")
     ap.add_argument("--cpu-sample", default="64x64x64")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")

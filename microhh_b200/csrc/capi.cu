@@ -931,11 +931,12 @@ int mom4_launch(Ctx<TF>* c, const MomArgs<TF>& a, const ScalArgs<TF>* sc, bool s
     const size_t smem = mom4_smem(sizeof(TF), t.kchunk, tyw, nsc);
     CUtensorMap tu, tv, tw, te, ts, tut, tvt, twt, tst;
     const int by = t4_rows(tyw);
+    constexpr int T4_PX = t4_px((int)sizeof(TF));
     if (!make_field_tmap<TF>(&tu, a.u, g, T4_PX, by) || !make_field_tmap<TF>(&tv, a.v, g, T4_PX, by) ||
         !make_field_tmap<TF>(&tw, a.w, g, T4_PX, by) || !make_field_tmap<TF>(&te, a.evisc, g, T4_PX, by) ||
         !make_field_tmap<TF>(&ts, sc ? (const void*)sc->s : (const void*)a.u, g, T4_PX, by) ||
-        !make_field_tmap<TF>(&tut, a.ut, g, T4_W + 4, rows) || !make_field_tmap<TF>(&tvt, a.vt, g, T4_W + 4, rows) ||
-        !make_field_tmap<TF>(&twt, a.wt, g, T4_W + 4, rows) || !make_field_tmap<TF>(&tst, sc ? (const void*)sc->st : (const void*)a.ut, g, T4_W + 4, rows))
+        !make_field_tmap<TF>(&tut, a.ut, g, T4_PX, rows) || !make_field_tmap<TF>(&tvt, a.vt, g, T4_PX, rows) ||
+        !make_field_tmap<TF>(&twt, a.wt, g, T4_PX, rows) || !make_field_tmap<TF>(&tst, sc ? (const void*)sc->st : (const void*)a.ut, g, T4_PX, rows))
     { c->err = "cuTensorMapEncodeTiled failed"; return MHH_E_CUDA; }
 #define M4(S, B, N, W) do { \
         static size_t attr_smem_dev[64] = {0}; size_t& attr_smem = attr_smem_dev[c->device & 63];   /* the attribute is per device */ \
@@ -1005,7 +1006,9 @@ int tend_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, bool adv, 
     {
         const bool tma_any = !c->no_tma && tma_ok<TF>(g, {a.u, a.v, a.w, a.evisc, a.ut, a.vt, a.wt, buoy ? (const void*)a.th : (const void*)a.u});
         const bool tma = tma_any && sizeof(TF) == 8;          // mom2 / mom3 are fp64-only (odd-aligned 8-byte pairs)
-        if (tma_any && c->mom_variant == 4)
+        // the TMA box origin istart - halo must be 16-byte aligned (fp64: igc odd, fp32: igc a multiple of 4)
+        const bool origin_ok = ((g.igc - t4_hl((int)sizeof(TF))) * (int)sizeof(TF)) % 16 == 0;
+        if (tma_any && origin_ok && c->mom_variant == 4)
         {
             // fp64 and fp32 (USESP: needs a row pitch that is a multiple of 16 bytes, i.e. icells % 4 == 0 -- igc = 4)
             ScalArgs<TF> s0{};

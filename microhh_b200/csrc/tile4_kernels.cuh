@@ -6,9 +6,8 @@
 //   * every thread owns TWO rows x TWO columns, so the three y-face fluxes of its two rows are computed once (3 instead
 //     of 4), the y-direction column loads serve two rows (8 row reads for 2 rows instead of 7 per row) and the
 //     viscosity / velocity rows shared by neighbouring rows are read once;
-//   * the tile sits at an EVEN shared-memory column (x halo of 4 instead of 3; TMA box coordinates need no alignment,
-//     the out-of-range column is zero-filled), so the own pair and every column read is one aligned 128-bit LDS instead
-//     of two strided 64-bit ones that each waste half a wavefront;
+//   * every shared-memory row read is an aligned vector LDS; where the own pair sits at an odd column (fp64, see t4_hl)
+//     the two vectors that cover it also deliver the x neighbours the stencils need, so no wavefront is wasted;
 //   * a CTA covers 64 x (2*TYW) columns with TYW warps per component, so the halo amplification of the staged planes
 //     drops from (3+6)/3 = 3.0 to (6+6)/6 = 2.0 rows per row.
 // Warp roles as in mom3: groups of TYW warps compute u, v, w(+buoyancy) and the first scalar on the same TMA-staged
@@ -23,13 +22,18 @@
 namespace mhh {
 
 constexpr int T4_W = 64;                   // tile width: 2 columns per lane
-constexpr int T4_HL = 4;                   // x halo (3 needed; 4 keeps the own pair 16-byte aligned in shared memory)
-constexpr int T4_PX = T4_W + 2 * T4_HL;    // 72: plane pitch = TMA box width (a multiple of 16 bytes in fp64 and fp32)
+// x halo.  The TMA box origin must be 16-byte aligned in global memory (measured: an odd fp64 x coordinate raises
+// "illegal instruction"; negative even ones are fine and zero-filled): fp64 fields with igc = 3 start their interior at an
+// odd element, so the box starts 3 columns to the left and the own pair sits at an ODD shared-memory column (every
+// 128-bit LDS then starts one column early and also delivers a neighbour); fp32 fields with igc = 4 use a halo of 4
+// and the own pair is an aligned 64-bit LDS.
+constexpr int t4_hl(int elem) { return elem == 8 ? 3 : 4; }
+constexpr int t4_px(int elem) { return T4_W + 2 * t4_hl(elem); }   // 70 / 72: plane pitch = TMA box width (multiples of 16 bytes)
 constexpr int T4_H = 3;                    // y halo
 constexpr int T4_RING = 4;
 constexpr int t4_rows(int tyw) { return 2 * tyw + 2 * T4_H; }
-constexpr int t4_plane(int tyw, int elem) { return (T4_PX * t4_rows(tyw) * elem + 127) / 128 * 128 / elem; }
-constexpr int t4_box_bytes(int tyw, int elem) { return T4_PX * t4_rows(tyw) * elem; }
+constexpr int t4_plane(int tyw, int elem) { return (t4_px(elem) * t4_rows(tyw) * elem + 127) / 128 * 128 / elem; }
+constexpr int t4_box_bytes(int tyw, int elem) { return t4_px(elem) * t4_rows(tyw) * elem; }
 
 inline size_t mom4_smem(size_t elem, int kchunk, int tyw, int nsc)
 { return 128 + ((size_t)(4 + nsc) * T4_RING * t4_plane(tyw, (int)elem) + (size_t)8 * (kchunk + 3)) * elem + 128; }
@@ -49,7 +53,9 @@ mom4_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(sbase);     // full[RING], empty[RING]
     TF* sm = reinterpret_cast<TF*>(sbase + 128);
     constexpr int RING = T4_RING, R = 2 * TYW;
-    constexpr int PLANE = t4_plane(TYW, (int)sizeof(TF)), P = T4_PX, NCW = (3 + NSC) * TYW, NT = 32 * (NCW + 1);
+    constexpr int PLANE = t4_plane(TYW, (int)sizeof(TF)), P = t4_px((int)sizeof(TF)), T4_HL = t4_hl((int)sizeof(TF));
+    constexpr int NCW = (3 + NSC) * TYW, NT = 32 * (NCW + 1);
+    constexpr bool ODD = (T4_HL & 1) != 0;          // own pair at an odd shared-memory column
     constexpr int NF = 4 + NSC;
     constexpr unsigned PLANE_BYTES = PLANE * sizeof(TF), BOX_BYTES = t4_box_bytes(TYW, (int)sizeof(TF));
 
@@ -59,7 +65,7 @@ mom4_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
     const int comp = NSC ? (warp & 3) : warp / TYW, tw = NSC ? (warp >> 2) : warp - (warp / TYW) * TYW;
     const int i = g.istart + blockIdx.x * T4_W + 2 * tx;
     const int j0 = g.jstart + blockIdx.y * R + 2 * tw;
-    const int gi0 = g.istart + blockIdx.x * T4_W - T4_HL;          // may be -1 (igc = 3): TMA zero-fills the column
+    const int gi0 = g.istart + blockIdx.x * T4_W - T4_HL;          // 16-byte aligned (checked by the launcher)
     const int gj0 = g.jstart + blockIdx.y * R - T4_H;
     const bool xact = (i + 1 < g.iend);
     const bool act[2] = {xact && (j0 < g.jend), xact && (j0 + 1 < g.jend)};
@@ -69,7 +75,7 @@ mom4_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
     const long long jj = g.icells, kk = g.ijcells;
     const int ic = min(i, g.iend - 2);
     const long long ij[2] = {ic + min(j0, g.jend - 1) * jj, ic + min(j0 + 1, g.jend - 1) * jj};
-    const int sidx = (2 * tw + T4_H) * P + T4_HL + 2 * tx;          // even column: 16-byte aligned pairs
+    const int sidx = (2 * tw + T4_H) * P + T4_HL + 2 * tx;
     const TF dxi = g.dxi, dyi = g.dyi, visc = a.visc;
     const TF q = TF(0.25);
 
@@ -124,9 +130,9 @@ mom4_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
                     const int pt = lev + args.prefetch - 1;
                     if (pt >= kc0 && pt < kc1)
                     {
-                        tma_prefetch_3d(&tm_ut, gi0 + T4_HL, gj0 + T4_H, pt); tma_prefetch_3d(&tm_vt, gi0 + T4_HL, gj0 + T4_H, pt);
-                        tma_prefetch_3d(&tm_wt, gi0 + T4_HL, gj0 + T4_H, pt + 1);
-                        if (NSC) tma_prefetch_3d(&tm_st, gi0 + T4_HL, gj0 + T4_H, pt);
+                        tma_prefetch_3d(&tm_ut, gi0, gj0 + T4_H, pt); tma_prefetch_3d(&tm_vt, gi0, gj0 + T4_H, pt);
+                        tma_prefetch_3d(&tm_wt, gi0, gj0 + T4_H, pt + 1);
+                        if (NSC) tma_prefetch_3d(&tm_st, gi0, gj0 + T4_H, pt);
                     }
                 }
             }
@@ -139,22 +145,28 @@ mom4_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
         return (lev >= 0 && lev < g.kcells) ? fld[ij[r] + c + (long long)lev * kk] : TF(0);
     };
     auto LD2 = [](const TF* p) -> V2 { return *reinterpret_cast<const V2*>(p); };
-    // aligned row readers around the own pair (x[0], x[1]); x[n] lands at array index n + 4 / n + 2 / n
-    auto rowA = [&](const TF* p, TF (&x)[10]) {            // x[-4..5]   (x[-3..4] are used)
+    // Aligned vector row readers around the own pair (x[0], x[1]).  ODD: vectors start at x[-3], x[-1], x[1], x[3];
+    // otherwise at x[-4], x[-2], x[0], x[2], x[4].  x[n] lands at array index n + O? (the X? macros below).
+    constexpr int OA = ODD ? 3 : 4, NA = ODD ? 4 : 5;      // rowA: x[-3..4] are used
+    constexpr int OB = ODD ? 1 : 2, NB = ODD ? 2 : 3;      // rowB: x[-1..2] are used
+    constexpr int OL = ODD ? 1 : 2;                        // rowL: x[-1..1] are used (two vectors)
+    constexpr int OR_ = ODD ? 1 : 0;                       // rowR: x[0..2]  are used (two vectors)
+    auto rowA = [&](const TF* p, TF (&x)[10]) {
 #pragma unroll
-        for (int n = 0; n < 5; ++n) { const V2 t = LD2(p + 2 * n - 4); x[2 * n] = t.x; x[2 * n + 1] = t.y; } };
-    auto rowB = [&](const TF* p, TF (&x)[6]) {             // x[-2..3]   (x[-1..2] are used)
+        for (int n = 0; n < NA; ++n) { const V2 t = LD2(p + 2 * n - OA); x[2 * n] = t.x; x[2 * n + 1] = t.y; } };
+    auto rowB = [&](const TF* p, TF (&x)[6]) {
 #pragma unroll
-        for (int n = 0; n < 3; ++n) { const V2 t = LD2(p + 2 * n - 2); x[2 * n] = t.x; x[2 * n + 1] = t.y; } };
-    auto rowL = [&](const TF* p, TF (&x)[4]) {             // x[-2..1]   (x[-1..1] are used)
-        const V2 t0 = LD2(p - 2), t1 = LD2(p); x[0] = t0.x; x[1] = t0.y; x[2] = t1.x; x[3] = t1.y; };
-    auto rowR = [&](const TF* p, TF (&x)[4]) {             // x[0..3]    (x[0..2] are used)
-        const V2 t0 = LD2(p), t1 = LD2(p + 2); x[0] = t0.x; x[1] = t0.y; x[2] = t1.x; x[3] = t1.y; };
-    auto pair = [&](const TF* p, TF (&x)[2]) { const V2 t = LD2(p); x[0] = t.x; x[1] = t.y; };
-    // pair sums along x of a viscosity row: S[m] = E[m-1] + E[m], m = 0..2, from x[-2..3]
+        for (int n = 0; n < NB; ++n) { const V2 t = LD2(p + 2 * n - OB); x[2 * n] = t.x; x[2 * n + 1] = t.y; } };
+    auto rowL = [&](const TF* p, TF (&x)[4]) {
+        const V2 t0 = LD2(p - OL), t1 = LD2(p - OL + 2); x[0] = t0.x; x[1] = t0.y; x[2] = t1.x; x[3] = t1.y; };
+    auto rowR = [&](const TF* p, TF (&x)[4]) {
+        const V2 t0 = LD2(p - OR_), t1 = LD2(p - OR_ + 2); x[0] = t0.x; x[1] = t0.y; x[2] = t1.x; x[3] = t1.y; };
+    auto pair = [&](const TF* p, TF (&x)[2]) {
+        if (ODD) { x[0] = p[0]; x[1] = p[1]; } else { const V2 t = LD2(p); x[0] = t.x; x[1] = t.y; } };
+    // pair sums along x of a viscosity row: S[m] = E[m-1] + E[m], m = 0..2
     auto psum = [&](const TF (&e)[6], TF (&sum)[3]) {
 #pragma unroll
-        for (int m = 0; m < 3; ++m) sum[m] = e[m + 1] + e[m + 2]; };
+        for (int m = 0; m < 3; ++m) sum[m] = e[m - 1 + OB] + e[m + OB]; };
     auto plane = [&](int fld, int slot) -> const TF* { return sm + (fld * RING + slot) * PLANE + sidx; };
     auto acquire = [&](int k, int& s0, int& s1) {
         const int n = k - k0;
@@ -164,9 +176,10 @@ mom4_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
     };
     auto release = [&](int s0) { __syncwarp(); if (tx == 0) mbar_arrive(empty0 + 8 * s0); };
 
-#define XA(a, n) a[(n) + 4]
-#define XB(a, n) a[(n) + 2]
-#define XL(a, n) a[(n) + 2]
+#define XA(a, n) a[(n) + OA]
+#define XB(a, n) a[(n) + OB]
+#define XL(a, n) a[(n) + OL]
+#define XR(a, n) a[(n) + OR_]
     if (comp == 0)
     {
         // ------------------------------------------------------------------ u
@@ -358,9 +371,9 @@ mom4_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
 #pragma unroll
                     for (int m = 0; m < 3; ++m)
                     {
-                        const TF fa = flux65(interp2(u4[r][m], u4[r + 1][m]), XA(vx[r], m - 3), XA(vx[r], m - 2), XA(vx[r], m - 1), XA(vx[r], m), XA(vx[r], m + 1), XA(vx[r], m + 2));
+                        const TF fa = flux65(interp2(XR(u4[r], m), XR(u4[r + 1], m)), XA(vx[r], m - 3), XA(vx[r], m - 2), XA(vx[r], m - 1), XA(vx[r], m), XA(vx[r], m + 1), XA(vx[r], m + 2));
                         const TF eviscc = q * (sE[r][m] + sE[r + 1][m]) + visc;
-                        fx[r][m] = fa - eviscc * ((XA(vx[r], m) - XA(vx[r], m - 1)) * dxi + (u4[r + 1][m] - u4[r][m]) * dyi);
+                        fx[r][m] = fa - eviscc * ((XA(vx[r], m) - XA(vx[r], m - 1)) * dxi + (XR(u4[r + 1], m) - XR(u4[r], m)) * dyi);
                     }
                 // y "faces" yf = 0..2 are the centres of cells j0-1+yf (evisc row yf-1 -> e0[yf])
                 TF F[3][2];
@@ -477,7 +490,7 @@ mom4_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
 #pragma unroll
                     for (int m = 0; m < 3; ++m)
                     {
-                        fx[r][m] = flux65(u4[r][m], XA(sx[r], m - 3), XA(sx[r], m - 2), XA(sx[r], m - 1), XA(sx[r], m), XA(sx[r], m + 1), XA(sx[r], m + 2));
+                        fx[r][m] = flux65(XR(u4[r], m), XA(sx[r], m - 3), XA(sx[r], m - 2), XA(sx[r], m - 1), XA(sx[r], m), XA(sx[r], m + 1), XA(sx[r], m + 2));
                         const TF eviscx = h * (XB(e0[r], m - 1) + XB(e0[r], m)) * tPr_i + svisc;
                         dx_[r][m] = eviscx * (XA(sx[r], m) - XA(sx[r], m - 1));
                     }
@@ -590,9 +603,9 @@ mom4_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
 #pragma unroll
                     for (int m = 0; m < 3; ++m)
                     {
-                        const TF fa = flux65(interp2(u4[r][m], u14[r][m]), XA(wx[r], m - 3), XA(wx[r], m - 2), XA(wx[r], m - 1), XA(wx[r], m), XA(wx[r], m + 1), XA(wx[r], m + 2));
+                        const TF fa = flux65(interp2(XR(u4[r], m), XR(u14[r], m)), XA(wx[r], m - 3), XA(wx[r], m - 2), XA(wx[r], m - 1), XA(wx[r], m), XA(wx[r], m + 1), XA(wx[r], m + 2));
                         const TF eviscx = q * (s0r[r][m] + s1r[r][m]) + visc;
-                        fx[r][m] = fa - eviscx * ((XA(wx[r], m) - XA(wx[r], m - 1)) * dxi + (u14[r][m] - u4[r][m]) * dzhi_f);
+                        fx[r][m] = fa - eviscx * ((XA(wx[r], m) - XA(wx[r], m - 1)) * dxi + (XR(u14[r], m) - XR(u4[r], m)) * dzhi_f);
                     }
                 TF wy[8][2], V0P[3][2], V1P[3][2], EP0[4][2], EP1[4][2];
 #pragma unroll
@@ -646,6 +659,7 @@ mom4_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
 #undef XA
 #undef XB
 #undef XL
+#undef XR
 }
 
 } // namespace mhh
