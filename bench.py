@@ -207,9 +207,11 @@ def run_ours(args):
         "tend_uvw_kernel": 4 + 6, "tend_s_kernel": 5 + 2, "evisc_kernel": 5,
         # z-marching tile kernels: R u,v,w,evisc,th + RMW ut,vt,wt | R s,u,v,w,evisc + RMW st | R u,v,w,th + W evisc
         # mom3 carries scalar 0 as a fourth warp group: R u,v,w,evisc,th + RMW ut,vt,wt,tht
-        "mom_tile_kernel": 5 + 6, "mom2_kernel": 5 + 6, "mom3_kernel": 5 + 8, "mom4_kernel": 5 + 8, "scal_tile_kernel": 5 + 2, "evisc_tile_kernel": 5,
+        "mom_tile_kernel": 5 + 6, "mom2_kernel": 5 + 6, "mom3_kernel": 5 + 8, "scal_tile_kernel": 5 + 2, "evisc_tile_kernel": 5,
         "fft_x_forward_kernel": 7, "fft_y_forward_kernel": 2, "fft_y_backward_kernel": 2,
         "tdma_solve_kernel": 2, "fft_x_backward_kernel": 2, "pres_out_rk3_kernel": 13, "rk3_kernel": 4,
+        # Pres_2 version 2: y transform fused with the Thomas sweeps (R + W of the spectral array each; the pivot table is overhead)
+        "fft_y_tdma_forward_kernel": 2, "tdma_fft_y_backward_kernel": 2,
     }
     # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this very workload
     # (profiles/r01/ncu_full_mom3_evisc_raw.csv: dram__bytes_read.sum + dram__bytes_write.sum); null for other workloads

@@ -1,0 +1,199 @@
+// mhhb200 -- host side of the C ABI, shared by the translation units (host_core.cu, host_tend.cu, host_pres.cu):
+// the context, error / launch macros and the declarations of the per-stage drivers.  No CPU compute path exists.
+#pragma once
+#include <cmath>
+#include <cstdlib>
+#include <cstdint>
+#include <initializer_list>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <new>
+
+#include "../../include/mhhb200.h"
+#include "common.cuh"
+#include "stencil_kernels.cuh"
+#include "poisson_kernels.cuh"
+#include "fft_warp.cuh"
+#include "poisson_fused.cuh"
+#include "tile_kernels.cuh"
+#include "tile2_kernels.cuh"
+#include "tile3_kernels.cuh"
+#include "slab_kernels.cuh"
+#include "order2_kernels.cuh"
+#include "order4_kernels.cuh"
+#include "pres4_kernels.cuh"
+#include <cudaTypedefs.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+using namespace mhh;
+
+struct mhh_ctx
+{
+    int dtype = MHH_F64;
+    int device = 0;
+    std::string err;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    long long launches = 0;
+    long long ws_bytes = 0;
+    int num_sms = 148;
+    // optional per-kernel timing: one event after every launch; a kernel's time is the gap to the
+    // previous event on the (in-order) stream
+    int tile_y = 8;             // MHH_TILE_Y=8|16: tile height of the z-marching kernels
+    bool force_plain = false;   // MHH_FORCE_PLAIN=1: use the point-wise kernels everywhere (A/B comparisons)
+    bool no_tma = false;        // MHH_NO_TMA=1: keep the cp.async tile kernels (A/B comparisons)
+    int tile3_y = 0;            // MHH_TILE3_Y: rows per CTA of the warp-specialised kernel; 0 = 3 rows with the scalar group (13 warps), 4 without
+    bool fuse_scalar = true;    // MHH_FUSE_SCALAR=0: keep scalar 0 out of the momentum kernel (A/B comparisons)
+    int evisc_mb = 4;           // MHH_EVISC_MB=2|3|4 (measured 512^3 fp64: 2.72 | 2.51 | 2.11 ms): resident CTAs per SM the eddy-viscosity kernel is compiled for (register cap)
+    int prefetch = 1;           // MHH_PREFETCH: L2 prefetch distance (levels) of the TMA tile kernels, 0 = off
+    bool prof = false;
+    std::vector<std::pair<const char*, cudaEvent_t>> prof_events;
+    std::vector<cudaEvent_t> prof_pool;
+    std::string prof_json;
+    // y-slab decomposition (npx = 1, npy = nranks): NCCL communicator over the slab ranks
+    int nranks = 1, rank = 0;
+    ncclComm_t comm = nullptr;
+    virtual ~mhh_ctx() {}
+};
+
+// ---- NCCL, bound at run time (dlopen) so that single-GPU users need no NCCL at all; inside a torch
+// process this resolves to the libnccl.so.2 torch has already loaded.
+struct NcclApi
+{
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+
+NcclApi* nccl_api(std::string& err);
+void prof_mark(mhh_ctx* c, const char* name);
+
+namespace mhhhost {
+using namespace mhh;
+
+
+#define CUDA_TRY(ctx, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_); return MHH_E_CUDA; } } while (0)
+
+#define NCCL_TRY(ctx, api, call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) { \
+    (ctx)->err = std::string(#call) + ": " + (api)->GetErrorString(r_); return MHH_E_CUDA; } } while (0)
+
+#define KCHECKN(ctx, name) do { (ctx)->launches++; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) { \
+    (ctx)->err = std::string("kernel launch ") + name + ": " + cudaGetErrorString(e_) + " at " + __FILE__ + ":" + std::to_string(__LINE__); \
+    return MHH_E_CUDA; } prof_mark(ctx, name); } while (0)
+
+
+FftPlan make_plan(int n, bool& ok);
+
+template <typename TF>
+struct Ctx : mhh_ctx
+{
+    GridDev<TF> g{};
+    mhh_grid_desc desc{};
+    // device copies of the profiles
+    TF *d_prof = nullptr;          // 12 profiles x kcells
+    TF *d_mlen0 = nullptr;
+    // Pres_2
+    int nm = 0;
+    FftPlan plan_x{}, plan_y{};
+    cplx<TF> *tw_xh = nullptr, *tw_xf = nullptr, *tw_y = nullptr;
+    TF *d_bmati = nullptr, *d_bmatj = nullptr, *d_a = nullptr, *d_c = nullptr, *d_dz2rho = nullptr, *d_dz2 = nullptr;
+    TF *spec = nullptr;            // spectral workspace, x side: nm*jmax*ktot complex
+    TF *specT = nullptr;           // y side: mcl*jtot*ktot complex (== spec on a single GPU)
+    TF *fac = nullptr;             // tdma factors, mcl*jtot*ktot
+    // Pres_4: band coefficients (7 x kmax), 4th-order modified wavenumbers, LU factors of every mode (7 x (kmax+4) x ncol)
+    TF *d_m7 = nullptr, *d_bmati4 = nullptr, *d_bmatj4 = nullptr, *lu4 = nullptr;
+    std::vector<TF> h_dzi4, h_dzhi4, h_z;
+    SpecLayout lay{};
+    PeerPtrs<TF> peers{};          // IPC-mapped workspaces of all slab ranks (peers.on: fused transposes)
+    int *d_barrier = nullptr;      // dummy word for the all-reduce that closes a fused transpose
+    // peer halos: two alternating sets of (from north, from south) receive buffers, exported over CUDA IPC; the
+    // neighbours' sets are mapped in peer_halo_{south,north}
+    TF *phalo = nullptr;           // own: [set][dir] x phalo_cap elements
+    size_t phalo_cap = 0;
+    TF *phalo_south = nullptr, *phalo_north = nullptr;     // base of the south / north neighbour's phalo
+    unsigned phalo_count = 0;
+    TF *halo = nullptr;            // 4 staging buffers (send south/north, recv north/south) of halo_cap elements
+    size_t halo_cap = 0;
+    bool basestate_set = false;
+    double *d_red = nullptr;       // reduction scalar
+    double *h_red = nullptr;       // pinned
+    std::vector<TF> h_rhoref, h_rhorefh, h_dz, h_dzhi;
+    int rows_x = 1, mc_y = 4;
+    bool wfft_x = false, wfft_y = false;   // warp-per-sequence FFT kernels (power-of-two lengths)
+    // Pres_2 version 2 (poisson_fused.cuh): y transforms fused with the Thomas sweeps.  In this mode `spec` is the X side,
+    // `specT` the Y side (the names the IPC export uses), `fac` holds the reciprocal pivots T[ml][k][pos].
+    bool fused = false;
+    Spec2 lay2{};
+    int jlog2 = 0;
+    cplx<TF>* stage2 = nullptr;    // NCCL transport only: send staging of the backward transpose
+    size_t smem_x = 0, smem_y = 0;
+
+    ~Ctx() override
+    {
+        cudaSetDevice(device);
+        cudaFree(d_prof); cudaFree(d_mlen0); cudaFree(tw_xh); cudaFree(tw_xf); cudaFree(tw_y);
+        cudaFree(d_bmati); cudaFree(d_bmatj); cudaFree(d_a); cudaFree(d_c); cudaFree(d_dz2rho); cudaFree(d_dz2);
+        for (int r = 0; r < MAX_SLAB_RANKS; ++r)
+            if (peers.on && r != rank) { if (peers.x[r]) cudaIpcCloseMemHandle(peers.x[r]); if (peers.y[r]) cudaIpcCloseMemHandle(peers.y[r]); }
+        if (phalo_south && phalo_south != phalo) cudaIpcCloseMemHandle(phalo_south);
+        if (phalo_north && phalo_north != phalo && phalo_north != phalo_south) cudaIpcCloseMemHandle(phalo_north);
+        cudaFree(phalo);
+        cudaFree(d_barrier);
+        cudaFree(d_m7); cudaFree(d_bmati4); cudaFree(d_bmatj4); cudaFree(lu4); cudaFree(stage2);
+        if (specT != spec) cudaFree(specT);
+        cudaFree(spec); cudaFree(fac); cudaFree(d_red); cudaFree(halo);
+        if (comm) { std::string e; NcclApi* api = nccl_api(e); if (api) api->CommDestroy(comm); }
+        if (h_red) cudaFreeHost(h_red);
+        if (own_stream) cudaStreamDestroy(own_stream);
+    }
+
+    TdmaCoef<TF> coef() const { return {d_a, d_c, d_dz2rho, d_dz2, d_bmati, d_bmatj}; }
+
+    dim3 blk() const { return dim3(64, 4, 1); }
+    dim3 grd_interior() const { return dim3((g.imax + 63) / 64, (g.jmax + 3) / 4, g.kmax); }
+    dim3 grd_all() const { return dim3((g.icells + 63) / 64, (g.jcells + 3) / 4, g.kcells); }
+};
+
+template <typename TF> inline TF* P(void* p) { return static_cast<TF*>(p); }
+template <typename TF> inline const TF* P(const void* p) { return static_cast<const TF*>(p); }
+
+#define NEED_BASE(c) do { if (!(c)->basestate_set) { (c)->err = "mhh_set_basestate has not been called"; return MHH_E_INVALID; } } while (0)
+#define NEED(c, ptr, what) do { if (!(ptr)) { (c)->err = std::string(what) + " is NULL"; return MHH_E_INVALID; } } while (0)
+
+
+
+// ---- per-stage drivers (defined in one translation unit each, instantiated for double and float) ----
+// host_core.cu
+template <typename TF> int slab_barrier(Ctx<TF>* c, const char* name);
+template <typename TF> int exchange_ns(Ctx<TF>* c, TF* const* flds, int nf, int w, int nk);
+template <typename TF> int cyclic_impl(Ctx<TF>* c, TF* fld, int edge, bool two_d);
+template <typename TF> int cyclic_fields(Ctx<TF>* c, TF* const* flds, int nf);
+// host_tend.cu
+template <typename TF> int check_mom(Ctx<TF>* c, const mhh_fields* f, bool need_evisc, bool surface);
+template <typename TF> int evisc_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, const TF* n2);
+template <typename TF> int tend_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, bool adv, bool diff, bool buoy);
+template <typename TF> int o2_impl(Ctx<TF>* c, const mhh_fields* f, bool adv, bool diff, bool buoy);
+template <typename TF> int o4_impl(Ctx<TF>* c, const mhh_fields* f, bool adv, bool diff);
+template <typename TF> int o2_cfl_impl(Ctx<TF>* c, const mhh_fields* f, double* out, int order);
+template <typename TF> int reduce_mode_impl(Ctx<TF>* c, int mode, const TF* u, const TF* v, const TF* w, TF p0, TF p1, TF p2, double* out);
+// host_pres.cu
+template <typename TF> int pres_create(Ctx<TF>* c);
+template <typename TF> int pres_set_values(Ctx<TF>* c);
+template <typename TF> int pres_solve_impl(Ctx<TF>* c, const mhh_fields* f, double sub_dt);
+template <typename TF> int pres_exec_impl(Ctx<TF>* c, const mhh_fields* f, double sub_dt);
+template <typename TF> int pres4_exec_impl(Ctx<TF>* c, const mhh_fields* f, double sub_dt);
+template <typename TF> int pres4_div_impl(Ctx<TF>* c, const mhh_fields* f, double* out);
+template <typename TF> int fft_roundtrip_impl(Ctx<TF>* c, const TF* in, TF* out, int solve);
+
+} // namespace mhhhost

@@ -23,7 +23,7 @@
 // (src/fft.cxx:338-452 serial, :455-587 MPI), Transpose::exec_xy/yx (src/transpose.cxx:117-271).
 #pragma once
 #include "fft_warp.cuh"
-#include "tile2_kernels.cuh"      // mbarrier primitives
+#include "tile3_kernels.cuh"      // mbarrier primitives, cp_async
 
 namespace mhh {
 
@@ -264,18 +264,13 @@ __device__ __forceinline__ long long p2_yoff(const Spec2& lay, const int jlog2, 
     return (long long)s * lay.mcl * lay.ktot * lay.jmax + jl;
 }
 
-template <int BYTES>
-__device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" :: "r"(smem_u32(smem_dst)), "l"(gsrc), "n"(BYTES) : "memory");
-}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
 template <typename TF, int J>
 __global__ void __launch_bounds__(32 * p2_y_warps<TF, J>()) p2_y_forward_kernel(cplx<TF>* __restrict__ Y, const TF* __restrict__ T, const Spec2 lay,
         const TF* __restrict__ ak, const TF* __restrict__ dz2, const cplx<TF>* __restrict__ tw, const int jlog2, const int solve)
 {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NW = p2_y_warps<TF, J>(), RS = FftRow<J>::SIZE, NI = (J + 31) / 32;
     constexpr bool TREG = NI <= 32;          // table entries of the level prefetched into registers (issued before the transform)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -342,7 +337,7 @@ template <typename TF, int J>
 __global__ void __launch_bounds__(32 * p2_y_warps<TF, J>()) p2_y_backward_kernel(const cplx<TF>* __restrict__ Y, const TF* __restrict__ T, const Spec2 lay,
         const XferPtrs<TF> xf, const TF* __restrict__ ck, const cplx<TF>* __restrict__ tw, const int jlog2, const int solve)
 {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NW = p2_y_warps<TF, J>(), RS = FftRow<J>::SIZE, NI = (J + 31) / 32;
     constexpr bool TREG = NI <= 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

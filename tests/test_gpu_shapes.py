@@ -42,6 +42,32 @@ def check_step(g, f, case, names, tol):
     return errs
 
 
+def truth_fp64(case32, shape, dt, oprm, **pair_kw):
+    """The same step in fp64 on the same (fp32-representable) inputs: the yardstick for fp32 runs on grids where two
+    independent fp32 evaluations differ by more than 1e-5 from each other through rounding alone (the Poisson solve
+    amplifies the rounding noise of the divergence with the grid size)."""
+    import copy
+    g64, gd64, c64 = make_pair(*shape, np.float64, **pair_kw)
+    for k, a in case32.items():
+        if isinstance(a, np.ndarray):
+            c64[k] = a.astype(np.float64)
+    ostep.dycore_step(g64, kernels(g64), c64, copy.deepcopy(oprm), dt)
+    return g64, c64
+
+
+def check_fp32_at_reference_level(g, f, case32, g64, c64, names):
+    """fp32 on large grids: the GPU result must be as close to the fp64 truth as the reference's own fp32 CPU kernels are
+    (<= 1.25 x the reference's error + 1e-6), which is the strongest statement rounding allows."""
+    out = {}
+    for n in names:
+        t = interior(g64, c64[n])
+        e_gpu = rel_l2(interior(g, f[n].cpu().numpy()), t)
+        e_ref = rel_l2(interior(g, case32[n]), t)
+        out[n] = (e_gpu, e_ref)
+    assert all(eg <= 1.25*er + 1e-6 for eg, er in out.values()), out
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ LES configurations
 @pytest.mark.parametrize("swadvec", ["2i5", "2"])
 def test_drycblles_128_fp64(swadvec):
@@ -69,13 +95,15 @@ def test_drycblles_128_fp64(swadvec):
 def test_les_256x256x128_fp32(igc):
     """USESP build of the LES path (the bomex-shaped grid is 512 x 512 x 256; this is its 1/8 at oracle-friendly cost).
     igc = 4 (16-byte row pitch) takes the TMA-staged kernels, igc = 3 the cp.async ones."""
-    g, gd, case = make_pair(256, 256, 128, np.float32, stretched=True, anelastic=True, sizes=(6400., 6400., 3200.), igc=igc)
+    kw = dict(stretched=True, anelastic=True, sizes=(6400., 6400., 3200.), igc=igc)
+    g, gd, case = make_pair(256, 256, 128, np.float32, **kw)
     D, ctx, f = gpu_setup(gd, case)
     dt = 4.0
+    g64, c64 = truth_fp64(case, (256, 256, 128), dt, ostep.default_params(), **kw)
     D.Dycore(ctx, D.make_params()).step(f, dt)
     ostep.dycore_step(g, kernels(g), case, ostep.default_params(), dt)
     ctx.sync()
-    check_step(g, f, case, ("u", "v", "w", "th"), TOL[np.float32])
+    check_fp32_at_reference_level(g, f, case, g64, c64, ("u", "v", "w", "th"))
 
 
 @pytest.mark.parametrize("dtype,igc", [(np.float64, 3), (np.float32, 3), (np.float32, 4), (np.float64, 4)])
@@ -84,13 +112,21 @@ def test_les_256x256x128_fp32(igc):
 def test_multi_tile_step(dtype, igc, shape, ns):
     """>= 2 x-tiles of the 64-wide marching kernels (blockIdx.x > 0 TMA coordinates), ragged last x tile (160 = 2.5
     tiles), rows that are not a multiple of the CTA height, ktot that splits into uneven z-chunks; one and two scalars."""
-    g, gd, case = make_pair(*shape, dtype, stretched=True, anelastic=True, ns=ns, igc=igc)
+    kw = dict(stretched=True, anelastic=True, ns=ns, igc=igc)
+    g, gd, case = make_pair(*shape, dtype, **kw)
     D, ctx, f = gpu_setup(gd, case, ns)
     dt = 2.0
+    names = ["u", "v", "w"] + case["scalars"]
+    if dtype == np.float32:
+        g64, c64 = truth_fp64(case, shape, dt, ostep.default_params(), **kw)
     D.Dycore(ctx, D.make_params(ns=ns)).step(f, dt)
     ostep.dycore_step(g, kernels(g), case, ostep.default_params(), dt)
     ctx.sync()
-    check_step(g, f, case, ["u", "v", "w"] + case["scalars"], 2*TOL[dtype])
+    if dtype == np.float32:
+        check_fp32_at_reference_level(g, f, case, g64, c64, names)
+        check_step(g, f, case, names, 5*TOL[dtype])          # and never far from the reference's fp32 result itself
+    else:
+        check_step(g, f, case, names, TOL[dtype])
 
 
 @pytest.mark.parametrize("dtype,igc", [(np.float64, 3), (np.float32, 3), (np.float32, 4)])
