@@ -118,6 +118,20 @@ typedef struct mhh_params
     int    sbcbot[MHH_MAX_SCALARS], sbctop[MHH_MAX_SCALARS];
 } mhh_params;
 
+/* State of the Monin-Obukhov surface model (Boundary_surface<TF>, include/boundary_surface.h): 2-D device arrays of
+ * ijcells entries, caller-owned (in MicroHH they are Boundary_surface's ustar_g, obuk_g, nobuk_g, z0m_g, z0h_g). */
+typedef struct mhh_surface
+{
+    void *ustar, *obuk;          /* friction velocity and Obukhov length (start from Constants::dsmall like init_surface) */
+    int  *nobuk;                 /* last lookup-table index per column (search hint), start from 0 */
+    void *z0m, *z0h;             /* roughness lengths */
+    void *dutot;                 /* scratch plane */
+    int   sbcbot[MHH_MAX_SCALARS];   /* per scalar: MHH_SBC_DIRICHLET (surface value given -> flux computed), MHH_SBC_FLUX (flux given ->
+                                      * surface value computed), anything else: left alone (src/boundary_surface.cxx:292-340) */
+} mhh_surface;
+#define MHH_SBC_DIRICHLET 0
+#define MHH_SBC_FLUX      2
+
 /* ---- context ----------------------------------------------------------------------------- */
 MHH_API int  mhh_ctx_create(const mhh_grid_desc* grid, int dtype, int device, mhh_ctx** out);
 MHH_API void mhh_ctx_destroy(mhh_ctx* ctx);
@@ -254,6 +268,17 @@ MHH_API int mhh_dycore_substep_pre(mhh_ctx* ctx, const mhh_fields* f, const mhh_
 MHH_API int mhh_dycore_set_ghost_cells(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm);
 MHH_API int mhh_dycore_tendencies(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm);
 MHH_API int mhh_dycore_substep_post(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm, int substep, double dt);
+/* ---- Boundary_surface<TF>: Monin-Obukhov surface model with constant z0 and the z/L lookup solver
+ * (src/boundary_surface.cxx:818-990; include/boundary_surface_kernels.h).  init builds the lookup table for (z0m, z0h, z[kstart])
+ * like Boundary_surface::init_solver; mbcbot must be MHH_BC_DIRICHLET (no-slip), thermobc MHH_SBC_DIRICHLET or MHH_SBC_FLUX
+ * (the bottom BC of th).  exec updates ustar / obuk, the momentum fluxes and gradients, the scalars' surface value or flux and
+ * gradient, and the MO gradients dudz_mo / dvdz_mo / dbdz_mo that exec_viscosity uses -- for Thermo_dry (prm->swthermo = 1)
+ * or without thermo (stability_neutral). */
+MHH_API int mhh_boundary_surface_init(mhh_ctx* ctx, double z0m, double z0h, int mbcbot, int thermobc);
+MHH_API int mhh_boundary_surface_exec(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm, const mhh_surface* s);
+/* The self-driven LES sub-step in Model::exec's order (src/model.cxx:368-504): mhh_dycore_substep_pre, the surface model,
+ * Boundary::set_ghost_cells again, mhh_dycore_substep_post. */
+MHH_API int mhh_dycore_substep_surface(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm, const mhh_surface* s, int substep, double dt);
 /* Three sub-steps. */
 MHH_API int mhh_dycore_step(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm, double dt);
 /* End-to-end variant with HOST buffers (ghosted layout): copies u,v,w and the scalars to the

@@ -43,6 +43,11 @@ class FieldsC(C.Structure):
                 ("s_fluxlimit", C.c_int * MHH_MAX_SCALARS)]
 
 
+class SurfaceC(C.Structure):
+    _fields_ = [("ustar", C.c_void_p), ("obuk", C.c_void_p), ("nobuk", C.c_void_p), ("z0m", C.c_void_p), ("z0h", C.c_void_p),
+                ("dutot", C.c_void_p), ("sbcbot", C.c_int * MHH_MAX_SCALARS)]
+
+
 class SlabInfo(C.Structure):
     _fields_ = [("nm", C.c_int), ("mcl", C.c_int), ("m_off", C.c_int), ("jmax", C.c_int),
                 ("rows", C.c_longlong), ("xside_elems", C.c_longlong), ("yside_elems", C.c_longlong)]
@@ -103,6 +108,9 @@ SIGNATURES = {
     "mhh_dycore_set_ghost_cells": (C.c_int, [_vp, _PF, _PP]),
     "mhh_dycore_tendencies": (C.c_int, [_vp, _PF, _PP]),
     "mhh_dycore_substep_post": (C.c_int, [_vp, _PF, _PP, C.c_int, C.c_double]),
+    "mhh_boundary_surface_init": (C.c_int, [_vp, C.c_double, C.c_double, C.c_int, C.c_int]),
+    "mhh_boundary_surface_exec": (C.c_int, [_vp, _PF, _PP, C.POINTER(SurfaceC)]),
+    "mhh_dycore_substep_surface": (C.c_int, [_vp, _PF, _PP, C.POINTER(SurfaceC), C.c_int, C.c_double]),
     "mhh_dycore_step": (C.c_int, [_vp, _PF, _PP, C.c_double]),
     "mhh_dycore_step_host": (C.c_int, [_vp, _PF, _PP, C.c_double, C.c_int, _vp, _vp, _vp, C.POINTER(_vp)]),
 }

@@ -54,6 +54,17 @@ def _get(ini, sec, key, default=None, conv=str):
     return conv(v)
 
 
+def _get_sub(ini, sec, key, sub, default=None, conv=str):
+    """Input::get_item(section, key, subitem) (src/input.cxx): `key[sub]` wins over the plain `key`; no default -> required."""
+    d = ini.get(sec, {})
+    v = d.get(f"{key}[{sub}]", d.get(key))
+    if v is None:
+        if default is None:
+            raise KeyError(f"[{sec}] {key} (or {key}[{sub}]) is required")
+        return default
+    return conv(v)
+
+
 _MBC = {"noslip": capi.BC_DIRICHLET, "freeslip": capi.BC_NEUMANN, "neumann": capi.BC_NEUMANN}
 _SBC = {"dirichlet": capi.BC_DIRICHLET, "neumann": capi.BC_NEUMANN, "flux": capi.BC_NEUMANN}
 _SWADVEC = {"2": 2, "2i5": 25, "4": 4}
@@ -84,13 +95,15 @@ class CaseConfig:
         self.tPr = _get(ini, "diff", "tPr", 1./3., float)
         self.swmason = _get(ini, "diff", "swmason", True, bool)
         self.visc = _get(ini, "fields", "visc", 0., float)
-        self.svisc = _get(ini, "fields", "svisc", 0., float)
-        self.mbcbot = _get(ini, "boundary", "mbcbot", "noslip")
-        self.mbctop = _get(ini, "boundary", "mbctop", "noslip")
-        self.sbcbot = _get(ini, "boundary", "sbcbot", "neumann")
-        self.sbctop = _get(ini, "boundary", "sbctop", "neumann")
+        # src/boundary.cxx:188-189: mbcbot / mbctop are required keys
+        self.mbcbot = _get(ini, "boundary", "mbcbot")
+        self.mbctop = _get(ini, "boundary", "mbctop")
         sl = _get(ini, "fields", "slist", "")
         self.scalars = (["th"] if self.swthermo == "dry" else []) + [x.strip() for x in sl.split(",") if x.strip()]
+        # per scalar, `key[name]` before `key` (src/boundary.cxx:234-235, src/fields.cxx:412); required when there are scalars
+        self.sbcbot = {n: _get_sub(ini, "boundary", "sbcbot", n) for n in self.scalars}
+        self.sbctop = {n: _get_sub(ini, "boundary", "sbctop", n) for n in self.scalars}
+        self.svisc = {n: _get_sub(ini, "fields", "svisc", n, conv=float) for n in self.scalars}
 
     @classmethod
     def from_file(cls, path):
@@ -123,8 +136,11 @@ class CaseConfig:
             bad.append("4th-order grid with thermo")
         if self.mbcbot not in _MBC or self.mbctop not in _MBC:
             bad.append(f"mbcbot/mbctop={self.mbcbot}/{self.mbctop}")
-        if self.sbcbot not in _SBC or self.sbctop not in _SBC:
-            bad.append(f"sbcbot/sbctop={self.sbcbot}/{self.sbctop}")
+        for n in self.scalars:
+            if self.sbcbot[n] not in _SBC or self.sbctop[n] not in _SBC:
+                bad.append(f"sbcbot/sbctop[{n}]={self.sbcbot[n]}/{self.sbctop[n]}")
+        if len(self.scalars) > capi.MHH_MAX_SCALARS:
+            bad.append(f"{len(self.scalars)} scalars (max {capi.MHH_MAX_SCALARS})")
         if self.npx != 1:
             bad.append(f"npx={self.npx} (the decomposition is y slabs: npx=1)")
         if self.fluxlimit_list and self.ghost_cells()[2] != 1:
@@ -148,6 +164,6 @@ class CaseConfig:
         p.sw_mason = int(self.swmason)
         p.cs = self.cs; p.tPr = self.tPr
         p.mbcbot = _MBC[self.mbcbot]; p.mbctop = _MBC[self.mbctop]
-        for i in range(capi.MHH_MAX_SCALARS):
-            p.sbcbot[i] = _SBC[self.sbcbot]; p.sbctop[i] = _SBC[self.sbctop]
+        for i, n in enumerate(self.scalars):
+            p.sbcbot[i] = _SBC[self.sbcbot[n]]; p.sbctop[i] = _SBC[self.sbctop[n]]
         return p

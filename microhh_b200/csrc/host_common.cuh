@@ -20,6 +20,7 @@
 #include "tile2_kernels.cuh"
 #include "tile3_kernels.cuh"
 #include "slab_kernels.cuh"
+#include "surface_kernels.cuh"
 #include "order2_kernels.cuh"
 #include "order4_kernels.cuh"
 #include "pres4_kernels.cuh"
@@ -126,6 +127,10 @@ struct Ctx : mhh_ctx
     TF *halo = nullptr;            // 4 staging buffers (send south/north, recv north/south) of halo_cap elements
     size_t halo_cap = 0;
     bool basestate_set = false;
+    // Boundary_surface lookup table (z/L nodes and evaluation function, float like the reference), built by mhh_boundary_surface_init
+    float *d_zL_sl = nullptr, *d_f_sl = nullptr;
+    int surf_mbcbot = -1, surf_thermobc = -1;
+    std::vector<TF> h_thref, h_threfh;
     double *d_red = nullptr;       // reduction scalar
     double *h_red = nullptr;       // pinned
     std::vector<TF> h_rhoref, h_rhorefh, h_dz, h_dzhi;
@@ -142,6 +147,7 @@ struct Ctx : mhh_ctx
     ~Ctx() override
     {
         cudaSetDevice(device);
+        cudaFree(d_zL_sl); cudaFree(d_f_sl);
         cudaFree(d_prof); cudaFree(d_mlen0); cudaFree(tw_xh); cudaFree(tw_xf); cudaFree(tw_y);
         cudaFree(d_bmati); cudaFree(d_bmatj); cudaFree(d_a); cudaFree(d_c); cudaFree(d_dz2rho); cudaFree(d_dz2);
         for (int r = 0; r < MAX_SLAB_RANKS; ++r)

@@ -170,6 +170,8 @@ int set_basestate_impl(Ctx<TF>* c, const void* rhoref, const void* rhorefh, cons
     const TF* rr = static_cast<const TF*>(rhoref);
     const TF* rh = static_cast<const TF*>(rhorefh);
     c->h_rhoref.assign(rr, rr + kc); c->h_rhorefh.assign(rh, rh + kc);
+    if (thref) c->h_thref.assign(static_cast<const TF*>(thref), static_cast<const TF*>(thref) + kc);
+    if (threfh) c->h_threfh.assign(static_cast<const TF*>(threfh), static_cast<const TF*>(threfh) + kc);
 
     {
         std::vector<TF> mlen0(kc, TF(0));
@@ -499,6 +501,120 @@ int substep_post_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, in
     for (int n = 0; n < f->ns; ++n)
         if ((rc = rk3_impl<TF>(c, P<TF>(f->s[n]), P<TF>(f->st[n]), substep, dt)) != MHH_OK) return rc;
     return MHH_OK;
+}
+
+// ---- Boundary_surface (Monin-Obukhov surface model, constant z0, lookup solver) --------------------------------------
+// bsk::prepare_lut (include/boundary_surface_kernels.h:78-138), in the reference's mix of TF / double / float arithmetic
+template <typename TF>
+int surface_init_impl(Ctx<TF>* c, double z0m_d, double z0h_d, int mbcbot, int thermobc)
+{
+    if (mbcbot != 0) { c->err = "boundary_surface: only mbcbot = noslip (Dirichlet) is implemented"; return MHH_E_INVALID; }
+    if (thermobc != 0 && thermobc != 2) { c->err = "boundary_surface: thermobc must be Dirichlet (0) or flux (2)"; return MHH_E_INVALID; }
+    const int nlut = SURF_NLUT;
+    const TF z0m = (TF)z0m_d, z0h = (TF)z0h_d, zsl = c->h_z[c->g.kstart];
+    std::vector<TF> zL_tmp(nlut);
+    const TF zL_max = 10., zL_min = -1.e4, zLrange_min = -5.;
+    TF dzL = (zL_max - zLrange_min) / (9. * nlut / 10. - 1.);
+    zL_tmp[0] = -zL_max;
+    for (int n = 1; n < 9 * nlut / 10; ++n) zL_tmp[n] = zL_tmp[n - 1] + dzL;
+    const TF zLend = -(zL_min - zLrange_min);
+    TF r = 1.01, r0 = 1.e30;
+    while (std::abs((r - r0) / r0) > 1.e-10)
+    {
+        r0 = r;
+        r = std::pow(1. - (zLend / dzL) * (1. - r), (1. / (nlut / 10.)));
+    }
+    for (int n = 9 * nlut / 10; n < nlut; ++n) { zL_tmp[n] = zL_tmp[n - 1] + dzL; dzL *= r; }
+    std::vector<float> zL(nlut), fs(nlut);
+    for (int n = 0; n < nlut; ++n) zL[n] = -zL_tmp[nlut - n - 1];
+    // host twins of the stability functions (include/monin_obukhov.h)
+    auto psim = [](TF zeta, bool unstable) -> TF {
+        if (unstable) { const TF ph = std::pow(TF(1.) + TF(3.6) * std::pow(std::abs(zeta), TF(2. / 3.)), TF(-1. / 2.)); return TF(3.) * std::log((TF(1.) + TF(1.) / ph) / TF(2.)); }
+        const TF a = 1, b = TF(2) / TF(3), cc = 5, dd = TF(0.35);
+        return -b * (zeta - (cc / dd)) * std::exp(-dd * zeta) - a * zeta - (b * cc) / dd; };
+    auto psih = [](TF zeta, bool unstable) -> TF {
+        if (unstable) { const TF ph = std::pow(TF(1.) + TF(7.9) * std::pow(std::abs(zeta), TF(2. / 3.)), TF(-1. / 2.)); return TF(3.) * std::log((TF(1.) + TF(1.) / ph) / TF(2.)); }
+        const TF a = 1, b = TF(2) / TF(3), cc = 5, dd = TF(0.35);
+        return -b * (zeta - (cc / dd)) * std::exp(-dd * zeta) - std::pow(TF(1) + b * a * zeta, TF(1.5)) - (b * cc) / dd + TF(1); };
+    auto fm = [&](TF L) -> TF { const bool u = L <= TF(0.); return TF(0.4) / (std::log(zsl / z0m) - psim(zsl / L, u) + psim(z0m / L, u)); };
+    auto fh = [&](TF L) -> TF { const bool u = L <= TF(0.); return TF(0.4) / (std::log(zsl / z0h) - psih(zsl / L, u) + psih(z0h / L, u)); };
+    for (int n = 0; n < nlut; ++n)
+    {
+        const TF L = zsl / zL[n];
+        if (thermobc == 2) fs[n] = zL[n] * std::pow(fm(L), 3);
+        else fs[n] = zL[n] * std::pow(fm(L), 2) / fh(L);
+    }
+    if (!c->d_zL_sl) { CUDA_TRY(c, cudaMalloc(&c->d_zL_sl, sizeof(float) * nlut)); CUDA_TRY(c, cudaMalloc(&c->d_f_sl, sizeof(float) * nlut)); }
+    CUDA_TRY(c, cudaMemcpy(c->d_zL_sl, zL.data(), sizeof(float) * nlut, cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(c->d_f_sl, fs.data(), sizeof(float) * nlut, cudaMemcpyHostToDevice));
+    c->surf_mbcbot = mbcbot; c->surf_thermobc = thermobc;
+    return MHH_OK;
+}
+
+// Boundary_surface<TF>::exec (src/boundary_surface.cxx:836-990), Thermo_dry or Thermo_disabled
+template <typename TF>
+int surface_exec_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, const mhh_surface* s)
+{
+    NEED_BASE(c);
+    const GridDev<TF>& g = c->g;
+    NEED(c, s, "surface"); NEED(c, f, "fields");
+    if (!c->d_zL_sl) { c->err = "mhh_boundary_surface_init has not been called"; return MHH_E_INVALID; }
+    if (g.igc < 2 || g.jgc < 2) { c->err = "boundary_surface: the wind filter needs igc, jgc >= 2"; return MHH_E_INVALID; }
+    const bool neutral = prm->swthermo == 0;
+    SurfArgs<TF> a{};
+    a.ustar = P<TF>(s->ustar); a.obuk = P<TF>(s->obuk); a.nobuk = static_cast<int*>(s->nobuk); a.dutot = P<TF>(s->dutot);
+    a.z0m = P<TF>(s->z0m); a.z0h = P<TF>(s->z0h); a.zL_sl = c->d_zL_sl; a.f_sl = c->d_f_sl;
+    NEED(c, a.ustar, "ustar"); NEED(c, a.obuk, "obuk"); NEED(c, a.nobuk, "nobuk"); NEED(c, a.dutot, "dutot"); NEED(c, a.z0m, "z0m"); NEED(c, a.z0h, "z0h");
+    a.u = P<TF>(f->u); a.v = P<TF>(f->v); a.ubot = P<TF>(f->u_bot); a.vbot = P<TF>(f->v_bot);
+    a.ufluxbot = P<TF>(f->u_fluxbot); a.vfluxbot = P<TF>(f->v_fluxbot); a.ugradbot = P<TF>(f->u_gradbot); a.vgradbot = P<TF>(f->v_gradbot);
+    a.dudz = P<TF>(f->dudz_mo); a.dvdz = P<TF>(f->dvdz_mo); a.dbdz = P<TF>(f->dbdz_mo);
+    NEED(c, a.u, "u"); NEED(c, a.v, "v"); NEED(c, a.ubot, "u_bot"); NEED(c, a.vbot, "v_bot"); NEED(c, a.ufluxbot, "u_fluxbot"); NEED(c, a.vfluxbot, "v_fluxbot");
+    NEED(c, a.ugradbot, "u_gradbot"); NEED(c, a.vgradbot, "v_gradbot"); NEED(c, a.dudz, "dudz_mo"); NEED(c, a.dvdz, "dvdz_mo");
+    if (f->ns < 0 || f->ns > MHH_MAX_SCALARS) { c->err = "ns out of range"; return MHH_E_INVALID; }
+    a.ns = f->ns;
+    for (int n = 0; n < f->ns; ++n)
+    {
+        a.s[n] = P<TF>(f->s[n]); a.sbot[n] = P<TF>(f->s_bot[n]); a.sgradbot[n] = P<TF>(f->s_gradbot[n]); a.sfluxbot[n] = P<TF>(f->s_fluxbot[n]);
+        a.sbc[n] = s->sbcbot[n];
+        NEED(c, a.s[n], "scalar"); NEED(c, a.sbot[n], "s_bot"); NEED(c, a.sgradbot[n], "s_gradbot"); NEED(c, a.sfluxbot[n], "s_fluxbot");
+    }
+    a.mbcbot = c->surf_mbcbot; a.thermobc = c->surf_thermobc; a.neutral = neutral ? 1 : 0;
+    if (!neutral)
+    {
+        if (f->ns < 1) { c->err = "boundary_surface: thermo dry needs scalar 0 (th)"; return MHH_E_INVALID; }
+        if (c->h_thref.empty() || c->h_threfh.empty()) { c->err = "boundary_surface: thref / threfh were not given to mhh_set_basestate"; return MHH_E_INVALID; }
+        NEED(c, a.dbdz, "dbdz_mo");
+        if (s->sbcbot[0] != c->surf_thermobc) { c->err = "boundary_surface: sbcbot[0] differs from the thermobc the lookup table was built for"; return MHH_E_INVALID; }
+        a.thref = c->h_thref[g.kstart]; a.threfh = c->h_threfh[g.kstart];
+        a.gthref = TF(GRAV) / a.thref; a.gthrefh = TF(GRAV) / a.threfh;
+    }
+    a.zsl = c->h_z[g.kstart];
+    dim3 b(64, 4), gi((g.imax + 63) / 64, (g.jmax + 3) / 4), ga((g.icells + 63) / 64, (g.jcells + 3) / 4);
+    int rc;
+    surface_dutot_kernel<TF><<<gi, b, 0, c->stream>>>(a, g);
+    KCHECKN(c, "surface_dutot_kernel");
+    if ((rc = cyclic_impl<TF>(c, a.dutot, MHH_EDGE_BOTH, true)) != MHH_OK) return rc;
+    surface_stability_kernel<TF><<<ga, b, 0, c->stream>>>(a, g);
+    KCHECKN(c, "surface_stability_kernel");
+    surface_flux_kernel<TF><<<gi, b, 0, c->stream>>>(a, g);
+    KCHECKN(c, "surface_flux_kernel");
+    if ((rc = cyclic_impl<TF>(c, a.ufluxbot, MHH_EDGE_BOTH, true)) != MHH_OK) return rc;
+    if ((rc = cyclic_impl<TF>(c, a.vfluxbot, MHH_EDGE_BOTH, true)) != MHH_OK) return rc;
+    surface_values_kernel<TF><<<ga, b, 0, c->stream>>>(a, g);
+    KCHECKN(c, "surface_values_kernel");
+    return MHH_OK;
+}
+
+// The self-driven LES sub-step in the reference's order (src/model.cxx:368-504): cyclic + ghost cells -> exec_viscosity ->
+// boundary.exec (surface model) -> set_ghost_cells -> thermo + advec + diff -> pres -> timeloop
+template <typename TF>
+int substep_surface_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, const mhh_surface* s, int substep, double dt)
+{
+    int rc;
+    if ((rc = substep_pre_impl<TF>(c, f, prm)) != MHH_OK) return rc;
+    if ((rc = surface_exec_impl<TF>(c, f, prm, s)) != MHH_OK) return rc;
+    if ((rc = ghost_all_impl<TF>(c, f, prm)) != MHH_OK) return rc;
+    return substep_post_impl<TF>(c, f, prm, substep, dt);
 }
 
 template <typename TF>
@@ -985,6 +1101,23 @@ int mhh_dycore_substep_post(mhh_ctx* ctx, const mhh_fields* f, const mhh_params*
 {
     if (!f) return MHH_E_INVALID;
     DISPATCH1(ctx, substep_post_impl<TF>(c, f, prm, substep, dt));
+}
+
+int mhh_boundary_surface_init(mhh_ctx* ctx, double z0m, double z0h, int mbcbot, int thermobc)
+{
+    DISPATCH1(ctx, surface_init_impl<TF>(c, z0m, z0h, mbcbot, thermobc));
+}
+
+int mhh_boundary_surface_exec(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm, const mhh_surface* s)
+{
+    if (!f || !prm) return MHH_E_INVALID;
+    DISPATCH1(ctx, surface_exec_impl<TF>(c, f, prm, s));
+}
+
+int mhh_dycore_substep_surface(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm, const mhh_surface* s, int substep, double dt)
+{
+    if (!f || !prm) return MHH_E_INVALID;
+    DISPATCH1(ctx, substep_surface_impl<TF>(c, f, prm, s, substep, dt));
 }
 
 int mhh_dycore_step(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm, double dt)

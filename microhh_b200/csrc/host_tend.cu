@@ -239,11 +239,12 @@ int mom3_launch(Ctx<TF>* c, const MomArgs<TF>& a, const ScalArgs<TF>* sc, bool s
     const size_t smem = mom3_smem(sizeof(TF), t.kchunk, ty, nsc);
     CUtensorMap tu, tv, tw, te, ts, tut, tvt, twt, tst;
     const int by = ty + 2 * T2_H;
+    constexpr int T2_PX = t2_px((int)sizeof(TF));
     if (!make_field_tmap<TF>(&tu, a.u, g, T2_PX, by) || !make_field_tmap<TF>(&tv, a.v, g, T2_PX, by) ||
         !make_field_tmap<TF>(&tw, a.w, g, T2_PX, by) || !make_field_tmap<TF>(&te, a.evisc, g, T2_PX, by) ||
         !make_field_tmap<TF>(&ts, sc ? (const void*)sc->s : (const void*)a.u, g, T2_PX, by) ||
-        !make_field_tmap<TF>(&tut, a.ut, g, T2_W + 2, ty) || !make_field_tmap<TF>(&tvt, a.vt, g, T2_W + 2, ty) ||
-        !make_field_tmap<TF>(&twt, a.wt, g, T2_W + 2, ty) || !make_field_tmap<TF>(&tst, sc ? (const void*)sc->st : (const void*)a.ut, g, T2_W + 2, ty))
+        !make_field_tmap<TF>(&tut, a.ut, g, T2_PX, ty) || !make_field_tmap<TF>(&tvt, a.vt, g, T2_PX, ty) ||
+        !make_field_tmap<TF>(&twt, a.wt, g, T2_PX, ty) || !make_field_tmap<TF>(&tst, sc ? (const void*)sc->st : (const void*)a.ut, g, T2_PX, ty))
     { c->err = "cuTensorMapEncodeTiled failed"; return MHH_E_CUDA; }
 #define M3(S, B, N, Y) do { \
         static size_t attr_smem_dev[64] = {0}; size_t& attr_smem = attr_smem_dev[c->device & 63];   /* the attribute is per device */ \
@@ -311,8 +312,9 @@ int tend_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, bool adv, 
     int first_scalar = 0;       // scalars [0, first_scalar) were handled by the fused momentum kernel
     if (tiles)
     {
-        // mom3 is fp64-only (odd-aligned 8-byte pairs); its TMA box origin istart - 3 must be 16-byte aligned (igc odd)
-        const bool tma = !c->no_tma && sizeof(TF) == 8 && ((g.igc - T2_HL) % 2) == 0
+        // the TMA box origin istart - halo must be 16-byte aligned: fp64 igc odd (3), fp32 igc a multiple of 4 (the USESP
+        // adapters ask Grid for igc = 4); everything else runs the cp.async tile kernels
+        const bool tma = !c->no_tma && (((g.igc - t2_hl((int)sizeof(TF))) * (int)sizeof(TF)) % 16) == 0
                          && tma_ok<TF>(g, {a.u, a.v, a.w, a.evisc, a.ut, a.vt, a.wt, buoy ? (const void*)a.th : (const void*)a.u});
         if (tma)
         {

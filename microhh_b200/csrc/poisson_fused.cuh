@@ -14,7 +14,7 @@
 // accesses into its private shared-memory row, transforms it there (in-place DIF, digit-reversed result) and applies the
 // elimination in the digit-reversed order (the Thomas recurrence couples levels, not y-modes, so the order is immaterial);
 // consecutive levels are pipelined over the warps of the CTA, the only coupling being the previous level's solution handed
-// over in a two-slot shared-memory ring guarded by mbarriers.  The downward pass mirrors it and ends with the matching
+// over in a two-slot shared-memory ring behind a "levels done" counter.  The downward pass mirrors it and ends with the matching
 // decimation-in-time inverse (digit-reversed in, natural out), so no permutation pass exists anywhere.
 //
 // Both transposes of the y-slab decomposition are the store phases of the x-forward and y-inverse kernels (8-row chunks of
@@ -247,10 +247,10 @@ __global__ void __launch_bounds__(32 * P2_ROWS) p2_x_forward_kernel(const TF* __
 // ------------------------------------------------------------------------------------------
 // y forward transform + forward elimination, one CTA per local x-mode (blockIdx.x), warps pipeline the levels upwards.
 //   Y[.][ml][k][.] (natural y order)  ->  p'_k in digit-reversed y order, in place.   solve = 0: transform only.
-// Shared memory: [full barriers: 128 B][state ring: 2 x J][rows: NW x FftRow<J>]
-// Hand-over protocol: level k writes ring slot k & 1 after it has read slot (k-1) & 1, then arrives on full[k & 1]
-// (its (k >> 1)-th completion); level k+1 waits for exactly that completion.  Level k+2 reuses slot k & 1 only after
-// level k+1 -- the slot's only reader -- has arrived, so two slots suffice and no "empty" barrier is needed.
+// Shared memory: [level counter: 128 B][state ring: 2 x J][rows: NW x FftRow<J>]
+// Hand-over protocol: level k writes ring slot k & 1 after it has read slot (k-1) & 1, then publishes done = k + 1;
+// level k+1 waits for done >= k + 1.  Level k+2 reuses slot k & 1 only after level k+1 -- the slot's only reader -- has
+// published, so two slots suffice and no "slot free" signal is needed.
 // ------------------------------------------------------------------------------------------
 template <typename TF, int J> constexpr int p2_y_warps() { return (sizeof(TF) * J > 8 * 1024) ? 4 : 8; }     // fp64 J = 2048: 4 rows fit
 template <typename TF, int J> constexpr size_t p2_y_smem()
@@ -262,6 +262,20 @@ __device__ __forceinline__ long long p2_yoff(const Spec2& lay, const int jlog2, 
     if (lay.P == 1) return j;
     const int s = j >> jlog2, jl = j & (lay.jmax - 1);
     return (long long)s * lay.mcl * lay.ktot * lay.jmax + jl;
+}
+
+// Level hand-over between the warps of a CTA: a monotonically increasing "levels done" counter in shared memory.
+// (mbarrier parities cannot be used here: a warp may start waiting several levels ahead of the producer, and a parity wait
+// that starts more than one phase early returns at the wrong completion.)
+__device__ __forceinline__ void level_wait(const volatile int* done, const int need)
+{
+    while (*done < need) __nanosleep(40);
+    __threadfence_block();          // acquire: the producer's ring slot is visible
+}
+__device__ __forceinline__ void level_publish(volatile int* done, const int value, const int lane)
+{
+    __syncwarp();
+    if (lane == 0) { __threadfence_block(); *done = value; }
 }
 
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
@@ -276,8 +290,8 @@ __global__ void __launch_bounds__(32 * p2_y_warps<TF, J>()) p2_y_forward_kernel(
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     cplx<TF>* state = reinterpret_cast<cplx<TF>*>(smem_raw + 128);
     cplx<TF>* row = state + 2 * J + warp * RS;
-    const unsigned full0 = smem_u32(smem_raw);
-    if (threadIdx.x == 0) { mbar_init(full0, 1); mbar_init(full0 + 8, 1); mbar_fence_init(); }
+    volatile int* done = reinterpret_cast<volatile int*>(smem_raw);          // levels completed so far (in order)
+    if (threadIdx.x == 0) *done = 0;
     __syncthreads();
     const int K = lay.ktot;
     const int ml = blockIdx.x;
@@ -299,7 +313,7 @@ __global__ void __launch_bounds__(32 * p2_y_warps<TF, J>()) p2_y_forward_kernel(
         if (solve)
         {
             const TF a = ak[k], d2 = dz2[k];
-            if (k > 0) mbar_wait(full0 + 8 * ((k - 1) & 1), ((k - 1) >> 1) & 1);
+            if (k > 0) level_wait(done, k);                     // level k-1 has published its slot
             const cplx<TF>* prev = state + ((k - 1) & 1) * J;
             cplx<TF>* cur = state + (k & 1) * J;
 #pragma unroll
@@ -317,8 +331,7 @@ __global__ void __launch_bounds__(32 * p2_y_warps<TF, J>()) p2_y_forward_kernel(
                     seq[p2_yoff(lay, jlog2, pos)] = o;
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(full0 + 8 * (k & 1));
+            level_publish(done, k + 1, lane);
         }
         else
         {
@@ -343,8 +356,8 @@ __global__ void __launch_bounds__(32 * p2_y_warps<TF, J>()) p2_y_backward_kernel
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     cplx<TF>* state = reinterpret_cast<cplx<TF>*>(smem_raw + 128);
     cplx<TF>* row = state + 2 * J + warp * RS;
-    const unsigned full0 = smem_u32(smem_raw);
-    if (threadIdx.x == 0) { mbar_init(full0, 1); mbar_init(full0 + 8, 1); mbar_fence_init(); }
+    volatile int* done = reinterpret_cast<volatile int*>(smem_raw);
+    if (threadIdx.x == 0) *done = 0;
     __syncthreads();
     const int K = lay.ktot;
     const int cnt = lay.mcl;
@@ -372,7 +385,7 @@ __global__ void __launch_bounds__(32 * p2_y_warps<TF, J>()) p2_y_backward_kernel
             __syncwarp();
             if (n > 0)
             {
-                mbar_wait(full0 + 8 * ((n - 1) & 1), ((n - 1) >> 1) & 1);
+                level_wait(done, n);
                 const cplx<TF>* prev = state + ((n - 1) & 1) * J;
                 cplx<TF>* cur = state + (n & 1) * J;
 #pragma unroll
@@ -396,8 +409,7 @@ __global__ void __launch_bounds__(32 * p2_y_warps<TF, J>()) p2_y_backward_kernel
 #pragma unroll 4
                 for (int pos = lane; pos < J; pos += 32) cur[pos] = row[fpad(pos)];
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(full0 + 8 * (n & 1));
+            level_publish(done, n + 1, lane);
         }
         else
         {

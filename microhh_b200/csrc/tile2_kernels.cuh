@@ -65,13 +65,18 @@ template <> struct V2T<float>  { typedef float2 type; };
 
 // ---- tile geometry ---------------------------------------------------------------------------
 constexpr int T2_W  = 64;                 // tile width  (2 columns per lane)
-constexpr int T2_HL = 3;                  // x halo.  TMA needs a 16-byte aligned box origin: istart - 3 = 0 is even, so the
-                                          // thread's own pair sits at an ODD shared-memory column and is read as two 8-byte
-                                          // loads; rows along x are read as aligned 16-byte pairs starting one column early.
-constexpr int T2_PX = T2_W + 2 * T2_HL;   // 70: plane pitch (= TMA box width; 560 bytes, a multiple of 16)
+// x halo.  The TMA box origin must be 16-byte aligned in global memory (probed on B200: an odd fp64 x coordinate raises
+// "illegal instruction", a negative even one is fine and zero-filled).
+//   fp64, igc = 3: the interior starts at an odd element, so the box starts 3 columns to the left (origin 64 bx, even) and
+//     the thread's own pair sits at an ODD shared-memory column: rows along x are read as aligned 16-byte pairs starting
+//     one column early, the pair itself as two 8-byte loads.
+//   fp32, igc = 4 (what the USESP adapters ask Grid for: icells % 4 == 0 makes the row pitch a multiple of 16 bytes):
+//     halo 4, origin 64 bx (a multiple of 4 elements), own pair at an even column = one aligned 8-byte load.
+constexpr int t2_hl(int elem) { return elem == 8 ? 3 : 4; }
+constexpr int t2_px(int elem) { return T2_W + 2 * t2_hl(elem); }      // 70 / 72: plane pitch = TMA box width (multiples of 16 bytes)
 constexpr int T2_H  = 3;                  // y halo
 // plane size in elements, padded so that every plane starts on a 128-byte boundary (TMA destination alignment)
-constexpr int t2_plane(int ty, int elem = 8) { return (T2_PX * (ty + 2 * T2_H) * elem + 127) / 128 * 128 / elem; }
-constexpr int t2_box_bytes(int ty, int elem = 8) { return T2_PX * (ty + 2 * T2_H) * elem; }
+constexpr int t2_plane(int ty, int elem) { return (t2_px(elem) * (ty + 2 * T2_H) * elem + 127) / 128 * 128 / elem; }
+constexpr int t2_box_bytes(int ty, int elem) { return t2_px(elem) * (ty + 2 * T2_H) * elem; }
 
 } // namespace mhh

@@ -52,7 +52,9 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(sbase);     // full[RING], empty[RING]
     TF* sm = reinterpret_cast<TF*>(sbase + 128);
     constexpr int RING = T3_RING;
-    constexpr int PLANE = t2_plane(TY, (int)sizeof(TF)), P = T2_PX, NT = 32 * ((3 + NSC) * TY + 1), NCW = (3 + NSC) * TY;
+    constexpr int PLANE = t2_plane(TY, (int)sizeof(TF)), P = t2_px((int)sizeof(TF)), T2_HL = t2_hl((int)sizeof(TF));
+    constexpr int NT = 32 * ((3 + NSC) * TY + 1), NCW = (3 + NSC) * TY;
+    constexpr bool ODD = (T2_HL & 1) != 0;          // own pair at an odd shared-memory column (fp64)
     constexpr int NF = 4 + NSC;
     constexpr unsigned PLANE_BYTES = PLANE * sizeof(TF), BOX_BYTES = t2_box_bytes(TY, (int)sizeof(TF));
 
@@ -130,9 +132,9 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
                     const int pt = lev + args.prefetch - 1;
                     if (pt >= kc0 && pt < kc1)
                     {
-                        tma_prefetch_3d(&tm_ut, gi0 + 2, gj0 + T2_H, pt); tma_prefetch_3d(&tm_vt, gi0 + 2, gj0 + T2_H, pt);
-                        tma_prefetch_3d(&tm_wt, gi0 + 2, gj0 + T2_H, pt + 1);
-                        if (NSC) tma_prefetch_3d(&tm_st, gi0 + 2, gj0 + T2_H, pt);
+                        tma_prefetch_3d(&tm_ut, gi0, gj0 + T2_H, pt); tma_prefetch_3d(&tm_vt, gi0, gj0 + T2_H, pt);
+                        tma_prefetch_3d(&tm_wt, gi0, gj0 + T2_H, pt + 1);
+                        if (NSC) tma_prefetch_3d(&tm_st, gi0, gj0 + T2_H, pt);
                     }
                 }
             }
@@ -145,25 +147,28 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
         return (lev >= 0 && lev < g.kcells) ? fld[ij + c + (long long)lev * kk] : TF(0);
     };
     auto LD2 = [](const TF* p) -> V2 { return *reinterpret_cast<const V2*>(p); };
+    // Aligned vector row readers around the own pair (x[0], x[1]).  ODD: vectors start at x[-5], x[-3], x[-1], x[1] ...;
+    // otherwise at x[-4], x[-2], x[0], x[2] ...  The value x[n] lands at array index n + O? (macros X10 / X6 / X4 below).
+    constexpr int O10 = ODD ? 5 : 4, N10 = ODD ? 6 : 5;          // row10: x[-3..4] are used
+    constexpr int O3 = ODD ? 1 : 2, N3 = ODD ? 2 : 3;            // row3:  x[-1..2] are used
     auto row10 = [&](const TF* p, TF (&x)[12]) {
 #pragma unroll
-        for (int n = 0; n < 6; ++n) { const V2 t = LD2(p + 2 * n - 5); x[2 * n] = t.x; x[2 * n + 1] = t.y; } };
-    auto row6 = [&](const TF* p, TF (&x)[8]) {
+        for (int n = 0; n < N10; ++n) { const V2 t = LD2(p + 2 * n - O10); x[2 * n] = t.x; x[2 * n + 1] = t.y; } };
+    auto row3 = [&](const TF* p, TF (&x)[6]) {
 #pragma unroll
-        for (int n = 0; n < 4; ++n) { const V2 t = LD2(p + 2 * n - 3); x[2 * n] = t.x; x[2 * n + 1] = t.y; } };
-    auto row4 = [&](const TF* p, TF (&x)[6]) {
-#pragma unroll
-        for (int n = 0; n < 3; ++n) { const V2 t = LD2(p + 2 * n - 1); x[2 * n] = t.x; x[2 * n + 1] = t.y; } };
-    // row3: x[-1..2] -> array index n+1: two aligned vector loads (shared-memory bandwidth co-limits this kernel)
-    auto row3 = [&](const TF* p, TF (&x)[4]) {
-        const V2 t0 = LD2(p - 1), t1 = LD2(p + 1); x[0] = t0.x; x[1] = t0.y; x[2] = t1.x; x[3] = t1.y; };
+        for (int n = 0; n < N3; ++n) { const V2 t = LD2(p + 2 * n - O3); x[2 * n] = t.x; x[2 * n + 1] = t.y; } };
     auto col7 = [&](const TF* p, TF (&y)[7][2]) {
 #pragma unroll
-        for (int d = -3; d <= 3; ++d) { y[d + 3][0] = p[d * P]; y[d + 3][1] = p[d * P + 1]; } };
-    auto pair = [&](const TF* p, TF (&x)[2]) { x[0] = p[0]; x[1] = p[1]; };
-    auto psum = [&](const TF (&e)[4], TF (&sum)[3]) {
+        for (int d = -3; d <= 3; ++d)
+        {
+            if (ODD) { y[d + 3][0] = p[d * P]; y[d + 3][1] = p[d * P + 1]; }
+            else { const V2 t = LD2(p + d * P); y[d + 3][0] = t.x; y[d + 3][1] = t.y; }
+        } };
+    auto pair = [&](const TF* p, TF (&x)[2]) {
+        if (ODD) { x[0] = p[0]; x[1] = p[1]; } else { const V2 t = LD2(p); x[0] = t.x; x[1] = t.y; } };
+    auto psum = [&](const TF (&e)[6], TF (&sum)[3]) {
 #pragma unroll
-        for (int m = 0; m < 3; ++m) sum[m] = e[m] + e[m + 1]; };
+        for (int m = 0; m < 3; ++m) sum[m] = e[m - 1 + O3] + e[m + O3]; };
     auto plane = [&](int fld, int slot) -> const TF* { return sm + (fld * RING + slot) * PLANE + sidx; };
     // wait for plane (k+1), hand back the slots of planes k and k+1
     auto acquire = [&](int k, int& s0, int& s1) {
@@ -174,9 +179,9 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
     };
     auto release = [&](int k, int s0) { (void)k; __syncwarp(); if (tx == 0) mbar_arrive(empty0 + 8 * s0); };
 
-#define X10(a, n) a[(n) + 5]
-#define X6(a, n) a[(n) + 1]
-#define X4(a, n) a[(n) + 1]
+#define X10(a, n) a[(n) + O10]
+#define X6(a, n) a[(n) + O3]
+#define X4(a, n) a[(n) + O3]
     if (comp == 0)
     {
         // ------------------------------------------------------------------ u
@@ -199,7 +204,7 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
             const TF* __restrict__ U0 = plane(0, s0); const TF* __restrict__ U1 = plane(0, s1);
             const TF* __restrict__ V0 = plane(1, s0); const TF* __restrict__ W1 = plane(2, s1);
             const TF* __restrict__ E0 = plane(3, s0); const TF* __restrict__ E1 = plane(3, s1);
-            TF ux[12], w6[4], e0[4], e1[4], s0r[3], s1r[3], U1R[2];
+            TF ux[12], w6[6], e0[6], e1[6], s0r[3], s1r[3], U1R[2];
             row10(U0, ux); row3(W1, w6); row3(E0, e0); row3(E1, e1); pair(U1, U1R);
             psum(e0, s0r); psum(e1, s1r);
             TF fx[3], dx_[3];
@@ -227,7 +232,7 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
             }
             if (st)
             {
-                TF uy[7][2], v6[4], vp6[4], em[4], ep[4], s0m[3], s0p[3];
+                TF uy[7][2], v6[6], vp6[6], em[6], ep[6], s0m[3], s0p[3];
                 col7(U0, uy); row3(V0, v6); row3(V0 + P, vp6); row3(E0 - P, em); row3(E0 + P, ep);
                 psum(em, s0m); psum(ep, s0p);
 #pragma unroll
@@ -273,7 +278,7 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
             const TF* __restrict__ V0 = plane(1, s0); const TF* __restrict__ V1 = plane(1, s1);
             const TF* __restrict__ W1 = plane(2, s1);
             const TF* __restrict__ E0 = plane(3, s0); const TF* __restrict__ E1 = plane(3, s1);
-            TF vx[12], e0[4], em[4], V1R[2], W1R[2], W1M[2], E1R[2], E1M[2];
+            TF vx[12], e0[6], em[6], V1R[2], W1R[2], W1M[2], E1R[2], E1M[2];
             row10(V0, vx); row3(E0, e0); row3(E0 - P, em);
             pair(V1, V1R); pair(W1, W1R); pair(W1 - P, W1M); pair(E1, E1R); pair(E1 - P, E1M);
             TF gt[2];
@@ -294,7 +299,7 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
             }
             if (st)
             {
-                TF u4[4], um4[4], vy[7][2], s0r[3], s0m[3];
+                TF u4[6], um4[6], vy[7][2], s0r[3], s0m[3];
                 row3(U0, u4); row3(U0 - P, um4); col7(V0, vy);
                 psum(e0, s0r); psum(em, s0m);
                 TF fx[3], dx_[3];
@@ -347,7 +352,7 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
             const TF* __restrict__ W1 = plane(2, s1);
             const TF* __restrict__ E0 = plane(3, s0); const TF* __restrict__ E1 = plane(3, s1);
             const TF* __restrict__ S0 = plane(4, s0); const TF* __restrict__ S1 = plane(4, s1);
-            TF sx[12], S1R[2], W1R[2], E1R[2], e0[4];
+            TF sx[12], S1R[2], W1R[2], E1R[2], e0[6];
             row10(S0, sx); pair(S1, S1R); pair(W1, W1R); pair(E1, E1R); row3(E0, e0);
             TF gt[2];
 #pragma unroll
@@ -367,7 +372,7 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
             }
             if (st)
             {
-                TF u4[4], sy[7][2], V0R[2], V0P[2], EM0[2], EP0[2];
+                TF u4[6], sy[7][2], V0R[2], V0P[2], EM0[2], EP0[2];
                 row3(U0, u4); col7(S0, sy); pair(V0, V0R); pair(V0 + P, V0P); pair(E0 - P, EM0); pair(E0 + P, EP0);
                 TF fx[3], dx_[3];
 #pragma unroll
@@ -440,7 +445,7 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
             }
             if (st)
             {
-                TF u4[4], u14[4], e0[4], e16[4], s0r[3], s1r[3];
+                TF u4[6], u14[6], e0[6], e16[6], s0r[3], s1r[3];
                 row3(U0, u4); row3(U1, u14); row3(E0, e0); row3(E1, e16);
                 psum(e0, s0r); psum(e16, s1r);
                 TF fx[3], dx_[3];

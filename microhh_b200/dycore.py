@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import capi
-from .capi import FieldsC, ParamsC, GridDesc, MhhError
+from .capi import FieldsC, ParamsC, GridDesc, SurfaceC, MhhError
 
 SWADVEC = {"2i5": 25, "2": 2, "4": 4}
 SWDIFF = {"smag2": 1, "2": 2, "4": 4}
@@ -323,6 +323,32 @@ class Pres:
         self.ctx.check(self.ctx.lib.mhh_pres_fft_roundtrip(self.ctx.h, _ptr(a_in), _ptr(a_out), int(solve)))
 
 
+class Boundary_surface:
+    """Boundary_surface<TF> (src/boundary_surface.cxx): Monin-Obukhov surface model with constant z0 and the lookup solver.
+    Owns the 2-D state (ustar, obuk, nobuk, z0m, z0h) like the reference class does."""
+    SBC_DIRICHLET, SBC_FLUX = 0, 2
+
+    def __init__(self, ctx, fields, z0m=0.1, z0h=0.1, thermobc=2, sbcbot=None):
+        self.ctx = ctx
+        gd = ctx.gd
+        dev = fields["u"].device
+        z2 = lambda v, dt=ctx.torch_dtype: torch.full(gd.shape2d, v, dtype=dt, device=dev)
+        self.ustar = z2(1.e-9); self.obuk = z2(1.e-9)          # Constants::dsmall (init_surface)
+        self.nobuk = z2(0, torch.int32)
+        self.z0m = z2(z0m); self.z0h = z2(z0h); self.dutot = z2(0.)
+        ctx.check(ctx.lib.mhh_boundary_surface_init(ctx.h, float(z0m), float(z0h), capi.BC_DIRICHLET, int(thermobc)))
+        c = SurfaceC()
+        c.ustar = self.ustar.data_ptr(); c.obuk = self.obuk.data_ptr(); c.nobuk = self.nobuk.data_ptr()
+        c.z0m = self.z0m.data_ptr(); c.z0h = self.z0h.data_ptr(); c.dutot = self.dutot.data_ptr()
+        sb = list(sbcbot) if sbcbot is not None else [thermobc] + [self.SBC_FLUX]*(len(fields.scalars) - 1)
+        for i in range(capi.MHH_MAX_SCALARS):
+            c.sbcbot[i] = sb[i] if i < len(sb) else 1
+        self.c = c
+
+    def exec(self, fields, prm):
+        self.ctx.check(self.ctx.lib.mhh_boundary_surface_exec(self.ctx.h, C.byref(fields.c), C.byref(prm), C.byref(self.c)))
+
+
 class Timeloop:
     def __init__(self, ctx):
         self.ctx = ctx
@@ -353,6 +379,14 @@ class Dycore:
 
     def substep_post(self, fields, substep, dt):
         self.ctx.check(self.ctx.lib.mhh_dycore_substep_post(self.ctx.h, C.byref(fields.c), C.byref(self.prm), substep, dt))
+
+    def substep_surface(self, fields, surface, substep, dt):
+        """Model::exec order with the surface model on the device (src/model.cxx:368-504)."""
+        self.ctx.check(self.ctx.lib.mhh_dycore_substep_surface(self.ctx.h, C.byref(fields.c), C.byref(self.prm), C.byref(surface.c), substep, dt))
+
+    def step_surface(self, fields, surface, dt):
+        for ss in range(3):
+            self.substep_surface(fields, surface, ss, dt)
 
     def step(self, fields, dt):
         self.ctx.check(self.ctx.lib.mhh_dycore_step(self.ctx.h, C.byref(fields.c), C.byref(self.prm), dt))

@@ -224,10 +224,15 @@ namespace mhhb200
             void exec_viscosity(Stats<TF>&, Thermo<TF>& thermo) override
             {
                 prm.surface_model = this->boundary.get_switch() != "default";
-                prm.swthermo = thermo.get_switch() == Thermo_type::Dry ? 1 : 0;
+                // three ways, as the reference dispatches on thermo.get_switch() (src/diff_smag2.cu:131,181):
+                //   Disabled -> calc_evisc_neutral (no N2 at all: Thermo_disabled::get_thermo_field_g throws, include/thermo_disabled.h:81)
+                //   Dry      -> N2 derived from th inside the fused kernel
+                //   other    -> N2 fetched from the thermo class
+                const Thermo_type sw = thermo.get_switch();
+                prm.swthermo = sw == Thermo_type::Dry ? 1 : 0;
                 const mhh_fields f = fields_view(this->fields, &this->boundary);
-                if (prm.swthermo == 1)
-                    MHH_CHECK(c->ctx, mhh_diff_smag2_exec_viscosity(c->ctx, &f, &prm, nullptr));   // N2 derived from th
+                if (sw == Thermo_type::Disabled || sw == Thermo_type::Dry)
+                    MHH_CHECK(c->ctx, mhh_diff_smag2_exec_viscosity(c->ctx, &f, &prm, nullptr));
                 else
                 {
                     auto n2 = this->fields.get_tmp_g();

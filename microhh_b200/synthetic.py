@@ -95,3 +95,62 @@ def slab_of(case, gd_global, gd_local):
         else:
             out[k] = a
     return out
+
+
+def fill_fields_device(f, gd, seed=2, noise=0.01):
+    """The same synthetic dry-CBL-shaped state as make_case, generated ON THE DEVICE straight into the tensors of a
+    dycore.Fields `f` (u, v, w, th and the 2-D surface-model companions), level by level, so that grids whose host copy
+    would not fit the box (1024^3 fp64: 8.7 GB per field) can be benchmarked.  Returns the 1-D base-state profiles
+    (host numpy) for Context.set_basestate.  Values follow make_case's formulas; the noise stream differs (torch)."""
+    import torch
+    dev = f["u"].device
+    tdt = f["u"].dtype
+    gen = torch.Generator(device=dev); gen.manual_seed(seed + 7919*gd.mpicoordy)
+    kc, jc, ic = gd.shape
+    f64 = torch.float64
+    joff = gd.mpicoordy*gd.jmax
+    ar = lambda n: torch.arange(n, device=dev, dtype=f64)
+    x = (ar(ic) - gd.igc + 0.5)*float(gd.dx); xh = (ar(ic) - gd.igc)*float(gd.dx)
+    y = (ar(jc) - gd.jgc + 0.5 + joff)*float(gd.dy); yh = (ar(jc) - gd.jgc + joff)*float(gd.dy)
+    z = gd.z.astype(np.float64); zh = gd.zh.astype(np.float64)
+    Lx, Ly, Lz = float(gd.xsize), float(gd.ysize), float(gd.zsize)
+    twopi = 2.*np.pi
+
+    def modes(xx, yy, zk, phase):
+        X = xx[None, :]; Y = yy[:, None]
+        return (torch.sin(twopi*X/Lx + phase)*torch.cos(twopi*2*Y/Ly)*np.cos(np.pi*zk/Lz)
+                + 0.5*torch.cos(twopi*3*X/Lx)*torch.sin(twopi*Y/Ly + phase)*np.sin(twopi*zk/Lz))
+
+    def inoise(amp):
+        a = torch.zeros((jc, ic), device=dev, dtype=f64)
+        a[gd.jstart:gd.jend, gd.istart:gd.iend] = amp*(torch.rand((gd.jmax, gd.imax), device=dev, dtype=f64, generator=gen) - 0.5)
+        return a
+
+    for k in range(kc):
+        f["u"][k].copy_((modes(xh, y, z[k], 0.3) + inoise(noise)).to(tdt))
+        f["v"][k].copy_((modes(x, yh, z[k], 1.1) + inoise(noise)).to(tdt))
+        if k <= gd.kstart or k >= gd.kend:
+            f["w"][k].zero_()
+        else:
+            f["w"][k].copy_((0.5*modes(x, y, zh[k], 2.0)*np.sin(np.pi*zh[k]/Lz) + inoise(noise)).to(tdt))
+        th = 300. + 0.003*z[k] + 0.1*modes(x, y, z[k], 0.7)
+        if z[k] < 0.1*Lz:
+            th = th + inoise(0.1)
+        f["th"][k].copy_(th.to(tdt))
+        for n, s in enumerate(f.scalars[1:], start=1):
+            f[s][k].copy_((1. + 0.5*modes(x, y, z[k], 0.5*n) + inoise(noise)).to(tdt))
+    X2 = x[None, :]; Y2 = y[:, None]
+    smooth2 = lambda ph: 1. + 0.3*torch.sin(twopi*X2/Lx + ph)*torch.cos(twopi*Y2/Ly)
+    two_d = dict(dudz_mo=0.05*smooth2(0.2), dvdz_mo=0.03*smooth2(1.3), dbdz_mo=-1e-4*smooth2(0.6),
+                 z0m=torch.full((jc, ic), 0.1, device=dev, dtype=f64),
+                 u_fluxbot=-0.02*smooth2(0.9), v_fluxbot=-0.01*smooth2(2.1),
+                 u_gradbot=0.05*smooth2(0.2), v_gradbot=0.03*smooth2(1.3))
+    for s in f.scalars:
+        two_d[f"{s}_fluxbot"] = 0.1*smooth2(0.4)
+        two_d[f"{s}_gradbot"] = -0.01*smooth2(0.4)
+        two_d[f"{s}_gradtop"] = torch.full((jc, ic), 0.003, device=dev, dtype=f64)
+    for n, a in two_d.items():
+        f[n].copy_(a.to(tdt))
+    TF = gd.TF
+    ones = np.ones(kc, TF)
+    return dict(rhoref=ones, rhorefh=ones.copy(), thref=np.full(kc, 300., TF), threfh=np.full(kc, 300., TF))

@@ -1510,6 +1510,221 @@ def rk3_subdt(dt, substep):
 # --------------------------------------------------------------------------------------
 # Same call surface as refbind.RefKernels, backed by the numpy restatement above
 # --------------------------------------------------------------------------------------
+# --------------------------------------------------------------------------------------
+# Boundary_surface: Monin-Obukhov surface model (reference src/boundary_surface.cxx:55-340, 836-990;
+# include/boundary_surface_kernels.h:78-330; include/monin_obukhov.h).  Pinned against the reference's own compiled kernels to
+# rounding (tests/test_oracle_vs_ref.py): the transcendental functions come from numpy instead of libm and the table search is
+# done at float accuracy as in the reference, so the comparison is relative 1e-12 (fp64), not bitwise.
+# --------------------------------------------------------------------------------------
+BC_FLUX, BC_USTAR = 2, 3
+NZL_LUT = 10000          # include/boundary.h:56
+ZL_MAX, ZL_MIN = 10., -1.e4          # include/constants.h:55-56
+DBIG, DHUGE = 1.e9, 1.e30
+
+
+def _most_psim(zeta):
+    """psim_unstable / psim_stable (include/monin_obukhov.h:75-96), selected like fm() does: by the sign of L (= sign of zeta)."""
+    TF = zeta.dtype.type
+    with np.errstate(all="ignore"):
+        phim_u = np.power(TF(1.) + TF(3.6)*np.power(np.abs(zeta), TF(2./3.)), TF(-1./2.))
+        un = TF(3.)*np.log((TF(1.) + TF(1.)/phim_u)/TF(2.))
+        a, b, c, d = TF(1), TF(2)/TF(3), TF(5), TF(0.35)
+        st = -b*(zeta - (c/d))*np.exp(-d*zeta) - a*zeta - (b*c)/d
+    return un, st
+
+
+def _most_psih(zeta):
+    TF = zeta.dtype.type
+    with np.errstate(all="ignore"):
+        phih_u = np.power(TF(1.) + TF(7.9)*np.power(np.abs(zeta), TF(2./3.)), TF(-1./2.))
+        un = TF(3.)*np.log((TF(1.) + TF(1.)/phih_u)/TF(2.))
+        a, b, c, d = TF(1), TF(2)/TF(3), TF(5), TF(0.35)
+        st = -b*(zeta - (c/d))*np.exp(-d*zeta) - np.power(TF(1) + b*a*zeta, TF(1.5)) - (b*c)/d + TF(1)
+    return un, st
+
+
+def most_fm(zsl, z0m, L):
+    """include/monin_obukhov.h:113-119"""
+    TF = L.dtype.type
+    zsl = TF(zsl); z0m = np.asarray(z0m, TF)
+    u1, s1 = _most_psim(zsl/L); u0, s0 = _most_psim(z0m/L)
+    lg = np.log(zsl/z0m)
+    return np.where(L <= TF(0.), TF(KAPPA)/(lg - u1 + u0), TF(KAPPA)/(lg - s1 + s0)).astype(TF)
+
+
+def most_fh(zsl, z0h, L):
+    """include/monin_obukhov.h:121-127"""
+    TF = L.dtype.type
+    zsl = TF(zsl); z0h = np.asarray(z0h, TF)
+    u1, s1 = _most_psih(zsl/L); u0, s0 = _most_psih(z0h/L)
+    lg = np.log(zsl/z0h)
+    return np.where(L <= TF(0.), TF(KAPPA)/(lg - u1 + u0), TF(KAPPA)/(lg - s1 + s0)).astype(TF)
+
+
+def most_phim(zeta):
+    TF = zeta.dtype.type
+    with np.errstate(all="ignore"):
+        un = np.power(TF(1.) + TF(3.6)*np.power(np.abs(zeta), TF(2./3.)), TF(-1./2.))
+    return np.where(zeta <= TF(0.), un, TF(1) + TF(5)*zeta).astype(TF)
+
+
+def most_phih(zeta):
+    TF = zeta.dtype.type
+    with np.errstate(all="ignore"):
+        un = np.power(TF(1.) + TF(7.9)*np.power(np.abs(zeta), TF(2./3.)), TF(-1./2.))
+    return np.where(zeta <= TF(0.), un, (TF(1) + TF(4)*zeta)**2).astype(TF)
+
+
+def surface_prepare_lut(TF, z0m, z0h, zsl, mbcbot, thermobc, nlut=NZL_LUT):
+    """bsk::prepare_lut (include/boundary_surface_kernels.h:78-138): z/L nodes (float) and the evaluation function (float)."""
+    zL_tmp = np.zeros(nlut, TF)
+    zLrange_min = TF(-5.)
+    dzL = TF((ZL_MAX - float(zLrange_min))/(9.*nlut/10. - 1.))
+    zL_tmp[0] = -TF(ZL_MAX)
+    for n in range(1, 9*nlut//10):
+        zL_tmp[n] = zL_tmp[n-1] + dzL
+    zLend = TF(-(ZL_MIN - float(zLrange_min)))
+    r = TF(1.01); r0 = TF(DHUGE)
+    while abs((float(r) - float(r0))/float(r0)) > 1.e-10:
+        r0 = r
+        r = TF(np.power(1. - (float(zLend)/float(dzL))*(1. - float(r)), 1./(nlut/10.)))
+    for n in range(9*nlut//10, nlut):
+        zL_tmp[n] = zL_tmp[n-1] + dzL
+        dzL = TF(dzL*r)
+    zL_sl = (-zL_tmp[::-1]).astype(np.float32)
+    L = (TF(zsl)/zL_sl.astype(TF)).astype(TF)
+    if mbcbot == BC_DIRICHLET and thermobc == BC_FLUX:
+        f_sl = (zL_sl.astype(np.float64)*np.power(most_fm(zsl, TF(z0m), L).astype(np.float64), 3)).astype(np.float32)
+    elif mbcbot == BC_DIRICHLET and thermobc == BC_DIRICHLET:
+        f_sl = (zL_sl.astype(np.float64)*np.power(most_fm(zsl, TF(z0m), L).astype(np.float64), 2)
+                / most_fh(zsl, TF(z0h), L).astype(np.float64)).astype(np.float32)
+    else:
+        f_sl = np.zeros(nlut, np.float32)
+    return zL_sl, f_sl
+
+
+def _find_zL(TF, zL, f, Ri):
+    """bsk::find_zL (include/boundary_surface_kernels.h:245-260), vectorised: the bracket search at float accuracy ends at the
+    first node with f[n] > Ri (or the table ends); inside the table the result is the linear interpolation between n-1 and n."""
+    nl = len(f)
+    n = np.clip(np.searchsorted(f, Ri.astype(np.float32), side="right"), 0, nl - 1)
+    nm = np.maximum(n - 1, 0)
+    Ri = Ri.astype(np.float32)
+    with np.errstate(all="ignore"):
+        interp = (zL[nm] + (Ri - f[nm])/(f[n] - f[nm])*(zL[n] - zL[nm]))
+    edge = (n == 0) | (n == nl - 1)
+    # the reference evaluates the float expression and converts to TF
+    return np.where(edge, zL[n], interp).astype(TF), n
+
+
+class BoundarySurface:
+    """Boundary_surface<TF> with constant z0 and the lookup solver (drycblles: mbcbot = noslip, sbcbot[th] = flux), or
+    Thermo_type::Disabled (neutral).  State: ustar, obuk (jcells, icells)."""
+
+    def __init__(self, g, z0m, z0h, mbcbot, thermobc):
+        TF = g.TF
+        self.g = g
+        self.mbcbot, self.thermobc = mbcbot, thermobc
+        self.z0m = np.full((g.jcells, g.icells), z0m, TF); self.z0h = np.full((g.jcells, g.icells), z0h, TF)
+        self.ustar = np.full((g.jcells, g.icells), DSMALL, TF)      # Boundary_surface::init_surface: ustar = dsmall, obuk = dsmall
+        self.obuk = np.full((g.jcells, g.icells), DSMALL, TF)
+        self.zL_sl, self.f_sl = surface_prepare_lut(TF, z0m, z0h, g.z[g.kstart], mbcbot, thermobc)
+
+    def calc_dutot(self, u, v, ubot, vbot):
+        """bsk::calc_dutot (include/boundary_surface_kernels.h:140-186)"""
+        g = self.g; TF = g.TF
+        k = g.kstart
+        U = u[k]; V = v[k]
+        js, je, is_, ie = g.jstart, g.jend, g.istart, g.iend
+        def S(a, dj=0, di=0):
+            return a[js+dj:je+dj, is_+di:ie+di]
+        h = TF(0.5)
+        uf = TF(1./9)*(h*S(U, -1, -1) + S(U, -1, 0) + S(U, -1, 1) + h*S(U, -1, 2)
+                       + h*S(U, 0, -1) + S(U, 0, 0) + S(U, 0, 1) + h*S(U, 0, 2)
+                       + h*S(U, 1, -1) + S(U, 1, 0) + S(U, 1, 1) + h*S(U, 1, 2))
+        vf = TF(1./9)*(h*S(V, -1, -1) + S(V, 0, -1) + S(V, 1, -1) + h*S(V, 2, -1)
+                       + h*S(V, -1, 0) + S(V, 0, 0) + S(V, 1, 0) + h*S(V, 2, 0)
+                       + h*S(V, -1, 1) + S(V, 0, 1) + S(V, 1, 1) + h*S(V, 2, 1))
+        du2 = (uf - h*(S(ubot) + S(ubot, 0, 1)))**2 + (vf - h*(S(vbot) + S(vbot, 1, 0)))**2
+        dutot = np.zeros((g.jcells, g.icells), TF)
+        dutot[js:je, is_:ie] = np.maximum(np.power(du2, TF(0.5)), TF(1.e-1))
+        boundary_cyclic_2d(g, dutot)
+        return dutot
+
+    def exec(self, c, thref=None, threfh=None, neutral=False):
+        """Boundary_surface::exec (src/boundary_surface.cxx:836-990) on the case dict `c` (u, v, th and their 2-D companions
+        u_bot, u_fluxbot, u_gradbot, ..., dudz_mo, dvdz_mo, dbdz_mo are updated in place)."""
+        g = self.g; TF = g.TF
+        k = g.kstart
+        zsl = g.z[k]
+        dutot = self.calc_dutot(c["u"], c["v"], c["u_bot"], c["v_bot"])
+        if neutral:
+            # stability_neutral (:136-180)
+            if self.mbcbot == BC_USTAR:
+                self.obuk[g.jstart:g.jend, g.istart:g.iend] = -TF(DBIG)
+            else:
+                self.obuk[...] = -TF(DBIG)
+                self.ustar[...] = dutot*most_fm(zsl, self.z0m, self.obuk)
+            bfluxbot = None
+        else:
+            th = c[c["scalars"][0]]; name = c["scalars"][0]
+            # Thermo_dry::get_buoyancy_surf / get_buoyancy_fluxbot / get_db_ref (src/thermo_dry.cxx:133-162, 700-784)
+            bbot = TF(GRAV)/threfh[k]*(c[name + "_bot"] - threfh[k])
+            b = TF(GRAV)/thref[k]*(th[k] - thref[k])
+            bfluxbot = TF(GRAV)/threfh[k]*c[name + "_fluxbot"]
+            db_ref = TF(GRAV)/thref[k]*(thref[k] - threfh[k])
+            if self.mbcbot == BC_USTAR and self.thermobc == BC_FLUX:
+                self.obuk[...] = -self.ustar**3/(TF(KAPPA)*bfluxbot)
+            elif self.mbcbot == BC_DIRICHLET and self.thermobc == BC_FLUX:
+                Ri = (-TF(KAPPA)*bfluxbot*zsl/dutot**3)
+                zL, _ = _find_zL(TF, self.zL_sl, self.f_sl, Ri)
+                self.obuk[...] = zsl/zL
+                self.ustar[...] = dutot*most_fm(zsl, self.z0m, self.obuk)
+            elif self.mbcbot == BC_DIRICHLET and self.thermobc == BC_DIRICHLET:
+                db = b - bbot + db_ref
+                Ri = (TF(KAPPA)*db*zsl/dutot**2)
+                zL, _ = _find_zL(TF, self.zL_sl, self.f_sl, Ri)
+                self.obuk[...] = zsl/zL
+                self.ustar[...] = dutot*most_fm(zsl, self.z0m, self.obuk)
+        ustar, obuk, z0m = self.ustar, self.obuk, self.z0m
+        u, v = c["u"][k], c["v"][k]
+        js, je, is_, ie = g.jstart, g.jend, g.istart, g.iend
+        def S(a, dj=0, di=0):
+            return a[js+dj:je+dj, is_+di:ie+di]
+        # surfm (:182-290), mbcbot = Dirichlet (no-slip): fluxes from the interpolated stability function
+        if self.mbcbot == BC_DIRICHLET:
+            sf = ustar*most_fm(zsl, z0m, obuk)
+            S(c["u_fluxbot"])[...] = -(S(u) - S(c["u_bot"]))*TF(0.5)*(S(sf, 0, -1) + S(sf))
+            S(c["v_fluxbot"])[...] = -(S(v) - S(c["v_bot"]))*TF(0.5)*(S(sf, -1, 0) + S(sf))
+            boundary_cyclic_2d(g, c["u_fluxbot"]); boundary_cyclic_2d(g, c["v_fluxbot"])
+        else:
+            raise NotImplementedError("surfm with mbcbot = ustar is not restated")
+        c["u_gradbot"][...] = (u - c["u_bot"])/zsl
+        c["v_gradbot"][...] = (v - c["v_bot"])/zsl
+        # surfs (:292-340) per scalar
+        for name in c["scalars"]:
+            var = c[name][k]
+            bc = c.get(name + "_bcbot", self.thermobc if name == c["scalars"][0] else BC_FLUX)
+            if bc == BC_DIRICHLET:
+                c[name + "_fluxbot"][...] = -(var - c[name + "_bot"])*ustar*most_fh(zsl, self.z0h, obuk)
+                c[name + "_gradbot"][...] = (var - c[name + "_bot"])/zsl
+            elif bc == BC_FLUX:
+                c[name + "_bot"][...] = c[name + "_fluxbot"]/(ustar*most_fh(zsl, self.z0h, obuk)) + var
+                c[name + "_gradbot"][...] = (var - c[name + "_bot"])/zsl
+        # calc_duvdz_mo / calc_dbdz_mo (include/boundary_surface_kernels.h:188-243)
+        du_c = TF(0.5)*((S(u) - S(c["u_bot"])) + (S(u, 0, 1) - S(c["u_bot"], 0, 1)))
+        dv_c = TF(0.5)*((S(v) - S(c["v_bot"])) + (S(v, 1, 0) - S(c["v_bot"], 1, 0)))
+        fmv = most_fm(zsl, S(z0m), S(obuk))
+        uflux = -du_c*S(ustar)*fmv
+        vflux = -dv_c*S(ustar)*fmv
+        phim = most_phim(zsl/S(obuk))
+        S(c["dudz_mo"])[...] = -uflux/(TF(KAPPA)*zsl*S(ustar))*phim
+        S(c["dvdz_mo"])[...] = -vflux/(TF(KAPPA)*zsl*S(ustar))*phim
+        if not neutral:
+            S(c["dbdz_mo"])[...] = -S(bfluxbot)/(TF(KAPPA)*zsl*S(ustar))*most_phih(zsl/S(obuk))
+        return dutot
+
+
 class NumpyKernels:
     def __init__(self, g):
         self.g = g

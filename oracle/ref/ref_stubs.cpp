@@ -72,6 +72,41 @@ void Boundary_cyclic<TF>::exec(TF* const restrict data, Edge edge)
         }
     }
 }
+// 2-D variant (reference src/boundary_cyclic.cxx:445-507): one level, jtot == 1 replicates the single row.
+template<typename TF>
+void Boundary_cyclic<TF>::exec_2d(TF* restrict data)
+{
+    const Ref_geom& g = ref_geom;
+    const std::ptrdiff_t jj = g.icells;
+    for (int j = 0; j < g.jcells; ++j)
+    {
+        TF* row = data + j*jj;
+        for (int i = 0; i < g.igc; ++i)
+            row[i] = row[g.iend - g.igc + i];
+        for (int i = 0; i < g.igc; ++i)
+            row[g.iend + i] = row[g.istart + i];
+    }
+    if (g.jtot > 1)
+    {
+        for (int j = 0; j < g.jgc; ++j)
+            for (int i = 0; i < g.icells; ++i)
+                data[i + j*jj] = data[i + (g.jend - g.jgc + j)*jj];
+        for (int j = 0; j < g.jgc; ++j)
+            for (int i = 0; i < g.icells; ++i)
+                data[i + (g.jend + j)*jj] = data[i + (g.jstart + j)*jj];
+    }
+    else
+    {
+        for (int j = 0; j < g.jgc; ++j)
+            for (int i = 0; i < g.icells; ++i)
+            {
+                data[i + j*jj]            = data[i + g.jstart*jj];
+                data[i + (g.jend + j)*jj] = data[i + g.jstart*jj];
+            }
+    }
+}
+template void Boundary_cyclic<double>::exec_2d(double* restrict);
+template void Boundary_cyclic<float>::exec_2d(float* restrict);
 template void Boundary_cyclic<double>::exec(double* const restrict, Edge);
 template void Boundary_cyclic<float>::exec(float* const restrict, Edge);
 

@@ -192,3 +192,57 @@ class RefKernels:
 
     def rk3(self, a, at, substep, dt):
         self._call("ref_rk3", a, at, int(substep), float(dt))
+
+
+class RefSurface:
+    """The reference's Monin-Obukhov surface solver (oracle/ref/ref_boundary_surface.cpp): same state and call signature as
+    oracle.BoundarySurface, arithmetic by the reference's own compiled kernels."""
+
+    def __init__(self, g, z0m, z0h, mbcbot, thermobc, fast=False):
+        self.lib = C.CDLL(lib_path(fast))
+        self.g = g
+        TF = g.TF
+        self.sfx = "f64" if TF == np.float64 else "f32"
+        self.ct = C.c_double if TF == np.float64 else C.c_float
+        self.lib.ref_set_geom(g.itot, g.jtot, g.ktot, g.igc, g.jgc, g.kgc)
+        self.mbcbot, self.thermobc = mbcbot, thermobc
+        self.z0m = np.full((g.jcells, g.icells), z0m, TF); self.z0h = np.full((g.jcells, g.icells), z0h, TF)
+        self.ustar = np.full((g.jcells, g.icells), 1.e-9, TF); self.obuk = np.full((g.jcells, g.icells), 1.e-9, TF)
+        n = getattr(self.lib, "ref_surface_nlut_" + self.sfx)()
+        self.nobuk = np.zeros((g.jcells, g.icells), np.int32)
+        self.zL_sl = np.zeros(n, np.float32); self.f_sl = np.zeros(n, np.float32)
+        getattr(self.lib, "ref_surface_lut_" + self.sfx)(self._p(self.zL_sl), self._p(self.f_sl), self.ct(z0m), self.ct(z0h),
+                                                       self.ct(float(g.z[g.kstart])), int(mbcbot), int(thermobc))
+
+    @staticmethod
+    def _p(a):
+        assert a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data_as(C.c_void_p)
+
+    def exec(self, c, thref=None, threfh=None, neutral=False):
+        g = self.g; TF = g.TF
+        self.lib.ref_set_geom(g.itot, g.jtot, g.ktot, g.igc, g.jgc, g.kgc)
+        k = g.kstart
+        dutot = np.zeros((g.jcells, g.icells), TF)
+        if neutral:
+            bfluxbot = np.zeros((g.jcells, g.icells), TF); b = np.zeros(g.shape if hasattr(g, "shape") else c["u"].shape, TF)
+            bbot = np.zeros((g.jcells, g.icells), TF); db_ref = 0.
+        else:
+            name = c["scalars"][0]
+            GRAV = TF(9.81)
+            bbot = np.ascontiguousarray(GRAV/threfh[k]*(c[name + "_bot"] - threfh[k])).astype(TF)
+            b = np.zeros_like(c[name]); b[k] = GRAV/thref[k]*(c[name][k] - thref[k])
+            bfluxbot = np.ascontiguousarray(GRAV/threfh[k]*c[name + "_fluxbot"]).astype(TF)
+            db_ref = float(GRAV/thref[k]*(thref[k] - threfh[k]))
+        f = getattr(self.lib, "ref_surface_exec_" + self.sfx)
+        P = self._p
+        f(P(self.ustar), P(self.obuk), P(self.nobuk), P(dutot), P(c["u"]), P(c["v"]), P(c["u_bot"]), P(c["v_bot"]),
+          P(c["u_fluxbot"]), P(c["v_fluxbot"]), P(c["u_gradbot"]), P(c["v_gradbot"]), P(bfluxbot), P(b), P(bbot), self.ct(db_ref),
+          P(np.ascontiguousarray(g.z)), P(self.z0m), P(self.z0h), P(self.zL_sl), P(self.f_sl), int(self.mbcbot), int(self.thermobc),
+          1, int(bool(neutral)), P(c["dudz_mo"]), P(c["dvdz_mo"]), P(c["dbdz_mo"]))
+        fs = getattr(self.lib, "ref_surface_surfs_" + self.sfx)
+        for name in c["scalars"]:
+            bc = c.get(name + "_bcbot", self.thermobc if name == c["scalars"][0] else 2)
+            fs(P(c[name + "_bot"]), P(c[name + "_gradbot"]), P(c[name + "_fluxbot"]), P(self.ustar), P(self.obuk), P(c[name]),
+               P(self.z0h), self.ct(float(g.z[k])), int(bc))
+        return dutot

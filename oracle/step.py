@@ -20,7 +20,7 @@ def default_params(ns=1):
                 visc=1.e-5, svisc=1.e-5)
 
 
-def dycore_substep(g, K, c, prm, substep, dt, pres=None, timers=None):
+def dycore_substep(g, K, c, prm, substep, dt, pres=None, timers=None, surface_model=None):
     """c: dict of numpy arrays as made by microhh_b200.synthetic.make_case (modified in place)."""
     import time
     t0 = time.perf_counter()
@@ -55,6 +55,15 @@ def dycore_substep(g, K, c, prm, substep, dt, pres=None, timers=None):
     # thermo.exec
     if prm["swthermo"] == "dry":
         K.thermo_dry_buoyancy_tend_2nd(c["wt"], c[scal[0]], c["threfh"])
+    # boundary.exec (Monin-Obukhov surface model) + boundary.set_ghost_cells again (src/model.cxx:398-401)
+    if surface_model is not None:
+        surface_model.exec(c, c["thref"], c["threfh"], neutral=prm["swthermo"] != "dry")
+        for n in ["u", "v"]:
+            K.ghost_cells_bot_2nd(c[n], prm["mbcbot"], c.get(n + "_bot"), c.get(n + "_gradbot"))
+            K.ghost_cells_top_2nd(c[n], prm["mbctop"], c.get(n + "_top"), c.get(n + "_gradtop"))
+        for s_ in scal:
+            K.ghost_cells_bot_2nd(c[s_], prm["sbcbot"], c.get(s_ + "_bot"), c.get(s_ + "_gradbot"))
+            K.ghost_cells_top_2nd(c[s_], prm["sbctop"], c.get(s_ + "_top"), c.get(s_ + "_gradtop"))
     # advec.exec (Advec_2i5::exec src/advec_2i5.cxx:1017-1063, Advec_2::exec src/advec_2.cxx:311-345)
     A = {"2i5": (K.advec_2i5_u, K.advec_2i5_v, K.advec_2i5_w, K.advec_2i5_s),
          "2": (getattr(K, "advec_2_u", None), getattr(K, "advec_2_v", None), getattr(K, "advec_2_w", None), getattr(K, "advec_2_s", None))}[swadvec]
@@ -140,11 +149,11 @@ def dycore_substep_o4(g, K, c, prm, substep, dt, pres=None):
     return pres
 
 
-def dycore_step(g, K, c, prm, dt, timers=None):
+def dycore_step(g, K, c, prm, dt, timers=None, surface_model=None):
     pres = None
     for ss in range(3):
         if prm.get("swadvec") == "4":
             pres = dycore_substep_o4(g, K, c, prm, ss, dt, pres)
         else:
-            pres = dycore_substep(g, K, c, prm, ss, dt, pres, timers)
+            pres = dycore_substep(g, K, c, prm, ss, dt, pres, timers, surface_model)
     return pres

@@ -64,6 +64,20 @@ def test_out_of_path_switches_are_named():
     assert case("andren1994").unsupported() == []                                # neutral LES: calc_evisc_neutral
 
 
+def test_per_scalar_keys_win():
+    """`key[scalar]` overrides (src/boundary.cxx:234-235, src/fields.cxx:412): gabls1 has sbcbot[th]=dirichlet, sbctop[th]=flux."""
+    c = case("gabls1")
+    assert c.scalars == ["th"] and c.sbcbot["th"] == "dirichlet" and c.sbctop["th"] == "flux"
+    p = c.make_params()
+    assert p.sbcbot[0] == capi.BC_DIRICHLET and p.sbctop[0] == capi.BC_NEUMANN
+    assert c.svisc["th"] == 1e-5
+    # neither form present -> required, as in the reference
+    ini = {k: dict(v) for k, v in c.ini.items()}
+    del ini["boundary"]["sbcbot[th]"]
+    with pytest.raises(KeyError):
+        CaseConfig(ini)
+
+
 def test_ini_syntax(tmp_path):
     p = tmp_path / "x.ini"
     p.write_text("[grid]\nitot=8 # comment\n\n# full-line comment\njtot = 4\n[fields]\nrndamp[th]=0.1\n")

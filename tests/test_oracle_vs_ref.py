@@ -277,3 +277,32 @@ def test_full_rk3_step_bitexact(dtype, shape, anel, stretched):
     # the step does something and stays finite
     assert np.isfinite(interior(g, c0["u"])).all()
     assert not np.array_equal(c0["u"], case["u"])
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("thermobc", [O.BC_FLUX, O.BC_DIRICHLET])
+def test_boundary_surface_pinned(dtype, thermobc):
+    """The Monin-Obukhov surface model (lookup solver, constant z0): the numpy restatement against the reference's own compiled
+    kernels (stability, surfm, surfs, calc_dutot, calc_duvdz_mo, calc_dbdz_mo, prepare_lut) over two consecutive calls (the second
+    starts the table search from the first one's index).  Transcendentals come from numpy vs libm: relative 1e-12 / 1e-5."""
+    import copy
+    from util import make_pair, prepare_halos, rel_l2
+    g, gd, case = make_pair(24, 16, 8, dtype, stretched=True)
+    prepare_halos(g, case)
+    for n in ("u", "v", "th"):
+        case[n + "_bot"] = np.zeros(gd.shape2d, dtype)
+    case["th_bot"][...] = 300.5 if thermobc == O.BC_DIRICHLET else 0.
+    a = copy.deepcopy(case); b = copy.deepcopy(case)
+    S1 = O.BoundarySurface(g, 0.1, 0.01, O.BC_DIRICHLET, thermobc)
+    S2 = refbind.RefSurface(g, 0.1, 0.01, O.BC_DIRICHLET, thermobc)
+    assert np.array_equal(S1.zL_sl, S2.zL_sl)
+    tol = 1e-12 if dtype == np.float64 else 1e-5
+    assert rel_l2(S1.f_sl, S2.f_sl) <= (1e-7 if dtype == np.float64 else 1e-5)          # float table
+    for it in range(2):
+        d1 = S1.exec(a, case["thref"], case["threfh"]); d2 = S2.exec(b, case["thref"], case["threfh"])
+    assert rel_l2(d1, d2) <= tol and rel_l2(S1.obuk, S2.obuk) <= tol and rel_l2(S1.ustar, S2.ustar) <= tol
+    sl = (slice(g.jstart, g.jend), slice(g.istart, g.iend))
+    for n in ("u_fluxbot", "v_fluxbot", "u_gradbot", "v_gradbot", "th_bot", "th_gradbot", "th_fluxbot"):
+        assert rel_l2(a[n], b[n]) <= tol, n
+    for n in ("dudz_mo", "dvdz_mo", "dbdz_mo"):
+        assert rel_l2(a[n][sl], b[n][sl]) <= tol, n
