@@ -171,7 +171,8 @@ __global__ void __launch_bounds__(32 * WFFT_WARPS) wfft_x_forward_kernel(TF* __r
         }
         else
         {
-            const cplx<TF>* in = reinterpret_cast<const cplx<TF>*>(spec + r * (2 * nm));
+            // rows of the workspace itself (pitch 2*nm reals), or of a separate compact (k, j, i) array (pitch itot) when src.u is set
+            const cplx<TF>* in = src.u ? reinterpret_cast<const cplx<TF>*>(src.u + r * N) : reinterpret_cast<const cplx<TF>*>(spec + r * (2 * nm));
 #pragma unroll
             for (int n = lane; n < L; n += 32) row[fpad(n)] = in[n];
         }

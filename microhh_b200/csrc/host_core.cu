@@ -370,7 +370,6 @@ int ghost4w_impl(Ctx<TF>* c, TF* w, int conservation)
 template <typename TF>
 int substep_o4_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, int substep, double dt)
 {
-    if (c->nranks > 1) { c->err = "the 4th-order sub-step is single-GPU in this version"; return MHH_E_INVALID; }
     if (prm->swthermo != 0) { c->err = "the 4th-order sub-step has no thermo coupling (swthermo = 0)"; return MHH_E_INVALID; }
     int rc = check_mom<TF>(c, f, false, false);
     if (rc != MHH_OK) return rc;

@@ -350,8 +350,9 @@ int slab_all_to_all(Ctx<TF>* c, bool forward)
     return MHH_OK;
 }
 
+// solver: 0 = transforms only, 2 = tridiagonal (Pres_2), 4 = 7-band (Pres_4)
 template <typename TF>
-int pres_spectral_solve(Ctx<TF>* c, bool do_solve)
+int pres_spectral_solve(Ctx<TF>* c, int solver)
 {
     const GridDev<TF>& g = c->g;
     const int mcl = c->lay.mcl;
@@ -367,11 +368,17 @@ int pres_spectral_solve(Ctx<TF>* c, bool do_solve)
         else fft_y_kernel<TF><<<grid_p, 256, c->smem_y, c->stream>>>(c->specT, c->lay, c->peers, mcl, g.jtot, g.ktot, c->plan_y, c->tw_y, c->mc_y, 0);
         KCHECKN(c, "fft_y_forward_kernel");
     }
-    if (do_solve)
+    if (solver == 2)
     {
         const long long ncol = (long long)mcl * g.jtot;
         tdma_solve_kernel<TF><<<(unsigned)((ncol + 127) / 128), 128, 0, c->stream>>>(c->specT, c->fac, c->coef(), c->lay, mcl, g.jtot, g.kmax, c->lay.m_off, 0);
         KCHECKN(c, "tdma_solve_kernel");
+    }
+    else if (solver == 4)
+    {
+        const long long ncol = (long long)mcl * g.jtot;
+        hdma_solve_kernel<TF><<<(unsigned)((ncol + 127) / 128), 128, 0, c->stream>>>(c->specT, c->lu4, c->lay, mcl, g.jtot, g.kmax);
+        KCHECKN(c, "hdma_solve_kernel");
     }
     if (g.jtot > 1)
     {
@@ -494,7 +501,7 @@ int pres_solve_impl(Ctx<TF>* c, const mhh_fields* f, double sub_dt)
     if (c->wfft_x) wfft_x_forward_launch<TF>(g.itot / 2, true, grid_wx, c->stream, c->spec, src, g, c->lay, c->peers, c->tw_xh, c->tw_xf, nrows);
     else fft_x_forward_kernel<TF, true><<<grid_x, 256, c->smem_x, c->stream>>>(c->spec, src, g, c->lay, c->peers, c->plan_x, c->tw_xh, c->tw_xf, c->rows_x, nrows);
     KCHECKN(c, "fft_x_forward_kernel");
-    int rc = pres_spectral_solve<TF>(c, true);
+    int rc = pres_spectral_solve<TF>(c, 2);
     if (rc != MHH_OK) return rc;
     const TF norm = TF(1.) / ((TF)g.itot * (TF)g.jtot);
     const int fill = slab ? 0 : 1;          // slabs get their north/south ghost rows of p from the neighbours below
@@ -537,7 +544,6 @@ int pres4_prepare(Ctx<TF>* c)
     if (c->lu4) return MHH_OK;
     const GridDev<TF>& g = c->g;
     if (!g.dzi4) { c->err = "Pres_4 needs a 4th-order grid (dzi4 / dzhi4 in mhh_grid_desc, three ghost cells)"; return MHH_E_INVALID; }
-    if (c->nranks > 1) { c->err = "Pres_4 is single-GPU in this version"; return MHH_E_INVALID; }
     if (g.kmax < 4) { c->err = "Pres_4 needs ktot >= 4"; return MHH_E_INVALID; }
     const int kmax = g.kmax, ks = g.kstart;
     const TF dxidxi = (TF)(1. / (double)(g.dx * g.dx)), dyidyi = (TF)(1. / (double)(g.dy * g.dy));
@@ -588,7 +594,7 @@ int pres4_prepare(Ctx<TF>* c)
             M(6, k) = 0.;
         }
     }
-    const long long ncol = (long long)c->nm * g.jtot;
+    const long long ncol = (long long)c->lay.mcl * g.jtot;          // this rank's modes (all of them on a single GPU)
     CUDA_TRY(c, cudaMalloc(&c->d_m7, sizeof(TF) * m.size()));
     CUDA_TRY(c, cudaMalloc(&c->d_bmati4, sizeof(TF) * bi.size()));
     CUDA_TRY(c, cudaMalloc(&c->d_bmatj4, sizeof(TF) * bj.size()));
@@ -599,7 +605,7 @@ int pres4_prepare(Ctx<TF>* c)
     CUDA_TRY(c, cudaMalloc(&c->lu4, sizeof(TF) * nlu));
     c->ws_bytes += (long long)(sizeof(TF) * nlu);
     HdmaCoef<TF> cf{c->d_m7, c->d_bmati4, c->d_bmatj4};
-    hdma_setup_kernel<TF><<<(unsigned)((ncol + 127) / 128), 128, 0, c->stream>>>(c->lu4, cf, c->nm, g.jtot, kmax);
+    hdma_setup_kernel<TF><<<(unsigned)((ncol + 127) / 128), 128, 0, c->stream>>>(c->lu4, cf, c->lay.mcl, g.jtot, kmax, c->lay.m_off);
     KCHECKN(c, "hdma_setup_kernel");
     return MHH_OK;
 }
@@ -623,39 +629,30 @@ int pres4_exec_impl(Ctx<TF>* c, const mhh_fields* f, double sub_dt)
         KCHECKN(c, "pres4_wtbc_kernel");
     }
     const TF dti = (TF)(1. / sub_dt);
-    const long long pitch = 2 * c->nm;
-    if (dim3) pres4_in_kernel<TF, true><<<c->grd_interior(), c->blk(), 0, c->stream>>>(P<TF>(f->u), P<TF>(f->v), P<TF>(f->w), P<TF>(f->ut), P<TF>(f->vt), P<TF>(f->wt), c->spec, pitch, dti, g);
-    else pres4_in_kernel<TF, false><<<c->grd_interior(), c->blk(), 0, c->stream>>>(P<TF>(f->u), P<TF>(f->v), P<TF>(f->w), P<TF>(f->ut), P<TF>(f->vt), P<TF>(f->wt), c->spec, pitch, dti, g);
+    const bool slab = c->nranks > 1;
+    // the right-hand side goes into the (free) p array as a compact (k, j, i) block, like the reference's pres_in does: the x
+    // transform then reads it from there and its store phase is free to be the forward transpose
+    TF* rhs = P<TF>(f->p);
+    const long long pitch = g.itot;
+    if (dim3) pres4_in_kernel<TF, true><<<c->grd_interior(), c->blk(), 0, c->stream>>>(P<TF>(f->u), P<TF>(f->v), P<TF>(f->w), P<TF>(f->ut), P<TF>(f->vt), P<TF>(f->wt), rhs, pitch, dti, g);
+    else pres4_in_kernel<TF, false><<<c->grd_interior(), c->blk(), 0, c->stream>>>(P<TF>(f->u), P<TF>(f->v), P<TF>(f->w), P<TF>(f->ut), P<TF>(f->vt), P<TF>(f->wt), rhs, pitch, dti, g);
     KCHECKN(c, "pres4_in_kernel");
     const long long nrows = (long long)g.jmax * g.ktot;
     const int grid_x = (int)std::min<long long>((nrows + c->rows_x - 1) / c->rows_x, (long long)c->num_sms * 4);
     const int grid_wx = (int)std::min<long long>((nrows + WFFT_WARPS - 1) / WFFT_WARPS, (long long)c->num_sms * 8);
-    RhsSrc<TF> none{};
-    if (c->wfft_x) wfft_x_forward_launch<TF>(g.itot / 2, false, grid_wx, c->stream, c->spec, none, g, c->lay, c->peers, c->tw_xh, c->tw_xf, nrows);
-    else fft_x_forward_kernel<TF, false><<<grid_x, 256, c->smem_x, c->stream>>>(c->spec, none, g, c->lay, c->peers, c->plan_x, c->tw_xh, c->tw_xf, c->rows_x, nrows);
+    RhsSrc<TF> from_p{};
+    from_p.u = rhs;
+    if (c->wfft_x) wfft_x_forward_launch<TF>(g.itot / 2, false, grid_wx, c->stream, c->spec, from_p, g, c->lay, c->peers, c->tw_xh, c->tw_xf, nrows);
+    else fft_x_forward_kernel<TF, false><<<grid_x, 256, c->smem_x, c->stream>>>(c->spec, from_p, g, c->lay, c->peers, c->plan_x, c->tw_xh, c->tw_xf, c->rows_x, nrows);
     KCHECKN(c, "fft_x_forward_kernel");
-    const int grid_p = c->num_sms * 2;
-    const long long ypanels = (long long)((c->nm + WFFT_WARPS - 1) / WFFT_WARPS) * g.ktot;
-    const int grid_wy = (int)std::max<long long>(1, std::min<long long>(ypanels, (long long)c->num_sms * 8));
-    if (dim3)
-    {
-        if (c->wfft_y) wfft_y_launch<TF>(g.jtot, grid_wy, c->stream, c->spec, c->lay, c->peers, c->nm, g.ktot, c->tw_y, 0);
-        else fft_y_kernel<TF><<<grid_p, 256, c->smem_y, c->stream>>>(c->spec, c->lay, c->peers, c->nm, g.jtot, g.ktot, c->plan_y, c->tw_y, c->mc_y, 0);
-        KCHECKN(c, "fft_y_forward_kernel");
-    }
-    const long long ncol = (long long)c->nm * g.jtot;
-    hdma_solve_kernel<TF><<<(unsigned)((ncol + 127) / 128), 128, 0, c->stream>>>(c->spec, c->lu4, c->nm, g.jtot, g.kmax);
-    KCHECKN(c, "hdma_solve_kernel");
-    if (dim3)
-    {
-        if (c->wfft_y) wfft_y_launch<TF>(g.jtot, grid_wy, c->stream, c->spec, c->lay, c->peers, c->nm, g.ktot, c->tw_y, 1);
-        else fft_y_kernel<TF><<<grid_p, 256, c->smem_y, c->stream>>>(c->spec, c->lay, c->peers, c->nm, g.jtot, g.ktot, c->plan_y, c->tw_y, c->mc_y, 1);
-        KCHECKN(c, "fft_y_backward_kernel");
-    }
+    if (slab && !dim3) { c->err = "Pres_4 on y slabs needs jtot > 1"; return MHH_E_INVALID; }
+    if ((rc = pres_spectral_solve<TF>(c, 4)) != MHH_OK) return rc;
     const TF norm = TF(1.) / ((TF)g.itot * (TF)g.jtot);
-    if (c->wfft_x) wfft_x_backward_launch<TF>(g.itot / 2, grid_wx, c->stream, c->spec, P<TF>(f->p), g, c->lay, c->tw_xh, c->tw_xf, nrows, norm, 1);
-    else fft_x_backward_kernel<TF><<<grid_x, 256, c->smem_x, c->stream>>>(c->spec, P<TF>(f->p), g, c->lay, c->plan_x, c->tw_xh, c->tw_xf, c->rows_x, nrows, norm, 1);
+    const int fill = slab ? 0 : 1;
+    if (c->wfft_x) wfft_x_backward_launch<TF>(g.itot / 2, grid_wx, c->stream, c->spec, P<TF>(f->p), g, c->lay, c->tw_xh, c->tw_xf, nrows, norm, fill);
+    else fft_x_backward_kernel<TF><<<grid_x, 256, c->smem_x, c->stream>>>(c->spec, P<TF>(f->p), g, c->lay, c->plan_x, c->tw_xh, c->tw_xf, c->rows_x, nrows, norm, fill);
     KCHECKN(c, "fft_x_backward_kernel");
+    if (slab) { TF* pp = P<TF>(f->p); if ((rc = exchange_ns<TF>(c, &pp, 1, g.jgc, g.kcells)) != MHH_OK) return rc; }
     if (!dim3 && (rc = cyclic_impl<TF>(c, P<TF>(f->p), MHH_EDGE_NORTH_SOUTH, false)) != MHH_OK) return rc;
     {
         ::dim3 b2(64, 4), g2((g.icells + 63) / 64, (g.jcells + 3) / 4);
@@ -677,6 +674,13 @@ int pres4_div_impl(Ctx<TF>* c, const mhh_fields* f, double* out)
     CUDA_TRY(c, cudaMemsetAsync(c->d_red, 0, sizeof(double), c->stream));
     pres4_div_kernel<TF><<<c->grd_interior(), c->blk(), 0, c->stream>>>(P<TF>(f->u), P<TF>(f->v), P<TF>(f->w), g, c->d_red);
     KCHECKN(c, "pres4_div_kernel");
+    if (c->nranks > 1)
+    {
+        if (!c->comm) { c->err = "slab context without communicator: call mhh_comm_init first"; return MHH_E_INVALID; }
+        NcclApi* api = nccl_api(c->err);
+        if (!api) return MHH_E_CUDA;
+        NCCL_TRY(c, api, api->AllReduce(c->d_red, c->d_red, 1, ncclFloat64, ncclMax, c->comm, c->stream));
+    }
     CUDA_TRY(c, cudaMemcpyAsync(c->h_red, c->d_red, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     *out = *c->h_red;
@@ -717,7 +721,7 @@ int fft_roundtrip_impl(Ctx<TF>* c, const TF* in, TF* out, int solve)
     if (c->wfft_x) wfft_x_forward_launch<TF>(g.itot / 2, false, grid_wx, c->stream, c->spec, none, g, c->lay, c->peers, c->tw_xh, c->tw_xf, nrows);
     else fft_x_forward_kernel<TF, false><<<grid_x, 256, c->smem_x, c->stream>>>(c->spec, none, g, c->lay, c->peers, c->plan_x, c->tw_xh, c->tw_xf, c->rows_x, nrows);
     KCHECKN(c, "fft_x_forward_kernel");
-    int rc = pres_spectral_solve<TF>(c, solve != 0);
+    int rc = pres_spectral_solve<TF>(c, solve != 0 ? 2 : 0);
     if (rc != MHH_OK) return rc;
     // backward x into a temporary ghosted array is overkill here: use a private ghosted buffer
     TF* tmp = nullptr;

@@ -349,7 +349,7 @@ __global__ void fft_x_forward_kernel(TF* __restrict__ spec, const RhsSrc<TF> src
             }
             else
             {
-                const TF* in = spec + row * (2 * nm);
+                const TF* in = src.u ? src.u + row * (long long)N : spec + row * (2 * nm);     // separate compact source when src.u is set
                 const int i = i0 + lane;
                 if (i < N) dst[i] = in[i];
             }

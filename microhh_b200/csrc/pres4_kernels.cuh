@@ -58,12 +58,13 @@ struct HdmaCoef
 // LU factorisation of the 7-band matrix of every mode (src/pres_4.cxx:573-667), one thread per mode column.
 // lu: [7][kmax+4][ncol]
 template <typename TF>
-__global__ void hdma_setup_kernel(TF* __restrict__ lu, const HdmaCoef<TF> cf, const int nm, const int jtot, const int kmax)
+__global__ void hdma_setup_kernel(TF* __restrict__ lu, const HdmaCoef<TF> cf, const int nm, const int jtot, const int kmax, const int m_off)
 {
+    // nm: x-modes owned by this rank (all of them on a single GPU), the first being global mode m_off
     const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long ncol = (long long)nm * jtot;
     if (col >= ncol) return;
-    const int l = (int)(col / nm), mx = (int)(col % nm);
+    const int l = (int)(col / nm), mx = (int)(col % nm) + m_off;
     const bool mode00 = (l == 0 && mx == 0);
     const int nr = kmax + 4;
     const long long rs = ncol;                          // row stride
@@ -131,15 +132,17 @@ __global__ void hdma_setup_kernel(TF* __restrict__ lu, const HdmaCoef<TF> cf, co
 // Substitution sweeps (src/pres_4.cxx:669-729) on the complex right-hand side of every mode; rows 2..kmax+1 of the
 // system are the levels of the spectral workspace, the four boundary rows (zero right-hand side) live in registers.
 template <typename TF>
-__global__ void __launch_bounds__(128) hdma_solve_kernel(TF* __restrict__ spec, const TF* __restrict__ lu, const int nm, const int jtot, const int kmax)
+__global__ void __launch_bounds__(128) hdma_solve_kernel(TF* __restrict__ spec, const TF* __restrict__ lu, const SpecLayout lay, const int nm, const int jtot, const int kmax)
 {
     const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long ncol = (long long)nm * jtot;
-    if (col >= ncol) return;
+    const long long ncol_ = (long long)nm * jtot;
+    if (col >= ncol_) return;
     const int nr = kmax + 4;
-    const long long bs = (long long)nr * ncol;
-    cplx<TF>* S = reinterpret_cast<cplx<TF>*>(spec) + col;           // S[k * ncol]: level k
-    auto Lf = [&](int n, int r) -> TF { return lu[n * bs + (long long)r * ncol + col]; };
+    const long long bs = (long long)nr * ncol_;
+    // the y side of the workspace (single GPU: [k][l][m]; slabs: one block per source rank), a column advances by ks per level
+    cplx<TF>* S = reinterpret_cast<cplx<TF>*>(spec) + lay.yidx(0, (int)(col / nm), (int)(col % nm));
+    const long long ncol = lay.ykstride();
+    auto Lf = [&](int n, int r) -> TF { return lu[n * bs + (long long)r * ncol_ + col]; };
     // L y = p: y0 = y1 = 0 (zero right-hand sides), then the interior rows
     cplx<TF> y1 = {0, 0}, y2 = {0, 0}, y3 = {0, 0};                  // y[r-1], y[r-2], y[r-3]
 #pragma unroll 2

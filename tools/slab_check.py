@@ -8,7 +8,8 @@ Multi-GPU parity check of the y-slab decomposition; run under torchrun, one rank
 Every rank owns a slab of ONE global domain.  Checked:
   (1) small grids: one full RK3 step of the slabs == the oracle's single-domain step (rel. L2 within
       BASELINE.json's tolerance), cfl / divergence reductions == the oracle's global values;
-  (2) medium grids (warp-FFT and TMA paths): slabs == the same library on a single GPU, bit for bit.
+  (2) medium grids (warp-FFT and TMA paths): slabs == the same library on a single GPU, bit for bit;
+  (3) the 4th-order DNS configuration (advec_4 + diff_4 + pres_4) on slabs == the oracle.
 TEST INFRASTRUCTURE: imports oracle/.
 """
 import os
@@ -113,6 +114,44 @@ def main():
                 if rank == 0:
                     print(f"[1gpu]   {np.dtype(dtype).name} {shape} P={world} {n}: max|diff| {float(t):.2e} {'ok' if good else 'FAIL'}", flush=True)
             ctx.close(); ctx1.close()
+
+    # ---- (3) the 4th-order DNS configuration (advec_4 + diff_4 + pres_4, 7-band solve) on slabs, against the oracle ----
+    for dtype in (np.float64, np.float32):
+        for shape in ((32, 16*world, 16), (48, 12*world, 12)):
+            itot, jtot, ktot = shape
+            z = stretched_z(ktot, 2.)
+            gg = GridData(itot, jtot, ktot, 6., 4., 2., 3, 3, 3, dtype, z=z, order=4)
+            gl = GridData(itot, jtot, ktot, 6., 4., 2., 3, 3, 3, dtype, z=z, order=4, npy=world, mpicoordy=rank)
+            case_g = make_case(gg, seed=5, noise=0.02)
+            ks, ke = gg.kstart, gg.kend
+            case_g["w"][:ks+1] = 0; case_g["w"][ke:] = 0
+            case_g["th"] = (1. + 0.1*case_g["u"]).astype(dtype)
+            for n in ("u", "v"):
+                for sfx in ("_bot", "_top", "_gradbot", "_gradtop"):
+                    case_g[n + sfx] = np.zeros(gg.shape2d, dtype)
+            case_g["th_gradbot"] = np.zeros(gg.shape2d, dtype); case_g["th_gradtop"] = np.zeros(gg.shape2d, dtype)
+            case_l = slab_of(case_g, gg, gl)
+            ctx = D.Context(gl, lr)
+            ones = np.ones(gl.kcells, dtype)
+            ctx.set_basestate(ones, ones, 300*ones, 300*ones)
+            visc = 1e-3
+            f = D.Fields(ctx, case_l, visc=visc, svisc=visc)
+            prm = D.make_params(swadvec="4", swdiff="4", swthermo=None, surface_model=False, mbcbot=0, mbctop=0)
+            D.Dycore(ctx, prm).step(f, 0.01)
+            ctx.sync()
+            g = O.Grid(itot, jtot, ktot, 6., 4., 2., 3, 3, 3, dtype, z=z, order=4)
+            oprm = ostep.default_params(); oprm.update(swadvec="4", swdiff="4", visc=visc, svisc=visc, mbcbot=0, mbctop=0)
+            ostep.dycore_step(g, O.NumpyKernels(g), case_g, oprm, 0.01)
+            for n in ("u", "v", "w", "th"):
+                a = inter(gl, f[n].cpu().numpy()).astype(np.float64); b = loc(gl, case_g[n]).astype(np.float64)
+                t = torch.tensor([((a - b)**2).sum(), (b**2).sum()], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t)
+                err = float(torch.sqrt(t[0]/t[1]))
+                good = err <= 20*TOL[dtype]
+                ok &= good
+                if rank == 0:
+                    print(f"[o4]     {np.dtype(dtype).name} {shape} P={world} {n}: rel-L2 {err:.2e} {'ok' if good else 'FAIL'}", flush=True)
+            ctx.close()
 
     t = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(t)
