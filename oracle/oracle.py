@@ -1162,11 +1162,16 @@ def thermo_dry_buoyancy_tend_2nd(g, wt, th, threfh):
 # --------------------------------------------------------------------------------------
 # FFTW r2r semantics (reference call sites src/fft.cxx:145-155; FFTW3 manual "The Halfcomplex-format DFT")
 # --------------------------------------------------------------------------------------
+import scipy.fft as _sfft
+
+
 def r2hc(x, axis):
     """FFTW_R2HC along `axis`: [r0, r1, ..., r_{n/2}, i_{(n+1)/2-1}, ..., i_1], unnormalised."""
     n = x.shape[axis]
-    X = np.fft.rfft(x.astype(np.float64), axis=axis)
-    out = np.empty(x.shape, np.float64)
+    # the USESP build of the reference links fftwf: single-precision data are transformed in single precision
+    # (scipy's pocketfft keeps float32; numpy.fft would silently promote to double and flatter the fp32 result)
+    X = _sfft.rfft(x, axis=axis) if x.dtype == np.float32 else np.fft.rfft(x.astype(np.float64), axis=axis)
+    out = np.empty(x.shape, X.real.dtype)
     sl = [slice(None)]*x.ndim
     def put(dst, src):
         d = list(sl); d[axis] = dst
@@ -1184,7 +1189,7 @@ def hc2r(x, axis):
     n = x.shape[axis]
     nre = n//2 + 1
     shp = list(x.shape); shp[axis] = nre
-    X = np.zeros(shp, np.complex128)
+    X = np.zeros(shp, np.complex64 if x.dtype == np.float32 else np.complex128)
     sl = [slice(None)]*x.ndim
     s = list(sl); s[axis] = slice(0, nre)
     X.real[...] = x[tuple(s)]
@@ -1193,7 +1198,7 @@ def hc2r(x, axis):
         d = list(sl); d[axis] = slice(1, nim+1)
         s2 = list(sl); s2[axis] = slice(n-1, nre-1, -1)
         X.imag[tuple(d)] = x[tuple(s2)]
-    out = np.fft.irfft(X, n=n, axis=axis) * n
+    out = (_sfft.irfft(X, n=n, axis=axis) if x.dtype == np.float32 else np.fft.irfft(X, n=n, axis=axis)) * x.dtype.type(n)
     return out.astype(x.dtype)
 
 
@@ -1723,6 +1728,64 @@ class BoundarySurface:
         if not neutral:
             S(c["dbdz_mo"])[...] = -S(bfluxbot)/(TF(KAPPA)*zsl*S(ustar))*most_phih(zsl/S(obuk))
         return dutot
+
+
+# --------------------------------------------------------------------------------------
+# Buffer (damping layer, reference src/buffer.cxx:38-58, 98-124) and Force (large-scale forcings, src/force.cxx:47-272)
+# --------------------------------------------------------------------------------------
+def buffer_kstart(g, zstart):
+    """Buffer::create (src/buffer.cxx:103-116): first full level / half level inside the damping layer."""
+    ks = g.kstart + int((g.z[g.kstart:g.kend] < g.TF(zstart)).sum())
+    ksh = g.kstart + int((g.zh[g.kstart:g.kend] < g.TF(zstart)).sum())
+    return ks, ksh
+
+
+def calc_buffer(g, at, a, abuf, z, zstart, beta, sigma, bufferkstart):
+    """calc_buffer (src/buffer.cxx:38-58): at -= sigma ((z - zstart)/(zsize - zstart))^beta (a - abuf[k]) for k >= bufferkstart."""
+    TF = g.TF
+    zsizebuf = TF(g.zsize) - TF(zstart)
+    for k in range(bufferkstart, g.kend):
+        sigmaz = TF(TF(sigma)*np.power((z[k] - TF(zstart))/zsizebuf, TF(beta)))
+        at[k, g.jstart:g.jend, g.istart:g.iend] -= sigmaz*(a[k, g.jstart:g.jend, g.istart:g.iend] - abuf[k])
+
+
+def field_mean(g, a):
+    """Field3d_operators::calc_mean (src/field3d_operators.cxx:135-155): dz-weighted mean, summed in double."""
+    w = g.dz[g.kstart:g.kend].astype(np.float64)[:, None, None]
+    s = (_S(g, a).astype(np.float64)*w).sum()
+    return g.TF(s/(g.itot*g.jtot*float(g.zsize)))
+
+
+def force_fixed_flux(g, ut, u, uflux, utrans, dt):
+    """Force::exec, Fixed_flux (src/force.cxx:612-624) + enforce_fixed_flux (:65-75)"""
+    TF = g.TF
+    u_mean = field_mean(g, u); ut_mean = field_mean(g, ut)
+    fbody = (TF(uflux) - u_mean - TF(utrans))/TF(dt) - ut_mean
+    _S(g, ut)[...] += TF(fbody)
+    return fbody
+
+
+def force_coriolis_2nd(g, ut, vt, u, v, ug, vg, fc, ugrid, vgrid):
+    """calc_coriolis_2nd (src/force.cxx:78-108)"""
+    TF = g.TF
+    q = TF(0.25)
+    _S(g, ut)[...] += TF(fc)*(q*(_S(g, v, 0, 0, -1) + _S(g, v) + _S(g, v, 0, 1, -1) + _S(g, v, 0, 1, 0)) + TF(vgrid) - _K(g, vg))
+    _S(g, vt)[...] -= TF(fc)*(q*(_S(g, u, 0, -1, 0) + _S(g, u) + _S(g, u, 0, -1, 1) + _S(g, u, 0, 0, 1)) + TF(ugrid) - _K(g, ug))
+
+
+def force_ls_source(g, st, sls):
+    """calc_large_scale_source (src/force.cxx:154-170)"""
+    _S(g, st)[...] += _K(g, sls)
+
+
+def force_wls_local(g, st, s, wls):
+    """advec_wls_2nd_local (src/force.cxx:238-272): first-order upwind with the prescribed subsidence velocity"""
+    for k in range(g.kstart, g.kend):
+        sl = (slice(g.jstart, g.jend), slice(g.istart, g.iend))
+        if wls[k] > 0.:
+            st[k][sl] -= wls[k]*(s[k][sl] - s[k-1][sl])*g.dzhi[k]
+        else:
+            st[k][sl] -= wls[k]*(s[k+1][sl] - s[k][sl])*g.dzhi[k+1]
 
 
 class NumpyKernels:

@@ -107,7 +107,7 @@ def test_les_256x256x128_fp32(igc):
 
 
 @pytest.mark.parametrize("dtype,igc", [(np.float64, 3), (np.float32, 3), (np.float32, 4), (np.float64, 4)])
-@pytest.mark.parametrize("shape", [(160, 20, 24), (192, 36, 40), (128, 10, 33), (64, 7, 17)])
+@pytest.mark.parametrize("shape", [(160, 20, 24), (192, 36, 40), (128, 10, 33), (64, 9, 17)])
 @pytest.mark.parametrize("ns", [1, 2])
 def test_multi_tile_step(dtype, igc, shape, ns):
     """>= 2 x-tiles of the 64-wide marching kernels (blockIdx.x > 0 TMA coordinates), ragged last x tile (160 = 2.5
@@ -135,7 +135,7 @@ def test_multi_tile_step(dtype, igc, shape, ns):
 def test_fused_tendencies_multi_tile(dtype, igc, itot, surface):
     """The fused tendency stage alone (thermo.exec + advec.exec + diff.exec = mom3 / tile kernels) and the eddy-viscosity
     tile kernel on multi-tile grids, against the individual oracle kernels."""
-    g, gd, case = make_pair(itot, 23, 20, dtype, stretched=True, anelastic=True, igc=igc)
+    g, gd, case = make_pair(itot, 25, 20, dtype, stretched=True, anelastic=True, igc=igc)
     prepare_halos(g, case)
     D, ctx, f = gpu_setup(gd, case)
     prm = D.make_params(surface_model=surface)

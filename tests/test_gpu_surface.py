@@ -47,12 +47,16 @@ def test_boundary_surface_exec(dtype, thermobc, shape):
     prm = D.make_params()
     S = D.Boundary_surface(ctx, f, z0m=0.1, z0h=0.01, thermobc=thermobc)
     R = oracle_surface(g, 0.1, 0.01, thermobc)
-    tol = 50*TOL[dtype]
+    # The Obukhov length comes out of a FLOAT table searched with a float Richardson number (include/boundary_surface_kernels.h:
+    # 245-290): a one-ulp difference of the double input flips the float, so everything downstream agrees to float accuracy only.
+    tol = 5e-6 if dtype == np.float64 else 50*TOL[dtype]
     for it in range(2):              # the second call starts the table search from the first one's index
         S.exec(f, prm)
         R.exec(case, case["thref"], case["threfh"])
     ctx.sync()
-    assert rel_l2(S.obuk.cpu().numpy(), R.obuk) <= tol and rel_l2(S.ustar.cpu().numpy(), R.ustar) <= tol
+    zsl = float(g.z[g.kstart])
+    # z/L rather than L: L passes through +-infinity at neutral points
+    assert rel_l2(zsl/S.obuk.cpu().numpy(), zsl/R.obuk) <= tol and rel_l2(S.ustar.cpu().numpy(), R.ustar) <= tol
     sl = (slice(g.jstart, g.jend), slice(g.istart, g.iend))
     for n in ("u_fluxbot", "v_fluxbot", "u_gradbot", "v_gradbot", "th_bot", "th_gradbot", "th_fluxbot"):
         assert rel_l2(f[n].cpu().numpy(), case[n]) <= tol, n
@@ -102,4 +106,4 @@ def test_self_driven_les_three_steps(dtype):
     ctx.sync()
     for n in ("u", "v", "w", "th"):
         assert rel_l2(interior(g, f[n].cpu().numpy()), interior(g, case[n])) <= 20*TOL[dtype], n
-    assert rel_l2(S.ustar.cpu().numpy(), R.ustar) <= 100*TOL[dtype]
+    assert rel_l2(S.ustar.cpu().numpy(), R.ustar) <= (5e-6 if dtype == np.float64 else 100*TOL[dtype])      # float lookup table
