@@ -142,7 +142,7 @@ def side_config(torch, D, GridData, fill_fields_device, name, shape, dtype, S, p
         if order == 4:
             gd = GridData(it, jt, kt, 2*np.pi, np.pi, 2., 3, 3, 3, dtype, order=4)
         else:
-            gd = GridData(it, jt, kt, 25.*it, 25.*jt, 25.*kt, 3 if dtype == np.float64 else 4, 3, 1, dtype)
+            gd = GridData(it, jt, kt, 25.*it, 25.*jt, 25.*kt, 4, 3, 1, dtype)
         ctx = D.Context(gd, device)
         scal = ["th"] + [f"s{n}" for n in range(1, S)] if S > 0 else ["th"]
         f = D.Fields(ctx, None, scalars=scal, visc=1e-5 if order == 2 else 1e-3, svisc=1e-5 if order == 2 else 1e-3)
@@ -190,8 +190,9 @@ def run_ours(args):
     B = np.dtype(dtype).itemsize
     S = 1
     itot_g, jtot_g, ktot = decompose(args.workload, world, args.scaling)
-    # USESP: the adapters ask Grid for igc = 4 (set_minimum_ghost_cells), which makes the fp32 row pitch a multiple of 16 B
-    igc = args.igc if args.igc else (3 if dtype == np.float64 else 4)
+    # the adapters ask Grid for igc = 4 (Grid::set_minimum_ghost_cells): aligned pairs in the TMA-staged kernels, and for
+    # USESP a row pitch that is a multiple of 16 B; --igc 3 runs the reference's minimum for advec_2i5
+    igc = args.igc if args.igc else 4
     gd = GridData(itot_g, jtot_g, ktot, 25.*itot_g, 25.*jtot_g, 25.*ktot, igc, 3, 1, dtype, npy=world, mpicoordy=rank)
     ctx = D.Context(gd, local_rank)
     f = D.Fields(ctx, None)
@@ -435,7 +436,7 @@ def main():
     ap.add_argument("--no-side-configs", action="store_true")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--dt", type=float, default=1.0)
-    ap.add_argument("--igc", type=int, default=0, help="x ghost cells (0 = 3 for fp64, 4 for fp32)")
+    ap.add_argument("--igc", type=int, default=0, help="x ghost cells (0 = 4: what the adapters request; 3 = the reference's minimum)")
     ap.add_argument("--cpu-sample", default="64x64x64")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")

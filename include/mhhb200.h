@@ -132,6 +132,26 @@ typedef struct mhh_surface
 #define MHH_SBC_DIRICHLET 0
 #define MHH_SBC_FLUX      2
 
+/* Damping layer (Buffer<TF>, src/buffer.cxx) and large-scale forcings (Force<TF>, src/force.cxx).  Profiles are DEVICE arrays
+ * of kcells entries (the reference's bufferprofs / ug_g / vg_g / lsprofs_g / wls_g); NULL switches the term off. */
+#define MHH_LSPRES_OFF   0
+#define MHH_LSPRES_UFLUX 1    /* [force] swlspres=uflux: fixed mass flux (enforce_fixed_flux, src/force.cxx:65-75, 612-624) */
+#define MHH_LSPRES_DPDX  2    /* swlspres=dpdx: constant pressure gradient (:626-635) */
+#define MHH_LSPRES_GEO   3    /* swlspres=geo: Coriolis force with a geostrophic wind (:637-660; 2nd / 4th order by the grid) */
+typedef struct mhh_forcing
+{
+    int    swbuffer;                         /* [buffer] swbuffer */
+    double buffer_zstart, buffer_sigma, buffer_beta;
+    const void *bufferprof_u, *bufferprof_v, *bufferprof_w;
+    const void *bufferprof_s[MHH_MAX_SCALARS];
+    int    swlspres;
+    double uflux, dpdx, fc;                  /* [force] uflux, dpdx, fc */
+    const void *ug, *vg;                     /* geostrophic wind profiles */
+    double utrans, vtrans;                   /* [grid] utrans, vtrans (Galilean transformation) */
+    const void *ls_s[MHH_MAX_SCALARS];       /* [force] swls: large-scale source profile per scalar */
+    const void *wls;                         /* [force] swwls=local: subsidence velocity profile applied to every scalar */
+} mhh_forcing;
+
 /* ---- context ----------------------------------------------------------------------------- */
 MHH_API int  mhh_ctx_create(const mhh_grid_desc* grid, int dtype, int device, mhh_ctx** out);
 MHH_API void mhh_ctx_destroy(mhh_ctx* ctx);
@@ -279,6 +299,12 @@ MHH_API int mhh_boundary_surface_exec(mhh_ctx* ctx, const mhh_fields* f, const m
 /* The self-driven LES sub-step in Model::exec's order (src/model.cxx:368-504): mhh_dycore_substep_pre, the surface model,
  * Boundary::set_ghost_cells again, mhh_dycore_substep_post. */
 MHH_API int mhh_dycore_substep_surface(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm, const mhh_surface* s, int substep, double dt);
+/* ---- Buffer<TF>::exec (src/buffer.cxx:170-205) and Force<TF>::exec (src/force.cxx:608-700) on the tendencies in `f`.
+ * mhh_dycore_set_forcing registers them (a copy of the struct) for the fused sub-steps, which then run buffer.exec and
+ * force.exec between diff.exec and pres.exec as Model::exec does (src/model.cxx:416-430); NULL unregisters. */
+MHH_API int mhh_buffer_exec(mhh_ctx* ctx, const mhh_fields* f, const mhh_forcing* forcing);
+MHH_API int mhh_force_exec(mhh_ctx* ctx, const mhh_fields* f, const mhh_forcing* forcing, double sub_dt);
+MHH_API int mhh_dycore_set_forcing(mhh_ctx* ctx, const mhh_forcing* forcing);
 /* Three sub-steps. */
 MHH_API int mhh_dycore_step(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm, double dt);
 /* End-to-end variant with HOST buffers (ghosted layout): copies u,v,w and the scalars to the

@@ -43,6 +43,14 @@ class FieldsC(C.Structure):
                 ("s_fluxlimit", C.c_int * MHH_MAX_SCALARS)]
 
 
+class ForcingC(C.Structure):
+    _fields_ = [("swbuffer", C.c_int), ("buffer_zstart", C.c_double), ("buffer_sigma", C.c_double), ("buffer_beta", C.c_double),
+                ("bufferprof_u", C.c_void_p), ("bufferprof_v", C.c_void_p), ("bufferprof_w", C.c_void_p), ("bufferprof_s", _SA),
+                ("swlspres", C.c_int), ("uflux", C.c_double), ("dpdx", C.c_double), ("fc", C.c_double),
+                ("ug", C.c_void_p), ("vg", C.c_void_p), ("utrans", C.c_double), ("vtrans", C.c_double),
+                ("ls_s", _SA), ("wls", C.c_void_p)]
+
+
 class SurfaceC(C.Structure):
     _fields_ = [("ustar", C.c_void_p), ("obuk", C.c_void_p), ("nobuk", C.c_void_p), ("z0m", C.c_void_p), ("z0h", C.c_void_p),
                 ("dutot", C.c_void_p), ("sbcbot", C.c_int * MHH_MAX_SCALARS)]
@@ -108,6 +116,9 @@ SIGNATURES = {
     "mhh_dycore_set_ghost_cells": (C.c_int, [_vp, _PF, _PP]),
     "mhh_dycore_tendencies": (C.c_int, [_vp, _PF, _PP]),
     "mhh_dycore_substep_post": (C.c_int, [_vp, _PF, _PP, C.c_int, C.c_double]),
+    "mhh_buffer_exec": (C.c_int, [_vp, _PF, C.POINTER(ForcingC)]),
+    "mhh_force_exec": (C.c_int, [_vp, _PF, C.POINTER(ForcingC), C.c_double]),
+    "mhh_dycore_set_forcing": (C.c_int, [_vp, C.POINTER(ForcingC)]),
     "mhh_boundary_surface_init": (C.c_int, [_vp, C.c_double, C.c_double, C.c_int, C.c_int]),
     "mhh_boundary_surface_exec": (C.c_int, [_vp, _PF, _PP, C.POINTER(SurfaceC)]),
     "mhh_dycore_substep_surface": (C.c_int, [_vp, _PF, _PP, C.POINTER(SurfaceC), C.c_int, C.c_double]),

@@ -21,6 +21,7 @@
 #include "tile3_kernels.cuh"
 #include "slab_kernels.cuh"
 #include "surface_kernels.cuh"
+#include "forcing_kernels.cuh"
 #include "order2_kernels.cuh"
 #include "order4_kernels.cuh"
 #include "pres4_kernels.cuh"
@@ -56,6 +57,8 @@ struct mhh_ctx
     // y-slab decomposition (npx = 1, npy = nranks): NCCL communicator over the slab ranks
     int nranks = 1, rank = 0;
     ncclComm_t comm = nullptr;
+    // Buffer / Force registered for the fused sub-steps (mhh_dycore_set_forcing)
+    mhh_forcing forcing{}; bool forcing_set = false;
     virtual ~mhh_ctx() {}
 };
 
@@ -129,6 +132,9 @@ struct Ctx : mhh_ctx
     bool basestate_set = false;
     // Boundary_surface lookup table (z/L nodes and evaluation function, float like the reference), built by mhh_boundary_surface_init
     float *d_zL_sl = nullptr, *d_f_sl = nullptr;
+    // Buffer / Force: per-level damping factors (u, v, scalars | w) and the two device sums of the fixed-mass-flux forcing
+    TF *d_sigmaz = nullptr; double *d_sums = nullptr;
+    double buf_key[3] = {-1., -1., -1.}; int buf_k = 0, buf_kh = 0;
     int surf_mbcbot = -1, surf_thermobc = -1;
     std::vector<TF> h_thref, h_threfh;
     double *d_red = nullptr;       // reduction scalar
@@ -147,7 +153,7 @@ struct Ctx : mhh_ctx
     ~Ctx() override
     {
         cudaSetDevice(device);
-        cudaFree(d_zL_sl); cudaFree(d_f_sl);
+        cudaFree(d_zL_sl); cudaFree(d_f_sl); cudaFree(d_sigmaz); cudaFree(d_sums);
         cudaFree(d_prof); cudaFree(d_mlen0); cudaFree(tw_xh); cudaFree(tw_xf); cudaFree(tw_y);
         cudaFree(d_bmati); cudaFree(d_bmatj); cudaFree(d_a); cudaFree(d_c); cudaFree(d_dz2rho); cudaFree(d_dz2);
         for (int r = 0; r < MAX_SLAB_RANKS; ++r)
@@ -185,6 +191,8 @@ template <typename TF> int slab_barrier(Ctx<TF>* c, const char* name);
 template <typename TF> int exchange_ns(Ctx<TF>* c, TF* const* flds, int nf, int w, int nk);
 template <typename TF> int cyclic_impl(Ctx<TF>* c, TF* fld, int edge, bool two_d);
 template <typename TF> int cyclic_fields(Ctx<TF>* c, TF* const* flds, int nf);
+template <typename TF> int buffer_exec_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_forcing* fo);
+template <typename TF> int force_exec_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_forcing* fo, double sub_dt);
 // host_tend.cu
 template <typename TF> int check_mom(Ctx<TF>* c, const mhh_fields* f, bool need_evisc, bool surface);
 template <typename TF> int evisc_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, const TF* n2);

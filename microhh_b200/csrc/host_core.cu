@@ -386,8 +386,13 @@ int substep_o4_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, int 
     if ((rc = o4_impl<TF>(c, f, true, false)) != MHH_OK) return rc;
     if ((rc = ghost4w_impl<TF>(c, P<TF>(f->w), 0)) != MHH_OK) return rc;
     if ((rc = o4_impl<TF>(c, f, false, true)) != MHH_OK) return rc;
-    if ((rc = ghost4w_impl<TF>(c, P<TF>(f->w), 1)) != MHH_OK) return rc;
     const double cBd[3] = {1. / 3., 15. / 16., 8. / 15.};
+    if (c->forcing_set)
+    {
+        if ((rc = buffer_exec_impl<TF>(c, f, &c->forcing)) != MHH_OK) return rc;
+        if ((rc = force_exec_impl<TF>(c, f, &c->forcing, cBd[substep] * dt)) != MHH_OK) return rc;
+    }
+    if ((rc = ghost4w_impl<TF>(c, P<TF>(f->w), 1)) != MHH_OK) return rc;
     if ((rc = pres4_exec_impl<TF>(c, f, cBd[substep] * dt)) != MHH_OK) return rc;
     if ((rc = ghost4w_impl<TF>(c, P<TF>(f->w), 0)) != MHH_OK) return rc;
     TF* tend[3 + MHH_MAX_SCALARS] = {P<TF>(f->ut), P<TF>(f->vt), P<TF>(f->wt)};
@@ -486,6 +491,13 @@ int substep_post_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, in
     if (substep < 0 || substep > 2) { c->err = "substep must be 0..2"; return MHH_E_INVALID; }
     int rc = tendencies_impl<TF>(c, f, prm);
     if (rc != MHH_OK) return rc;
+    // buffer.exec and force.exec ("keep this one always right before the pressure", src/model.cxx:416-430) when registered
+    if (c->forcing_set)
+    {
+        const double cBf[3] = {1. / 3., 15. / 16., 8. / 15.};
+        if ((rc = buffer_exec_impl<TF>(c, f, &c->forcing)) != MHH_OK) return rc;
+        if ((rc = force_exec_impl<TF>(c, f, &c->forcing, cBf[substep] * dt)) != MHH_OK) return rc;
+    }
     // 4. pres.exec (solve), then pressure correction fused with timeloop.exec
     const TF cA[3] = {TF(0.), TF(-5. / 9.), TF(-153. / 128.)};
     const TF cB[3] = {TF(1. / 3.), TF(15. / 16.), TF(8. / 15.)};
@@ -499,6 +511,105 @@ int substep_post_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, in
     KCHECKN(c, "pres_out_rk3_kernel");
     for (int n = 0; n < f->ns; ++n)
         if ((rc = rk3_impl<TF>(c, P<TF>(f->s[n]), P<TF>(f->st[n]), substep, dt)) != MHH_OK) return rc;
+    return MHH_OK;
+}
+
+// ---- Buffer (damping layer) and Force (large-scale forcings) ----------------------------------------------------------
+// Buffer<TF>::exec (src/buffer.cxx:170-205): u, v and the scalars from the first full level inside the layer, w from the first
+// half level; the damping factor sigma ((z - zstart)/(zsize - zstart))^beta is tabulated per level.
+template <typename TF>
+int buffer_exec_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_forcing* fo)
+{
+    const GridDev<TF>& g = c->g;
+    NEED(c, fo, "forcing"); NEED(c, f, "fields");
+    if (!fo->swbuffer) return MHH_OK;
+    const int kc = g.kcells;
+    if (!c->d_sigmaz) CUDA_TRY(c, cudaMalloc(&c->d_sigmaz, sizeof(TF) * 2 * kc));
+    if (c->buf_key[0] != fo->buffer_zstart || c->buf_key[1] != fo->buffer_sigma || c->buf_key[2] != fo->buffer_beta)
+    {
+        // Buffer::create (src/buffer.cxx:103-124) and the per-level factors of calc_buffer (:46-49)
+        const TF zstart = (TF)fo->buffer_zstart, sigma = (TF)fo->buffer_sigma, beta = (TF)fo->buffer_beta;
+        const TF zsizebuf = g.zsize - zstart;
+        std::vector<TF> zh(kc), sg(2 * (size_t)kc, TF(0));
+        CUDA_TRY(c, cudaMemcpy(zh.data(), g.zh, sizeof(TF) * kc, cudaMemcpyDeviceToHost));
+        int kb = g.kstart, kbh = g.kstart;
+        for (int k = g.kstart; k < g.kend; ++k) { if (c->h_z[k] < zstart) ++kb; if (zh[k] < zstart) ++kbh; }
+        if (kbh == g.kend) { c->err = "Buffer is too close to the model top"; return MHH_E_INVALID; }
+        for (int k = kb; k < g.kend; ++k) sg[k] = sigma * std::pow((c->h_z[k] - zstart) / zsizebuf, beta);
+        for (int k = kbh; k < g.kend; ++k) sg[kc + k] = sigma * std::pow((zh[k] - zstart) / zsizebuf, beta);
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_sigmaz, sg.data(), sizeof(TF) * 2 * kc, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        c->buf_k = kb; c->buf_kh = kbh;
+        c->buf_key[0] = fo->buffer_zstart; c->buf_key[1] = fo->buffer_sigma; c->buf_key[2] = fo->buffer_beta;
+    }
+    dim3 b = c->blk();
+    auto launch = [&](TF* at, const TF* a, const TF* prof, bool half) -> int {
+        if (!prof) return MHH_OK;                          // no profile: the field is not damped
+        NEED(c, at, "tendency"); NEED(c, a, "field");
+        const int k0 = half ? c->buf_kh : c->buf_k;
+        if (k0 >= g.kend) return MHH_OK;
+        dim3 gr((g.imax + 63) / 64, (g.jmax + 3) / 4, g.kend - k0);
+        buffer_kernel<TF><<<gr, b, 0, c->stream>>>(at, a, prof, c->d_sigmaz + (half ? kc : 0), k0, g);
+        KCHECKN(c, "buffer_kernel");
+        return MHH_OK; };
+    int rc;
+    if ((rc = launch(P<TF>(f->ut), P<TF>(f->u), P<TF>(fo->bufferprof_u), false)) != MHH_OK) return rc;
+    if ((rc = launch(P<TF>(f->vt), P<TF>(f->v), P<TF>(fo->bufferprof_v), false)) != MHH_OK) return rc;
+    if ((rc = launch(P<TF>(f->wt), P<TF>(f->w), P<TF>(fo->bufferprof_w), true)) != MHH_OK) return rc;
+    for (int n = 0; n < f->ns; ++n)
+        if ((rc = launch(P<TF>(f->st[n]), P<TF>(f->s[n]), P<TF>(fo->bufferprof_s[n]), false)) != MHH_OK) return rc;
+    return MHH_OK;
+}
+
+// Force<TF>::exec (src/force.cxx:608-700): large-scale pressure force (fixed mass flux / pressure gradient / geostrophic wind
+// with Coriolis), large-scale sources and local subsidence of the scalars
+template <typename TF>
+int force_exec_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_forcing* fo, double sub_dt)
+{
+    const GridDev<TF>& g = c->g;
+    NEED(c, fo, "forcing"); NEED(c, f, "fields");
+    dim3 b = c->blk(), gr = c->grd_interior();
+    if (fo->swlspres == MHH_LSPRES_UFLUX)
+    {
+        NEED(c, f->u, "u"); NEED(c, f->ut, "ut");
+        if (!c->d_sums) CUDA_TRY(c, cudaMalloc(&c->d_sums, 2 * sizeof(double)));
+        CUDA_TRY(c, cudaMemsetAsync(c->d_sums, 0, 2 * sizeof(double), c->stream));
+        mean_uut_kernel<TF><<<gr, b, 0, c->stream>>>(P<TF>(f->u), P<TF>(f->ut), g, c->d_sums);
+        KCHECKN(c, "mean_uut_kernel");
+        if (c->nranks > 1)
+        {
+            if (!c->comm) { c->err = "slab context without communicator: call mhh_comm_init first"; return MHH_E_INVALID; }
+            NcclApi* api = nccl_api(c->err);
+            if (!api) return MHH_E_CUDA;
+            NCCL_TRY(c, api, api->AllReduce(c->d_sums, c->d_sums, 2, ncclFloat64, ncclSum, c->comm, c->stream));
+        }
+        const double inv_vol = 1. / ((double)g.itot * (double)g.jtot * (double)g.zsize);
+        body_force_kernel<TF, true><<<gr, b, 0, c->stream>>>(P<TF>(f->ut), c->d_sums, inv_vol, (TF)fo->uflux, (TF)fo->utrans, (TF)sub_dt, TF(0), g);
+        KCHECKN(c, "body_force_kernel");
+    }
+    else if (fo->swlspres == MHH_LSPRES_DPDX)
+    {
+        NEED(c, f->ut, "ut");
+        body_force_kernel<TF, false><<<gr, b, 0, c->stream>>>(P<TF>(f->ut), nullptr, 0., TF(0), TF(0), TF(1), (TF)(-1. * fo->dpdx), g);
+        KCHECKN(c, "body_force_kernel");
+    }
+    else if (fo->swlspres == MHH_LSPRES_GEO)
+    {
+        NEED(c, f->u, "u"); NEED(c, f->v, "v"); NEED(c, f->ut, "ut"); NEED(c, f->vt, "vt"); NEED(c, fo->ug, "ug"); NEED(c, fo->vg, "vg");
+        if (g.dzi4) coriolis_kernel<TF, 4><<<gr, b, 0, c->stream>>>(P<TF>(f->ut), P<TF>(f->vt), P<TF>(f->u), P<TF>(f->v), P<TF>(fo->ug), P<TF>(fo->vg), (TF)fo->fc, (TF)fo->utrans, (TF)fo->vtrans, g);
+        else coriolis_kernel<TF, 2><<<gr, b, 0, c->stream>>>(P<TF>(f->ut), P<TF>(f->vt), P<TF>(f->u), P<TF>(f->v), P<TF>(fo->ug), P<TF>(fo->vg), (TF)fo->fc, (TF)fo->utrans, (TF)fo->vtrans, g);
+        KCHECKN(c, "coriolis_kernel");
+    }
+    else if (fo->swlspres != MHH_LSPRES_OFF) { c->err = "force: unknown swlspres"; return MHH_E_INVALID; }
+    for (int n = 0; n < f->ns; ++n)
+    {
+        const TF* sls = P<TF>(fo->ls_s[n]);
+        const TF* wls = P<TF>(fo->wls);
+        if (!sls && !wls) continue;
+        NEED(c, f->s[n], "scalar"); NEED(c, f->st[n], "scalar tendency");
+        scalar_forcing_kernel<TF><<<gr, b, 0, c->stream>>>(P<TF>(f->st[n]), P<TF>(f->s[n]), sls, wls, g);
+        KCHECKN(c, "scalar_forcing_kernel");
+    }
     return MHH_OK;
 }
 
@@ -1100,6 +1211,23 @@ int mhh_dycore_substep_post(mhh_ctx* ctx, const mhh_fields* f, const mhh_params*
 {
     if (!f) return MHH_E_INVALID;
     DISPATCH1(ctx, substep_post_impl<TF>(c, f, prm, substep, dt));
+}
+
+int mhh_buffer_exec(mhh_ctx* ctx, const mhh_fields* f, const mhh_forcing* fo)
+{
+    DISPATCH1(ctx, buffer_exec_impl<TF>(c, f, fo));
+}
+
+int mhh_force_exec(mhh_ctx* ctx, const mhh_fields* f, const mhh_forcing* fo, double sub_dt)
+{
+    DISPATCH1(ctx, force_exec_impl<TF>(c, f, fo, sub_dt));
+}
+
+int mhh_dycore_set_forcing(mhh_ctx* ctx, const mhh_forcing* fo)
+{
+    if (!ctx) return MHH_E_INVALID;
+    if (fo) { ctx->forcing = *fo; ctx->forcing_set = true; } else ctx->forcing_set = false;
+    return MHH_OK;
 }
 
 int mhh_boundary_surface_init(mhh_ctx* ctx, double z0m, double z0h, int mbcbot, int thermobc)

@@ -225,7 +225,7 @@ int mom_tile_launch(Ctx<TF>* c, const MomArgs<TF>& a, bool surface, bool buoy)
 
 // warp-specialised variant (tile3_kernels.cuh): one CTA of (3+nsc)*ty+1 warps per SM; the first scalar rides along
 template <typename TF>
-int mom3_launch(Ctx<TF>* c, const MomArgs<TF>& a, const ScalArgs<TF>* sc, bool surface, bool buoy)
+int mom3_launch(Ctx<TF>* c, const MomArgs<TF>& a, const ScalArgs<TF>* sc, bool surface, bool buoy, int hl)
 {
     const GridDev<TF>& g = c->g;
     const int nsc = sc ? 1 : 0;
@@ -236,21 +236,23 @@ int mom3_launch(Ctx<TF>* c, const MomArgs<TF>& a, const ScalArgs<TF>* sc, bool s
     t.kchunk = pick_kchunk_waves(ntx * nty, g.kmax, c->num_sms, 2);
     t.prefetch = c->prefetch;
     dim3 grid(ntx, nty, (g.kmax + t.kchunk - 1) / t.kchunk);
-    const size_t smem = mom3_smem(sizeof(TF), t.kchunk, ty, nsc);
+    const size_t smem = mom3_smem(sizeof(TF), t.kchunk, ty, nsc, hl);
     CUtensorMap tu, tv, tw, te, ts, tut, tvt, twt, tst;
     const int by = ty + 2 * T2_H;
-    constexpr int T2_PX = t2_px((int)sizeof(TF));
-    if (!make_field_tmap<TF>(&tu, a.u, g, T2_PX, by) || !make_field_tmap<TF>(&tv, a.v, g, T2_PX, by) ||
-        !make_field_tmap<TF>(&tw, a.w, g, T2_PX, by) || !make_field_tmap<TF>(&te, a.evisc, g, T2_PX, by) ||
-        !make_field_tmap<TF>(&ts, sc ? (const void*)sc->s : (const void*)a.u, g, T2_PX, by) ||
-        !make_field_tmap<TF>(&tut, a.ut, g, T2_PX, ty) || !make_field_tmap<TF>(&tvt, a.vt, g, T2_PX, ty) ||
-        !make_field_tmap<TF>(&twt, a.wt, g, T2_PX, ty) || !make_field_tmap<TF>(&tst, sc ? (const void*)sc->st : (const void*)a.ut, g, T2_PX, ty))
+    const int px = t2_px(hl);
+    if (!make_field_tmap<TF>(&tu, a.u, g, px, by) || !make_field_tmap<TF>(&tv, a.v, g, px, by) ||
+        !make_field_tmap<TF>(&tw, a.w, g, px, by) || !make_field_tmap<TF>(&te, a.evisc, g, px, by) ||
+        !make_field_tmap<TF>(&ts, sc ? (const void*)sc->s : (const void*)a.u, g, px, by) ||
+        !make_field_tmap<TF>(&tut, a.ut, g, px, ty) || !make_field_tmap<TF>(&tvt, a.vt, g, px, ty) ||
+        !make_field_tmap<TF>(&twt, a.wt, g, px, ty) || !make_field_tmap<TF>(&tst, sc ? (const void*)sc->st : (const void*)a.ut, g, px, ty))
     { c->err = "cuTensorMapEncodeTiled failed"; return MHH_E_CUDA; }
-#define M3(S, B, N, Y) do { \
+#define M3(S, B, N, Y, H) do { \
         static size_t attr_smem_dev[64] = {0}; size_t& attr_smem = attr_smem_dev[c->device & 63];   /* the attribute is per device */ \
-        if (attr_smem < smem) { CUDA_TRY(c, cudaFuncSetAttribute(mom3_kernel<TF, S, B, N, Y>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; } \
-        mom3_kernel<TF, S, B, N, Y><<<grid, 32 * ((3 + N) * Y + 1), smem, c->stream>>>(tu, tv, tw, te, ts, tut, tvt, twt, tst, t, g); } while (0)
-#define M3Y(S, B, N) do { if (ty == 3) M3(S, B, N, 3); else if (ty == 5) M3(S, B, N, 5); else M3(S, B, N, 4); } while (0)
+        if (attr_smem < smem) { CUDA_TRY(c, cudaFuncSetAttribute(mom3_kernel<TF, S, B, N, Y, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; } \
+        mom3_kernel<TF, S, B, N, Y, H><<<grid, 32 * ((3 + N) * Y + 1), smem, c->stream>>>(tu, tv, tw, te, ts, tut, tvt, twt, tst, t, g); } while (0)
+    // the odd-aligned variant (halo 3) exists for fp64 only
+#define M3H(S, B, N, Y) do { if (hl == 4) M3(S, B, N, Y, 4); else if (sizeof(TF) == 8) M3(S, B, N, Y, (sizeof(TF) == 8 ? 3 : 4)); } while (0)
+#define M3Y(S, B, N) do { if (ty == 3) M3H(S, B, N, 3); else if (ty == 5) M3H(S, B, N, 5); else M3H(S, B, N, 4); } while (0)
     if (nsc)
     {
         if (surface && buoy) M3Y(true, true, 1);
@@ -266,6 +268,7 @@ int mom3_launch(Ctx<TF>* c, const MomArgs<TF>& a, const ScalArgs<TF>* sc, bool s
         else M3Y(false, false, 0);
     }
 #undef M3Y
+#undef M3H
 #undef M3
     KCHECKN(c, "mom3_kernel");
     return MHH_OK;
@@ -312,9 +315,10 @@ int tend_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, bool adv, 
     int first_scalar = 0;       // scalars [0, first_scalar) were handled by the fused momentum kernel
     if (tiles)
     {
-        // the TMA box origin istart - halo must be 16-byte aligned: fp64 igc odd (3), fp32 igc a multiple of 4 (the USESP
-        // adapters ask Grid for igc = 4); everything else runs the cp.async tile kernels
-        const bool tma = !c->no_tma && (((g.igc - t2_hl((int)sizeof(TF))) * (int)sizeof(TF)) % 16) == 0
+        // TMA-staged path: needs a 16-byte aligned box origin istart - halo (halo 4 with igc = 4, what the adapters request;
+        // halo 3 for fp64 fields with igc = 3); everything else runs the cp.async tile kernels
+        const int hl = t2_pick_hl(g.igc, (int)sizeof(TF));
+        const bool tma = !c->no_tma && hl != 0
                          && tma_ok<TF>(g, {a.u, a.v, a.w, a.evisc, a.ut, a.vt, a.wt, buoy ? (const void*)a.th : (const void*)a.u});
         if (tma)
         {
@@ -323,7 +327,7 @@ int tend_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, bool adv, 
             // measured on B200 fp64 (512^3): 5.8 ms fused (3 rows, 13 warps) vs 4.3 + 2.9 ms as two kernels
             bool fuse = f->ns > 0 && c->fuse_scalar && !f->s_fluxlimit[0];
             if (fuse) { s0 = scal_args<TF>(c, f, prm, 0); fuse = tma_ok<TF>(g, {s0.s, s0.st}); }
-            rc = mom3_launch<TF>(c, a, fuse ? &s0 : nullptr, surface, buoy);
+            rc = mom3_launch<TF>(c, a, fuse ? &s0 : nullptr, surface, buoy, hl);
             if (fuse) first_scalar = 1;
         }
         else rc = mom_tile_launch<TF>(c, a, surface, buoy);

@@ -65,18 +65,25 @@ template <> struct V2T<float>  { typedef float2 type; };
 
 // ---- tile geometry ---------------------------------------------------------------------------
 constexpr int T2_W  = 64;                 // tile width  (2 columns per lane)
-// x halo.  The TMA box origin must be 16-byte aligned in global memory (probed on B200: an odd fp64 x coordinate raises
-// "illegal instruction", a negative even one is fine and zero-filled).
-//   fp64, igc = 3: the interior starts at an odd element, so the box starts 3 columns to the left (origin 64 bx, even) and
-//     the thread's own pair sits at an ODD shared-memory column: rows along x are read as aligned 16-byte pairs starting
-//     one column early, the pair itself as two 8-byte loads.
-//   fp32, igc = 4 (what the USESP adapters ask Grid for: icells % 4 == 0 makes the row pitch a multiple of 16 bytes):
-//     halo 4, origin 64 bx (a multiple of 4 elements), own pair at an even column = one aligned 8-byte load.
-constexpr int t2_hl(int elem) { return elem == 8 ? 3 : 4; }
-constexpr int t2_px(int elem) { return T2_W + 2 * t2_hl(elem); }      // 70 / 72: plane pitch = TMA box width (multiples of 16 bytes)
+// x halo HL (3 or 4).  The TMA box origin istart + 64 bx - HL must be 16-byte aligned in global memory (probed on B200: an odd
+// fp64 x coordinate raises "illegal instruction", a negative even one is fine and zero-filled).
+//   HL = 4 (igc = 4: what the adapters ask Grid for, set_minimum_ghost_cells; fp64 and fp32): the thread's own pair sits at
+//     an EVEN column of the staged plane and at a 16-byte (fp32: 8-byte) aligned global address: one vector LDS / LDG / STG
+//     per pair.
+//   HL = 3 (fp64 fields with the reference's minimum igc = 3): the interior starts at an odd element, the own pair sits at
+//     an ODD shared-memory column and is read as two 8-byte loads; rows along x are read as aligned 16-byte pairs starting
+//     one column early.  24 % more shared-memory wavefronts than HL = 4 (ncu), and 8-byte global accesses.
+constexpr int t2_px(int hl) { return T2_W + 2 * hl; }      // 70 / 72: plane pitch = TMA box width (multiples of 16 bytes)
 constexpr int T2_H  = 3;                  // y halo
 // plane size in elements, padded so that every plane starts on a 128-byte boundary (TMA destination alignment)
-constexpr int t2_plane(int ty, int elem) { return (t2_px(elem) * (ty + 2 * T2_H) * elem + 127) / 128 * 128 / elem; }
-constexpr int t2_box_bytes(int ty, int elem) { return t2_px(elem) * (ty + 2 * T2_H) * elem; }
+constexpr int t2_plane(int ty, int elem, int hl) { return (t2_px(hl) * (ty + 2 * T2_H) * elem + 127) / 128 * 128 / elem; }
+constexpr int t2_box_bytes(int ty, int elem, int hl) { return t2_px(hl) * (ty + 2 * T2_H) * elem; }
+// the halo a grid can use: 4 when istart - 4 is 16-byte aligned, else 3 for fp64 when istart - 3 is; 0 = no TMA path
+inline int t2_pick_hl(int igc, int elem)
+{
+    if (igc >= 4 && ((igc - 4) * elem) % 16 == 0) return 4;
+    if (elem == 8 && igc >= 3 && ((igc - 3) * elem) % 16 == 0) return 3;
+    return 0;
+}
 
 } // namespace mhh

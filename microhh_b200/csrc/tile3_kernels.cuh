@@ -24,8 +24,8 @@ __device__ __forceinline__ void mbar_arrive(unsigned bar)
 
 constexpr int T3_RING = 4;
 
-inline size_t mom3_smem(size_t elem, int kchunk, int ty, int nsc)
-{ return 128 + ((size_t)(4 + nsc) * T3_RING * t2_plane(ty, (int)elem) + (size_t)8 * (kchunk + 3)) * elem + 128; }
+inline size_t mom3_smem(size_t elem, int kchunk, int ty, int nsc, int hl)
+{ return 128 + ((size_t)(4 + nsc) * T3_RING * t2_plane(ty, (int)elem, hl) + (size_t)8 * (kchunk + 3)) * elem + 128; }
 
 // the first prognostic scalar rides along as a fourth warp group (NSC = 1): advec_s + diff_c on the same planes
 template <typename TF>
@@ -37,7 +37,7 @@ struct Tend3Args
     int prefetch;
 };
 
-template <typename TF, bool SURFACE, bool BUOY, int NSC, int TY>
+template <typename TF, bool SURFACE, bool BUOY, int NSC, int TY, int HL>
 __global__ void __launch_bounds__(32 * ((3 + NSC) * TY + 1), 1)
 mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_v,
             const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_e,
@@ -52,11 +52,11 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(sbase);     // full[RING], empty[RING]
     TF* sm = reinterpret_cast<TF*>(sbase + 128);
     constexpr int RING = T3_RING;
-    constexpr int PLANE = t2_plane(TY, (int)sizeof(TF)), P = t2_px((int)sizeof(TF)), T2_HL = t2_hl((int)sizeof(TF));
+    constexpr int PLANE = t2_plane(TY, (int)sizeof(TF), HL), P = t2_px(HL), T2_HL = HL;
     constexpr int NT = 32 * ((3 + NSC) * TY + 1), NCW = (3 + NSC) * TY;
-    constexpr bool ODD = (T2_HL & 1) != 0;          // own pair at an odd shared-memory column (fp64)
+    constexpr bool ODD = (HL & 1) != 0;             // own pair at an odd shared-memory column (fp64 with igc = 3)
     constexpr int NF = 4 + NSC;
-    constexpr unsigned PLANE_BYTES = PLANE * sizeof(TF), BOX_BYTES = t2_box_bytes(TY, (int)sizeof(TF));
+    constexpr unsigned PLANE_BYTES = PLANE * sizeof(TF), BOX_BYTES = t2_box_bytes(TY, (int)sizeof(TF), HL);
 
     const MomArgs<TF>& a = args.m;
     const int warp = threadIdx.x >> 5, tx = threadIdx.x & 31;
@@ -147,6 +147,13 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
         return (lev >= 0 && lev < g.kcells) ? fld[ij + c + (long long)lev * kk] : TF(0);
     };
     auto LD2 = [](const TF* p) -> V2 { return *reinterpret_cast<const V2*>(p); };
+    // the own pair in GLOBAL memory: one vector access when it is aligned (HL = 4), two scalar ones otherwise
+    auto gload2 = [&](const TF* __restrict__ p, TF& x0, TF& x1) {
+        if (ODD) { x0 = p[0]; x1 = p[1]; } else { const V2 t = *reinterpret_cast<const V2*>(p); x0 = t.x; x1 = t.y; } };
+    auto gstore2 = [&](TF* __restrict__ p, const TF x0, const TF x1) {
+        if (ODD) { p[0] = x0; p[1] = x1; } else { V2 t; t.x = x0; t.y = x1; *reinterpret_cast<V2*>(p) = t; } };
+    auto colload2 = [&](const TF* __restrict__ fld, int lev, TF& x0, TF& x1) {
+        if (lev >= 0 && lev < g.kcells) gload2(fld + ij + (long long)lev * kk, x0, x1); else { x0 = TF(0); x1 = TF(0); } };
     // Aligned vector row readers around the own pair (x[0], x[1]).  ODD: vectors start at x[-5], x[-3], x[-1], x[1] ...;
     // otherwise at x[-4], x[-2], x[0], x[2] ...  The value x[n] lands at array index n + O? (macros X10 / X6 / X4 below).
     constexpr int O10 = ODD ? 5 : 4, N10 = ODD ? 6 : 5;          // row10: x[-3..4] are used
@@ -194,9 +201,9 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
             const int f = k + 1, pl = k - k0;
             const bool st = (k >= kc0) && active;
             const long long o_k = ij + (long long)k * kk;
-            const TF un0 = colload(a.u, k + 4, 0), un1 = colload(a.u, k + 4, 1);
+            TF un0, un1; colload2(a.u, k + 4, un0, un1);
             TF old0 = 0, old1 = 0;
-            if (st) { old0 = a.ut[o_k]; old1 = a.ut[o_k + 1]; }
+            if (st) gload2(a.ut + o_k, old0, old1);
             const TF rhoh_f = p_rhoh[pl + 1], rdzi_k = p_rdzi[pl], dzhi_f = p_dzhi[pl + 1];
             const int of = vorder(f, ks, ke);
             int s0, s1;
@@ -246,8 +253,9 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
                                + (eviscn * ((uy[4][c] - uy[3][c]) * dyi + (X6(vp6, c) - X6(vp6, c - 1)) * dxi)
                                 - eviscs * ((uy[3][c] - uy[2][c]) * dyi + (X6(v6, c) - X6(v6, c - 1)) * dxi)) * dyi;
                     const TF tu = -(fx[c + 1] - fx[c]) * dxi - (fn - fs) * dyi + d + (gt[c] - gu[c]) * rdzi_k;
-                    a.ut[o_k + c] = (c == 0 ? old0 : old1) + tu;
+                    if (c == 0) old0 += tu; else old1 += tu;
                 }
+                gstore2(a.ut + o_k, old0, old1);
             }
             release(k, s0);
             gu[0] = gt[0]; gu[1] = gt[1];
@@ -267,9 +275,9 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
             const int f = k + 1, pl = k - k0;
             const bool st = (k >= kc0) && active;
             const long long o_k = ij + (long long)k * kk;
-            const TF vn0 = colload(a.v, k + 4, 0), vn1 = colload(a.v, k + 4, 1);
+            TF vn0, vn1; colload2(a.v, k + 4, vn0, vn1);
             TF old0 = 0, old1 = 0;
-            if (st) { old0 = a.vt[o_k]; old1 = a.vt[o_k + 1]; }
+            if (st) gload2(a.vt + o_k, old0, old1);
             const TF rhoh_f = p_rhoh[pl + 1], rdzi_k = p_rdzi[pl], dzhi_f = p_dzhi[pl + 1];
             const int of = vorder(f, ks, ke);
             int s0, s1;
@@ -318,8 +326,9 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
                     const TF d = (dx_[c + 1] - dx_[c]) * dxi
                                + ((X6(e0, c) + visc) * (vy[4][c] - vy[3][c]) * dyi - (X6(em, c) + visc) * (vy[3][c] - vy[2][c]) * dyi) * TF(2.) * dyi;
                     const TF tv = -(fx[c + 1] - fx[c]) * dxi - (fn - fs) * dyi + d + (gt[c] - gv[c]) * rdzi_k;
-                    a.vt[o_k + c] = (c == 0 ? old0 : old1) + tv;
+                    if (c == 0) old0 += tv; else old1 += tv;
                 }
+                gstore2(a.vt + o_k, old0, old1);
             }
             release(k, s0);
             gv[0] = gt[0]; gv[1] = gt[1];
@@ -341,9 +350,9 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
             const int f = k + 1, pl = k - k0;
             const bool st = (k >= kc0) && active;
             const long long o_k = ij + (long long)k * kk;
-            const TF sn0 = colload(sa_.s, k + 4, 0), sn1 = colload(sa_.s, k + 4, 1);
+            TF sn0, sn1; colload2(sa_.s, k + 4, sn0, sn1);
             TF old0 = 0, old1 = 0;
-            if (st) { old0 = sa_.st[o_k]; old1 = sa_.st[o_k + 1]; }
+            if (st) gload2(sa_.st + o_k, old0, old1);
             const TF rhoh_f = p_rhoh[pl + 1], rdzi_k = p_rdzi[pl], dzhi_f = p_dzhi[pl + 1];
             const int of = vorder(f, ks, ke);
             int s0, s1;
@@ -392,8 +401,9 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
                     const TF d = (dx_[c + 1] - dx_[c]) * sa_.dxidxi
                                + (eviscn * (sy[4][c] - sy[3][c]) - eviscs * (sy[3][c] - sy[2][c])) * sa_.dyidyi;
                     const TF ts = -(fx[c + 1] - fx[c]) * dxi - (fn - fs) * dyi + d + (gt[c] - gs[c]) * rdzi_k;
-                    sa_.st[o_k + c] = (c == 0 ? old0 : old1) + ts;
+                    if (c == 0) old0 += ts; else old1 += ts;
                 }
+                gstore2(sa_.st + o_k, old0, old1);
             }
             release(k, s0);
             gs[0] = gt[0]; gs[1] = gt[1];
@@ -417,11 +427,11 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
             const int f = k + 1, pl = k - k0;
             const bool st = (k >= kc0) && active && f < ke;
             const long long o_f = ij + (long long)f * kk;
-            const TF wn0 = colload(a.w, k + 5, 0), wn1 = colload(a.w, k + 5, 1);
+            TF wn0, wn1; colload2(a.w, k + 5, wn0, wn1);
             TF thn0 = TF(0), thn1 = TF(0);          // th[k+1] straight from global when the scalar is not staged (issued early)
-            if (BUOY && !NSC) { thn0 = colload(a.th, k + 1, 0); thn1 = colload(a.th, k + 1, 1); }
+            if (BUOY && !NSC) colload2(a.th, k + 1, thn0, thn1);
             TF old0 = 0, old1 = 0;
-            if (st) { old0 = a.wt[o_f]; old1 = a.wt[o_f + 1]; }
+            if (st) gload2(a.wt + o_f, old0, old1);
             const int oc = vorder(f, ks - 1, ke);
             const TF rho_c = p_rho[pl + 1], dzi_c = p_dzi[pl + 1], rdzhi_f = p_rdzhi[pl + 1], dzhi_f = p_dzhi[pl + 1];
             int s0, s1;
@@ -473,8 +483,9 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
                            - eviscs * ((wy[3][c] - wy[2][c]) * dyi + (V1R[c] - V0R[c]) * dzhi_f)) * dyi
                           + (gt[c] - gw[c]) * rdzhi_f;
                     if (BUOY) tw += p_gth[pl + 1] * (interp2(thk[c], th1[c]) - p_thh[pl + 1]);
-                    a.wt[o_f + c] = (c == 0 ? old0 : old1) + tw;
+                    if (c == 0) old0 += tw; else old1 += tw;
                 }
+                gstore2(a.wt + o_f, old0, old1);
             }
             release(k, s0);
             gw[0] = gt[0]; gw[1] = gt[1];

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import capi
-from .capi import FieldsC, ParamsC, GridDesc, SurfaceC, MhhError
+from .capi import FieldsC, ParamsC, GridDesc, SurfaceC, ForcingC, MhhError
 
 SWADVEC = {"2i5": 25, "2": 2, "4": 4}
 SWDIFF = {"smag2": 1, "2": 2, "4": 4}
@@ -321,6 +321,49 @@ class Pres:
 
     def fft_roundtrip(self, a_in, a_out, solve=False):
         self.ctx.check(self.ctx.lib.mhh_pres_fft_roundtrip(self.ctx.h, _ptr(a_in), _ptr(a_out), int(solve)))
+
+
+class Forcing:
+    """Buffer<TF> (src/buffer.cxx) and Force<TF> (src/force.cxx): damping layer, large-scale pressure force, large-scale sources
+    and subsidence.  Profiles are host arrays of kcells entries (uploaded here) or None."""
+    LSPRES = {None: 0, "0": 0, "uflux": 1, "dpdx": 2, "geo": 3}
+
+    def __init__(self, ctx, fields, swbuffer=False, zstart=0., sigma=2., beta=2., bufferprofs=None,
+                 swlspres=None, uflux=0., dpdx=0., fc=0., ug=None, vg=None, utrans=0., vtrans=0., ls=None, wls=None):
+        self.ctx = ctx
+        dev = fields["u"].device
+        self._keep = []
+
+        def up(a):
+            if a is None:
+                return None
+            t = torch.from_numpy(np.ascontiguousarray(a, dtype=ctx.gd.dtype)).to(dev)
+            self._keep.append(t)
+            return t.data_ptr()
+        c = ForcingC()
+        c.swbuffer = int(bool(swbuffer)); c.buffer_zstart = zstart; c.buffer_sigma = sigma; c.buffer_beta = beta
+        bp = bufferprofs or {}
+        c.bufferprof_u = up(bp.get("u")); c.bufferprof_v = up(bp.get("v")); c.bufferprof_w = up(bp.get("w"))
+        for i, n in enumerate(fields.scalars):
+            c.bufferprof_s[i] = up(bp.get(n))
+            c.ls_s[i] = up((ls or {}).get(n))
+        c.swlspres = self.LSPRES[swlspres]; c.uflux = uflux; c.dpdx = dpdx; c.fc = fc
+        c.ug = up(ug); c.vg = up(vg); c.utrans = utrans; c.vtrans = vtrans
+        c.wls = up(wls)
+        self.c = c
+
+    def exec_buffer(self, fields):
+        self.ctx.check(self.ctx.lib.mhh_buffer_exec(self.ctx.h, C.byref(fields.c), C.byref(self.c)))
+
+    def exec_force(self, fields, sub_dt):
+        self.ctx.check(self.ctx.lib.mhh_force_exec(self.ctx.h, C.byref(fields.c), C.byref(self.c), sub_dt))
+
+    def register(self):
+        """Run buffer.exec + force.exec inside the fused sub-steps from now on (mhh_dycore_set_forcing)."""
+        self.ctx.check(self.ctx.lib.mhh_dycore_set_forcing(self.ctx.h, C.byref(self.c)))
+
+    def unregister(self):
+        self.ctx.check(self.ctx.lib.mhh_dycore_set_forcing(self.ctx.h, None))
 
 
 class Boundary_surface:
