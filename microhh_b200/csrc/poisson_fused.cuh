@@ -194,24 +194,21 @@ __global__ void __launch_bounds__(32 * P2_ROWS) p2_x_forward_kernel(const TF* __
                 const long long base = g.istart + j * jj + k * kk;
                 const long long jn_off = (src.ywrap && j + 1 == g.jend) ? (1 - g.jmax) * jj : jj;
                 const TF rho = g.rhoref[k], rhoh0 = g.rhorefh[k], rhoh1 = g.rhorefh[k + 1], dzi = g.dzi[k];
-                // One point per lane and step (unit-stride 8-byte loads: every wavefront is full; the pair-per-lane version
-                // spent 77 % of the kernel in the LSU pipe on half-empty wavefronts): the divergence of point i needs u(i+1)
-                // from the next lane, and lands in the real / imaginary half of element i / 2 of the packed sequence.
-                TF* rrow = reinterpret_cast<TF*>(row);
 #pragma unroll 2
-                for (int i = lane; i < N; i += 32)
+                for (int n = lane; n < L; n += 32)
                 {
+                    const int i = 2 * n;
                     const long long o = base + i;
-                    const TF uc = src.ut[o] + src.u[o] * dti;
-                    TF un = __shfl_down_sync(0xffffffffu, uc, 1);
-                    if (lane == 31 || i + 1 == N)
-                    {
-                        const long long o2 = (i + 1 == N) ? o + 1 - N : o + 1;          // periodic wrap instead of the ghost cell
-                        un = src.ut[o2] + src.u[o2] * dti;
-                    }
-                    const TF vc = src.vt[o] + src.v[o] * dti, vn = src.vt[o + jn_off] + src.v[o + jn_off] * dti;
-                    const TF wc = src.wt[o] + src.w[o] * dti, wn = src.wt[o + kk] + src.w[o + kk] * dti;
-                    rrow[2 * fpad(i >> 1) + (i & 1)] = rho * (un - uc) * dxi + rho * (vn - vc) * dyi + (rhoh1 * wn - rhoh0 * wc) * dzi;
+                    const long long o2 = (i + 2 == N) ? o + 2 - N : o + 2;          // periodic wrap instead of the ghost cell
+                    const TF u0 = src.ut[o] + src.u[o] * dti, u1 = src.ut[o + 1] + src.u[o + 1] * dti, u2 = src.ut[o2] + src.u[o2] * dti;
+                    const TF v0 = src.vt[o] + src.v[o] * dti, v1 = src.vt[o + 1] + src.v[o + 1] * dti;
+                    const TF vn0 = src.vt[o + jn_off] + src.v[o + jn_off] * dti, vn1 = src.vt[o + 1 + jn_off] + src.v[o + 1 + jn_off] * dti;
+                    const TF w0 = src.wt[o] + src.w[o] * dti, w1 = src.wt[o + 1] + src.w[o + 1] * dti;
+                    const TF wt0 = src.wt[o + kk] + src.w[o + kk] * dti, wt1 = src.wt[o + 1 + kk] + src.w[o + 1 + kk] * dti;
+                    cplx<TF> z;
+                    z.x = rho * (u1 - u0) * dxi + rho * (vn0 - v0) * dyi + (rhoh1 * wt0 - rhoh0 * w0) * dzi;
+                    z.y = rho * (u2 - u1) * dxi + rho * (vn1 - v1) * dyi + (rhoh1 * wt1 - rhoh0 * w1) * dzi;
+                    row[fpad(n)] = z;
                 }
             }
             else

@@ -246,3 +246,41 @@ class RefSurface:
             fs(P(c[name + "_bot"]), P(c[name + "_gradbot"]), P(c[name + "_fluxbot"]), P(self.ustar), P(self.obuk), P(c[name]),
                P(self.z0h), self.ct(float(g.z[k])), int(bc))
         return dutot
+
+
+class RefForcing:
+    """Buffer / Force kernels of the reference (oracle/ref/ref_buffer_force.cpp), numpy arrays in place."""
+
+    def __init__(self, g, fast=False):
+        self.lib = C.CDLL(lib_path(fast))
+        self.g = g
+        self.sfx = "f64" if g.TF == np.float64 else "f32"
+        self.ct = C.c_double if g.TF == np.float64 else C.c_float
+        self.lib.ref_set_geom(g.itot, g.jtot, g.ktot, g.igc, g.jgc, g.kgc)
+
+    def _f(self, name):
+        return getattr(self.lib, f"{name}_{self.sfx}")
+
+    @staticmethod
+    def _p(a):
+        assert a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data_as(C.c_void_p)
+
+    def buffer(self, at, a, abuf, z, zstart, beta, sigma, bufferkstart):
+        g = self.g; ct = self.ct
+        self._f("ref_buffer")(self._p(at), self._p(a), self._p(abuf), self._p(np.ascontiguousarray(z)), ct(zstart), ct(float(g.zsize)),
+                              ct(beta), ct(sigma), int(bufferkstart))
+
+    def fixed_flux(self, ut, uflux, u_mean, ut_mean, utrans, dt):
+        ct = self.ct
+        self._f("ref_force_fixed_flux")(self._p(ut), ct(uflux), ct(float(u_mean)), ct(float(ut_mean)), ct(utrans), ct(dt))
+
+    def coriolis(self, ut, vt, u, v, ug, vg, fc, ugrid, vgrid, order=2):
+        ct = self.ct
+        self._f("ref_force_coriolis")(self._p(ut), self._p(vt), self._p(u), self._p(v), self._p(ug), self._p(vg), ct(fc), ct(ugrid), ct(vgrid), int(order))
+
+    def ls_source(self, st, sls):
+        self._f("ref_force_ls_source")(self._p(st), self._p(sls))
+
+    def wls_local(self, st, s, wls):
+        self._f("ref_force_wls_local")(self._p(st), self._p(s), self._p(wls), self._p(np.ascontiguousarray(self.g.dzhi)))

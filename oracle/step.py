@@ -20,7 +20,7 @@ def default_params(ns=1):
                 visc=1.e-5, svisc=1.e-5)
 
 
-def dycore_substep(g, K, c, prm, substep, dt, pres=None, timers=None, surface_model=None):
+def dycore_substep(g, K, c, prm, substep, dt, pres=None, timers=None, surface_model=None, forcing=None):
     """c: dict of numpy arrays as made by microhh_b200.synthetic.make_case (modified in place)."""
     import time
     t0 = time.perf_counter()
@@ -85,6 +85,8 @@ def dycore_substep(g, K, c, prm, substep, dt, pres=None, timers=None, surface_mo
         for s in scal:
             K.diff_2_c(c[s + "t"], c[s], prm["svisc"])
         lap("diff")
+        if forcing is not None:
+            forcing(c, O.rk3_subdt(dt, substep))       # buffer.exec + force.exec (src/model.cxx:416-430)
         return _pres_and_rk3(g, K, c, prm, substep, dt, pres, lap)
     K.diff_u(c["ut"], c["u"], c["v"], c["w"], c["evisc"], c["u_fluxbot"], c["u_fluxtop"], rr, rh, prm["visc"], surface)
     K.diff_v(c["vt"], c["u"], c["v"], c["w"], c["evisc"], c["v_fluxbot"], c["v_fluxtop"], rr, rh, prm["visc"], surface)
@@ -92,6 +94,8 @@ def dycore_substep(g, K, c, prm, substep, dt, pres=None, timers=None, surface_mo
     for s in scal:
         K.diff_c(c[s + "t"], c[s], c["evisc"], c[s + "_fluxbot"], c[s + "_fluxtop"], rr, rh, prm["tPr"], prm["svisc"], surface)
     lap("diff")
+    if forcing is not None:
+        forcing(c, O.rk3_subdt(dt, substep))           # buffer.exec + force.exec (src/model.cxx:416-430)
     return _pres_and_rk3(g, K, c, prm, substep, dt, pres, lap)
 
 
@@ -149,11 +153,11 @@ def dycore_substep_o4(g, K, c, prm, substep, dt, pres=None):
     return pres
 
 
-def dycore_step(g, K, c, prm, dt, timers=None, surface_model=None):
+def dycore_step(g, K, c, prm, dt, timers=None, surface_model=None, forcing=None):
     pres = None
     for ss in range(3):
         if prm.get("swadvec") == "4":
             pres = dycore_substep_o4(g, K, c, prm, ss, dt, pres)
         else:
-            pres = dycore_substep(g, K, c, prm, ss, dt, pres, timers, surface_model)
+            pres = dycore_substep(g, K, c, prm, ss, dt, pres, timers, surface_model, forcing)
     return pres

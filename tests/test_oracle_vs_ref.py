@@ -306,3 +306,44 @@ def test_boundary_surface_pinned(dtype, thermobc):
         assert rel_l2(a[n], b[n]) <= tol, n
     for n in ("dudz_mo", "dvdz_mo", "dbdz_mo"):
         assert rel_l2(a[n][sl], b[n][sl]) <= tol, n
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_buffer_and_force_pinned(dtype):
+    """Damping layer and large-scale forcings: the numpy restatement against the reference's compiled kernels
+    (calc_buffer, enforce_fixed_flux, calc_coriolis_2nd, calc_large_scale_source, advec_wls_2nd_local)."""
+    from util import make_pair, prepare_halos, rel_l2
+    g, gd, case = make_pair(24, 16, 12, dtype, stretched=True)
+    prepare_halos(g, case)
+    R = refbind.RefForcing(g)
+    rng = np.random.default_rng(4)
+    tol = 1e-13 if dtype == np.float64 else 1e-6
+    prof = lambda: rng.standard_normal(gd.kcells).astype(dtype)
+    # buffer (the damping factor uses pow: numpy vs libm)
+    zstart = float(0.6*g.zsize)
+    ks, ksh = O.buffer_kstart(g, zstart)
+    assert g.kstart < ks < g.kend and ksh in (ks, ks + 1, ks - 1)
+    for fld, z, k0 in (("u", g.z, ks), ("w", g.zh, ksh), ("th", g.z, ks)):
+        abuf = prof()
+        a = rng.standard_normal(gd.shape).astype(dtype); b = a.copy()
+        O.calc_buffer(g, a, case[fld], abuf, z, zstart, 2., 2.5, k0)
+        R.buffer(b, case[fld], abuf, z, zstart, 2., 2.5, k0)
+        assert rel_l2(a, b) <= tol, fld
+    # fixed mass flux
+    ut = rng.standard_normal(gd.shape).astype(dtype); ut2 = ut.copy()
+    um, utm = O.field_mean(g, case["u"]), O.field_mean(g, ut)
+    O.force_fixed_flux(g, ut, case["u"], 0.11, 0.02, 0.7)
+    R.fixed_flux(ut2, 0.11, um, utm, 0.02, 0.7)
+    assert rel_l2(ut, ut2) <= tol
+    # Coriolis + geostrophic wind
+    ug, vg = prof(), prof()
+    a = {n: rng.standard_normal(gd.shape).astype(dtype) for n in ("ut", "vt")}; b = copy.deepcopy(a)
+    O.force_coriolis_2nd(g, a["ut"], a["vt"], case["u"], case["v"], ug, vg, 1e-4, 0.3, -0.2)
+    R.coriolis(b["ut"], b["vt"], case["u"], case["v"], ug, vg, 1e-4, 0.3, -0.2)
+    assert np.array_equal(a["ut"], b["ut"]) and np.array_equal(a["vt"], b["vt"])
+    # large-scale source and local subsidence
+    sls, wls = prof(), (0.01*prof())
+    st = rng.standard_normal(gd.shape).astype(dtype); st2 = st.copy()
+    O.force_ls_source(g, st, sls); O.force_wls_local(g, st, case["th"], wls)
+    R.ls_source(st2, sls); R.wls_local(st2, case["th"], wls)
+    assert np.array_equal(st, st2)
