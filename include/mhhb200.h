@@ -223,6 +223,21 @@ MHH_API long long mhh_slab_xindex(int itot, int jtot, int ktot, int npy, int ran
 MHH_API long long mhh_slab_xindex_tiled(int itot, int jtot, int ktot, int npy, int rank, long long row, int m, long long* total);
 MHH_API long long mhh_slab_yindex(int itot, int jtot, int ktot, int npy, int rank, int k, int j, int ml);
 
+/* Layout of the FUSED Pres_2 path (power-of-two itot/2 and jtot; y transforms fused with the two-sided Thomas sweeps):
+ *   Y side of the rank that owns a mode: [source rank s][local mode ml][level k][local row jl]  -- a y sequence of one
+ *     (mode, level) is npy contiguous pieces, block s IS the message from rank s;
+ *   X side of the rank that owns a row:  [mode owner d][level k][row panel jl/8][local mode ml][jl%8] -- the 8 rows of a mode are
+ *     one 128-byte chunk, block d IS the message from rank d.
+ * ksplit: levels below it are eliminated upwards, the others downwards (two CTAs per mode). */
+typedef struct mhh_slab2_info
+{
+    int nm, mcl, m_off, jmax, npan, ksplit;
+    long long xside_elems, yside_elems;
+} mhh_slab2_info;
+MHH_API int mhh_slab2_layout(int itot, int jtot, int ktot, int npy, int rank, mhh_slab2_info* out);
+MHH_API long long mhh_slab2_yindex(int itot, int jtot, int ktot, int npy, int owner, int src, int ml, int k, int jl);
+MHH_API long long mhh_slab2_xindex(int itot, int jtot, int ktot, int npy, int mode_owner, int k, int jl, int ml);
+
 /* ---- Boundary_cyclic<TF>::exec / exec_2d  (src/boundary_cyclic.cxx:369-507) ---------------- */
 MHH_API int mhh_boundary_cyclic(mhh_ctx* ctx, void* fld, int edge);
 MHH_API int mhh_boundary_cyclic_2d(mhh_ctx* ctx, void* fld2d);

@@ -43,6 +43,11 @@ class FieldsC(C.Structure):
                 ("s_fluxlimit", C.c_int * MHH_MAX_SCALARS)]
 
 
+class Slab2Info(C.Structure):
+    _fields_ = [("nm", C.c_int), ("mcl", C.c_int), ("m_off", C.c_int), ("jmax", C.c_int), ("npan", C.c_int), ("ksplit", C.c_int),
+                ("xside_elems", C.c_longlong), ("yside_elems", C.c_longlong)]
+
+
 class ForcingC(C.Structure):
     _fields_ = [("swbuffer", C.c_int), ("buffer_zstart", C.c_double), ("buffer_sigma", C.c_double), ("buffer_beta", C.c_double),
                 ("bufferprof_u", C.c_void_p), ("bufferprof_v", C.c_void_p), ("bufferprof_w", C.c_void_p), ("bufferprof_s", _SA),
@@ -91,6 +96,9 @@ SIGNATURES = {
     "mhh_slab_layout": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(SlabInfo)]),
     "mhh_slab_xindex": (C.c_longlong, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_int]),
     "mhh_slab_xindex_tiled": (C.c_longlong, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_int, C.POINTER(C.c_longlong)]),
+    "mhh_slab2_layout": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Slab2Info)]),
+    "mhh_slab2_yindex": (C.c_longlong, [C.c_int]*9),
+    "mhh_slab2_xindex": (C.c_longlong, [C.c_int]*8),
     "mhh_slab_yindex": (C.c_longlong, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "mhh_boundary_cyclic": (C.c_int, [_vp, _vp, C.c_int]),
     "mhh_boundary_cyclic_2d": (C.c_int, [_vp, _vp]),

@@ -986,6 +986,32 @@ long long mhh_slab_yindex(int itot, int jtot, int ktot, int npy, int rank, int k
     return l.yidx(k, j, ml);
 }
 
+// ---- layout of the fused Pres_2 path (poisson_fused.cuh, struct Spec2) ----
+int mhh_slab2_layout(int itot, int jtot, int ktot, int npy, int rank, mhh_slab2_info* out)
+{
+    if (!out || npy < 1 || rank < 0 || rank >= npy || itot < 2 || jtot < 1 || ktot < 1 || jtot % npy != 0 || itot / 2 + 1 < npy) return MHH_E_INVALID;
+    const Spec2 l = make_spec2(itot, jtot, ktot, npy, rank);
+    out->nm = l.nm; out->mcl = l.mcl; out->m_off = l.m_off; out->jmax = l.jmax; out->npan = l.npan; out->ksplit = p2_ksplit(ktot);
+    out->xside_elems = l.xside_elems(); out->yside_elems = l.yside_elems();
+    return MHH_OK;
+}
+
+long long mhh_slab2_yindex(int itot, int jtot, int ktot, int npy, int owner, int src, int ml, int k, int jl)
+{
+    if (npy < 1 || owner < 0 || owner >= npy || src < 0 || src >= npy || jtot % npy != 0 || itot / 2 + 1 < npy) return -1;
+    const Spec2 l = make_spec2(itot, jtot, ktot, npy, owner);
+    if (ml < 0 || ml >= l.mcl || k < 0 || k >= ktot || jl < 0 || jl >= l.jmax) return -1;
+    return l.yidx(l.mcl, src, ml, k, jl);
+}
+
+long long mhh_slab2_xindex(int itot, int jtot, int ktot, int npy, int mode_owner, int k, int jl, int ml)
+{
+    if (npy < 1 || mode_owner < 0 || mode_owner >= npy || jtot % npy != 0 || itot / 2 + 1 < npy) return -1;
+    const Spec2 l = make_spec2(itot, jtot, ktot, npy, 0);
+    if (ml < 0 || ml >= l.count(mode_owner) || k < 0 || k >= ktot || jl < 0 || jl >= l.jmax) return -1;
+    return l.xidx(mode_owner, k, jl / P2_ROWS, ml, jl % P2_ROWS);
+}
+
 int mhh_profile_start(mhh_ctx* ctx)
 {
     if (!ctx) return MHH_E_INVALID;

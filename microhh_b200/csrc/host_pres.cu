@@ -157,8 +157,8 @@ void p2_y_launch(int J, bool backward, cudaStream_t st, cplx<TF>* Y, const TF* T
 {
     switch (J)
     {
-#define X(N) case N: if (backward) p2_y_backward_kernel<TF, N><<<lay.mcl, 32 * p2_y_warps<TF, N>(), p2_y_smem<TF, N>(), st>>>(Y, T, lay, xf, cf.c, tw, jlog2, solve); \
-                     else p2_y_forward_kernel<TF, N><<<lay.mcl, 32 * p2_y_warps<TF, N>(), p2_y_smem<TF, N>(), st>>>(Y, T, lay, cf.a, cf.dz2, tw, jlog2, solve); break;
+#define X(N) case N: if (backward) p2_y_backward_kernel<TF, N><<<2 * lay.mcl, 32 * p2_y_warps<TF, N>(), p2_y_smem<TF, N>(), st>>>(Y, T, T + (size_t)lay.mcl * lay.ktot * N, lay, xf, cf.a, cf.c, tw, jlog2, solve); \
+                     else p2_y_forward_kernel<TF, N><<<2 * lay.mcl, 32 * p2_y_warps<TF, N>(), p2_y_smem<TF, N>(), st>>>(Y, T, lay, cf.a, cf.c, cf.dz2, tw, jlog2, solve); break;
         WFFT_Y_CASES(X)
 #undef X
     }
@@ -171,7 +171,7 @@ void p2_setup_launch(int J, cudaStream_t st, TF* T, const TdmaCoef<TF>& cf, int 
     const unsigned grid = (unsigned)((ncol + 127) / 128);
     switch (J)
     {
-#define X(N) case N: tdma2_setup_kernel<TF, N><<<grid, 128, 0, st>>>(T, cf, mcl, kmax, m_off); break;
+#define X(N) case N: tdma2_setup_kernel<TF, N><<<grid, 128, 0, st>>>(T, T + (size_t)mcl * kmax * N, cf, mcl, kmax, m_off); break;
         WFFT_Y_CASES(X)
 #undef X
     }
@@ -208,7 +208,8 @@ int pres_create(Ctx<TF>* c)
     }
     if (c->fused)
     {
-        const size_t nX = (size_t)2 * c->lay2.xside_elems(), nY = (size_t)2 * c->lay2.yside_elems(), nT = (size_t)c->lay2.yside_elems();
+        // pivot table T[ml][k][pos] followed by the interface factors Dinv[ml][pos]
+        const size_t nX = (size_t)2 * c->lay2.xside_elems(), nY = (size_t)2 * c->lay2.yside_elems(), nT = (size_t)c->lay2.yside_elems() + (size_t)c->lay2.mcl * g.jtot;
         CUDA_TRY(c, cudaMalloc(&c->spec, sizeof(TF) * nX));
         CUDA_TRY(c, cudaMalloc(&c->specT, sizeof(TF) * nY));
         CUDA_TRY(c, cudaMalloc(&c->fac, sizeof(TF) * nT));

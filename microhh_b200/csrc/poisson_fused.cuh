@@ -139,11 +139,23 @@ template <int L> __host__ __device__ __forceinline__ int digitrev_inv(int pos)
 }
 
 // ------------------------------------------------------------------------------------------
-// Table of reciprocal pivots, T[ml][k][pos] = 1 / w_k of column (mode m_off + ml, y-mode at digit-reversed position pos):
-//   w_0 = b_0,  w_k = b_k - a_k c_{k-1} / w_{k-1}     (src/pres_2.cxx:202-263 with b from :292-324)
+// Two-sided (twisted) factorisation of the tridiagonal systems of Pres_2::solve (src/pres_2.cxx:202-324): the lower half of
+// the levels, 0 .. ksplit-1, is eliminated upwards exactly like the reference's tdma (pivots w_k), the upper half,
+// ktot-1 .. ksplit, downwards (pivots v_k); the two meet in a 2 x 2 system per column.  Mathematically the same solution (the
+// rounding differs from a one-sided sweep at the 1e-16 level); the point is that the two halves are independent sequential
+// chains, so a mode is worked on by TWO CTAs at a time -- twice the parallelism where modes are scarce (y slabs: nm / P modes
+// per GPU) and half the length of the critical path.
+//   lower: w_0 = b_0,  w_k = b_k - a_k c_{k-1} / w_{k-1};   p'_k = (d_k - a_k p'_{k-1}) / w_k;   x_k = p'_k - (c_k / w_k) x_{k+1}
+//   upper: v_K = b_K,  v_k = b_k - c_k a_{k+1} / v_{k+1};   q'_k = (d_k - c_k q'_{k+1}) / v_k;   x_k = q'_k - (a_k / v_k) x_{k-1}
+//   interface (m = ksplit):  x_m = (q'_m - beta p'_{m-1}) / (1 - alpha beta),  x_{m-1} = p'_{m-1} - alpha x_m,
+//                            alpha = c_{m-1} / w_{m-1},  beta = a_m / v_m
+// Table T[ml][k][pos] = 1 / w_k (k < ksplit) or 1 / v_k (k >= ksplit) of column (mode m_off + ml, y-mode at digit-reversed
+// position pos); Dinv[ml][pos] = 1 / (1 - alpha beta) follows the table.
 // ------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ int p2_ksplit(const int ktot) { return ktot / 2; }
+
 template <typename TF, int J>
-__global__ void tdma2_setup_kernel(TF* __restrict__ T, const TdmaCoef<TF> cf, const int mcl, const int kmax, const int m_off)
+__global__ void tdma2_setup_kernel(TF* __restrict__ T, TF* __restrict__ Dinv, const TdmaCoef<TF> cf, const int mcl, const int kmax, const int m_off)
 {
     const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= (long long)mcl * J) return;
@@ -151,15 +163,26 @@ __global__ void tdma2_setup_kernel(TF* __restrict__ T, const TdmaCoef<TF> cf, co
     const int l = digitrev_inv<J>(pos), m = ml + m_off;
     const TF lam = cf.bmati[m] + cf.bmatj[l];
     const bool mode00 = (m == 0) && (l == 0);
+    const int ks = p2_ksplit(kmax);
     TF* t = T + (long long)ml * kmax * J + pos;
     TF w = tdma_b(cf, 0, kmax, lam, mode00);
     t[0] = TF(1) / w;
-    for (int k = 1; k < kmax; ++k)
+    for (int k = 1; k < ks; ++k)
     {
         const TF f = cf.c[k - 1] / w;
         w = tdma_b(cf, k, kmax, lam, mode00) - cf.a[k] * f;
         t[(long long)k * J] = TF(1) / w;
     }
+    TF v = tdma_b(cf, kmax - 1, kmax, lam, mode00);
+    t[(long long)(kmax - 1) * J] = TF(1) / v;
+    for (int k = kmax - 2; k >= ks; --k)
+    {
+        const TF f = cf.a[k + 1] / v;
+        v = tdma_b(cf, k, kmax, lam, mode00) - cf.c[k] * f;
+        t[(long long)k * J] = TF(1) / v;
+    }
+    const TF alpha = cf.c[ks - 1] / w, beta = cf.a[ks] / v;
+    Dinv[col] = TF(1) / (TF(1) - alpha * beta);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -282,7 +305,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 template <typename TF, int J>
 __global__ void __launch_bounds__(32 * p2_y_warps<TF, J>(), (sizeof(TF) * J <= 8 * 512) ? 2 : 1) p2_y_forward_kernel(cplx<TF>* __restrict__ Y, const TF* __restrict__ T, const Spec2 lay,
-        const TF* __restrict__ ak, const TF* __restrict__ dz2, const cplx<TF>* __restrict__ tw, const int jlog2, const int solve)
+        const TF* __restrict__ ak, const TF* __restrict__ ck, const TF* __restrict__ dz2, const cplx<TF>* __restrict__ tw, const int jlog2, const int solve)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NW = p2_y_warps<TF, J>(), RS = FftRow<J>::SIZE, NI = (J + 31) / 32;
@@ -294,11 +317,17 @@ __global__ void __launch_bounds__(32 * p2_y_warps<TF, J>(), (sizeof(TF) * J <= 8
     if (threadIdx.x == 0) *done = 0;
     __syncthreads();
     const int K = lay.ktot;
-    const int ml = blockIdx.x;
+    // blockIdx.x = 2 * mode + half: the lower half eliminates levels 0 .. ksplit-1 upwards (coupling a_k to the level below),
+    // the upper half levels ktot-1 .. ksplit downwards (coupling c_k to the level above)
+    const int ml = blockIdx.x >> 1, half = blockIdx.x & 1;
+    const int ksp = p2_ksplit(K);
+    const int nlev = half ? K - ksp : ksp;
+    const TF* __restrict__ coef = half ? ck : ak;
     cplx<TF>* Ym = Y + (long long)ml * K * lay.jmax;
     const TF* Tm = T + (long long)ml * K * J;
-    for (int k = warp; k < K; k += NW)
+    for (int n = warp; n < nlev; n += NW)
     {
+        const int k = half ? K - 1 - n : n;
         cplx<TF>* seq = Ym + (long long)k * lay.jmax;
         TF tk[TREG ? NI : 1];
         if (solve && TREG)
@@ -312,10 +341,10 @@ __global__ void __launch_bounds__(32 * p2_y_warps<TF, J>(), (sizeof(TF) * J <= 8
         wfft<TF, J>(row, tw, lane);
         if (solve)
         {
-            const TF a = ak[k], d2 = dz2[k];
-            if (k > 0) level_wait(done, k);                     // level k-1 has published its slot
-            const cplx<TF>* prev = state + ((k - 1) & 1) * J;
-            cplx<TF>* cur = state + (k & 1) * J;
+            const TF a = coef[k], d2 = dz2[k];
+            if (n > 0) level_wait(done, n);                     // the previous level of this half has published its slot
+            const cplx<TF>* prev = state + ((n - 1) & 1) * J;
+            cplx<TF>* cur = state + (n & 1) * J;
 #pragma unroll
             for (int i = 0; i < NI; ++i)
             {
@@ -325,13 +354,13 @@ __global__ void __launch_bounds__(32 * p2_y_warps<TF, J>(), (sizeof(TF) * J <= 8
                     const TF t = TREG ? tk[TREG ? i : 0] : Tm[(long long)k * J + pos];
                     const cplx<TF> z = row[fpad(pos)];
                     cplx<TF> pv = {TF(0), TF(0)};
-                    if (k > 0) pv = prev[pos];
+                    if (n > 0) pv = prev[pos];
                     const cplx<TF> o = {(d2 * z.x - a * pv.x) * t, (d2 * z.y - a * pv.y) * t};
                     cur[pos] = o;
                     seq[p2_yoff(lay, jlog2, pos)] = o;
                 }
             }
-            level_publish(done, k + 1, lane);
+            level_publish(done, n + 1, lane);
         }
         else
         {
@@ -347,8 +376,8 @@ __global__ void __launch_bounds__(32 * p2_y_warps<TF, J>(), (sizeof(TF) * J <= 8
 // (natural y order, unnormalised) goes to the X side of the rank that owns the rows, in 8-row chunks.
 // ------------------------------------------------------------------------------------------
 template <typename TF, int J>
-__global__ void __launch_bounds__(32 * p2_y_warps<TF, J>(), (sizeof(TF) * J <= 8 * 512) ? 2 : 1) p2_y_backward_kernel(const cplx<TF>* __restrict__ Y, const TF* __restrict__ T, const Spec2 lay,
-        const XferPtrs<TF> xf, const TF* __restrict__ ck, const cplx<TF>* __restrict__ tw, const int jlog2, const int solve)
+__global__ void __launch_bounds__(32 * p2_y_warps<TF, J>(), (sizeof(TF) * J <= 8 * 512) ? 2 : 1) p2_y_backward_kernel(const cplx<TF>* __restrict__ Y, const TF* __restrict__ T, const TF* __restrict__ Dinv,
+        const Spec2 lay, const XferPtrs<TF> xf, const TF* __restrict__ ak, const TF* __restrict__ ck, const cplx<TF>* __restrict__ tw, const int jlog2, const int solve)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NW = p2_y_warps<TF, J>(), RS = FftRow<J>::SIZE, NI = (J + 31) / 32;
@@ -361,21 +390,26 @@ __global__ void __launch_bounds__(32 * p2_y_warps<TF, J>(), (sizeof(TF) * J <= 8
     __syncthreads();
     const int K = lay.ktot;
     const int cnt = lay.mcl;
-    const int ml = blockIdx.x;
+    // blockIdx.x = 2 * mode + half: the lower half substitutes from level ksplit-1 down to 0, the upper half from ksplit up to
+    // ktot-1; both start from the 2 x 2 interface system (each solves it for itself: two loads and five flops per column)
+    const int ml = blockIdx.x >> 1, half = blockIdx.x & 1;
+    const int ksp = p2_ksplit(K);
+    const int nlev = half ? K - ksp : ksp;
+    const TF* __restrict__ coef = half ? ak : ck;
     const cplx<TF>* Ym = Y + (long long)ml * K * lay.jmax;
     const TF* Tm = T + (long long)ml * K * J;
-    for (int n = warp; n < K; n += NW)
+    for (int n = warp; n < nlev; n += NW)
     {
-        const int k = K - 1 - n;                                  // levels downwards
+        const int k = half ? ksp + n : ksp - 1 - n;
         const cplx<TF>* seq = Ym + (long long)k * lay.jmax;
         // p'_k straight into the warp's row (asynchronous copies: issued before the hand-over wait, no registers)
 #pragma unroll 4
         for (int pos = lane; pos < J; pos += 32) cp_async<(int)sizeof(cplx<TF>)>(&row[fpad(pos)], &seq[p2_yoff(lay, jlog2, pos)]);
         if (solve)
         {
-            // work3d[k+1] = c[k] / w_k = c[k] * T[k]
+            // the coupling factor of this level: c_k / w_k (lower half) or a_k / v_k (upper half) = coef_k * T[k]
             TF fk[TREG ? NI : 1];
-            const TF c = ck[k];
+            const TF c = coef[k];
             if (TREG)
             {
 #pragma unroll
@@ -405,9 +439,27 @@ __global__ void __launch_bounds__(32 * p2_y_warps<TF, J>(), (sizeof(TF) * J <= 8
             }
             else
             {
+                // first level of the half: the interface.  x_m = (q'_m - beta p'_{m-1}) Dinv;  lower half: x_{m-1} = p'_{m-1} - alpha x_m
+                const cplx<TF>* oth = Ym + (long long)(half ? ksp - 1 : ksp) * lay.jmax;      // the other half's last eliminated level
+                const TF* To = Tm + (long long)(half ? ksp - 1 : ksp) * J;
+                const TF co = half ? ck[ksp - 1] : ak[ksp];
                 cplx<TF>* cur = state;
 #pragma unroll 4
-                for (int pos = lane; pos < J; pos += 32) cur[pos] = row[fpad(pos)];
+                for (int pos = lane; pos < J; pos += 32)
+                {
+                    const cplx<TF> own = row[fpad(pos)];
+                    const cplx<TF> ot = oth[p2_yoff(lay, jlog2, pos)];
+                    const TF fo = c * Tm[(long long)k * J + pos];          // own coupling factor: alpha (lower) or beta (upper)
+                    const TF fx = co * To[pos];                            // the other one
+                    const TF di = Dinv[(long long)ml * J + pos];
+                    const TF beta = half ? fo : fx, alpha = half ? fx : fo;
+                    const cplx<TF> q = half ? own : ot, pm = half ? ot : own;   // q'_m, p'_{m-1}
+                    const cplx<TF> xm = {(q.x - beta * pm.x) * di, (q.y - beta * pm.y) * di};
+                    cplx<TF> o = xm;
+                    if (!half) { o.x = pm.x - alpha * xm.x; o.y = pm.y - alpha * xm.y; }
+                    cur[pos] = o;
+                    row[fpad(pos)] = o;
+                }
             }
             level_publish(done, n + 1, lane);
         }

@@ -246,3 +246,97 @@ def test_panel_tiled_x_side_is_injective_and_panel_contiguous(shape, P):
         if r > 0:
             first = [lib.mhh_slab_xindex_tiled(itot, jtot, ktot, P, q, 0, infos[1].m_off, None) for q in (0, r)]
             assert first[0] == first[1]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The fused Pres_2 path: mode-major Y side, 8-row-panel X side, two-sided factorisation
+# ---------------------------------------------------------------------------------------------------------------------
+def slab2_info(lib, itot, jtot, ktot, P, r):
+    s = capi.Slab2Info()
+    assert lib.mhh_slab2_layout(itot, jtot, ktot, P, r, C.byref(s)) == 0
+    return s
+
+
+@pytest.mark.parametrize("shape,P", [((32, 16, 6), 2), ((64, 32, 3), 4), ((32, 8, 4), 1), ((32, 24, 2), 2)])
+def test_fused_layout_is_a_bijection_with_contiguous_sequences_and_chunks(shape, P):
+    lib = capi.load()
+    itot, jtot, ktot = shape
+    nm = itot//2 + 1
+    infos = [slab2_info(lib, itot, jtot, ktot, P, r) for r in range(P)]
+    assert sum(s.mcl for s in infos) == nm and all(s.ksplit == ktot//2 for s in infos)
+    jmax = infos[0].jmax
+    for d in range(P):
+        s = infos[d]
+        # Y side of rank d: every (source, mode, level, row) exactly once; rows of a sequence piece are contiguous
+        seen = np.zeros(s.yside_elems, bool)
+        for src in range(P):
+            for ml in range(s.mcl):
+                for k in range(ktot):
+                    idx = np.array([lib.mhh_slab2_yindex(itot, jtot, ktot, P, d, src, ml, k, jl) for jl in range(jmax)])
+                    assert np.all(np.diff(idx) == 1) and not seen[idx].any()
+                    seen[idx] = True
+            # block src is one contiguous message
+            first = lib.mhh_slab2_yindex(itot, jtot, ktot, P, d, src, 0, 0, 0)
+            assert first == src*s.mcl*ktot*jmax
+        assert seen.all()
+    # X side (the same on every rank): every (mode owner, level, row, mode) once; 8 consecutive rows of a mode are contiguous
+    seen = np.zeros(infos[0].xside_elems, bool)
+    for d in range(P):
+        for k in range(ktot):
+            for ml in range(infos[d].mcl):
+                idx = np.array([lib.mhh_slab2_xindex(itot, jtot, ktot, P, d, k, jl, ml) for jl in range(jmax)])
+                assert idx.min() >= 0 and not seen[idx].any()
+                seen[idx] = True
+                for j0 in range(0, jmax - 7, 8):
+                    assert np.all(np.diff(idx[j0:j0+8]) == 1) and idx[j0] % 8 == 0
+    assert seen.sum() == nm*ktot*jmax                      # the rest is panel padding (jmax not a multiple of 8)
+    assert lib.mhh_slab2_xindex(itot, jtot, ktot, P, 0, ktot, 0, 0) == -1
+
+
+def twisted_tdma(a, b, c, d, ks):
+    """The two-sided factorisation of the fused kernels (poisson_fused.cuh), in numpy, vectorised over the trailing axes:
+    levels < ks eliminated upwards, the others downwards, 2 x 2 interface, substitution outwards from the interface."""
+    K = d.shape[0]
+    T = np.empty_like(b); pp = np.empty_like(d)
+    w = b[0].copy(); T[0] = 1./w; pp[0] = d[0]*T[0]
+    for k in range(1, ks):
+        w = b[k] - a[k]*(c[k-1]/w); T[k] = 1./w
+        pp[k] = (d[k] - a[k]*pp[k-1])*T[k]
+    v = b[K-1].copy(); T[K-1] = 1./v; pp[K-1] = d[K-1]*T[K-1]
+    for k in range(K-2, ks-1, -1):
+        v = b[k] - c[k]*(a[k+1]/v); T[k] = 1./v
+        pp[k] = (d[k] - c[k]*pp[k+1])*T[k]
+    alpha = c[ks-1]*T[ks-1]; beta = a[ks]*T[ks]
+    x = np.empty_like(d)
+    x[ks] = (pp[ks] - beta*pp[ks-1])/(1. - alpha*beta)
+    x[ks-1] = pp[ks-1] - alpha*x[ks]
+    for k in range(ks-2, -1, -1):
+        x[k] = pp[k] - (c[k]*T[k])*x[k+1]
+    for k in range(ks+1, K):
+        x[k] = pp[k] - (a[k]*T[k])*x[k-1]
+    return x
+
+
+@pytest.mark.parametrize("K", [6, 7, 16, 33])
+def test_two_sided_factorisation_equals_the_reference_tdma(K):
+    """The fused kernels' two-sided sweep solves the reference's tridiagonal systems (src/pres_2.cxx:202-324) to rounding."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import oracle as O
+    itot, jtot = 16, 8
+    g = O.Grid(itot, jtot, K, 100., 80., 60., 3, 3, 1, np.float64,
+               z=np.cumsum(np.linspace(0.7, 1.3, K))*60./np.linspace(0.7, 1.3, K).sum() - 0.3)
+    rho = np.exp(-g.z/8000.); rhoh = np.exp(-g.zh/8000.)
+    pres = O.Pres2(g, rho, rhoh)
+    kg = g.kgc
+    dz = g.dz[kg:kg+K][:, None, None]; rr = rho[kg:kg+K][:, None, None]
+    lam = pres.bmatj[None, :, None] + pres.bmati[None, None, :itot//2+1]
+    b = dz*dz*rr*lam - (pres.a + pres.c)[:, None, None]
+    b[0] += pres.a[0]
+    top = np.full((jtot, itot//2+1), pres.c[K-1]); top[0, 0] = -pres.c[K-1]
+    b[K-1] += top
+    d = np.random.default_rng(K).standard_normal(b.shape)
+    ref = d.copy()
+    pres.tdma(ref, b.copy())
+    a3 = pres.a[:, None, None]*np.ones_like(b); c3 = pres.c[:, None, None]*np.ones_like(b)
+    x = twisted_tdma(a3, b, c3, d, K//2)
+    assert np.sqrt(((x - ref)**2).sum()/(ref**2).sum()) <= 1e-13
