@@ -793,6 +793,10 @@ using namespace mhhhost;
          else { typedef float TF; Ctx<TF>* c = static_cast<Ctx<TF>*>(ctx); (void)c; return (expr32); } } while (0)
 #define DISPATCH1(ctx, expr) DISPATCH(ctx, expr, expr)
 
+// entry points that dispatch on the dtype by hand still have to run on the context's device
+#define SET_DEVICE(ctx) do { cudaError_t e_ = cudaSetDevice((ctx)->device); \
+    if (e_ != cudaSuccess) { (ctx)->err = std::string("cudaSetDevice: ") + cudaGetErrorString(e_); return MHH_E_CUDA; } } while (0)
+
 extern "C" {
 
 int mhh_ctx_create(const mhh_grid_desc* grid, int dtype, int device, mhh_ctx** out)
@@ -898,21 +902,37 @@ int mhh_comm_open_peers(mhh_ctx* ctx, const void* all, int nbytes)
         if (c->g.jtot == 1) return MHH_OK;
         const cudaIpcMemHandle_t* h = static_cast<const cudaIpcMemHandle_t*>(all);
         PeerPtrs<TF> pp{};
+        void *ps = nullptr, *pn = nullptr;
+        // on any failure close what has been opened so far (peers.on stays 0, so nobody else would)
+        auto fail = [&](cudaError_t e, const char* what) -> int {
+            for (int q = 0; q < c->nranks; ++q)
+                if (q != c->rank) { if (pp.x[q]) cudaIpcCloseMemHandle(pp.x[q]); if (pp.y[q]) cudaIpcCloseMemHandle(pp.y[q]); }
+            if (ps) cudaIpcCloseMemHandle(ps);
+            if (pn && pn != ps) cudaIpcCloseMemHandle(pn);
+            c->err = std::string(what) + ": " + cudaGetErrorString(e);
+            return MHH_E_CUDA; };
         for (int r = 0; r < c->nranks; ++r)
         {
             if (r == c->rank) { pp.x[r] = c->spec; pp.y[r] = c->specT; continue; }
             void *px = nullptr, *py = nullptr;
-            CUDA_TRY(c, cudaIpcOpenMemHandle(&px, h[3 * r], cudaIpcMemLazyEnablePeerAccess));
-            CUDA_TRY(c, cudaIpcOpenMemHandle(&py, h[3 * r + 1], cudaIpcMemLazyEnablePeerAccess));
-            pp.x[r] = static_cast<TF*>(px); pp.y[r] = static_cast<TF*>(py);
+            cudaError_t e = cudaIpcOpenMemHandle(&px, h[3 * r], cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) return fail(e, "cudaIpcOpenMemHandle(x side)");
+            pp.x[r] = static_cast<TF*>(px);
+            e = cudaIpcOpenMemHandle(&py, h[3 * r + 1], cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) return fail(e, "cudaIpcOpenMemHandle(y side)");
+            pp.y[r] = static_cast<TF*>(py);
         }
         if (c->phalo && !(getenv("MHH_NO_PEER_HALO") && getenv("MHH_NO_PEER_HALO")[0] == '1'))
         {
             const int south = (c->rank + c->nranks - 1) % c->nranks, north = (c->rank + 1) % c->nranks;
-            void *ps = nullptr, *pn = nullptr;
-            CUDA_TRY(c, cudaIpcOpenMemHandle(&ps, h[3 * south + 2], cudaIpcMemLazyEnablePeerAccess));
+            cudaError_t e = cudaIpcOpenMemHandle(&ps, h[3 * south + 2], cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) { ps = nullptr; return fail(e, "cudaIpcOpenMemHandle(halo south)"); }
             if (north == south) pn = ps;
-            else CUDA_TRY(c, cudaIpcOpenMemHandle(&pn, h[3 * north + 2], cudaIpcMemLazyEnablePeerAccess));
+            else
+            {
+                e = cudaIpcOpenMemHandle(&pn, h[3 * north + 2], cudaIpcMemLazyEnablePeerAccess);
+                if (e != cudaSuccess) { pn = nullptr; return fail(e, "cudaIpcOpenMemHandle(halo north)"); }
+            }
             c->phalo_south = static_cast<TF*>(ps); c->phalo_north = static_cast<TF*>(pn);
         }
         pp.on = 1;
@@ -1099,6 +1119,7 @@ int mhh_diff_4_exec(mhh_ctx* ctx, const mhh_fields* f)
 int mhh_diff_2_get_dn(mhh_ctx* ctx, const mhh_fields* f, double dt, double* dn)
 {
     if (!ctx || !f || !dn) return MHH_E_INVALID;
+    SET_DEVICE(ctx);
     if (f->ns < 0 || f->ns > MHH_MAX_SCALARS) { ctx->err = "ns out of range"; return MHH_E_INVALID; }
     // Diff_2::create + get_dn (src/diff_2.cxx:133-152): host arithmetic on the grid metrics, no field pass
     DISPATCH1(ctx, ([&]() -> int {
@@ -1118,6 +1139,7 @@ int mhh_diff_2_get_dn(mhh_ctx* ctx, const mhh_fields* f, double dt, double* dn)
 int mhh_advec_get_cfl(mhh_ctx* ctx, int swadvec, const mhh_fields* f, double dt, double* cfl)
 {
     if (!ctx || !f || !cfl) return MHH_E_INVALID;
+    SET_DEVICE(ctx);
     if (swadvec != 25 && swadvec != 2 && swadvec != 4) { ctx->err = "advec_get_cfl: swadvec must be 25 (2i5), 2 or 4"; return MHH_E_INVALID; }
     int rc;
     if (swadvec == 2 || swadvec == 4)
@@ -1146,6 +1168,7 @@ int mhh_diff_smag2_exec(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm
 int mhh_diff_smag2_get_dn(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm, double dt, double* dn)
 {
     if (!ctx || !f || !prm || !dn) return MHH_E_INVALID;
+    SET_DEVICE(ctx);
     int rc;
     if (ctx->dtype == MHH_F64)
     {
@@ -1193,6 +1216,7 @@ int mhh_pres_exec(mhh_ctx* ctx, int swpres, const mhh_fields* f, double sub_dt)
 int mhh_pres_check_divergence(mhh_ctx* ctx, int swpres, const mhh_fields* f, double* divmax)
 {
     if (!ctx || !f || !divmax) return MHH_E_INVALID;
+    SET_DEVICE(ctx);
     if (swpres != 2 && swpres != 4) { ctx->err = "pres_check_divergence: swpres must be 2 or 4"; return MHH_E_INVALID; }
     if (swpres == 4)
     {

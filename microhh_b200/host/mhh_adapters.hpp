@@ -92,7 +92,12 @@ namespace mhhb200
                     std::vector<unsigned char> mine(MHH_IPC_BYTES), all((size_t)MHH_IPC_BYTES * md.nprocs);
                     MHH_CHECK(ctx, mhh_comm_get_ipc_handles(ctx, mine.data(), MHH_IPC_BYTES));
                     MPI_Allgather(mine.data(), MHH_IPC_BYTES, MPI_BYTE, all.data(), MHH_IPC_BYTES, MPI_BYTE, md.commxy);
-                    MHH_CHECK(ctx, mhh_comm_open_peers(ctx, all.data(), (int)all.size()));
+                    // the transport is a collective property: if the mapping failed on ANY rank, every rank goes back to NCCL
+                    // (a throw on one rank alone would leave the others hanging in their next collective)
+                    int ok = mhh_comm_open_peers(ctx, all.data(), (int)all.size()) == MHH_OK ? 1 : 0, all_ok = 0;
+                    MPI_Allreduce(&ok, &all_ok, 1, MPI_INT, MPI_MIN, md.commxy);
+                    if (!all_ok)
+                        MHH_CHECK(ctx, mhh_comm_disable_peers(ctx));
                 }
                 #endif
             }
@@ -164,7 +169,10 @@ namespace mhhb200
                 // ghost cells as the reference constructors ask for them (src/advec_2i5.cxx:42-45, src/advec_2.cxx:40-43,
                 // src/advec_4.cxx:41-48)
                 if (SW == 25) fluxlimit_list = in.get_list<std::string>("advec", "fluxlimit_list", "", std::vector<std::string>());   // src/advec_2i5.cxx:39-40
-                if (SW == 25) g.set_minimum_ghost_cells(3, 3, fluxlimit_list.empty() ? 1 : 2);                                        // :42-46
+                // :42-46 asks for (3, 3, 1|2); FOUR ghost cells in x make the interior start at a 16-byte aligned element (fp64 and
+                // fp32) and, for USESP, the row pitch a multiple of 16 bytes: the TMA-staged kernels then use aligned vector
+                // accesses throughout (with 3 the fp64 path still works, ~3 % slower; fp32 falls back to the cp.async kernels)
+                if (SW == 25) g.set_minimum_ghost_cells(4, 3, fluxlimit_list.empty() ? 1 : 2);
                 else if (SW == 2) g.set_minimum_ghost_cells(1, 1, 1);
                 else g.set_minimum_ghost_cells(3, 3, 3);
             }

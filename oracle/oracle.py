@@ -750,6 +750,93 @@ def advec_4_s(g, st, s, u, v, w):
     _advec4_generic(g, st, s, vx, vy, vz, g.dzi4, g.kstart)
 
 
+# --------------------------------------------------------------------------------------
+# Advec_4m (reference src/advec_4m.cxx:88-480): fully conservative 4th-order advection.  Every direction is
+#   - grad4( V(-1) * interp2(q[-3], q[0]),  V(0) * interp2(q[-1], q[0]),  V(+1) * interp2(q[0], q[+1]),  V(+2) * interp2(q[0], q[+3]) )
+# with V the advecting velocity interpolated (interp4c) to the four flux points; the whole right-hand side is ONE `+=` statement.
+# At the first / last row the outermost vertical term is mirrored over the wall (no-penetration).
+# --------------------------------------------------------------------------------------
+def _i4c(TF, a, b, c, d):
+    """interp4c (include/finite_difference.h:94-97): ci0*(a+d) + ci1*(b+c)"""
+    return TF(CI[0])*(a + d) + TF(CI[1])*(b + c)
+
+
+def _g4(TF, a, b, c, d):
+    """grad4 (include/finite_difference.h:128-131): -cg0*(d-a) - cg1*(c-b)"""
+    return -TF(CG[0])*(d - a) - TF(CG[1])*(c - b)
+
+
+def _advec4m_generic(g, at, q, velx, vely, velz, dzx, lo, wall_rows=True):
+    TF = g.TF
+    dxi, dyi = TF(1.)/g.dx, TF(1.)/g.dy
+    h = TF(0.5)
+    i2 = lambda a, b: h*(a + b)
+    rows = _advec4_rows(g, lo) if wall_rows else ((lo, g.kend, False, False),)
+    for (k0, k1, bot, top) in rows:
+        if k1 <= k0:
+            continue
+        Q = lambda dk=0, dj=0, di=0: _S(g, q, dk, dj, di, k0, k1)
+        tgt = _S(g, at, 0, 0, 0, k0, k1)
+        fx = _g4(TF, velx(0, k0, k1)*i2(Q(0, 0, -3), Q()), velx(1, k0, k1)*i2(Q(0, 0, -1), Q()),
+                     velx(2, k0, k1)*i2(Q(), Q(0, 0, 1)), velx(3, k0, k1)*i2(Q(), Q(0, 0, 3)))
+        fy = _g4(TF, vely(0, k0, k1)*i2(Q(0, -3), Q()), vely(1, k0, k1)*i2(Q(0, -1), Q()),
+                     vely(2, k0, k1)*i2(Q(), Q(0, 1)), vely(3, k0, k1)*i2(Q(), Q(0, 3)))
+        if bot:
+            z0 = -velz(2, k0, k1)*i2(Q(-1), Q(2))
+        else:
+            z0 = velz(0, k0, k1)*i2(Q(-3), Q())
+        if top:
+            z3 = -velz(1, k0, k1)*i2(Q(-2), Q(1))
+        else:
+            z3 = velz(3, k0, k1)*i2(Q(), Q(3))
+        fz = _g4(TF, z0, velz(1, k0, k1)*i2(Q(-1), Q()), velz(2, k0, k1)*i2(Q(), Q(1)), z3)
+        tgt[...] += - fx*dxi - fy*dyi - fz*_K(g, dzx, 0, k0, k1)
+
+
+def advec_4m_u(g, ut, u, v, w):
+    """src/advec_4m.cxx:90-182"""
+    TF = g.TF
+    U = lambda k0, k1, dk=0, dj=0, di=0: _S(g, u, dk, dj, di, k0, k1)
+    V = lambda k0, k1, dk=0, dj=0, di=0: _S(g, v, dk, dj, di, k0, k1)
+    W = lambda k0, k1, dk=0, dj=0, di=0: _S(g, w, dk, dj, di, k0, k1)
+    vx = lambda m, k0, k1: _i4c(TF, U(k0, k1, 0, 0, m-3), U(k0, k1, 0, 0, m-2), U(k0, k1, 0, 0, m-1), U(k0, k1, 0, 0, m))
+    vy = lambda m, k0, k1: _i4c(TF, V(k0, k1, 0, m-1, -2), V(k0, k1, 0, m-1, -1), V(k0, k1, 0, m-1, 0), V(k0, k1, 0, m-1, 1))
+    vz = lambda m, k0, k1: _i4c(TF, W(k0, k1, m-1, 0, -2), W(k0, k1, m-1, 0, -1), W(k0, k1, m-1, 0, 0), W(k0, k1, m-1, 0, 1))
+    _advec4m_generic(g, ut, u, vx, vy, vz, g.dzi4, g.kstart)
+
+
+def advec_4m_v(g, vt, u, v, w):
+    """src/advec_4m.cxx:184-276"""
+    TF = g.TF
+    U = lambda k0, k1, dk=0, dj=0, di=0: _S(g, u, dk, dj, di, k0, k1)
+    V = lambda k0, k1, dk=0, dj=0, di=0: _S(g, v, dk, dj, di, k0, k1)
+    W = lambda k0, k1, dk=0, dj=0, di=0: _S(g, w, dk, dj, di, k0, k1)
+    vx = lambda m, k0, k1: _i4c(TF, U(k0, k1, 0, -2, m-1), U(k0, k1, 0, -1, m-1), U(k0, k1, 0, 0, m-1), U(k0, k1, 0, 1, m-1))
+    vy = lambda m, k0, k1: _i4c(TF, V(k0, k1, 0, m-3), V(k0, k1, 0, m-2), V(k0, k1, 0, m-1), V(k0, k1, 0, m))
+    vz = lambda m, k0, k1: _i4c(TF, W(k0, k1, m-1, -2), W(k0, k1, m-1, -1), W(k0, k1, m-1, 0), W(k0, k1, m-1, 1))
+    _advec4m_generic(g, vt, v, vx, vy, vz, g.dzi4, g.kstart)
+
+
+def advec_4m_w(g, wt, u, v, w):
+    """src/advec_4m.cxx:278-323 (rows kstart+1 .. kend-1, no wall rows: w at the walls is zero)"""
+    TF = g.TF
+    U = lambda k0, k1, dk=0, dj=0, di=0: _S(g, u, dk, dj, di, k0, k1)
+    V = lambda k0, k1, dk=0, dj=0, di=0: _S(g, v, dk, dj, di, k0, k1)
+    W = lambda k0, k1, dk=0, dj=0, di=0: _S(g, w, dk, dj, di, k0, k1)
+    vx = lambda m, k0, k1: _i4c(TF, U(k0, k1, -2, 0, m-1), U(k0, k1, -1, 0, m-1), U(k0, k1, 0, 0, m-1), U(k0, k1, 1, 0, m-1))
+    vy = lambda m, k0, k1: _i4c(TF, V(k0, k1, -2, m-1), V(k0, k1, -1, m-1), V(k0, k1, 0, m-1), V(k0, k1, 1, m-1))
+    vz = lambda m, k0, k1: _i4c(TF, W(k0, k1, m-3), W(k0, k1, m-2), W(k0, k1, m-1), W(k0, k1, m))
+    _advec4m_generic(g, wt, w, vx, vy, vz, g.dzhi4, g.kstart+1, wall_rows=False)
+
+
+def advec_4m_s(g, st, s, u, v, w):
+    """src/advec_4m.cxx:325-400 (face velocities used directly)"""
+    vx = lambda m, k0, k1: _S(g, u, 0, 0, m-1, k0, k1)
+    vy = lambda m, k0, k1: _S(g, v, 0, m-1, 0, k0, k1)
+    vz = lambda m, k0, k1: _S(g, w, m-1, 0, 0, k0, k1)
+    _advec4m_generic(g, st, s, vx, vy, vz, g.dzi4, g.kstart)
+
+
 def advec_4_cfl(g, u, v, w, dt):
     """src/advec_4.cxx:50-86: interp4c(a,b,c,d) = ci0*(a+d) + ci1*(b+c)"""
     TF = g.TF
@@ -1815,6 +1902,10 @@ class NumpyKernels:
     def advec_4_w(self, wt, u, v, w): advec_4_w(self.g, wt, u, v, w)
     def advec_4_s(self, st, s, u, v, w): advec_4_s(self.g, st, s, u, v, w)
     def advec_4_cfl(self, u, v, w, dt): return float(advec_4_cfl(self.g, u, v, w, dt))
+    def advec_4m_u(self, ut, u, v, w): advec_4m_u(self.g, ut, u, v, w)
+    def advec_4m_v(self, vt, u, v, w): advec_4m_v(self.g, vt, u, v, w)
+    def advec_4m_w(self, wt, u, v, w): advec_4m_w(self.g, wt, u, v, w)
+    def advec_4m_s(self, st, s, u, v, w): advec_4m_s(self.g, st, s, u, v, w)
     def diff_4_c(self, at, a, visc): diff_4_c(self.g, at, a, visc)
     def diff_4_w(self, wt, w, visc): diff_4_w(self.g, wt, w, visc)
     def diff_2_w(self, wt, w, visc): diff_2_w(self.g, wt, w, visc)

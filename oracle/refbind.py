@@ -125,6 +125,18 @@ class RefKernels:
     def advec_4_s(self, st, s, u, v, w):
         g = self.g; self._call("ref_advec_4_s", st, s, u, v, w, g.dzi4, g.dx, g.dy)
 
+    def advec_4m_u(self, ut, u, v, w):
+        g = self.g; self._call("ref_advec_4m_u", ut, u, v, w, g.dzi4, g.dx, g.dy)
+
+    def advec_4m_v(self, vt, u, v, w):
+        g = self.g; self._call("ref_advec_4m_v", vt, u, v, w, g.dzi4, g.dx, g.dy)
+
+    def advec_4m_w(self, wt, u, v, w):
+        g = self.g; self._call("ref_advec_4m_w", wt, u, v, w, g.dzhi4, g.dx, g.dy)
+
+    def advec_4m_s(self, st, s, u, v, w):
+        g = self.g; self._call("ref_advec_4m_s", st, s, u, v, w, g.dzi4, g.dx, g.dy)
+
     def advec_4_cfl(self, u, v, w, dt):
         g = self.g
         return self._call("ref_advec_4_cfl", u, v, w, g.dzi, g.dx, g.dy, float(dt), restype=C.c_double)
