@@ -108,7 +108,7 @@ typedef struct mhh_fields
 /* Run-time switches of the path ([advec] [diff] [boundary] [thermo] of the .ini). */
 typedef struct mhh_params
 {
-    int    swadvec;              /* 25 = 2i5, 2 = 2, 4 = 4 */
+    int    swadvec;              /* 25 = 2i5, 2 = 2, 4 = 4, 41 = 4m */
     int    swdiff;               /* 1 = smag2, 2 = 2, 4 = 4 (the 4th-order configuration: 4 + 4 + pres_4 on a 4th-order grid) */
     int    swthermo;             /* 0 = off, 1 = dry (buoyancy from scalar 0 = th) */
     int    surface_model;        /* Boundary switch != "default"  (Surface_model::Enabled) */
@@ -253,7 +253,8 @@ MHH_API int mhh_boundary_ghost_cells_4th(mhh_ctx* ctx, void* fld, int bcbot, con
 MHH_API int mhh_boundary_ghost_cells_w_4th(mhh_ctx* ctx, void* w, int conservation);
 
 /* ---- Advec<TF>::exec / get_cfl  (swadvec = 25: Advec_2i5, src/advec_2i5.cxx:955-1063;
- *      swadvec = 2: Advec_2, src/advec_2.cxx:288-345; swadvec = 4: Advec_4, src/advec_4.cxx:573-684) */
+ *      swadvec = 2: Advec_2, src/advec_2.cxx:288-345; swadvec = 4: Advec_4, src/advec_4.cxx:573-684;
+ *      swadvec = 41: Advec_4m, src/advec_4m.cxx:511-615 -- the fully conservative scheme cases/moser180 ships with) */
 MHH_API int mhh_advec_exec(mhh_ctx* ctx, int swadvec, const mhh_fields* f);
 MHH_API int mhh_advec_get_cfl(mhh_ctx* ctx, int swadvec, const mhh_fields* f, double dt, double* cfl);
 

@@ -67,7 +67,7 @@ def _get_sub(ini, sec, key, sub, default=None, conv=str):
 
 _MBC = {"noslip": capi.BC_DIRICHLET, "freeslip": capi.BC_NEUMANN, "neumann": capi.BC_NEUMANN}
 _SBC = {"dirichlet": capi.BC_DIRICHLET, "neumann": capi.BC_NEUMANN, "flux": capi.BC_NEUMANN}
-_SWADVEC = {"2": 2, "2i5": 25, "4": 4}
+_SWADVEC = {"2": 2, "2i5": 25, "4": 4, "4m": 41}
 _SWDIFF = {"smag2": 1, "2": 2, "4": 4}
 
 
@@ -130,7 +130,7 @@ class CaseConfig:
             bad.append(f"swpres={self.swpres}")
         if self.swthermo not in ("0", "dry"):
             bad.append(f"swthermo={self.swthermo}")
-        if self.order == "4" and (self.swadvec, self.swdiff, self.swpres) != ("4", "4", "4") and not bad:
+        if self.order == "4" and (self.swadvec not in ("4", "4m") or (self.swdiff, self.swpres) != ("4", "4")) and not bad:
             bad.append("4th-order grid with mixed schemes")
         if self.order == "4" and self.swthermo != "0":
             bad.append("4th-order grid with thermo")

@@ -198,7 +198,7 @@ template <typename TF> int check_mom(Ctx<TF>* c, const mhh_fields* f, bool need_
 template <typename TF> int evisc_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, const TF* n2);
 template <typename TF> int tend_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, bool adv, bool diff, bool buoy);
 template <typename TF> int o2_impl(Ctx<TF>* c, const mhh_fields* f, bool adv, bool diff, bool buoy);
-template <typename TF> int o4_impl(Ctx<TF>* c, const mhh_fields* f, bool adv, bool diff);
+template <typename TF> int o4_impl(Ctx<TF>* c, const mhh_fields* f, int adv_sw, bool diff);
 template <typename TF> int o2_cfl_impl(Ctx<TF>* c, const mhh_fields* f, double* out, int order);
 template <typename TF> int reduce_mode_impl(Ctx<TF>* c, int mode, const TF* u, const TF* v, const TF* w, TF p0, TF p1, TF p2, double* out);
 // host_pres.cu

@@ -383,9 +383,9 @@ int substep_o4_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, int 
         if ((rc = ghost4_impl<TF>(c, P<TF>(f->s[n]), prm->sbcbot[n], P<TF>(f->s_bot[n]), P<TF>(f->s_gradbot[n]),
                                   prm->sbctop[n], P<TF>(f->s_top[n]), P<TF>(f->s_gradtop[n]))) != MHH_OK) return rc;
     if ((rc = ghost4w_impl<TF>(c, P<TF>(f->w), 1)) != MHH_OK) return rc;        // (the normal-type fill right before is overwritten)
-    if ((rc = o4_impl<TF>(c, f, true, false)) != MHH_OK) return rc;
+    if ((rc = o4_impl<TF>(c, f, prm->swadvec, false)) != MHH_OK) return rc;
     if ((rc = ghost4w_impl<TF>(c, P<TF>(f->w), 0)) != MHH_OK) return rc;
-    if ((rc = o4_impl<TF>(c, f, false, true)) != MHH_OK) return rc;
+    if ((rc = o4_impl<TF>(c, f, 0, true)) != MHH_OK) return rc;
     const double cBd[3] = {1. / 3., 15. / 16., 8. / 15.};
     if (c->forcing_set)
     {
@@ -414,14 +414,15 @@ int substep_check(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, bool& 
     NEED_BASE(c);
     NEED(c, prm, "params");
     o4 = false;
-    if (prm->swadvec == 4 || prm->swdiff == 4)
+    if (prm->swadvec == 4 || prm->swadvec == 41 || prm->swdiff == 4)
     {
-        if (prm->swadvec != 4 || prm->swdiff != 4) { c->err = "dycore_substep: the 4th-order configuration is swadvec = 4 with swdiff = 4 (and pres_4)"; return MHH_E_INVALID; }
+        if ((prm->swadvec != 4 && prm->swadvec != 41) || prm->swdiff != 4)
+        { c->err = "dycore_substep: the 4th-order configuration is swadvec = 4 or 4m (41) with swdiff = 4 (and pres_4)"; return MHH_E_INVALID; }
         o4 = true;
         return MHH_OK;
     }
     if ((prm->swadvec != 25 && prm->swadvec != 2) || (prm->swdiff != 1 && prm->swdiff != 2))
-    { c->err = "dycore_substep: swadvec must be 2i5 (25), 2 or 4, swdiff smag2 (1), 2 or 4"; return MHH_E_INVALID; }
+    { c->err = "dycore_substep: swadvec must be 2i5 (25), 2, 4 or 4m (41), swdiff smag2 (1), 2 or 4"; return MHH_E_INVALID; }
     const bool smag = prm->swdiff == 1;
     int rc = check_mom<TF>(c, f, smag, smag && prm->surface_model != 0);
     if (rc != MHH_OK) return rc;
@@ -1098,9 +1099,9 @@ int mhh_boundary_ghost_cells_w_4th(mhh_ctx* ctx, void* w, int conservation)
 
 int mhh_advec_exec(mhh_ctx* ctx, int swadvec, const mhh_fields* f)
 {
-    if (ctx && swadvec != 25 && swadvec != 2 && swadvec != 4) { ctx->err = "advec_exec: swadvec must be 25 (2i5), 2 or 4"; return MHH_E_INVALID; }
+    if (ctx && swadvec != 25 && swadvec != 2 && swadvec != 4 && swadvec != 41) { ctx->err = "advec_exec: swadvec must be 25 (2i5), 2, 4 or 41 (4m)"; return MHH_E_INVALID; }
     if (swadvec == 2) DISPATCH1(ctx, o2_impl<TF>(c, f, true, false, false));
-    if (swadvec == 4) DISPATCH1(ctx, o4_impl<TF>(c, f, true, false));
+    if (swadvec == 4 || swadvec == 41) DISPATCH1(ctx, o4_impl<TF>(c, f, swadvec, false));
     DISPATCH1(ctx, tend_impl<TF>(c, f, nullptr, true, false, false));
 }
 
@@ -1113,7 +1114,7 @@ int mhh_diff_2_exec(mhh_ctx* ctx, const mhh_fields* f)
 int mhh_diff_4_exec(mhh_ctx* ctx, const mhh_fields* f)
 {
     if (!f) return MHH_E_INVALID;
-    DISPATCH1(ctx, o4_impl<TF>(c, f, false, true));
+    DISPATCH1(ctx, o4_impl<TF>(c, f, 0, true));
 }
 
 int mhh_diff_2_get_dn(mhh_ctx* ctx, const mhh_fields* f, double dt, double* dn)
@@ -1140,9 +1141,9 @@ int mhh_advec_get_cfl(mhh_ctx* ctx, int swadvec, const mhh_fields* f, double dt,
 {
     if (!ctx || !f || !cfl) return MHH_E_INVALID;
     SET_DEVICE(ctx);
-    if (swadvec != 25 && swadvec != 2 && swadvec != 4) { ctx->err = "advec_get_cfl: swadvec must be 25 (2i5), 2 or 4"; return MHH_E_INVALID; }
+    if (swadvec != 25 && swadvec != 2 && swadvec != 4 && swadvec != 41) { ctx->err = "advec_get_cfl: swadvec must be 25 (2i5), 2, 4 or 41 (4m)"; return MHH_E_INVALID; }
     int rc;
-    if (swadvec == 2 || swadvec == 4)
+    if (swadvec == 2 || swadvec == 4 || swadvec == 41)
     {
         if (ctx->dtype == MHH_F64) { rc = o2_cfl_impl<double>(static_cast<Ctx<double>*>(ctx), f, cfl, swadvec); if (rc == MHH_OK) *cfl = *cfl * dt; }
         else { rc = o2_cfl_impl<float>(static_cast<Ctx<float>*>(ctx), f, cfl, swadvec); if (rc == MHH_OK) *cfl = (double)((float)*cfl * (float)dt); }

@@ -416,10 +416,11 @@ int o2_impl(Ctx<TF>* c, const mhh_fields* f, bool adv, bool diff, bool buoy)
     return MHH_OK;
 }
 
-// Advec_4 / Diff_4 in any combination (order4_kernels.cuh)
+// Advec_4 (adv_sw = 4) or Advec_4m (adv_sw = 41) / Diff_4 in any combination (order4_kernels.cuh)
 template <typename TF>
-int o4_impl(Ctx<TF>* c, const mhh_fields* f, bool adv, bool diff)
+int o4_impl(Ctx<TF>* c, const mhh_fields* f, int adv_sw, bool diff)
 {
+    const bool adv = adv_sw == 4;
     const GridDev<TF>& g = c->g;
     if (!g.dzi4) { c->err = "4th-order schemes need a 4th-order grid (dzi4 / dzhi4 in mhh_grid_desc, three ghost cells)"; return MHH_E_INVALID; }
     if (g.kmax < 4) { c->err = "4th-order schemes need ktot >= 4"; return MHH_E_INVALID; }
@@ -434,6 +435,19 @@ int o4_impl(Ctx<TF>* c, const mhh_fields* f, bool adv, bool diff)
     const bool dim3 = g.jtot > 1;
     {
         ::dim3 gr = c->grd_interior(), b = c->blk();
+        if (adv_sw == 41)
+        {
+            o4m_uvw_kernel<TF><<<gr, b, 0, c->stream>>>(a, g);
+            KCHECKN(c, "o4m_uvw_kernel");
+            for (int n = 0; n < f->ns; ++n)
+            {
+                O4ScalArgs<TF> s{P<TF>(f->st[n]), P<TF>(f->s[n]), a.u, a.v, a.w, (TF)f->svisc[n], a.dxidxi_c, a.dyidyi_c};
+                o4m_s_kernel<TF><<<gr, b, 0, c->stream>>>(s, g);
+                KCHECKN(c, "o4m_s_kernel");
+            }
+            if (!diff) return MHH_OK;
+        }
+        else if (adv_sw != 0 && adv_sw != 4) { c->err = "o4_impl: the 4th-order advection schemes are 4 and 41 (4m)"; return MHH_E_INVALID; }
 #define O4(A, D, T) o4_uvw_kernel<TF, A, D, T><<<gr, b, 0, c->stream>>>(a, g)
         if (adv && diff) { if (dim3) O4(true, true, true); else O4(true, true, false); }
         else if (adv) { if (dim3) O4(true, false, true); else O4(true, false, false); }
@@ -461,9 +475,10 @@ int o2_cfl_impl(Ctx<TF>* c, const mhh_fields* f, double* out, int order)
     const GridDev<TF>& g = c->g;
     NEED(c, f->u, "u"); NEED(c, f->v, "v"); NEED(c, f->w, "w");
     CUDA_TRY(c, cudaMemsetAsync(c->d_red, 0, sizeof(double), c->stream));
-    if (order == 4) o4_cfl_kernel<TF><<<c->grd_interior(), c->blk(), 0, c->stream>>>(P<TF>(f->u), P<TF>(f->v), P<TF>(f->w), g, c->d_red);
+    if (order == 4) o4_cfl_kernel<TF, false><<<c->grd_interior(), c->blk(), 0, c->stream>>>(P<TF>(f->u), P<TF>(f->v), P<TF>(f->w), g, c->d_red);
+    else if (order == 41) o4_cfl_kernel<TF, true><<<c->grd_interior(), c->blk(), 0, c->stream>>>(P<TF>(f->u), P<TF>(f->v), P<TF>(f->w), g, c->d_red);
     else o2_cfl_kernel<TF><<<c->grd_interior(), c->blk(), 0, c->stream>>>(P<TF>(f->u), P<TF>(f->v), P<TF>(f->w), g, c->d_red);
-    const char* cfl_name = order == 4 ? "o4_cfl_kernel" : "o2_cfl_kernel";
+    const char* cfl_name = order == 2 ? "o2_cfl_kernel" : "o4_cfl_kernel";
     KCHECKN(c, cfl_name);
     if (c->nranks > 1)
     {
@@ -510,7 +525,7 @@ int reduce_mode_impl(Ctx<TF>* c, int mode, const TF* u, const TF* v, const TF* w
     template int check_mom<TF>(Ctx<TF>*, const mhh_fields*, bool, bool); \
     template int evisc_impl<TF>(Ctx<TF>*, const mhh_fields*, const mhh_params*, const TF*); \
     template int tend_impl<TF>(Ctx<TF>*, const mhh_fields*, const mhh_params*, bool, bool, bool); \
-    template int o2_impl<TF>(Ctx<TF>*, const mhh_fields*, bool, bool, bool); template int o4_impl<TF>(Ctx<TF>*, const mhh_fields*, bool, bool); \
+    template int o2_impl<TF>(Ctx<TF>*, const mhh_fields*, bool, bool, bool); template int o4_impl<TF>(Ctx<TF>*, const mhh_fields*, int, bool); \
     template int o2_cfl_impl<TF>(Ctx<TF>*, const mhh_fields*, double*, int); \
     template int reduce_mode_impl<TF>(Ctx<TF>*, int, const TF*, const TF*, const TF*, TF, TF, TF, double*);
 

@@ -189,6 +189,76 @@ __global__ void __launch_bounds__(256) o4_s_kernel(const O4ScalArgs<TF> a, const
     a.st[ijk] = st;
 }
 
+// ---- Advec_4m (src/advec_4m.cxx:88-415): the fully conservative 4th-order scheme.  Each direction is
+//   - grad4( V(-1) i2(q[-3], q[0]),  V(0) i2(q[-1], q[0]),  V(+1) i2(q[0], q[+1]),  V(+2) i2(q[0], q[+3]) ) * metric
+// with V the advecting velocity at the four flux points (interp4c across the direction, or the face velocity itself for a
+// scalar), i2 the two-point mean, and the three directions summed in ONE `+=`.  In the first / last cell-centred row the
+// outermost vertical term is mirrored over the wall: -V(+1) i2(q[-1], q[+2]) / -V(0) i2(q[-2], q[+1]).
+template <typename TF> __device__ __forceinline__ TF i4m(TF a, TF b, TF c, TF d)
+{ return W4<TF>::ci0 * (a + d) + W4<TF>::ci1 * (b + c); }
+template <typename TF> __device__ __forceinline__ TF g4m(TF a, TF b, TF c, TF d)
+{ return -W4<TF>::cg0 * (d - a) - W4<TF>::cg1 * (c - b); }
+
+//   VMODE 0: velocity interpolated across the direction with stride sv, 1: face velocity used directly,
+//         2: self-advection along the direction (vel == q, interpolated along sq).
+//   zmode 1 / 2: first / last cell-centred row of the vertical direction.
+template <typename TF, int VMODE>
+__device__ __forceinline__ TF o4m_div(const TF* __restrict__ q, const TF* __restrict__ vel, const long long ijk,
+        const long long sq, const long long sv, const int zmode)
+{
+    const TF h = TF(0.5);
+    TF V[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+    {
+        const long long o = ijk + (m - 1) * sq;
+        if (VMODE == 2) V[m] = i4m(q[o - 2 * sq], q[o - sq], q[o], q[o + sq]);
+        else if (VMODE == 1) V[m] = vel[o];
+        else V[m] = i4m(vel[o - 2 * sv], vel[o - sv], vel[o], vel[o + sv]);
+    }
+    const TF q0 = q[ijk];
+    const TF f0 = (zmode == 1) ? -V[2] * (h * (q[ijk - sq] + q[ijk + 2 * sq])) : V[0] * (h * (q[ijk - 3 * sq] + q0));
+    const TF f1 = V[1] * (h * (q[ijk - sq] + q0));
+    const TF f2 = V[2] * (h * (q0 + q[ijk + sq]));
+    const TF f3 = (zmode == 2) ? -V[1] * (h * (q[ijk - 2 * sq] + q[ijk + sq])) : V[3] * (h * (q0 + q[ijk + 3 * sq]));
+    return g4m(f0, f1, f2, f3);
+}
+
+template <typename TF>
+__global__ void __launch_bounds__(256) o4m_uvw_kernel(const O4Args<TF> a, const GridDev<TF> g)
+{
+    const int i = g.istart + blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = g.jstart + blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = g.kstart + blockIdx.z;
+    if (i >= g.iend || j >= g.jend) return;
+    const long long jj = g.icells, kk = g.ijcells;
+    const long long ijk = i + j * jj + k * kk;
+    const TF* __restrict__ u = a.u; const TF* __restrict__ v = a.v; const TF* __restrict__ w = a.w;
+    const TF dxi = g.dxi, dyi = g.dyi;
+    const int zc = (k == g.kstart) ? 1 : (k == g.kend - 1 ? 2 : 0);
+    a.ut[ijk] += - o4m_div<TF, 2>(u, u, ijk, 1, 1, 0) * dxi - o4m_div<TF, 0>(u, v, ijk, jj, 1, 0) * dyi
+                 - o4m_div<TF, 0>(u, w, ijk, kk, 1, zc) * g.dzi4[k];
+    a.vt[ijk] += - o4m_div<TF, 0>(v, u, ijk, 1, jj, 0) * dxi - o4m_div<TF, 2>(v, v, ijk, jj, jj, 0) * dyi
+                 - o4m_div<TF, 0>(v, w, ijk, kk, jj, zc) * g.dzi4[k];
+    if (k > g.kstart)       // w rows kstart+1 .. kend-1: no wall variants (w and its mirrored ghost levels vanish at the walls)
+        a.wt[ijk] += - o4m_div<TF, 0>(w, u, ijk, 1, kk, 0) * dxi - o4m_div<TF, 0>(w, v, ijk, jj, kk, 0) * dyi
+                     - o4m_div<TF, 2>(w, w, ijk, kk, kk, 0) * g.dzhi4[k];
+}
+
+template <typename TF>
+__global__ void __launch_bounds__(256) o4m_s_kernel(const O4ScalArgs<TF> a, const GridDev<TF> g)
+{
+    const int i = g.istart + blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = g.jstart + blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = g.kstart + blockIdx.z;
+    if (i >= g.iend || j >= g.jend) return;
+    const long long jj = g.icells, kk = g.ijcells;
+    const long long ijk = i + j * jj + k * kk;
+    const int zc = (k == g.kstart) ? 1 : (k == g.kend - 1 ? 2 : 0);
+    a.st[ijk] += - o4m_div<TF, 1>(a.s, a.u, ijk, 1, 0, 0) * g.dxi - o4m_div<TF, 1>(a.s, a.v, ijk, jj, 0, 0) * g.dyi
+                 - o4m_div<TF, 1>(a.s, a.w, ijk, kk, 0, zc) * g.dzi4[k];
+}
+
 // 4th-order vertical ghost cells of a cell-centred field (src/boundary.cxx:776-848): two levels at either wall from the
 // wall value (Dirichlet) or the wall gradient (Neumann / flux).  gb / gt = grad4 of the z levels around the wall.
 template <typename TF>
@@ -245,7 +315,8 @@ __global__ void ghost_cells_w_4th_kernel(TF* __restrict__ w, const GridDev<TF> g
 }
 
 // Advec_4 calc_cfl (src/advec_4.cxx:50-86): interp4c(a,b,c,d) = ci0*(a+d) + ci1*(b+c)
-template <typename TF>
+// Advec_4m calc_cfl (src/advec_4m.cxx:51-88) sums the four weighted terms one by one instead: SUM4 = true.
+template <typename TF, bool SUM4>
 __global__ void __launch_bounds__(256) o4_cfl_kernel(const TF* __restrict__ u, const TF* __restrict__ v, const TF* __restrict__ w,
         const GridDev<TF> g, double* __restrict__ out)
 {
@@ -257,7 +328,8 @@ __global__ void __launch_bounds__(256) o4_cfl_kernel(const TF* __restrict__ u, c
     {
         const long long jj = g.icells, kk = g.ijcells;
         const long long ijk = i + j * jj + k * kk;
-        auto c4 = [](TF a, TF b, TF c, TF d) { return W4<TF>::ci0 * (a + d) + W4<TF>::ci1 * (b + c); };
+        auto c4 = [](TF a, TF b, TF c, TF d) { return SUM4 ? W4<TF>::ci0 * a + W4<TF>::ci1 * b + W4<TF>::ci2 * c + W4<TF>::ci3 * d
+                                                           : W4<TF>::ci0 * (a + d) + W4<TF>::ci1 * (b + c); };
         val = absf(c4(u[ijk - 1], u[ijk], u[ijk + 1], u[ijk + 2])) * g.dxi
             + absf(c4(v[ijk - jj], v[ijk], v[ijk + jj], v[ijk + 2 * jj])) * g.dyi
             + absf(c4(w[ijk - kk], w[ijk], w[ijk + kk], w[ijk + 2 * kk])) * g.dzi[k];

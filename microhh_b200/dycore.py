@@ -13,7 +13,7 @@ import torch
 from . import capi
 from .capi import FieldsC, ParamsC, GridDesc, SurfaceC, ForcingC, MhhError
 
-SWADVEC = {"2i5": 25, "2": 2, "4": 4}
+SWADVEC = {"2i5": 25, "2": 2, "4": 4, "4m": 41}
 SWDIFF = {"smag2": 1, "2": 2, "4": 4}
 
 

@@ -158,7 +158,7 @@ namespace mhhb200
     }
 
     // ---- Advec_2i5 (src/advec_2i5.cxx:955-1063), Advec_2 (src/advec_2.cxx:288-345), Advec_4 (src/advec_4.cxx:573-684):
-    // SW = the C ABI's swadvec code (25, 2, 4)
+    // Advec_4m (src/advec_4m.cxx:511-615).  SW = the C ABI's swadvec code (25, 2, 4, 41)
     template<typename TF, int SW, Advection_type TYPE>
     class Advec_b200 : public Advec<TF>
     {
@@ -208,6 +208,7 @@ namespace mhhb200
     template<typename TF> using Advec_2i5_b200 = Advec_b200<TF, 25, Advection_type::Advec_2i5>;
     template<typename TF> using Advec_2_b200   = Advec_b200<TF, 2,  Advection_type::Advec_2>;
     template<typename TF> using Advec_4_b200   = Advec_b200<TF, 4,  Advection_type::Advec_4>;
+    template<typename TF> using Advec_4m_b200  = Advec_b200<TF, 41, Advection_type::Advec_4m>;
 
     // ---- Diff_smag2 (src/diff_smag2.cxx:312-607) ------------------------------------------------
     template<typename TF>

@@ -848,6 +848,18 @@ def advec_4_cfl(g, u, v, w, dt):
     return TF(TF(c.max())*TF(dt))
 
 
+def advec_4m_cfl(g, u, v, w, dt):
+    """src/advec_4m.cxx:51-88: the interpolation is the plain four-term sum ci0*a + ci1*b + ci2*c + ci3*d (not interp4c)"""
+    TF = g.TF
+    dxi, dyi = TF(1.)/g.dx, TF(1.)/g.dy
+    c0, c1, c2, c3 = (TF(x) for x in CI)
+    s4 = lambda a, b, c, d: c0*a + c1*b + c2*c + c3*d
+    c = ( np.abs(s4(_S(g, u, 0, 0, -1), _S(g, u), _S(g, u, 0, 0, 1), _S(g, u, 0, 0, 2)))*dxi
+        + np.abs(s4(_S(g, v, 0, -1), _S(g, v), _S(g, v, 0, 1), _S(g, v, 0, 2)))*dyi
+        + np.abs(s4(_S(g, w, -1), _S(g, w), _S(g, w, 1), _S(g, w, 2)))*_K(g, g.dzi) )
+    return TF(TF(c.max())*TF(dt))
+
+
 # --------------------------------------------------------------------------------------
 # Diff_4 (reference src/diff_4.cxx:40-175): nu * (7-point cdg laplacian in x, y; div(grad) with cg weights and
 # one-sided bg / tg gradients at the walls in z).  Three separate `+=` statements per point.
@@ -1902,6 +1914,7 @@ class NumpyKernels:
     def advec_4_w(self, wt, u, v, w): advec_4_w(self.g, wt, u, v, w)
     def advec_4_s(self, st, s, u, v, w): advec_4_s(self.g, st, s, u, v, w)
     def advec_4_cfl(self, u, v, w, dt): return float(advec_4_cfl(self.g, u, v, w, dt))
+    def advec_4m_cfl(self, u, v, w, dt): return float(advec_4m_cfl(self.g, u, v, w, dt))
     def advec_4m_u(self, ut, u, v, w): advec_4m_u(self.g, ut, u, v, w)
     def advec_4m_v(self, vt, u, v, w): advec_4m_v(self.g, vt, u, v, w)
     def advec_4m_w(self, wt, u, v, w): advec_4m_w(self.g, wt, u, v, w)

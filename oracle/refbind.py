@@ -137,6 +137,10 @@ class RefKernels:
     def advec_4m_s(self, st, s, u, v, w):
         g = self.g; self._call("ref_advec_4m_s", st, s, u, v, w, g.dzi4, g.dx, g.dy)
 
+    def advec_4m_cfl(self, u, v, w, dt):
+        g = self.g
+        return self._call("ref_advec_4m_cfl", u, v, w, g.dzi, g.dx, g.dy, float(dt), restype=C.c_double)
+
     def advec_4_cfl(self, u, v, w, dt):
         g = self.g
         return self._call("ref_advec_4_cfl", u, v, w, g.dzi, g.dx, g.dy, float(dt), restype=C.c_double)

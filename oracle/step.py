@@ -118,7 +118,7 @@ def _pres_and_rk3(g, K, c, prm, substep, dt, pres, lap):
 
 
 def dycore_substep_o4(g, K, c, prm, substep, dt, pres=None):
-    """The 4th-order DNS configuration (swspatialorder=4: advec_4 + diff_4 + pres_4, no thermo), same call order of
+    """The 4th-order DNS configuration (swspatialorder=4: advec_4 or advec_4m + diff_4 + pres_4, no thermo), same call order of
     Model<TF>::exec (src/model.cxx:368-437): cyclic -> 4th-order ghost cells (w: normal type) -> w conservation type ->
     advec -> w normal -> diff -> w conservation -> pres -> w normal -> rk3."""
     scal = c["scalars"]
@@ -132,11 +132,12 @@ def dycore_substep_o4(g, K, c, prm, substep, dt, pres=None):
         K.ghost_cells_bot_4th(c[s], prm["sbcbot"], c.get(s + "_bot"), c.get(s + "_gradbot"))
         K.ghost_cells_top_4th(c[s], prm["sbctop"], c.get(s + "_top"), c.get(s + "_gradtop"))
     K.ghost_cells_w_4th(c["w"], True)
-    K.advec_4_u(c["ut"], c["u"], c["v"], c["w"])
-    K.advec_4_v(c["vt"], c["u"], c["v"], c["w"])
-    K.advec_4_w(c["wt"], c["u"], c["v"], c["w"])
+    a4 = "advec_4m_" if prm.get("swadvec") == "4m" else "advec_4_"          # src/advec.cxx:79-84
+    getattr(K, a4 + "u")(c["ut"], c["u"], c["v"], c["w"])
+    getattr(K, a4 + "v")(c["vt"], c["u"], c["v"], c["w"])
+    getattr(K, a4 + "w")(c["wt"], c["u"], c["v"], c["w"])
     for s in scal:
-        K.advec_4_s(c[s + "t"], c[s], c["u"], c["v"], c["w"])
+        getattr(K, a4 + "s")(c[s + "t"], c[s], c["u"], c["v"], c["w"])
     K.ghost_cells_w_4th(c["w"], False)
     K.diff_4_c(c["ut"], c["u"], prm["visc"])
     K.diff_4_c(c["vt"], c["v"], prm["visc"])
@@ -156,7 +157,7 @@ def dycore_substep_o4(g, K, c, prm, substep, dt, pres=None):
 def dycore_step(g, K, c, prm, dt, timers=None, surface_model=None, forcing=None):
     pres = None
     for ss in range(3):
-        if prm.get("swadvec") == "4":
+        if prm.get("swadvec") in ("4", "4m"):
             pres = dycore_substep_o4(g, K, c, prm, ss, dt, pres)
         else:
             pres = dycore_substep(g, K, c, prm, ss, dt, pres, timers, surface_model, forcing)

@@ -56,7 +56,8 @@ def test_defaults_follow_the_grid_order():
 
 
 def test_out_of_path_switches_are_named():
-    assert case("moser180").unsupported() == ["swadvec=4m"]
+    m180 = case("moser180")                                                      # ships with swadvec=4m
+    assert m180.swadvec == "4m" and m180.unsupported() == [] and m180.make_params().swadvec == 41
     assert "swthermo=moist" in case("bomex").unsupported()
     assert "swthermo=buoy" in case("weakscaling").unsupported()
     with pytest.raises(ValueError):

@@ -269,9 +269,41 @@ def test_pres_4_exec(dtype, shape, stretched):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(32, 16, 12), (24, 1, 8), (20, 12, 6)])
+@pytest.mark.parametrize("stretched", [False, True])
+def test_advec_4m(dtype, shape, stretched):
+    """Advec_4m (src/advec_4m.cxx:51-415), the fully conservative 4th-order scheme cases/moser180 ships with: tendencies of
+    u, v, w and a scalar and the CFL number through mhh_advec_exec / mhh_advec_get_cfl with swadvec = 41."""
+    from util import stretched_z
+    from microhh_b200 import dycore as D
+    from microhh_b200.grid import GridData
+    it, jt, kt = shape
+    z = stretched_z(kt, 2.) if stretched else None
+    g = O.Grid(it, jt, kt, 6.28, 3.14, 2., 3, 3, 3, dtype, z=z, order=4)
+    gd = GridData(it, jt, kt, 6.28, 3.14, 2., 3, 3, 3, dtype, z=z, order=4)
+    rng = np.random.default_rng(7)
+    fld = lambda: rng.standard_normal(gd.shape).astype(dtype)
+    case = dict(u=fld(), v=fld(), w=fld(), th=fld(), ut=fld(), vt=fld(), wt=fld(), tht=fld())
+    ctx = D.Context(gd, 0)
+    ones = np.ones(gd.kcells, dtype)
+    ctx.set_basestate(ones, ones, 300*ones, 300*ones)
+    f = D.Fields(ctx, case, visc=0.7, svisc=1.3)
+    D.Advec(ctx, "4m").exec(f)
+    ref = {n: case[n].copy() for n in ("ut", "vt", "wt", "tht")}
+    O.advec_4m_u(g, ref["ut"], case["u"], case["v"], case["w"]); O.advec_4m_v(g, ref["vt"], case["u"], case["v"], case["w"])
+    O.advec_4m_w(g, ref["wt"], case["u"], case["v"], case["w"]); O.advec_4m_s(g, ref["tht"], case["th"], case["u"], case["v"], case["w"])
+    for n in ref:
+        assert rel_l2(f[n].cpu().numpy(), ref[n]) <= TOL[dtype], n
+        assert np.array_equal(f[n].cpu().numpy()[:g.kstart], case[n][:g.kstart])        # ghost levels untouched
+    cfl = D.Advec(ctx, "4m").get_cfl(f, 3.0)
+    assert abs(cfl - float(O.advec_4m_cfl(g, case["u"], case["v"], case["w"], 3.0))) <= 10*TOL[dtype]*cfl
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("shape,mbc", [((32, 24, 16), 0), ((24, 1, 12), 0), ((32, 16, 12), 1)])
-def test_full_rk3_step_order4(dtype, shape, mbc):
-    """The 4th-order DNS configuration (moser180 / taylorgreen style: advec_4 + diff_4 + pres_4, 4th-order ghost cells,
+@pytest.mark.parametrize("swadvec", ["4", "4m"])
+def test_full_rk3_step_order4(dtype, shape, mbc, swadvec):
+    """The 4th-order DNS configuration (moser180 / taylorgreen style: advec_4 or advec_4m + diff_4 + pres_4, 4th-order ghost cells,
     no thermo): one full RK3 step == the oracle in the reference's call order; no-slip (Dirichlet) and free-slip walls."""
     from util import stretched_z
     from microhh_b200 import dycore as D, capi
@@ -296,8 +328,8 @@ def test_full_rk3_step_order4(dtype, shape, mbc):
     ctx.set_basestate(ones, ones, 300*ones, 300*ones)
     visc = 1e-3
     f = D.Fields(ctx, case, visc=visc, svisc=visc)
-    prm = D.make_params(swadvec="4", swdiff="4", swthermo=None, surface_model=False, mbcbot=mbc, mbctop=mbc)
-    oprm = ostep.default_params(); oprm.update(swadvec="4", swdiff="4", visc=visc, svisc=visc, mbcbot=mbc, mbctop=mbc)
+    prm = D.make_params(swadvec=swadvec, swdiff="4", swthermo=None, surface_model=False, mbcbot=mbc, mbctop=mbc)
+    oprm = ostep.default_params(); oprm.update(swadvec=swadvec, swdiff="4", visc=visc, svisc=visc, mbcbot=mbc, mbctop=mbc)
     dt = 0.01
     D.Dycore(ctx, prm).step(f, dt)
     ostep.dycore_step(g, O.NumpyKernels(g), case, oprm, dt)

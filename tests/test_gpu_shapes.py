@@ -169,8 +169,10 @@ def test_fused_tendencies_multi_tile(dtype, igc, itot, surface):
 
 
 # ------------------------------------------------------------------------------------------------ 4th-order DNS
-def test_moser180_shape_order4_fp64():
-    """configs[2]: moser180-shaped 256 x 192 x 128 channel (advec_4 + diff_4 + pres_4, no-slip walls, stretched z)."""
+@pytest.mark.parametrize("swadvec", ["4m", "4"])
+def test_moser180_shape_order4_fp64(swadvec):
+    """configs[2]: moser180-shaped 256 x 192 x 128 channel (no-slip walls, stretched z): advec_4m + diff_4 + pres_4 as
+    cases/moser180/moser180.ini ships it, and the plain advec_4 variant."""
     from microhh_b200.grid import GridData
     from microhh_b200.synthetic import make_case
     from microhh_b200 import dycore as D
@@ -193,8 +195,8 @@ def test_moser180_shape_order4_fp64():
     ctx.set_basestate(ones, ones, 300*ones, 300*ones)
     visc = 1e-3
     f = D.Fields(ctx, case, visc=visc, svisc=visc)
-    prm = D.make_params(swadvec="4", swdiff="4", swthermo=None, surface_model=False, mbcbot=0, mbctop=0)
-    oprm = ostep.default_params(); oprm.update(swadvec="4", swdiff="4", visc=visc, svisc=visc, mbcbot=0, mbctop=0,
+    prm = D.make_params(swadvec=swadvec, swdiff="4", swthermo=None, surface_model=False, mbcbot=0, mbctop=0)
+    oprm = ostep.default_params(); oprm.update(swadvec=swadvec, swdiff="4", visc=visc, svisc=visc, mbcbot=0, mbctop=0,
                                                swthermo=None, surface_model=False)
     dt = 0.002
     D.Dycore(ctx, prm).step(f, dt)

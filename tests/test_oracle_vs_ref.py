@@ -166,6 +166,34 @@ def test_order4_kernels_bitexact(dtype, shape, stretched):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(16, 12, 10), (24, 1, 8), (12, 10, 6)])
+@pytest.mark.parametrize("stretched", [False, True])
+def test_advec_4m_bitexact(dtype, shape, stretched):
+    """Advec_4m (src/advec_4m.cxx:51-415, the fully conservative 4th-order scheme moser180 ships with): numpy oracle ==
+    compiled reference, bit for bit, tendencies and CFL number; it is not Advec_4 under another name."""
+    from util import stretched_z
+    rng = np.random.default_rng(5)
+    it, jt, kt = shape
+    g = O.Grid(it, jt, kt, 6.28, 3.14, 2., 3, 3, 3, dtype, z=stretched_z(kt, 2.) if stretched else None, order=4)
+    N, R = both(g)
+    fld = lambda: rng.standard_normal((g.kcells, g.jcells, g.icells)).astype(dtype)
+    u, v, w, s = fld(), fld(), fld(), fld()
+    t0 = {n: fld() for n in ("ut", "vt", "wt", "st")}
+    res = []
+    for K in (N, R):
+        t = {n: a.copy() for n, a in t0.items()}
+        K.advec_4m_u(t["ut"], u, v, w); K.advec_4m_v(t["vt"], u, v, w); K.advec_4m_w(t["wt"], u, v, w)
+        K.advec_4m_s(t["st"], s, u, v, w)
+        res.append((t, K.advec_4m_cfl(u, v, w, 2.0)))
+    for n in t0:
+        assert np.array_equal(res[0][0][n], res[1][0][n]), (n, float(np.abs(res[0][0][n].astype(np.float64) - res[1][0][n]).max()))
+        assert not np.array_equal(res[0][0][n], t0[n])
+    assert res[0][1] == res[1][1]
+    t4 = t0["ut"].copy(); N.advec_4_u(t4, u, v, w)
+    assert not np.array_equal(t4, res[0][0]["ut"])
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("surface", [True, False])
 def test_full_rk3_step_neutral_bitexact(dtype, surface):
     """LES step without thermo (swthermo=0): calc_evisc_neutral, no buoyancy."""
