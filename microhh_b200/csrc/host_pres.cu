@@ -271,18 +271,21 @@ int pres_set_values(Ctx<TF>* c)
     GridDev<TF>& g = c->g;
     const int kc = g.kcells; (void)kc;
     const TF* rr = c->h_rhoref.data(); const TF* rh = c->h_rhorefh.data();
-    // Pres_2::set_values (src/pres_2.cxx:124-153), in TF arithmetic like the reference
+    // Pres_2::set_values (src/pres_2.cxx:124-153) with the reference's own precision mix: the literals `2.`, `1.` are
+    // double, so for TF = float the cosine and the products are evaluated in double from a FLOAT pi and narrowed on the
+    // store; 1./(dx*dx) divides in double a product formed in TF.  (Pinned against the compiled reference:
+    // tests/test_oracle_vs_ref.py::test_pres_2_glue_bitexact.)
     const TF* dz = c->h_dz.data();          // context-owned copies: the caller's metric arrays need not outlive mhh_ctx_create
     const TF* dzhi = c->h_dzhi.data();
-    const TF dxidxi = TF(1.) / (g.dx * g.dx), dyidyi = TF(1.) / (g.dy * g.dy);
-    const TF pi = std::acos(TF(-1.));
+    const TF dxidxi = (TF)(1. / (double)(TF)(g.dx * g.dx)), dyidyi = (TF)(1. / (double)(TF)(g.dy * g.dy));
+    const TF pi = (TF)std::acos(-1.);
     std::vector<TF> bmati(c->nm), bmatj(g.jtot), a(g.kmax), cc(g.kmax), dz2rho(g.kmax), dz2(g.kmax);
     for (int j = 0; j < g.jtot / 2 + 1; ++j)
-        bmatj[j] = TF(2.) * (std::cos(TF(2.) * pi * (TF)j / (TF)g.jtot) - TF(1.)) * dyidyi;
+        bmatj[j] = (TF)(2. * (std::cos(2. * (double)pi * (double)(TF)j / (double)(TF)g.jtot) - 1.) * (double)dyidyi);
     for (int j = g.jtot / 2 + 1; j < g.jtot; ++j)
         bmatj[j] = bmatj[g.jtot - j];
     for (int i = 0; i < g.itot / 2 + 1; ++i)
-        bmati[i] = TF(2.) * (std::cos(TF(2.) * pi * (TF)i / (TF)g.itot) - TF(1.)) * dxidxi;
+        bmati[i] = (TF)(2. * (std::cos(2. * (double)pi * (double)(TF)i / (double)(TF)g.itot) - 1.) * (double)dxidxi);
     for (int k = 0; k < g.kmax; ++k)
     {
         a[k] = dz[k + g.kgc] * rh[k + g.kgc] * dzhi[k + g.kgc];

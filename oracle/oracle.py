@@ -11,16 +11,17 @@ results are bit-identical to the reference's own CPU kernels compiled with
 `-ffp-contract=off` (`oracle/_ref/libmhh_ref.so`; checked in tests/test_oracle_vs_ref.py
 and pinned by the golden vectors in tests/golden/).
 
-Parity status: PINNED for advec_2i5 / advec_2 / advec_4 / diff_smag2 / diff_2 / diff_4 / thermo_dry /
-boundary (cyclic, 2nd- and 4th-order vertical ghost cells) / rk3 / tdma against the reference's own
-compiled kernels (bit-exact).  "Parity unpinned" (class-member code of the reference that needs live
-Grid/Fields objects, restated and pinned by properties instead): Pres_2 / Pres_4 glue (input, matrix
-build, hdma, output; property = the corrected velocity is divergence-free to rounding) and the
-4th-order grid metrics (property = exact for a uniform grid).  The FFT (FFTW3, a system
-package that is not vendored in the reference; call sites reference src/fft.cxx:145-155,
-338-452) is restated from its published definition with numpy.fft (pocketfft):
-"parity unpinned" at the FFTW boundary, pinned instead by the DFT definition and by the
-post-pressure divergence.
+Parity status: PINNED, bit for bit, against the reference's own compiled code (tests/test_oracle_vs_ref.py):
+  * free-function kernels: advec_2i5 / advec_2 / advec_4 / advec_4m / diff_smag2 / diff_2 / diff_4 / thermo_dry /
+    boundary (cyclic, 2nd- and 4th-order vertical ghost cells) / rk3 / tdma / Monin-Obukhov surface solver / buffer / force;
+  * class-member code, run on stand-in objects (oracle/ref/ref_fake_pres.h, ref_grid.cpp): Grid::init + calculate (all
+    metrics incl. dzi4 / dzhi4), FFT::init / load / exec_forward / exec_backward (plans, slice loops, normalisation),
+    Pres_2 and Pres_4 set_values / input / solve (+ hdma) / output / calc_divergence, and full RK3 steps through them.
+ONE thing is "parity unpinned": the 1-D transform inside FFTW3 itself (a system package that is not in the reference
+tree nor in this image; call sites src/fft.cxx:145-155).  It is restated from FFTW's published R2HC / HC2R definition with
+pocketfft (numpy / scipy), checked against the DFT definition and through the post-pressure divergence; the reference's
+plans are executed by THIS transform in the tier-2 pin (oracle/ref/ref_fftw_shim.cpp), so last-bit differences between
+FFTW's and pocketfft's butterflies are the only part of the path no test here can see.
 """
 import numpy as np
 
@@ -1309,15 +1310,18 @@ class Pres2:
         """set_values: src/pres_2.cxx:124-153"""
         TF = g.TF
         self.g = g
-        dxidxi = TF(1./(g.dx*g.dx)); dyidyi = TF(1./(g.dy*g.dy))
-        pi = TF(np.arccos(TF(-1.)))
+        # the reference's own precision mix (pinned bit for bit against the compiled Pres_2::set_values): `2.`, `1.` are
+        # double literals, so the cosine and the products run in double from a TF-rounded pi and are narrowed on the store
+        D = np.float64
+        dxidxi = TF(1./D(TF(g.dx)*TF(g.dx))); dyidyi = TF(1./D(TF(g.dy)*TF(g.dy)))
+        pi = D(TF(np.arccos(-1.)))
         self.bmati = np.zeros(g.itot, TF); self.bmatj = np.zeros(g.jtot, TF)
         for j in range(g.jtot//2+1):
-            self.bmatj[j] = TF(2.) * (np.cos(TF(2.)*pi*TF(j)/TF(g.jtot))-TF(1.)) * dyidyi
+            self.bmatj[j] = TF(2. * (np.cos(2.*pi*D(TF(j))/D(TF(g.jtot)))-1.) * D(dyidyi))
         for j in range(g.jtot//2+1, g.jtot):
             self.bmatj[j] = self.bmatj[g.jtot-j]
         for i in range(g.itot//2+1):
-            self.bmati[i] = TF(2.) * (np.cos(TF(2.)*pi*TF(i)/TF(g.itot))-TF(1.)) * dxidxi
+            self.bmati[i] = TF(2. * (np.cos(2.*pi*D(TF(i))/D(TF(g.itot)))-1.) * D(dxidxi))
         for i in range(g.itot//2+1, g.itot):
             self.bmati[i] = self.bmati[g.itot-i]
         kgc = g.kgc

@@ -16,3 +16,8 @@ struct Ref_geom
     int igc, jgc, jtot;
 };
 extern Ref_geom ref_geom;
+
+// The reference's own Grid<TF> (ref_grid.cpp): one image per precision, shared by every stand-in object, and the zeroed
+// Master image (serial: npx = npy = 1) its `master` reference points to.
+void* ref_grid_image(int is_float);
+void* ref_master_image();

@@ -9,6 +9,8 @@
 #include "defines.h"
 #include "master.h"
 #include "boundary_cyclic.h"
+#include "grid.h"
+#include "transpose.h"
 #include "ref_common.h"
 
 Ref_geom ref_geom = {};
@@ -130,3 +132,25 @@ MHH_EXPORT void ref_boundary_cyclic_f32(float* data, int edge)
     alignas(16) static char buf[sizeof(Boundary_cyclic<float>)];
     reinterpret_cast<Boundary_cyclic<float>*>(buf)->exec(data, static_cast<Edge>(edge));
 }
+
+// ---- stand-ins for the objects the reference's FFT / Pres_2 / Pres_4 member functions reach through (tier-2 pin of the
+// pressure glue): Transpose / Boundary_cyclic::init / Master::print_message are the serial no-ops; the Grid is the
+// reference's own (ref_grid.cpp).
+cuda_raw_buffer::cuda_raw_buffer(size_t) {}        // CPU build: no device allocation (src/cuda_buffer.cxx, host branch)
+void cuda_raw_buffer::reallocate(size_t) {}
+
+template<typename TF> Transpose<TF>::Transpose(Master& m, Grid<TF>& g) : master(m), grid(g), mpi_types_allocated(false) {}
+template<typename TF> Transpose<TF>::~Transpose() {}
+template<typename TF> void Transpose<TF>::init() {}
+template Transpose<double>::Transpose(Master&, Grid<double>&);
+template Transpose<float>::Transpose(Master&, Grid<float>&);
+template Transpose<double>::~Transpose();
+template Transpose<float>::~Transpose();
+template void Transpose<double>::init();
+template void Transpose<float>::init();
+
+template<typename TF> void Boundary_cyclic<TF>::init() {}
+template void Boundary_cyclic<double>::init();
+template void Boundary_cyclic<float>::init();
+
+void Master::print_message(const char*, ...) {}

@@ -300,3 +300,150 @@ class RefForcing:
 
     def wls_local(self, st, s, wls):
         self._f("ref_force_wls_local")(self._p(st), self._p(s), self._p(wls), self._p(np.ascontiguousarray(self.g.dzhi)))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Tier-2 pin of the pressure glue: the reference's own FFT<TF> (src/fft.cxx), Pres_2<TF> (src/pres_2.cxx) and Pres_4<TF>
+# (src/pres_4.cxx) member functions, compiled where they lie and run on stand-in objects (oracle/ref/ref_fake_pres.h).
+# FFTW is not in this image: the plans the reference creates forward their batched 1-D transform to `_fft_callback`
+# below, i.e. to the oracle's own r2hc / hc2r -- so everything AROUND the 1-D transform (slice loops and strides, rhs,
+# modified wave numbers, matrix build, tdma / hdma, ghost cells, the gradient) is the reference's compiled code.
+# ---------------------------------------------------------------------------------------------------------------------
+_FFT_CB_TYPE = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int)
+
+
+def _fft_callback(pin, pout, n, howmany, stride, dist, kind, is_float):
+    from . import oracle as O
+    dt = np.float32 if is_float else np.float64
+    ct = C.c_float if is_float else C.c_double
+    extent = (howmany - 1)*dist + (n - 1)*stride + 1
+    isz = np.dtype(dt).itemsize
+    def view(ptr):
+        flat = np.ctypeslib.as_array((ct*extent).from_address(ptr))
+        return np.lib.stride_tricks.as_strided(flat, shape=(howmany, n), strides=(dist*isz, stride*isz))
+    x = np.ascontiguousarray(view(pin))
+    view(pout)[...] = O.r2hc(x, 1) if kind == 0 else O.hc2r(x, 1)
+
+
+_fft_cb_keepalive = _FFT_CB_TYPE(_fft_callback)
+
+
+class RefPres:
+    """Pres_2 (order 2) or Pres_4 (order 4) of the reference through its own init / set_values / input / solve / output."""
+
+    def __init__(self, g, order, rhoref=None, rhorefh=None):
+        self.lib = C.CDLL(lib_path(False))
+        self.g = g; self.order = order
+        TF = g.TF
+        self.sfx = "f64" if TF == np.float64 else "f32"
+        self.ct = C.c_double if TF == np.float64 else C.c_float
+        self.lib.ref_set_fft_callback(_fft_cb_keepalive)
+        arr = lambda a: np.ascontiguousarray(np.asarray(a, TF)[:g.kcells]) if a is not None else None
+        self._z = arr(g.z)
+        self._set_grid()
+        for n in ("ref_fft_create", "ref_pres_2_create", "ref_pres_4_create"):
+            self._f(n).restype = C.c_void_p
+        self.fft = C.c_void_p(self._f("ref_fft_create")())
+        if order == 2:
+            rr, rh = arr(rhoref), arr(rhorefh)
+            self.h = C.c_void_p(self._f("ref_pres_2_create")(self.fft, self._p(rr), self._p(rh), g.kcells))     # runs Pres_2::init -> FFT::init
+        else:
+            self.h = C.c_void_p(self._f("ref_pres_4_create")(self.fft, g.kcells))
+        self._f("ref_fft_load")(self.fft)                                                                      # FFT::load: plan creation
+        self.bmati = np.zeros(g.itot, TF); self.bmatj = np.zeros(g.jtot, TF)
+        if order == 2:
+            self.a = np.zeros(g.kmax, TF); self.c = np.zeros(g.kmax, TF)
+            self._f("ref_pres_2_set_values")(self.h, self._p(self.bmati), self._p(self.bmatj), self._p(self.a), self._p(self.c))
+        else:
+            self.m = np.zeros((7, g.kmax), TF)
+            self._f("ref_pres_4_set_values")(self.h, self._p(self.bmati), self._p(self.bmatj), self._p(self.m))
+
+    def _set_grid(self):
+        """(re)build the reference's own Grid<TF> for this case: Grid::init + Grid::calculate (oracle/ref/ref_grid.cpp); the
+        Pres / FFT member functions then read the REFERENCE's metrics, not the oracle's"""
+        g = self.g; ct = self.ct
+        self._f("ref_grid_setup")(g.itot, g.jtot, g.ktot, ct(float(g.xsize)), ct(float(g.ysize)), ct(float(g.zsize)),
+                                  g.igc, g.jgc, g.kgc, int(getattr(g, "order", 2)), self._p(self._z))
+
+    def grid_metrics(self):
+        """z, zh, dz, dzh, dzi, dzhi, dzi4, dzhi4 (kcells each) and (dx, dy, dxi, dyi, dzhi4bot, dzhi4top) of the reference's Grid"""
+        self._set_grid()
+        g = self.g
+        out = np.zeros((8, g.kcells), g.TF); scal = np.zeros(6, g.TF)
+        self._f("ref_grid_get")(self._p(out), self._p(scal))
+        return dict(zip(("z", "zh", "dz", "dzh", "dzi", "dzhi", "dzi4", "dzhi4"), out)), scal
+
+    def _f(self, name):
+        return getattr(self.lib, f"{name}_{self.sfx}")
+
+    @staticmethod
+    def _p(a):
+        if a is None:
+            return None
+        assert a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data_as(C.c_void_p)
+
+    def fft_forward(self, data):
+        """FFT<TF>::exec_forward on a compact (kmax, jmax, imax) array, in place"""
+        self._set_grid()
+        tmp = np.zeros_like(data)
+        self._f("ref_fft_forward")(self.fft, self._p(data), self._p(tmp))
+
+    def fft_backward(self, data):
+        """FFT<TF>::exec_backward: the result lands in the work array (src/fft.cxx:446-448); copied back here"""
+        self._set_grid()
+        tmp = np.zeros_like(data)
+        self._f("ref_fft_backward")(self.fft, self._p(data), self._p(tmp))
+        data[...] = tmp
+
+    def input(self, p, u, v, w, ut, vt, wt, dt):
+        self._set_grid()
+        self._f(f"ref_pres_{self.order}_input")(self.h, self._p(p), self._p(u), self._p(v), self._p(w), self._p(ut), self._p(vt), self._p(wt), self.ct(dt))
+
+    def solve(self, p):
+        self._set_grid()
+        tmp1 = np.zeros_like(p)
+        if self.order == 2:
+            tmp2 = np.zeros_like(p)
+            self._f("ref_pres_2_solve")(self.h, self._p(p), self._p(tmp1), self._p(tmp2))
+        else:
+            self._f("ref_pres_4_solve")(self.h, self._p(p), self._p(tmp1))
+
+    def output(self, ut, vt, wt, p):
+        self._set_grid()
+        self._f(f"ref_pres_{self.order}_output")(self.h, self._p(ut), self._p(vt), self._p(wt), self._p(p))
+
+    def exec(self, p, u, v, w, ut, vt, wt, dt, tdma=None):
+        """Pres_2::exec (src/pres_2.cxx:66-94) / Pres_4::exec (src/pres_4.cxx:77-144) without the statistics calls
+        (`tdma` is accepted for call compatibility with oracle.Pres2.exec and ignored: the reference's own solver runs)"""
+        p0 = p.copy()
+        self.input(p, u, v, w, ut, vt, wt, dt)
+        self.solve(p)
+        self.output(ut, vt, wt, p)
+        # The reference builds the compact rhs in place at the head of the p array; ghost locations that solve() does not
+        # define afterwards (never read by anything) keep that scratch.  They are put back to their old contents here so
+        # that whole-array comparisons against the oracle (which leaves them untouched) stay meaningful.
+        defined = self.defined_mask()
+        p[~defined] = p0[~defined]
+
+    def defined_mask(self):
+        """Where solve() leaves a defined pressure: the interior, the ghost levels it sets (one below for Pres_2, two below
+        and above for Pres_4) over the interior columns, and what the cyclic fill derives from those."""
+        g = self.g
+        ks, ke = g.kstart, g.kend
+        ng = 2 if self.order == 4 else 1
+        nt = 2 if self.order == 4 else 0
+        defined = np.zeros((g.kcells, g.jcells, g.icells), bool)
+        if g.jtot > 1:                                # boundary_cyclic fills every level (src/boundary_cyclic.cxx:369-443) ...
+            defined[ks-ng:ke+nt] = True
+        else:                                         # ... but the y ghost rows only on the interior levels of a 2-D (jtot = 1) run
+            defined[ks:ke] = True
+            defined[ks-ng:ks, g.jstart:g.jend, :] = True
+            defined[ke:ke+nt, g.jstart:g.jend, :] = True
+        return defined
+
+    def divergence(self, u, v, w):
+        assert self.order == 4
+        self._set_grid()
+        f = self._f("ref_pres_4_divergence"); f.restype = C.c_double
+        return f(self.h, self._p(u), self._p(v), self._p(w))

@@ -154,8 +154,9 @@ def dycore_substep_o4(g, K, c, prm, substep, dt, pres=None):
     return pres
 
 
-def dycore_step(g, K, c, prm, dt, timers=None, surface_model=None, forcing=None):
-    pres = None
+def dycore_step(g, K, c, prm, dt, timers=None, surface_model=None, forcing=None, pres=None):
+    """One RK3 step.  `pres`: the pressure solver object (default: the numpy Pres2 / Pres4 restatement; the tier-2 pin passes
+    refbind.RefPres, the reference's own compiled Pres_2 / Pres_4 member functions)."""
     for ss in range(3):
         if prm.get("swadvec") in ("4", "4m"):
             pres = dycore_substep_o4(g, K, c, prm, ss, dt, pres)

@@ -97,7 +97,7 @@ def main4():
         for n in ("ut", "vt", "wt", "tht"):
             out["advdiff4_" + n] = ck[n].copy()
         cs = copy.deepcopy(case)
-        ostep.dycore_step(g, refbind.RefKernels(g), cs, params4(mbc), DT4)
+        ostep.dycore_step(g, refbind.RefKernels(g), cs, params4(mbc), DT4, pres=refbind.RefPres(g, 4))     # the reference's own Pres_4
         for n in ("u", "v", "w", "th", "p"):
             out["step_" + n] = cs[n].copy()
         np.savez_compressed(os.path.join(HERE, "golden", name + ".npz"), input_sha256=np.array(digest), shape=np.array(shape),
@@ -152,14 +152,14 @@ def main():
         # full RK3 step with the plain 2nd-order schemes (swadvec=2, swdiff=2)
         c4 = copy.deepcopy(case)
         prm2 = ostep.default_params(); prm2.update(swadvec="2", swdiff="2", visc=VISC2, svisc=SVISC2)
-        ostep.dycore_step(g, refbind.RefKernels(g), c4, prm2, DT)
+        ostep.dycore_step(g, refbind.RefKernels(g), c4, prm2, DT, pres=refbind.RefPres(g, 2, c4["rhoref"], c4["rhorefh"]))
         for n in ("u", "v", "w", "th"):
             out["step22_" + n] = c4[n].copy()
         # full RK3 step(s) in Model::exec order
         cs = copy.deepcopy(case)
         prm = ostep.default_params()
         for _ in range(nsteps):
-            ostep.dycore_step(g, refbind.RefKernels(g), cs, prm, DT)
+            ostep.dycore_step(g, refbind.RefKernels(g), cs, prm, DT, pres=refbind.RefPres(g, 2, cs["rhoref"], cs["rhorefh"]))     # the reference's own Pres_2
         for n in ("u", "v", "w", "th", "p"):
             out["step_" + n] = cs[n].copy()
         np.savez_compressed(os.path.join(HERE, "golden", name + ".npz"), input_sha256=np.array(digest),

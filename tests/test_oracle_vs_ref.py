@@ -202,7 +202,7 @@ def test_full_rk3_step_neutral_bitexact(dtype, surface):
     N, R = both(g)
     prm = ostep.default_params(); prm.update(swthermo=None, surface_model=surface, visc=1e-2)
     ostep.dycore_step(g, N, c0, prm, 2.0)
-    ostep.dycore_step(g, R, c1, prm, 2.0)
+    ostep.dycore_step(g, R, c1, prm, 2.0, pres=refbind.RefPres(g, 2, c1["rhoref"], c1["rhorefh"]))    # the reference's own Pres_2
     for n in ("u", "v", "w", "th", "evisc"):
         assert np.array_equal(c0[n], c1[n]), n
 
@@ -215,7 +215,7 @@ def test_full_rk3_step_fluxlimit_bitexact(dtype):
     N, R = both(g)
     prm = ostep.default_params(); prm.update(fluxlimit_list=("s1",))
     ostep.dycore_step(g, N, c0, prm, 2.0)
-    ostep.dycore_step(g, R, c1, prm, 2.0)
+    ostep.dycore_step(g, R, c1, prm, 2.0, pres=refbind.RefPres(g, 2, c1["rhoref"], c1["rhorefh"]))    # the reference's own Pres_2
     for n in ("u", "v", "w", "th", "s1"):
         assert np.array_equal(c0[n], c1[n]), n
     c2 = copy.deepcopy(case)
@@ -225,9 +225,10 @@ def test_full_rk3_step_fluxlimit_bitexact(dtype):
 
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("shape", [(16, 12, 10), (24, 1, 8)])
-def test_full_rk3_step_order4_bitexact(dtype, shape):
-    """4th-order DNS step (advec_4 + diff_4 + pres_4 + 4th-order ghost cells) in Model::exec order: numpy kernels ==
-    compiled reference kernels (the Pres_4 member-function glue is the oracle's restatement in both)."""
+@pytest.mark.parametrize("swadvec", ["4", "4m"])
+def test_full_rk3_step_order4_bitexact(dtype, shape, swadvec):
+    """4th-order DNS step (advec_4 or advec_4m + diff_4 + pres_4 + 4th-order ghost cells) in Model::exec order: the numpy
+    oracle == the compiled reference (its kernels AND its own Pres_4 / FFT / Grid member functions)."""
     from util import stretched_z
     from microhh_b200.grid import GridData
     from microhh_b200.synthetic import make_case
@@ -243,11 +244,11 @@ def test_full_rk3_step_order4_bitexact(dtype, shape):
         for sfx in ("_bot", "_top", "_gradbot", "_gradtop"):
             case[n + sfx] = np.zeros(gd.shape2d, dtype)
     case["th_gradbot"] = np.zeros(gd.shape2d, dtype); case["th_gradtop"] = np.zeros(gd.shape2d, dtype)
-    prm = ostep.default_params(); prm.update(swadvec="4", swdiff="4", visc=1e-3, svisc=1e-3, mbcbot=0, mbctop=0)
+    prm = ostep.default_params(); prm.update(swadvec=swadvec, swdiff="4", visc=1e-3, svisc=1e-3, mbcbot=0, mbctop=0)
     c0, c1 = copy.deepcopy(case), copy.deepcopy(case)
     N, R = both(g)
     ostep.dycore_step(g, N, c0, prm, 0.01)
-    ostep.dycore_step(g, R, c1, prm, 0.01)
+    ostep.dycore_step(g, R, c1, prm, 0.01, pres=refbind.RefPres(g, 4))                                  # the reference's own Pres_4
     for n in ("u", "v", "w", "th", "p"):
         assert np.array_equal(interior(g, c0[n]), interior(g, c1[n])), n
     assert np.isfinite(interior(g, c0["u"])).all() and not np.array_equal(c0["u"], case["u"])
@@ -284,7 +285,7 @@ def test_full_rk3_step_scheme_combinations_bitexact(dtype, swadvec, swdiff):
     N, R = both(g)
     prm = ostep.default_params(); prm.update(swadvec=swadvec, swdiff=swdiff, visc=0.5, svisc=0.7)
     ostep.dycore_step(g, N, c0, prm, 2.0)
-    ostep.dycore_step(g, R, c1, prm, 2.0)
+    ostep.dycore_step(g, R, c1, prm, 2.0, pres=refbind.RefPres(g, 2, c1["rhoref"], c1["rhorefh"]))    # the reference's own Pres_2
     for n in ("u", "v", "w", "th", "p"):
         assert np.array_equal(c0[n], c1[n]), n
     assert np.isfinite(interior(g, c0["u"])).all()
@@ -299,7 +300,7 @@ def test_full_rk3_step_bitexact(dtype, shape, anel, stretched):
     N, R = both(g)
     prm = ostep.default_params()
     ostep.dycore_step(g, N, c0, prm, 2.0)
-    ostep.dycore_step(g, R, c1, prm, 2.0)
+    ostep.dycore_step(g, R, c1, prm, 2.0, pres=refbind.RefPres(g, 2, c1["rhoref"], c1["rhorefh"]))    # the reference's own Pres_2
     for n in ("u", "v", "w", "th", "p", "evisc"):
         assert np.array_equal(c0[n], c1[n]), n
     # the step does something and stays finite
@@ -375,3 +376,109 @@ def test_buffer_and_force_pinned(dtype):
     O.force_ls_source(g, st, sls); O.force_wls_local(g, st, case["th"], wls)
     R.ls_source(st2, sls); R.wls_local(st2, case["th"], wls)
     assert np.array_equal(st, st2)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Tier-2 pin of the pressure glue: the reference's own FFT<TF>, Pres_2<TF>, Pres_4<TF> member functions (compiled where
+# they lie, run on stand-in objects -- oracle/ref/ref_fake_pres.h) against the numpy restatement.  FFTW is absent from the
+# image, so the plans the reference creates forward the batched 1-D R2HC / HC2R to the oracle's transform; everything
+# around it -- slice loops and strides (src/fft.cxx:338-452), rhs, modified wave numbers, matrix build, tdma / hdma, ghost
+# cells, pressure gradient -- is the reference's compiled code, and must agree bit for bit.
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(16, 12, 8), (20, 9, 6), (24, 1, 8)])
+def test_fft_glue_bitexact(dtype, shape):
+    """FFT<TF>::init / load / exec_forward / exec_backward (src/fft.cxx): x then y transforms slice by slice."""
+    g, gd, case = make_pair(*shape, dtype)
+    R = refbind.RefPres(g, 2, case["rhoref"], case["rhorefh"])
+    x = np.random.default_rng(0).standard_normal((g.kmax, g.jtot, g.itot)).astype(dtype)
+    y = x.copy()
+    R.fft_forward(x)
+    y = O.r2hc(O.r2hc(y, 2), 1)
+    assert np.array_equal(x, y)
+    R.fft_backward(x)                     # normalises by jtot, itot (src/fft.cxx:424-449)
+    y = O.hc2r(y, 1)/dtype(g.jtot)
+    y = O.hc2r(y, 2)/dtype(g.itot)
+    assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(16, 12, 8), (20, 9, 6), (24, 1, 8)])
+@pytest.mark.parametrize("anelastic", [False, True])
+def test_pres_2_glue_bitexact(dtype, shape, anelastic):
+    """Pres_2::set_values / input / solve / output (src/pres_2.cxx:124-387) in the order of Pres_2::exec (:66-94)."""
+    g, gd, case = make_pair(*shape, dtype, stretched=True, anelastic=anelastic)
+    R = refbind.RefPres(g, 2, case["rhoref"], case["rhorefh"])
+    P = O.Pres2(g, case["rhoref"], case["rhorefh"])
+    for n in ("bmati", "bmatj", "a", "c"):
+        assert np.array_equal(getattr(R, n), getattr(P, n)), n
+    rng = np.random.default_rng(1)
+    c0 = copy.deepcopy(case)
+    for n in ("ut", "vt", "wt"):
+        c0[n] = rng.standard_normal(gd.shape).astype(dtype)
+    c1 = copy.deepcopy(c0)
+    P.exec(c0["p"], c0["u"], c0["v"], c0["w"], c0["ut"], c0["vt"], c0["wt"], 0.7)
+    R.exec(c1["p"], c1["u"], c1["v"], c1["w"], c1["ut"], c1["vt"], c1["wt"], 0.7)
+    for n in ("ut", "vt", "wt"):
+        assert np.array_equal(c0[n], c1[n]), (n, float(np.abs(c0[n].astype(np.float64) - c1[n]).max()))
+    # p where solve() defines it: interior, the bottom ghost level and their cyclic ghost cells (elsewhere the reference's
+    # array keeps scratch of the in-place compact rhs; nothing reads it)
+    mask = R.defined_mask()
+    assert np.array_equal(c0["p"][mask], c1["p"][mask])
+    assert not np.array_equal(c0["ut"], case["ut"])
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(16, 12, 10), (20, 9, 6), (24, 1, 8)])
+@pytest.mark.parametrize("stretched", [False, True])
+def test_pres_4_glue_bitexact(dtype, shape, stretched):
+    """Pres_4::set_values / input<dim3> / solve (+ hdma) / output<dim3> / calc_divergence (src/pres_4.cxx:179-767) in the
+    order and with the work-array carving of Pres_4::exec (:77-144), 3-D and 2-D (jtot = 1)."""
+    from util import stretched_z
+    it, jt, kt = shape
+    g = O.Grid(it, jt, kt, 6.28, 3.14, 2., 3, 3, 3, dtype, z=stretched_z(kt, 2.) if stretched else None, order=4)
+    R = refbind.RefPres(g, 4)
+    P = O.Pres4(g)
+    for n in ("bmati", "bmatj", "m"):
+        assert np.array_equal(getattr(R, n), getattr(P, n)), n
+    rng = np.random.default_rng(2)
+    f = lambda: rng.standard_normal((g.kcells, g.jcells, g.icells)).astype(dtype)
+    c0 = dict(p=f(), u=f(), v=f(), w=f(), ut=f(), vt=f(), wt=f())
+    c1 = copy.deepcopy(c0)
+    t0 = c0["ut"].copy()
+    P.exec(c0["p"], c0["u"], c0["v"], c0["w"], c0["ut"], c0["vt"], c0["wt"], 0.7)
+    R.exec(c1["p"], c1["u"], c1["v"], c1["w"], c1["ut"], c1["vt"], c1["wt"], 0.7)
+    for n in ("ut", "vt", "wt"):
+        assert np.array_equal(c0[n], c1[n]), (n, float(np.abs(c0[n].astype(np.float64) - c1[n]).max()))
+    # p where solve() defines it: two ghost levels either side (read by output) and their cyclic ghost cells
+    mask = R.defined_mask()
+    assert np.array_equal(c0["p"][mask], c1["p"][mask])
+    assert not np.array_equal(c0["ut"], t0)
+    assert float(P.divergence(c0["u"], c0["v"], c0["w"])) == R.divergence(c1["u"], c1["v"], c1["w"])
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("order", [2, 4])
+@pytest.mark.parametrize("stretched", [False, True])
+def test_grid_metrics_bitexact(dtype, order, stretched):
+    """Grid<TF>::init + calculate (src/grid.cxx:106-376) compiled from the reference: ghost levels of z / zh, dz, dzh and their
+    reciprocals, and the 4th-order metrics dzi4 / dzhi4 == the oracle's Grid AND the product's GridData, bit for bit."""
+    from util import stretched_z
+    from microhh_b200.grid import GridData
+    it, jt, kt = 16, 12, 10
+    gc = (3, 3, 3) if order == 4 else (3, 3, 1)
+    z = stretched_z(kt, 2.) if stretched else None
+    g = O.Grid(it, jt, kt, 6.28, 3.14, 2., *gc, dtype, z=z, order=order)
+    gd = GridData(it, jt, kt, 6.28, 3.14, 2., *gc, dtype, z=z, order=order)
+    if order == 4:
+        R = refbind.RefPres(g, 4)
+    else:
+        ones = np.ones(g.kcells, dtype)
+        R = refbind.RefPres(g, 2, ones, ones)
+    m, scal = R.grid_metrics()
+    names = ("z", "zh", "dz", "dzh", "dzi", "dzhi") + (("dzi4", "dzhi4") if order == 4 else ())
+    for n in names:
+        assert np.array_equal(np.asarray(getattr(g, n))[:g.kcells], m[n]), ("oracle", n)
+        if hasattr(gd, n):
+            assert np.array_equal(np.asarray(getattr(gd, n))[:g.kcells], m[n]), ("product", n)
+    assert scal[0] == g.dx == gd.dx and scal[1] == g.dy == gd.dy
