@@ -19,6 +19,7 @@
 #include "tile_kernels.cuh"
 #include "tile2_kernels.cuh"
 #include "tile3_kernels.cuh"
+#include "evisc3_kernels.cuh"
 #include "slab_kernels.cuh"
 #include "surface_kernels.cuh"
 #include "forcing_kernels.cuh"
@@ -48,6 +49,9 @@ struct mhh_ctx
     bool no_tma = false;        // MHH_NO_TMA=1: keep the cp.async tile kernels (A/B comparisons)
     int tile3_y = 0;            // MHH_TILE3_Y: rows per CTA of the warp-specialised kernel; 0 = 3 rows with the scalar group (13 warps), 4 without
     bool fuse_scalar = true;    // MHH_FUSE_SCALAR=0: keep scalar 0 out of the momentum kernel (A/B comparisons)
+    bool evisc_tma = true;      // MHH_EVISC_TMA=0: keep the cp.async eddy-viscosity kernel (A/B switch)
+    int evisc3_npl = 0;         // MHH_EVISC3_NPL=1|2: points per lane of the TMA eddy-viscosity kernel (tile 32 or 64 wide; 0: 1 for fp64, 2 for fp32)
+    int evisc3_mb = 0;          // MHH_EVISC3_MB=2|3|4: resident CTAs per SM the TMA eddy-viscosity kernel is compiled for (0: 3)
     int evisc_mb = 4;           // MHH_EVISC_MB=2|3|4 (measured 512^3 fp64: 2.72 | 2.51 | 2.11 ms): resident CTAs per SM the eddy-viscosity kernel is compiled for (register cap)
     int prefetch = 1;           // MHH_PREFETCH: L2 prefetch distance (levels) of the TMA tile kernels, 0 = off
     bool prof = false;

@@ -76,6 +76,9 @@ int create_impl(const mhh_grid_desc* d, int dtype, int device, mhh_ctx** out)
     { const char* e = getenv("MHH_FUSE_SCALAR"); if (e) c->fuse_scalar = e[0] == '1'; }
     { const char* e = getenv("MHH_TILE3_Y"); if (e) { int v = atoi(e); if (v == 3 || v == 4 || v == 5) c->tile3_y = v; } }
     { const char* e = getenv("MHH_EVISC_MB"); if (e) c->evisc_mb = atoi(e); }
+    { const char* e = getenv("MHH_EVISC_TMA"); if (e) c->evisc_tma = atoi(e) != 0; }
+    { const char* e = getenv("MHH_EVISC3_MB"); if (e) c->evisc3_mb = atoi(e); }
+    { const char* e = getenv("MHH_EVISC3_NPL"); if (e) c->evisc3_npl = atoi(e); }
     { const char* e = getenv("MHH_PREFETCH"); if (e) c->prefetch = std::max(0, std::min(8, atoi(e))); }
     { const char* e = getenv("MHH_TILE_Y"); if (e && atoi(e) == 16) c->tile_y = 16; else if (e && atoi(e) == 8) c->tile_y = 8; }
     CUDA_TRY(c, cudaSetDevice(device));

@@ -24,6 +24,11 @@ inline int pick_kchunk(int ntiles_xy, int kmax, int num_sms)
     return (kmax + nz - 1) / nz;
 }
 
+// (defined with the other TMA helpers below)
+template <typename TF> bool make_field_tmap(CUtensorMap* m, const void* fld, const GridDev<TF>& g, int bx, int by);
+template <typename TF> bool tma_ok(const GridDev<TF>& g, std::initializer_list<const void*> ptrs);
+inline int pick_kchunk_waves(int ntiles_xy, int kmax, int slots, int warm);
+
 template <typename TF>
 int evisc_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, const TF* n2)
 {
@@ -53,6 +58,47 @@ int evisc_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, const TF*
     {
         evisc_neutral_kernel<TF><<<c->grd_interior(), c->blk(), 0, c->stream>>>(a, g, c->d_mlen0, (TF)f->visc);
         KCHECKN(c, "evisc_neutral_kernel");
+    }
+    else if (!c->force_plain && c->evisc_tma && e3_pick_hl(g.istart, (int)sizeof(TF)) > 0 && g.igc >= e3_pick_hl(g.istart, (int)sizeof(TF))
+             && tma_ok<TF>(g, {a.u, a.v, a.w, a.n2mode == 1 ? (const void*)a.th : (const void*)a.u}))
+    {
+        // TMA-staged, warp-specialised kernel (evisc3_kernels.cuh): (32 | 64) x 8 tiles, eight consumer warps + one producer warp
+        constexpr int TY = 8;
+        const int hl = e3_pick_hl(g.istart, (int)sizeof(TF));
+        // points per lane (tile 32 or 64 wide) and resident CTAs per SM the kernel is compiled for (register cap); measured at
+        // 512^3 in ms/step (cp.async kernel: fp64 6.09, fp32 3.96):
+        //   fp64  NPL=1: MB 2 | 3 | 4 = 4.82 | 4.59 | 5.73      NPL=2: MB 2 = 5.33 (3, 4 spill)
+        //   fp32  NPL=2: MB 3 | 4 = 2.86 | 3.00                  NPL=1: MB 4 = 3.04
+        // (deeper rings -- 6 or 8 planes per field -- and 128-wide tiles with four points per lane were slower: the kernel is
+        // bound by the latency of its dependent fp64 chains, so resident warps count, not bytes in flight)
+        const int npl = (c->evisc3_npl == 1 || c->evisc3_npl == 2) ? c->evisc3_npl : (sizeof(TF) == 8 ? 1 : 2);
+        const int mb = (c->evisc3_mb >= 2 && c->evisc3_mb <= 4) ? c->evisc3_mb : 3;
+        const int ring = 4;
+        const int ew = e3_w(npl);
+        const int ntx = (g.imax + ew - 1) / ew, nty = (g.jmax + TY - 1) / TY;
+        EviscTileArgs<TF> t{a, c->d_mlen0, pick_kchunk_waves(ntx * nty, g.kmax, c->num_sms * mb, 1)};
+        dim3 grid(ntx, nty, (g.kmax + t.kchunk - 1) / t.kchunk);
+        const size_t smem = evisc3_smem(sizeof(TF), t.kchunk, TY, hl, npl, ring);
+        CUtensorMap tu, tv, tw, tth;
+        if (!make_field_tmap<TF>(&tu, a.u, g, e3_px(hl, npl), TY + 2) || !make_field_tmap<TF>(&tv, a.v, g, e3_px(hl, npl), TY + 2) ||
+            !make_field_tmap<TF>(&tw, a.w, g, e3_px(hl, npl), TY + 2) ||
+            !make_field_tmap<TF>(&tth, a.n2mode == 1 ? (const void*)a.th : (const void*)a.u, g, e3_px(hl, npl), TY + 2))
+        { c->err = "cuTensorMapEncodeTiled failed"; return MHH_E_CUDA; }
+#define E3(S, H, MB, N, R) do { \
+            static size_t attr_smem_dev[64] = {0}; size_t& attr_smem = attr_smem_dev[c->device & 63];   /* the attribute is per device */ \
+            if (attr_smem < smem) { CUDA_TRY(c, cudaFuncSetAttribute(evisc3_kernel<TF, S, TY, H, MB, N, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; } \
+            evisc3_kernel<TF, S, TY, H, MB, N, R><<<grid, 32 * (TY + 1), smem, c->stream>>>(tu, tv, tw, tth, t, g); } while (0)
+#define E3R(S, H, MB, N) E3(S, H, MB, N, 4)       /* deeper rings (6, 8 planes per field) measured slower: 5.96 - 6.94 vs 5.66 ms/step */
+#define E3N(S, H, MB) do { if (npl == 1) E3R(S, H, MB, 1); else E3R(S, H, MB, 2); } while (0)
+#define E3M(S, H) do { if (mb == 2) E3N(S, H, 2); else if (mb == 4) E3N(S, H, 4); else E3N(S, H, 3); } while (0)
+#define E3H(S) do { if (hl == 1) E3M(S, 1); else if (hl == 2) E3M(S, 2); else E3M(S, 4); } while (0)
+        if (a.surface) E3H(true); else E3H(false);
+#undef E3H
+#undef E3M
+#undef E3N
+#undef E3R
+#undef E3
+        KCHECKN(c, "evisc3_kernel");
     }
     else if (!c->force_plain)
     {

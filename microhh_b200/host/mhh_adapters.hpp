@@ -383,4 +383,52 @@ namespace mhhb200
         const mhh_fields f = fields_view(fields, &boundary);
         MHH_CHECK(c.ctx, mhh_dycore_substep(c.ctx, &f, &prm, substep, dt));
     }
+
+    // ---- "next" rows of the scope table: the bodies of three member functions whose classes are not polymorphic per scheme
+    // (Boundary_surface / Buffer / Force keep their device arrays private), so the binding is a one-line body, not a subclass:
+    //
+    //   Boundary_surface<TF>::exec (src/boundary_surface.cu, CPU: src/boundary_surface.cxx:836-990), constant z0:
+    //       mhhb200::surface_exec_b200(*b200, fields, *this, prm,
+    //                                  {ustar_g, obuk_g, nobuk_g, z0m_g, z0h_g, dutot_tmp, {sbc codes}});
+    //   Buffer<TF>::exec (src/buffer.cu, CPU: src/buffer.cxx:170-205)  and  Force<TF>::exec (src/force.cu, CPU: src/force.cxx:608-700):
+    //       mhhb200::buffer_exec_b200(*b200, fields, forcing);   mhhb200::force_exec_b200(*b200, fields, forcing, sub_dt);
+    //   with `forcing` filled once from the classes' own members (bufferprofs_g, ug_g, vg_g, lsprofs_g, wls_g, the [buffer] /
+    //   [force] ini values) -- or registered with mhh_dycore_set_forcing so that the fused sub-step runs both in place.
+    // mhh_boundary_surface_init (lookup table of the Obukhov solver, include/boundary_surface_kernels.h:78-138) is called once
+    // from Boundary_surface<TF>::init_solver.
+    template<typename TF>
+    void surface_exec_b200(Context<TF>& c, Fields<TF>& fields, Boundary<TF>& boundary, const mhh_params& prm, const mhh_surface& s)
+    {
+        const mhh_fields f = fields_view(fields, &boundary);
+        MHH_CHECK(c.ctx, mhh_boundary_surface_exec(c.ctx, &f, &prm, &s));
+    }
+    template<typename TF>
+    void buffer_exec_b200(Context<TF>& c, Fields<TF>& fields, const mhh_forcing& forcing)
+    {
+        const mhh_fields f = fields_view(fields);
+        MHH_CHECK(c.ctx, mhh_buffer_exec(c.ctx, &f, &forcing));
+    }
+    template<typename TF>
+    void force_exec_b200(Context<TF>& c, Fields<TF>& fields, const mhh_forcing& forcing, const double sub_dt)
+    {
+        const mhh_fields f = fields_view(fields);
+        MHH_CHECK(c.ctx, mhh_force_exec(c.ctx, &f, &forcing, sub_dt));
+    }
+
+    // ---- staged sub-step: the fused path with MicroHH's own stages kept in between (surface model, statistics, ...), in the
+    // order of Model::exec (src/model.cxx:368-504): pre = cyclic + ghost cells + diff.exec_viscosity; [MicroHH's surface model];
+    // set_ghost_cells again (:401); post = thermo + advec + diff fused, (buffer, force if registered), pres, rk3.
+    template<typename TF>
+    void dycore_substep_pre_b200(Context<TF>& c, Fields<TF>& fields, Boundary<TF>& boundary, const mhh_params& prm)
+    { const mhh_fields f = fields_view(fields, &boundary); MHH_CHECK(c.ctx, mhh_dycore_substep_pre(c.ctx, &f, &prm)); }
+    template<typename TF>
+    void dycore_set_ghost_cells_b200(Context<TF>& c, Fields<TF>& fields, Boundary<TF>& boundary, const mhh_params& prm)
+    { const mhh_fields f = fields_view(fields, &boundary); MHH_CHECK(c.ctx, mhh_dycore_set_ghost_cells(c.ctx, &f, &prm)); }
+    template<typename TF>
+    void dycore_tendencies_b200(Context<TF>& c, Fields<TF>& fields, Boundary<TF>& boundary, const mhh_params& prm)
+    { const mhh_fields f = fields_view(fields, &boundary); MHH_CHECK(c.ctx, mhh_dycore_tendencies(c.ctx, &f, &prm)); }
+    template<typename TF>
+    void dycore_substep_post_b200(Context<TF>& c, Fields<TF>& fields, Boundary<TF>& boundary, const mhh_params& prm,
+                                  const int substep, const double dt)
+    { const mhh_fields f = fields_view(fields, &boundary); MHH_CHECK(c.ctx, mhh_dycore_substep_post(c.ctx, &f, &prm, substep, dt)); }
 }

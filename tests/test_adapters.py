@@ -26,6 +26,14 @@ template class mhhb200::Pres_b200<double, 4>;
 template struct mhhb200::Boundary_cyclic_b200<double>;
 template void mhhb200::timeloop_exec_b200<double>(mhhb200::Context<double>&, Fields<double>&, int, double);
 template void mhhb200::dycore_substep_b200<float>(mhhb200::Context<float>&, Fields<float>&, Boundary<float>&, const mhh_params&, int, double);
+template class mhhb200::Advec_b200<double, 41, Advection_type::Advec_4m>;
+template void mhhb200::surface_exec_b200<double>(mhhb200::Context<double>&, Fields<double>&, Boundary<double>&, const mhh_params&, const mhh_surface&);
+template void mhhb200::buffer_exec_b200<float>(mhhb200::Context<float>&, Fields<float>&, const mhh_forcing&);
+template void mhhb200::force_exec_b200<double>(mhhb200::Context<double>&, Fields<double>&, const mhh_forcing&, double);
+template void mhhb200::dycore_substep_pre_b200<double>(mhhb200::Context<double>&, Fields<double>&, Boundary<double>&, const mhh_params&);
+template void mhhb200::dycore_set_ghost_cells_b200<double>(mhhb200::Context<double>&, Fields<double>&, Boundary<double>&, const mhh_params&);
+template void mhhb200::dycore_tendencies_b200<float>(mhhb200::Context<float>&, Fields<float>&, Boundary<float>&, const mhh_params&);
+template void mhhb200::dycore_substep_post_b200<double>(mhhb200::Context<double>&, Fields<double>&, Boundary<double>&, const mhh_params&, int, double);
 '''
 
 

@@ -130,7 +130,7 @@ def test_multi_tile_step(dtype, igc, shape, ns):
         check_step(g, f, case, names, TOL[dtype])
 
 
-@pytest.mark.parametrize("dtype,igc", [(np.float64, 3), (np.float64, 4), (np.float32, 3), (np.float32, 4)])
+@pytest.mark.parametrize("dtype,igc", [(np.float64, 3), (np.float64, 4), (np.float32, 3), (np.float32, 4), (np.float32, 6)])
 @pytest.mark.parametrize("itot", [128, 160, 192])
 @pytest.mark.parametrize("surface", [True, False])
 def test_fused_tendencies_multi_tile(dtype, igc, itot, surface):

@@ -1,47 +1,76 @@
 #!/usr/bin/env python
-"""Summarise an `ncu --set full` report (exported with `ncu -i X.ncu-rep --page raw --csv`) as a
-markdown table: one row per captured launch with duration, DRAM traffic, achieved GB/s and the
-limiter-relevant percentages.  Usage: tools/ncu_summary.py raw.csv [bytes_per_pass] > profiles/X.md"""
+"""Condenses `ncu -i X.ncu-rep --page raw --csv` (and, optionally, `--page source --csv`) of ONE kernel launch into the
+handful of numbers DESIGN.md / bench.py quote: duration, DRAM traffic, registers, occupancy, pipe utilisation, shared-memory
+wavefronts and bank conflicts, opcode mix.   usage: ncu_summary.py raw.csv [source.csv] > profiles/rNN/ncu_<kernel>.txt"""
+import collections
 import csv
 import sys
 
-COLS = [("gpu__time_duration.sum", "ms"), ("dram__bytes_read.sum", "GB rd"), ("dram__bytes_write.sum", "GB wr"),
-        ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram %"),
-        ("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "fp64 pipe %"),
-        ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue %"),
-        ("sm__warps_active.avg.pct_of_peak_sustained_active", "occupancy %"),
-        ("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex %"),
-        ("launch__registers_per_thread", "regs"), ("smsp__inst_executed.sum", "warp-inst")]
-
-
-def conv(v, unit, want):
-    v = float(v.replace(",", ""))
-    scale = {"ns": 1e-6, "us": 1e-3, "ms": 1., "s": 1e3}
-    if want == "ms":
-        return v*scale.get(unit, 1.)
-    if want.startswith("GB"):
-        return v*{"byte": 1e-9, "Kbyte": 1e-6, "Mbyte": 1e-3, "Gbyte": 1.}.get(unit, 1e-9)
-    return v
+WANT = [
+    ("gpu__time_duration.sum", "duration"),
+    ("dram__bytes_read.sum", "DRAM read"),
+    ("dram__bytes_write.sum", "DRAM write"),
+    ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM throughput"),
+    ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 throughput"),
+    ("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "L1/TEX throughput"),
+    ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "LSU data-pipe wavefronts"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "shared-memory wavefronts"),
+    ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "shared-memory bank conflicts"),
+    ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput"),
+    ("sm__inst_issued.avg.pct_of_peak_sustained_active", "issue slots busy"),
+    ("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "fp64 pipe"),
+    ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "fma pipe"),
+    ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "alu pipe"),
+    ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved occupancy"),
+    ("launch__registers_per_thread", "registers / thread"),
+    ("launch__shared_mem_per_block", "shared memory / block"),
+    ("launch__grid_size", "grid size"),
+    ("launch__block_size", "block size"),
+    ("launch__occupancy_limit_registers", "blocks/SM limit: registers"),
+    ("launch__occupancy_limit_shared_mem", "blocks/SM limit: shared memory"),
+    ("launch__occupancy_limit_warps", "blocks/SM limit: warps"),
+    ("smsp__inst_executed.sum", "warp instructions executed"),
+    ("smsp__inst_executed_op_local_ld.sum", "local-memory loads (spills)"),
+    ("smsp__inst_executed_op_local_st.sum", "local-memory stores (spills)"),
+]
 
 
 def main():
     rows = list(csv.reader(open(sys.argv[1])))
-    pass_bytes = float(sys.argv[2]) if len(sys.argv) > 2 else None
-    hdr, units = rows[0], rows[1]
-    idx = {h: i for i, h in enumerate(hdr)}
-    print("| kernel | " + " | ".join(c[1] for c in COLS) + " | traffic GB/s |" + (" passes |" if pass_bytes else ""))
-    print("|---|" + "---|"*(len(COLS) + 1 + (1 if pass_bytes else 0)))
-    for r in rows[2:]:
-        name = r[idx["Kernel Name"]].replace("void ", "").replace("mhh::", "").split("(")[0]
-        vals = []
-        for m, w in COLS:
-            vals.append(conv(r[idx[m]], units[idx[m]], w) if m in idx else float("nan"))
-        ms, rd, wr = vals[0], vals[1], vals[2]
-        cells = [f"{v:.3f}" if i < 3 else (f"{v:.0f}" if v >= 100 else f"{v:.1f}") for i, v in enumerate(vals)]
-        line = f"| `{name}` | " + " | ".join(cells) + f" | {(rd+wr)/(ms*1e-3):.0f} |"
-        if pass_bytes:
-            line += f" {(rd+wr)*1e9/pass_bytes:.2f} |"
-        print(line)
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    ix = {h: i for i, h in enumerate(hdr)}
+    name = vals[ix["Kernel Name"]] if "Kernel Name" in ix else "?"
+    print(f"kernel: {name}")
+    print(f"source: {sys.argv[1]}  (ncu --set full --clock-control none, one launch; cold-cache, serialised)")
+    for key, label in WANT:
+        if key in ix:
+            print(f"  {label:36s} {vals[ix[key]]:>18s} {units[ix[key]]}")
+    if len(sys.argv) > 2:
+        src = list(csv.reader(open(sys.argv[2])))
+        h = src[1]; jx = {x: i for i, x in enumerate(h)}
+        ops = collections.Counter(); tot = 0
+        sh = collections.defaultdict(lambda: [0, 0, 0])
+        stall = collections.Counter()
+        for r in src[2:]:
+            if len(r) < len(h):
+                continue
+            t = r[jx["Source"]].split()
+            if not t:
+                continue
+            op = t[1] if t[0].startswith("@") and len(t) > 1 else t[0]
+            ex = int(r[jx["Instructions Executed"]] or 0)
+            ops[op.split(".")[0]] += ex; tot += ex
+            if op.startswith("LDS") or op.startswith("STS"):
+                a = sh[op]
+                a[0] += ex; a[1] += int(r[jx["L1 Wavefronts Shared"]] or 0); a[2] += int(r[jx["L1 Wavefronts Shared Ideal"]] or 0)
+            for c in h:
+                if c.startswith("stall_"):
+                    stall[c] += int(r[jx[c]] or 0)
+        print(f"  opcode mix (warp instructions, {tot} total): " + ", ".join(f"{k} {v/tot:.1%}" for k, v in ops.most_common(12)))
+        for op, (ex, wf, ideal) in sorted(sh.items(), key=lambda kv: -kv[1][1]):
+            print(f"  {op:10s} executed {ex:>12d}  wavefronts {wf:>12d}  ideal {ideal:>12d}  ({wf/max(ideal,1):.2f}x)")
+        ts = sum(stall.values()) or 1
+        print("  stall samples: " + ", ".join(f"{k[6:]} {v/ts:.1%}" for k, v in stall.most_common(8)))
 
 
 if __name__ == "__main__":
