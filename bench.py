@@ -90,7 +90,7 @@ ALG_PASSES = {  # algorithmic array passes per launch, in units of N
     "tend_uvw_kernel": 4 + 6, "tend_s_kernel": 5 + 2, "evisc_kernel": 5,
     # z-marching tile kernels: R u,v,w,evisc,th + RMW ut,vt,wt | R s,u,v,w,evisc + RMW st | R u,v,w,th + W evisc
     # mom3 carries scalar 0 as a fourth warp group: R u,v,w,evisc,th + RMW ut,vt,wt,tht
-    "mom_tile_kernel": 5 + 6, "mom3_kernel": 5 + 8, "scal_tile_kernel": 5 + 2, "evisc_tile_kernel": 5,
+    "mom_tile_kernel": 5 + 6, "mom3_kernel": 5 + 8, "scal_tile_kernel": 5 + 2, "evisc_tile_kernel": 5, "evisc3_kernel": 5,
     "fft_x_forward_kernel": 7, "fft_y_forward_kernel": 2, "fft_y_backward_kernel": 2,
     "tdma_solve_kernel": 2, "fft_x_backward_kernel": 2, "pres_out_rk3_kernel": 13, "rk3_kernel": 4,
     # Pres_2 version 2: y transform fused with the Thomas sweeps (R + W of the spectral array each; the pivot table is overhead)
@@ -216,16 +216,19 @@ def run_ours(args):
         sampler.stop_flag.set(); sampler.join(timeout=2)
     finite = bool(torch.isfinite(f["u"]).all().item())
     # size-independent property at the full size: after the pressure correction the velocity is divergence-free to
-    # rounding (Pres_2::check_divergence on the cyclic-filled fields; relative to |u|max/dx)
+    # rounding (Pres_2::check_divergence on the cyclic-filled fields; relative to |u|max/dx).  On slabs this is collective
+    # (halo rows over NVLink, max all-reduced: the same calls tools/slab_check.py validates) and checks the distributed
+    # transposes of the solve at the benchmarked size.
     post_div = None
     try:
-        if world > 1:
-            raise RuntimeError("reported at N=1 only (kept out of the collective path)")
         bc = D.Boundary_cyclic(ctx)
         for n in ("u", "v", "w"):
             bc.exec(f[n])
         div = D.Pres(ctx).check_divergence(f)
-        umax = float(f["u"].abs().max())
+        umax_t = f["u"].abs().max().to(torch.float64).reshape(1)
+        if world > 1:
+            dist.all_reduce(umax_t, op=dist.ReduceOp.MAX)
+        umax = float(umax_t.item())
         post_div = {"max_abs_divergence": div, "relative_to_umax_over_dx": div/(umax/float(gd.dx))}
     except Exception as ex:      # a diagnostic must never cost the bench line
         post_div = {"error": str(ex)[:200]}
