@@ -33,6 +33,11 @@ struct GridDev
 
 template <typename TF> __device__ __forceinline__ TF ld(const TF* __restrict__ p) { return __ldg(p); }
 
+// two-element vector type of TF (one 2*sizeof(TF) memory access)
+template <typename TF> struct V2T;
+template <> struct V2T<double> { typedef double2 type; };
+template <> struct V2T<float>  { typedef float2 type; };
+
 // ---- Finite differences ----------------------------------------------------------------
 template <typename TF> __device__ __forceinline__ TF interp2(TF a, TF b) { return TF(0.5) * (a + b); }
 template <typename TF> __device__ __forceinline__ TF interp4_ws(TF a, TF b, TF c, TF d)

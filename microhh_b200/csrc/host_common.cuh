@@ -49,6 +49,7 @@ struct mhh_ctx
     bool no_tma = false;        // MHH_NO_TMA=1: keep the cp.async tile kernels (A/B comparisons)
     int tile3_y = 0;            // MHH_TILE3_Y: rows per CTA of the warp-specialised kernel; 0 = 3 rows with the scalar group (13 warps), 4 without
     bool fuse_scalar = true;    // MHH_FUSE_SCALAR=0: keep scalar 0 out of the momentum kernel (A/B comparisons)
+    bool stream_vec2 = true;    // MHH_STREAM_VEC2=0: one cell per thread in rk3 / pres_out_rk3 (A/B switch)
     bool evisc_tma = true;      // MHH_EVISC_TMA=0: keep the cp.async eddy-viscosity kernel (A/B switch)
     int evisc3_npl = 0;         // MHH_EVISC3_NPL=1|2: points per lane of the TMA eddy-viscosity kernel (tile 32 or 64 wide; 0: 1 for fp64, 2 for fp32)
     int evisc3_mb = 0;          // MHH_EVISC3_MB=2|3|4: resident CTAs per SM the TMA eddy-viscosity kernel is compiled for (0: 3)

@@ -77,6 +77,7 @@ int create_impl(const mhh_grid_desc* d, int dtype, int device, mhh_ctx** out)
     { const char* e = getenv("MHH_TILE3_Y"); if (e) { int v = atoi(e); if (v == 3 || v == 4 || v == 5) c->tile3_y = v; } }
     { const char* e = getenv("MHH_EVISC_MB"); if (e) c->evisc_mb = atoi(e); }
     { const char* e = getenv("MHH_EVISC_TMA"); if (e) c->evisc_tma = atoi(e) != 0; }
+    { const char* e = getenv("MHH_STREAM_VEC2"); if (e) c->stream_vec2 = atoi(e) != 0; }
     { const char* e = getenv("MHH_EVISC3_MB"); if (e) c->evisc3_mb = atoi(e); }
     { const char* e = getenv("MHH_EVISC3_NPL"); if (e) c->evisc3_npl = atoi(e); }
     { const char* e = getenv("MHH_PREFETCH"); if (e) c->prefetch = std::max(0, std::min(8, atoi(e))); }
@@ -318,6 +319,16 @@ int ghost_impl(Ctx<TF>* c, TF* fld, int bcbot, const TF* bot, const TF* gradbot,
     return MHH_OK;
 }
 
+// two cells per thread in the streaming kernels: even icells (every row starts on a vector boundary) and vector-aligned arrays
+template <typename TF>
+static bool stream_vec2(const Ctx<TF>* c, std::initializer_list<const void*> ptrs)
+{
+    if (!c->stream_vec2 || (c->g.icells & 1)) return false;
+    for (const void* p : ptrs)
+        if (reinterpret_cast<uintptr_t>(p) % (2 * sizeof(TF)) != 0) return false;
+    return true;
+}
+
 template <typename TF>
 int rk3_impl(Ctx<TF>* c, TF* a, TF* at, int substep, double dt)
 {
@@ -327,7 +338,10 @@ int rk3_impl(Ctx<TF>* c, TF* a, TF* at, int substep, double dt)
     const TF cA[3] = {TF(0.), TF(-5. / 9.), TF(-153. / 128.)};
     const TF cB[3] = {TF(1. / 3.), TF(15. / 16.), TF(8. / 15.)};
     const int nxt = (substep + 1) % 3;
-    rk3_kernel<TF><<<c->grd_all(), c->blk(), 0, c->stream>>>(a, at, cB[substep] * (TF)dt, cA[nxt], nxt == 0, g);
+    if (stream_vec2<TF>(c, {a, at}))
+        rk3_v2_kernel<TF><<<dim3((g.icells / 2 + 63) / 64, (g.jcells + 3) / 4, g.kcells), c->blk(), 0, c->stream>>>(a, at, cB[substep] * (TF)dt, cA[nxt], nxt == 0, g);
+    else
+        rk3_kernel<TF><<<c->grd_all(), c->blk(), 0, c->stream>>>(a, at, cB[substep] * (TF)dt, cA[nxt], nxt == 0, g);
     KCHECKN(c, "rk3_kernel");
     return MHH_OK;
 }
@@ -510,8 +524,12 @@ int substep_post_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, in
     if ((rc = pres_solve_impl<TF>(c, f, sub_dt)) != MHH_OK) return rc;
     const int nxt = (substep + 1) % 3;
     PresArgs<TF> a{P<TF>(f->ut), P<TF>(f->vt), P<TF>(f->wt), P<TF>(f->u), P<TF>(f->v), P<TF>(f->w), P<TF>(f->p)};
-    pres_out_rk3_kernel<TF><<<c->grd_all(), c->blk(), 0, c->stream>>>(a, P<TF>(f->u), P<TF>(f->v), P<TF>(f->w),
-            cB[substep] * (TF)dt, cA[nxt], nxt == 0, g);
+    if (stream_vec2<TF>(c, {a.ut, a.vt, a.wt, a.u, a.v, a.w, a.p}))
+        pres_out_rk3_v2_kernel<TF><<<dim3((g.icells / 2 + 63) / 64, (g.jcells + 3) / 4, g.kcells), c->blk(), 0, c->stream>>>(a, P<TF>(f->u), P<TF>(f->v), P<TF>(f->w),
+                cB[substep] * (TF)dt, cA[nxt], nxt == 0, g);
+    else
+        pres_out_rk3_kernel<TF><<<c->grd_all(), c->blk(), 0, c->stream>>>(a, P<TF>(f->u), P<TF>(f->v), P<TF>(f->w),
+                cB[substep] * (TF)dt, cA[nxt], nxt == 0, g);
     KCHECKN(c, "pres_out_rk3_kernel");
     for (int n = 0; n < f->ns; ++n)
         if ((rc = rk3_impl<TF>(c, P<TF>(f->s[n]), P<TF>(f->st[n]), substep, dt)) != MHH_OK) return rc;

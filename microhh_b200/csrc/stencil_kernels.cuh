@@ -725,4 +725,78 @@ __global__ void __launch_bounds__(256) pres_out_rk3_kernel(const PresArgs<TF> a,
     }
 }
 
+// ---- two cells per thread (one 2*sizeof(TF) vector access per array): same arithmetic as rk3_kernel / pres_out_rk3_kernel.
+// Needs an even icells and 2*sizeof(TF)-aligned arrays (every row then starts on a vector boundary).  In single precision a
+// thread of the scalar kernels has only 4 bytes in flight per array, which is what kept them at 58 % / 74 % of the HBM rate.
+template <typename TF>
+__global__ void __launch_bounds__(256) rk3_v2_kernel(TF* __restrict__ a, TF* __restrict__ at, const TF cbdt, const TF ca_next,
+        const int wrap, const GridDev<TF> g)
+{
+    typedef typename V2T<TF>::type V2;
+    const int i = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = blockIdx.z;
+    if (i >= g.icells || j >= g.jcells) return;
+    const long long ijk = i + (long long)j * g.icells + k * g.ijcells;
+    const bool row = j >= g.jstart && j < g.jend && k >= g.kstart && k < g.kend;
+    const bool in0 = row && i >= g.istart && i < g.iend, in1 = row && i + 1 >= g.istart && i + 1 < g.iend;
+    if (!in0 && !in1 && !wrap) return;
+    V2 t = *reinterpret_cast<const V2*>(at + ijk);
+    if (in0 || in1)
+    {
+        V2 x = *reinterpret_cast<const V2*>(a + ijk);
+        if (in0) x.x += cbdt * t.x;
+        if (in1) x.y += cbdt * t.y;
+        *reinterpret_cast<V2*>(a + ijk) = x;
+    }
+    t.x = wrap ? TF(0) : (in0 ? t.x * ca_next : t.x);
+    t.y = wrap ? TF(0) : (in1 ? t.y * ca_next : t.y);
+    *reinterpret_cast<V2*>(at + ijk) = t;
+}
+
+template <typename TF>
+__global__ void __launch_bounds__(256) pres_out_rk3_v2_kernel(const PresArgs<TF> a, TF* __restrict__ u, TF* __restrict__ v, TF* __restrict__ w,
+        const TF cbdt, const TF ca_next, const int wrap, const GridDev<TF> g)
+{
+    typedef typename V2T<TF>::type V2;
+    const int i = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = blockIdx.z;
+    if (i >= g.icells || j >= g.jcells) return;
+    const long long jj = g.icells, kk = g.ijcells;
+    const long long ijk = i + j * jj + k * kk;
+    const bool row = j >= g.jstart && j < g.jend && k >= g.kstart && k < g.kend;
+    const bool in0 = row && i >= g.istart && i < g.iend, in1 = row && i + 1 >= g.istart && i + 1 < g.iend;
+    auto LD = [](const TF* p) -> V2 { return *reinterpret_cast<const V2*>(p); };
+    auto ST = [](TF* p, const V2 x) { *reinterpret_cast<V2*>(p) = x; };
+    if (in0 || in1)
+    {
+        const V2 pc = LD(a.p + ijk), ps = LD(a.p + ijk - jj), pb = LD(a.p + ijk - kk);
+        const TF pw = a.p[ijk - 1];                 // in0 implies i >= istart >= 1; with !in0 the value is not used
+        V2 tu = LD(a.ut + ijk), tv = LD(a.vt + ijk), tw = LD(a.wt + ijk);
+        V2 xu = LD(u + ijk), xv = LD(v + ijk), xw = LD(w + ijk);
+        const TF dzhi = g.dzhi[k];
+        if (in0)
+        {
+            const TF nu = tu.x - (pc.x - pw) * g.dxi, nv = tv.x - (pc.x - ps.x) * g.dyi, nw = tw.x - (pc.x - pb.x) * dzhi;
+            xu.x += cbdt * nu; xv.x += cbdt * nv; xw.x += cbdt * nw;
+            tu.x = nu * ca_next; tv.x = nv * ca_next; tw.x = nw * ca_next;
+        }
+        if (in1)
+        {
+            const TF nu = tu.y - (pc.y - pc.x) * g.dxi, nv = tv.y - (pc.y - ps.y) * g.dyi, nw = tw.y - (pc.y - pb.y) * dzhi;
+            xu.y += cbdt * nu; xv.y += cbdt * nv; xw.y += cbdt * nw;
+            tu.y = nu * ca_next; tv.y = nv * ca_next; tw.y = nw * ca_next;
+        }
+        ST(u + ijk, xu); ST(v + ijk, xv); ST(w + ijk, xw);
+        if (wrap) { tu.x = tu.y = tv.x = tv.y = tw.x = tw.y = TF(0); }
+        ST(a.ut + ijk, tu); ST(a.vt + ijk, tv); ST(a.wt + ijk, tw);
+    }
+    else if (wrap)
+    {
+        V2 z; z.x = TF(0); z.y = TF(0);
+        ST(a.ut + ijk, z); ST(a.vt + ijk, z); ST(a.wt + ijk, z);
+    }
+}
+
 } // namespace mhh

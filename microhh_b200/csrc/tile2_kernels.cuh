@@ -59,9 +59,6 @@ __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* tmap, int x, 
                  :: "l"(reinterpret_cast<unsigned long long>(tmap)), "r"(x), "r"(y), "r"(z) : "memory");
 }
 
-template <typename TF> struct V2T;
-template <> struct V2T<double> { typedef double2 type; };
-template <> struct V2T<float>  { typedef float2 type; };
 
 // ---- tile geometry ---------------------------------------------------------------------------
 constexpr int T2_W  = 64;                 // tile width  (2 columns per lane)

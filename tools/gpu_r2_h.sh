@@ -14,7 +14,7 @@ python - <<PY
 import json
 try:
     d=json.load(open('gpurun_out/bench_n${N}_strong.json'))
-    print('strong', d['n_gpus'], f"{d['ms_per_step']:.2f} ms/step", d['config']['global_grid'], d['nvlink'], 'e2e', d['e2e'] and d['e2e']['value'])
+    print('strong', d['n_gpus'], f"{d['ms_per_step']:.2f} ms/step", d['config']['global_grid'], d['nvlink'], 'e2e', d['e2e'] and d['e2e']['value'], 'div', d.get('post_step_divergence'))
     print(' '.join(f"{k.replace('_kernel','')}={v:.2f}" for k,v in d['kernels_ms_per_step'].items()))
 except Exception as e:
     print('strong FAILED', e, open('gpurun_out/bench_n${N}_strong.err').read()[-1500:])
@@ -24,7 +24,7 @@ python - <<PY
 import json
 try:
     d=json.load(open('gpurun_out/bench_n${N}_weak.json'))
-    print('weak', d['n_gpus'], f"{d['ms_per_step']:.2f} ms/step", d['config']['global_grid'], d['nvlink'])
+    print('weak', d['n_gpus'], f"{d['ms_per_step']:.2f} ms/step", d['config']['global_grid'], d['nvlink'], 'div', d.get('post_step_divergence'))
     print(' '.join(f"{k.replace('_kernel','')}={v:.2f}" for k,v in d['kernels_ms_per_step'].items()))
 except Exception as e:
     print('weak FAILED', e, open('gpurun_out/bench_n${N}_weak.err').read()[-1500:])
