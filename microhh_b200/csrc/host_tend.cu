@@ -279,7 +279,7 @@ int mom3_launch(Ctx<TF>* c, const MomArgs<TF>& a, const ScalArgs<TF>* sc, bool s
     const int ntx = (g.imax + T2_W - 1) / T2_W, nty = (g.jmax + ty - 1) / ty;
     Tend3Args<TF> t{};
     t.m = a; if (sc) t.sc = *sc;
-    t.kchunk = pick_kchunk_waves(ntx * nty, g.kmax, c->num_sms, 2);
+    t.kchunk = pick_kchunk_waves(ntx * nty, g.kmax, c->num_sms * mom3_min_blocks<TF>(), 2);
     t.prefetch = c->prefetch;
     dim3 grid(ntx, nty, (g.kmax + t.kchunk - 1) / t.kchunk);
     const size_t smem = mom3_smem(sizeof(TF), t.kchunk, ty, nsc, hl);

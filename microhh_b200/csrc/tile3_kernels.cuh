@@ -37,8 +37,12 @@ struct Tend3Args
     int prefetch;
 };
 
+// resident CTAs per SM the kernel is compiled for: fp64 needs its 128 registers (one CTA); the fp32 variant uses 86, its planes
+// are half as large, and two CTAs (26 warps) hide more latency than the few spills of a 72-register cap cost
+template <typename TF> constexpr int mom3_min_blocks() { return sizeof(TF) == 4 ? 2 : 1; }
+
 template <typename TF, bool SURFACE, bool BUOY, int NSC, int TY, int HL>
-__global__ void __launch_bounds__(32 * ((3 + NSC) * TY + 1), 1)
+__global__ void __launch_bounds__(32 * ((3 + NSC) * TY + 1), mom3_min_blocks<TF>())
 mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_v,
             const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_e,
             const __grid_constant__ CUtensorMap tm_s,

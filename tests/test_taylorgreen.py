@@ -1,0 +1,127 @@
+"""
+Known-answer test of the whole sub-step: the 2-D Taylor-Green vortex of the reference's own convergence test
+(cases/taylorgreen/taylorgreen.ini, taylorgreen_test.py, taylorgreen_funcs.py:47-60; BASELINE configs[1]).
+
+    u =  sin(2 pi x) cos(2 pi z) exp(-8 pi^2 nu t),   w = -cos(2 pi x) sin(2 pi z) exp(-8 pi^2 nu t),
+    p = (1/4 (cos 4 pi x + cos 4 pi z) - 1/4) exp(-16 pi^2 nu t)
+
+on x in [0, 1), z in [0, 0.5], free-slip walls, jtot = 1, initialised like Fields::add_vortex_pair (src/fields.cxx:1137-1160).
+The reference checks the order of convergence of the L1 error for swspatialorder 2 (advec 2), 4 (advec 4) and 4 (advec 4m);
+so do these tests -- with the numpy oracle on the CPU and with the CUDA path on the GPU -- and the two are compared with each
+other after the same number of steps.
+"""
+import numpy as np
+import pytest
+
+from util import interior
+from oracle import oracle as O, step as ostep
+
+VISC = 1./(8.*np.pi**2*100.)        # taylorgreen_test.py:41
+ORDERS = {"2": ("2", "2", 2), "4": ("4", "4", 4), "4m": ("4m", "4", 4)}        # swadvec, swdiff, grid order
+
+
+def tg_setup(n, order, dtype=np.float64):
+    from microhh_b200.grid import GridData
+    swadvec, swdiff, go = ORDERS[order]
+    gc = (3, 3, 3) if go == 4 else (1, 1, 1)
+    it, jt, kt = n, 1, n//2
+    g = O.Grid(it, jt, kt, 1., 1., 0.5, *gc, dtype, order=go)
+    gd = GridData(it, jt, kt, 1., 1., 0.5, *gc, dtype, order=go)
+    x = (np.arange(g.icells) - g.igc + 0.5)*float(g.dx); xh = (np.arange(g.icells) - g.igc)*float(g.dx)
+    z = np.asarray(g.z, np.float64); zh = np.asarray(g.zh, np.float64)
+    c = {n_: np.zeros(gd.shape, dtype) for n_ in ("u", "v", "w", "th", "ut", "vt", "wt", "tht", "p", "evisc")}
+    ks, ke = g.kstart, g.kend
+    two_pi = 2.*np.pi
+    c["u"][ks:ke, g.jstart:g.jend, g.istart:g.iend] = (np.sin(two_pi*xh[g.istart:g.iend])[None, None, :]
+                                                       * np.cos(np.pi*z[ks:ke]/0.5)[:, None, None])
+    c["w"][ks:ke, g.jstart:g.jend, g.istart:g.iend] = (-np.cos(two_pi*x[g.istart:g.iend])[None, None, :]
+                                                       * np.sin(np.pi*zh[ks:ke]/0.5)[:, None, None])
+    c["w"][ks] = 0; c["w"][ke] = 0                                            # src/fields.cxx:1023-1031
+    c["th"][...] = 1.
+    c["scalars"] = ["th"]
+    zero2 = lambda: np.zeros(gd.shape2d, dtype)
+    for n_ in ("u", "v", "th"):
+        for s in ("_bot", "_top", "_gradbot", "_gradtop", "_fluxbot", "_fluxtop"):
+            c[n_ + s] = zero2()
+    ones = np.ones(g.kcells, dtype)
+    c.update(rhoref=ones, rhorefh=ones.copy(), thref=300*ones, threfh=300*ones)
+    prm = ostep.default_params()
+    prm.update(swadvec=swadvec, swdiff=swdiff, swthermo=None, surface_model=False, visc=VISC, svisc=VISC,
+               mbcbot=O.BC_NEUMANN, mbctop=O.BC_NEUMANN, sbcbot=O.BC_NEUMANN, sbctop=O.BC_NEUMANN)
+    return g, gd, c, prm, (x, xh, z, zh)
+
+
+def tg_errors(g, coords, u, w, p, t):
+    """L1 errors as taylorgreen_funcs.py:51-72"""
+    x, xh, z, zh = coords
+    ks, ke, i0, i1 = g.kstart, g.kend, g.istart, g.iend
+    dec = np.exp(-8.*np.pi**2*VISC*t)
+    two_pi = 2.*np.pi
+    u_ref = np.sin(two_pi*xh[i0:i1])[None, :]*np.cos(two_pi*z[ks:ke])[:, None]*dec
+    w_ref = -np.cos(two_pi*x[i0:i1])[None, :]*np.sin(two_pi*zh[ks:ke])[:, None]*dec
+    p_ref = (0.25*(np.cos(2*two_pi*x[i0:i1])[None, :] + np.cos(2*two_pi*z[ks:ke])[:, None]) - 0.25)*dec**2
+    da = float(g.dx)*float(g.dx)            # equidistant, dz = dx
+    sl = (slice(ks, ke), g.jstart, slice(i0, i1))
+    return (da*np.abs(u[sl] - u_ref).sum(), da*np.abs(w[sl] - w_ref).sum(), da*np.abs(p[sl] - p_ref).sum())
+
+
+def order_of(errs, ns):
+    return (np.log(errs[-1]) - np.log(errs[0]))/(np.log(1./ns[-1]) - np.log(1./ns[0]))
+
+
+def run_oracle(n, order, nsteps, dt):
+    g, gd, c, prm, coords = tg_setup(n, order)
+    K = O.NumpyKernels(g)
+    pres = None
+    for _ in range(nsteps):
+        pres = ostep.dycore_step(g, K, c, prm, dt, pres=pres)
+    return g, c, coords
+
+
+@pytest.mark.parametrize("order", ["2", "4", "4m"])
+def test_taylorgreen_convergence_oracle(order):
+    """The oracle itself reproduces the analytic solution with the scheme's order (coarse grids: the CPU suite stays short)."""
+    ns = (16, 32)
+    T, dt = 0.25, 0.005
+    errs = []
+    for n in ns:
+        g, c, coords = run_oracle(n, order, int(round(T/dt)), dt)
+        errs.append(tg_errors(g, coords, c["u"], c["w"], c["p"], T))
+    eu, ew, ep = (np.array(e) for e in zip(*errs))
+    want = 1.8 if order == "2" else 3.5
+    assert order_of(eu, ns) > want and order_of(ew, ns) > want, (order_of(eu, ns), order_of(ew, ns))
+    assert order_of(ep, ns) > 1.8, order_of(ep, ns)
+    assert eu[-1] < (2e-3 if order == "2" else 2e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("order", ["2", "4", "4m"])
+def test_taylorgreen_convergence_gpu(order):
+    """The CUDA path: 400 steps to t = 1 at 16 ... 128 points (the reference test's resolutions below 256), L1 error against
+    the analytic solution, order of convergence; and the same fields as the oracle after 50 steps at n = 32."""
+    from microhh_b200 import dycore as D
+    swadvec, swdiff, go = ORDERS[order]
+    ns = (16, 32, 64, 128)
+    T, dt = 1.0, 0.0025
+    errs = []
+    for n in ns:
+        g, gd, c, prm, coords = tg_setup(n, order)
+        ctx = D.Context(gd, 0)
+        ctx.set_basestate(c["rhoref"], c["rhorefh"], c["thref"], c["threfh"])
+        f = D.Fields(ctx, c, visc=VISC, svisc=VISC)
+        dprm = D.make_params(swadvec=swadvec, swdiff=swdiff, swthermo=None, surface_model=False, mbcbot=1, mbctop=1)
+        dyc = D.Dycore(ctx, dprm)
+        for step in range(int(round(T/dt))):
+            dyc.step(f, dt)
+            if n == 32 and step == 49:
+                go_, co, _ = run_oracle(32, order, 50, dt)
+                for name in ("u", "w", "p"):
+                    a = interior(go_, f[name].cpu().numpy()); b = interior(go_, co[name])
+                    assert np.sqrt(((a - b)**2).sum()/(b**2).sum()) <= 1e-11, name
+        ctx.sync()
+        errs.append(tg_errors(g, coords, f["u"].cpu().numpy(), f["w"].cpu().numpy(), f["p"].cpu().numpy(), T))
+        ctx.close()
+    eu, ew, ep = (np.array(e) for e in zip(*errs))
+    want = 1.9 if order == "2" else 3.8
+    assert order_of(eu, ns) > want and order_of(ew, ns) > want, (eu, ew)
+    assert order_of(ep, ns) > 1.9, ep
