@@ -38,6 +38,11 @@ struct mhh_ctx
     int device = 0;
     std::string err;
     cudaStream_t own_stream = nullptr;
+    // side stream for work that is independent of the pressure solve (the RK3 update of the scalars): forked / joined with the
+    // two events inside one sub-step.  MHH_OVERLAP=0 keeps everything on the main stream.
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool overlap = true;
     cudaStream_t stream = nullptr;
     long long launches = 0;
     long long ws_bytes = 0;
@@ -172,6 +177,9 @@ struct Ctx : mhh_ctx
         cudaFree(spec); cudaFree(fac); cudaFree(d_red); cudaFree(halo);
         if (comm) { std::string e; NcclApi* api = nccl_api(e); if (api) api->CommDestroy(comm); }
         if (h_red) cudaFreeHost(h_red);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
+        if (side_stream) cudaStreamDestroy(side_stream);
         if (own_stream) cudaStreamDestroy(own_stream);
     }
 
