@@ -58,7 +58,29 @@ def test_layout_is_a_bijection_and_blocks_are_messages(shape, P):
     assert lib.mhh_slab_layout(itot, jtot + 1, ktot, 2, 0, C.byref(capi.SlabInfo())) != 0 or (jtot + 1) % 2 == 0
 
 
-def _slab_worker(rank, world, port, shape, out_q):
+def _pres4_solve_modes(pres, g, S, m_off, mcl):
+    """Pres_4::solve's 7-band system (src/pres_4.cxx:346-470, oracle.Pres4.solve) for the x-modes [m_off, m_off + mcl) of a
+    real array S of shape (kmax, jtot, mcl): the matrix rows, the boundary rows and hdma, exactly as on a single domain."""
+    kmax, jtot = g.kmax, g.jtot
+    shp = (kmax + 4, jtot, mcl)
+    M = [np.zeros(shp) for _ in range(7)]
+    pt = np.zeros(shp)
+    M[3][0] = 1.; M[6][0] = -1.
+    M[3][1] = 1.; M[4][1] = -1.
+    for n in range(7):
+        M[n][2:kmax+2] = pres.m[n][:, None, None]
+    M[3][2:kmax+2] = M[3][2:kmax+2] + pres.bmati[None, None, m_off:m_off+mcl] + pres.bmatj[None, :, None]
+    pt[2:kmax+2] = S
+    M[2][kmax+2] = -1.; M[3][kmax+2] = 1.
+    M[0][kmax+3] = -1.; M[3][kmax+3] = 1.
+    if m_off == 0:          # mode (0, 0) lives on the rank that owns x-mode 0
+        M[0][kmax+2, 0, 0] = 0.; M[1][kmax+2, 0, 0] = -1/3.; M[2][kmax+2, 0, 0] = 2.; M[3][kmax+2, 0, 0] = 1.
+        M[0][kmax+3, 0, 0] = -2.; M[1][kmax+3, 0, 0] = 9.; M[2][kmax+3, 0, 0] = 0.; M[3][kmax+3, 0, 0] = 1.
+    pres.hdma(*M, pt)
+    return pt[2:kmax+2]
+
+
+def _slab_worker(rank, world, port, shape, out_q, order=2):
     import torch
     import torch.distributed as dist
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -68,10 +90,14 @@ def _slab_worker(rank, world, port, shape, out_q):
     try:
         lib = capi.load()
         itot, jtot, ktot = shape
-        g = O.Grid(itot, jtot, ktot, 100., 80., 60., 3, 3, 1, np.float64,
-                   z=np.cumsum(np.linspace(0.7, 1.3, ktot))*60./np.linspace(0.7, 1.3, ktot).sum() - 0.3)
-        rho = np.exp(-g.z/8000.); rhoh = np.exp(-g.zh/8000.)
-        pres = O.Pres2(g, rho, rhoh)
+        zst = np.cumsum(np.linspace(0.7, 1.3, ktot))*60./np.linspace(0.7, 1.3, ktot).sum() - 0.3
+        if order == 4:
+            g = O.Grid(itot, jtot, ktot, 100., 80., 60., 3, 3, 3, np.float64, z=zst, order=4)
+            pres = O.Pres4(g)
+        else:
+            g = O.Grid(itot, jtot, ktot, 100., 80., 60., 3, 3, 1, np.float64, z=zst)
+            rho = np.exp(-g.z/8000.); rhoh = np.exp(-g.zh/8000.)
+            pres = O.Pres2(g, rho, rhoh)
         rhs = np.random.default_rng(5).standard_normal((ktot, jtot, itot))
         rhs -= rhs.mean()
         infos = [slab_info(lib, itot, jtot, ktot, world, r) for r in range(world)]
@@ -118,6 +144,18 @@ def _slab_worker(rank, world, port, shape, out_q):
                 for ml in range(me.mcl):
                     yi[k, j, ml] = lib.mhh_slab_yindex(itot, jtot, ktot, world, rank, k, j, ml)
         S = np.fft.fft(ybuf[yi], axis=1)                                  # (k, l, ml)
+        if order == 4:
+            # Pres_4: the 7-band solve on my modes, real and imaginary parts separately (the matrix is real)
+            re = _pres4_solve_modes(pres, g, np.ascontiguousarray(S.real), me.m_off, me.mcl)
+            im = _pres4_solve_modes(pres, g, np.ascontiguousarray(S.imag), me.m_off, me.mcl)
+            ybuf[yi] = np.fft.ifft(re + 1j*im, axis=1)
+            xbuf = exchange(ybuf, False)
+            p_loc = np.fft.irfft(xbuf[xi], n=itot, axis=2)
+            p = g.field()
+            pres.solve(rhs.copy(), p)
+            ref = p[g.kstart:g.kend, g.jstart:g.jend, g.istart:g.iend][:, rank*jmax:(rank+1)*jmax, :]
+            out_q.put((rank, float(np.sqrt(((p_loc - ref)**2).sum()/(ref**2).sum()))))
+            return
         # Pres_2::solve matrix (src/pres_2.cxx:292-324) for my modes, complex right-hand side
         kg = g.kgc
         dz = g.dz[kg:kg+ktot][:, None, None]; rr = rho[kg:kg+ktot][:, None, None]
@@ -145,13 +183,14 @@ def _slab_worker(rank, world, port, shape, out_q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("shape", [(16, 8, 6), (20, 12, 5)])
-def test_gloo_world2_slab_solve_matches_single_domain(shape):
+@pytest.mark.parametrize("shape,order", [((16, 8, 6), 2), ((20, 12, 5), 2), ((16, 8, 8), 4), ((20, 12, 6), 4)])
+def test_gloo_world2_slab_solve_matches_single_domain(shape, order):
+    """order 2: Pres_2 (tridiagonal); order 4: Pres_4 (7-band hdma on the owner's modes, mode (0, 0) rows on rank 0)."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_slab_worker, args=(r, 2, port, shape, q)) for r in range(2)]
+    port = 29500 + (os.getpid() % 2000) + 7*order
+    procs = [ctx.Process(target=_slab_worker, args=(r, 2, port, shape, q, order)) for r in range(2)]
     for p in procs:
         p.start()
     res = []
