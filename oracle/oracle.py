@@ -1246,6 +1246,119 @@ def diff_dnmul(g, evisc, tPr):
 
 
 # --------------------------------------------------------------------------------------
+# Diff_tke2: Deardorff (1980) SGS-TKE closure (reference src/diff_tke2.cxx:48-512) and the Limiter's
+# tendency_limiter (src/limiter.cxx:35-59).  Surface model only ("Resolved wall not supported").
+# --------------------------------------------------------------------------------------
+SGSTKE_MIN = 1.e-7    # Constants::sgstke_min (include/constants.h:59)
+
+def _tke2_mlen0(g):
+    """std::pow(dx*dy*dz[k], TF(1./3.)) per level (src/diff_tke2.cxx:104,167,188)"""
+    TF = g.TF
+    return _libm_pow((g.dx*g.dy*g.dz).astype(TF), TF(1./3.)).astype(TF)
+
+def _tke2_ij(g):
+    return (slice(g.jstart, g.jend), slice(g.istart, g.iend))
+
+def tke2_enforce_min(g, sgstke):
+    """src/diff_tke2.cxx:48-71"""
+    TF = g.TF
+    a = _S(g, sgstke)
+    a[...] = np.maximum(a, TF(SGSTKE_MIN))
+    boundary_cyclic(g, sgstke)
+
+def tke2_evisc_neutral(g, evisc, sgstke, z0m, cn, cm, mason=True):
+    """src/diff_tke2.cxx:73-134 (note: the Mason correction uses z[kstart] at every level, :118)"""
+    TF = g.TF
+    cm = TF(cm)
+    m0 = _K(g, _tke2_mlen0(g))
+    a = _S(g, sgstke)
+    if mason:
+        zz = TF(KAPPA)*(g.z[g.kstart] + z0m[_tke2_ij(g)])[None, :, :]
+        fac = np.sqrt(TF(1.)/(TF(1.)/_pow2(m0) + TF(1.)/_pow2(zz)))
+    else:
+        fac = m0 + np.zeros_like(a)
+    _S(g, evisc)[...] = cm*fac*np.sqrt(a)
+    boundary_cyclic(g, evisc)
+
+def _tke2_fac(g, a, N2, bgradbot, z0m, cn, mason, variant):
+    """Length scale of calc_evisc / calc_evisc_heat (variant 0: cn*sqrt(a/N2), Mason by sqrt / pow2, src/diff_tke2.cxx:170-228)
+    and of sgstke_diss_tend (variant 1: cn*sqrt(a)/sqrt(N2), Mason by std::pow, :420-466).  Returns (fac, mlen0) on the interior."""
+    TF = g.TF
+    cn = TF(cn)
+    ks, ke = g.kstart, g.kend
+    m0 = _K(g, _tke2_mlen0(g)) + np.zeros_like(_S(g, a))
+    n2 = _S(g, N2).copy()
+    n2[0] = bgradbot[_tke2_ij(g)]                   # lowest level: the surface model's db/dz
+    aa = _S(g, a)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        if variant == 0:
+            mlen = cn*np.sqrt(aa/n2)
+        else:
+            mlen = cn*np.sqrt(aa)/np.sqrt(n2)
+    mlen = np.where(n2 > 0, mlen, m0)
+    fac = np.minimum(m0, mlen)
+    if mason:
+        zz = TF(KAPPA)*(_K(g, g.z) + z0m[_tke2_ij(g)][None, :, :])
+        if variant == 0:
+            fac = np.sqrt(TF(1.)/(TF(1.)/_pow2(fac) + TF(1.)/_pow2(zz)))
+        else:
+            two = TF(2.)
+            fac = _libm_pow(TF(1.)/(TF(1.)/_libm_pow(fac, two) + TF(1.)/_libm_pow(zz, two)), TF(1.)/two)
+    return fac, m0, n2
+
+def tke2_evisc(g, evisc, sgstke, N2, bgradbot, z0m, cn, cm, mason=True):
+    """src/diff_tke2.cxx:136-234"""
+    TF = g.TF
+    fac, _, _ = _tke2_fac(g, sgstke, N2, bgradbot, z0m, cn, mason, 0)
+    _S(g, evisc)[...] = TF(cm)*fac*np.sqrt(_S(g, sgstke))
+    boundary_cyclic(g, evisc)
+
+def tke2_evisc_heat(g, evisch, evisc, sgstke, N2, bgradbot, z0m, cn, ch1, ch2, mason=True):
+    """src/diff_tke2.cxx:236-332"""
+    TF = g.TF
+    fac, m0, _ = _tke2_fac(g, sgstke, N2, bgradbot, z0m, cn, mason, 0)
+    _S(g, evisch)[...] = (TF(ch1) + TF(ch2)*fac/m0)*_S(g, evisc)
+    boundary_cyclic(g, evisch)
+
+def tke2_shear_tend(g, at, evisc, strain2):
+    """src/diff_tke2.cxx:334-357"""
+    _S(g, at)[...] += _S(g, evisc)*_S(g, strain2)
+
+def tke2_buoy_tend(g, at, evisch, N2, bgradbot):
+    """src/diff_tke2.cxx:359-393"""
+    n2 = _S(g, N2).copy()
+    n2[0] = bgradbot[_tke2_ij(g)]
+    _S(g, at)[...] -= _S(g, evisch)*n2
+
+def tke2_diss_tend(g, at, a, N2, bgradbot, z0m, cn, ce1, ce2, mason=True):
+    """src/diff_tke2.cxx:395-469"""
+    TF = g.TF
+    fac, m0, _ = _tke2_fac(g, a, N2, bgradbot, z0m, cn, mason, 1)
+    _S(g, at)[...] -= (TF(ce1) + TF(ce2)*fac/m0)*_libm_pow(_S(g, a), TF(3./2.))/fac
+
+def tke2_diss_tend_neutral(g, at, a, z0m, ce1, ce2, mason=True):
+    """src/diff_tke2.cxx:471-511"""
+    TF = g.TF
+    m0 = _K(g, _tke2_mlen0(g)) + np.zeros_like(_S(g, a))
+    if mason:
+        two = TF(2.)
+        zz = TF(KAPPA)*(_K(g, g.z) + z0m[_tke2_ij(g)][None, :, :])
+        fac = _libm_pow(TF(1.)/(TF(1.)/_libm_pow(m0, two) + TF(1.)/_libm_pow(zz, two)), TF(1.)/two)
+    else:
+        fac = m0
+    _S(g, at)[...] -= (TF(ce1) + TF(ce2)*fac/m0)*_libm_pow(_S(g, a), TF(3./2.))/fac
+
+def tendency_limiter(g, at, a, min_value, dt):
+    """src/limiter.cxx:35-59"""
+    TF = g.TF
+    dt = TF(dt); mv = TF(min_value)
+    dti = TF(1.)/dt
+    t = _S(g, at)
+    a_new = _S(g, a) + dt*t
+    t[...] += np.where(a_new < mv, (-a_new + mv)*dti, TF(0.))
+
+
+# --------------------------------------------------------------------------------------
 # Thermo_dry (reference src/thermo_dry.cxx:66-78, 165-179)
 # --------------------------------------------------------------------------------------
 def thermo_dry_N2(g, N2, th, thref):
@@ -1934,6 +2047,15 @@ class NumpyKernels:
     def diff_w(self, wt, u, v, w, evisc, rhoref, rhorefh, visc): diff_w(self.g, wt, u, v, w, evisc, rhoref, rhorefh, visc)
     def diff_c(self, at, a, evisc, fluxbot, fluxtop, rhoref, rhorefh, tPr, visc, surface): diff_c(self.g, at, a, evisc, fluxbot, fluxtop, rhoref, rhorefh, tPr, visc, surface)
     def diff_dnmul(self, evisc, tPr): return float(diff_dnmul(self.g, evisc, tPr))
+    def tke2_enforce_min(self, sgstke): tke2_enforce_min(self.g, sgstke)
+    def tke2_evisc_neutral(self, evisc, sgstke, u, v, w, z0m, cn, cm, mason=True): tke2_evisc_neutral(self.g, evisc, sgstke, z0m, cn, cm, mason)
+    def tke2_evisc(self, evisc, sgstke, u, v, w, N2, bgradbot, z0m, cn, cm, mason=True): tke2_evisc(self.g, evisc, sgstke, N2, bgradbot, z0m, cn, cm, mason)
+    def tke2_evisc_heat(self, evisch, evisc, sgstke, N2, bgradbot, z0m, cn, ch1, ch2, mason=True): tke2_evisc_heat(self.g, evisch, evisc, sgstke, N2, bgradbot, z0m, cn, ch1, ch2, mason)
+    def tke2_shear_tend(self, at, a, evisc, strain2): tke2_shear_tend(self.g, at, evisc, strain2)
+    def tke2_buoy_tend(self, at, a, evisch, N2, bgradbot): tke2_buoy_tend(self.g, at, evisch, N2, bgradbot)
+    def tke2_diss_tend(self, at, a, N2, bgradbot, z0m, cn, ce1, ce2, mason=True): tke2_diss_tend(self.g, at, a, N2, bgradbot, z0m, cn, ce1, ce2, mason)
+    def tke2_diss_tend_neutral(self, at, a, z0m, ce1, ce2, mason=True): tke2_diss_tend_neutral(self.g, at, a, z0m, ce1, ce2, mason)
+    def tendency_limiter(self, at, a, min_value, dt): tendency_limiter(self.g, at, a, min_value, dt)
     def thermo_dry_N2(self, N2, th, thref): thermo_dry_N2(self.g, N2, th, thref)
     def thermo_dry_buoyancy_tend_2nd(self, wt, th, threfh): thermo_dry_buoyancy_tend_2nd(self.g, wt, th, threfh)
     def rk3(self, a, at, substep, dt): rk3(self.g, a, at, substep, dt)

@@ -192,6 +192,40 @@ class RefKernels:
         return self._call("ref_diff_dnmul", evisc, g.dzi, TF(1./(float(g.dx)*float(g.dx))), TF(1./(float(g.dy)*float(g.dy))),
                           float(tPr), restype=C.c_double)
 
+    # --- diff_tke2 + limiter (oracle/ref/ref_diff_tke2.cpp)
+    def tke2_enforce_min(self, sgstke):
+        self._call("ref_tke2_enforce_min", sgstke)
+
+    def tke2_evisc_neutral(self, evisc, sgstke, u, v, w, z0m, cn, cm, mason=True):
+        g = self.g
+        self._call("ref_tke2_evisc_neutral", evisc, sgstke, u, v, w, g.z, g.dz, z0m, g.dx, g.dy, float(cn), float(cm), int(mason))
+
+    def tke2_evisc(self, evisc, sgstke, u, v, w, N2, bgradbot, z0m, cn, cm, mason=True):
+        g = self.g
+        self._call("ref_tke2_evisc", evisc, sgstke, u, v, w, N2, bgradbot, g.z, g.dz, z0m, g.dx, g.dy, float(cn), float(cm), int(mason))
+
+    def tke2_evisc_heat(self, evisch, evisc, sgstke, N2, bgradbot, z0m, cn, ch1, ch2, mason=True):
+        g = self.g
+        self._call("ref_tke2_evisc_heat", evisch, evisc, sgstke, N2, bgradbot, g.z, g.dz, z0m, g.dx, g.dy,
+                   float(cn), float(ch1), float(ch2), int(mason))
+
+    def tke2_shear_tend(self, at, a, evisc, strain2):
+        self._call("ref_tke2_shear_tend", at, a, evisc, strain2)
+
+    def tke2_buoy_tend(self, at, a, evisch, N2, bgradbot):
+        self._call("ref_tke2_buoy_tend", at, a, evisch, N2, bgradbot)
+
+    def tke2_diss_tend(self, at, a, N2, bgradbot, z0m, cn, ce1, ce2, mason=True):
+        g = self.g
+        self._call("ref_tke2_diss_tend", at, a, N2, bgradbot, g.z, g.dz, z0m, g.dx, g.dy, float(cn), float(ce1), float(ce2), int(mason))
+
+    def tke2_diss_tend_neutral(self, at, a, z0m, ce1, ce2, mason=True):
+        g = self.g
+        self._call("ref_tke2_diss_tend_neutral", at, a, g.z, g.dz, z0m, g.dx, g.dy, float(ce1), float(ce2), int(mason))
+
+    def tendency_limiter(self, at, a, min_value, dt):
+        self._call("ref_limiter", at, a, float(min_value), float(dt))
+
     # --- thermo_dry
     def thermo_dry_N2(self, N2, th, thref):
         self._call("ref_thermo_dry_N2", N2, th, self.g.dzi, thref)

@@ -51,6 +51,8 @@ def dycore_substep(g, K, c, prm, substep, dt, pres=None, timers=None, surface_mo
         else:
             # Thermo_type::Disabled (src/diff_smag2.cxx:507-545)
             K.diff_evisc_neutral(c["evisc"], c["u"], c["v"], c["w"], c["z0m"], prm["cs"], prm["visc"], surface, prm["sw_mason"])
+    elif swdiff == "tke2":
+        _tke2_exec_viscosity(K, c, prm)
     lap("evisc")
     # thermo.exec
     if prm["swthermo"] == "dry":
@@ -88,15 +90,47 @@ def dycore_substep(g, K, c, prm, substep, dt, pres=None, timers=None, surface_mo
         if forcing is not None:
             forcing(c, O.rk3_subdt(dt, substep))       # buffer.exec + force.exec (src/model.cxx:416-430)
         return _pres_and_rk3(g, K, c, prm, substep, dt, pres, lap)
+    if swdiff == "tke2":
+        surface = True                                 # Diff_tke2::exec: Surface_model::Enabled throughout (src/diff_tke2.cxx:684-789)
     K.diff_u(c["ut"], c["u"], c["v"], c["w"], c["evisc"], c["u_fluxbot"], c["u_fluxtop"], rr, rh, prm["visc"], surface)
     K.diff_v(c["vt"], c["u"], c["v"], c["w"], c["evisc"], c["v_fluxbot"], c["v_fluxtop"], rr, rh, prm["visc"], surface)
     K.diff_w(c["wt"], c["u"], c["v"], c["w"], c["evisc"], rr, rh, prm["visc"])
     for s in scal:
-        K.diff_c(c[s + "t"], c[s], c["evisc"], c[s + "_fluxbot"], c[s + "_fluxtop"], rr, rh, prm["tPr"], prm["svisc"], surface)
+        if swdiff == "tke2":
+            # sgstke diffuses with the eddy viscosity for momentum, the other scalars with the one for heat when there is
+            # buoyancy; tPr_dummy = 1 (src/diff_tke2.cxx:733-789)
+            ev = c["evisc"] if (s == "sgstke" or prm["swthermo"] != "dry") else c["eviscs"]
+            K.diff_c(c[s + "t"], c[s], ev, c[s + "_fluxbot"], c[s + "_fluxtop"], rr, rh, 1., prm["svisc"], True)
+        else:
+            K.diff_c(c[s + "t"], c[s], c["evisc"], c[s + "_fluxbot"], c[s + "_fluxtop"], rr, rh, prm["tPr"], prm["svisc"], surface)
     lap("diff")
     if forcing is not None:
         forcing(c, O.rk3_subdt(dt, substep))           # buffer.exec + force.exec (src/model.cxx:416-430)
     return _pres_and_rk3(g, K, c, prm, substep, dt, pres, lap)
+
+
+TKE2_DEFAULTS = dict(ap=1.5, cf=2.5, ce1=0.19, ce2=0.51, cm=0.12, ch1=1., ch2=2., cn=0.76)    # src/diff_tke2.cxx:525-532
+
+
+def _tke2_exec_viscosity(K, c, prm):
+    """Diff_tke2::exec_viscosity (src/diff_tke2.cxx:799-983): strain^2 with the MO gradients at the lowest level, eddy
+    viscosities from the prognostic SGS TKE, and the buoyancy / dissipation / shear tendencies of sgstke."""
+    t = {**TKE2_DEFAULTS, **prm.get("tke2", {})}
+    mason = prm["sw_mason"]
+    scal = c["scalars"]
+    str2 = np.zeros_like(c["evisc"])
+    K.diff_strain2(str2, c["u"], c["v"], c["w"], c["dudz_mo"], c["dvdz_mo"], True)
+    if prm["swthermo"] != "dry":
+        K.tke2_evisc_neutral(c["evisc"], c["sgstke"], c["u"], c["v"], c["w"], c["z0m"], t["cn"], t["cm"], mason)
+        K.tke2_diss_tend_neutral(c["sgstket"], c["sgstke"], c["z0m"], t["ce1"], t["ce2"], mason)
+    else:
+        N2 = np.zeros_like(c["evisc"])
+        K.thermo_dry_N2(N2, c[scal[0]], c["thref"])
+        K.tke2_evisc(c["evisc"], c["sgstke"], c["u"], c["v"], c["w"], N2, c["dbdz_mo"], c["z0m"], t["cn"], t["cm"], mason)
+        K.tke2_evisc_heat(c["eviscs"], c["evisc"], c["sgstke"], N2, c["dbdz_mo"], c["z0m"], t["cn"], t["ch1"], t["ch2"], mason)
+        K.tke2_buoy_tend(c["sgstket"], c["sgstke"], c["eviscs"], N2, c["dbdz_mo"])
+        K.tke2_diss_tend(c["sgstket"], c["sgstke"], N2, c["dbdz_mo"], c["z0m"], t["cn"], t["ce1"], t["ce2"], mason)
+    K.tke2_shear_tend(c["sgstket"], c["sgstke"], c["evisc"], str2)
 
 
 def _pres_and_rk3(g, K, c, prm, substep, dt, pres, lap):
@@ -110,6 +144,9 @@ def _pres_and_rk3(g, K, c, prm, substep, dt, pres, lap):
         tdma = lambda p, b: K.tdma(pres.a.copy(), b, pres.c.copy(), p)
     pres.exec(c["p"], c["u"], c["v"], c["w"], c["ut"], c["vt"], c["wt"], O.rk3_subdt(dt, substep), tdma)
     lap("pres")
+    # limiter.exec: "apply the limiter as the last tendency" (src/model.cxx:439-440, src/limiter.cxx:117-129)
+    if prm.get("swdiff") == "tke2":
+        K.tendency_limiter(c["sgstket"], c["sgstke"], O.SGSTKE_MIN, O.rk3_subdt(dt, substep))
     # timeloop.exec
     for n in ["u", "v", "w"] + scal:
         K.rk3(c[n], c[n + "t"], substep, dt)

@@ -9,7 +9,7 @@ import copy
 import numpy as np
 import pytest
 
-from util import make_pair, prepare_halos, interior
+from util import make_pair, prepare_halos, interior, add_sgstke
 from oracle import oracle as O
 from oracle import step as ostep
 from oracle import refbind
@@ -482,3 +482,59 @@ def test_grid_metrics_bitexact(dtype, order, stretched):
         if hasattr(gd, n):
             assert np.array_equal(np.asarray(getattr(gd, n))[:g.kcells], m[n]), ("product", n)
     assert scal[0] == g.dx == gd.dx and scal[1] == g.dy == gd.dy
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape,anel,stretched", CASES)
+@pytest.mark.parametrize("mason", [True, False])
+def test_diff_tke2_kernels_bitexact(dtype, shape, anel, stretched, mason):
+    """Deardorff SGS-TKE closure (src/diff_tke2.cxx:48-512) and the limiter (src/limiter.cxx:35-59), kernel by kernel."""
+    g, gd, case = make_pair(*shape, dtype, stretched=stretched, anelastic=anel)
+    add_sgstke(g, case)
+    prepare_halos(g, case)
+    N, R = both(g)
+    t = ostep.TKE2_DEFAULTS
+    rng = np.random.default_rng(3)
+    N2 = (1.e-4*rng.standard_normal(gd.shape)).astype(dtype)           # both signs: stable and unstable points
+    str2 = (1.e-3*rng.random(gd.shape)).astype(dtype)
+    seed_t = rng.standard_normal(gd.shape).astype(dtype)
+    res = []
+    for K in (N, R):
+        c = copy.deepcopy(case)
+        o = {}
+        K.tke2_enforce_min(c["sgstke"]); o["sgstke"] = c["sgstke"].copy()
+        ev = np.zeros(gd.shape, dtype); K.tke2_evisc_neutral(ev, c["sgstke"], c["u"], c["v"], c["w"], c["z0m"], t["cn"], t["cm"], mason); o["evisc_neutral"] = ev
+        ev = np.zeros(gd.shape, dtype); K.tke2_evisc(ev, c["sgstke"], c["u"], c["v"], c["w"], N2, c["dbdz_mo"], c["z0m"], t["cn"], t["cm"], mason); o["evisc"] = ev
+        evh = np.zeros(gd.shape, dtype); K.tke2_evisc_heat(evh, ev, c["sgstke"], N2, c["dbdz_mo"], c["z0m"], t["cn"], t["ch1"], t["ch2"], mason); o["eviscs"] = evh
+        at = seed_t.copy(); K.tke2_shear_tend(at, c["sgstke"], ev, str2); o["shear"] = at
+        at = seed_t.copy(); K.tke2_buoy_tend(at, c["sgstke"], evh, N2, c["dbdz_mo"]); o["buoy"] = at
+        at = seed_t.copy(); K.tke2_diss_tend(at, c["sgstke"], N2, c["dbdz_mo"], c["z0m"], t["cn"], t["ce1"], t["ce2"], mason); o["diss"] = at
+        at = seed_t.copy(); K.tke2_diss_tend_neutral(at, c["sgstke"], c["z0m"], t["ce1"], t["ce2"], mason); o["diss_neutral"] = at
+        at = (-0.5*seed_t).copy(); K.tendency_limiter(at, c["sgstke"], O.SGSTKE_MIN, 1.7); o["limiter"] = at
+        res.append(o)
+    for n in res[0]:
+        a, b = res[0][n], res[1][n]
+        assert np.array_equal(a, b), (n, float(np.abs(a.astype(np.float64) - b).max()))
+    assert np.isfinite(interior(g, res[0]["diss"])).all() and np.isfinite(interior(g, res[0]["evisc"])).all()
+    assert (interior(g, res[0]["sgstke"]) >= dtype(O.SGSTKE_MIN)).all()
+    assert not np.array_equal(res[0]["limiter"], -0.5*seed_t)           # the limiter engaged somewhere
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("swthermo", ["dry", None])
+@pytest.mark.parametrize("swadvec", ["2i5", "2"])
+def test_full_rk3_step_tke2_bitexact(dtype, swthermo, swadvec):
+    """One RK3 step with swdiff = tke2 in Model::exec's order (exec_viscosity incl. the sgstke sources, diffusion with evisc /
+    eviscs and tPr = 1, the limiter after the pressure solve): numpy oracle == compiled reference kernels."""
+    g, gd, case = make_pair(20, 12, 10, dtype, stretched=True, anelastic=True, ns=2)
+    add_sgstke(g, case)
+    O.tke2_enforce_min(g, case["sgstke"])                               # Diff_tke2::create at a cold start
+    c0, c1 = copy.deepcopy(case), copy.deepcopy(case)
+    N, R = both(g)
+    prm = ostep.default_params(); prm.update(swdiff="tke2", swthermo=swthermo, swadvec=swadvec)
+    ostep.dycore_step(g, N, c0, prm, 2.0)
+    ostep.dycore_step(g, R, c1, prm, 2.0, pres=refbind.RefPres(g, 2, c1["rhoref"], c1["rhorefh"]))    # the reference's own Pres_2
+    for n in ("u", "v", "w", "th", "s1", "sgstke", "evisc", "eviscs", "p"):
+        assert np.array_equal(c0[n], c1[n]), n
+    assert np.isfinite(interior(g, c0["sgstke"])).all() and np.isfinite(interior(g, c0["u"])).all()
+    assert not np.array_equal(c0["sgstke"], case["sgstke"])

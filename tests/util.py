@@ -49,3 +49,26 @@ def prepare_halos(g, case):
     for s in case["scalars"]:
         O.ghost_cells_bot_2nd(g, case[s], prm["sbcbot"], None, case[s + "_gradbot"])
         O.ghost_cells_top_2nd(g, case[s], prm["sbctop"], None, case[s + "_gradtop"])
+
+
+def add_sgstke(g, case, seed=5, stable_bottom=True):
+    """Extends a synthetic case with the prognostic SGS TKE of Diff_tke2 (src/diff_tke2.cxx:544): a positive field with a few
+    values below Constants::sgstke_min, its tendency, zero-flux 2-D companions and the `eviscs` diagnostic.  With
+    `stable_bottom` half of the surface points get a positive db/dz so that both branches of the length scale run."""
+    TF = g.TF
+    rng = np.random.default_rng(seed)
+    shape = case["u"].shape
+    e = 0.05 + 0.4*rng.random(shape)
+    e[rng.random(shape) < 0.02] = 1.e-9
+    case["sgstke"] = np.ascontiguousarray(e.astype(TF))
+    case["sgstket"] = np.zeros(shape, TF)
+    case["eviscs"] = np.zeros(shape, TF)
+    for n in ("fluxbot", "fluxtop", "gradbot", "gradtop"):
+        case["sgstke_" + n] = np.zeros(shape[1:], TF)
+    if "sgstke" not in case["scalars"]:
+        case["scalars"] = list(case["scalars"]) + ["sgstke"]
+    if stable_bottom:
+        d = case["dbdz_mo"].copy()
+        d[:, ::2] = -d[:, ::2]
+        case["dbdz_mo"] = d
+    return case
