@@ -90,7 +90,7 @@ ALG_PASSES = {  # algorithmic array passes per launch, in units of N
     "tend_uvw_kernel": 4 + 6, "tend_s_kernel": 5 + 2, "evisc_kernel": 5,
     # z-marching tile kernels: R u,v,w,evisc,th + RMW ut,vt,wt | R s,u,v,w,evisc + RMW st | R u,v,w,th + W evisc
     # mom3 carries scalar 0 as a fourth warp group: R u,v,w,evisc,th + RMW ut,vt,wt,tht
-    "mom_tile_kernel": 5 + 6, "mom3_kernel": 5 + 8, "scal_tile_kernel": 5 + 2, "evisc_tile_kernel": 5, "evisc3_kernel": 5,
+    "mom_tile_kernel": 5 + 6, "mom3_kernel": 5 + 8, "mom3_kernel_advec2": 5 + 8, "scal_tile_kernel": 5 + 2, "evisc_tile_kernel": 5, "evisc3_kernel": 5,
     "fft_x_forward_kernel": 7, "fft_y_forward_kernel": 2, "fft_y_backward_kernel": 2,
     "tdma_solve_kernel": 2, "fft_x_backward_kernel": 2, "pres_out_rk3_kernel": 13, "rk3_kernel": 4,
     # Pres_2 version 2: y transform fused with the Thomas sweeps (R + W of the spectral array each; the pivot table is overhead)
@@ -134,7 +134,7 @@ def timed_steps(torch, dist, world, dyc, f, dt, steps, warmup, ctx):
     return ms, prof, ctx.launch_count - l0
 
 
-def side_config(torch, D, GridData, fill_fields_device, name, shape, dtype, S, peaks, steps, order=2, dt=1.0, device=0):
+def side_config(torch, D, GridData, fill_fields_device, name, shape, dtype, S, peaks, steps, order=2, dt=1.0, device=0, swadvec="2i5"):
     """One more single-GPU configuration of BASELINE.json's list, reported beside the main line (N = 1 only)."""
     it, jt, kt = shape
     B = np.dtype(dtype).itemsize
@@ -152,7 +152,7 @@ def side_config(torch, D, GridData, fill_fields_device, name, shape, dtype, S, p
             prm = D.make_params(swadvec="4m", swdiff="4", swthermo=None, surface_model=False, mbcbot=0, mbctop=0, ns=len(scal))
             dt = 1e-3
         else:
-            prm = D.make_params(ns=len(scal))
+            prm = D.make_params(swadvec=swadvec, ns=len(scal))
         dyc = D.Dycore(ctx, prm)
         ms, prof, launches = timed_steps(torch, None, 1, dyc, f, dt, steps, 3, ctx)
         npts = it*jt*kt
@@ -198,7 +198,7 @@ def run_ours(args):
     f = D.Fields(ctx, None)
     prof1d = fill_fields_device(f, gd, seed=2, noise=0.01)          # generated on the device: 1024^3 never exists on the host
     ctx.set_basestate(prof1d["rhoref"], prof1d["rhorefh"], prof1d["thref"], prof1d["threfh"])
-    prm = D.make_params()
+    prm = D.make_params(swadvec=args.swadvec)
     dyc = D.Dycore(ctx, prm)
     dt = args.dt
     npts = gd.npoints // world        # per GPU
@@ -333,6 +333,7 @@ def run_ours(args):
         ctx.close(); del f; torch.cuda.empty_cache()
         other = [
             side_config(torch, D, GridData, fill_fields_device, "drycblles-shaped LES 512^3 fp64 (round-1 workload)", (512, 512, 512), np.float64, 1, peaks, args.steps),
+            side_config(torch, D, GridData, fill_fields_device, "drycblles as shipped: swadvec=2 + smag2, 512^3 fp64 (Advec_2's fluxes in the fused TMA kernel)", (512, 512, 512), np.float64, 1, peaks, args.steps, swadvec="2"),
             side_config(torch, D, GridData, fill_fields_device, "bomex-shaped LES 512x512x256 fp32 (USESP), two scalars", (512, 512, 256), np.float32, 2, peaks, args.steps),
             side_config(torch, D, GridData, fill_fields_device, "moser180-shaped DNS 256x192x128 fp64 (advec_4m + diff_4 + pres_4, as cases/moser180 ships)", (256, 192, 128), np.float64, 1, peaks, args.steps, order=4),
         ]
@@ -341,7 +342,7 @@ def run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic (generated on the device)",
-            "config": {"workload": f"drycblles-shaped LES, global grid {itot_g}x{jtot_g}x{ktot} ({itot}x{jtot}x{ktot_l} points per GPU), advec_2i5+diff_smag2+pres_2+thermo_dry, S=1",
+            "config": {"workload": f"drycblles-shaped LES, global grid {itot_g}x{jtot_g}x{ktot} ({itot}x{jtot}x{ktot_l} points per GPU), advec_{args.swadvec}+diff_smag2+pres_2+thermo_dry, S=1",
                        "global_grid": f"{itot_g}x{jtot_g}x{ktot}",
                        "parallelism": (f"one domain in {world} y-slabs (npx=1, npy={world}); transposes and ghost rows: "
                                        + ("stores of the FFT / pack kernels straight into peer memory over NVLink (CUDA IPC), 4-byte NCCL all-reduce as barrier"
@@ -439,6 +440,7 @@ def main():
     ap.add_argument("--no-side-configs", action="store_true")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--dt", type=float, default=1.0)
+    ap.add_argument("--swadvec", default="2i5", choices=["2i5", "2"], help="2 = cases/drycblles as shipped (side measurement; the headline is 2i5)")
     ap.add_argument("--igc", type=int, default=0, help="x ghost cells (0 = 4: what the adapters request; 3 = the reference's minimum)")
     ap.add_argument("--cpu-sample", default="64x64x64")
     ap.add_argument("--e2e-steps", type=int, default=2)

@@ -109,7 +109,8 @@ typedef struct mhh_fields
 typedef struct mhh_params
 {
     int    swadvec;              /* 25 = 2i5, 2 = 2, 4 = 4, 41 = 4m */
-    int    swdiff;               /* 1 = smag2, 2 = 2, 4 = 4 (the 4th-order configuration: 4 + 4 + pres_4 on a 4th-order grid) */
+    int    swdiff;               /* 1 = smag2, 2 = 2, 3 = tke2 (needs mhh_dycore_set_tke2), 4 = 4 (the 4th-order configuration:
+                                  * 4 + 4 + pres_4 on a 4th-order grid) */
     int    swthermo;             /* 0 = off, 1 = dry (buoyancy from scalar 0 = th) */
     int    surface_model;        /* Boundary switch != "default"  (Surface_model::Enabled) */
     int    sw_mason;             /* [diff] swmason */
@@ -151,6 +152,17 @@ typedef struct mhh_forcing
     const void *ls_s[MHH_MAX_SCALARS];       /* [force] swls: large-scale source profile per scalar */
     const void *wls;                         /* [force] swwls=local: subsidence velocity profile applied to every scalar */
 } mhh_forcing;
+
+/* Deardorff (1980) SGS-TKE closure (Diff_tke2<TF>, src/diff_tke2.cxx): the prognostic scalar `sgstke` is one of the
+ * scalars of mhh_fields (fields.sp["sgstke"], src/diff_tke2.cxx:544), `eviscs` the eddy viscosity for heat / scalars
+ * (fields.sd["eviscs"], only with buoyancy: prm->swthermo != 0).  Constants: [diff] ap, cf, ce1, ce2, cm, ch1, ch2, cn
+ * (reference defaults 1.5, 2.5, 0.19, 0.51, 0.12, 1, 2, 0.76; src/diff_tke2.cxx:525-532). */
+typedef struct mhh_tke2
+{
+    int    isgstke;              /* index of sgstke in mhh_fields.s / .st */
+    void  *eviscs;               /* DEVICE field (ghosted layout); may be NULL when swthermo == 0 */
+    double ap, cf, ce1, ce2, cm, ch1, ch2, cn;
+} mhh_tke2;
 
 /* ---- context ----------------------------------------------------------------------------- */
 MHH_API int  mhh_ctx_create(const mhh_grid_desc* grid, int dtype, int device, mhh_ctx** out);
@@ -264,6 +276,24 @@ MHH_API int mhh_advec_get_cfl(mhh_ctx* ctx, int swadvec, const mhh_fields* f, do
 MHH_API int mhh_diff_smag2_exec_viscosity(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm, const void* n2);
 MHH_API int mhh_diff_smag2_exec(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm);
 MHH_API int mhh_diff_smag2_get_dn(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm, double dt, double* dn);
+
+/* ---- Diff_tke2<TF> (src/diff_tke2.cxx; the surface model is mandatory, :557):
+ *   create          cold start: sgstke = max(sgstke, Constants::sgstke_min) + cyclic fill (:641-660)
+ *   exec_viscosity  strain^2, evisc (and eviscs) from sgstke, and the buoyancy / dissipation / shear sources added to the
+ *                   tendency of sgstke, fused into one kernel (:799-983); n2 as in mhh_diff_smag2_exec_viscosity
+ *   exec            diff_u / diff_v / diff_w with evisc; diff_c with tPr = 1: sgstke with evisc, the other scalars with
+ *                   eviscs when there is buoyancy (:676-797)
+ *   get_dn          calc_dnmul on eviscs (buoyancy) or evisc, tPr = 1 (:611-638)
+ * and Limiter<TF>::exec's tendency_limiter on one (tendency, field) pair (src/limiter.cxx:35-59, 117-129; for sgstke:
+ * min_value = Constants::sgstke_min = 1e-7).
+ * mhh_dycore_set_tke2 registers the closure (a copy of the struct) for the fused sub-steps with prm->swdiff = 3, which then
+ * run exec_viscosity, exec and the limiter on sgstke where Model::exec does (src/model.cxx:376, 414, 440); NULL unregisters. */
+MHH_API int mhh_diff_tke2_create(mhh_ctx* ctx, void* sgstke);
+MHH_API int mhh_diff_tke2_exec_viscosity(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm, const mhh_tke2* tke, const void* n2);
+MHH_API int mhh_diff_tke2_exec(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm, const mhh_tke2* tke);
+MHH_API int mhh_diff_tke2_get_dn(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm, const mhh_tke2* tke, double dt, double* dn);
+MHH_API int mhh_limiter_exec(mhh_ctx* ctx, void* at, const void* a, double min_value, double sub_dt);
+MHH_API int mhh_dycore_set_tke2(mhh_ctx* ctx, const mhh_tke2* tke);
 
 /* ---- Diff_2<TF>::exec / get_dn  (src/diff_2.cxx:133-190): nu * laplacian on u, v, w and every scalar ---- */
 MHH_API int mhh_diff_2_exec(mhh_ctx* ctx, const mhh_fields* f);

@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmhhb200.so")
+# MHH_LIB: another build of the same library (A/B measurements of compile-time switches, tools/gpu_*.sh)
+LIB_PATH = os.environ.get("MHH_LIB") or os.path.join(_HERE, "lib", "libmhhb200.so")
 
 MHH_F64, MHH_F32 = 0, 1
 MHH_MAX_SCALARS = 8
@@ -54,6 +55,12 @@ class ForcingC(C.Structure):
                 ("swlspres", C.c_int), ("uflux", C.c_double), ("dpdx", C.c_double), ("fc", C.c_double),
                 ("ug", C.c_void_p), ("vg", C.c_void_p), ("utrans", C.c_double), ("vtrans", C.c_double),
                 ("ls_s", _SA), ("wls", C.c_void_p)]
+
+
+class Tke2C(C.Structure):
+    _fields_ = [("isgstke", C.c_int), ("eviscs", C.c_void_p),
+                ("ap", C.c_double), ("cf", C.c_double), ("ce1", C.c_double), ("ce2", C.c_double),
+                ("cm", C.c_double), ("ch1", C.c_double), ("ch2", C.c_double), ("cn", C.c_double)]
 
 
 class SurfaceC(C.Structure):
@@ -110,6 +117,12 @@ SIGNATURES = {
     "mhh_diff_smag2_exec_viscosity": (C.c_int, [_vp, _PF, _PP, _vp]),
     "mhh_diff_smag2_exec": (C.c_int, [_vp, _PF, _PP]),
     "mhh_diff_smag2_get_dn": (C.c_int, [_vp, _PF, _PP, C.c_double, C.POINTER(C.c_double)]),
+    "mhh_diff_tke2_create": (C.c_int, [_vp, _vp]),
+    "mhh_diff_tke2_exec_viscosity": (C.c_int, [_vp, _PF, _PP, C.POINTER(Tke2C), _vp]),
+    "mhh_diff_tke2_exec": (C.c_int, [_vp, _PF, _PP, C.POINTER(Tke2C)]),
+    "mhh_diff_tke2_get_dn": (C.c_int, [_vp, _PF, _PP, C.POINTER(Tke2C), C.c_double, C.POINTER(C.c_double)]),
+    "mhh_limiter_exec": (C.c_int, [_vp, _vp, _vp, C.c_double, C.c_double]),
+    "mhh_dycore_set_tke2": (C.c_int, [_vp, C.POINTER(Tke2C)]),
     "mhh_diff_2_exec": (C.c_int, [_vp, _PF]),
     "mhh_diff_4_exec": (C.c_int, [_vp, _PF]),
     "mhh_diff_2_get_dn": (C.c_int, [_vp, _PF, C.c_double, C.POINTER(C.c_double)]),

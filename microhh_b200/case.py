@@ -68,7 +68,7 @@ def _get_sub(ini, sec, key, sub, default=None, conv=str):
 _MBC = {"noslip": capi.BC_DIRICHLET, "freeslip": capi.BC_NEUMANN, "neumann": capi.BC_NEUMANN}
 _SBC = {"dirichlet": capi.BC_DIRICHLET, "neumann": capi.BC_NEUMANN, "flux": capi.BC_NEUMANN}
 _SWADVEC = {"2": 2, "2i5": 25, "4": 4, "4m": 41}
-_SWDIFF = {"smag2": 1, "2": 2, "4": 4}
+_SWDIFF = {"smag2": 1, "2": 2, "tke2": 3, "4": 4}
 
 
 class CaseConfig:
@@ -100,6 +100,8 @@ class CaseConfig:
         self.mbctop = _get(ini, "boundary", "mbctop")
         sl = _get(ini, "fields", "slist", "")
         self.scalars = (["th"] if self.swthermo == "dry" else []) + [x.strip() for x in sl.split(",") if x.strip()]
+        if self.swdiff == "tke2":
+            self.scalars.append("sgstke")       # Diff_tke2's constructor adds the prognostic SGS TKE (src/diff_tke2.cxx:544)
         # per scalar, `key[name]` before `key` (src/boundary.cxx:234-235, src/fields.cxx:412); required when there are scalars
         self.sbcbot = {n: _get_sub(ini, "boundary", "sbcbot", n) for n in self.scalars}
         self.sbctop = {n: _get_sub(ini, "boundary", "sbctop", n) for n in self.scalars}
@@ -132,6 +134,8 @@ class CaseConfig:
             bad.append(f"swthermo={self.swthermo}")
         if self.order == "4" and (self.swadvec not in ("4", "4m") or (self.swdiff, self.swpres) != ("4", "4")) and not bad:
             bad.append("4th-order grid with mixed schemes")
+        if self.swdiff == "tke2" and (self.order != "2" or self.swboundary == "default"):
+            bad.append("swdiff=tke2 needs a 2nd-order grid and a surface model (src/diff_tke2.cxx:555-558)")
         if self.order == "4" and self.swthermo != "0":
             bad.append("4th-order grid with thermo")
         if self.mbcbot not in _MBC or self.mbctop not in _MBC:

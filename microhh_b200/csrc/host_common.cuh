@@ -23,6 +23,7 @@
 #include "slab_kernels.cuh"
 #include "surface_kernels.cuh"
 #include "forcing_kernels.cuh"
+#include "tke2_kernels.cuh"
 #include "order2_kernels.cuh"
 #include "order4_kernels.cuh"
 #include "pres4_kernels.cuh"
@@ -54,6 +55,7 @@ struct mhh_ctx
     bool no_tma = false;        // MHH_NO_TMA=1: keep the cp.async tile kernels (A/B comparisons)
     int tile3_y = 0;            // MHH_TILE3_Y: rows per CTA of the warp-specialised kernel; 0 = 3 rows with the scalar group (13 warps), 4 without
     bool fuse_scalar = true;    // MHH_FUSE_SCALAR=0: keep scalar 0 out of the momentum kernel (A/B comparisons)
+    bool fuse_advec2 = true;    // MHH_FUSE_ADVEC2=0: Advec_2 + Diff_smag2 as two point-wise kernels instead of the fused TMA kernel (A/B switch)
     bool stream_vec2 = true;    // MHH_STREAM_VEC2=0: one cell per thread in rk3 / pres_out_rk3 (A/B switch)
     bool evisc_tma = true;      // MHH_EVISC_TMA=0: keep the cp.async eddy-viscosity kernel (A/B switch)
     int evisc3_npl = 0;         // MHH_EVISC3_NPL=1|2: points per lane of the TMA eddy-viscosity kernel (tile 32 or 64 wide; 0: 1 for fp64, 2 for fp32)
@@ -69,6 +71,8 @@ struct mhh_ctx
     ncclComm_t comm = nullptr;
     // Buffer / Force registered for the fused sub-steps (mhh_dycore_set_forcing)
     mhh_forcing forcing{}; bool forcing_set = false;
+    // Diff_tke2 registered for the fused sub-steps (mhh_dycore_set_tke2)
+    mhh_tke2 tke2{}; bool tke2_set = false;
     virtual ~mhh_ctx() {}
 };
 
@@ -209,11 +213,17 @@ template <typename TF> int force_exec_impl(Ctx<TF>* c, const mhh_fields* f, cons
 // host_tend.cu
 template <typename TF> int check_mom(Ctx<TF>* c, const mhh_fields* f, bool need_evisc, bool surface);
 template <typename TF> int evisc_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, const TF* n2);
-template <typename TF> int tend_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, bool adv, bool diff, bool buoy);
+// adv2: Advec_2's fluxes inside the fused TMA kernel; returns MHH_NOT_FUSED (nothing launched) when that variant does not apply
+#define MHH_NOT_FUSED 1
+template <typename TF> int tend_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, bool adv, bool diff, bool buoy, const mhh_tke2* tke = nullptr, bool adv2 = false);
 template <typename TF> int o2_impl(Ctx<TF>* c, const mhh_fields* f, bool adv, bool diff, bool buoy);
 template <typename TF> int o4_impl(Ctx<TF>* c, const mhh_fields* f, int adv_sw, bool diff);
 template <typename TF> int o2_cfl_impl(Ctx<TF>* c, const mhh_fields* f, double* out, int order);
 template <typename TF> int reduce_mode_impl(Ctx<TF>* c, int mode, const TF* u, const TF* v, const TF* w, TF p0, TF p1, TF p2, double* out);
+// host_tke2.cu
+template <typename TF> int tke2_check(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, const mhh_tke2* tke);
+template <typename TF> int tke2_visc_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, const mhh_tke2* tke, const TF* n2);
+template <typename TF> int limiter_impl(Ctx<TF>* c, TF* at, const TF* a, TF min_value, TF sub_dt);
 // host_pres.cu
 template <typename TF> int pres_create(Ctx<TF>* c);
 template <typename TF> int pres_set_values(Ctx<TF>* c);

@@ -74,6 +74,7 @@ int create_impl(const mhh_grid_desc* d, int dtype, int device, mhh_ctx** out)
     { const char* e = getenv("MHH_FORCE_PLAIN"); c->force_plain = e && e[0] == '1'; }
     { const char* e = getenv("MHH_NO_TMA"); c->no_tma = e && e[0] == '1'; }
     { const char* e = getenv("MHH_FUSE_SCALAR"); if (e) c->fuse_scalar = e[0] == '1'; }
+    { const char* e = getenv("MHH_FUSE_ADVEC2"); if (e) c->fuse_advec2 = e[0] == '1'; }
     { const char* e = getenv("MHH_TILE3_Y"); if (e) { int v = atoi(e); if (v == 3 || v == 4 || v == 5) c->tile3_y = v; } }
     { const char* e = getenv("MHH_EVISC_MB"); if (e) c->evisc_mb = atoi(e); }
     { const char* e = getenv("MHH_EVISC_TMA"); if (e) c->evisc_tma = atoi(e) != 0; }
@@ -446,11 +447,16 @@ int substep_check(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, bool& 
         o4 = true;
         return MHH_OK;
     }
-    if ((prm->swadvec != 25 && prm->swadvec != 2) || (prm->swdiff != 1 && prm->swdiff != 2))
-    { c->err = "dycore_substep: swadvec must be 2i5 (25), 2, 4 or 4m (41), swdiff smag2 (1), 2 or 4"; return MHH_E_INVALID; }
-    const bool smag = prm->swdiff == 1;
+    if ((prm->swadvec != 25 && prm->swadvec != 2) || (prm->swdiff != 1 && prm->swdiff != 2 && prm->swdiff != 3))
+    { c->err = "dycore_substep: swadvec must be 2i5 (25), 2, 4 or 4m (41), swdiff smag2 (1), 2, tke2 (3) or 4"; return MHH_E_INVALID; }
+    const bool smag = prm->swdiff == 1 || prm->swdiff == 3;
     int rc = check_mom<TF>(c, f, smag, smag && prm->surface_model != 0);
     if (rc != MHH_OK) return rc;
+    if (prm->swdiff == 3)
+    {
+        if (!c->tke2_set) { c->err = "dycore_substep: swdiff = tke2 needs mhh_dycore_set_tke2"; return MHH_E_INVALID; }
+        if ((rc = tke2_check<TF>(c, f, prm, &c->tke2)) != MHH_OK) return rc;
+    }
     NEED(c, f->p, "p");
     return MHH_OK;
 }
@@ -482,6 +488,7 @@ int substep_pre_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm)
     if ((rc = ghost_all_impl<TF>(c, f, prm)) != MHH_OK) return rc;
     // 2. diff.exec_viscosity
     if (prm->swdiff == 1 && (rc = evisc_impl<TF>(c, f, prm, nullptr)) != MHH_OK) return rc;
+    if (prm->swdiff == 3 && (rc = tke2_visc_impl<TF>(c, f, prm, &c->tke2, nullptr)) != MHH_OK) return rc;
     return MHH_OK;
 }
 
@@ -493,13 +500,20 @@ int tendencies_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm)
     int rc = substep_check<TF>(c, f, prm, o4);
     if (rc != MHH_OK) return rc;
     if (o4) { c->err = "dycore_tendencies: use mhh_advec_exec / mhh_diff_4_exec on a 4th-order grid (they see different w ghost cells)"; return MHH_E_INVALID; }
-    const bool smag = prm->swdiff == 1, adv5 = prm->swadvec == 25, buoy = prm->swthermo == 1;
-    if (adv5 && smag) rc = tend_impl<TF>(c, f, prm, true, true, buoy);                       // 2i5 + smag2 (+ buoyancy)
+    const bool smag = prm->swdiff == 1 || prm->swdiff == 3, adv5 = prm->swadvec == 25, buoy = prm->swthermo == 1;
+    const mhh_tke2* tke = prm->swdiff == 3 ? &c->tke2 : nullptr;                             // Diff_tke2::exec = the smag2 kernels, evisc per scalar
+    if (adv5 && smag) rc = tend_impl<TF>(c, f, prm, true, true, buoy, tke);                  // 2i5 + smag2 | tke2 (+ buoyancy)
     else if (!adv5 && !smag) rc = o2_impl<TF>(c, f, true, true, buoy);                       // 2 + 2 (+ buoyancy)
     else if (!adv5)                                                                          // 2 + smag2 (drycblles as shipped)
     {
-        if ((rc = o2_impl<TF>(c, f, true, false, buoy)) != MHH_OK) return rc;
-        rc = tend_impl<TF>(c, f, prm, false, true, false);
+        // one fused TMA-staged kernel when it applies (igc >= 3, at most the one scalar that rides along) ...
+        rc = c->fuse_advec2 ? tend_impl<TF>(c, f, prm, true, true, buoy, tke, true) : MHH_NOT_FUSED;
+        if (rc == MHH_NOT_FUSED)
+        {
+            // ... else Advec_2 point-wise, then the diffusion alone
+            if ((rc = o2_impl<TF>(c, f, true, false, buoy)) != MHH_OK) return rc;
+            rc = tend_impl<TF>(c, f, prm, false, true, false, tke);
+        }
     }
     else                                                                                     // 2i5 + 2
     {
@@ -523,6 +537,14 @@ int substep_post_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, in
         const double cBf[3] = {1. / 3., 15. / 16., 8. / 15.};
         if ((rc = buffer_exec_impl<TF>(c, f, &c->forcing)) != MHH_OK) return rc;
         if ((rc = force_exec_impl<TF>(c, f, &c->forcing, cBf[substep] * dt)) != MHH_OK) return rc;
+    }
+    // limiter.exec on sgstke: the reference applies it "as the last tendency", after pres.exec (src/model.cxx:439-440); the
+    // pressure solve neither reads nor writes a scalar tendency, so it runs here, ahead of the forked scalar update
+    if (prm->swdiff == 3)
+    {
+        const double cBl[3] = {1. / 3., 15. / 16., 8. / 15.};
+        const int n = c->tke2.isgstke;
+        if ((rc = limiter_impl<TF>(c, P<TF>(f->st[n]), P<TF>(f->s[n]), TF(MHH_SGSTKE_MIN), (TF)(cBl[substep] * dt))) != MHH_OK) return rc;
     }
     // 4. pres.exec (solve), then pressure correction fused with timeloop.exec
     const TF cA[3] = {TF(0.), TF(-5. / 9.), TF(-153. / 128.)};

@@ -153,7 +153,7 @@ MomArgs<TF> mom_args(const mhh_fields* f)
 }
 
 template <typename TF>
-ScalArgs<TF> scal_args(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, int n)
+ScalArgs<TF> scal_args(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, int n, const mhh_tke2* tke = nullptr)
 {
     const GridDev<TF>& g = c->g;
     ScalArgs<TF> a{};
@@ -163,6 +163,13 @@ ScalArgs<TF> scal_args(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, i
     a.fluxbot = P<TF>(f->s_fluxbot[n]); a.fluxtop = P<TF>(f->s_fluxtop[n]);
     a.visc = (TF)f->svisc[n];
     a.tPr = prm ? (TF)prm->tPr : TF(1);
+    if (tke)
+    {
+        // Diff_tke2::exec (src/diff_tke2.cxx:733-789): tPr_dummy = 1; sgstke diffuses with the eddy viscosity for momentum,
+        // every other scalar with the one for heat when there is buoyancy
+        a.tPr = TF(1);
+        if (n != tke->isgstke && prm && prm->swthermo != 0) a.evisc = P<TF>(tke->eviscs);
+    }
     // 1./(dx*dx) is formed in double in the reference and narrowed to TF (src/diff_smag2.cxx:445)
     a.dxidxi = (TF)(1. / ((double)g.dx * (double)g.dx));
     a.dyidyi = (TF)(1. / ((double)g.dy * (double)g.dy));
@@ -271,11 +278,11 @@ int mom_tile_launch(Ctx<TF>* c, const MomArgs<TF>& a, bool surface, bool buoy)
 
 // warp-specialised variant (tile3_kernels.cuh): one CTA of (3+nsc)*ty+1 warps per SM; the first scalar rides along
 template <typename TF>
-int mom3_launch(Ctx<TF>* c, const MomArgs<TF>& a, const ScalArgs<TF>* sc, bool surface, bool buoy, int hl)
+int mom3_launch(Ctx<TF>* c, const MomArgs<TF>& a, const ScalArgs<TF>* sc, bool surface, bool buoy, int hl, bool adv2 = false)
 {
     const GridDev<TF>& g = c->g;
     const int nsc = sc ? 1 : 0;
-    const int ty = c->tile3_y ? c->tile3_y : (nsc ? 3 : 4);
+    const int ty = (c->tile3_y && !adv2) ? c->tile3_y : (nsc ? 3 : 4);       // the Advec_2 variant exists for the default tile heights
     const int ntx = (g.imax + T2_W - 1) / T2_W, nty = (g.jmax + ty - 1) / ty;
     Tend3Args<TF> t{};
     t.m = a; if (sc) t.sc = *sc;
@@ -292,13 +299,15 @@ int mom3_launch(Ctx<TF>* c, const MomArgs<TF>& a, const ScalArgs<TF>* sc, bool s
         !make_field_tmap<TF>(&tut, a.ut, g, px, ty) || !make_field_tmap<TF>(&tvt, a.vt, g, px, ty) ||
         !make_field_tmap<TF>(&twt, a.wt, g, px, ty) || !make_field_tmap<TF>(&tst, sc ? (const void*)sc->st : (const void*)a.ut, g, px, ty))
     { c->err = "cuTensorMapEncodeTiled failed"; return MHH_E_CUDA; }
-#define M3(S, B, N, Y, H) do { \
+#define M3A(S, B, N, Y, H, A) do { \
         static size_t attr_smem_dev[64] = {0}; size_t& attr_smem = attr_smem_dev[c->device & 63];   /* the attribute is per device */ \
-        if (attr_smem < smem) { CUDA_TRY(c, cudaFuncSetAttribute(mom3_kernel<TF, S, B, N, Y, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; } \
-        mom3_kernel<TF, S, B, N, Y, H><<<grid, 32 * ((3 + N) * Y + 1), smem, c->stream>>>(tu, tv, tw, te, ts, tut, tvt, twt, tst, t, g); } while (0)
+        if (attr_smem < smem) { CUDA_TRY(c, cudaFuncSetAttribute(mom3_kernel<TF, S, B, N, Y, H, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; } \
+        mom3_kernel<TF, S, B, N, Y, H, A><<<grid, 32 * ((3 + N) * Y + 1), smem, c->stream>>>(tu, tv, tw, te, ts, tut, tvt, twt, tst, t, g); } while (0)
+#define M3(S, B, N, Y, H) M3A(S, B, N, Y, H, false)
     // the odd-aligned variant (halo 3) exists for fp64 only
 #define M3H(S, B, N, Y) do { if (hl == 4) M3(S, B, N, Y, 4); else if (sizeof(TF) == 8) M3(S, B, N, Y, (sizeof(TF) == 8 ? 3 : 4)); } while (0)
-#define M3Y(S, B, N) do { if (ty == 3) M3H(S, B, N, 3); else if (ty == 5) M3H(S, B, N, 5); else M3H(S, B, N, 4); } while (0)
+#define M3Y(S, B, N) do { if (adv2) { if (hl == 4) M3A(S, B, N, (N ? 3 : 4), 4, true); else if (sizeof(TF) == 8) M3A(S, B, N, (N ? 3 : 4), (sizeof(TF) == 8 ? 3 : 4), true); } \
+                          else if (ty == 3) M3H(S, B, N, 3); else if (ty == 5) M3H(S, B, N, 5); else M3H(S, B, N, 4); } while (0)
     if (nsc)
     {
         if (surface && buoy) M3Y(true, true, 1);
@@ -316,7 +325,8 @@ int mom3_launch(Ctx<TF>* c, const MomArgs<TF>& a, const ScalArgs<TF>* sc, bool s
 #undef M3Y
 #undef M3H
 #undef M3
-    KCHECKN(c, "mom3_kernel");
+#undef M3A
+    if (adv2) KCHECKN(c, "mom3_kernel_advec2"); else KCHECKN(c, "mom3_kernel");
     return MHH_OK;
 }
 
@@ -345,11 +355,26 @@ int scal_tile_launch(Ctx<TF>* c, const ScalArgs<TF>& a, bool surface)
 
 // tendencies: adv / diff / buoyancy in any combination (templates keep the unused parts out)
 template <typename TF>
-int tend_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, bool adv, bool diff, bool buoy)
+int tend_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, bool adv, bool diff, bool buoy, const mhh_tke2* tke, bool adv2)
 {
     NEED_BASE(c);
     const GridDev<TF>& g = c->g;
-    const bool surface = diff && prm && prm->surface_model;
+    if (!diff) tke = nullptr;
+    if (adv2)
+    {
+        // Advec_2 + Diff_smag2 | Diff_tke2 fused (cases/drycblles as shipped): only the TMA-staged kernel has the variant, and only
+        // the scalar that rides along in it is covered; MHH_NOT_FUSED tells the caller to run the two schemes separately
+        const int hl2 = t2_pick_hl(g.igc, (int)sizeof(TF));
+        bool ok = adv && diff && !c->force_plain && !c->no_tma && c->fuse_scalar && hl2 != 0 && g.igc >= TILE_H && g.jgc >= TILE_H && f->ns <= 1
+                  && tma_ok<TF>(g, {f->u, f->v, f->w, f->evisc, f->ut, f->vt, f->wt, (buoy && f->ns > 0) ? (const void*)f->s[0] : (const void*)f->u});
+        if (ok && f->ns == 1)
+        {
+            const ScalArgs<TF> s0 = scal_args<TF>(c, f, prm, 0, tke);
+            ok = !f->s_fluxlimit[0] && tma_ok<TF>(g, {s0.s, s0.st}) && s0.evisc == P<TF>(f->evisc);
+        }
+        if (!ok) return MHH_NOT_FUSED;
+    }
+    const bool surface = diff && prm && (prm->surface_model || tke);
     int rc = check_mom<TF>(c, f, diff, surface);
     if (rc != MHH_OK) return rc;
     if (adv && (g.igc < 3 || g.jgc < 3)) { c->err = "advec_2i5 needs igc, jgc >= 3"; return MHH_E_INVALID; }
@@ -372,8 +397,10 @@ int tend_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, bool adv, 
             ScalArgs<TF> s0{};
             // measured on B200 fp64 (512^3): 5.8 ms fused (3 rows, 13 warps) vs 4.3 + 2.9 ms as two kernels
             bool fuse = f->ns > 0 && c->fuse_scalar && !f->s_fluxlimit[0];
-            if (fuse) { s0 = scal_args<TF>(c, f, prm, 0); fuse = tma_ok<TF>(g, {s0.s, s0.st}); }
-            rc = mom3_launch<TF>(c, a, fuse ? &s0 : nullptr, surface, buoy, hl);
+            // (the fused scalar group reads the momentum kernel's evisc planes: with Diff_tke2 only a scalar that diffuses
+            // with evisc qualifies)
+            if (fuse) { s0 = scal_args<TF>(c, f, prm, 0, tke); fuse = tma_ok<TF>(g, {s0.s, s0.st}) && s0.evisc == a.evisc; }
+            rc = mom3_launch<TF>(c, a, fuse ? &s0 : nullptr, surface, buoy, hl, adv2);
             if (fuse) first_scalar = 1;
         }
         else rc = mom_tile_launch<TF>(c, a, surface, buoy);
@@ -391,7 +418,7 @@ int tend_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, bool adv, 
     if (!tiles) KCHECKN(c, "tend_uvw_kernel");
     for (int n = first_scalar; n < f->ns; ++n)
     {
-        const ScalArgs<TF> s = scal_args<TF>(c, f, prm, n);
+        const ScalArgs<TF> s = scal_args<TF>(c, f, prm, n, tke);
         if (adv && f->s_fluxlimit[n])
         {
             // `fluxlimit_list` scalar (src/advec_2i5.cxx:1046-1056): Koren-limited advection, then the diffusion alone
@@ -570,7 +597,7 @@ int reduce_mode_impl(Ctx<TF>* c, int mode, const TF* u, const TF* v, const TF* w
 #define INST(TF) \
     template int check_mom<TF>(Ctx<TF>*, const mhh_fields*, bool, bool); \
     template int evisc_impl<TF>(Ctx<TF>*, const mhh_fields*, const mhh_params*, const TF*); \
-    template int tend_impl<TF>(Ctx<TF>*, const mhh_fields*, const mhh_params*, bool, bool, bool); \
+    template int tend_impl<TF>(Ctx<TF>*, const mhh_fields*, const mhh_params*, bool, bool, bool, const mhh_tke2*, bool); \
     template int o2_impl<TF>(Ctx<TF>*, const mhh_fields*, bool, bool, bool); template int o4_impl<TF>(Ctx<TF>*, const mhh_fields*, int, bool); \
     template int o2_cfl_impl<TF>(Ctx<TF>*, const mhh_fields*, double*, int); \
     template int reduce_mode_impl<TF>(Ctx<TF>*, int, const TF*, const TF*, const TF*, TF, TF, TF, double*);

@@ -41,7 +41,9 @@ struct Tend3Args
 // are half as large, and two CTAs (26 warps) hide more latency than the few spills of a 72-register cap cost
 template <typename TF> constexpr int mom3_min_blocks() { return sizeof(TF) == 4 ? 2 : 1; }
 
-template <typename TF, bool SURFACE, bool BUOY, int NSC, int TY, int HL>
+// ADV2: the advective fluxes of Advec_2 (src/advec_2.cxx:48-202: velocity * interp2 on every face) instead of Advec_2i5's --
+// cases/drycblles as shipped (swadvec = 2 with smag2) on the same staged planes.
+template <typename TF, bool SURFACE, bool BUOY, int NSC, int TY, int HL, bool ADV2 = false>
 __global__ void __launch_bounds__(32 * ((3 + NSC) * TY + 1), mom3_min_blocks<TF>())
 mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_v,
             const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_e,
@@ -147,6 +149,10 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
     }
 
     // ================================================================== consumer warps
+    auto hflux = [](const TF vel, const TF x0, const TF x1, const TF x2, const TF x3, const TF x4, const TF x5) -> TF {
+        return ADV2 ? flux2(vel, x2, x3) : flux65(vel, x0, x1, x2, x3, x4, x5); };
+    auto vfl = [](const int order, const TF vel, const TF c0, const TF c1, const TF c2, const TF c3, const TF c4, const TF c5) -> TF {
+        return vflux_col<TF>(ADV2 ? min(order, 2) : order, vel, c0, c1, c2, c3, c4, c5); };
     auto colload = [&](const TF* __restrict__ fld, int lev, int c) -> TF {
         return (lev >= 0 && lev < g.kcells) ? fld[ij + c + (long long)lev * kk] : TF(0);
     };
@@ -222,7 +228,7 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
 #pragma unroll
             for (int m = 0; m < 3; ++m)
             {
-                fx[m] = flux65(interp2(X10(ux, m - 1), X10(ux, m)), X10(ux, m - 3), X10(ux, m - 2), X10(ux, m - 1), X10(ux, m), X10(ux, m + 1), X10(ux, m + 2));
+                fx[m] = hflux(interp2(X10(ux, m - 1), X10(ux, m)), X10(ux, m - 3), X10(ux, m - 2), X10(ux, m - 1), X10(ux, m), X10(ux, m + 1), X10(ux, m + 2));
                 dx_[m] = (X6(e0, m - 1) + visc) * (X10(ux, m) - X10(ux, m - 1)) * dxi;
             }
             TF gt[2];
@@ -230,7 +236,7 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
             for (int c = 0; c < 2; ++c)
             {
                 const TF uk = X10(ux, c), uk1 = U1R[c];
-                const TF ft_a = rhoh_f * vflux_col<TF>(of, interp2(X6(w6, c - 1), X6(w6, c)), ua[c], ub[c], uk, uk1, uc[c], ud[c]);
+                const TF ft_a = rhoh_f * vfl(of, interp2(X6(w6, c - 1), X6(w6, c)), ua[c], ub[c], uk, uk1, uc[c], ud[c]);
                 TF ft_d;
                 if (SURFACE && f == ks) ft_d = -rhoh_f * a.u_fluxbot[ij + c];
                 else if (SURFACE && f == ke) ft_d = -rhoh_f * a.u_fluxtop[ij + c];
@@ -249,8 +255,8 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
 #pragma unroll
                 for (int c = 0; c < 2; ++c)
                 {
-                    const TF fn = flux65(interp2(X6(vp6, c - 1), X6(vp6, c)), uy[1][c], uy[2][c], uy[3][c], uy[4][c], uy[5][c], uy[6][c]);
-                    const TF fs = flux65(interp2(X6(v6, c - 1), X6(v6, c)), uy[0][c], uy[1][c], uy[2][c], uy[3][c], uy[4][c], uy[5][c]);
+                    const TF fn = hflux(interp2(X6(vp6, c - 1), X6(vp6, c)), uy[1][c], uy[2][c], uy[3][c], uy[4][c], uy[5][c], uy[6][c]);
+                    const TF fs = hflux(interp2(X6(v6, c - 1), X6(v6, c)), uy[0][c], uy[1][c], uy[2][c], uy[3][c], uy[4][c], uy[5][c]);
                     const TF eviscn = q * (s0r[c] + s0p[c]) + visc;
                     const TF eviscs = q * (s0m[c] + s0r[c]) + visc;
                     const TF d = (dx_[c + 1] - dx_[c]) * TF(2.) * dxi
@@ -298,7 +304,7 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
             for (int c = 0; c < 2; ++c)
             {
                 const TF vk = X10(vx, c), vk1 = V1R[c];
-                const TF ft_a = rhoh_f * vflux_col<TF>(of, interp2(W1M[c], W1R[c]), va[c], vb[c], vk, vk1, vc[c], vd[c]);
+                const TF ft_a = rhoh_f * vfl(of, interp2(W1M[c], W1R[c]), va[c], vb[c], vk, vk1, vc[c], vd[c]);
                 TF ft_d;
                 if (SURFACE && f == ks) ft_d = -rhoh_f * a.v_fluxbot[ij + c];
                 else if (SURFACE && f == ke) ft_d = -rhoh_f * a.v_fluxtop[ij + c];
@@ -318,15 +324,15 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
 #pragma unroll
                 for (int m = 0; m < 3; ++m)
                 {
-                    fx[m] = flux65(interp2(X4(um4, m), X4(u4, m)), X10(vx, m - 3), X10(vx, m - 2), X10(vx, m - 1), X10(vx, m), X10(vx, m + 1), X10(vx, m + 2));
+                    fx[m] = hflux(interp2(X4(um4, m), X4(u4, m)), X10(vx, m - 3), X10(vx, m - 2), X10(vx, m - 1), X10(vx, m), X10(vx, m + 1), X10(vx, m + 2));
                     const TF eviscc = q * (s0m[m] + s0r[m]) + visc;
                     dx_[m] = eviscc * ((X10(vx, m) - X10(vx, m - 1)) * dxi + (X4(u4, m) - X4(um4, m)) * dyi);
                 }
 #pragma unroll
                 for (int c = 0; c < 2; ++c)
                 {
-                    const TF fn = flux65(interp2(vy[3][c], vy[4][c]), vy[1][c], vy[2][c], vy[3][c], vy[4][c], vy[5][c], vy[6][c]);
-                    const TF fs = flux65(interp2(vy[2][c], vy[3][c]), vy[0][c], vy[1][c], vy[2][c], vy[3][c], vy[4][c], vy[5][c]);
+                    const TF fn = hflux(interp2(vy[3][c], vy[4][c]), vy[1][c], vy[2][c], vy[3][c], vy[4][c], vy[5][c], vy[6][c]);
+                    const TF fs = hflux(interp2(vy[2][c], vy[3][c]), vy[0][c], vy[1][c], vy[2][c], vy[3][c], vy[4][c], vy[5][c]);
                     const TF d = (dx_[c + 1] - dx_[c]) * dxi
                                + ((X6(e0, c) + visc) * (vy[4][c] - vy[3][c]) * dyi - (X6(em, c) + visc) * (vy[3][c] - vy[2][c]) * dyi) * TF(2.) * dyi;
                     const TF tv = -(fx[c + 1] - fx[c]) * dxi - (fn - fs) * dyi + d + (gt[c] - gv[c]) * rdzi_k;
@@ -372,7 +378,7 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
             for (int c = 0; c < 2; ++c)
             {
                 const TF sk = X10(sx, c), sk1 = S1R[c];
-                const TF ft_a = rhoh_f * vflux_col<TF>(of, W1R[c], sa[c], sb[c], sk, sk1, sc[c], sd[c]);
+                const TF ft_a = rhoh_f * vfl(of, W1R[c], sa[c], sb[c], sk, sk1, sc[c], sd[c]);
                 TF ft_d;
                 if (SURFACE && f == ks) ft_d = -rhoh_f * sa_.fluxbot[ij + c];
                 else if (SURFACE && f == ke) ft_d = -rhoh_f * sa_.fluxtop[ij + c];
@@ -391,15 +397,15 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
 #pragma unroll
                 for (int m = 0; m < 3; ++m)
                 {
-                    fx[m] = flux65(X4(u4, m), X10(sx, m - 3), X10(sx, m - 2), X10(sx, m - 1), X10(sx, m), X10(sx, m + 1), X10(sx, m + 2));
+                    fx[m] = hflux(X4(u4, m), X10(sx, m - 3), X10(sx, m - 2), X10(sx, m - 1), X10(sx, m), X10(sx, m + 1), X10(sx, m + 2));
                     const TF eviscx = h * (X6(e0, m - 1) + X6(e0, m)) * tPr_i + svisc;
                     dx_[m] = eviscx * (X10(sx, m) - X10(sx, m - 1));
                 }
 #pragma unroll
                 for (int c = 0; c < 2; ++c)
                 {
-                    const TF fn = flux65(V0P[c], sy[1][c], sy[2][c], sy[3][c], sy[4][c], sy[5][c], sy[6][c]);
-                    const TF fs = flux65(V0R[c], sy[0][c], sy[1][c], sy[2][c], sy[3][c], sy[4][c], sy[5][c]);
+                    const TF fn = hflux(V0P[c], sy[1][c], sy[2][c], sy[3][c], sy[4][c], sy[5][c], sy[6][c]);
+                    const TF fs = hflux(V0R[c], sy[0][c], sy[1][c], sy[2][c], sy[3][c], sy[4][c], sy[5][c]);
                     const TF eviscn = h * (X6(e0, c) + EP0[c]) * tPr_i + svisc;
                     const TF eviscs = h * (EM0[c] + X6(e0, c)) * tPr_i + svisc;
                     const TF d = (dx_[c + 1] - dx_[c]) * sa_.dxidxi
@@ -453,7 +459,7 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
             for (int c = 0; c < 2; ++c)
             {
                 const TF wf = X10(wx, c);
-                const TF ft_a = rho_c * vflux_col<TF>(oc, interp2(wf, we[c]), wa[c], wb[c], wf, we[c], wc[c], wd[c]);
+                const TF ft_a = rho_c * vfl(oc, interp2(wf, we[c]), wa[c], wb[c], wf, we[c], wc[c], wd[c]);
                 const TF ft_d = rho_c * (E1R[c] + visc) * (we[c] - wf) * dzi_c;
                 gt[c] = TF(2.) * ft_d - ft_a;
             }
@@ -466,7 +472,7 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
 #pragma unroll
                 for (int m = 0; m < 3; ++m)
                 {
-                    fx[m] = flux65(interp2(X4(u4, m), X4(u14, m)), X10(wx, m - 3), X10(wx, m - 2), X10(wx, m - 1), X10(wx, m), X10(wx, m + 1), X10(wx, m + 2));
+                    fx[m] = hflux(interp2(X4(u4, m), X4(u14, m)), X10(wx, m - 3), X10(wx, m - 2), X10(wx, m - 1), X10(wx, m), X10(wx, m + 1), X10(wx, m + 2));
                     const TF eviscx = q * (s0r[m] + s1r[m]) + visc;
                     dx_[m] = eviscx * ((X10(wx, m) - X10(wx, m - 1)) * dxi + (X4(u14, m) - X4(u4, m)) * dzhi_f);
                 }
@@ -477,8 +483,8 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
 #pragma unroll
                 for (int c = 0; c < 2; ++c)
                 {
-                    const TF fn = flux65(interp2(V0P[c], V1P[c]), wy[1][c], wy[2][c], wy[3][c], wy[4][c], wy[5][c], wy[6][c]);
-                    const TF fs = flux65(interp2(V0R[c], V1R[c]), wy[0][c], wy[1][c], wy[2][c], wy[3][c], wy[4][c], wy[5][c]);
+                    const TF fn = hflux(interp2(V0P[c], V1P[c]), wy[1][c], wy[2][c], wy[3][c], wy[4][c], wy[5][c], wy[6][c]);
+                    const TF fs = hflux(interp2(V0R[c], V1R[c]), wy[0][c], wy[1][c], wy[2][c], wy[3][c], wy[4][c], wy[5][c]);
                     const TF eviscn = q * ((X6(e0, c) + X6(e16, c)) + (EP0[c] + EP1[c])) + visc;
                     const TF eviscs = q * ((EM0[c] + X6(e0, c)) + (EM1[c] + X6(e16, c))) + visc;
                     TF tw = -(fx[c + 1] - fx[c]) * dxi - (fn - fs) * dyi

@@ -14,7 +14,7 @@ from . import capi
 from .capi import FieldsC, ParamsC, GridDesc, SurfaceC, ForcingC, MhhError
 
 SWADVEC = {"2i5": 25, "2": 2, "4": 4, "4m": 41}
-SWDIFF = {"smag2": 1, "2": 2, "4": 4}
+SWDIFF = {"smag2": 1, "2": 2, "tke2": 3, "4": 4}
 
 
 def _ptr(t):
@@ -269,6 +269,55 @@ class Diff:
         out = C.c_double()
         self.ctx.check(self.ctx.lib.mhh_diff_smag2_get_dn(self.ctx.h, C.byref(fields.c), C.byref(self.prm), dt, C.byref(out)))
         return out.value
+
+
+class Diff_tke2:
+    """Diff_tke2<TF> (src/diff_tke2.cxx): Deardorff SGS-TKE closure.  `sgstke` is one of the prognostic scalars of `fields`;
+    the eddy viscosity for heat / scalars (`eviscs`) is owned here, like fields.sd["eviscs"] in the reference."""
+    DEFAULTS = dict(ap=1.5, cf=2.5, ce1=0.19, ce2=0.51, cm=0.12, ch1=1., ch2=2., cn=0.76)       # src/diff_tke2.cxx:525-532
+
+    def __init__(self, ctx, params, fields, sgstke="sgstke", **constants):
+        self.ctx = ctx; self.prm = params
+        self.eviscs = torch.zeros_like(fields["evisc"]) if params.swthermo != 0 else None
+        c = capi.Tke2C()
+        c.isgstke = fields.scalars.index(sgstke)
+        c.eviscs = _ptr(self.eviscs)
+        for k, v in {**self.DEFAULTS, **constants}.items():
+            setattr(c, k, v)
+        self.c = c
+
+    def create(self, fields):
+        """cold start: limit the initial field at Constants::sgstke_min (src/diff_tke2.cxx:641-660)"""
+        self.ctx.check(self.ctx.lib.mhh_diff_tke2_create(self.ctx.h, _ptr(fields[fields.scalars[self.c.isgstke]])))
+
+    def exec_viscosity(self, fields, n2=None):
+        self.ctx.check(self.ctx.lib.mhh_diff_tke2_exec_viscosity(self.ctx.h, C.byref(fields.c), C.byref(self.prm), C.byref(self.c), _ptr(n2)))
+
+    def exec(self, fields):
+        self.ctx.check(self.ctx.lib.mhh_diff_tke2_exec(self.ctx.h, C.byref(fields.c), C.byref(self.prm), C.byref(self.c)))
+
+    def get_dn(self, fields, dt):
+        out = C.c_double()
+        self.ctx.check(self.ctx.lib.mhh_diff_tke2_get_dn(self.ctx.h, C.byref(fields.c), C.byref(self.prm), C.byref(self.c), dt, C.byref(out)))
+        return out.value
+
+    def register(self):
+        """Run the closure inside the fused sub-steps of a Dycore with swdiff = "tke2" (mhh_dycore_set_tke2)."""
+        self.ctx.check(self.ctx.lib.mhh_dycore_set_tke2(self.ctx.h, C.byref(self.c)))
+
+    def unregister(self):
+        self.ctx.check(self.ctx.lib.mhh_dycore_set_tke2(self.ctx.h, None))
+
+
+class Limiter:
+    """Limiter<TF>::exec on one field (src/limiter.cxx:35-59, 117-129)."""
+    SGSTKE_MIN = 1.e-7
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    def exec(self, at, a, min_value, sub_dt):
+        self.ctx.check(self.ctx.lib.mhh_limiter_exec(self.ctx.h, _ptr(at), _ptr(a), min_value, sub_dt))
 
 
 class Diff_2:

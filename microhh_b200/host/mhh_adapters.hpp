@@ -282,6 +282,104 @@ namespace mhhb200
             double dnmax;
     };
 
+    // ---- Diff_tke2 (src/diff_tke2.cxx:514-983): Deardorff SGS-TKE closure.  Same constructor work as the reference (ini keys,
+    // the prognostic "sgstke", the diagnostics "evisc" / "eviscs"); the limiter on sgstke (Limiter<TF>::exec,
+    // src/limiter.cxx:117-129) is limiter_exec_b200 below.
+    template<typename TF>
+    class Diff_tke2_b200 : public Diff<TF>
+    {
+        public:
+            Diff_tke2_b200(Master& m, Grid<TF>& g, Fields<TF>& f, Boundary<TF>& b, Input& in, std::shared_ptr<Context<TF>> c) :
+                Diff<TF>(m, g, f, b, in), c(std::move(c))
+            {
+                // same .ini keys as src/diff_tke2.cxx:522-557
+                dnmax = in.get_item<double>("diff", "dnmax", "", 0.4);
+                tke.ap  = in.get_item<TF>("diff", "ap",  "", 1.5);  tke.cf  = in.get_item<TF>("diff", "cf",  "", 2.5);
+                tke.ce1 = in.get_item<TF>("diff", "ce1", "", 0.19); tke.ce2 = in.get_item<TF>("diff", "ce2", "", 0.51);
+                tke.cm  = in.get_item<TF>("diff", "cm",  "", 0.12); tke.ch1 = in.get_item<TF>("diff", "ch1", "", 1.);
+                tke.ch2 = in.get_item<TF>("diff", "ch2", "", 2.);   tke.cn  = in.get_item<TF>("diff", "cn",  "", 0.76);
+                prm.sw_mason = in.get_item<bool>("diff", "swmason", "", true);
+                sw_buoy = in.get_item<std::string>("thermo", "swthermo", "", "0") != "0";
+                prm.swadvec = 25; prm.swdiff = 3; prm.tPr = 1.; prm.surface_model = 1;
+                const std::string group_name = "sgstke";
+                f.init_prognostic_field("sgstke", "SGS TKE", "m2 s-2", group_name, g.get_grid_data().sloc, false);
+                f.sp.at("sgstke")->visc = in.get_item<TF>("fields", "svisc", "sgstke");
+                f.init_diagnostic_field("evisc", "Eddy viscosity for momentum", "m2 s-1", group_name, g.get_grid_data().sloc);
+                if (sw_buoy)
+                    f.init_diagnostic_field("eviscs", "Eddy viscosity for scalars", "m2 s-1", group_name, g.get_grid_data().sloc);
+                if (g.get_spatial_order() != Grid_order::Second)
+                    throw std::runtime_error("Diff_tke2 only runs with second order grids.");
+                if (b.get_switch() == "default")
+                    throw std::runtime_error("Diff_tke2 does not support resolved walls.");
+            }
+            Diffusion_type get_switch() const override { return Diffusion_type::Diff_tke2; }
+            void init() override {}
+            void create(Stats<TF>&, const bool cold_start) override
+            {
+                if (cold_start)
+                    MHH_CHECK(c->ctx, mhh_diff_tke2_create(c->ctx, this->fields.sp.at("sgstke")->fld_g));
+            }
+            // sgstke's position in the C ABI's scalar list follows fields_view's ordering
+            const mhh_tke2& closure(const mhh_fields& f)
+            {
+                tke.isgstke = -1;
+                const void* e = this->fields.sp.at("sgstke")->fld_g;
+                for (int n = 0; n < f.ns; ++n)
+                    if (f.s[n] == e) tke.isgstke = n;
+                tke.eviscs = nullptr;
+                if (sw_buoy) tke.eviscs = this->fields.sd.at("eviscs")->fld_g;
+                return tke;
+            }
+            void exec_viscosity(Stats<TF>&, Thermo<TF>& thermo) override
+            {
+                const Thermo_type sw = thermo.get_switch();
+                prm.swthermo = sw == Thermo_type::Disabled ? 0 : 1;
+                const mhh_fields f = fields_view(this->fields, &this->boundary);
+                if (sw == Thermo_type::Disabled || sw == Thermo_type::Dry)
+                    MHH_CHECK(c->ctx, mhh_diff_tke2_exec_viscosity(c->ctx, &f, &prm, &closure(f), nullptr));
+                else
+                {
+                    auto n2 = this->fields.get_tmp_g();
+                    thermo.get_thermo_field_g(*n2, "N2", false);
+                    const int rc = mhh_diff_tke2_exec_viscosity(c->ctx, &f, &prm, &closure(f), n2->fld_g);
+                    this->fields.release_tmp_g(n2);
+                    MHH_CHECK(c->ctx, rc);
+                }
+            }
+            void exec(Stats<TF>&) override
+            {
+                const mhh_fields f = fields_view(this->fields, &this->boundary);
+                MHH_CHECK(c->ctx, mhh_diff_tke2_exec(c->ctx, &f, &prm, &closure(f)));
+            }
+            void exec_stats(Stats<TF>&, Thermo<TF>&) override {}
+            void diff_flux(Field3d<TF>&, const Field3d<TF>&) override
+            { throw std::runtime_error("mhhb200: diff_flux is a statistics path (out of scope)"); }
+            double get_dn(double dt) override
+            {
+                const mhh_fields f = fields_view(this->fields, &this->boundary);
+                double dn = 0.;
+                MHH_CHECK(c->ctx, mhh_diff_tke2_get_dn(c->ctx, &f, &prm, &closure(f), dt, &dn));
+                return dn;
+            }
+            unsigned long get_time_limit(unsigned long idt, double dt) override
+            { return idt * dnmax / std::max(Constants::dsmall, get_dn(dt)); }         // src/diff_tke2.cxx:580-608
+            void prepare_device(Boundary<TF>&) override {}
+            void clear_device() override {}
+
+        private:
+            std::shared_ptr<Context<TF>> c;
+            mhh_params prm{};
+            mhh_tke2 tke{};
+            bool sw_buoy = false;
+            double dnmax;
+    };
+
+    // ---- Limiter<TF>::exec (src/limiter.cu, CPU: src/limiter.cxx:98-130) on one prognostic field; for Diff_tke2:
+    //   limiter_exec_b200(*b200, fields, "sgstke", Constants::sgstke_min<TF>, sub_dt)
+    template<typename TF>
+    void limiter_exec_b200(Context<TF>& c, Fields<TF>& fields, const std::string& name, const double min_value, const double sub_dt)
+    { MHH_CHECK(c.ctx, mhh_limiter_exec(c.ctx, fields.at.at(name)->fld_g, fields.ap.at(name)->fld_g, min_value, sub_dt)); }
+
     // ---- Diff_2 (src/diff_2.cxx:120-190) and Diff_4 (src/diff_4.cxx:200-310): ORDER = 2 | 4 --------------------
     template<typename TF, int ORDER>
     class Diff_const_b200 : public Diff<TF>

@@ -19,6 +19,9 @@ template class mhhb200::Advec_b200<double, 25, Advection_type::Advec_2i5>;
 template class mhhb200::Advec_b200<float, 2, Advection_type::Advec_2>;
 template class mhhb200::Advec_b200<double, 4, Advection_type::Advec_4>;
 template class mhhb200::Diff_smag2_b200<double>;
+template class mhhb200::Diff_tke2_b200<double>;
+template class mhhb200::Diff_tke2_b200<float>;
+template void mhhb200::limiter_exec_b200<double>(mhhb200::Context<double>&, Fields<double>&, const std::string&, double, double);
 template class mhhb200::Diff_const_b200<double, 2>;
 template class mhhb200::Diff_const_b200<float, 4>;
 template class mhhb200::Pres_b200<float, 2>;

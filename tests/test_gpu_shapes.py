@@ -69,7 +69,7 @@ def check_fp32_at_reference_level(g, f, case32, g64, c64, names):
 
 
 # ------------------------------------------------------------------------------------------------ LES configurations
-@pytest.mark.parametrize("swadvec,igc", [("2i5", 3), ("2i5", 4), ("2", 3)])
+@pytest.mark.parametrize("swadvec,igc", [("2i5", 3), ("2i5", 4), ("2", 3), ("2", 4)])
 def test_drycblles_128_fp64(swadvec, igc):
     """configs[0]: drycblles 128^3 fp64 (3200 m cube, dt = 6 s is the case's dtmax); `2` is the .ini as shipped; igc = 4 is what
     the adapters ask Grid for (aligned pairs in the TMA-staged kernel), igc = 3 the reference's minimum for advec_2i5."""
@@ -90,6 +90,43 @@ def test_drycblles_128_fp64(swadvec, igc):
     div_gpu = float(P.divergence(un["u"], un["v"], un["w"])); div_ref = float(P.divergence(case["u"], case["v"], case["w"]))
     scale = float(np.abs(interior(g, case["u"])).max())/float(g.dx)
     assert div_gpu <= max(10*div_ref, 200*np.finfo(np.float64).eps*scale), (div_gpu, div_ref)
+
+
+@pytest.mark.parametrize("dtype,igc", [(np.float64, 3), (np.float64, 4), (np.float32, 4)])
+@pytest.mark.parametrize("shape", [(160, 20, 24), (128, 10, 33)])
+@pytest.mark.parametrize("swthermo,surface", [("dry", True), (None, True), ("dry", False)])
+def test_advec2_smag2_fused(dtype, igc, shape, swthermo, surface, monkeypatch):
+    """cases/drycblles as shipped (swadvec = 2 + smag2): Advec_2's fluxes run inside the TMA-staged fused tendency kernel
+    (mom3_kernel<..., ADV2>) when the grid has igc >= 3; multi-tile / ragged grids, with and without thermo and surface model.
+    The same step with MHH_FUSE_ADVEC2=0 (Advec_2 point-wise, then the diffusion alone) must agree with it too."""
+    kw = dict(stretched=True, anelastic=True, igc=igc)
+    g, gd, case = make_pair(*shape, dtype, **kw)
+    oprm = ostep.default_params(); oprm.update(swadvec="2", swthermo=swthermo, surface_model=surface, visc=1e-2 if not surface else 1e-5)
+    dt = 2.0
+    names = ["u", "v", "w", "th"]
+    if dtype == np.float32:
+        g64, c64 = truth_fp64(case, shape, dt, oprm, **kw)
+    res = {}
+    for fused in ("1", "0"):
+        monkeypatch.setenv("MHH_FUSE_ADVEC2", fused)
+        D, ctx, f = gpu_setup(gd, case, visc=oprm["visc"])
+        prm = D.make_params(swadvec="2", swthermo=swthermo or "0", surface_model=surface)
+        ctx.profile_start()
+        D.Dycore(ctx, prm).step(f, dt)
+        prof = ctx.profile_stop()
+        ctx.sync()
+        assert ("mom3_kernel_advec2" in prof) == (fused == "1"), sorted(prof)
+        res[fused] = {n: f[n].cpu().numpy() for n in names}
+        if fused == "1":
+            f1 = f
+    ostep.dycore_step(g, kernels(g), case, oprm, dt)
+    if dtype == np.float32:
+        check_fp32_at_reference_level(g, f1, case, g64, c64, names)
+        check_step(g, f1, case, names, 5*TOL[dtype])
+    else:
+        check_step(g, f1, case, names, TOL[dtype])
+    for n in names:
+        assert rel_l2(interior(g, res["1"][n]), interior(g, res["0"][n])) <= (TOL[dtype] if dtype == np.float64 else 5*TOL[dtype]), n
 
 
 @pytest.mark.parametrize("igc", [3, 4])

@@ -1,0 +1,143 @@
+"""
+Deardorff SGS-TKE closure on the device (Diff_tke2; reference src/diff_tke2.cxx) and the Limiter
+(src/limiter.cxx): `mhh_diff_tke2_*` / `mhh_limiter_exec` against the oracle (pinned bit for bit to the compiled reference in
+tests/test_oracle_vs_ref.py), and full RK3 steps with swdiff = tke2 inside the fused sub-step against the oracle stepping
+in Model::exec's order.
+"""
+import copy
+import numpy as np
+import pytest
+
+from util import TOL, rel_l2, make_pair, interior, prepare_halos, add_sgstke
+from oracle import oracle as O
+from oracle import step as ostep
+from oracle import refbind
+
+pytestmark = pytest.mark.gpu
+
+
+def kernels(g):
+    return refbind.RefKernels(g, fast=False) if refbind.available(False) else O.NumpyKernels(g)
+
+
+def setup(shape, dtype, swthermo, mason, igc=3, swadvec="2i5", ns=2):
+    from microhh_b200 import dycore as D
+    g, gd, case = make_pair(*shape, dtype, stretched=True, anelastic=True, ns=ns, igc=igc)
+    add_sgstke(g, case)
+    ctx = D.Context(gd, 0)
+    ctx.set_basestate(case["rhoref"], case["rhorefh"], case["thref"], case["threfh"])
+    prm_o = ostep.default_params(); prm_o.update(swdiff="tke2", swthermo=swthermo, sw_mason=mason, swadvec=swadvec)
+    prm = D.make_params(swadvec=swadvec, swdiff="tke2", swthermo=swthermo or "0", sw_mason=mason)
+    return D, g, gd, case, ctx, prm, prm_o
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("swthermo", ["dry", None])
+@pytest.mark.parametrize("mason", [True, False])
+def test_tke2_create_and_exec_viscosity(dtype, swthermo, mason):
+    D, g, gd, case, ctx, prm, prm_o = setup((96, 40, 24), dtype, swthermo, mason)
+    prepare_halos(g, case)
+    rng = np.random.default_rng(12)
+    case["sgstket"] = (1.e-3*rng.standard_normal(gd.shape)).astype(dtype)
+    f = D.Fields(ctx, case, scalars=case["scalars"])
+    T = D.Diff_tke2(ctx, prm, f)
+    T.create(f)
+    K = kernels(g)
+    K.tke2_enforce_min(case["sgstke"])
+    assert np.array_equal(f["sgstke"].cpu().numpy(), case["sgstke"])            # max + periodic copy: exact
+    T.exec_viscosity(f)
+    ctx.sync()
+    ostep._tke2_exec_viscosity(K, case, prm_o)
+    assert rel_l2(f["evisc"].cpu().numpy(), case["evisc"]) <= TOL[dtype]         # whole array: the cyclic halos too
+    if swthermo == "dry":
+        assert rel_l2(T.eviscs.cpu().numpy(), case["eviscs"]) <= TOL[dtype]
+    assert rel_l2(interior(g, f["sgstket"].cpu().numpy()), interior(g, case["sgstket"])) <= 10*TOL[dtype]
+    # time-step limiter of the closure
+    dn = T.get_dn(f, 2.5)
+    ev = case["eviscs"] if swthermo == "dry" else case["evisc"]
+    dn_ref = float(K.diff_dnmul(ev, 1.))*2.5
+    assert abs(dn - dn_ref) <= 10*TOL[dtype]*abs(dn_ref)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_tke2_exec_viscosity_with_n2_array(dtype):
+    """N2 handed over as a field (Thermo::get_thermo_field("N2")) instead of derived from th."""
+    D, g, gd, case, ctx, prm, prm_o = setup((64, 32, 20), dtype, "dry", True)
+    prepare_halos(g, case)
+    f = D.Fields(ctx, case, scalars=case["scalars"])
+    T = D.Diff_tke2(ctx, prm, f)
+    K = kernels(g)
+    N2 = np.zeros(gd.shape, dtype)
+    K.thermo_dry_N2(N2, case["th"], case["thref"])
+    import torch
+    T.exec_viscosity(f, n2=torch.from_numpy(N2).cuda())
+    ctx.sync()
+    ostep._tke2_exec_viscosity(K, case, prm_o)
+    assert rel_l2(f["evisc"].cpu().numpy(), case["evisc"]) <= TOL[dtype]
+    assert rel_l2(T.eviscs.cpu().numpy(), case["eviscs"]) <= TOL[dtype]
+    assert rel_l2(interior(g, f["sgstket"].cpu().numpy()), interior(g, case["sgstket"])) <= 10*TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("swthermo", ["dry", None])
+@pytest.mark.parametrize("igc", [3, 4])
+def test_tke2_exec_and_limiter(dtype, swthermo, igc):
+    """Diff_tke2::exec (diffusion with evisc / eviscs, tPr = 1) and the limiter on sgstke."""
+    D, g, gd, case, ctx, prm, prm_o = setup((128, 40, 24), dtype, swthermo, True, igc=igc)
+    prepare_halos(g, case)
+    O.boundary_cyclic(g, case["sgstke"])
+    rng = np.random.default_rng(13)
+    case["evisc"] = (0.5 + rng.random(gd.shape)).astype(dtype)
+    case["eviscs"] = (1.5 + rng.random(gd.shape)).astype(dtype)
+    import torch
+    f = D.Fields(ctx, case, scalars=case["scalars"])
+    T = D.Diff_tke2(ctx, prm, f)
+    if T.eviscs is not None:
+        T.eviscs.copy_(torch.from_numpy(case["eviscs"]))
+    T.exec(f)
+    ctx.sync()
+    K = kernels(g)
+    rr, rh = case["rhoref"], case["rhorefh"]
+    K.diff_u(case["ut"], case["u"], case["v"], case["w"], case["evisc"], case["u_fluxbot"], case["u_fluxtop"], rr, rh, prm_o["visc"], True)
+    K.diff_v(case["vt"], case["u"], case["v"], case["w"], case["evisc"], case["v_fluxbot"], case["v_fluxtop"], rr, rh, prm_o["visc"], True)
+    K.diff_w(case["wt"], case["u"], case["v"], case["w"], case["evisc"], rr, rh, prm_o["visc"])
+    for s in case["scalars"]:
+        ev = case["evisc"] if (s == "sgstke" or swthermo != "dry") else case["eviscs"]
+        K.diff_c(case[s + "t"], case[s], ev, case[s + "_fluxbot"], case[s + "_fluxtop"], rr, rh, 1., prm_o["svisc"], True)
+    for n in ["ut", "vt", "wt"] + [s + "t" for s in case["scalars"]]:
+        assert rel_l2(interior(g, f[n].cpu().numpy()), interior(g, case[n])) <= 10*TOL[dtype], n
+    # limiter: drive part of the field below the minimum
+    at = (-0.4*rng.random(gd.shape)).astype(dtype)
+    d_at = torch.from_numpy(at.copy()).cuda()
+    D.Limiter(ctx).exec(d_at, f["sgstke"], D.Limiter.SGSTKE_MIN, 1.3)
+    ctx.sync()
+    K.tendency_limiter(at, case["sgstke"], O.SGSTKE_MIN, 1.3)
+    assert rel_l2(interior(g, d_at.cpu().numpy()), interior(g, at)) <= TOL[dtype]
+    new = interior(g, case["sgstke"]).astype(np.float64) + 1.3*interior(g, d_at.cpu().numpy()).astype(np.float64)
+    assert (new >= O.SGSTKE_MIN*(1. - 1e-3) - 1e-6*(dtype == np.float32)).all()
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("swthermo", ["dry", None])
+@pytest.mark.parametrize("swadvec,igc,shape", [("2i5", 3, (64, 32, 24)), ("2i5", 4, (128, 48, 32)), ("2", 3, (64, 32, 24))])
+def test_full_rk3_step_tke2(dtype, swthermo, swadvec, igc, shape):
+    """One RK3 step with the closure registered into the fused sub-step (exec_viscosity, exec, limiter in Model::exec's order).
+    The igc = 4 / 128-wide case runs the TMA-staged momentum kernel with scalar 0 (th: diffuses with eviscs) outside it."""
+    D, g, gd, case, ctx, prm, prm_o = setup(shape, dtype, swthermo, True, igc=igc, swadvec=swadvec)
+    O.tke2_enforce_min(g, case["sgstke"])
+    f = D.Fields(ctx, case, scalars=case["scalars"])
+    T = D.Diff_tke2(ctx, prm, f)
+    T.register()
+    D.Dycore(ctx, prm).step(f, 2.0)
+    ctx.sync()
+    c = copy.deepcopy(case)
+    ostep.dycore_step(g, kernels(g), c, prm_o, 2.0)
+    tol = TOL[dtype] if dtype == np.float64 else 3*TOL[dtype]
+    for n in ("u", "v", "w", "th", "s1", "sgstke"):
+        assert rel_l2(interior(g, f[n].cpu().numpy()), interior(g, c[n])) <= tol, n
+    assert rel_l2(f["evisc"].cpu().numpy(), c["evisc"]) <= tol
+    assert (interior(g, f["sgstke"].cpu().numpy()) >= 0.99*O.SGSTKE_MIN).all()
+    # swdiff = tke2 without a registered closure is refused
+    T.unregister()
+    with pytest.raises(Exception):
+        D.Dycore(ctx, prm).step(f, 2.0)
