@@ -42,6 +42,7 @@ extern "C" {
 #define MHH_E_INVALID  -1   /* bad argument / unsupported configuration */
 #define MHH_E_CUDA     -2   /* CUDA runtime error (message has the detail) */
 #define MHH_E_NOMEM    -3
+#define MHH_E_IO       -4   /* restart file cannot be created / opened / is too short (the reference's save/load return 1) */
 
 #define MHH_MAX_SCALARS 8
 
@@ -351,6 +352,13 @@ MHH_API int mhh_dycore_substep_surface(mhh_ctx* ctx, const mhh_fields* f, const 
 MHH_API int mhh_buffer_exec(mhh_ctx* ctx, const mhh_fields* f, const mhh_forcing* forcing);
 MHH_API int mhh_force_exec(mhh_ctx* ctx, const mhh_fields* f, const mhh_forcing* forcing, double sub_dt);
 MHH_API int mhh_dycore_set_forcing(mhh_ctx* ctx, const mhh_forcing* forcing);
+/* ---- Field3d_io<TF>::save_field3d / load_field3d (src/field3d_io.cxx:669-751 serial, :57-246 MPI-IO): restart IO of one
+ * DEVICE field in the reference's unchanged file layout -- the interior levels [kstart, kend) x jtot x itot as raw TF, no
+ * header (Fields::save / load call it for every prognostic field with offset 0, src/fields.cxx:1243-1320).  On y slabs every
+ * rank reads / writes its rows of the ONE file (the MPI build's subarray view); single GPU: an existing file is an error as with
+ * fopen(..., "wbx").  Synchronous: returns after the file operation. */
+MHH_API int mhh_field3d_save(mhh_ctx* ctx, const void* fld, const char* filename, double offset, int kstart, int kend);
+MHH_API int mhh_field3d_load(mhh_ctx* ctx, void* fld, const char* filename, double offset, int kstart, int kend);
 /* Three sub-steps. */
 MHH_API int mhh_dycore_step(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm, double dt);
 /* End-to-end variant with HOST buffers (ghosted layout): copies u,v,w and the scalars to the

@@ -143,6 +143,8 @@ SIGNATURES = {
     "mhh_boundary_surface_init": (C.c_int, [_vp, C.c_double, C.c_double, C.c_int, C.c_int]),
     "mhh_boundary_surface_exec": (C.c_int, [_vp, _PF, _PP, C.POINTER(SurfaceC)]),
     "mhh_dycore_substep_surface": (C.c_int, [_vp, _PF, _PP, C.POINTER(SurfaceC), C.c_int, C.c_double]),
+    "mhh_field3d_save": (C.c_int, [_vp, _vp, C.c_char_p, C.c_double, C.c_int, C.c_int]),
+    "mhh_field3d_load": (C.c_int, [_vp, _vp, C.c_char_p, C.c_double, C.c_int, C.c_int]),
     "mhh_dycore_step": (C.c_int, [_vp, _PF, _PP, C.c_double]),
     "mhh_dycore_step_host": (C.c_int, [_vp, _PF, _PP, C.c_double, C.c_int, _vp, _vp, _vp, C.POINTER(_vp)]),
 }

@@ -61,10 +61,12 @@ template <typename TF> __device__ __forceinline__ TF pow2(TF a) { return a * a; 
 // flux65 in its one-sided form (MHH_UPWIND_F64 / MHH_UPWIND_F32 = 1): vel*i6 - |vel|*i5 is vel*(i6 - i5) for vel >= 0 and
 // vel*(i6 + i5) otherwise, and i6 -/+ i5 collapses to the five-point upwind stencil (2, -13, 47, 27, -3)/60 over the cells
 // on the upwind side -- 6 floating-point instructions instead of 14 (the six sums / differences of the symmetric form go
-// away), at the price of five register selects on the sign of the velocity, which run on the ALU pipe and not on the fp64
-// pipe the fp64 kernels queue on.  Same real number, rounded differently (well inside the 1e-12 / 1e-5 parity budget).
+// away), at the price of five register selects on the sign of the velocity.  Same real number, rounded differently (well
+// inside the 1e-12 / 1e-5 parity budget).  Measured on the B200 at 512^3 (profiles/r02/ab_flux65_*.json): fp32 mom3
+// 3.58 -> 3.44 ms per launch (72 instead of 86 registers) -> on; fp64 5.76 -> 7.14 ms (a 64-bit select is two FSEL: 265 fewer
+// fp64 instructions but 400 more on the ALU pipe, +12 % issued instructions) -> off.
 #ifndef MHH_UPWIND_F64
-#define MHH_UPWIND_F64 1
+#define MHH_UPWIND_F64 0
 #endif
 #ifndef MHH_UPWIND_F32
 #define MHH_UPWIND_F32 1

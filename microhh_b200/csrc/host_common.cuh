@@ -71,6 +71,8 @@ struct mhh_ctx
     ncclComm_t comm = nullptr;
     // Buffer / Force registered for the fused sub-steps (mhh_dycore_set_forcing)
     mhh_forcing forcing{}; bool forcing_set = false;
+    // restart IO staging (device + pinned host), grown on demand by mhh_field3d_save / _load
+    void *io_dev = nullptr, *io_host = nullptr; size_t io_cap = 0;
     // Diff_tke2 registered for the fused sub-steps (mhh_dycore_set_tke2)
     mhh_tke2 tke2{}; bool tke2_set = false;
     virtual ~mhh_ctx() {}
@@ -167,6 +169,7 @@ struct Ctx : mhh_ctx
     ~Ctx() override
     {
         cudaSetDevice(device);
+        cudaFree(io_dev); if (io_host) cudaFreeHost(io_host);
         cudaFree(d_zL_sl); cudaFree(d_f_sl); cudaFree(d_sigmaz); cudaFree(d_sums);
         cudaFree(d_prof); cudaFree(d_mlen0); cudaFree(tw_xh); cudaFree(tw_xf); cudaFree(tw_y);
         cudaFree(d_bmati); cudaFree(d_bmatj); cudaFree(d_a); cudaFree(d_c); cudaFree(d_dz2rho); cudaFree(d_dz2);

@@ -441,6 +441,24 @@ class Boundary_surface:
         self.ctx.check(self.ctx.lib.mhh_boundary_surface_exec(self.ctx.h, C.byref(fields.c), C.byref(prm), C.byref(self.c)))
 
 
+class Field3d_io:
+    """Field3d_io<TF>::save_field3d / load_field3d (src/field3d_io.cxx): restart IO of one device field in the reference's
+    file layout (interior as raw TF, no header); on y slabs every rank handles its rows of the one file."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    def save_field3d(self, fld, filename, offset=0., kstart=None, kend=None):
+        gd = self.ctx.gd
+        return self.ctx.lib.mhh_field3d_save(self.ctx.h, _ptr(fld), str(filename).encode(), offset,
+                                             gd.kstart if kstart is None else kstart, gd.kend if kend is None else kend)
+
+    def load_field3d(self, fld, filename, offset=0., kstart=None, kend=None):
+        gd = self.ctx.gd
+        return self.ctx.lib.mhh_field3d_load(self.ctx.h, _ptr(fld), str(filename).encode(), offset,
+                                             gd.kstart if kstart is None else kstart, gd.kend if kend is None else kend)
+
+
 class Timeloop:
     def __init__(self, ctx):
         self.ctx = ctx

@@ -513,6 +513,17 @@ namespace mhhb200
         MHH_CHECK(c.ctx, mhh_force_exec(c.ctx, &f, &forcing, sub_dt));
     }
 
+    // ---- Field3d_io<TF>::save_field3d / load_field3d (src/field3d_io.cxx): restart IO straight from / into the device field, same
+    // file layout; the bodies of Fields<TF>::save / load (src/fields.cxx:1243-1320) become, per prognostic field,
+    //     nerror += mhhb200::field3d_save_b200(*b200, f.second->fld_g, filename, no_offset, gd.kstart, gd.kend);
+    // Return value as the reference's: 0 = ok, 1 = failed (the message is in mhh_last_error).
+    template<typename TF>
+    int field3d_save_b200(Context<TF>& c, const TF* fld_g, const char* filename, const TF offset, const int kstart, const int kend)
+    { return mhh_field3d_save(c.ctx, fld_g, filename, offset, kstart, kend) == MHH_OK ? 0 : 1; }
+    template<typename TF>
+    int field3d_load_b200(Context<TF>& c, TF* fld_g, const char* filename, const TF offset, const int kstart, const int kend)
+    { return mhh_field3d_load(c.ctx, fld_g, filename, offset, kstart, kend) == MHH_OK ? 0 : 1; }
+
     // ---- staged sub-step: the fused path with MicroHH's own stages kept in between (surface model, statistics, ...), in the
     // order of Model::exec (src/model.cxx:368-504): pre = cyclic + ghost cells + diff.exec_viscosity; [MicroHH's surface model];
     // set_ghost_cells again (:401); post = thermo + advec + diff fused, (buffer, force if registered), pres, rk3.

@@ -2004,6 +2004,35 @@ def force_wls_local(g, st, s, wls):
             st[k][sl] -= wls[k]*(s[k+1][sl] - s[k][sl])*g.dzhi[k+1]
 
 
+# --------------------------------------------------------------------------------------
+# Restart IO of one 3-D field: Field3d_io<TF>::save_field3d / load_field3d (serial build, src/field3d_io.cxx:669-751; called
+# for every prognostic field by Fields::save / load with offset 0, src/fields.cxx:1243-1320).  File = the interior
+# [kstart,kend) x jtot x itot as raw TF in C order, no header.  The MPI build writes the same single file through MPI-IO
+# subarrays (src/field3d_io.cxx:57-160): a y slab owns rows [mpicoordy*jmax, (mpicoordy+1)*jmax) of every level.
+# --------------------------------------------------------------------------------------
+def field3d_save(g, data, filename, offset=0., kstart=None, kend=None):
+    TF = g.TF
+    k0 = g.kstart if kstart is None else kstart
+    k1 = g.kend if kend is None else kend
+    import os
+    if os.path.exists(filename):
+        return 1                                    # fopen(filename, "wbx"): exclusive create
+    (data[k0:k1, g.jstart:g.jend, g.istart:g.iend] + TF(offset)).astype(TF).tofile(filename)
+    return 0
+
+def field3d_load(g, data, filename, offset=0., kstart=None, kend=None):
+    TF = g.TF
+    k0 = g.kstart if kstart is None else kstart
+    k1 = g.kend if kend is None else kend
+    import os
+    n = (k1 - k0)*g.jmax*g.imax
+    if not os.path.exists(filename) or os.path.getsize(filename) < n*np.dtype(TF).itemsize:
+        return 1
+    a = np.fromfile(filename, dtype=TF, count=n).reshape(k1 - k0, g.jmax, g.imax)
+    data[k0:k1, g.jstart:g.jend, g.istart:g.iend] = a - TF(offset)
+    return 0
+
+
 class NumpyKernels:
     def __init__(self, g):
         self.g = g

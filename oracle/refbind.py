@@ -481,3 +481,34 @@ class RefPres:
         self._set_grid()
         f = self._f("ref_pres_4_divergence"); f.restype = C.c_double
         return f(self.h, self._p(u), self._p(v), self._p(w))
+
+
+class RefField3dIO:
+    """Field3d_io<TF>::save_field3d / load_field3d of the reference (oracle/ref/ref_field3d_io.cpp) on its own Grid<TF>."""
+
+    def __init__(self, g):
+        self.lib = C.CDLL(lib_path(False))
+        self.g = g
+        TF = g.TF
+        self.sfx = "f64" if TF == np.float64 else "f32"
+        self.ct = C.c_double if TF == np.float64 else C.c_float
+        z = np.ascontiguousarray(np.asarray(g.z, TF)[:g.kcells])
+        getattr(self.lib, f"ref_grid_setup_{self.sfx}")(
+            g.itot, g.jtot, g.ktot, self.ct(float(g.xsize)), self.ct(float(g.ysize)), self.ct(float(g.zsize)),
+            g.igc, g.jgc, g.kgc, int(getattr(g, "order", 2)), z.ctypes.data_as(C.c_void_p))
+
+    def _io(self, name, data, filename, offset, kstart, kend):
+        g = self.g
+        assert data.flags["C_CONTIGUOUS"] and data.dtype == g.TF
+        tmp1 = np.zeros_like(data); tmp2 = np.zeros_like(data)
+        k0 = g.kstart if kstart is None else kstart
+        k1 = g.kend if kend is None else kend
+        f = getattr(self.lib, f"{name}_{self.sfx}"); f.restype = C.c_int
+        return f(data.ctypes.data_as(C.c_void_p), tmp1.ctypes.data_as(C.c_void_p), tmp2.ctypes.data_as(C.c_void_p),
+                 C.c_char_p(str(filename).encode()), self.ct(float(offset)), C.c_int(k0), C.c_int(k1))
+
+    def save(self, data, filename, offset=0., kstart=None, kend=None):
+        return self._io("ref_field3d_save", data, filename, offset, kstart, kend)
+
+    def load(self, data, filename, offset=0., kstart=None, kend=None):
+        return self._io("ref_field3d_load", data, filename, offset, kstart, kend)

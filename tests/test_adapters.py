@@ -22,6 +22,8 @@ template class mhhb200::Diff_smag2_b200<double>;
 template class mhhb200::Diff_tke2_b200<double>;
 template class mhhb200::Diff_tke2_b200<float>;
 template void mhhb200::limiter_exec_b200<double>(mhhb200::Context<double>&, Fields<double>&, const std::string&, double, double);
+template int mhhb200::field3d_save_b200<double>(mhhb200::Context<double>&, const double*, const char*, double, int, int);
+template int mhhb200::field3d_load_b200<float>(mhhb200::Context<float>&, float*, const char*, float, int, int);
 template class mhhb200::Diff_const_b200<double, 2>;
 template class mhhb200::Diff_const_b200<float, 4>;
 template class mhhb200::Pres_b200<float, 2>;

@@ -538,3 +538,26 @@ def test_full_rk3_step_tke2_bitexact(dtype, swthermo, swadvec):
         assert np.array_equal(c0[n], c1[n]), n
     assert np.isfinite(interior(g, c0["sgstke"])).all() and np.isfinite(interior(g, c0["u"])).all()
     assert not np.array_equal(c0["sgstke"], case["sgstke"])
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape,order", [((16, 12, 8), 2), ((24, 1, 8), 2), ((12, 10, 6), 4)])
+@pytest.mark.parametrize("offset", [0., 300.])
+def test_field3d_io_bitexact(dtype, shape, order, offset, tmp_path):
+    """Restart IO (src/field3d_io.cxx:669-751): the oracle's file is byte for byte the reference's, either side loads the
+    other's file, an existing file is refused (fopen "wbx") and a missing / short one reported."""
+    g = O.Grid(*shape, 100., 80., 60., 3, 3, 3 if order == 4 else 1, dtype, order=order)
+    rng = np.random.default_rng(9)
+    a = rng.standard_normal(g.field().shape).astype(dtype)
+    R = refbind.RefField3dIO(g)
+    fo, fr = tmp_path / "u.oracle", tmp_path / "u.ref"
+    assert O.field3d_save(g, a, str(fo), offset) == 0 and R.save(a.copy(), fr, offset) == 0
+    assert fo.read_bytes() == fr.read_bytes()
+    assert fo.stat().st_size == g.itot*g.jtot*g.ktot*np.dtype(dtype).itemsize
+    assert O.field3d_save(g, a, str(fo), offset) != 0 and R.save(a.copy(), fr, offset) != 0          # exclusive create
+    b0 = np.full_like(a, 7.); b1 = np.full_like(a, 7.)
+    assert O.field3d_load(g, b0, str(fr), offset) == 0 and R.load(b1, fo, offset) == 0
+    assert np.array_equal(b0, b1)
+    assert np.array_equal(interior(g, b0), (interior(g, a) + dtype(offset)) - dtype(offset))
+    assert (b0[0] == 7.).all()                                                                       # ghost cells untouched
+    assert O.field3d_load(g, b0, str(tmp_path / "missing"), offset) != 0 and R.load(b1, tmp_path / "missing", offset) != 0
