@@ -359,8 +359,12 @@ MHH_API int mhh_dycore_set_forcing(mhh_ctx* ctx, const mhh_forcing* forcing);
  * fopen(..., "wbx").  Synchronous: returns after the file operation. */
 MHH_API int mhh_field3d_save(mhh_ctx* ctx, const void* fld, const char* filename, double offset, int kstart, int kend);
 MHH_API int mhh_field3d_load(mhh_ctx* ctx, void* fld, const char* filename, double offset, int kstart, int kend);
-/* Three sub-steps. */
+/* Three sub-steps.  On a single GPU the second call with identical arguments (same structs, same dt) is captured into a CUDA
+ * graph on the context's own stream and replayed from then on, ordered after / before the work on the stream set with
+ * mhh_set_stream: the ~240 launches of a step are launch-bound on small grids.  Changing arguments (adaptive dt), profiling,
+ * slabs, or MHH_GRAPH=0 in the environment run the step eagerly.  mhh_graph_replays: how many steps were replays so far. */
 MHH_API int mhh_dycore_step(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm, double dt);
+MHH_API long long mhh_graph_replays(const mhh_ctx* ctx);
 /* End-to-end variant with HOST buffers (ghosted layout): copies u,v,w and the scalars to the
  * device fields in `f`, zeroes nothing (tendencies in `f` are used as they are), runs `nsteps`
  * full RK3 steps and copies u,v,w,scalars back.  Host pointers should be pinned. */

@@ -146,6 +146,7 @@ SIGNATURES = {
     "mhh_field3d_save": (C.c_int, [_vp, _vp, C.c_char_p, C.c_double, C.c_int, C.c_int]),
     "mhh_field3d_load": (C.c_int, [_vp, _vp, C.c_char_p, C.c_double, C.c_int, C.c_int]),
     "mhh_dycore_step": (C.c_int, [_vp, _PF, _PP, C.c_double]),
+    "mhh_graph_replays": (C.c_longlong, [_vp]),
     "mhh_dycore_step_host": (C.c_int, [_vp, _PF, _PP, C.c_double, C.c_int, _vp, _vp, _vp, C.POINTER(_vp)]),
 }
 

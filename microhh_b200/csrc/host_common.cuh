@@ -71,6 +71,17 @@ struct mhh_ctx
     ncclComm_t comm = nullptr;
     // Buffer / Force registered for the fused sub-steps (mhh_dycore_set_forcing)
     mhh_forcing forcing{}; bool forcing_set = false;
+    // CUDA graph of one full RK3 step (mhh_dycore_step / _step_host on a single GPU): the ~80 launches per sub-step are
+    // launch-bound on the small grids (drycblles 128^3, moser180), so the second step with identical arguments is captured on
+    // the context's own stream and replayed from then on.  MHH_GRAPH=0 keeps every step eager; profiling, slabs (NCCL), a failed
+    // capture or changing arguments (adaptive dt) run eagerly as well.
+    bool use_graph = true;
+    cudaGraphExec_t graph_exec = nullptr;
+    unsigned long long graph_key = 0, graph_seen = 0;
+    long long graph_launches = 0, graph_replays = 0;
+    bool graph_failed = false;
+    cudaEvent_t ev_g0 = nullptr, ev_g1 = nullptr;
+    void drop_graph() { if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; } graph_key = graph_seen = 0; }
     // restart IO staging (device + pinned host), grown on demand by mhh_field3d_save / _load
     void *io_dev = nullptr, *io_host = nullptr; size_t io_cap = 0;
     // Diff_tke2 registered for the fused sub-steps (mhh_dycore_set_tke2)
@@ -169,6 +180,9 @@ struct Ctx : mhh_ctx
     ~Ctx() override
     {
         cudaSetDevice(device);
+        drop_graph();
+        if (ev_g0) cudaEventDestroy(ev_g0);
+        if (ev_g1) cudaEventDestroy(ev_g1);
         cudaFree(io_dev); if (io_host) cudaFreeHost(io_host);
         cudaFree(d_zL_sl); cudaFree(d_f_sl); cudaFree(d_sigmaz); cudaFree(d_sums);
         cudaFree(d_prof); cudaFree(d_mlen0); cudaFree(tw_xh); cudaFree(tw_xf); cudaFree(tw_y);

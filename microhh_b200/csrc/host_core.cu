@@ -75,6 +75,7 @@ int create_impl(const mhh_grid_desc* d, int dtype, int device, mhh_ctx** out)
     { const char* e = getenv("MHH_NO_TMA"); c->no_tma = e && e[0] == '1'; }
     { const char* e = getenv("MHH_FUSE_SCALAR"); if (e) c->fuse_scalar = e[0] == '1'; }
     { const char* e = getenv("MHH_FUSE_ADVEC2"); if (e) c->fuse_advec2 = e[0] == '1'; }
+    { const char* e = getenv("MHH_GRAPH"); if (e) c->use_graph = e[0] == '1'; }
     { const char* e = getenv("MHH_TILE3_Y"); if (e) { int v = atoi(e); if (v == 3 || v == 4 || v == 5) c->tile3_y = v; } }
     { const char* e = getenv("MHH_EVISC_MB"); if (e) c->evisc_mb = atoi(e); }
     { const char* e = getenv("MHH_EVISC_TMA"); if (e) c->evisc_tma = atoi(e) != 0; }
@@ -805,6 +806,86 @@ int substep_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, int sub
     return substep_post_impl<TF>(c, f, prm, substep, dt);
 }
 
+// ---- one full RK3 step: eager, or as a replayed CUDA graph --------------------------------------------------------------
+inline unsigned long long fnv1a(unsigned long long h, const void* p, size_t n)
+{
+    const unsigned char* b = static_cast<const unsigned char*>(p);
+    for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+template <typename TF>
+int step_eager(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, double dt)
+{
+    for (int ss = 0; ss < 3; ++ss)
+    {
+        const int rc = substep_impl<TF>(c, f, prm, ss, dt);
+        if (rc != MHH_OK) return rc;
+    }
+    return MHH_OK;
+}
+
+template <typename TF>
+int step_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, double dt)
+{
+    if (!c->use_graph || c->nranks > 1 || c->desc.npy > 1 || c->prof || c->graph_failed || !c->own_stream)
+        return step_eager<TF>(c, f, prm, dt);
+    // everything a captured launch bakes in: the field / parameter structs (pointers, switches, viscosities), dt, the registered
+    // forcing and closure.  The user's stream is not part of it: the graph always runs on the context's own stream.
+    unsigned long long key = 1469598103934665603ull;
+    key = fnv1a(key, f, sizeof(*f)); key = fnv1a(key, prm, sizeof(*prm)); key = fnv1a(key, &dt, sizeof(dt));
+    const int flags[3] = {c->forcing_set ? 1 : 0, c->tke2_set ? 1 : 0, c->overlap ? 1 : 0};
+    key = fnv1a(key, flags, sizeof(flags));
+    if (c->forcing_set) key = fnv1a(key, &c->forcing, sizeof(c->forcing));
+    if (c->tke2_set) key = fnv1a(key, &c->tke2, sizeof(c->tke2));
+    if (key == 0) key = 1;
+    cudaStream_t user = c->stream;
+    if (!(c->graph_exec && c->graph_key == key))
+    {
+        if (c->graph_seen != key) { c->graph_seen = key; return step_eager<TF>(c, f, prm, dt); }       // first sighting: lazy set-up runs here
+        // second sighting: capture the step on the own stream (the user's stream may be the legacy default stream, which cannot
+        // be captured), instantiate, and fall through to the replay
+        if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+        if (!c->ev_g0 && (cudaEventCreateWithFlags(&c->ev_g0, cudaEventDisableTiming) != cudaSuccess ||
+                          cudaEventCreateWithFlags(&c->ev_g1, cudaEventDisableTiming) != cudaSuccess))
+        { cudaGetLastError(); c->graph_failed = true; return step_eager<TF>(c, f, prm, dt); }
+        const long long l0 = c->launches;
+        if (cudaStreamBeginCapture(c->own_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+        { cudaGetLastError(); c->graph_failed = true; return step_eager<TF>(c, f, prm, dt); }
+        c->stream = c->own_stream;
+        const int rc = step_eager<TF>(c, f, prm, dt);
+        c->stream = user;
+        cudaGraph_t graph = nullptr;
+        const cudaError_t e = cudaStreamEndCapture(c->own_stream, &graph);
+        const long long nl = c->launches - l0;
+        c->launches = l0;
+        if (rc != MHH_OK) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); c->graph_failed = true; return rc; }
+        if (e != cudaSuccess || !graph || cudaGraphInstantiate(&c->graph_exec, graph, 0) != cudaSuccess)
+        {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError(); c->graph_exec = nullptr; c->graph_failed = true;
+            return step_eager<TF>(c, f, prm, dt);                                                        // nothing has run yet
+        }
+        cudaGraphDestroy(graph);
+        c->graph_key = key; c->graph_launches = nl;
+    }
+    // replay: own stream after everything queued on the user's stream, user's stream after the graph
+    if (user != c->own_stream)
+    {
+        CUDA_TRY(c, cudaEventRecord(c->ev_g0, user));
+        CUDA_TRY(c, cudaStreamWaitEvent(c->own_stream, c->ev_g0, 0));
+    }
+    CUDA_TRY(c, cudaGraphLaunch(c->graph_exec, c->own_stream));
+    if (user != c->own_stream)
+    {
+        CUDA_TRY(c, cudaEventRecord(c->ev_g1, c->own_stream));
+        CUDA_TRY(c, cudaStreamWaitEvent(user, c->ev_g1, 0));
+    }
+    c->launches += c->graph_launches;
+    c->graph_replays++;
+    return MHH_OK;
+}
+
 template <typename TF>
 int step_host_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, double dt, int nsteps,
                    void* h_u, void* h_v, void* h_w, void* const* h_s)
@@ -821,11 +902,10 @@ int step_host_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, doubl
         CUDA_TRY(c, cudaMemcpyAsync(f->s[n], h_s[n], bytes, cudaMemcpyHostToDevice, c->stream));
     }
     for (int it = 0; it < nsteps; ++it)
-        for (int ss = 0; ss < 3; ++ss)
-        {
-            int rc = substep_impl<TF>(c, f, prm, ss, dt);
-            if (rc != MHH_OK) return rc;
-        }
+    {
+        const int rc = step_impl<TF>(c, f, prm, dt);
+        if (rc != MHH_OK) return rc;
+    }
     CUDA_TRY(c, cudaMemcpyAsync(h_u, f->u, bytes, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaMemcpyAsync(h_v, f->v, bytes, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaMemcpyAsync(h_w, f->w, bytes, cudaMemcpyDeviceToHost, c->stream));
@@ -1143,7 +1223,7 @@ int mhh_profile_stop(mhh_ctx* ctx, const char** json)
 long long mhh_workspace_bytes(const mhh_ctx* ctx) { return ctx ? ctx->ws_bytes : 0; }
 
 int mhh_set_basestate(mhh_ctx* ctx, const void* rhoref, const void* rhorefh, const void* thref, const void* threfh)
-{ DISPATCH1(ctx, set_basestate_impl<TF>(c, rhoref, rhorefh, thref, threfh)); }
+{ if (ctx) ctx->drop_graph(); DISPATCH1(ctx, set_basestate_impl<TF>(c, rhoref, rhorefh, thref, threfh)); }
 
 int mhh_boundary_cyclic(mhh_ctx* ctx, void* fld, int edge)
 { DISPATCH1(ctx, cyclic_impl<TF>(c, P<TF>(fld), edge, false)); }
@@ -1343,6 +1423,7 @@ int mhh_dycore_set_forcing(mhh_ctx* ctx, const mhh_forcing* fo)
 {
     if (!ctx) return MHH_E_INVALID;
     if (fo) { ctx->forcing = *fo; ctx->forcing_set = true; } else ctx->forcing_set = false;
+    ctx->drop_graph();
     return MHH_OK;
 }
 
@@ -1365,13 +1446,11 @@ int mhh_dycore_substep_surface(mhh_ctx* ctx, const mhh_fields* f, const mhh_para
 
 int mhh_dycore_step(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm, double dt)
 {
-    for (int ss = 0; ss < 3; ++ss)
-    {
-        int rc = mhh_dycore_substep(ctx, f, prm, ss, dt);
-        if (rc != MHH_OK) return rc;
-    }
-    return MHH_OK;
+    if (!f || !prm) return MHH_E_INVALID;
+    DISPATCH1(ctx, step_impl<TF>(c, f, prm, dt));
 }
+
+long long mhh_graph_replays(const mhh_ctx* ctx) { return ctx ? ctx->graph_replays : 0; }
 
 int mhh_dycore_step_host(mhh_ctx* ctx, const mhh_fields* f, const mhh_params* prm, double dt, int nsteps,
                          void* h_u, void* h_v, void* h_w, void* const* h_s)

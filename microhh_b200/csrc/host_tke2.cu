@@ -128,6 +128,7 @@ int mhh_dycore_set_tke2(mhh_ctx* ctx, const mhh_tke2* tke)
     if (!ctx) return MHH_E_INVALID;
     if (tke) { ctx->tke2 = *tke; ctx->tke2_set = true; }
     else { ctx->tke2 = mhh_tke2{}; ctx->tke2_set = false; }
+    ctx->drop_graph();
     return MHH_OK;
 }
 

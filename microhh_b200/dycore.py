@@ -116,6 +116,11 @@ class Context:
         return json.loads(out.value.decode())
 
     @property
+    def graph_replays(self):
+        """steps of mhh_dycore_step / _step_host that ran as a replayed CUDA graph"""
+        return int(self.lib.mhh_graph_replays(self.h))
+
+    @property
     def transport(self):
         """'single', 'nccl' (grouped send/recv transposes and halos) or 'peer' (fused NVLink peer stores)"""
         return ("single", "nccl", "peer")[int(self.lib.mhh_comm_transport(self.h))]
