@@ -113,6 +113,7 @@ evisc3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ 
     }
     const TF dxi = g.dxi, dyi = g.dyi;
     const TF e8 = TF(0.125);
+    const TF tPr_i = TF(1.) / a.tPr;
 
     auto colload = [&](const TF* __restrict__ fld, int lev, int c) -> TF {
         return (lev >= 0 && lev < g.kcells) ? fld[ij[c] + (long long)lev * kk] : TF(0);
@@ -184,8 +185,8 @@ evisc3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ 
                 if (bottom_mo) n2 = a.dbdz[ij[c]];
                 else if (a.n2mode == 1) n2 = p_gth[n] * TF(0.5) * (th_p - th_m[c]) * dzi_k;
                 else n2 = n2v[c];
-                TF rit = n2 / (s2 * a.tPr);
-                rit = rit < TF(1. - DSMALL) ? rit : TF(1. - DSMALL);
+                // S2 (1 - min(Ri / tPr, 1 - dsmall)) without the division: max(S2 - N2 / tPr, S2 (1 - (1 - dsmall)))
+                const TF lo = s2 * (TF(1.) - TF(1. - DSMALL)), sr = s2 - n2 * tPr_i;
                 TF m2 = p_m0[n];
                 if (SURFACE && a.mason)
                 {
@@ -193,7 +194,7 @@ evisc3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ 
                     const TF t2 = t * t;
                     m2 = m2 * t2 / (m2 + t2);       // == 1/(1/mlen0^2 + 1/(kappa (z+z0))^2)
                 }
-                a.evisc[o_k] = m2 * sqrtf_(s2 * (TF(1.) - rit));
+                a.evisc[o_k] = m2 * sqrtf_(sr > lo ? sr : lo);
             }
             t0[c] = nt0; t1[c] = nt1; r0[c] = nr0; r1[c] = nr1;
             th_m[c] = th_c[c]; th_c[c] = th_p;

@@ -75,7 +75,9 @@ struct mhh_ctx
     // launch-bound on the small grids (drycblles 128^3, moser180), so the second step with identical arguments is captured on
     // the context's own stream and replayed from then on.  MHH_GRAPH=0 keeps every step eager; profiling, slabs (NCCL), a failed
     // capture or changing arguments (adaptive dt) run eagerly as well.
-    bool use_graph = true;
+    // MHH_GRAPH unset: replay when a field is at most 512 MiB (measured: 128^3 fp64 1.18 -> 1.00 ms/step, moser180-shaped DNS
+    // 4.59 -> 4.16, 512x512x256 fp32 18.6 -> 18.4; nothing to gain at 512^3 fp64 and beyond); 1: always; 0: never
+    bool use_graph = true; int graph_mode = -1;
     cudaGraphExec_t graph_exec = nullptr;
     unsigned long long graph_key = 0, graph_seen = 0;
     long long graph_launches = 0, graph_replays = 0;

@@ -75,7 +75,7 @@ int create_impl(const mhh_grid_desc* d, int dtype, int device, mhh_ctx** out)
     { const char* e = getenv("MHH_NO_TMA"); c->no_tma = e && e[0] == '1'; }
     { const char* e = getenv("MHH_FUSE_SCALAR"); if (e) c->fuse_scalar = e[0] == '1'; }
     { const char* e = getenv("MHH_FUSE_ADVEC2"); if (e) c->fuse_advec2 = e[0] == '1'; }
-    { const char* e = getenv("MHH_GRAPH"); if (e) c->use_graph = e[0] == '1'; }
+    { const char* e = getenv("MHH_GRAPH"); if (e) { c->use_graph = e[0] == '1'; c->graph_mode = c->use_graph ? 1 : 0; } }
     { const char* e = getenv("MHH_TILE3_Y"); if (e) { int v = atoi(e); if (v == 3 || v == 4 || v == 5) c->tile3_y = v; } }
     { const char* e = getenv("MHH_EVISC_MB"); if (e) c->evisc_mb = atoi(e); }
     { const char* e = getenv("MHH_EVISC_TMA"); if (e) c->evisc_tma = atoi(e) != 0; }
@@ -828,7 +828,8 @@ int step_eager(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, double dt
 template <typename TF>
 int step_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, double dt)
 {
-    if (!c->use_graph || c->nranks > 1 || c->desc.npy > 1 || c->prof || c->graph_failed || !c->own_stream)
+    if (!c->use_graph || c->nranks > 1 || c->desc.npy > 1 || c->prof || c->graph_failed || !c->own_stream
+        || (c->graph_mode < 0 && (size_t)c->g.ncells * sizeof(TF) > ((size_t)512 << 20)))
         return step_eager<TF>(c, f, prm, dt);
     // everything a captured launch bakes in: the field / parameter structs (pointers, switches, viscosities), dt, the registered
     // forcing and closure.  The user's stream is not part of it: the graph always runs on the context's own stream.

@@ -44,7 +44,8 @@ def les(dtype, swdiff="smag2", forcing=False, igc=4):
             rng = np.random.default_rng(4)
             p = lambda s=1.: (s*rng.standard_normal(gd.kcells)).astype(dtype)
             F = D.Forcing(ctx, f, swbuffer=True, zstart=float(0.7*g.zsize), sigma=2., beta=2.,
-                          bufferprofs=dict(u=p(), v=p(), w=p(0.1), th=(300. + p()).astype(dtype)), swlspres="uflux", uflux=0.1)
+                          bufferprofs=dict(u=p(), v=p(), w=p(0.1), th=(300. + p()).astype(dtype)), swlspres="geo", fc=1e-4, ug=p(), vg=p())
+            # (not swlspres = uflux: its domain means are atomic sums, whose rounding differs from run to run even eagerly)
             F.register(); keep.append(F)
         f._keep_alive = keep
         return D, ctx, f, D.Dycore(ctx, prm)
