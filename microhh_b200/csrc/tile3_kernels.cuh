@@ -149,13 +149,11 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
     }
 
     // ================================================================== consumer warps
-    // Velocities interpolated to a face enter the fluxes as the SUM of the two neighbours (twice the velocity) and the factor
-    // 1/2 moves into the metric (hdxi, hdyi, the fma that forms gt): scaling by two is exact in binary floating point, so the
-    // tendencies are bit for bit the same and every face flux saves one multiplication (13.5 per grid point).
+    // (Measured and rejected, profiles/r02/ab_mom3_sum2_*.json: passing face velocities as the SUM of the two neighbours and
+    // folding the exact factor 1/2 into the metric saves 13.5 multiplications per point bit for bit, yet ran 2.5 % slower in
+    // fp64 -- 17.2 / 17.6 vs 17.8 / 17.9 ms per step at 512^3: the register allocation under the 128-register cap got worse.)
     auto hflux = [](const TF vel, const TF x0, const TF x1, const TF x2, const TF x3, const TF x4, const TF x5) -> TF {
         return ADV2 ? flux2(vel, x2, x3) : flux65(vel, x0, x1, x2, x3, x4, x5); };
-    auto sum2 = [](const TF x0, const TF x1) -> TF { return x0 + x1; };
-    const TF hdxi = TF(0.5) * g.dxi, hdyi = TF(0.5) * g.dyi, mhalf = TF(-0.5);
     auto vfl = [](const int order, const TF vel, const TF c0, const TF c1, const TF c2, const TF c3, const TF c4, const TF c5) -> TF {
         return vflux_col<TF>(ADV2 ? min(order, 2) : order, vel, c0, c1, c2, c3, c4, c5); };
     auto colload = [&](const TF* __restrict__ fld, int lev, int c) -> TF {
@@ -233,7 +231,7 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
 #pragma unroll
             for (int m = 0; m < 3; ++m)
             {
-                fx[m] = hflux(sum2(X10(ux, m - 1), X10(ux, m)), X10(ux, m - 3), X10(ux, m - 2), X10(ux, m - 1), X10(ux, m), X10(ux, m + 1), X10(ux, m + 2));
+                fx[m] = hflux(interp2(X10(ux, m - 1), X10(ux, m)), X10(ux, m - 3), X10(ux, m - 2), X10(ux, m - 1), X10(ux, m), X10(ux, m + 1), X10(ux, m + 2));
                 dx_[m] = (X6(e0, m - 1) + visc) * (X10(ux, m) - X10(ux, m - 1)) * dxi;
             }
             TF gt[2];
@@ -241,7 +239,7 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
             for (int c = 0; c < 2; ++c)
             {
                 const TF uk = X10(ux, c), uk1 = U1R[c];
-                const TF ft_a = rhoh_f * vfl(of, sum2(X6(w6, c - 1), X6(w6, c)), ua[c], ub[c], uk, uk1, uc[c], ud[c]);      // twice the flux
+                const TF ft_a = rhoh_f * vfl(of, interp2(X6(w6, c - 1), X6(w6, c)), ua[c], ub[c], uk, uk1, uc[c], ud[c]);
                 TF ft_d;
                 if (SURFACE && f == ks) ft_d = -rhoh_f * a.u_fluxbot[ij + c];
                 else if (SURFACE && f == ke) ft_d = -rhoh_f * a.u_fluxtop[ij + c];
@@ -250,7 +248,7 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
                     const TF evisct = q * (s0r[c] + s1r[c]) + visc;
                     ft_d = rhoh_f * evisct * ((uk1 - uk) * dzhi_f + (X6(w6, c) - X6(w6, c - 1)) * dxi);
                 }
-                gt[c] = mhalf * ft_a + ft_d;
+                gt[c] = ft_d - ft_a;
             }
             if (st)
             {
@@ -260,14 +258,14 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
 #pragma unroll
                 for (int c = 0; c < 2; ++c)
                 {
-                    const TF fn = hflux(sum2(X6(vp6, c - 1), X6(vp6, c)), uy[1][c], uy[2][c], uy[3][c], uy[4][c], uy[5][c], uy[6][c]);
-                    const TF fs = hflux(sum2(X6(v6, c - 1), X6(v6, c)), uy[0][c], uy[1][c], uy[2][c], uy[3][c], uy[4][c], uy[5][c]);
+                    const TF fn = hflux(interp2(X6(vp6, c - 1), X6(vp6, c)), uy[1][c], uy[2][c], uy[3][c], uy[4][c], uy[5][c], uy[6][c]);
+                    const TF fs = hflux(interp2(X6(v6, c - 1), X6(v6, c)), uy[0][c], uy[1][c], uy[2][c], uy[3][c], uy[4][c], uy[5][c]);
                     const TF eviscn = q * (s0r[c] + s0p[c]) + visc;
                     const TF eviscs = q * (s0m[c] + s0r[c]) + visc;
                     const TF d = (dx_[c + 1] - dx_[c]) * TF(2.) * dxi
                                + (eviscn * ((uy[4][c] - uy[3][c]) * dyi + (X6(vp6, c) - X6(vp6, c - 1)) * dxi)
                                 - eviscs * ((uy[3][c] - uy[2][c]) * dyi + (X6(v6, c) - X6(v6, c - 1)) * dxi)) * dyi;
-                    const TF tu = -(fx[c + 1] - fx[c]) * hdxi - (fn - fs) * hdyi + d + (gt[c] - gu[c]) * rdzi_k;
+                    const TF tu = -(fx[c + 1] - fx[c]) * dxi - (fn - fs) * dyi + d + (gt[c] - gu[c]) * rdzi_k;
                     if (c == 0) old0 += tu; else old1 += tu;
                 }
                 gstore2(a.ut + o_k, old0, old1);
@@ -309,7 +307,7 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
             for (int c = 0; c < 2; ++c)
             {
                 const TF vk = X10(vx, c), vk1 = V1R[c];
-                const TF ft_a = rhoh_f * vfl(of, sum2(W1M[c], W1R[c]), va[c], vb[c], vk, vk1, vc[c], vd[c]);                  // twice the flux
+                const TF ft_a = rhoh_f * vfl(of, interp2(W1M[c], W1R[c]), va[c], vb[c], vk, vk1, vc[c], vd[c]);
                 TF ft_d;
                 if (SURFACE && f == ks) ft_d = -rhoh_f * a.v_fluxbot[ij + c];
                 else if (SURFACE && f == ke) ft_d = -rhoh_f * a.v_fluxtop[ij + c];
@@ -318,7 +316,7 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
                     const TF evisct = q * ((X6(em, c) + X6(e0, c)) + (E1M[c] + E1R[c])) + visc;
                     ft_d = rhoh_f * evisct * ((vk1 - vk) * dzhi_f + (W1R[c] - W1M[c]) * dyi);
                 }
-                gt[c] = mhalf * ft_a + ft_d;
+                gt[c] = ft_d - ft_a;
             }
             if (st)
             {
@@ -329,18 +327,18 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
 #pragma unroll
                 for (int m = 0; m < 3; ++m)
                 {
-                    fx[m] = hflux(sum2(X4(um4, m), X4(u4, m)), X10(vx, m - 3), X10(vx, m - 2), X10(vx, m - 1), X10(vx, m), X10(vx, m + 1), X10(vx, m + 2));
+                    fx[m] = hflux(interp2(X4(um4, m), X4(u4, m)), X10(vx, m - 3), X10(vx, m - 2), X10(vx, m - 1), X10(vx, m), X10(vx, m + 1), X10(vx, m + 2));
                     const TF eviscc = q * (s0m[m] + s0r[m]) + visc;
                     dx_[m] = eviscc * ((X10(vx, m) - X10(vx, m - 1)) * dxi + (X4(u4, m) - X4(um4, m)) * dyi);
                 }
 #pragma unroll
                 for (int c = 0; c < 2; ++c)
                 {
-                    const TF fn = hflux(sum2(vy[3][c], vy[4][c]), vy[1][c], vy[2][c], vy[3][c], vy[4][c], vy[5][c], vy[6][c]);
-                    const TF fs = hflux(sum2(vy[2][c], vy[3][c]), vy[0][c], vy[1][c], vy[2][c], vy[3][c], vy[4][c], vy[5][c]);
+                    const TF fn = hflux(interp2(vy[3][c], vy[4][c]), vy[1][c], vy[2][c], vy[3][c], vy[4][c], vy[5][c], vy[6][c]);
+                    const TF fs = hflux(interp2(vy[2][c], vy[3][c]), vy[0][c], vy[1][c], vy[2][c], vy[3][c], vy[4][c], vy[5][c]);
                     const TF d = (dx_[c + 1] - dx_[c]) * dxi
                                + ((X6(e0, c) + visc) * (vy[4][c] - vy[3][c]) * dyi - (X6(em, c) + visc) * (vy[3][c] - vy[2][c]) * dyi) * TF(2.) * dyi;
-                    const TF tv = -(fx[c + 1] - fx[c]) * hdxi - (fn - fs) * hdyi + d + (gt[c] - gv[c]) * rdzi_k;
+                    const TF tv = -(fx[c + 1] - fx[c]) * dxi - (fn - fs) * dyi + d + (gt[c] - gv[c]) * rdzi_k;
                     if (c == 0) old0 += tv; else old1 += tv;
                 }
                 gstore2(a.vt + o_k, old0, old1);
@@ -464,9 +462,9 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
             for (int c = 0; c < 2; ++c)
             {
                 const TF wf = X10(wx, c);
-                const TF ft_a = rho_c * vfl(oc, sum2(wf, we[c]), wa[c], wb[c], wf, we[c], wc[c], wd[c]);                      // twice the flux
+                const TF ft_a = rho_c * vfl(oc, interp2(wf, we[c]), wa[c], wb[c], wf, we[c], wc[c], wd[c]);
                 const TF ft_d = rho_c * (E1R[c] + visc) * (we[c] - wf) * dzi_c;
-                gt[c] = mhalf * ft_a + TF(2.) * ft_d;
+                gt[c] = TF(2.) * ft_d - ft_a;
             }
             if (st)
             {
@@ -477,7 +475,7 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
 #pragma unroll
                 for (int m = 0; m < 3; ++m)
                 {
-                    fx[m] = hflux(sum2(X4(u4, m), X4(u14, m)), X10(wx, m - 3), X10(wx, m - 2), X10(wx, m - 1), X10(wx, m), X10(wx, m + 1), X10(wx, m + 2));
+                    fx[m] = hflux(interp2(X4(u4, m), X4(u14, m)), X10(wx, m - 3), X10(wx, m - 2), X10(wx, m - 1), X10(wx, m), X10(wx, m + 1), X10(wx, m + 2));
                     const TF eviscx = q * (s0r[m] + s1r[m]) + visc;
                     dx_[m] = eviscx * ((X10(wx, m) - X10(wx, m - 1)) * dxi + (X4(u14, m) - X4(u4, m)) * dzhi_f);
                 }
@@ -488,11 +486,11 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
 #pragma unroll
                 for (int c = 0; c < 2; ++c)
                 {
-                    const TF fn = hflux(sum2(V0P[c], V1P[c]), wy[1][c], wy[2][c], wy[3][c], wy[4][c], wy[5][c], wy[6][c]);
-                    const TF fs = hflux(sum2(V0R[c], V1R[c]), wy[0][c], wy[1][c], wy[2][c], wy[3][c], wy[4][c], wy[5][c]);
+                    const TF fn = hflux(interp2(V0P[c], V1P[c]), wy[1][c], wy[2][c], wy[3][c], wy[4][c], wy[5][c], wy[6][c]);
+                    const TF fs = hflux(interp2(V0R[c], V1R[c]), wy[0][c], wy[1][c], wy[2][c], wy[3][c], wy[4][c], wy[5][c]);
                     const TF eviscn = q * ((X6(e0, c) + X6(e16, c)) + (EP0[c] + EP1[c])) + visc;
                     const TF eviscs = q * ((EM0[c] + X6(e0, c)) + (EM1[c] + X6(e16, c))) + visc;
-                    TF tw = -(fx[c + 1] - fx[c]) * hdxi - (fn - fs) * hdyi
+                    TF tw = -(fx[c + 1] - fx[c]) * dxi - (fn - fs) * dyi
                           + (dx_[c + 1] - dx_[c]) * dxi
                           + (eviscn * ((wy[4][c] - wy[3][c]) * dyi + (V1P[c] - V0P[c]) * dzhi_f)
                            - eviscs * ((wy[3][c] - wy[2][c]) * dyi + (V1R[c] - V0R[c]) * dzhi_f)) * dyi

@@ -33,7 +33,12 @@ B="python bench.py --workload 512x512x512 --no-side-configs --no-cpu-baseline --
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:mom3_kernel -s 4 -c 1 -o gpurun_out/z_mom3_advec2 -f $B --swadvec 2 > gpurun_out/z_ncu_a.log 2>&1; echo "ncu advec2 exit $?"
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:mom3_kernel -s 4 -c 1 -o gpurun_out/z_mom3_2i5 -f $B > gpurun_out/z_ncu_b.log 2>&1; echo "ncu 2i5 exit $?"
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:tke2_visc_kernel -s 4 -c 1 -o gpurun_out/z_tke2_visc -f python tools/tke2_bench.py --steps 1 > gpurun_out/z_ncu_c.log 2>&1; echo "ncu tke2 exit $?"
+# the reports themselves (~40 MB each) would push gpurun_out/ over the 64 MiB that travel back: keep the CSV pages only
 for n in z_mom3_advec2 z_mom3_2i5 z_tke2_visc; do
-  [ -f gpurun_out/$n.ncu-rep ] && ncu -i gpurun_out/$n.ncu-rep --page raw --csv > gpurun_out/${n}_raw.csv 2>/dev/null
+  if [ -f gpurun_out/$n.ncu-rep ]; then
+    ncu -i gpurun_out/$n.ncu-rep --page raw --csv > gpurun_out/${n}_raw.csv 2>/dev/null
+    ncu -i gpurun_out/$n.ncu-rep --page source --csv > gpurun_out/${n}_source.csv 2>/dev/null
+    rm -f gpurun_out/$n.ncu-rep
+  fi
 done
-ls -la gpurun_out/z_*.ncu-rep gpurun_out/z_*_raw.csv
+ls -la gpurun_out/z_*_raw.csv gpurun_out/z_*_source.csv; du -sh gpurun_out
