@@ -55,6 +55,7 @@ struct mhh_ctx
     bool no_tma = false;        // MHH_NO_TMA=1: keep the cp.async tile kernels (A/B comparisons)
     int tile3_y = 0;            // MHH_TILE3_Y: rows per CTA of the warp-specialised kernel; 0 = 3 rows with the scalar group (13 warps), 4 without
     bool fuse_scalar = true;    // MHH_FUSE_SCALAR=0: keep scalar 0 out of the momentum kernel (A/B comparisons)
+    bool scal_tma = true;       // MHH_SCAL_TMA=0: further scalars with the cp.async tile kernel instead of the TMA-staged scalar kernel (A/B switch)
     bool fuse_advec2 = true;    // MHH_FUSE_ADVEC2=0: Advec_2 + Diff_smag2 as two point-wise kernels instead of the fused TMA kernel (A/B switch)
     bool stream_vec2 = true;    // MHH_STREAM_VEC2=0: one cell per thread in rk3 / pres_out_rk3 (A/B switch)
     bool evisc_tma = true;      // MHH_EVISC_TMA=0: keep the cp.async eddy-viscosity kernel (A/B switch)

@@ -75,6 +75,7 @@ int create_impl(const mhh_grid_desc* d, int dtype, int device, mhh_ctx** out)
     { const char* e = getenv("MHH_NO_TMA"); c->no_tma = e && e[0] == '1'; }
     { const char* e = getenv("MHH_FUSE_SCALAR"); if (e) c->fuse_scalar = e[0] == '1'; }
     { const char* e = getenv("MHH_FUSE_ADVEC2"); if (e) c->fuse_advec2 = e[0] == '1'; }
+    { const char* e = getenv("MHH_SCAL_TMA"); if (e) c->scal_tma = e[0] == '1'; }
     { const char* e = getenv("MHH_GRAPH"); if (e) { c->use_graph = e[0] == '1'; c->graph_mode = c->use_graph ? 1 : 0; } }
     { const char* e = getenv("MHH_TILE3_Y"); if (e) { int v = atoi(e); if (v == 3 || v == 4 || v == 5) c->tile3_y = v; } }
     { const char* e = getenv("MHH_EVISC_MB"); if (e) c->evisc_mb = atoi(e); }

@@ -330,6 +330,44 @@ int mom3_launch(Ctx<TF>* c, const MomArgs<TF>& a, const ScalArgs<TF>* sc, bool s
     return MHH_OK;
 }
 
+// One further scalar with the TMA-staged kernel: the scalar group of mom3_kernel alone (SONLY), 64 x (8 | 12) tiles.  Returns
+// MHH_NOT_FUSED when the shared memory of the tile does not fit (the caller then runs the cp.async tile kernel).
+template <typename TF>
+int scal3_launch(Ctx<TF>* c, const ScalArgs<TF>& sc, bool surface, int hl)
+{
+    const GridDev<TF>& g = c->g;
+    constexpr int TYS = t3_sonly_ty<TF>();
+    if (hl != 4 && !(hl == 3 && sizeof(TF) == 8)) return MHH_NOT_FUSED;
+    const int ntx = (g.imax + T2_W - 1) / T2_W, nty = (g.jmax + TYS - 1) / TYS;
+    Tend3Args<TF> t{};
+    t.m.u = sc.u; t.m.v = sc.v; t.m.w = sc.w; t.m.evisc = sc.evisc; t.m.visc = sc.visc;
+    t.sc = sc;
+    t.kchunk = pick_kchunk_waves(ntx * nty, g.kmax, c->num_sms * mom3_min_blocks<TF>(), 2);
+    // the per-level profiles live in shared memory beside the planes: shorten the z-chunk until the CTA fits
+    const size_t limit = (size_t)227 * 1024;
+    while (t.kchunk > 16 && mom3_smem(sizeof(TF), t.kchunk, TYS, 1, hl) > limit) t.kchunk = (t.kchunk + 1) / 2;
+    const size_t smem = mom3_smem(sizeof(TF), t.kchunk, TYS, 1, hl);
+    if (smem > limit) return MHH_NOT_FUSED;
+    t.prefetch = c->prefetch;
+    dim3 grid(ntx, nty, (g.kmax + t.kchunk - 1) / t.kchunk);
+    CUtensorMap tu, tv, tw, te, ts, tst;
+    const int by = TYS + 2 * T2_H, px = t2_px(hl);
+    if (!make_field_tmap<TF>(&tu, sc.u, g, px, by) || !make_field_tmap<TF>(&tv, sc.v, g, px, by) ||
+        !make_field_tmap<TF>(&tw, sc.w, g, px, by) || !make_field_tmap<TF>(&te, sc.evisc, g, px, by) ||
+        !make_field_tmap<TF>(&ts, sc.s, g, px, by) || !make_field_tmap<TF>(&tst, sc.st, g, px, TYS))
+    { c->err = "cuTensorMapEncodeTiled failed"; return MHH_E_CUDA; }
+#define S3(S, H) do { \
+        static size_t attr_smem_dev[64] = {0}; size_t& attr_smem = attr_smem_dev[c->device & 63];   /* the attribute is per device */ \
+        if (attr_smem < smem) { CUDA_TRY(c, cudaFuncSetAttribute(mom3_kernel<TF, S, false, 1, TYS, H, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; } \
+        mom3_kernel<TF, S, false, 1, TYS, H, false, true><<<grid, 32 * (TYS + 1), smem, c->stream>>>(tu, tv, tw, te, ts, tst, tst, tst, tst, t, g); } while (0)
+#define S3H(S) do { if (hl == 4) S3(S, 4); else S3(S, (sizeof(TF) == 8 ? 3 : 4)); } while (0)
+    if (surface) S3H(true); else S3H(false);
+#undef S3H
+#undef S3
+    KCHECKN(c, "scal3_kernel");
+    return MHH_OK;
+}
+
 template <typename TF>
 int scal_tile_launch(Ctx<TF>* c, const ScalArgs<TF>& a, bool surface)
 {
@@ -384,13 +422,13 @@ int tend_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, bool adv, 
 #define LAUNCH_MOM(A, D, S, B) tend_uvw_kernel<TF, A, D, S, B><<<gr, b, 0, c->stream>>>(a, g)
     const bool tiles = adv && diff && g.igc >= TILE_H && g.jgc >= TILE_H && !c->force_plain;
     int first_scalar = 0;       // scalars [0, first_scalar) were handled by the fused momentum kernel
+    // TMA-staged path: needs a 16-byte aligned box origin istart - halo (halo 4 with igc = 4, what the adapters request;
+    // halo 3 for fp64 fields with igc = 3); everything else runs the cp.async tile kernels
+    const int hl = tiles ? t2_pick_hl(g.igc, (int)sizeof(TF)) : 0;
+    const bool tma = tiles && !c->no_tma && hl != 0
+                     && tma_ok<TF>(g, {a.u, a.v, a.w, a.evisc, a.ut, a.vt, a.wt, buoy ? (const void*)a.th : (const void*)a.u});
     if (tiles)
     {
-        // TMA-staged path: needs a 16-byte aligned box origin istart - halo (halo 4 with igc = 4, what the adapters request;
-        // halo 3 for fp64 fields with igc = 3); everything else runs the cp.async tile kernels
-        const int hl = t2_pick_hl(g.igc, (int)sizeof(TF));
-        const bool tma = !c->no_tma && hl != 0
-                         && tma_ok<TF>(g, {a.u, a.v, a.w, a.evisc, a.ut, a.vt, a.wt, buoy ? (const void*)a.th : (const void*)a.u});
         if (tma)
         {
             // scalar 0 rides along as the fourth warp group when its arrays qualify for TMA too
@@ -434,7 +472,10 @@ int tend_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, bool adv, 
         }
         if (tiles)
         {
-            if ((rc = scal_tile_launch<TF>(c, s, surface)) != MHH_OK) return rc;
+            // further scalars: the scalar group of the TMA kernel on its own, else the cp.async tile kernel
+            rc = (tma && c->scal_tma && tma_ok<TF>(g, {s.s, s.st, s.evisc})) ? scal3_launch<TF>(c, s, surface, hl) : MHH_NOT_FUSED;
+            if (rc == MHH_NOT_FUSED) rc = scal_tile_launch<TF>(c, s, surface);
+            if (rc != MHH_OK) return rc;
             continue;
         }
 #define LAUNCH_S(A, D, S) tend_s_kernel<TF, A, D, S><<<gr, b, 0, c->stream>>>(s, g)

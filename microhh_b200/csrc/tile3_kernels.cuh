@@ -26,6 +26,11 @@ constexpr int T3_RING = 4;
 
 inline size_t mom3_smem(size_t elem, int kchunk, int ty, int nsc, int hl)
 { return 128 + ((size_t)(4 + nsc) * T3_RING * t2_plane(ty, (int)elem, hl) + (size_t)8 * (kchunk + 3)) * elem + 128; }
+// consumer warps / threads of a CTA: (3 + NSC) groups of TY rows, or TY rows of the scalar alone (SONLY)
+constexpr int mom3_ncw(int nsc, int ty, bool sonly) { return sonly ? ty : (3 + nsc) * ty; }
+// rows of the scalar-only variant: fp32 12 (13 warps like the fused kernel, two CTAs per SM), fp64 8 (five fields x four ring
+// slots x the plane must fit the 227 KB of shared memory beside the profiles)
+template <typename TF> constexpr int t3_sonly_ty() { return sizeof(TF) == 4 ? 12 : 8; }
 
 // the first prognostic scalar rides along as a fourth warp group (NSC = 1): advec_s + diff_c on the same planes
 template <typename TF>
@@ -43,8 +48,10 @@ template <typename TF> constexpr int mom3_min_blocks() { return sizeof(TF) == 4 
 
 // ADV2: the advective fluxes of Advec_2 (src/advec_2.cxx:48-202: velocity * interp2 on every face) instead of Advec_2i5's --
 // cases/drycblles as shipped (swadvec = 2 with smag2) on the same staged planes.
-template <typename TF, bool SURFACE, bool BUOY, int NSC, int TY, int HL, bool ADV2 = false>
-__global__ void __launch_bounds__(32 * ((3 + NSC) * TY + 1), mom3_min_blocks<TF>())
+// SONLY (with NSC = 1): every consumer warp is a scalar warp -- advec_s + diff_c of ONE further prognostic scalar on the same
+// staged planes (u, v, w, the scalar's eddy viscosity, the scalar); the momentum tendencies are not touched.
+template <typename TF, bool SURFACE, bool BUOY, int NSC, int TY, int HL, bool ADV2 = false, bool SONLY = false>
+__global__ void __launch_bounds__(32 * (mom3_ncw(NSC, TY, SONLY) + 1), mom3_min_blocks<TF>())
 mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_v,
             const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_e,
             const __grid_constant__ CUtensorMap tm_s,
@@ -59,7 +66,8 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
     TF* sm = reinterpret_cast<TF*>(sbase + 128);
     constexpr int RING = T3_RING;
     constexpr int PLANE = t2_plane(TY, (int)sizeof(TF), HL), P = t2_px(HL), T2_HL = HL;
-    constexpr int NT = 32 * ((3 + NSC) * TY + 1), NCW = (3 + NSC) * TY;
+    constexpr int NCW = mom3_ncw(NSC, TY, SONLY), NT = 32 * (NCW + 1);
+    static_assert(!SONLY || (NSC == 1 && !BUOY), "the scalar-only variant is the scalar group alone");
     constexpr bool ODD = (HL & 1) != 0;             // own pair at an odd shared-memory column (fp64 with igc = 3)
     constexpr int NF = 4 + NSC;
     constexpr unsigned PLANE_BYTES = PLANE * sizeof(TF), BOX_BYTES = t2_box_bytes(TY, (int)sizeof(TF), HL);
@@ -69,7 +77,7 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
     // NSC = 1: four groups, group = warp % 4.  Warps are dealt round-robin to the four SM sub-partitions, so each
     // sub-partition then runs ONE component's loop and its instruction cache holds one code path instead of four
     // (measured: 14 % of the stall samples were instruction fetches with group = warp / TY).
-    const int comp = NSC ? (warp & 3) : warp / TY, ty = NSC ? (warp >> 2) : warp - (warp / TY) * TY;
+    const int comp = SONLY ? 3 : (NSC ? (warp & 3) : warp / TY), ty = SONLY ? warp : (NSC ? (warp >> 2) : warp - (warp / TY) * TY);
     const int i = g.istart + blockIdx.x * T2_W + 2 * tx;
     const int j = g.jstart + blockIdx.y * TY + ty;
     const int gi0 = g.istart + blockIdx.x * T2_W - T2_HL;
@@ -138,8 +146,11 @@ mom3_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
                     const int pt = lev + args.prefetch - 1;
                     if (pt >= kc0 && pt < kc1)
                     {
-                        tma_prefetch_3d(&tm_ut, gi0, gj0 + T2_H, pt); tma_prefetch_3d(&tm_vt, gi0, gj0 + T2_H, pt);
-                        tma_prefetch_3d(&tm_wt, gi0, gj0 + T2_H, pt + 1);
+                        if (!SONLY)
+                        {
+                            tma_prefetch_3d(&tm_ut, gi0, gj0 + T2_H, pt); tma_prefetch_3d(&tm_vt, gi0, gj0 + T2_H, pt);
+                            tma_prefetch_3d(&tm_wt, gi0, gj0 + T2_H, pt + 1);
+                        }
                         if (NSC) tma_prefetch_3d(&tm_st, gi0, gj0 + T2_H, pt);
                     }
                 }
