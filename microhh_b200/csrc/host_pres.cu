@@ -500,7 +500,7 @@ int pres_solve_impl(Ctx<TF>* c, const mhh_fields* f, double sub_dt)
         int rc0 = exchange_ns<TF>(c, &vt, 1, 1, g.kcells);
         if (rc0 != MHH_OK) return rc0;
     }
-    RhsSrc<TF> src{P<TF>(f->u), P<TF>(f->v), P<TF>(f->w), P<TF>(f->ut), P<TF>(f->vt), P<TF>(f->wt), (TF)(TF(1.) / sub_dt), slab ? 0 : 1};
+    RhsSrc<TF> src{P<TF>(f->u), P<TF>(f->v), P<TF>(f->w), P<TF>(f->ut), P<TF>(f->vt), P<TF>(f->wt), TF(1.) / (TF)sub_dt /* Pres_2::input takes dt as TF: TF(1.)/dt, src/pres_2.cxx:160,173 */, slab ? 0 : 1};
     if (c->fused)
     {
         int rcf = pres_fused_solve<TF>(c, nullptr, src, P<TF>(f->p), slab ? 0 : 1, true);
@@ -641,7 +641,7 @@ int pres4_exec_impl(Ctx<TF>* c, const mhh_fields* f, double sub_dt)
         pres4_wtbc_kernel<TF><<<g2, b2, 0, c->stream>>>(P<TF>(f->wt), g);
         KCHECKN(c, "pres4_wtbc_kernel");
     }
-    const TF dti = (TF)(1. / sub_dt);
+    const TF dti = (TF)(1. / (double)(TF)sub_dt);       // Pres_4::input takes dt as TF and forms 1./dt in double (src/pres_4.cxx:262,276)
     const bool slab = c->nranks > 1;
     // the right-hand side goes into the (free) p array as a compact (k, j, i) block, like the reference's pres_in does: the x
     // transform then reads it from there and its store phase is free to be the forward transpose

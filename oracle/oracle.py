@@ -1578,7 +1578,7 @@ class Pres4:
         """src/pres_4.cxx:254-317 (fills the ut/vt cyclic ghosts and the wt wall ghosts as a side effect)"""
         g = self.g; TF = g.TF
         dxi, dyi = TF(1./np.float64(g.dx)), TF(1./np.float64(g.dy))
-        dti = TF(1./dt)
+        dti = TF(1./np.float64(TF(dt)))      # `const TF dt` narrows the sub-step first, then `1./dt` in double (src/pres_4.cxx:262,276)
         dim3 = g.jtot > 1
         boundary_cyclic(g, ut, EDGE_EW)
         if dim3:
@@ -2005,6 +2005,68 @@ def force_wls_local(g, st, s, wls):
 
 
 # --------------------------------------------------------------------------------------
+# Thermo_buoy (reference src/thermo_buoy.cxx:41-296, exec :345-391): the prognostic scalar IS the buoyancy.
+# --------------------------------------------------------------------------------------
+def _sin(TF, a):
+    return TF(np.sin(TF(a)))      # std::sin(TF): libm sinf / sin; numpy calls the same libm scalar routine for a 0-d input
+
+def _cos(TF, a):
+    return TF(np.cos(TF(a)))
+
+def thermo_buoy_N2(g, N2, b, bg_n2):
+    """src/thermo_buoy.cxx:48-62"""
+    TF = g.TF
+    _S(g, N2)[...] = TF(0.5)*(_S(g, b, 1) - _S(g, b, -1))*_K(g, g.dzi) + TF(bg_n2)
+
+def _buoy_interp_z(g, b, order, k0, k1):
+    TF = g.TF
+    if order == 4:
+        return _i4c(TF, _S(g, b, -2, 0, 0, k0, k1), _S(g, b, -1, 0, 0, k0, k1), _S(g, b, 0, 0, 0, k0, k1), _S(g, b, 1, 0, 0, k0, k1))
+    return interp2(_S(g, b, -1, 0, 0, k0, k1), _S(g, b, 0, 0, 0, k0, k1))
+
+def thermo_buoy_tend(g, wt, b, order=2):
+    """calc_buoyancy_tend_2nd / _4th (src/thermo_buoy.cxx:93-108, 166-183)"""
+    k0, k1 = g.kstart+1, g.kend
+    _S(g, wt, 0, 0, 0, k0, k1)[...] += _buoy_interp_z(g, b, order, k0, k1)
+
+def thermo_buoy_tend_slope(g, ut, wt, bt, b, u, w, alpha, n2, utrans, order=2):
+    """calc_buoyancy_tend_u / _w / _b, 2nd and 4th order (src/thermo_buoy.cxx:110-164, 185-246)"""
+    TF = g.TF
+    sa, ca = _sin(TF, alpha), _cos(TF, alpha)
+    if order == 4:
+        bi = _i4c(TF, _S(g, b, 0, 0, -2), _S(g, b, 0, 0, -1), _S(g, b, 0, 0, 0), _S(g, b, 0, 0, 1))
+        ui = _i4c(TF, _S(g, u, 0, 0, -1), _S(g, u, 0, 0, 0), _S(g, u, 0, 0, 1), _S(g, u, 0, 0, 2))
+        wi = _i4c(TF, _S(g, w, -1), _S(g, w, 0), _S(g, w, 1), _S(g, w, 2))
+    else:
+        bi = interp2(_S(g, b, 0, 0, -1), _S(g, b))
+        ui = interp2(_S(g, u), _S(g, u, 0, 0, 1))
+        wi = interp2(_S(g, w), _S(g, w, 1))
+    _S(g, ut)[...] += sa*bi
+    k0, k1 = g.kstart+1, g.kend
+    _S(g, wt, 0, 0, 0, k0, k1)[...] += ca*_buoy_interp_z(g, b, order, k0, k1)
+    _S(g, bt)[...] -= TF(n2)*(sa*(ui + TF(utrans)) + ca*wi)
+
+def thermo_buoy_baroclinic(g, bt, v, dbdy_ls, order=2):
+    """calc_baroclinic_2nd / _4th (src/thermo_buoy.cxx:248-282)"""
+    TF = g.TF
+    if order == 4:
+        vi = _i4c(TF, _S(g, v, 0, -1), _S(g, v), _S(g, v, 0, 1), _S(g, v, 0, 2))
+    else:
+        vi = interp2(_S(g, v), _S(g, v, 0, 1))
+    _S(g, bt)[...] -= TF(dbdy_ls)*vi
+
+def thermo_buoy_exec(K, c, tb, order):
+    """Thermo_buoy::exec (src/thermo_buoy.cxx:345-391); tb: dict(alpha, n2, utrans, swbaroclinic, dbdy_ls); scalar 0 is b"""
+    b = c["scalars"][0]
+    if abs(tb.get("alpha", 0.)) > 0. or abs(tb.get("n2", 0.)) > 0.:
+        K.thermo_buoy_tend_slope(c["ut"], c["wt"], c[b + "t"], c[b], c["u"], c["w"], tb.get("alpha", 0.), tb.get("n2", 0.), tb.get("utrans", 0.), order)
+    else:
+        K.thermo_buoy_tend(c["wt"], c[b], order)
+    if tb.get("swbaroclinic", False):
+        K.thermo_buoy_baroclinic(c[b + "t"], c["v"], tb["dbdy_ls"], order)
+
+
+# --------------------------------------------------------------------------------------
 # Restart IO of one 3-D field: Field3d_io<TF>::save_field3d / load_field3d (serial build, src/field3d_io.cxx:669-751; called
 # for every prognostic field by Fields::save / load with offset 0, src/fields.cxx:1243-1320).  File = the interior
 # [kstart,kend) x jtot x itot as raw TF in C order, no header.  The MPI build writes the same single file through MPI-IO
@@ -2076,6 +2138,10 @@ class NumpyKernels:
     def diff_w(self, wt, u, v, w, evisc, rhoref, rhorefh, visc): diff_w(self.g, wt, u, v, w, evisc, rhoref, rhorefh, visc)
     def diff_c(self, at, a, evisc, fluxbot, fluxtop, rhoref, rhorefh, tPr, visc, surface): diff_c(self.g, at, a, evisc, fluxbot, fluxtop, rhoref, rhorefh, tPr, visc, surface)
     def diff_dnmul(self, evisc, tPr): return float(diff_dnmul(self.g, evisc, tPr))
+    def thermo_buoy_N2(self, N2, b, bg_n2): thermo_buoy_N2(self.g, N2, b, bg_n2)
+    def thermo_buoy_tend(self, wt, b, order=2): thermo_buoy_tend(self.g, wt, b, order)
+    def thermo_buoy_tend_slope(self, ut, wt, bt, b, u, w, alpha, n2, utrans, order=2): thermo_buoy_tend_slope(self.g, ut, wt, bt, b, u, w, alpha, n2, utrans, order)
+    def thermo_buoy_baroclinic(self, bt, v, dbdy_ls, order=2): thermo_buoy_baroclinic(self.g, bt, v, dbdy_ls, order)
     def tke2_enforce_min(self, sgstke): tke2_enforce_min(self.g, sgstke)
     def tke2_evisc_neutral(self, evisc, sgstke, u, v, w, z0m, cn, cm, mason=True): tke2_evisc_neutral(self.g, evisc, sgstke, z0m, cn, cm, mason)
     def tke2_evisc(self, evisc, sgstke, u, v, w, N2, bgradbot, z0m, cn, cm, mason=True): tke2_evisc(self.g, evisc, sgstke, N2, bgradbot, z0m, cn, cm, mason)

@@ -192,6 +192,19 @@ class RefKernels:
         return self._call("ref_diff_dnmul", evisc, g.dzi, TF(1./(float(g.dx)*float(g.dx))), TF(1./(float(g.dy)*float(g.dy))),
                           float(tPr), restype=C.c_double)
 
+    # --- thermo_buoy (oracle/ref/ref_thermo_buoy.cpp)
+    def thermo_buoy_N2(self, N2, b, bg_n2):
+        self._call("ref_thermo_buoy_N2", N2, b, float(bg_n2), self.g.dzi)
+
+    def thermo_buoy_tend(self, wt, b, order=2):
+        self._call("ref_thermo_buoy_tend", wt, b, int(order))
+
+    def thermo_buoy_tend_slope(self, ut, wt, bt, b, u, w, alpha, n2, utrans, order=2):
+        self._call("ref_thermo_buoy_tend_slope", ut, wt, bt, b, u, w, float(alpha), float(n2), float(utrans), int(order))
+
+    def thermo_buoy_baroclinic(self, bt, v, dbdy_ls, order=2):
+        self._call("ref_thermo_buoy_baroclinic", bt, v, float(dbdy_ls), int(order))
+
     # --- diff_tke2 + limiter (oracle/ref/ref_diff_tke2.cpp)
     def tke2_enforce_min(self, sgstke):
         self._call("ref_tke2_enforce_min", sgstke)

@@ -154,7 +154,7 @@ def _pres_and_rk3(g, K, c, prm, substep, dt, pres, lap):
     return pres
 
 
-def dycore_substep_o4(g, K, c, prm, substep, dt, pres=None):
+def dycore_substep_o4(g, K, c, prm, substep, dt, pres=None, forcing=None):
     """The 4th-order DNS configuration (swspatialorder=4: advec_4 or advec_4m + diff_4 + pres_4, no thermo), same call order of
     Model<TF>::exec (src/model.cxx:368-437): cyclic -> 4th-order ghost cells (w: normal type) -> w conservation type ->
     advec -> w normal -> diff -> w conservation -> pres -> w normal -> rk3."""
@@ -168,6 +168,8 @@ def dycore_substep_o4(g, K, c, prm, substep, dt, pres=None):
     for s in scal:
         K.ghost_cells_bot_4th(c[s], prm["sbcbot"], c.get(s + "_bot"), c.get(s + "_gradbot"))
         K.ghost_cells_top_4th(c[s], prm["sbctop"], c.get(s + "_top"), c.get(s + "_gradtop"))
+    if prm.get("swthermo") == "buoy":
+        O.thermo_buoy_exec(K, c, prm.get("thermo_buoy", {}), 4)              # thermo.exec (src/model.cxx:388): w ghost cells still of the normal type
     K.ghost_cells_w_4th(c["w"], True)
     a4 = "advec_4m_" if prm.get("swadvec") == "4m" else "advec_4_"          # src/advec.cxx:79-84
     getattr(K, a4 + "u")(c["ut"], c["u"], c["v"], c["w"])
@@ -181,6 +183,8 @@ def dycore_substep_o4(g, K, c, prm, substep, dt, pres=None):
     K.diff_4_w(c["wt"], c["w"], prm["visc"])
     for s in scal:
         K.diff_4_c(c[s + "t"], c[s], prm["svisc"])
+    if forcing is not None:
+        forcing(c, O.rk3_subdt(dt, substep))       # buffer.exec + force.exec (src/model.cxx:416-430)
     K.ghost_cells_w_4th(c["w"], True)
     if pres is None:
         pres = O.Pres4(g)
@@ -196,7 +200,7 @@ def dycore_step(g, K, c, prm, dt, timers=None, surface_model=None, forcing=None,
     refbind.RefPres, the reference's own compiled Pres_2 / Pres_4 member functions)."""
     for ss in range(3):
         if prm.get("swadvec") in ("4", "4m"):
-            pres = dycore_substep_o4(g, K, c, prm, ss, dt, pres)
+            pres = dycore_substep_o4(g, K, c, prm, ss, dt, pres, forcing)
         else:
             pres = dycore_substep(g, K, c, prm, ss, dt, pres, timers, surface_model, forcing)
     return pres

@@ -561,3 +561,70 @@ def test_field3d_io_bitexact(dtype, shape, order, offset, tmp_path):
     assert np.array_equal(interior(g, b0), (interior(g, a) + dtype(offset)) - dtype(offset))
     assert (b0[0] == 7.).all()                                                                       # ghost cells untouched
     assert O.field3d_load(g, b0, str(tmp_path / "missing"), offset) != 0 and R.load(b1, tmp_path / "missing", offset) != 0
+
+
+def _o4_pair(shape, dtype, stretched):
+    """4th-order grid + synthetic case for both sides (as test_full_rk3_step_order4_bitexact)"""
+    from microhh_b200.grid import GridData
+    from microhh_b200.synthetic import make_case
+    from util import stretched_z
+    z = stretched_z(shape[2], 2.) if stretched else None
+    g = O.Grid(*shape, 2*np.pi, np.pi, 2., 3, 3, 3, dtype, z=z, order=4)
+    gd = GridData(*shape, 2*np.pi, np.pi, 2., 3, 3, 3, dtype, z=z, order=4)
+    case = make_case(gd, seed=5, noise=0.02)
+    case["w"][:g.kstart+1] = 0; case["w"][g.kend:] = 0
+    for n in ("u", "v"):
+        for sfx in ("_bot", "_top", "_gradbot", "_gradtop"):
+            case[n + sfx] = np.zeros(gd.shape2d, dtype)
+    case["th_gradbot"] = np.full(gd.shape2d, -0.3, dtype); case["th_gradtop"] = np.full(gd.shape2d, 0.2, dtype)
+    return g, gd, case
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("order", [2, 4])
+@pytest.mark.parametrize("stretched", [False, True])
+def test_thermo_buoy_kernels_bitexact(dtype, order, stretched):
+    """Thermo_buoy (src/thermo_buoy.cxx:41-296): N2, buoyancy tendency, slope variants, baroclinic term, 2nd and 4th order."""
+    if order == 4:
+        g, gd, case = _o4_pair((16, 12, 10), dtype, stretched)
+    else:
+        g, gd, case = make_pair(16, 12, 10, dtype, stretched=stretched)
+    N, R = both(g)
+    rng = np.random.default_rng(17)
+    b = (0.1*rng.standard_normal(gd.shape)).astype(dtype)
+    seeds = {n: rng.standard_normal(gd.shape).astype(dtype) for n in ("ut", "wt", "bt")}
+    res = []
+    for K in (N, R):
+        o = {}
+        n2 = np.zeros(gd.shape, dtype); K.thermo_buoy_N2(n2, b, 1.5e-4); o["N2"] = n2
+        wt = seeds["wt"].copy(); K.thermo_buoy_tend(wt, b, order); o["wt"] = wt
+        ut, wt, bt = seeds["ut"].copy(), seeds["wt"].copy(), seeds["bt"].copy()
+        K.thermo_buoy_tend_slope(ut, wt, bt, b, case["u"], case["w"], 0.17, 2.e-3, 0.4, order)
+        o["ut_s"], o["wt_s"], o["bt_s"] = ut, wt, bt
+        bt = seeds["bt"].copy(); K.thermo_buoy_baroclinic(bt, case["v"], 3.e-4, order); o["bt_b"] = bt
+        res.append(o)
+    for n in res[0]:
+        assert np.array_equal(res[0][n], res[1][n]), (n, float(np.abs(res[0][n].astype(np.float64) - res[1][n]).max()))
+    assert not np.array_equal(res[0]["bt_s"], seeds["bt"])
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("tb", [{}, dict(alpha=0.2, n2=1.e-2, utrans=0.1), dict(swbaroclinic=True, dbdy_ls=2.e-3)])
+def test_full_rk3_step_order4_buoy_bitexact(dtype, tb):
+    """The 4th-order DNS step with swthermo = buoy (cases/drycbl, rayleighbenard, weakscaling ...): thermo.exec between the
+    ghost cells and the advection, plain / slope-enabled / baroclinic."""
+    g, gd, case = _o4_pair((16, 12, 10), dtype, True)
+    case["scalars"] = ["th"]            # scalar 0 is the buoyancy
+    case["th"] = (case["th"] - dtype(300.)).astype(dtype)
+    c0, c1 = copy.deepcopy(case), copy.deepcopy(case)
+    N, R = both(g)
+    prm = ostep.default_params(); prm.update(swadvec="4m", swdiff="4", swthermo="buoy", thermo_buoy=tb, visc=1e-3, svisc=1e-3,
+                                             mbcbot=0, mbctop=0)
+    ostep.dycore_step(g, N, c0, prm, 1e-3)
+    ostep.dycore_step(g, R, c1, prm, 1e-3, pres=refbind.RefPres(g, 4))
+    for n in ("u", "v", "w", "th", "p"):
+        assert np.array_equal(c0[n], c1[n]), n
+    c2 = copy.deepcopy(case)
+    prm2 = dict(prm); prm2.update(swthermo=None)
+    ostep.dycore_step(g, N, c2, prm2, 1e-3)
+    assert not np.array_equal(c0["w"], c2["w"])                          # the buoyancy does act
