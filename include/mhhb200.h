@@ -112,7 +112,8 @@ typedef struct mhh_params
     int    swadvec;              /* 25 = 2i5, 2 = 2, 4 = 4, 41 = 4m */
     int    swdiff;               /* 1 = smag2, 2 = 2, 3 = tke2 (needs mhh_dycore_set_tke2), 4 = 4 (the 4th-order configuration:
                                   * 4 + 4 + pres_4 on a 4th-order grid) */
-    int    swthermo;             /* 0 = off, 1 = dry (buoyancy from scalar 0 = th) */
+    int    swthermo;             /* 0 = off, 1 = dry (buoyancy from scalar 0 = th), 2 = buoy (scalar 0 IS the buoyancy b;
+                                  * the fused sub-steps need mhh_dycore_set_thermo_buoy) */
     int    surface_model;        /* Boundary switch != "default"  (Surface_model::Enabled) */
     int    sw_mason;             /* [diff] swmason */
     double cs, tPr;              /* [diff] cs, tPr */
@@ -164,6 +165,16 @@ typedef struct mhh_tke2
     void  *eviscs;               /* DEVICE field (ghosted layout); may be NULL when swthermo == 0 */
     double ap, cf, ce1, ce2, cm, ch1, ch2, cn;
 } mhh_tke2;
+
+/* Thermo_buoy<TF> (src/thermo_buoy.cxx:306-330): [thermo] alpha (slope angle, rad), N2 (background stratification),
+ * swbaroclinic / dbdy_ls, and [grid] utrans.  Slope-enabled thermodynamics is on when |alpha| > 0 or |N2| > 0. */
+typedef struct mhh_thermo_buoy
+{
+    double alpha, n2;
+    double utrans;               /* Grid_data::utrans (calc_buoyancy_tend_b adds it to the interpolated u) */
+    int    swbaroclinic;
+    double dbdy_ls;
+} mhh_thermo_buoy;
 
 /* ---- context ----------------------------------------------------------------------------- */
 MHH_API int  mhh_ctx_create(const mhh_grid_desc* grid, int dtype, int device, mhh_ctx** out);
@@ -306,6 +317,14 @@ MHH_API int mhh_diff_4_exec(mhh_ctx* ctx, const mhh_fields* f);
 /* ---- Thermo_dry<TF>::exec (buoyancy on wt) and get_thermo_field("N2")  (src/thermo_dry.cxx) -- */
 MHH_API int mhh_thermo_dry_exec(mhh_ctx* ctx, void* wt, const void* th);
 MHH_API int mhh_thermo_dry_n2(mhh_ctx* ctx, void* n2, const void* th);
+/* ---- Thermo_buoy<TF>::exec (src/thermo_buoy.cxx:345-391; 2nd- or 4th-order by the context's grid): buoyancy on wt, with
+ * slope-enabled thermodynamics also on ut and on the buoyancy tendency st[0], the baroclinic term on st[0]; one kernel.
+ * Reads s[0] = b (cyclic + vertical ghost cells filled), u, v, w.  get_thermo_field("N2") (:410-413) = _n2 with bg_n2 = [thermo] N2.
+ * mhh_dycore_set_thermo_buoy registers the parameters for the fused sub-steps with prm->swthermo = 2 (NULL: unregister);
+ * thermo.exec then runs where Model::exec has it (src/model.cxx:388), before the advection. */
+MHH_API int mhh_thermo_buoy_exec(mhh_ctx* ctx, const mhh_fields* f, const mhh_thermo_buoy* tb);
+MHH_API int mhh_thermo_buoy_n2(mhh_ctx* ctx, void* n2, const void* b, double bg_n2);
+MHH_API int mhh_dycore_set_thermo_buoy(mhh_ctx* ctx, const mhh_thermo_buoy* tb);
 
 /* ---- Pres<TF>::exec / check_divergence: swpres = 2 -> Pres_2 (src/pres_2.cxx:66-105);
  *      swpres = 4 -> Pres_4 (src/pres_4.cxx:76-156; 7-band solve per mode; needs a 4th-order grid; single GPU) -- */

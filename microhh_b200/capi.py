@@ -63,6 +63,10 @@ class Tke2C(C.Structure):
                 ("cm", C.c_double), ("ch1", C.c_double), ("ch2", C.c_double), ("cn", C.c_double)]
 
 
+class ThermoBuoyC(C.Structure):
+    _fields_ = [("alpha", C.c_double), ("n2", C.c_double), ("utrans", C.c_double), ("swbaroclinic", C.c_int), ("dbdy_ls", C.c_double)]
+
+
 class SurfaceC(C.Structure):
     _fields_ = [("ustar", C.c_void_p), ("obuk", C.c_void_p), ("nobuk", C.c_void_p), ("z0m", C.c_void_p), ("z0h", C.c_void_p),
                 ("dutot", C.c_void_p), ("sbcbot", C.c_int * MHH_MAX_SCALARS)]
@@ -128,6 +132,9 @@ SIGNATURES = {
     "mhh_diff_2_get_dn": (C.c_int, [_vp, _PF, C.c_double, C.POINTER(C.c_double)]),
     "mhh_thermo_dry_exec": (C.c_int, [_vp, _vp, _vp]),
     "mhh_thermo_dry_n2": (C.c_int, [_vp, _vp, _vp]),
+    "mhh_thermo_buoy_exec": (C.c_int, [_vp, _PF, C.POINTER(ThermoBuoyC)]),
+    "mhh_thermo_buoy_n2": (C.c_int, [_vp, _vp, _vp, C.c_double]),
+    "mhh_dycore_set_thermo_buoy": (C.c_int, [_vp, C.POINTER(ThermoBuoyC)]),
     "mhh_pres_exec": (C.c_int, [_vp, C.c_int, _PF, C.c_double]),
     "mhh_pres_check_divergence": (C.c_int, [_vp, C.c_int, _PF, C.POINTER(C.c_double)]),
     "mhh_pres_fft_roundtrip": (C.c_int, [_vp, _vp, _vp, C.c_int]),

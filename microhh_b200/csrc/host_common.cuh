@@ -27,6 +27,7 @@
 #include "order2_kernels.cuh"
 #include "order4_kernels.cuh"
 #include "pres4_kernels.cuh"
+#include "thermo_buoy_kernels.cuh"
 #include <cudaTypedefs.h>
 #include <dlfcn.h>
 #include <nccl.h>
@@ -89,6 +90,8 @@ struct mhh_ctx
     void *io_dev = nullptr, *io_host = nullptr; size_t io_cap = 0;
     // Diff_tke2 registered for the fused sub-steps (mhh_dycore_set_tke2)
     mhh_tke2 tke2{}; bool tke2_set = false;
+    // Thermo_buoy registered for the fused sub-steps (mhh_dycore_set_thermo_buoy; prm->swthermo = 2)
+    mhh_thermo_buoy buoy{}; bool buoy_set = false;
     virtual ~mhh_ctx() {}
 };
 
@@ -244,6 +247,8 @@ template <typename TF> int reduce_mode_impl(Ctx<TF>* c, int mode, const TF* u, c
 template <typename TF> int tke2_check(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, const mhh_tke2* tke);
 template <typename TF> int tke2_visc_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, const mhh_tke2* tke, const TF* n2);
 template <typename TF> int limiter_impl(Ctx<TF>* c, TF* at, const TF* a, TF min_value, TF sub_dt);
+// host_thermo.cu
+template <typename TF> int thermo_buoy_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_thermo_buoy* tb);
 // host_pres.cu
 template <typename TF> int pres_create(Ctx<TF>* c);
 template <typename TF> int pres_set_values(Ctx<TF>* c);

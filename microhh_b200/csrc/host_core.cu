@@ -398,7 +398,10 @@ int ghost4w_impl(Ctx<TF>* c, TF* w, int conservation)
 template <typename TF>
 int substep_o4_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, int substep, double dt)
 {
-    if (prm->swthermo != 0) { c->err = "the 4th-order sub-step has no thermo coupling (swthermo = 0)"; return MHH_E_INVALID; }
+    // thermo on a 4th-order grid is Thermo_buoy (every shipped swspatialorder = 4 case with thermo: drycbl, drycblslope,
+    // prandtlslope, rayleighbenard, rayleightaylor, vanheerwaarden2016, weakscaling); Thermo_dry's kernels are 2nd-order only
+    if (prm->swthermo != 0 && prm->swthermo != 2) { c->err = "the 4th-order sub-step couples to swthermo = buoy (2) only"; return MHH_E_INVALID; }
+    if (prm->swthermo == 2 && !c->buoy_set) { c->err = "dycore_substep: swthermo = buoy needs mhh_dycore_set_thermo_buoy"; return MHH_E_INVALID; }
     int rc = check_mom<TF>(c, f, false, false);
     if (rc != MHH_OK) return rc;
     NEED(c, f->p, "p");
@@ -410,7 +413,13 @@ int substep_o4_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, int 
     for (int n = 0; n < f->ns; ++n)
         if ((rc = ghost4_impl<TF>(c, P<TF>(f->s[n]), prm->sbcbot[n], P<TF>(f->s_bot[n]), P<TF>(f->s_gradbot[n]),
                                   prm->sbctop[n], P<TF>(f->s_top[n]), P<TF>(f->s_gradtop[n]))) != MHH_OK) return rc;
-    if ((rc = ghost4w_impl<TF>(c, P<TF>(f->w), 1)) != MHH_OK) return rc;        // (the normal-type fill right before is overwritten)
+    if (prm->swthermo == 2)
+    {
+        // thermo.exec (src/model.cxx:388) still sees the normal-type w ghost cells of Boundary::set_ghost_cells
+        if ((rc = ghost4w_impl<TF>(c, P<TF>(f->w), 0)) != MHH_OK) return rc;
+        if ((rc = thermo_buoy_impl<TF>(c, f, &c->buoy)) != MHH_OK) return rc;
+    }
+    if ((rc = ghost4w_impl<TF>(c, P<TF>(f->w), 1)) != MHH_OK) return rc;        // (without thermo the normal-type fill before it would only be overwritten)
     if ((rc = o4_impl<TF>(c, f, prm->swadvec, false)) != MHH_OK) return rc;
     if ((rc = ghost4w_impl<TF>(c, P<TF>(f->w), 0)) != MHH_OK) return rc;
     if ((rc = o4_impl<TF>(c, f, 0, true)) != MHH_OK) return rc;
@@ -452,6 +461,13 @@ int substep_check(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, bool& 
     if ((prm->swadvec != 25 && prm->swadvec != 2) || (prm->swdiff != 1 && prm->swdiff != 2 && prm->swdiff != 3))
     { c->err = "dycore_substep: swadvec must be 2i5 (25), 2, 4 or 4m (41), swdiff smag2 (1), 2, tke2 (3) or 4"; return MHH_E_INVALID; }
     const bool smag = prm->swdiff == 1 || prm->swdiff == 3;
+    if (prm->swthermo < 0 || prm->swthermo > 2) { c->err = "dycore_substep: swthermo must be 0, dry (1) or buoy (2)"; return MHH_E_INVALID; }
+    if (prm->swthermo == 2)
+    {
+        // the eddy-viscosity kernels derive N2 and the surface buoyancy gradient the Thermo_dry way; no shipped case pairs buoy with an LES closure
+        if (smag) { c->err = "dycore_substep: swthermo = buoy goes with swdiff = 2 or 4 (the LES closures are wired to Thermo_dry)"; return MHH_E_INVALID; }
+        if (!c->buoy_set) { c->err = "dycore_substep: swthermo = buoy needs mhh_dycore_set_thermo_buoy"; return MHH_E_INVALID; }
+    }
     int rc = check_mom<TF>(c, f, smag, smag && prm->surface_model != 0);
     if (rc != MHH_OK) return rc;
     if (prm->swdiff == 3)
@@ -504,6 +520,7 @@ int tendencies_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm)
     if (o4) { c->err = "dycore_tendencies: use mhh_advec_exec / mhh_diff_4_exec on a 4th-order grid (they see different w ghost cells)"; return MHH_E_INVALID; }
     const bool smag = prm->swdiff == 1 || prm->swdiff == 3, adv5 = prm->swadvec == 25, buoy = prm->swthermo == 1;
     const mhh_tke2* tke = prm->swdiff == 3 ? &c->tke2 : nullptr;                             // Diff_tke2::exec = the smag2 kernels, evisc per scalar
+    if (prm->swthermo == 2 && (rc = thermo_buoy_impl<TF>(c, f, &c->buoy)) != MHH_OK) return rc;  // Thermo_buoy::exec, ahead of advec.exec like Model::exec
     if (adv5 && smag) rc = tend_impl<TF>(c, f, prm, true, true, buoy, tke);                  // 2i5 + smag2 | tke2 (+ buoyancy)
     else if (!adv5 && !smag) rc = o2_impl<TF>(c, f, true, true, buoy);                       // 2 + 2 (+ buoyancy)
     else if (!adv5)                                                                          // 2 + smag2 (drycblles as shipped)
@@ -836,8 +853,9 @@ int step_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, double dt)
     // forcing and closure.  The user's stream is not part of it: the graph always runs on the context's own stream.
     unsigned long long key = 1469598103934665603ull;
     key = fnv1a(key, f, sizeof(*f)); key = fnv1a(key, prm, sizeof(*prm)); key = fnv1a(key, &dt, sizeof(dt));
-    const int flags[3] = {c->forcing_set ? 1 : 0, c->tke2_set ? 1 : 0, c->overlap ? 1 : 0};
+    const int flags[4] = {c->forcing_set ? 1 : 0, c->tke2_set ? 1 : 0, c->overlap ? 1 : 0, c->buoy_set ? 1 : 0};
     key = fnv1a(key, flags, sizeof(flags));
+    if (c->buoy_set) key = fnv1a(key, &c->buoy, sizeof(c->buoy));
     if (c->forcing_set) key = fnv1a(key, &c->forcing, sizeof(c->forcing));
     if (c->tke2_set) key = fnv1a(key, &c->tke2, sizeof(c->tke2));
     if (key == 0) key = 1;

@@ -15,6 +15,7 @@ from .capi import FieldsC, ParamsC, GridDesc, SurfaceC, ForcingC, MhhError
 
 SWADVEC = {"2i5": 25, "2": 2, "4": 4, "4m": 41}
 SWDIFF = {"smag2": 1, "2": 2, "tke2": 3, "4": 4}
+SWTHERMO = {"0": 0, None: 0, "disabled": 0, "dry": 1, "buoy": 2}
 
 
 def _ptr(t):
@@ -204,7 +205,7 @@ def make_params(swadvec="2i5", swdiff="smag2", swthermo="dry", surface_model=Tru
                 sbcbot=capi.BC_NEUMANN, sbctop=capi.BC_NEUMANN, ns=1):
     p = ParamsC()
     p.swadvec = SWADVEC[swadvec]; p.swdiff = SWDIFF[swdiff]
-    p.swthermo = 1 if swthermo == "dry" else 0
+    p.swthermo = SWTHERMO[swthermo]
     p.surface_model = int(surface_model); p.sw_mason = int(sw_mason)
     p.cs = cs; p.tPr = tPr
     p.mbcbot = mbcbot; p.mbctop = mbctop
@@ -359,6 +360,28 @@ class Thermo_dry:
 
     def get_thermo_field_N2(self, out, fields):
         self.ctx.check(self.ctx.lib.mhh_thermo_dry_n2(self.ctx.h, _ptr(out), _ptr(fields[fields.scalars[0]])))
+
+
+class Thermo_buoy:
+    """Thermo_buoy<TF> (src/thermo_buoy.cxx): scalar 0 of the fields is the buoyancy b.  alpha / n2: [thermo] alpha, N2
+    (slope-enabled thermodynamics when either is non-zero), utrans: [grid] utrans, swbaroclinic / dbdy_ls: [thermo]."""
+
+    def __init__(self, ctx, alpha=0., n2=0., utrans=0., swbaroclinic=False, dbdy_ls=0.):
+        self.ctx = ctx
+        self.c = capi.ThermoBuoyC(float(alpha), float(n2), float(utrans), int(bool(swbaroclinic)), float(dbdy_ls))
+
+    def exec(self, fields):
+        self.ctx.check(self.ctx.lib.mhh_thermo_buoy_exec(self.ctx.h, C.byref(fields.c), C.byref(self.c)))
+
+    def get_thermo_field_N2(self, out, fields):
+        self.ctx.check(self.ctx.lib.mhh_thermo_buoy_n2(self.ctx.h, _ptr(out), _ptr(fields[fields.scalars[0]]), self.c.n2))
+
+    def register(self):
+        """Run thermo.exec inside the fused sub-steps of a Dycore with swthermo = "buoy" (mhh_dycore_set_thermo_buoy)."""
+        self.ctx.check(self.ctx.lib.mhh_dycore_set_thermo_buoy(self.ctx.h, C.byref(self.c)))
+
+    def unregister(self):
+        self.ctx.check(self.ctx.lib.mhh_dycore_set_thermo_buoy(self.ctx.h, None))
 
 
 class Pres:

@@ -57,6 +57,8 @@ def dycore_substep(g, K, c, prm, substep, dt, pres=None, timers=None, surface_mo
     # thermo.exec
     if prm["swthermo"] == "dry":
         K.thermo_dry_buoyancy_tend_2nd(c["wt"], c[scal[0]], c["threfh"])
+    elif prm["swthermo"] == "buoy":
+        O.thermo_buoy_exec(K, c, prm.get("thermo_buoy", {}), 2)                 # Thermo_buoy::exec, Grid_order::Second branch
     # boundary.exec (Monin-Obukhov surface model) + boundary.set_ghost_cells again (src/model.cxx:398-401)
     if surface_model is not None:
         surface_model.exec(c, c["thref"], c["threfh"], neutral=prm["swthermo"] != "dry")

@@ -628,3 +628,22 @@ def test_full_rk3_step_order4_buoy_bitexact(dtype, tb):
     prm2 = dict(prm); prm2.update(swthermo=None)
     ostep.dycore_step(g, N, c2, prm2, 1e-3)
     assert not np.array_equal(c0["w"], c2["w"])                          # the buoyancy does act
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("tb", [{}, dict(alpha=0.2, n2=1.e-2, utrans=0.1, swbaroclinic=True, dbdy_ls=2.e-3)])
+def test_full_rk3_step_order2_buoy_bitexact(dtype, tb):
+    """swthermo = buoy on a 2nd-order grid (Thermo_buoy::exec's Grid_order::Second branch) with advec_2i5 + diff_2."""
+    g, gd, case = make_pair(16, 12, 10, dtype, stretched=True)
+    case["th"] = (case["th"] - dtype(300.)).astype(dtype)
+    c0, c1 = copy.deepcopy(case), copy.deepcopy(case)
+    N, R = both(g)
+    prm = ostep.default_params(); prm.update(swdiff="2", swthermo="buoy", thermo_buoy=tb, surface_model=False, visc=1e-2, svisc=1e-2)
+    ostep.dycore_step(g, N, c0, prm, 1e-2)
+    ostep.dycore_step(g, R, c1, prm, 1e-2, pres=refbind.RefPres(g, 2, c1["rhoref"], c1["rhorefh"]))
+    for n in ("u", "v", "w", "th", "p"):
+        assert np.array_equal(c0[n], c1[n]), n
+    c2 = copy.deepcopy(case)
+    prm2 = dict(prm); prm2.update(swthermo=None)
+    ostep.dycore_step(g, N, c2, prm2, 1e-2)
+    assert not np.array_equal(c0["w"], c2["w"])
