@@ -36,7 +36,7 @@ def grids(order, shape, dtype, stretched=True):
 
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("order", [2, 4])
-@pytest.mark.parametrize("shape", [(32, 16, 12), (70, 9, 10), (24, 1, 8)])
+@pytest.mark.parametrize("shape", [(32, 16, 12), (60, 9, 10), (24, 1, 8)])
 def test_thermo_buoy_exec(dtype, order, shape):
     from microhh_b200 import dycore as D
     g, gd = grids(order, shape, dtype)
