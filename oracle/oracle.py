@@ -2067,6 +2067,253 @@ def thermo_buoy_exec(K, c, tb, order):
 
 
 # --------------------------------------------------------------------------------------
+# Thermo_moist (reference src/thermo_moist.cxx, include/thermo_moist_functions.h): liquid-water potential temperature thl and
+# total water qt, buoyancy through the saturation adjustment.  Constants: include/constants.h:29-39, 73-84.  Every expression
+# keeps the reference's grouping (C++ evaluates a*b/c*d left to right).
+# --------------------------------------------------------------------------------------
+class _MC:
+    """Constants::* in precision TF (`template<typename TF> constexpr TF`: derived constants are formed in TF)"""
+    def __init__(self, TF):
+        self.TF = TF
+        self.grav, self.Rd, self.Rv, self.cp = TF(9.81), TF(287.04), TF(461.5), TF(1005)
+        self.Lv, self.Lf, self.T0, self.p0 = TF(2.501e6), TF(3.337e5), TF(273.15), TF(1.e5)
+        self.Ls = self.Lv + self.Lf
+        self.ep = self.Rd/self.Rv
+        self.c = [TF(x) for x in (+6.1121000000E+02, +4.4393067270E+01, +1.4279398448E+00, +2.6415206946E-02, +3.0291749160E-04,
+                                  +2.1159987257E-06, +7.5015702516E-09, -1.5604873363E-12, -9.9726710231E-14, -4.8165754883E-17,
+                                  +1.3839187032E-18)]
+
+_MCS = {}
+def _mc(TF):
+    if TF not in _MCS:
+        _MCS[TF] = _MC(TF)
+    return _MCS[TF]
+
+def moist_exner(TF, p):
+    """exner (functions.h:151-155): pow(p/p0, Rd/cp)"""
+    C = _mc(TF)
+    return _libm_pow(np.atleast_1d(np.asarray(p, TF)/C.p0).astype(TF), C.Rd/C.cp).reshape(np.shape(p)).astype(TF)
+
+def moist_esat_liq(TF, T):
+    C = _mc(TF)
+    x = np.minimum(np.maximum(TF(-75.), T - C.T0), TF(50.))
+    r = C.c[9] + x*C.c[10]
+    for n in range(8, -1, -1):
+        r = C.c[n] + x*r
+    return r
+
+def moist_qsat_liq(TF, p, T):
+    C = _mc(TF); es = moist_esat_liq(TF, T)
+    return C.ep*es/(p - (TF(1.) - C.ep)*es)
+
+def moist_esat_ice(TF, T):
+    C = _mc(TF)
+    x = np.minimum(np.maximum(TF(-100.), T - C.T0), TF(50.))
+    return TF(611.15)*_libm_exp(np.atleast_1d(TF(22.452)*x/(TF(272.55) + x)).astype(TF)).reshape(np.shape(x))
+
+def moist_qsat_ice(TF, p, T):
+    C = _mc(TF); es = moist_esat_ice(TF, T)
+    return C.ep*es/(p - (TF(1.) - C.ep)*es)
+
+def moist_water_fraction(TF, T):
+    C = _mc(TF)
+    return np.maximum(TF(0.), np.minimum((T - TF(233.15))/(C.T0 - TF(233.15)), TF(1.)))
+
+def moist_qsat(TF, p, T):
+    a = moist_water_fraction(TF, T)
+    return a*moist_qsat_liq(TF, p, T) + (TF(1.) - a)*moist_qsat_ice(TF, p, T)
+
+def _moist_dqsatdT(TF, p, T, es, L):
+    C = _mc(TF)
+    den = p - es*(TF(1.) - C.ep)
+    return (C.ep/den + (TF(1.) - C.ep)*C.ep*es/(den*den))*L*es/(C.Rv*(T*T))
+
+def moist_dqsatdT_liq(TF, p, T):
+    return _moist_dqsatdT(TF, p, T, moist_esat_liq(TF, T), _mc(TF).Lv)
+
+def moist_dqsatdT_ice(TF, p, T):
+    return _moist_dqsatdT(TF, p, T, moist_esat_ice(TF, T), _mc(TF).Ls)
+
+def moist_virtual_temperature(TF, exn, thl, qt, ql, qi):
+    C = _mc(TF)
+    th = thl + C.Lv*ql/(C.cp*exn) + C.Ls*qi/(C.cp*exn)
+    return th*(TF(1.) - (TF(1.) - C.Rv/C.Rd)*qt - C.Rv/C.Rd*(ql + qi))
+
+def moist_buoyancy(TF, exn, thl, qt, ql, qi, thvref):
+    return _mc(TF).grav*(moist_virtual_temperature(TF, exn, thl, qt, ql, qi) - thvref)/thvref
+
+def moist_buoyancy_no_ql(TF, thl, qt, thvref):
+    C = _mc(TF)
+    return C.grav*(thl*(TF(1.) - (TF(1.) - C.Rv/C.Rd)*qt) - thvref)/thvref
+
+def moist_buoyancy_flux_no_ql(TF, thl, thlflux, qt, qtflux, thvref):
+    C = _mc(TF)
+    return C.grav/thvref*(thlflux*(TF(1.) - (TF(1.) - C.Rv/C.Rd)*qt) - (TF(1.) - C.Rv/C.Rd)*thl*qtflux)
+
+def moist_sat_adjust(TF, thl, qt, p, exn):
+    """sat_adjust (functions.h:164-268) for arrays thl, qt at one pressure p / exner exn: returns ql, qi, t, qs.  The Newton
+    loops run per point exactly as often as the scalar code does (points drop out of the active set one by one)."""
+    C = _mc(TF)
+    thl = np.asarray(thl, TF); qt = np.asarray(qt, TF)
+    shape = thl.shape
+    thl = thl.ravel(); qt = qt.ravel()
+    p = TF(p); exn = TF(exn)
+    tl = thl*exn
+    qs = moist_qsat_liq(TF, p, tl)
+    ql = np.zeros_like(tl); qi = np.zeros_like(tl); t = tl.copy()
+    sat = ~((qt - qs) <= TF(0.))
+    idx = np.nonzero(sat)[0]
+    if idx.size:
+        tls, qts = tl[idx], qt[idx]
+        warm = tls >= C.T0
+        tnr = tls.copy(); tnr_old = np.full_like(tls, TF(1.e9)); niter = np.zeros(tls.shape, np.int64)
+        Lvcp = C.Lv/C.cp
+        with np.errstate(all="ignore"):
+            while True:
+                act = (np.abs(tnr - tnr_old)/tnr_old > TF(1.e-5)) & (niter < 10)
+                if not act.any():
+                    break
+                a = np.nonzero(act)[0]
+                niter[a] += 1
+                tn = tnr[a]; tnr_old[a] = tn
+                w = warm[a]
+                new = np.empty_like(tn)
+                if w.any():
+                    tw = tn[w]
+                    q = moist_qsat_liq(TF, p, tw)
+                    f = tw - tls[a][w] - Lvcp*(qts[a][w] - q)
+                    fp = TF(1.) + Lvcp*moist_dqsatdT_liq(TF, p, tw)
+                    new[w] = tw - f/fp
+                c = ~w
+                if c.any():
+                    tc = tn[c]; tlc = tls[a][c]; qtc = qts[a][c]
+                    q = moist_qsat(TF, p, tc)
+                    aw = moist_water_fraction(TF, tc); ai = TF(1.) - aw
+                    da = np.where((aw > TF(0.)) & (aw < TF(1.)), TF(0.025), TF(0.)).astype(TF)
+                    dw = moist_dqsatdT_liq(TF, p, tc); di = moist_dqsatdT_ice(TF, p, tc)
+                    f = (tc - tlc - aw*C.Lv/C.cp*qtc - ai*C.Ls/C.cp*qtc
+                         + aw*C.Lv/C.cp*q + ai*C.Ls/C.cp*q)
+                    fp = (TF(1.)
+                          - da*C.Lv/C.cp*qtc + da*C.Ls/C.cp*qtc
+                          + da*C.Lv/C.cp*q - da*C.Ls/C.cp*q
+                          + aw*C.Lv/C.cp*dw
+                          + ai*C.Ls/C.cp*di)
+                    new[c] = tc - f/fp
+                tnr[a] = new
+        if (niter == 10).any():
+            raise RuntimeError("Non-converging saturation adjustment")
+        qsw = moist_qsat_liq(TF, p, tnr)
+        qsc = moist_qsat(TF, p, tnr)
+        aw = moist_water_fraction(TF, tnr)
+        qlqi = np.maximum(TF(0.), qts - qsc)
+        ql[idx] = np.where(warm, np.maximum(TF(0.), qts - qsw), aw*qlqi)
+        qi[idx] = np.where(warm, TF(0.), (TF(1.) - aw)*qlqi)
+        t[idx] = tnr
+        qs[idx] = np.where(warm, qsw, qsc)
+    return ql.reshape(shape), qi.reshape(shape), t.reshape(shape), qs.reshape(shape)
+
+def _sa1(TF, thl, qt, p, exn):
+    ql, qi, _, _ = moist_sat_adjust(TF, np.array([thl], TF), np.array([qt], TF), p, exn)
+    return ql[0], qi[0]
+
+def moist_top_and_bot(g, thl0, qt0):
+    """calc_top_and_bot (src/thermo_moist.cxx:57-76): ghost values of the reference profiles"""
+    TF = g.TF; ks, ke = g.kstart, g.kend
+    for a in (thl0, qt0):
+        s = a[ks] - g.z[ks]*(a[ks+1] - a[ks])*g.dzhi[ks+1]
+        t = a[ke-1] + (g.zh[ke] - g.z[ke-1])*(a[ke-1] - a[ke-2])*g.dzhi[ke-1]
+        a[ks-1] = TF(2.)*s - a[ks]
+        a[ke] = TF(2.)*t - a[ke-1]
+
+def moist_base_state(g, thlmean, qtmean, pbot):
+    """calc_base_state (functions.h:271-340): hydrostatic pressure, exner, thv and density at full and half levels.
+    Returns dict(pref, prefh, rhoref, rhorefh, thvref, thvrefh, exnref, exnrefh) of kcells entries (zeros where the reference
+    leaves its vectors untouched)."""
+    TF = g.TF; C = _mc(TF); ks, ke = g.kstart, g.kend
+    z = lambda: np.zeros(g.kcells, TF)
+    pref, prefh, rho, rhoh, thv, thvh, ex, exh = z(), z(), z(), z(), z(), z(), z(), z()
+    e1 = lambda x: _libm_exp(np.array([x], TF))[0]
+    x1 = lambda p: moist_exner(TF, np.array([p], TF))[0]
+    thlsurf = TF(0.5)*(thlmean[ks-1] + thlmean[ks]); qtsurf = TF(0.5)*(qtmean[ks-1] + qtmean[ks])
+    prefh[ks] = TF(pbot); exh[ks] = x1(prefh[ks])
+    ql, qi = _sa1(TF, thlsurf, qtsurf, prefh[ks], exh[ks])
+    thvh[ks] = moist_virtual_temperature(TF, exh[ks], thlsurf, qtsurf, ql, qi)
+    rhoh[ks] = TF(pbot)/(C.Rd*exh[ks]*thvh[ks])
+    pref[ks] = prefh[ks]*e1(-C.grav*g.z[ks]/(C.Rd*exh[ks]*thvh[ks]))
+    for k in range(ks+1, ke+1):
+        ex[k-1] = x1(pref[k-1])
+        ql, qi = _sa1(TF, thlmean[k-1], qtmean[k-1], pref[k-1], ex[k-1])
+        thv[k-1] = moist_virtual_temperature(TF, ex[k-1], thlmean[k-1], qtmean[k-1], ql, qi)
+        rho[k-1] = pref[k-1]/(C.Rd*ex[k-1]*thv[k-1])
+        prefh[k] = prefh[k-1]*e1(-C.grav*g.dz[k-1]/(C.Rd*ex[k-1]*thv[k-1]))
+        exh[k] = x1(prefh[k])
+        thli = TF(0.5)*(thlmean[k-1] + thlmean[k]); qti = TF(0.5)*(qtmean[k-1] + qtmean[k])
+        ql, qi = _sa1(TF, thli, qti, prefh[k], exh[k])
+        thvh[k] = moist_virtual_temperature(TF, exh[k], thli, qti, ql, qi)
+        rhoh[k] = prefh[k]/(C.Rd*exh[k]*thvh[k])
+        pref[k] = pref[k-1]*e1(-C.grav*g.dzh[k]/(C.Rd*exh[k]*thvh[k]))
+    pref[ks-1] = TF(2.)*prefh[ks] - pref[ks]
+    return dict(pref=pref, prefh=prefh, rhoref=rho, rhorefh=rhoh, thvref=thv, thvrefh=thvh, exnref=ex, exnrefh=exh)
+
+def mean_profile(g, fld):
+    """Field3d_operators::calc_mean_profile (src/field3d_operators.cxx:45-66): double accumulation over the interior of every
+    level (ghost levels included), in i-fastest order, divided by itot*jtot"""
+    TF = g.TF
+    n = np.float64(g.itot*g.jtot)
+    inner = fld[:, g.jstart:g.jend, g.istart:g.iend].astype(np.float64).reshape(g.kcells, -1)
+    out = np.empty(g.kcells, np.float64)
+    for k in range(g.kcells):
+        out[k] = np.add.accumulate(inner[k])[-1] if inner.shape[1] else 0.      # sequential sum, not numpy's pairwise one
+    return (out/n).astype(TF)
+
+def thermo_moist_buoyancy_tend_2nd(g, wt, thl, qt, ph, thvrefh):
+    """calc_buoyancy_tend_2nd (src/thermo_moist.cxx:77-120)"""
+    TF = g.TF
+    for k in range(g.kstart+1, g.kend):
+        exnh = moist_exner(TF, np.array([ph[k]], TF))[0]
+        sl = (k, slice(g.jstart, g.jend), slice(g.istart, g.iend)); sm = (k-1,) + sl[1:]
+        thlh = interp2(thl[sm], thl[sl]); qth = interp2(qt[sm], qt[sl])
+        ql, qi, _, _ = moist_sat_adjust(TF, thlh, qth, ph[k], exnh)
+        wt[sl] += moist_buoyancy(TF, exnh, thlh, qth, ql, qi, thvrefh[k])
+
+def thermo_moist_buoyancy(g, b, thl, qt, p, thvref):
+    """calc_buoyancy (src/thermo_moist.cxx:122-168): get_thermo_field("b"); no condensate outside kstart..kend-1"""
+    TF = g.TF
+    for k in range(g.kcells):
+        ex = moist_exner(TF, np.array([p[k]], TF))[0]
+        sl = (k, slice(g.jstart, g.jend), slice(g.istart, g.iend))
+        if g.kstart <= k < g.kend:
+            ql, qi, _, _ = moist_sat_adjust(TF, thl[sl], qt[sl], p[k], ex)
+        else:
+            ql = np.zeros_like(thl[sl]); qi = ql
+        b[sl] = moist_buoyancy(TF, ex, thl[sl], qt[sl], ql, qi, thvref[k])
+
+def thermo_moist_liquid_water(g, ql, thl, qt, p):
+    """calc_liquid_water (src/thermo_moist.cxx:230-250): get_thermo_field("ql")"""
+    TF = g.TF
+    for k in range(g.kstart, g.kend):
+        ex = moist_exner(TF, np.array([p[k]], TF))[0]
+        sl = (k, slice(g.jstart, g.jend), slice(g.istart, g.iend))
+        ql[sl] = moist_sat_adjust(TF, thl[sl], qt[sl], p[k], ex)[0]
+
+def thermo_moist_N2(g, N2, thl, thvref):
+    """calc_N2 (src/thermo_moist.cxx:459-475)"""
+    TF = g.TF
+    _S(g, N2)[...] = TF(GRAV)/_K(g, thvref)*TF(0.5)*(_S(g, thl, 1) - _S(g, thl, -1))*_K(g, g.dzi)
+
+def thermo_moist_buoyancy_bot(g, b, bbot, thl, thlbot, qt, qtbot, thvref, thvrefh):
+    """calc_buoyancy_bot (src/thermo_moist.cxx:637-655): whole 2-D planes, ghost cells included"""
+    TF = g.TF; ks = g.kstart
+    bbot[...] = moist_buoyancy_no_ql(TF, thlbot, qtbot, thvrefh[ks])
+    b[ks] = moist_buoyancy_no_ql(TF, thl[ks], qt[ks], thvref[ks])
+
+def thermo_moist_buoyancy_fluxbot(g, bfluxbot, thl, thlfluxbot, qt, qtfluxbot, thvrefh):
+    """calc_buoyancy_fluxbot (src/thermo_moist.cxx:675-693)"""
+    TF = g.TF; ks = g.kstart
+    bfluxbot[...] = moist_buoyancy_flux_no_ql(TF, thl[ks], thlfluxbot, qt[ks], qtfluxbot, thvrefh[ks])
+
+
+# --------------------------------------------------------------------------------------
 # Restart IO of one 3-D field: Field3d_io<TF>::save_field3d / load_field3d (serial build, src/field3d_io.cxx:669-751; called
 # for every prognostic field by Fields::save / load with offset 0, src/fields.cxx:1243-1320).  File = the interior
 # [kstart,kend) x jtot x itot as raw TF in C order, no header.  The MPI build writes the same single file through MPI-IO
@@ -2139,6 +2386,15 @@ class NumpyKernels:
     def diff_c(self, at, a, evisc, fluxbot, fluxtop, rhoref, rhorefh, tPr, visc, surface): diff_c(self.g, at, a, evisc, fluxbot, fluxtop, rhoref, rhorefh, tPr, visc, surface)
     def diff_dnmul(self, evisc, tPr): return float(diff_dnmul(self.g, evisc, tPr))
     def thermo_buoy_N2(self, N2, b, bg_n2): thermo_buoy_N2(self.g, N2, b, bg_n2)
+    def moist_base_state(self, thlmean, qtmean, pbot): return moist_base_state(self.g, thlmean, qtmean, pbot)
+    def moist_top_and_bot(self, thl0, qt0): moist_top_and_bot(self.g, thl0, qt0)
+    def mean_profile(self, fld): return mean_profile(self.g, fld)
+    def thermo_moist_buoyancy_tend_2nd(self, wt, thl, qt, ph, thvrefh): thermo_moist_buoyancy_tend_2nd(self.g, wt, thl, qt, ph, thvrefh)
+    def thermo_moist_buoyancy(self, b, thl, qt, p, thvref): thermo_moist_buoyancy(self.g, b, thl, qt, p, thvref)
+    def thermo_moist_liquid_water(self, ql, thl, qt, p): thermo_moist_liquid_water(self.g, ql, thl, qt, p)
+    def thermo_moist_N2(self, N2, thl, thvref): thermo_moist_N2(self.g, N2, thl, thvref)
+    def thermo_moist_buoyancy_bot(self, b, bbot, thl, thlbot, qt, qtbot, thvref, thvrefh): thermo_moist_buoyancy_bot(self.g, b, bbot, thl, thlbot, qt, qtbot, thvref, thvrefh)
+    def thermo_moist_buoyancy_fluxbot(self, bfluxbot, thl, thlfluxbot, qt, qtfluxbot, thvrefh): thermo_moist_buoyancy_fluxbot(self.g, bfluxbot, thl, thlfluxbot, qt, qtfluxbot, thvrefh)
     def thermo_buoy_tend(self, wt, b, order=2): thermo_buoy_tend(self.g, wt, b, order)
     def thermo_buoy_tend_slope(self, ut, wt, bt, b, u, w, alpha, n2, utrans, order=2): thermo_buoy_tend_slope(self.g, ut, wt, bt, b, u, w, alpha, n2, utrans, order)
     def thermo_buoy_baroclinic(self, bt, v, dbdy_ls, order=2): thermo_buoy_baroclinic(self.g, bt, v, dbdy_ls, order)

@@ -205,6 +205,42 @@ class RefKernels:
     def thermo_buoy_baroclinic(self, bt, v, dbdy_ls, order=2):
         self._call("ref_thermo_buoy_baroclinic", bt, v, float(dbdy_ls), int(order))
 
+    # --- thermo_moist (oracle/ref/ref_thermo_moist.cpp)
+    def moist_base_state(self, thlmean, qtmean, pbot):
+        g = self.g; TF = g.TF
+        names = ("pref", "prefh", "rhoref", "rhorefh", "thvref", "thvrefh", "exnref", "exnrefh")
+        out = {n: np.zeros(g.kcells, TF) for n in names}
+        c = lambda a: np.ascontiguousarray(np.asarray(a, TF)[:g.kcells])
+        self._call("ref_moist_base_state", *[out[n] for n in names], c(thlmean), c(qtmean), float(pbot), c(g.z), c(g.dz), c(g.dzh))
+        return out
+
+    def moist_top_and_bot(self, thl0, qt0):
+        g = self.g; self._call("ref_moist_top_and_bot", thl0, qt0, g.z, g.zh, g.dzhi)
+
+    def mean_profile(self, fld):
+        g = self.g
+        out = np.zeros(g.kcells, g.TF)
+        self._call("ref_mean_profile", out, fld, int(g.itot), int(g.jtot))
+        return out
+
+    def thermo_moist_buoyancy_tend_2nd(self, wt, thl, qt, ph, thvrefh):
+        self._call("ref_moist_buoyancy_tend_2nd", wt, thl, qt, ph, thvrefh)
+
+    def thermo_moist_buoyancy(self, b, thl, qt, p, thvref):
+        self._call("ref_moist_buoyancy", b, thl, qt, p, thvref)
+
+    def thermo_moist_liquid_water(self, ql, thl, qt, p):
+        self._call("ref_moist_liquid_water", ql, thl, qt, p)
+
+    def thermo_moist_N2(self, N2, thl, thvref):
+        self._call("ref_moist_N2", N2, thl, self.g.dzi, thvref)
+
+    def thermo_moist_buoyancy_bot(self, b, bbot, thl, thlbot, qt, qtbot, thvref, thvrefh):
+        self._call("ref_moist_buoyancy_bot", b, bbot, thl, thlbot, qt, qtbot, thvref, thvrefh)
+
+    def thermo_moist_buoyancy_fluxbot(self, bfluxbot, thl, thlfluxbot, qt, qtfluxbot, thvrefh):
+        self._call("ref_moist_buoyancy_fluxbot", bfluxbot, thl, thlfluxbot, qt, qtfluxbot, thvrefh)
+
     # --- diff_tke2 + limiter (oracle/ref/ref_diff_tke2.cpp)
     def tke2_enforce_min(self, sgstke):
         self._call("ref_tke2_enforce_min", sgstke)

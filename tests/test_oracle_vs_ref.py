@@ -647,3 +647,60 @@ def test_full_rk3_step_order2_buoy_bitexact(dtype, tb):
     prm2 = dict(prm); prm2.update(swthermo=None)
     ostep.dycore_step(g, N, c2, prm2, 1e-2)
     assert not np.array_equal(c0["w"], c2["w"])
+
+
+def moist_case(g, gd, dtype, seed=3, cold=False):
+    """A bomex-like (or, `cold`, mixed-phase) moist state on the test grid: thl rising with height, qt falling, noise, and a
+    moist layer that saturates a good share of the points so that the Newton loops of sat_adjust run."""
+    rng = np.random.default_rng(seed)
+    zfull = np.asarray(g.z, np.float64)[:, None, None]
+    zrel = zfull/float(g.zsize)
+    t0 = 262. if cold else 298.
+    thl = t0 + 6.*zrel + 0.3*rng.standard_normal(gd.shape)
+    qsurf = 2.4e-3 if cold else 17.e-3
+    qt = qsurf*(1. - 0.5*zrel) + (0.8e-3 if cold else 3.e-3)*np.exp(-((zrel - 0.45)/0.15)**2) + 1.e-4*rng.standard_normal(gd.shape)
+    return thl.astype(dtype), np.maximum(qt, 1e-5).astype(dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("cold", [False, True])
+def test_thermo_moist_bitexact(dtype, cold):
+    """Thermo_moist (src/thermo_moist.cxx, include/thermo_moist_functions.h): base state, saturation adjustment inside the
+    buoyancy tendency, the b / ql / N2 diagnostics and the surface buoyancy helpers, warm and mixed-phase."""
+    g, gd, case = make_pair(16, 12, 24, dtype, stretched=True, sizes=(3200., 3200., 3000.))
+    N, R = both(g)
+    thl, qt = moist_case(g, gd, dtype, cold=cold)
+    rng = np.random.default_rng(23)
+    # mean profiles (ghost levels included) -> reference profiles with calc_top_and_bot ghosts -> base state
+    mt = [K.mean_profile(thl) for K in (N, R)]; mq = [K.mean_profile(qt) for K in (N, R)]
+    assert np.array_equal(mt[0], mt[1]) and np.array_equal(mq[0], mq[1])
+    tb = []
+    for K in (N, R):
+        a, b = mt[0].copy(), mq[0].copy(); K.moist_top_and_bot(a, b); tb.append((a, b))
+    assert np.array_equal(tb[0][0], tb[1][0]) and np.array_equal(tb[0][1], tb[1][1])
+    pbot = 101500. if not cold else 70000.
+    bs = [K.moist_base_state(tb[0][0], tb[0][1], pbot) for K in (N, R)]
+    for n in bs[0]:
+        assert np.array_equal(bs[0][n], bs[1][n]), (n, bs[0][n], bs[1][n])
+    assert 0.9 < bs[0]["rhorefh"][g.kstart] < 1.3 or cold
+    b0 = bs[0]
+    res = []
+    for K in (N, R):
+        o = {}
+        wt = rng.standard_normal(gd.shape).astype(dtype) if not res else res[0]["wt0"].copy()
+        o["wt0"] = wt.copy()
+        K.thermo_moist_buoyancy_tend_2nd(wt, thl, qt, b0["prefh"], b0["thvrefh"]); o["wt"] = wt
+        b = np.zeros(gd.shape, dtype); K.thermo_moist_buoyancy(b, thl, qt, b0["pref"], b0["thvref"] + (b0["thvref"] == 0)*dtype(300.)); o["b"] = b
+        ql = np.zeros(gd.shape, dtype); K.thermo_moist_liquid_water(ql, thl, qt, b0["pref"]); o["ql"] = ql
+        n2 = np.zeros(gd.shape, dtype); K.thermo_moist_N2(n2, thl, b0["thvref"]); o["N2"] = n2
+        bb = np.zeros(gd.shape, dtype); bbot = np.zeros(gd.shape2d, dtype)
+        K.thermo_moist_buoyancy_bot(bb, bbot, thl, thl[g.kstart] + dtype(0.5), qt, qt[g.kstart]*dtype(1.1), b0["thvref"], b0["thvrefh"])
+        o["b_ks"], o["bbot"] = bb, bbot
+        bf = np.zeros(gd.shape2d, dtype)
+        K.thermo_moist_buoyancy_fluxbot(bf, thl, np.full(gd.shape2d, 8.e-3, dtype), qt, np.full(gd.shape2d, 5.2e-5, dtype), b0["thvrefh"])
+        o["bfluxbot"] = bf
+        res.append(o)
+    for n in res[0]:
+        assert np.array_equal(res[0][n], res[1][n]), (n, float(np.abs(res[0][n].astype(np.float64) - res[1][n]).max()))
+    frac = float((interior(g, res[0]["ql"]) > 0).mean())
+    assert 0.05 < frac < 0.95, frac                       # both branches of the adjustment are exercised
