@@ -113,7 +113,8 @@ typedef struct mhh_params
     int    swdiff;               /* 1 = smag2, 2 = 2, 3 = tke2 (needs mhh_dycore_set_tke2), 4 = 4 (the 4th-order configuration:
                                   * 4 + 4 + pres_4 on a 4th-order grid) */
     int    swthermo;             /* 0 = off, 1 = dry (buoyancy from scalar 0 = th), 2 = buoy (scalar 0 IS the buoyancy b;
-                                  * the fused sub-steps need mhh_dycore_set_thermo_buoy) */
+                                  * the fused sub-steps need mhh_dycore_set_thermo_buoy), 3 = moist (scalars thl and qt, thl first;
+                                  * needs mhh_dycore_set_thermo_moist and a base state, see mhh_thermo_moist_*) */
     int    surface_model;        /* Boundary switch != "default"  (Surface_model::Enabled) */
     int    sw_mason;             /* [diff] swmason */
     double cs, tPr;              /* [diff] cs, tPr */
@@ -175,6 +176,18 @@ typedef struct mhh_thermo_buoy
     int    swbaroclinic;
     double dbdy_ls;
 } mhh_thermo_buoy;
+
+/* Thermo_moist<TF> (src/thermo_moist.cxx:1080-1133): the prognostic scalars thl and qt, [thermo] pbot and swupdatebasestate. */
+typedef struct mhh_thermo_moist
+{
+    int    ithl, iqt;            /* indices of thl and qt in mhh_fields.s / .st */
+    double pbot;                 /* surface pressure [Pa] */
+    int    swupdatebasestate;    /* != 0: exec re-integrates the hydrostatic base state from the horizontal means of thl and qt */
+} mhh_thermo_moist;
+/* get_thermo_field names served on the device */
+#define MHH_MOIST_B  0
+#define MHH_MOIST_QL 1
+#define MHH_MOIST_N2 2
 
 /* ---- context ----------------------------------------------------------------------------- */
 MHH_API int  mhh_ctx_create(const mhh_grid_desc* grid, int dtype, int device, mhh_ctx** out);
@@ -325,6 +338,36 @@ MHH_API int mhh_thermo_dry_n2(mhh_ctx* ctx, void* n2, const void* th);
 MHH_API int mhh_thermo_buoy_exec(mhh_ctx* ctx, const mhh_fields* f, const mhh_thermo_buoy* tb);
 MHH_API int mhh_thermo_buoy_n2(mhh_ctx* ctx, void* n2, const void* b, double bg_n2);
 MHH_API int mhh_dycore_set_thermo_buoy(mhh_ctx* ctx, const mhh_thermo_buoy* tb);
+
+/* ---- Thermo_moist<TF> (src/thermo_moist.cxx, include/thermo_moist_functions.h) ---------------------------------------------
+ * Base state `bs` (pref, prefh, rhoref, rhorefh, thvref, thvrefh, exnref, exnrefh; kcells entries) lives in the context;
+ * thvref / thvrefh share storage with the thref / threfh of mhh_set_basestate (the closures' N2 and the surface model read them
+ * there, as Thermo_moist::get_thermo_field("N2") uses thvref).  fields.rhoref / rhorefh of the dynamics stay what
+ * mhh_set_basestate set (create_basestate step 6 copies the INITIAL rhoref there; they are not updated afterwards).
+ *   _calc_base_state  Thermo_moist_functions::calc_base_state (functions.h:271-340) on the device from HOST mean profiles
+ *                     thl0 / qt0 (kcells, ghost entries kstart-1 and kend set, e.g. by calc_top_and_bot) = create_basestate step 4
+ *   _set_profiles     overwrite any of the eight profiles from HOST arrays (NULL = keep): the Boussinesq override of
+ *                     create_basestate step 5, or a base state loaded from a restart file (Thermo_moist::load)
+ *   _get_profiles     copy them to HOST arrays (NULL = skip); synchronises
+ *   _exec             Thermo_moist::exec (:1415-1447): with swupdatebasestate the mean profiles of thl and qt
+ *                     (Field3d_operators::calc_mean_profile) and calc_base_state run on the device, stream-ordered, no host
+ *                     round trip (single GPU); then calc_buoyancy_tend_2nd (saturation adjustment at the half levels) on wt
+ *   _get_thermo_field get_thermo_field(name) for "b", "ql", "N2" (MHH_MOIST_*); out: DEVICE field
+ *   _get_buoyancy_surf / _fluxbot   get_buoyancy_surf (b at kstart + b_bot from s_bot[ithl], s_bot[iqt]) and
+ *                     get_buoyancy_fluxbot (from s_fluxbot[ithl], s_fluxbot[iqt]); bbot / bfluxbot: DEVICE planes (ijcells)
+ *   _nonconverged     number of saturation adjustments that hit the iteration cap since the last call (the reference throws
+ *                     "Non-converging saturation adjustment"); synchronises */
+MHH_API int mhh_thermo_moist_calc_base_state(mhh_ctx* ctx, const void* thl0, const void* qt0, double pbot);
+MHH_API int mhh_thermo_moist_set_profiles(mhh_ctx* ctx, const void* pref, const void* prefh, const void* rhoref, const void* rhorefh,
+                                          const void* thvref, const void* thvrefh, const void* exnref, const void* exnrefh);
+MHH_API int mhh_thermo_moist_get_profiles(mhh_ctx* ctx, void* pref, void* prefh, void* rhoref, void* rhorefh,
+                                          void* thvref, void* thvrefh, void* exnref, void* exnrefh);
+MHH_API int mhh_thermo_moist_exec(mhh_ctx* ctx, const mhh_fields* f, const mhh_thermo_moist* tm);
+MHH_API int mhh_thermo_moist_get_thermo_field(mhh_ctx* ctx, int which, void* out, const mhh_fields* f, const mhh_thermo_moist* tm);
+MHH_API int mhh_thermo_moist_get_buoyancy_surf(mhh_ctx* ctx, void* b, void* bbot, const mhh_fields* f, const mhh_thermo_moist* tm);
+MHH_API int mhh_thermo_moist_get_buoyancy_fluxbot(mhh_ctx* ctx, void* bfluxbot, const mhh_fields* f, const mhh_thermo_moist* tm);
+MHH_API int mhh_thermo_moist_nonconverged(mhh_ctx* ctx, long long* count);
+MHH_API int mhh_dycore_set_thermo_moist(mhh_ctx* ctx, const mhh_thermo_moist* tm);
 
 /* ---- Pres<TF>::exec / check_divergence: swpres = 2 -> Pres_2 (src/pres_2.cxx:66-105);
  *      swpres = 4 -> Pres_4 (src/pres_4.cxx:76-156; 7-band solve per mode; needs a 4th-order grid; single GPU) -- */

@@ -67,6 +67,13 @@ class ThermoBuoyC(C.Structure):
     _fields_ = [("alpha", C.c_double), ("n2", C.c_double), ("utrans", C.c_double), ("swbaroclinic", C.c_int), ("dbdy_ls", C.c_double)]
 
 
+class ThermoMoistC(C.Structure):
+    _fields_ = [("ithl", C.c_int), ("iqt", C.c_int), ("pbot", C.c_double), ("swupdatebasestate", C.c_int)]
+
+
+MOIST_B, MOIST_QL, MOIST_N2 = 0, 1, 2
+
+
 class SurfaceC(C.Structure):
     _fields_ = [("ustar", C.c_void_p), ("obuk", C.c_void_p), ("nobuk", C.c_void_p), ("z0m", C.c_void_p), ("z0h", C.c_void_p),
                 ("dutot", C.c_void_p), ("sbcbot", C.c_int * MHH_MAX_SCALARS)]
@@ -135,6 +142,15 @@ SIGNATURES = {
     "mhh_thermo_buoy_exec": (C.c_int, [_vp, _PF, C.POINTER(ThermoBuoyC)]),
     "mhh_thermo_buoy_n2": (C.c_int, [_vp, _vp, _vp, C.c_double]),
     "mhh_dycore_set_thermo_buoy": (C.c_int, [_vp, C.POINTER(ThermoBuoyC)]),
+    "mhh_thermo_moist_calc_base_state": (C.c_int, [_vp, _vp, _vp, C.c_double]),
+    "mhh_thermo_moist_set_profiles": (C.c_int, [_vp] + [_vp]*8),
+    "mhh_thermo_moist_get_profiles": (C.c_int, [_vp] + [_vp]*8),
+    "mhh_thermo_moist_exec": (C.c_int, [_vp, _PF, C.POINTER(ThermoMoistC)]),
+    "mhh_thermo_moist_get_thermo_field": (C.c_int, [_vp, C.c_int, _vp, _PF, C.POINTER(ThermoMoistC)]),
+    "mhh_thermo_moist_get_buoyancy_surf": (C.c_int, [_vp, _vp, _vp, _PF, C.POINTER(ThermoMoistC)]),
+    "mhh_thermo_moist_get_buoyancy_fluxbot": (C.c_int, [_vp, _vp, _PF, C.POINTER(ThermoMoistC)]),
+    "mhh_thermo_moist_nonconverged": (C.c_int, [_vp, C.POINTER(C.c_longlong)]),
+    "mhh_dycore_set_thermo_moist": (C.c_int, [_vp, C.POINTER(ThermoMoistC)]),
     "mhh_pres_exec": (C.c_int, [_vp, C.c_int, _PF, C.c_double]),
     "mhh_pres_check_divergence": (C.c_int, [_vp, C.c_int, _PF, C.POINTER(C.c_double)]),
     "mhh_pres_fft_roundtrip": (C.c_int, [_vp, _vp, _vp, C.c_int]),

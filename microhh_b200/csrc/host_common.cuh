@@ -28,6 +28,7 @@
 #include "order4_kernels.cuh"
 #include "pres4_kernels.cuh"
 #include "thermo_buoy_kernels.cuh"
+#include "thermo_moist_kernels.cuh"
 #include <cudaTypedefs.h>
 #include <dlfcn.h>
 #include <nccl.h>
@@ -92,6 +93,8 @@ struct mhh_ctx
     mhh_tke2 tke2{}; bool tke2_set = false;
     // Thermo_buoy registered for the fused sub-steps (mhh_dycore_set_thermo_buoy; prm->swthermo = 2)
     mhh_thermo_buoy buoy{}; bool buoy_set = false;
+    // Thermo_moist registered for the fused sub-steps (mhh_dycore_set_thermo_moist; prm->swthermo = 3)
+    mhh_thermo_moist moist{}; bool moist_set = false;
     virtual ~mhh_ctx() {}
 };
 
@@ -170,6 +173,15 @@ struct Ctx : mhh_ctx
     double buf_key[3] = {-1., -1., -1.}; int buf_k = 0, buf_kh = 0;
     int surf_mbcbot = -1, surf_thermobc = -1;
     std::vector<TF> h_thref, h_threfh;
+    // Thermo_moist: pref, prefh, rhoref, rhorefh, exnref, exnrefh of its base state + the mean profiles of thl and qt (8 x kcells;
+    // thvref / thvrefh live in g.thref / g.threfh), and the count of non-converged saturation adjustments
+    TF *d_moist = nullptr; int *d_moist_flag = nullptr; bool moist_profiles_set = false;
+    MoistProfiles<TF> moist_profiles() const
+    {
+        const int kc = g.kcells;
+        return {d_moist, d_moist + kc, d_moist + 2 * kc, d_moist + 3 * kc, const_cast<TF*>(g.thref), const_cast<TF*>(g.threfh),
+                d_moist + 4 * kc, d_moist + 5 * kc};
+    }
     double *d_red = nullptr;       // reduction scalar
     double *h_red = nullptr;       // pinned
     std::vector<TF> h_rhoref, h_rhorefh, h_dz, h_dzhi;
@@ -190,6 +202,7 @@ struct Ctx : mhh_ctx
         if (ev_g0) cudaEventDestroy(ev_g0);
         if (ev_g1) cudaEventDestroy(ev_g1);
         cudaFree(io_dev); if (io_host) cudaFreeHost(io_host);
+        cudaFree(d_moist); cudaFree(d_moist_flag);
         cudaFree(d_zL_sl); cudaFree(d_f_sl); cudaFree(d_sigmaz); cudaFree(d_sums);
         cudaFree(d_prof); cudaFree(d_mlen0); cudaFree(tw_xh); cudaFree(tw_xf); cudaFree(tw_y);
         cudaFree(d_bmati); cudaFree(d_bmatj); cudaFree(d_a); cudaFree(d_c); cudaFree(d_dz2rho); cudaFree(d_dz2);
@@ -249,6 +262,7 @@ template <typename TF> int tke2_visc_impl(Ctx<TF>* c, const mhh_fields* f, const
 template <typename TF> int limiter_impl(Ctx<TF>* c, TF* at, const TF* a, TF min_value, TF sub_dt);
 // host_thermo.cu
 template <typename TF> int thermo_buoy_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_thermo_buoy* tb);
+template <typename TF> int thermo_moist_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_thermo_moist* tm);
 // host_pres.cu
 template <typename TF> int pres_create(Ctx<TF>* c);
 template <typename TF> int pres_set_values(Ctx<TF>* c);

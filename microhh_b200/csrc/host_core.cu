@@ -461,7 +461,14 @@ int substep_check(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, bool& 
     if ((prm->swadvec != 25 && prm->swadvec != 2) || (prm->swdiff != 1 && prm->swdiff != 2 && prm->swdiff != 3))
     { c->err = "dycore_substep: swadvec must be 2i5 (25), 2, 4 or 4m (41), swdiff smag2 (1), 2, tke2 (3) or 4"; return MHH_E_INVALID; }
     const bool smag = prm->swdiff == 1 || prm->swdiff == 3;
-    if (prm->swthermo < 0 || prm->swthermo > 2) { c->err = "dycore_substep: swthermo must be 0, dry (1) or buoy (2)"; return MHH_E_INVALID; }
+    if (prm->swthermo < 0 || prm->swthermo > 3) { c->err = "dycore_substep: swthermo must be 0, dry (1), buoy (2) or moist (3)"; return MHH_E_INVALID; }
+    if (prm->swthermo == 3)
+    {
+        if (!c->moist_set) { c->err = "dycore_substep: swthermo = moist needs mhh_dycore_set_thermo_moist"; return MHH_E_INVALID; }
+        // the closures derive N2 from scalar 0 and the context's thref (= thvref for Thermo_moist, src/thermo_moist.cxx:459-475)
+        if (smag && c->moist.ithl != 0) { c->err = "dycore_substep: swthermo = moist with an LES closure needs thl as scalar 0"; return MHH_E_INVALID; }
+        if (prm->swdiff == 3) { c->err = "dycore_substep: swthermo = moist goes with swdiff = smag2 or 2 (Diff_tke2 is wired to Thermo_dry)"; return MHH_E_INVALID; }
+    }
     if (prm->swthermo == 2)
     {
         // the eddy-viscosity kernels derive N2 and the surface buoyancy gradient the Thermo_dry way; no shipped case pairs buoy with an LES closure
@@ -521,6 +528,7 @@ int tendencies_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm)
     const bool smag = prm->swdiff == 1 || prm->swdiff == 3, adv5 = prm->swadvec == 25, buoy = prm->swthermo == 1;
     const mhh_tke2* tke = prm->swdiff == 3 ? &c->tke2 : nullptr;                             // Diff_tke2::exec = the smag2 kernels, evisc per scalar
     if (prm->swthermo == 2 && (rc = thermo_buoy_impl<TF>(c, f, &c->buoy)) != MHH_OK) return rc;  // Thermo_buoy::exec, ahead of advec.exec like Model::exec
+    if (prm->swthermo == 3 && (rc = thermo_moist_impl<TF>(c, f, &c->moist)) != MHH_OK) return rc; // Thermo_moist::exec (base-state update + buoyancy)
     if (adv5 && smag) rc = tend_impl<TF>(c, f, prm, true, true, buoy, tke);                  // 2i5 + smag2 | tke2 (+ buoyancy)
     else if (!adv5 && !smag) rc = o2_impl<TF>(c, f, true, true, buoy);                       // 2 + 2 (+ buoyancy)
     else if (!adv5)                                                                          // 2 + smag2 (drycblles as shipped)
@@ -755,6 +763,7 @@ int surface_exec_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, co
     NEED(c, s, "surface"); NEED(c, f, "fields");
     if (!c->d_zL_sl) { c->err = "mhh_boundary_surface_init has not been called"; return MHH_E_INVALID; }
     if (g.igc < 2 || g.jgc < 2) { c->err = "boundary_surface: the wind filter needs igc, jgc >= 2"; return MHH_E_INVALID; }
+    if (prm->swthermo > 1) { c->err = "boundary_surface on the device: Thermo_dry or no thermo (swthermo = buoy / moist: keep the host's surface model, mhh_dycore_substep_pre / _post)"; return MHH_E_INVALID; }
     const bool neutral = prm->swthermo == 0;
     SurfArgs<TF> a{};
     a.ustar = P<TF>(s->ustar); a.obuk = P<TF>(s->obuk); a.nobuk = static_cast<int*>(s->nobuk); a.dutot = P<TF>(s->dutot);
@@ -853,9 +862,10 @@ int step_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, double dt)
     // forcing and closure.  The user's stream is not part of it: the graph always runs on the context's own stream.
     unsigned long long key = 1469598103934665603ull;
     key = fnv1a(key, f, sizeof(*f)); key = fnv1a(key, prm, sizeof(*prm)); key = fnv1a(key, &dt, sizeof(dt));
-    const int flags[4] = {c->forcing_set ? 1 : 0, c->tke2_set ? 1 : 0, c->overlap ? 1 : 0, c->buoy_set ? 1 : 0};
+    const int flags[5] = {c->forcing_set ? 1 : 0, c->tke2_set ? 1 : 0, c->overlap ? 1 : 0, c->buoy_set ? 1 : 0, c->moist_set ? 1 : 0};
     key = fnv1a(key, flags, sizeof(flags));
     if (c->buoy_set) key = fnv1a(key, &c->buoy, sizeof(c->buoy));
+    if (c->moist_set) key = fnv1a(key, &c->moist, sizeof(c->moist));
     if (c->forcing_set) key = fnv1a(key, &c->forcing, sizeof(c->forcing));
     if (c->tke2_set) key = fnv1a(key, &c->tke2, sizeof(c->tke2));
     if (key == 0) key = 1;

@@ -15,7 +15,7 @@ from .capi import FieldsC, ParamsC, GridDesc, SurfaceC, ForcingC, MhhError
 
 SWADVEC = {"2i5": 25, "2": 2, "4": 4, "4m": 41}
 SWDIFF = {"smag2": 1, "2": 2, "tke2": 3, "4": 4}
-SWTHERMO = {"0": 0, None: 0, "disabled": 0, "dry": 1, "buoy": 2}
+SWTHERMO = {"0": 0, None: 0, "disabled": 0, "dry": 1, "buoy": 2, "moist": 3}
 
 
 def _ptr(t):
@@ -382,6 +382,58 @@ class Thermo_buoy:
 
     def unregister(self):
         self.ctx.check(self.ctx.lib.mhh_dycore_set_thermo_buoy(self.ctx.h, None))
+
+
+class Thermo_moist:
+    """Thermo_moist<TF> (src/thermo_moist.cxx): prognostic thl and qt (scalars `thl`, `qt` of the fields), saturation adjustment,
+    hydrostatic base state kept in the context (thvref / thvrefh share the context's thref / threfh)."""
+    PROFILES = ("pref", "prefh", "rhoref", "rhorefh", "thvref", "thvrefh", "exnref", "exnrefh")
+
+    def __init__(self, ctx, fields, pbot, swupdatebasestate=True, thl="thl", qt="qt"):
+        self.ctx = ctx
+        self.c = capi.ThermoMoistC(fields.scalars.index(thl), fields.scalars.index(qt), float(pbot), int(bool(swupdatebasestate)))
+
+    def _np(self, a):
+        return np.ascontiguousarray(np.asarray(a, self.ctx.gd.dtype)[:self.ctx.gd.kcells])
+
+    def calc_base_state(self, thl0, qt0):
+        """create_basestate step 4: calc_base_state from the (ghosted) reference profiles of thl and qt"""
+        a, b = self._np(thl0), self._np(qt0)
+        self.ctx.check(self.ctx.lib.mhh_thermo_moist_calc_base_state(self.ctx.h, a.ctypes.data, b.ctypes.data, self.c.pbot))
+
+    def set_profiles(self, **prof):
+        keep = [self._np(prof[n]) if prof.get(n) is not None else None for n in self.PROFILES]
+        self.ctx.check(self.ctx.lib.mhh_thermo_moist_set_profiles(self.ctx.h, *[a.ctypes.data if a is not None else None for a in keep]))
+
+    def get_profiles(self):
+        out = {n: np.zeros(self.ctx.gd.kcells, self.ctx.gd.dtype) for n in self.PROFILES}
+        self.ctx.check(self.ctx.lib.mhh_thermo_moist_get_profiles(self.ctx.h, *[out[n].ctypes.data for n in self.PROFILES]))
+        return out
+
+    def exec(self, fields):
+        self.ctx.check(self.ctx.lib.mhh_thermo_moist_exec(self.ctx.h, C.byref(fields.c), C.byref(self.c)))
+
+    def get_thermo_field(self, out, name, fields):
+        which = {"b": capi.MOIST_B, "ql": capi.MOIST_QL, "N2": capi.MOIST_N2}[name]
+        self.ctx.check(self.ctx.lib.mhh_thermo_moist_get_thermo_field(self.ctx.h, which, _ptr(out), C.byref(fields.c), C.byref(self.c)))
+
+    def get_buoyancy_surf(self, b, bbot, fields):
+        self.ctx.check(self.ctx.lib.mhh_thermo_moist_get_buoyancy_surf(self.ctx.h, _ptr(b), _ptr(bbot), C.byref(fields.c), C.byref(self.c)))
+
+    def get_buoyancy_fluxbot(self, bfluxbot, fields):
+        self.ctx.check(self.ctx.lib.mhh_thermo_moist_get_buoyancy_fluxbot(self.ctx.h, _ptr(bfluxbot), C.byref(fields.c), C.byref(self.c)))
+
+    def nonconverged(self):
+        n = C.c_longlong()
+        self.ctx.check(self.ctx.lib.mhh_thermo_moist_nonconverged(self.ctx.h, C.byref(n)))
+        return n.value
+
+    def register(self):
+        """Run thermo.exec inside the fused sub-steps of a Dycore with swthermo = "moist" (mhh_dycore_set_thermo_moist)."""
+        self.ctx.check(self.ctx.lib.mhh_dycore_set_thermo_moist(self.ctx.h, C.byref(self.c)))
+
+    def unregister(self):
+        self.ctx.check(self.ctx.lib.mhh_dycore_set_thermo_moist(self.ctx.h, None))
 
 
 class Pres:

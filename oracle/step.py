@@ -44,9 +44,12 @@ def dycore_substep(g, K, c, prm, substep, dt, pres=None, timers=None, surface_mo
     # exec_viscosity (Diff_smag2 only; Diff_2::exec_viscosity is empty)
     if swdiff == "smag2":
         K.diff_strain2(c["evisc"], c["u"], c["v"], c["w"], c["dudz_mo"], c["dvdz_mo"], surface)
-        if prm["swthermo"] == "dry":
+        if prm["swthermo"] in ("dry", "moist"):
             N2 = np.zeros_like(c["evisc"])
-            K.thermo_dry_N2(N2, c[scal[0]], c["thref"])
+            if prm["swthermo"] == "moist":
+                K.thermo_moist_N2(N2, c["thl"], c["moist_bs"]["thvref"])       # Thermo_moist::get_thermo_field("N2"), src/thermo_moist.cxx:1612-1616
+            else:
+                K.thermo_dry_N2(N2, c[scal[0]], c["thref"])
             K.diff_evisc(c["evisc"], c["u"], c["v"], c["w"], N2, c["dbdz_mo"], c["z0m"], prm["cs"], prm["tPr"], surface, prm["sw_mason"])
         else:
             # Thermo_type::Disabled (src/diff_smag2.cxx:507-545)
@@ -59,6 +62,8 @@ def dycore_substep(g, K, c, prm, substep, dt, pres=None, timers=None, surface_mo
         K.thermo_dry_buoyancy_tend_2nd(c["wt"], c[scal[0]], c["threfh"])
     elif prm["swthermo"] == "buoy":
         O.thermo_buoy_exec(K, c, prm.get("thermo_buoy", {}), 2)                 # Thermo_buoy::exec, Grid_order::Second branch
+    elif prm["swthermo"] == "moist":
+        thermo_moist_exec(K, c, prm["thermo_moist"])
     # boundary.exec (Monin-Obukhov surface model) + boundary.set_ghost_cells again (src/model.cxx:398-401)
     if surface_model is not None:
         surface_model.exec(c, c["thref"], c["threfh"], neutral=prm["swthermo"] != "dry")
@@ -109,6 +114,15 @@ def dycore_substep(g, K, c, prm, substep, dt, pres=None, timers=None, surface_mo
     if forcing is not None:
         forcing(c, O.rk3_subdt(dt, substep))           # buffer.exec + force.exec (src/model.cxx:416-430)
     return _pres_and_rk3(g, K, c, prm, substep, dt, pres, lap)
+
+
+def thermo_moist_exec(K, c, tm):
+    """Thermo_moist::exec (src/thermo_moist.cxx:1415-1447); tm: dict(pbot, swupdatebasestate); c["moist_bs"]: the base state `bs`
+    (updated in place when swupdatebasestate: Fields::exec's mean profiles, src/fields.cxx:542-551, then calc_base_state)."""
+    if tm.get("swupdatebasestate", True):
+        c["moist_bs"] = K.moist_base_state(K.mean_profile(c["thl"]), K.mean_profile(c["qt"]), tm["pbot"])
+    bs = c["moist_bs"]
+    K.thermo_moist_buoyancy_tend_2nd(c["wt"], c["thl"], c["qt"], bs["prefh"], bs["thvrefh"])
 
 
 TKE2_DEFAULTS = dict(ap=1.5, cf=2.5, ce1=0.19, ce2=0.51, cm=0.12, ch1=1., ch2=2., cn=0.76)    # src/diff_tke2.cxx:525-532

@@ -9,7 +9,7 @@ import copy
 import numpy as np
 import pytest
 
-from util import make_pair, prepare_halos, interior, add_sgstke
+from util import moist_case, make_moist_pair, make_pair, prepare_halos, interior, add_sgstke
 from oracle import oracle as O
 from oracle import step as ostep
 from oracle import refbind
@@ -649,19 +649,6 @@ def test_full_rk3_step_order2_buoy_bitexact(dtype, tb):
     assert not np.array_equal(c0["w"], c2["w"])
 
 
-def moist_case(g, gd, dtype, seed=3, cold=False):
-    """A bomex-like (or, `cold`, mixed-phase) moist state on the test grid: thl rising with height, qt falling, noise, and a
-    moist layer that saturates a good share of the points so that the Newton loops of sat_adjust run."""
-    rng = np.random.default_rng(seed)
-    zfull = np.asarray(g.z, np.float64)[:, None, None]
-    zrel = zfull/float(g.zsize)
-    t0 = 262. if cold else 298.
-    thl = t0 + 6.*zrel + 0.3*rng.standard_normal(gd.shape)
-    qsurf = 2.4e-3 if cold else 17.e-3
-    qt = qsurf*(1. - 0.5*zrel) + (0.8e-3 if cold else 3.e-3)*np.exp(-((zrel - 0.45)/0.15)**2) + 1.e-4*rng.standard_normal(gd.shape)
-    return thl.astype(dtype), np.maximum(qt, 1e-5).astype(dtype)
-
-
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("cold", [False, True])
 def test_thermo_moist_bitexact(dtype, cold):
@@ -704,3 +691,26 @@ def test_thermo_moist_bitexact(dtype, cold):
         assert np.array_equal(res[0][n], res[1][n]), (n, float(np.abs(res[0][n].astype(np.float64) - res[1][n]).max()))
     frac = float((interior(g, res[0]["ql"]) > 0).mean())
     assert 0.05 < frac < 0.95, frac                       # both branches of the adjustment are exercised
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("swdiff,update", [("smag2", True), ("smag2", False), ("2", True)])
+def test_full_rk3_step_moist_bitexact(dtype, swdiff, update):
+    """One RK3 step with swthermo = moist (bomex-like state): N2 of the closure from thvref, the base state re-integrated from
+    the mean profiles in every sub-step (swupdatebasestate), buoyancy through the saturation adjustment."""
+    g, gd, case, pbot = make_moist_pair(16, 12, 20, dtype)
+    c0, c1 = copy.deepcopy(case), copy.deepcopy(case)
+    N, R = both(g)
+    prm = ostep.default_params(); prm.update(swdiff=swdiff, swthermo="moist", thermo_moist=dict(pbot=pbot, swupdatebasestate=update),
+                                             surface_model=(swdiff == "smag2"), visc=1e-5 if swdiff == "smag2" else 1e-2, svisc=1e-5 if swdiff == "smag2" else 1e-2)
+    ostep.dycore_step(g, N, c0, prm, 2.0)
+    ostep.dycore_step(g, R, c1, prm, 2.0, pres=refbind.RefPres(g, 2, c1["rhoref"], c1["rhorefh"]))
+    for n in ("u", "v", "w", "thl", "qt", "p"):
+        assert np.array_equal(c0[n], c1[n]), n
+    for n in c0["moist_bs"]:
+        assert np.array_equal(c0["moist_bs"][n], c1["moist_bs"][n]), n
+    assert update == (not np.array_equal(c0["moist_bs"]["thvrefh"], case["moist_bs"]["thvrefh"]))
+    c2 = copy.deepcopy(case)
+    prm2 = dict(prm); prm2.update(swthermo=None)
+    ostep.dycore_step(g, N, c2, prm2, 2.0)
+    assert not np.array_equal(c0["w"], c2["w"])

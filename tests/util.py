@@ -72,3 +72,43 @@ def add_sgstke(g, case, seed=5, stable_bottom=True):
         d[:, ::2] = -d[:, ::2]
         case["dbdz_mo"] = d
     return case
+
+
+def moist_case(g, gd, dtype, seed=3, cold=False):
+    """A bomex-like (or, `cold`, mixed-phase) moist state on the test grid: thl rising with height, qt falling, noise, and a
+    moist layer that saturates a good share of the points so that the Newton loops of sat_adjust run."""
+    rng = np.random.default_rng(seed)
+    zfull = np.asarray(g.z, np.float64)[:, None, None]
+    zrel = zfull/float(g.zsize)
+    t0 = 262. if cold else 298.
+    thl = t0 + 6.*zrel + 0.3*rng.standard_normal(gd.shape)
+    qsurf = 2.4e-3 if cold else 17.e-3
+    qt = qsurf*(1. - 0.5*zrel) + (0.8e-3 if cold else 3.e-3)*np.exp(-((zrel - 0.45)/0.15)**2) + 1.e-4*rng.standard_normal(gd.shape)
+    return thl.astype(dtype), np.maximum(qt, 1e-5).astype(dtype)
+
+
+def make_moist_pair(itot, jtot, ktot, dtype, cold=False, igc=3, sizes=(3200., 3200., 3000.), anelastic=True):
+    """Grid pair + a synthetic moist case: scalars thl and qt (moist_case), zero surface fluxes replaced by bomex-like ones, and
+    the initial base state `moist_bs` from the mean profiles (create_basestate: calc_top_and_bot + calc_base_state)."""
+    g, gd, case = make_pair(itot, jtot, ktot, dtype, stretched=True, anelastic=anelastic, ns=2, sizes=sizes, igc=igc)
+    thl, qt = moist_case(g, gd, dtype, cold=cold)
+    ren = {"th": "thl", "s1": "qt"}
+    for old, new in ren.items():
+        for k in [k for k in case if k == old or k.startswith(old + "_") or k == old + "t"]:
+            case[new + k[len(old):]] = case.pop(k)
+    case["scalars"] = ["thl", "qt"]
+    case["thl"], case["qt"] = thl, qt
+    case["thl_fluxbot"] = np.full(gd.shape2d, 8.e-3, dtype); case["qt_fluxbot"] = np.full(gd.shape2d, 5.2e-5, dtype)
+    case["thl_gradbot"] = np.full(gd.shape2d, -1.e-3, dtype); case["qt_gradbot"] = np.full(gd.shape2d, -1.e-6, dtype)
+    case["thl_gradtop"] = np.full(gd.shape2d, 3.e-3, dtype); case["qt_gradtop"] = np.full(gd.shape2d, -1.e-6, dtype)
+    pbot = 70000. if cold else 101500.
+    thl0, qt0 = O.mean_profile(g, thl), O.mean_profile(g, qt)
+    O.moist_top_and_bot(g, thl0, qt0)
+    case["moist_bs"] = O.moist_base_state(g, thl0, qt0, pbot)
+    case["moist_ref"] = (thl0, qt0)
+    if anelastic:
+        case["rhoref"] = case["moist_bs"]["rhoref"].copy(); case["rhorefh"] = case["moist_bs"]["rhorefh"].copy()
+        # the dynamics read rhoref at the ghost levels too (advection weights): extend like Fields does (constant extrapolation)
+        for a, lo, hi in ((case["rhoref"], g.kstart, g.kend - 1), (case["rhorefh"], g.kstart, g.kend)):
+            a[:lo] = a[lo]; a[hi+1:] = a[hi]
+    return g, gd, case, pbot
