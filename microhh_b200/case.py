@@ -99,13 +99,18 @@ class CaseConfig:
         self.mbcbot = _get(ini, "boundary", "mbcbot")
         self.mbctop = _get(ini, "boundary", "mbctop")
         sl = _get(ini, "fields", "slist", "")
-        self.scalars = (["th"] if self.swthermo == "dry" else []) + [x.strip() for x in sl.split(",") if x.strip()]
+        # the thermo class registers its prognostic scalars first (Thermo_dry: th, src/thermo_dry.cxx:377; Thermo_buoy: b,
+        # src/thermo_buoy.cxx:316; Thermo_moist: thl and qt, src/thermo_moist.cxx:1089-1090)
+        thermo_scalars = {"dry": ["th"], "buoy": ["b"], "moist": ["thl", "qt"]}.get(self.swthermo, [])
+        self.scalars = thermo_scalars + [x.strip() for x in sl.split(",") if x.strip()]
+        self.swmicro = _get(ini, "micro", "swmicro", "0")
         if self.swdiff == "tke2":
             self.scalars.append("sgstke")       # Diff_tke2's constructor adds the prognostic SGS TKE (src/diff_tke2.cxx:544)
         # per scalar, `key[name]` before `key` (src/boundary.cxx:234-235, src/fields.cxx:412); required when there are scalars
         self.sbcbot = {n: _get_sub(ini, "boundary", "sbcbot", n) for n in self.scalars}
         self.sbctop = {n: _get_sub(ini, "boundary", "sbctop", n) for n in self.scalars}
-        self.svisc = {n: _get_sub(ini, "fields", "svisc", n, conv=float) for n in self.scalars}
+        # Thermo_buoy reads the diffusivity of b under the name th (src/thermo_buoy.cxx:320)
+        self.svisc = {n: _get_sub(ini, "fields", "svisc", "th" if (n == "b" and self.swthermo == "buoy") else n, conv=float) for n in self.scalars}
 
     @classmethod
     def from_file(cls, path):
@@ -130,14 +135,20 @@ class CaseConfig:
             bad.append(f"swdiff={self.swdiff}")
         if self.swpres not in ("2", "4"):
             bad.append(f"swpres={self.swpres}")
-        if self.swthermo not in ("0", "dry"):
+        if self.swthermo not in ("0", "dry", "buoy", "moist"):
             bad.append(f"swthermo={self.swthermo}")
+        if self.swthermo == "buoy" and self.swdiff not in ("2", "4"):
+            bad.append("swthermo=buoy with an LES closure (the closures are wired to Thermo_dry / Thermo_moist)")
+        if self.swthermo == "moist" and (self.order != "2" or self.swdiff not in ("smag2", "2")):
+            bad.append("swthermo=moist needs a 2nd-order grid and swdiff=smag2 or 2")
+        if self.swmicro != "0":
+            bad.append(f"swmicro={self.swmicro}")
         if self.order == "4" and (self.swadvec not in ("4", "4m") or (self.swdiff, self.swpres) != ("4", "4")) and not bad:
             bad.append("4th-order grid with mixed schemes")
         if self.swdiff == "tke2" and (self.order != "2" or self.swboundary == "default"):
             bad.append("swdiff=tke2 needs a 2nd-order grid and a surface model (src/diff_tke2.cxx:555-558)")
-        if self.order == "4" and self.swthermo != "0":
-            bad.append("4th-order grid with thermo")
+        if self.order == "4" and self.swthermo not in ("0", "buoy"):
+            bad.append("4th-order grid with thermo other than buoy")
         if self.mbcbot not in _MBC or self.mbctop not in _MBC:
             bad.append(f"mbcbot/mbctop={self.mbcbot}/{self.mbctop}")
         for n in self.scalars:
@@ -163,7 +174,7 @@ class CaseConfig:
             raise ValueError("outside the accelerated path: " + ", ".join(bad))
         p = capi.ParamsC()
         p.swadvec = _SWADVEC[self.swadvec]; p.swdiff = _SWDIFF[self.swdiff]
-        p.swthermo = 1 if self.swthermo == "dry" else 0
+        p.swthermo = {"0": 0, "dry": 1, "buoy": 2, "moist": 3}[self.swthermo]
         p.surface_model = int(self.swboundary != "default")
         p.sw_mason = int(self.swmason)
         p.cs = self.cs; p.tPr = self.tPr
@@ -171,3 +182,16 @@ class CaseConfig:
         for i, n in enumerate(self.scalars):
             p.sbcbot[i] = _SBC[self.sbcbot[n]]; p.sbctop[i] = _SBC[self.sbctop[n]]
         return p
+
+    def thermo_buoy_params(self):
+        """Keyword arguments of dycore.Thermo_buoy ([thermo] alpha, N2, swbaroclinic, dbdy_ls; [grid] utrans; src/thermo_buoy.cxx:318-329)."""
+        ini = self.ini
+        sw = _get(ini, "thermo", "swbaroclinic", False, bool)
+        return dict(alpha=_get(ini, "thermo", "alpha", 0., float), n2=_get(ini, "thermo", "N2", 0., float),
+                    utrans=_get(ini, "grid", "utrans", 0., float), swbaroclinic=sw,
+                    dbdy_ls=_get(ini, "thermo", "dbdy_ls", conv=float) if sw else 0.)
+
+    def thermo_moist_params(self):
+        """pbot and swupdatebasestate of dycore.Thermo_moist ([thermo] pbot is required, src/thermo_moist.cxx:1105, 1115)."""
+        return dict(pbot=_get(self.ini, "thermo", "pbot", conv=float), swupdatebasestate=_get(self.ini, "thermo", "swupdatebasestate", True, bool))
+

@@ -15,6 +15,9 @@
 //   Boundary_cyclic  include/boundary_cyclic.h:35   Boundary_cyclic_b200<TF>     mhh_boundary_cyclic / _2d
 //   Timeloop::exec   include/timeloop.h:65          timeloop_exec_b200()         mhh_timeloop_rk3
 //   Model::exec loop src/model.cxx:356-504          dycore_substep_b200()        mhh_dycore_substep (fused fast path)
+//   Thermo_buoy<TF>  include/thermo_buoy.h:47       Thermo_buoy_b200<TF>         mhh_thermo_buoy_exec / _n2, mhh_dycore_set_thermo_buoy
+//   Thermo_moist<TF> include/thermo_moist.h:54      Thermo_moist_b200<TF>        mhh_thermo_moist_exec / _set_profiles / _get_profiles /
+//                                                                                _get_thermo_field, mhh_dycore_set_thermo_moist
 //
 // Errors: the C ABI never throws; MHH_CHECK rethrows as std::runtime_error, which main() already
 // turns into "message + exit code 1" (main/microhh.cxx:59-68).
@@ -36,6 +39,8 @@
 #include "boundary.h"
 #include "boundary_cyclic.h"
 #include "thermo.h"
+#include "thermo_buoy.h"
+#include "thermo_moist.h"
 #include "stats.h"
 #include "constants.h"
 
@@ -129,11 +134,11 @@ namespace mhhb200
         f.v_bot = fields.mp.at("v")->fld_bot_g; f.v_gradbot = fields.mp.at("v")->grad_bot_g;
         f.v_top = fields.mp.at("v")->fld_top_g; f.v_gradtop = fields.mp.at("v")->grad_top_g;
         int n = 0;
-        // the thermodynamic scalar must be scalar 0 (buoyancy / N2 source): std::map order puts "th" / "thl" after
-        // e.g. "qt", so it is moved to the front explicitly
+        // the thermodynamic scalar must be scalar 0 (buoyancy / N2 source; Thermo_buoy's "b"): std::map order puts "th" / "thl"
+        // after e.g. "qt", so it is moved to the front explicitly
         std::vector<std::string> names;
         for (auto& it : fields.sp) names.push_back(it.first);
-        for (const char* thname : {"th", "thl"})
+        for (const char* thname : {"th", "thl", "b"})
             for (size_t i = 0; i < names.size(); ++i)
                 if (names[i] == thname) { std::swap(names[0], names[i]); }
         for (const std::string& name : names)
@@ -540,4 +545,113 @@ namespace mhhb200
     void dycore_substep_post_b200(Context<TF>& c, Fields<TF>& fields, Boundary<TF>& boundary, const mhh_params& prm,
                                   const int substep, const double dt)
     { const mhh_fields f = fields_view(fields, &boundary); MHH_CHECK(c.ctx, mhh_dycore_substep_post(c.ctx, &f, &prm, substep, dt)); }
+    // index of a prognostic scalar in fields_view's ordering
+    template<typename TF>
+    int scalar_index(Fields<TF>& fields, const std::string& name)
+    {
+        std::vector<std::string> names;
+        for (auto& it : fields.sp) names.push_back(it.first);
+        for (const char* thname : {"th", "thl", "b"})
+            for (size_t i = 0; i < names.size(); ++i)
+                if (names[i] == thname) { std::swap(names[0], names[i]); }
+        for (size_t i = 0; i < names.size(); ++i)
+            if (names[i] == name) return (int)i;
+        throw std::runtime_error("mhhb200: no prognostic scalar " + name);
+    }
+
+    // ---- Thermo_buoy (src/thermo_buoy.cxx:306-391): the reference class keeps everything but the device work.  `bs` is private
+    // there, so the constructor reads the same .ini keys again (:318-329).  Thermo<TF>::factory (src/thermo.cxx) returns this class
+    // for swthermo = buoy.
+    template<typename TF>
+    class Thermo_buoy_b200 : public Thermo_buoy<TF>
+    {
+        public:
+            Thermo_buoy_b200(Master& m, Grid<TF>& g, Fields<TF>& f, Input& in, std::shared_ptr<Context<TF>> c) :
+                Thermo_buoy<TF>(m, g, f, in), flds(f), c(std::move(c))
+            {
+                tb.alpha = in.get_item<TF>("thermo", "alpha", "", 0.);
+                tb.n2 = in.get_item<TF>("thermo", "N2", "", 0.);
+                tb.utrans = g.get_grid_data().utrans;
+                tb.swbaroclinic = in.get_item<bool>("thermo", "swbaroclinic", "", false);
+                tb.dbdy_ls = tb.swbaroclinic ? in.get_item<TF>("thermo", "dbdy_ls", "") : TF(0.);
+            }
+            void exec(const double, Stats<TF>& stats) override
+            {
+                const mhh_fields f = fields_view(flds);
+                MHH_CHECK(c->ctx, mhh_thermo_buoy_exec(c->ctx, &f, &tb));
+                stats.calc_tend(*flds.mt.at("w"), "buoy");
+            }
+            // run thermo.exec inside mhh_dycore_substep (prm.swthermo = 2) instead
+            void register_fused() { MHH_CHECK(c->ctx, mhh_dycore_set_thermo_buoy(c->ctx, &tb)); }
+            // get_thermo_field_g("N2") (src/thermo_buoy.cu): N2 into a device field
+            void get_N2_g(TF* n2_g) { MHH_CHECK(c->ctx, mhh_thermo_buoy_n2(c->ctx, n2_g, flds.sp.at("b")->fld_g, tb.n2)); }
+            mhh_thermo_buoy tb{};
+        private:
+            Fields<TF>& flds;          // the base classes re-declare Thermo<TF>::fields private
+            std::shared_ptr<Context<TF>> c;
+    };
+
+    // ---- Thermo_moist (src/thermo_moist.cxx:1080-1447, GPU twin src/thermo_moist.cu:902-959): create_basestate / load stay the
+    // reference's (host calc_base_state from the input profiles or the restart file); its eight profiles go to the context once
+    // (get_basestate_vector is the public accessor).  exec then runs on the device INCLUDING the base-state update, where the
+    // reference's GPU build copies two mean profiles to the host, integrates there and copies eight profiles back, every sub-step.
+    // sync_host (default on) mirrors the updated profiles back into the reference object's host vectors and its own device copies
+    // (forward_device) after every exec, for the parts of MicroHH that read them (statistics, radiation, microphysics); a run
+    // that only needs them at output time can switch it off and call backward_basestate() there.
+    template<typename TF>
+    class Thermo_moist_b200 : public Thermo_moist<TF>
+    {
+        public:
+            Thermo_moist_b200(Master& m, Grid<TF>& g, Fields<TF>& f, Input& in, const Sim_mode sim_mode, std::shared_ptr<Context<TF>> c) :
+                Thermo_moist<TF>(m, g, f, in, sim_mode), flds(f), c(std::move(c))
+            {
+                tm.pbot = in.get_item<TF>("thermo", "pbot", "");
+                tm.swupdatebasestate = in.get_item<bool>("thermo", "swupdatebasestate", "", true);
+            }
+            // call after create_basestate / load (the profiles exist) and Fields::create (the scalar order is final)
+            void forward_basestate()
+            {
+                tm.ithl = scalar_index(flds, "thl"); tm.iqt = scalar_index(flds, "qt");
+                auto p = [&](const char* n) { return static_cast<const void*>(this->get_basestate_vector(n).data()); };
+                MHH_CHECK(c->ctx, mhh_thermo_moist_set_profiles(c->ctx, p("p"), p("ph"), p("rho"), p("rhoh"), p("thv"), p("thvh"), p("exner"), p("exnerh")));
+                uploaded = true;
+            }
+            void backward_basestate()
+            {
+                auto p = [&](const char* n) { return static_cast<void*>(const_cast<TF*>(this->get_basestate_vector(n).data())); };
+                MHH_CHECK(c->ctx, mhh_thermo_moist_get_profiles(c->ctx, p("p"), p("ph"), p("rho"), p("rhoh"), p("thv"), p("thvh"), p("exner"), p("exnerh")));
+                this->forward_device();
+            }
+            void exec(const double, Stats<TF>& stats) override
+            {
+                if (!uploaded) forward_basestate();
+                const mhh_fields f = fields_view(flds);
+                MHH_CHECK(c->ctx, mhh_thermo_moist_exec(c->ctx, &f, &tm));
+                if (tm.swupdatebasestate && sync_host) backward_basestate();
+                long long bad = 0;
+                if (check_convergence)
+                {
+                    MHH_CHECK(c->ctx, mhh_thermo_moist_nonconverged(c->ctx, &bad));
+                    if (bad) throw std::runtime_error("Non-converging saturation adjustment");        // functions.h:252-263
+                }
+                stats.calc_tend(*flds.mt.at("w"), "buoy");
+            }
+            void register_fused()
+            {
+                if (!uploaded) forward_basestate();
+                MHH_CHECK(c->ctx, mhh_dycore_set_thermo_moist(c->ctx, &tm));
+            }
+            // get_thermo_field_g for "b", "ql", "N2" (MHH_MOIST_*) into a device field
+            void get_thermo_field_b200(TF* out_g, const int which)
+            {
+                const mhh_fields f = fields_view(flds);
+                MHH_CHECK(c->ctx, mhh_thermo_moist_get_thermo_field(c->ctx, which, out_g, &f, &tm));
+            }
+            mhh_thermo_moist tm{};
+            bool sync_host = true, check_convergence = true;
+        private:
+            Fields<TF>& flds;
+            std::shared_ptr<Context<TF>> c;
+            bool uploaded = false;
+    };
 }

@@ -58,10 +58,24 @@ def test_defaults_follow_the_grid_order():
 def test_out_of_path_switches_are_named():
     m180 = case("moser180")                                                      # ships with swadvec=4m
     assert m180.swadvec == "4m" and m180.unsupported() == [] and m180.make_params().swadvec == 41
-    assert "swthermo=moist" in case("bomex").unsupported()
-    assert "swthermo=buoy" in case("weakscaling").unsupported()
+    bx = case("bomex")                                                           # moist is on the path, mbcbot=ustar is not
+    assert bx.scalars == ["thl", "qt"] and bx.unsupported() == ["mbcbot/mbctop=ustar/freeslip"]
+    assert bx.thermo_moist_params() == dict(pbot=101500., swupdatebasestate=True)
     with pytest.raises(ValueError):
-        case("bomex").make_params()
+        bx.make_params()
+    assert "swmicro=2mom_warm" in case("dycoms").unsupported()
+    assert "swadvec=2i4" in case("gabls4s3").unsupported()
+    arm = case("arm")
+    assert arm.unsupported() == [] and arm.make_params().swthermo == 3
+    ws = case("weakscaling")                                                     # 4th-order DNS with swthermo=buoy
+    assert ws.scalars == ["b"] and ws.unsupported() == [] and ws.make_params().swthermo == 2
+    assert ws.thermo_buoy_params() == dict(alpha=0., n2=0., utrans=0., swbaroclinic=False, dbdy_ls=0.)
+    ps = case("prandtlslope")
+    tb = ps.thermo_buoy_params()
+    assert abs(tb["alpha"] - 0.5235) < 1e-12 and tb["n2"] == 1. and ps.unsupported() == []
+    ini = {k: dict(v) for k, v in ws.ini.items()}
+    ini.setdefault("diff", {})["swdiff"] = "smag2"
+    assert any("buoy" in b for b in CaseConfig(ini).unsupported())
     assert case("andren1994").unsupported() == []                                # neutral LES: calc_evisc_neutral
 
 
