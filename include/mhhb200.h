@@ -367,6 +367,8 @@ MHH_API int mhh_thermo_moist_get_thermo_field(mhh_ctx* ctx, int which, void* out
 MHH_API int mhh_thermo_moist_get_buoyancy_surf(mhh_ctx* ctx, void* b, void* bbot, const mhh_fields* f, const mhh_thermo_moist* tm);
 MHH_API int mhh_thermo_moist_get_buoyancy_fluxbot(mhh_ctx* ctx, void* bfluxbot, const mhh_fields* f, const mhh_thermo_moist* tm);
 MHH_API int mhh_thermo_moist_nonconverged(mhh_ctx* ctx, long long* count);
+/* diagnostics: fixed-point sweeps the last base-state integration on the device took (see thermo_moist_kernels.cuh); synchronises */
+MHH_API int mhh_thermo_moist_base_state_sweeps(mhh_ctx* ctx, int* sweeps);
 MHH_API int mhh_dycore_set_thermo_moist(mhh_ctx* ctx, const mhh_thermo_moist* tm);
 
 /* ---- Pres<TF>::exec / check_divergence: swpres = 2 -> Pres_2 (src/pres_2.cxx:66-105);

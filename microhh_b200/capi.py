@@ -150,6 +150,7 @@ SIGNATURES = {
     "mhh_thermo_moist_get_buoyancy_surf": (C.c_int, [_vp, _vp, _vp, _PF, C.POINTER(ThermoMoistC)]),
     "mhh_thermo_moist_get_buoyancy_fluxbot": (C.c_int, [_vp, _vp, _PF, C.POINTER(ThermoMoistC)]),
     "mhh_thermo_moist_nonconverged": (C.c_int, [_vp, C.POINTER(C.c_longlong)]),
+    "mhh_thermo_moist_base_state_sweeps": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "mhh_dycore_set_thermo_moist": (C.c_int, [_vp, C.POINTER(ThermoMoistC)]),
     "mhh_pres_exec": (C.c_int, [_vp, C.c_int, _PF, C.c_double]),
     "mhh_pres_check_divergence": (C.c_int, [_vp, C.c_int, _PF, C.POINTER(C.c_double)]),

@@ -50,10 +50,10 @@ int moist_alloc(Ctx<TF>* c)
 {
     if (c->d_moist) return MHH_OK;
     const size_t kc = c->g.kcells;
-    CUDA_TRY(c, cudaMalloc(&c->d_moist, sizeof(TF) * kc * 8));
-    CUDA_TRY(c, cudaMemset(c->d_moist, 0, sizeof(TF) * kc * 8));
-    CUDA_TRY(c, cudaMalloc(&c->d_moist_flag, sizeof(int)));
-    CUDA_TRY(c, cudaMemset(c->d_moist_flag, 0, sizeof(int)));
+    CUDA_TRY(c, cudaMalloc(&c->d_moist, sizeof(TF) * kc * 10));
+    CUDA_TRY(c, cudaMemset(c->d_moist, 0, sizeof(TF) * kc * 10));
+    CUDA_TRY(c, cudaMalloc(&c->d_moist_flag, 2 * sizeof(int)));        // [0] non-converged adjustments, [1] sweeps of the last base state
+    CUDA_TRY(c, cudaMemset(c->d_moist_flag, 0, 2 * sizeof(int)));
     return MHH_OK;
 }
 
@@ -71,9 +71,11 @@ int moist_check(Ctx<TF>* c, const mhh_fields* f, const mhh_thermo_moist* tm)
 
 // calc_base_state on the device from device mean profiles
 template <typename TF>
-int moist_base_state_launch(Ctx<TF>* c, const TF* thlmean, const TF* qtmean, double pbot)
+int moist_base_state_launch(Ctx<TF>* c, const TF* thlmean, const TF* qtmean, double pbot, bool cold)
 {
-    moist_base_state_kernel<TF><<<1, 32, 0, c->stream>>>(c->moist_profiles(), thlmean, qtmean, (TF)pbot, c->g, c->d_moist_flag);
+    TF* scratch = c->d_moist + 8 * (size_t)c->g.kcells;
+    moist_base_state_kernel<TF><<<1, 256, 0, c->stream>>>(c->moist_profiles(), thlmean, qtmean, (TF)pbot, c->g, scratch, scratch + c->g.kcells,
+                                                          cold ? 1 : 0, c->d_moist_flag);
     KCHECKN(c, "moist_base_state_kernel");
     return MHH_OK;
 }
@@ -89,7 +91,7 @@ int moist_calc_base_state_impl(Ctx<TF>* c, const TF* thl0, const TF* qt0, double
     CUDA_TRY(c, cudaMemcpyAsync(means, thl0, sizeof(TF) * kc, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaMemcpyAsync(means + kc, qt0, sizeof(TF) * kc, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));          // the host arrays may be pageable and go out of scope
-    if ((rc = moist_base_state_launch<TF>(c, means, means + kc, pbot)) != MHH_OK) return rc;
+    if ((rc = moist_base_state_launch<TF>(c, means, means + kc, pbot, true)) != MHH_OK) return rc;
     c->moist_profiles_set = true;
     return MHH_OK;
 }
@@ -128,9 +130,9 @@ int thermo_moist_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_thermo_moist* t
         // Fields::exec's mean profiles (src/fields.cxx:542-551) + calc_base_state, on the device
         if (c->nranks > 1) { c->err = "thermo_moist: swupdatebasestate on y slabs needs the sum of the mean profiles over the ranks (not in this version)"; return MHH_E_INVALID; }
         TF* means = c->d_moist + 6 * (size_t)g.kcells;
-        moist_mean_profile_kernel<TF><<<dim3(g.kcells, 2), 256, 0, c->stream>>>(thl, qt, means, means + g.kcells, g, (double)g.itot * (double)g.jtot);
+        moist_mean_profile_kernel<TF><<<dim3(g.kcells, 2), 1024, 0, c->stream>>>(thl, qt, means, means + g.kcells, g, (double)g.itot * (double)g.jtot);
         KCHECKN(c, "moist_mean_profile_kernel");
-        if ((rc = moist_base_state_launch<TF>(c, means, means + g.kcells, tm->pbot)) != MHH_OK) return rc;
+        if ((rc = moist_base_state_launch<TF>(c, means, means + g.kcells, tm->pbot, false)) != MHH_OK) return rc;   // starts from the previous base state
     }
     if (g.kmax > 1)
     {
@@ -174,6 +176,17 @@ int moist_surf_impl(Ctx<TF>* c, TF* b3d, TF* plane, const mhh_fields* f, const m
     dim3 bl(64, 4), gr((g.icells + 63) / 64, (g.jcells + 3) / 4);
     moist_surf_kernel<TF><<<gr, bl, 0, c->stream>>>(b3d, plane, P<TF>(f->s[tm->ithl]), thl2, P<TF>(f->s[tm->iqt]), qt2, g.thref, g.threfh, g, mode);
     KCHECKN(c, "moist_surf_kernel");
+    return MHH_OK;
+}
+
+template <typename TF>
+int moist_sweeps_impl(Ctx<TF>* c, int* sweeps)
+{
+    NEED(c, sweeps, "sweeps");
+    *sweeps = 0;
+    if (!c->d_moist_flag) return MHH_OK;
+    CUDA_TRY(c, cudaMemcpyAsync(sweeps, c->d_moist_flag + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return MHH_OK;
 }
 
@@ -258,6 +271,9 @@ int mhh_thermo_moist_get_buoyancy_surf(mhh_ctx* ctx, void* b, void* bbot, const 
 
 int mhh_thermo_moist_get_buoyancy_fluxbot(mhh_ctx* ctx, void* bfluxbot, const mhh_fields* f, const mhh_thermo_moist* tm)
 { DISPATCH1(ctx, moist_surf_impl<TF>(c, (TF*)nullptr, P<TF>(bfluxbot), f, tm, 1)); }
+
+int mhh_thermo_moist_base_state_sweeps(mhh_ctx* ctx, int* sweeps)
+{ DISPATCH1(ctx, moist_sweeps_impl<TF>(c, sweeps)); }
 
 int mhh_thermo_moist_nonconverged(mhh_ctx* ctx, long long* count)
 { DISPATCH1(ctx, moist_nonconverged_impl<TF>(c, count)); }

@@ -9,8 +9,9 @@
 //   Field3d_operators::calc_mean_profile        src/field3d_operators.cxx:45-66
 // Where the reference's GPU build copies the mean profiles to the host, integrates the base state there and copies eight
 // profiles back on EVERY sub-step (src/thermo_moist.cu:914-943: two blocking D2H, one H2D), this path keeps the update on the
-// device: one reduction kernel for the two mean profiles and one single-lane kernel for the (inherently serial, kmax-long)
-// hydrostatic integration, both stream-ordered -- no host round trip, and the sub-step stays capturable in a CUDA graph.
+// device: one reduction kernel for the two mean profiles and one single-CTA kernel for the hydrostatic integration (as a
+// fixed-point sweep over all levels in parallel, see moist_base_state_kernel), both stream-ordered -- no host round trip, and
+// the sub-step stays capturable in a CUDA graph.
 // The buoyancy kernel is HBM-bound: thl and qt read once (the level below comes out of L2), wt read and written once = 4
 // array passes; the exner function of the level is evaluated by one lane per CTA.
 #pragma once
@@ -156,31 +157,38 @@ struct MoistProfiles
     TF *pref, *prefh, *rho, *rhoh, *thv, *thvh, *ex, *exh;
 };
 
-// Field3d_operators::calc_mean_profile for two fields at once: one CTA per (level, field), double accumulation like the
-// reference (its sum is sequential, this one a fixed-shape tree: deterministic, equal to rounding of the double sum).
+// Field3d_operators::calc_mean_profile for two fields at once: one CTA of 1024 threads per (level, field), double accumulation
+// like the reference (its sum is sequential, this one a fixed-shape tree: deterministic, equal to rounding of the double sum).
+// A warp walks whole rows (unit stride, no index division), four independent loads in flight per lane.
 template <typename TF>
-__global__ void __launch_bounds__(256) moist_mean_profile_kernel(const TF* __restrict__ f0, const TF* __restrict__ f1,
+__global__ void __launch_bounds__(1024) moist_mean_profile_kernel(const TF* __restrict__ f0, const TF* __restrict__ f1,
         TF* __restrict__ m0, TF* __restrict__ m1, const GridDev<TF> g, const double n)
 {
     const int k = blockIdx.x;
-    const TF* __restrict__ f = blockIdx.y == 0 ? f0 : f1;
+    const TF* __restrict__ f = (blockIdx.y == 0 ? f0 : f1) + (long long)k * g.ijcells + g.istart;
     TF* __restrict__ m = blockIdx.y == 0 ? m0 : m1;
-    const long long base = (long long)k * g.ijcells;
-    double s = 0.;
-    const int nij = g.imax * g.jmax;
-    for (int idx = threadIdx.x; idx < nij; idx += blockDim.x)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    double s0 = 0., s1 = 0., s2 = 0., s3 = 0.;
+    for (int j = warp; j < g.jmax; j += nwarp)
     {
-        const int j = idx / g.imax, i = idx - j * g.imax;
-        s += (double)f[base + (long long)(j + g.jstart) * g.icells + (i + g.istart)];
+        const TF* __restrict__ row = f + (long long)(j + g.jstart) * g.icells;
+        int i = lane;
+        for (; i + 96 < g.imax; i += 128)
+        {
+            const TF a = row[i], b = row[i + 32], c = row[i + 64], d = row[i + 96];
+            s0 += (double)a; s1 += (double)b; s2 += (double)c; s3 += (double)d;
+        }
+        for (; i < g.imax; i += 32) s0 += (double)row[i];
     }
-    __shared__ double red[8];
+    double s = (s0 + s1) + (s2 + s3);
+    __shared__ double red[32];
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    if (lane == 0) red[warp] = s;
     __syncthreads();
     if (threadIdx.x == 0)
     {
         double t = 0.;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+        for (int w = 0; w < nwarp; ++w) t += red[w];
         m[k] = (TF)(t / n);
     }
 }
@@ -222,14 +230,110 @@ MHH_HD int moist_base_state_serial(const MoistProfiles<TF> b, const TF* __restri
     return bad;
 }
 
-// one lane: the integration is a kmax-long dependent chain
+// ---- The same integration without the kmax-long chain of exp / pow / Newton calls on one lane ---------------------------
+// (measured on the B200: 0.58 ms fp32 / 1.24 ms fp64 per launch at kmax = 256 for the serial form, 29 % / 46 % of a bomex-shaped
+// step; the reference's GPU build gave up on it, "extremely slow", src/thermo_moist.cu:917-923).
+// The recurrences are  prefh[k+1] = prefh[k] F[k],  pref[k] = pref[k-1] Fh[k]  with  F[k] = exp(-g dz[k] / (Rd ex thv)(pref[k]))
+// and  Fh[k] = exp(-g dzh[k] / (Rd exh thvh)(prefh[k]))  (z[kstart] for dzh at the surface).  Fixed-point form: from the current
+// pressures ALL levels evaluate their factor in parallel (the expensive part: pow, exp, saturation adjustment), then one lane
+// forms the two running products (kmax dependent multiplications, nothing else).  The dependence is strictly lower triangular
+// -- level k needs only levels below it -- so after n sweeps the lowest n levels hold exactly the bits the serial code produces,
+// and since the factor depends only weakly on the pressure (d ln F / d ln p ~ 1e-3 per level) all levels stop changing after a
+// few sweeps: ~17 from scratch in fp64, 2-4 when the previous sub-step's pressures are the start.  The loop ends when a sweep
+// changes no bit (or after kmax + 2 sweeps, the triangular bound), i.e. at THE fixed point, which is the serial result bit
+// for bit -- tests/test_moist_hostcheck.py checks exactly that for the host build of these functions.
 template <typename TF>
-__global__ void moist_base_state_kernel(const MoistProfiles<TF> b, const TF* __restrict__ thlmean, const TF* __restrict__ qtmean,
-        const TF pbot, const GridDev<TF> g, int* __restrict__ nonconv)
+MHH_HD int moist_base_level(const MoistProfiles<TF> b, const TF* __restrict__ thlmean, const TF* __restrict__ qtmean, const int k,
+        const int kstart, const int kend, const TF* __restrict__ z, const TF* __restrict__ dz, const TF* __restrict__ dzh,
+        TF* __restrict__ F, TF* __restrict__ Fh)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const int bad = moist_base_state_serial<TF>(b, thlmean, qtmean, pbot, g.kstart, g.kend, g.z, g.dz, g.dzh);
-    if (bad) atomicAdd(nonconv, bad);
+    typedef MoistC<TF> C;
+    int bad = 0;
+    {
+        const TF thli = TF(0.5) * (thlmean[k - 1] + thlmean[k]);
+        const TF qti  = TF(0.5) * (qtmean[k - 1] + qtmean[k]);
+        const TF ph = b.prefh[k];
+        const TF exh = moist_exner(ph);
+        const SatAdjust<TF> ssa = moist_sat_adjust(thli, qti, ph, exh);
+        bad += ssa.converged ? 0 : 1;
+        const TF thvh = moist_virtual_temperature(exh, thli, qti, ssa.ql, ssa.qi);
+        b.exh[k] = exh; b.thvh[k] = thvh;
+        b.rhoh[k] = ph / (C::Rd * exh * thvh);
+        Fh[k] = m_exp(-C::grav * (k == kstart ? z[kstart] : dzh[k]) / (C::Rd * exh * thvh));
+    }
+    if (k < kend)
+    {
+        const TF p = b.pref[k];
+        const TF ex = moist_exner(p);
+        const SatAdjust<TF> ssa = moist_sat_adjust(thlmean[k], qtmean[k], p, ex);
+        bad += ssa.converged ? 0 : 1;
+        const TF thv = moist_virtual_temperature(ex, thlmean[k], qtmean[k], ssa.ql, ssa.qi);
+        b.ex[k] = ex; b.thv[k] = thv;
+        b.rho[k] = p / (C::Rd * ex * thv);
+        F[k] = m_exp(-C::grav * dz[k] / (C::Rd * ex * thv));
+    }
+    return bad;
+}
+
+MHH_HD bool moist_same_bits(double a, double b) { return a == b || (a != a && b != b); }
+MHH_HD bool moist_same_bits(float a, float b) { return a == b || (a != a && b != b); }
+
+// the two running products; returns whether any pressure changed
+template <typename TF>
+MHH_HD int moist_base_cumprod(const MoistProfiles<TF> b, const TF pbot, const int kstart, const int kend,
+        const TF* __restrict__ F, const TF* __restrict__ Fh)
+{
+    int changed = 0;
+    TF ph = pbot, p = pbot;
+    #pragma unroll 4
+    for (int k = kstart; k <= kend; ++k)
+    {
+        // prefh[k] = prefh[k-1] * F[k-1]  (k > kstart);  pref[k] = pref[k-1] * Fh[k]  (pref[kstart] = prefh[kstart] * Fh[kstart])
+        if (k > kstart) ph = ph * F[k - 1];
+        p = (k == kstart ? ph : p) * Fh[k];
+        changed |= (moist_same_bits(ph, b.prefh[k]) && moist_same_bits(p, b.pref[k])) ? 0 : 1;
+        b.prefh[k] = ph; b.pref[k] = p;
+    }
+    return changed;
+}
+
+// One CTA.  cold != 0: start from p = pbot everywhere; else from the pressures already in b (the previous base state).
+// info[0] += non-converged saturation adjustments of the final sweep, info[1] = number of sweeps.
+template <typename TF>
+__global__ void __launch_bounds__(256) moist_base_state_kernel(const MoistProfiles<TF> b, const TF* __restrict__ thlmean,
+        const TF* __restrict__ qtmean, const TF pbot, const GridDev<TF> g, TF* __restrict__ F, TF* __restrict__ Fh,
+        const int cold, int* __restrict__ info)
+{
+    __shared__ int s_changed, s_bad;
+    const int kstart = g.kstart, kend = g.kend, tid = threadIdx.x, nth = blockDim.x;
+    // no usable previous state (never computed, or profiles uploaded without pressures): start from scratch as well
+    const bool scratch = cold != 0 || !(b.pref[kstart] > TF(0.)) || !(b.prefh[kend] > TF(0.));
+    __syncthreads();
+    if (scratch)
+        for (int k = kstart + tid; k <= kend; k += nth) { b.prefh[k] = pbot; b.pref[k] = pbot; }
+    __syncthreads();
+    int sweeps = 0;
+    const int maxsweeps = kend - kstart + 3;
+    for (int it = 0; it < maxsweeps; ++it)
+    {
+        if (tid == 0) s_bad = 0;
+        __syncthreads();
+        int bad = 0;
+        for (int k = kstart + tid; k <= kend; k += nth)
+            bad += moist_base_level<TF>(b, thlmean, qtmean, k, kstart, kend, g.z, g.dz, g.dzh, F, Fh);
+        if (bad) atomicAdd(&s_bad, bad);
+        __syncthreads();
+        if (tid == 0) s_changed = moist_base_cumprod<TF>(b, pbot, kstart, kend, F, Fh);
+        __syncthreads();
+        ++sweeps;
+        if (!s_changed) break;
+    }
+    if (tid == 0)
+    {
+        b.pref[kstart - 1] = TF(2.) * b.prefh[kstart] - b.pref[kstart];
+        if (s_bad) atomicAdd(&info[0], s_bad);
+        info[1] = sweeps;
+    }
 }
 
 // calc_buoyancy_tend_2nd (src/thermo_moist.cxx:77-120): wt += buoyancy of (thl, qt) interpolated to the half level, with the

@@ -428,6 +428,11 @@ class Thermo_moist:
         self.ctx.check(self.ctx.lib.mhh_thermo_moist_nonconverged(self.ctx.h, C.byref(n)))
         return n.value
 
+    def base_state_sweeps(self):
+        n = C.c_int()
+        self.ctx.check(self.ctx.lib.mhh_thermo_moist_base_state_sweeps(self.ctx.h, C.byref(n)))
+        return n.value
+
     def register(self):
         """Run thermo.exec inside the fused sub-steps of a Dycore with swthermo = "moist" (mhh_dycore_set_thermo_moist)."""
         self.ctx.check(self.ctx.lib.mhh_dycore_set_thermo_moist(self.ctx.h, C.byref(self.c)))

@@ -21,7 +21,23 @@ EXPORT void hc_buoyancy_flux_no_ql_##SFX(long n, const TF* thl, const TF* thlflu
 EXPORT int hc_base_state_##SFX(TF* pref, TF* prefh, TF* rho, TF* rhoh, TF* thv, TF* thvh, TF* ex, TF* exh, \
         const TF* thlmean, const TF* qtmean, TF pbot, int kstart, int kend, const TF* z, const TF* dz, const TF* dzh) \
 { const MoistProfiles<TF> b{pref, prefh, rho, rhoh, thv, thvh, ex, exh}; \
-  return moist_base_state_serial<TF>(b, thlmean, qtmean, pbot, kstart, kend, z, dz, dzh); }
+  return moist_base_state_serial<TF>(b, thlmean, qtmean, pbot, kstart, kend, z, dz, dzh); } \
+/* host mirror of moist_base_state_kernel's skeleton (parallel sweep -> running products -> until no bit changes) */ \
+EXPORT int hc_base_state_fp_##SFX(TF* pref, TF* prefh, TF* rho, TF* rhoh, TF* thv, TF* thvh, TF* ex, TF* exh, \
+        const TF* thlmean, const TF* qtmean, TF pbot, int kstart, int kend, const TF* z, const TF* dz, const TF* dzh, \
+        TF* F, TF* Fh, int cold, int* sweeps) \
+{ const MoistProfiles<TF> b{pref, prefh, rho, rhoh, thv, thvh, ex, exh}; \
+  const bool scratch = cold != 0 || !(b.pref[kstart] > TF(0.)) || !(b.prefh[kend] > TF(0.)); \
+  if (scratch) for (int k = kstart; k <= kend; ++k) { b.prefh[k] = pbot; b.pref[k] = pbot; } \
+  int bad = 0; *sweeps = 0; \
+  for (int it = 0; it < kend - kstart + 3; ++it) \
+  { bad = 0; \
+    for (int k = kstart; k <= kend; ++k) bad += moist_base_level<TF>(b, thlmean, qtmean, k, kstart, kend, z, dz, dzh, F, Fh); \
+    const int changed = moist_base_cumprod<TF>(b, pbot, kstart, kend, F, Fh); \
+    ++*sweeps; \
+    if (!changed) break; } \
+  b.pref[kstart - 1] = TF(2.) * b.prefh[kstart] - b.pref[kstart]; \
+  return bad; }
 
 DEFINE(double, f64)
 DEFINE(float, f32)

@@ -54,6 +54,22 @@ def test_moist_arithmetic_host_bitexact(lib, dtype, cold):
     assert bad == 0
     for n in names:
         assert np.array_equal(got[n], ref[n]), (n, got[n], ref[n])
+    # the fixed-point form the device kernel uses: the same bits as the serial integration, from scratch, from the previous
+    # base state (here: the converged one of a 0.7 K warmer state) and from unusable pressures
+    fp = getattr(lib, "hc_base_state_fp_" + sfx); fp.restype = C.c_int
+    F = np.zeros(g.kcells, dtype); Fh = np.zeros(g.kcells, dtype); sweeps = C.c_int(0)
+    warm_from = O.moist_base_state(g, (thl0 + dtype(0.7)).astype(dtype), qt0, pbot)
+    nsw = {}
+    for start in ("cold", "warm", "zeros"):
+        got2 = {n: (warm_from[n].copy() if start == "warm" else np.zeros(g.kcells, dtype)) for n in names}
+        bad = fp(*[_p(got2[n]) for n in names], _p(thl0), _p(qt0), ct(pbot), C.c_int(g.kstart), C.c_int(g.kend), _p(z), _p(dz), _p(dzh),
+                 _p(F), _p(Fh), C.c_int(1 if start == "cold" else 0), C.byref(sweeps))
+        assert bad == 0
+        for n, (lo, hi) in dict(pref=(-1, 1), prefh=(0, 1), rhoref=(0, 0), thvref=(0, 0), exnref=(0, 0), rhorefh=(0, 1), thvrefh=(0, 1), exnrefh=(0, 1)).items():
+            sl = slice(g.kstart + lo, g.kend + hi)
+            assert np.array_equal(got2[n][sl], ref[n][sl]), (start, n, got2[n][sl], ref[n][sl])
+        nsw[start] = sweeps.value
+    assert nsw["warm"] <= nsw["cold"] <= 24 and nsw["zeros"] == nsw["cold"], nsw
     ex_fn = getattr(lib, "hc_exner_" + sfx); ex_fn.restype = ct; ex_fn.argtypes = [ct]
     sa = getattr(lib, "hc_sat_adjust_" + sfx); sa.restype = C.c_int
     bu = getattr(lib, "hc_buoyancy_" + sfx)

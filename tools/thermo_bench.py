@@ -40,7 +40,8 @@ def main():
         z = torch.from_numpy(np.asarray(gd.z, np.float64)).to(f["u"].device)
         zrel = (z/float(gd.zsize))[:, None, None]
         f["thl"].copy_((298. + 6.*zrel + (f["thl"].double() - 300. - 0.003*z[:, None, None])).to(f["thl"].dtype))
-        f["qt"].copy_((17.e-3*(1. - 0.5*zrel) + 3.e-3*torch.exp(-((zrel - 0.45)/0.15)**2)
+        # a cumulus-like layer: the mean profile stays just below saturation, the fluctuations saturate a few per cent of the points
+        f["qt"].copy_((17.e-3*(1. - 0.75*zrel) + 1.1e-3*torch.exp(-((zrel - 0.45)/0.15)**2)
                        + 1.e-4*torch.randn(gd.shape, device=z.device, dtype=torch.float64)).clamp_min(1e-5).to(f["qt"].dtype))
         for n, v in (("thl_fluxbot", 8.e-3), ("qt_fluxbot", 5.2e-5), ("thl_gradbot", -1.e-3), ("qt_gradbot", -1.e-6), ("qt_gradtop", -1.e-6)):
             f[n].fill_(v)
@@ -92,6 +93,9 @@ def main():
            "kernels_ms_per_step": {n: v["ms"]/a.steps for n, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:8]}}
     if moist:
         out["nonconverged"] = T.nonconverged()
+        out["base_state_sweeps_last"] = T.base_state_sweeps()
+        T.get_thermo_field(f["evisc"], "ql", f)
+        out["cloud_fraction"] = float((f["evisc"][ks:ke, gd.jstart:gd.jend, gd.istart:gd.iend] > 0).double().mean().item())
         bs = T.get_profiles()
         out["thvrefh_surface"] = float(bs["thvrefh"][ks]); out["prefh_top"] = float(bs["prefh"][ke])
     print(json.dumps(out))
