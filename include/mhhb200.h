@@ -109,7 +109,7 @@ typedef struct mhh_fields
 /* Run-time switches of the path ([advec] [diff] [boundary] [thermo] of the .ini). */
 typedef struct mhh_params
 {
-    int    swadvec;              /* 25 = 2i5, 2 = 2, 4 = 4, 41 = 4m */
+    int    swadvec;              /* 25 = 2i5, 2 = 2, 24 = 2i4, 262 = 2i62, 4 = 4, 41 = 4m */
     int    swdiff;               /* 1 = smag2, 2 = 2, 3 = tke2 (needs mhh_dycore_set_tke2), 4 = 4 (the 4th-order configuration:
                                   * 4 + 4 + pres_4 on a 4th-order grid) */
     int    swthermo;             /* 0 = off, 1 = dry (buoyancy from scalar 0 = th), 2 = buoy (scalar 0 IS the buoyancy b;
@@ -346,7 +346,8 @@ MHH_API int mhh_dycore_set_thermo_buoy(mhh_ctx* ctx, const mhh_thermo_buoy* tb);
  * mhh_set_basestate set (create_basestate step 6 copies the INITIAL rhoref there; they are not updated afterwards).
  *   _calc_base_state  Thermo_moist_functions::calc_base_state (functions.h:271-340) on the device from HOST mean profiles
  *                     thl0 / qt0 (kcells, ghost entries kstart-1 and kend set, e.g. by calc_top_and_bot) = create_basestate step 4
- *   _set_profiles     overwrite any of the eight profiles from HOST arrays (NULL = keep): the Boussinesq override of
+ *   _set_profiles     overwrite any of the eight profiles from HOST arrays (NULL = keep; pref with exnref and prefh with exnrefh,
+ *                     both or neither: the kernels take the exner function from the profile): the Boussinesq override of
  *                     create_basestate step 5, or a base state loaded from a restart file (Thermo_moist::load)
  *   _get_profiles     copy them to HOST arrays (NULL = skip); synchronises
  *   _exec             Thermo_moist::exec (:1415-1447): with swupdatebasestate the mean profiles of thl and qt

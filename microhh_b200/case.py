@@ -67,7 +67,7 @@ def _get_sub(ini, sec, key, sub, default=None, conv=str):
 
 _MBC = {"noslip": capi.BC_DIRICHLET, "freeslip": capi.BC_NEUMANN, "neumann": capi.BC_NEUMANN}
 _SBC = {"dirichlet": capi.BC_DIRICHLET, "neumann": capi.BC_NEUMANN, "flux": capi.BC_NEUMANN}
-_SWADVEC = {"2": 2, "2i5": 25, "4": 4, "4m": 41}
+_SWADVEC = {"2": 2, "2i5": 25, "2i4": 24, "2i62": 262, "4": 4, "4m": 41}
 _SWDIFF = {"smag2": 1, "2": 2, "tke2": 3, "4": 4}
 
 
@@ -122,8 +122,10 @@ class CaseConfig:
             return 3, 3, 3
         if self.swadvec == "2i5":
             return 3, 3, (2 if self.fluxlimit_list else 1)
-        if self.swadvec in ("2i4", "2i62"):
-            return (2, 2, 1) if self.swadvec == "2i4" else (3, 3, 1)
+        if self.swadvec == "2i4":
+            return 2, 2, 2                                    # src/advec_2i4.cxx:38-41
+        if self.swadvec == "2i62":
+            return 3, 3, (2 if self.fluxlimit_list else 1)    # src/advec_2i62.cxx:42-45
         return 1, 1, 1
 
     def unsupported(self):

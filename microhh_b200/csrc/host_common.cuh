@@ -26,6 +26,7 @@
 #include "tke2_kernels.cuh"
 #include "order2_kernels.cuh"
 #include "order4_kernels.cuh"
+#include "order2i_kernels.cuh"
 #include "pres4_kernels.cuh"
 #include "thermo_buoy_kernels.cuh"
 #include "thermo_moist_kernels.cuh"
@@ -254,6 +255,7 @@ template <typename TF> int evisc_impl(Ctx<TF>* c, const mhh_fields* f, const mhh
 template <typename TF> int tend_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, bool adv, bool diff, bool buoy, const mhh_tke2* tke = nullptr, bool adv2 = false);
 template <typename TF> int o2_impl(Ctx<TF>* c, const mhh_fields* f, bool adv, bool diff, bool buoy);
 template <typename TF> int o4_impl(Ctx<TF>* c, const mhh_fields* f, int adv_sw, bool diff);
+template <typename TF> int adv2i_impl(Ctx<TF>* c, const mhh_fields* f, int adv_sw);
 template <typename TF> int o2_cfl_impl(Ctx<TF>* c, const mhh_fields* f, double* out, int order);
 template <typename TF> int reduce_mode_impl(Ctx<TF>* c, int mode, const TF* u, const TF* v, const TF* w, TF p0, TF p1, TF p2, double* out);
 // host_tke2.cu

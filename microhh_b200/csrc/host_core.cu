@@ -458,8 +458,8 @@ int substep_check(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, bool& 
         o4 = true;
         return MHH_OK;
     }
-    if ((prm->swadvec != 25 && prm->swadvec != 2) || (prm->swdiff != 1 && prm->swdiff != 2 && prm->swdiff != 3))
-    { c->err = "dycore_substep: swadvec must be 2i5 (25), 2, 4 or 4m (41), swdiff smag2 (1), 2, tke2 (3) or 4"; return MHH_E_INVALID; }
+    if ((prm->swadvec != 25 && prm->swadvec != 2 && prm->swadvec != 24 && prm->swadvec != 262) || (prm->swdiff != 1 && prm->swdiff != 2 && prm->swdiff != 3))
+    { c->err = "dycore_substep: swadvec must be 2i5 (25), 2, 2i4 (24), 2i62 (262), 4 or 4m (41), swdiff smag2 (1), 2, tke2 (3) or 4"; return MHH_E_INVALID; }
     const bool smag = prm->swdiff == 1 || prm->swdiff == 3;
     if (prm->swthermo < 0 || prm->swthermo > 3) { c->err = "dycore_substep: swthermo must be 0, dry (1), buoy (2) or moist (3)"; return MHH_E_INVALID; }
     if (prm->swthermo == 3)
@@ -529,7 +529,12 @@ int tendencies_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm)
     const mhh_tke2* tke = prm->swdiff == 3 ? &c->tke2 : nullptr;                             // Diff_tke2::exec = the smag2 kernels, evisc per scalar
     if (prm->swthermo == 2 && (rc = thermo_buoy_impl<TF>(c, f, &c->buoy)) != MHH_OK) return rc;  // Thermo_buoy::exec, ahead of advec.exec like Model::exec
     if (prm->swthermo == 3 && (rc = thermo_moist_impl<TF>(c, f, &c->moist)) != MHH_OK) return rc; // Thermo_moist::exec (base-state update + buoyancy)
-    if (adv5 && smag) rc = tend_impl<TF>(c, f, prm, true, true, buoy, tke);                  // 2i5 + smag2 | tke2 (+ buoyancy)
+    if (prm->swadvec == 24 || prm->swadvec == 262)                                           // 2i4 | 2i62: the advection alone, then the diffusion (+ buoyancy)
+    {
+        if ((rc = adv2i_impl<TF>(c, f, prm->swadvec)) != MHH_OK) return rc;
+        rc = smag ? tend_impl<TF>(c, f, prm, false, true, buoy, tke) : o2_impl<TF>(c, f, false, true, buoy);
+    }
+    else if (adv5 && smag) rc = tend_impl<TF>(c, f, prm, true, true, buoy, tke);             // 2i5 + smag2 | tke2 (+ buoyancy)
     else if (!adv5 && !smag) rc = o2_impl<TF>(c, f, true, true, buoy);                       // 2 + 2 (+ buoyancy)
     else if (!adv5)                                                                          // 2 + smag2 (drycblles as shipped)
     {
@@ -1274,7 +1279,9 @@ int mhh_boundary_ghost_cells_w_4th(mhh_ctx* ctx, void* w, int conservation)
 
 int mhh_advec_exec(mhh_ctx* ctx, int swadvec, const mhh_fields* f)
 {
-    if (ctx && swadvec != 25 && swadvec != 2 && swadvec != 4 && swadvec != 41) { ctx->err = "advec_exec: swadvec must be 25 (2i5), 2, 4 or 41 (4m)"; return MHH_E_INVALID; }
+    if (ctx && swadvec != 25 && swadvec != 2 && swadvec != 4 && swadvec != 41 && swadvec != 24 && swadvec != 262)
+    { ctx->err = "advec_exec: swadvec must be 25 (2i5), 2, 24 (2i4), 262 (2i62), 4 or 41 (4m)"; return MHH_E_INVALID; }
+    if (swadvec == 24 || swadvec == 262) DISPATCH1(ctx, adv2i_impl<TF>(c, f, swadvec));
     if (swadvec == 2) DISPATCH1(ctx, o2_impl<TF>(c, f, true, false, false));
     if (swadvec == 4 || swadvec == 41) DISPATCH1(ctx, o4_impl<TF>(c, f, swadvec, false));
     DISPATCH1(ctx, tend_impl<TF>(c, f, nullptr, true, false, false));
@@ -1316,9 +1323,10 @@ int mhh_advec_get_cfl(mhh_ctx* ctx, int swadvec, const mhh_fields* f, double dt,
 {
     if (!ctx || !f || !cfl) return MHH_E_INVALID;
     SET_DEVICE(ctx);
-    if (swadvec != 25 && swadvec != 2 && swadvec != 4 && swadvec != 41) { ctx->err = "advec_get_cfl: swadvec must be 25 (2i5), 2, 4 or 41 (4m)"; return MHH_E_INVALID; }
+    if (swadvec != 25 && swadvec != 2 && swadvec != 4 && swadvec != 41 && swadvec != 24 && swadvec != 262)
+    { ctx->err = "advec_get_cfl: swadvec must be 25 (2i5), 2, 24 (2i4), 262 (2i62), 4 or 41 (4m)"; return MHH_E_INVALID; }
     int rc;
-    if (swadvec == 2 || swadvec == 4 || swadvec == 41)
+    if (swadvec == 2 || swadvec == 4 || swadvec == 41 || swadvec == 24 || swadvec == 262)
     {
         if (ctx->dtype == MHH_F64) { rc = o2_cfl_impl<double>(static_cast<Ctx<double>*>(ctx), f, cfl, swadvec); if (rc == MHH_OK) *cfl = *cfl * dt; }
         else { rc = o2_cfl_impl<float>(static_cast<Ctx<float>*>(ctx), f, cfl, swadvec); if (rc == MHH_OK) *cfl = (double)((float)*cfl * (float)dt); }

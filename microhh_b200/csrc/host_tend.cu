@@ -530,6 +530,43 @@ int o2_impl(Ctx<TF>* c, const mhh_fields* f, bool adv, bool diff, bool buoy)
     return MHH_OK;
 }
 
+// Advec_2i4 (adv_sw = 24) / Advec_2i62 (adv_sw = 262): the advection alone (order2i_kernels.cuh); flux-limited scalars of 2i62
+// take the Koren-limited kernel Advec_2i5 uses (src/advec_2i62.cxx:455-476 calls the same advec_s_lim)
+template <typename TF>
+int adv2i_impl(Ctx<TF>* c, const mhh_fields* f, int adv_sw)
+{
+    NEED_BASE(c);
+    const GridDev<TF>& g = c->g;
+    int rc = check_mom<TF>(c, f, false, false);
+    if (rc != MHH_OK) return rc;
+    const bool i4 = adv_sw == 24;
+    if (g.dzi4) { c->err = "advec 2i4 / 2i62: second-order grids only"; return MHH_E_INVALID; }
+    // the ghost cells the reference's constructors ask for (src/advec_2i4.cxx:38-41, src/advec_2i62.cxx:42-45)
+    if (i4 ? (g.igc < 2 || g.jgc < 2 || g.kgc < 2) : (g.igc < 3 || g.jgc < 3))
+    { c->err = i4 ? "advec_2i4 needs igc, jgc, kgc >= 2" : "advec_2i62 needs igc, jgc >= 3"; return MHH_E_INVALID; }
+    if (g.kmax < 4) { c->err = "advec 2i4 / 2i62 need ktot >= 4"; return MHH_E_INVALID; }
+    Adv2iArgs<TF> a{P<TF>(f->ut), P<TF>(f->vt), P<TF>(f->wt), P<TF>(f->u), P<TF>(f->v), P<TF>(f->w)};
+    dim3 gr = c->grd_interior(), b = c->blk();
+    if (i4) adv2i_uvw_kernel<TF, 4><<<gr, b, 0, c->stream>>>(a, g);
+    else    adv2i_uvw_kernel<TF, 6><<<gr, b, 0, c->stream>>>(a, g);
+    KCHECKN(c, "adv2i_uvw_kernel");
+    for (int n = 0; n < f->ns; ++n)
+    {
+        NEED(c, f->s[n], "scalar"); NEED(c, f->st[n], "scalar tendency");
+        if (!i4 && f->s_fluxlimit[n])
+        {
+            if (g.kgc < 2) { c->err = "flux-limited scalars need kgc >= 2 (src/advec_2i62.cxx:44)"; return MHH_E_INVALID; }
+            advec_s_lim_kernel<TF><<<gr, b, 0, c->stream>>>(P<TF>(f->st[n]), P<TF>(f->s[n]), a.u, a.v, a.w, g);
+            KCHECKN(c, "advec_s_lim_kernel");
+            continue;
+        }
+        if (i4) adv2i_s_kernel<TF, 4><<<gr, b, 0, c->stream>>>(P<TF>(f->st[n]), P<TF>(f->s[n]), a.u, a.v, a.w, g);
+        else    adv2i_s_kernel<TF, 6><<<gr, b, 0, c->stream>>>(P<TF>(f->st[n]), P<TF>(f->s[n]), a.u, a.v, a.w, g);
+        KCHECKN(c, "adv2i_s_kernel");
+    }
+    return MHH_OK;
+}
+
 // Advec_4 (adv_sw = 4) or Advec_4m (adv_sw = 41) / Diff_4 in any combination (order4_kernels.cuh)
 template <typename TF>
 int o4_impl(Ctx<TF>* c, const mhh_fields* f, int adv_sw, bool diff)
@@ -591,8 +628,10 @@ int o2_cfl_impl(Ctx<TF>* c, const mhh_fields* f, double* out, int order)
     CUDA_TRY(c, cudaMemsetAsync(c->d_red, 0, sizeof(double), c->stream));
     if (order == 4) o4_cfl_kernel<TF, false><<<c->grd_interior(), c->blk(), 0, c->stream>>>(P<TF>(f->u), P<TF>(f->v), P<TF>(f->w), g, c->d_red);
     else if (order == 41) o4_cfl_kernel<TF, true><<<c->grd_interior(), c->blk(), 0, c->stream>>>(P<TF>(f->u), P<TF>(f->v), P<TF>(f->w), g, c->d_red);
+    else if (order == 24) adv2i_cfl_kernel<TF, 4><<<c->grd_interior(), c->blk(), 0, c->stream>>>(P<TF>(f->u), P<TF>(f->v), P<TF>(f->w), g, c->d_red);
+    else if (order == 262) adv2i_cfl_kernel<TF, 6><<<c->grd_interior(), c->blk(), 0, c->stream>>>(P<TF>(f->u), P<TF>(f->v), P<TF>(f->w), g, c->d_red);
     else o2_cfl_kernel<TF><<<c->grd_interior(), c->blk(), 0, c->stream>>>(P<TF>(f->u), P<TF>(f->v), P<TF>(f->w), g, c->d_red);
-    const char* cfl_name = order == 2 ? "o2_cfl_kernel" : "o4_cfl_kernel";
+    const char* cfl_name = order == 2 ? "o2_cfl_kernel" : (order == 24 || order == 262) ? "adv2i_cfl_kernel" : "o4_cfl_kernel";
     KCHECKN(c, cfl_name);
     if (c->nranks > 1)
     {
@@ -641,6 +680,7 @@ int reduce_mode_impl(Ctx<TF>* c, int mode, const TF* u, const TF* v, const TF* w
     template int tend_impl<TF>(Ctx<TF>*, const mhh_fields*, const mhh_params*, bool, bool, bool, const mhh_tke2*, bool); \
     template int o2_impl<TF>(Ctx<TF>*, const mhh_fields*, bool, bool, bool); template int o4_impl<TF>(Ctx<TF>*, const mhh_fields*, int, bool); \
     template int o2_cfl_impl<TF>(Ctx<TF>*, const mhh_fields*, double*, int); \
+    template int adv2i_impl<TF>(Ctx<TF>*, const mhh_fields*, int); \
     template int reduce_mode_impl<TF>(Ctx<TF>*, int, const TF*, const TF*, const TF*, TF, TF, TF, double*);
 
 INST(double)

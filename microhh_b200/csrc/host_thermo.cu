@@ -101,6 +101,9 @@ int moist_profiles_copy(Ctx<TF>* c, void* const* host, bool to_host)
 {
     int rc = moist_alloc<TF>(c);
     if (rc != MHH_OK) return rc;
+    // a pressure profile travels with its exner function (the kernels read exnref / exnrefh instead of re-evaluating the pow)
+    if (!to_host && ((host[0] != nullptr) != (host[6] != nullptr) || (host[1] != nullptr) != (host[7] != nullptr)))
+    { c->err = "thermo_moist_set_profiles: pref goes with exnref and prefh with exnrefh (both or neither)"; return MHH_E_INVALID; }
     const MoistProfiles<TF> b = c->moist_profiles();
     TF* dev[8] = {b.pref, b.prefh, b.rho, b.rhoh, b.thv, b.thvh, b.ex, b.exh};
     const size_t bytes = sizeof(TF) * c->g.kcells;
@@ -137,7 +140,7 @@ int thermo_moist_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_thermo_moist* t
     if (g.kmax > 1)
     {
         dim3 b(64, 4), gr((g.imax + 63) / 64, (g.jmax + 3) / 4, g.kmax - 1);
-        moist_buoyancy_tend_kernel<TF><<<gr, b, 0, c->stream>>>(P<TF>(f->wt), thl, qt, c->moist_profiles().prefh, g.threfh, g, c->d_moist_flag);
+        moist_buoyancy_tend_kernel<TF><<<gr, b, 0, c->stream>>>(P<TF>(f->wt), thl, qt, c->moist_profiles().prefh, c->moist_profiles().exh, g.threfh, g, c->d_moist_flag);
         KCHECKN(c, "moist_buoyancy_tend_kernel");
     }
     return MHH_OK;

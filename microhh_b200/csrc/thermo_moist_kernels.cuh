@@ -338,18 +338,18 @@ __global__ void __launch_bounds__(256) moist_base_state_kernel(const MoistProfil
 
 // calc_buoyancy_tend_2nd (src/thermo_moist.cxx:77-120): wt += buoyancy of (thl, qt) interpolated to the half level, with the
 // condensate of the saturation adjustment at that level's pressure.  One level per blockIdx.z (k = kstart+1 .. kend-1).
+// exnh = exnrefh[k] of the base state: the reference evaluates exner(ph[k]) here, which is the very number its calc_base_state
+// stored in exnrefh[k] (same function, same argument).  A pow per CTA ahead of a 256-point tile was the bottleneck of the first
+// version (0.68 ms per launch at 512 x 512 x 256 fp32 with no cloud at all: 261 k CTAs each waiting for one lane's powf).
 template <typename TF>
 __global__ void __launch_bounds__(256) moist_buoyancy_tend_kernel(TF* __restrict__ wt, const TF* __restrict__ thl, const TF* __restrict__ qt,
-        const TF* __restrict__ ph, const TF* __restrict__ thvrefh, const GridDev<TF> g, int* __restrict__ nonconv)
+        const TF* __restrict__ ph, const TF* __restrict__ exh, const TF* __restrict__ thvrefh, const GridDev<TF> g, int* __restrict__ nonconv)
 {
     const int i = g.istart + blockIdx.x * blockDim.x + threadIdx.x;
     const int j = g.jstart + blockIdx.y * blockDim.y + threadIdx.y;
     const int k = g.kstart + 1 + blockIdx.z;
-    __shared__ TF s_exnh;
-    if (threadIdx.x == 0 && threadIdx.y == 0) s_exnh = moist_exner(ph[k]);
-    __syncthreads();
     if (i >= g.iend || j >= g.jend) return;
-    const TF exnh = s_exnh, p = ph[k];
+    const TF exnh = exh[k], p = ph[k];
     const long long ijk = i + (long long)j * g.icells + k * g.ijcells;
     const TF thlh = interp2(thl[ijk - g.ijcells], thl[ijk]);
     const TF qth  = interp2(qt[ijk - g.ijcells], qt[ijk]);

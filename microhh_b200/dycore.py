@@ -13,7 +13,7 @@ import torch
 from . import capi
 from .capi import FieldsC, ParamsC, GridDesc, SurfaceC, ForcingC, MhhError
 
-SWADVEC = {"2i5": 25, "2": 2, "4": 4, "4m": 41}
+SWADVEC = {"2i5": 25, "2": 2, "2i4": 24, "2i62": 262, "4": 4, "4m": 41}
 SWDIFF = {"smag2": 1, "2": 2, "tke2": 3, "4": 4}
 SWTHERMO = {"0": 0, None: 0, "disabled": 0, "dry": 1, "buoy": 2, "moist": 3}
 

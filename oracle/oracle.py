@@ -2005,6 +2005,118 @@ def force_wls_local(g, st, s, wls):
 
 
 # --------------------------------------------------------------------------------------
+# Advec_2i4 (reference src/advec_2i4.cxx:53-518) and Advec_2i62 (src/advec_2i62.cxx:59-306): 2nd-order flux divergence of
+# centred interpolations -- 2i4: interp4c in all directions, falling back to interp2 on the vertical faces next to the walls
+# and to no flux through the walls themselves (the reference writes those rows out one by one; `a - 0` and `-(-b)` are exact,
+# so one expression with the per-face choice gives the same bits); 2i62: interp6_ws horizontally, interp2 vertically throughout.
+# --------------------------------------------------------------------------------------
+def _2ix_h(TF, scheme, q, axis, g, k0, k1):
+    """interpolation of q to the LOWER face of every cell along a horizontal axis ('i' or 'j'); returns f(shift) giving the face
+    value at cell+shift"""
+    def sh(d, shift):
+        return _S(g, q, 0, d + shift if axis == 'j' else 0, d + shift if axis == 'i' else 0, k0, k1)
+    if scheme == "2i4":
+        return lambda shift=0: _i4c(TF, sh(-2, shift), sh(-1, shift), sh(0, shift), sh(1, shift))
+    return lambda shift=0: interp6_ws(sh(-3, shift), sh(-2, shift), sh(-1, shift), sh(0, shift), sh(1, shift), sh(2, shift))
+
+def _2ix_dxdy(g, scheme):
+    TF = g.TF
+    if scheme == "2i4":
+        return TF(1./np.float64(g.dx)), TF(1./np.float64(g.dy))        # gd.dxi = 1./gd.dx (src/grid.cxx:252-253), passed in by exec
+    return TF(1.)/g.dx, TF(1.)/g.dy                                    # src/advec_2i62.cxx:130-131
+
+def _2ix_vface(TF, scheme, q, g, k, lo, hi):
+    """vertical interpolation of q to the face below level k (one level, interior columns): order by the distance to the
+    walls for 2i4 (None = no flux), interp2 for 2i62.  lo / hi: first and last face that carry a flux of order >= 2 in 2i4."""
+    sl = lambda dk: q[k+dk, g.jstart:g.jend, g.istart:g.iend]
+    if scheme == "2i62":
+        return interp2(sl(-1), sl(0))
+    if k < lo or k > hi:
+        return None
+    if k == lo or k == hi:
+        return interp2(sl(-1), sl(0))
+    return _i4c(TF, sl(-2), sl(-1), sl(0), sl(1))
+
+def _advec_2ix_cc(g, at, a, u, v, w, rhoref, rhorefh, scheme, loc):
+    """tendency of a field whose vertical location is the cell centre: u (loc 'u'), v ('v') or a scalar ('s')"""
+    TF = g.TF
+    dxi, dyi = _2ix_dxdy(g, scheme)
+    ks, ke = g.kstart, g.kend
+    A = lambda dk=0, dj=0, di=0: _S(g, a, dk, dj, di)
+    U = lambda dk=0, dj=0, di=0: _S(g, u, dk, dj, di)
+    V = lambda dk=0, dj=0, di=0: _S(g, v, dk, dj, di)
+    hx = _2ix_h(TF, scheme, a, 'i', g, ks, ke); hy = _2ix_h(TF, scheme, a, 'j', g, ks, ke)
+    if loc == 'u':
+        tx = -(interp2(U(), U(0,0,1))*hx(1) - interp2(U(0,0,-1), U())*hx(0))*dxi
+        ty = -(interp2(V(0,1,-1), V(0,1,0))*hy(1) - interp2(V(0,0,-1), V())*hy(0))*dyi
+    elif loc == 'v':
+        tx = -(interp2(U(0,-1,1), U(0,0,1))*hx(1) - interp2(U(0,-1,0), U())*hx(0))*dxi
+        ty = -(interp2(V(), V(0,1,0))*hy(1) - interp2(V(0,-1,0), V())*hy(0))*dyi
+    else:
+        tx = -(U(0,0,1)*hx(1) - U()*hx(0))*dxi
+        ty = -(V(0,1,0)*hy(1) - V()*hy(0))*dyi
+    for k in range(ks, ke):
+        wsl = lambda kk, dj=0, di=0: w[kk, g.jstart+dj:g.jend+dj, g.istart+di:g.iend+di]
+        def wf(kk):
+            if loc == 'u': return interp2(wsl(kk, 0, -1), wsl(kk))
+            if loc == 'v': return interp2(wsl(kk, -1, 0), wsl(kk))
+            return wsl(kk)
+        top = _2ix_vface(TF, scheme, a, g, k+1, ks+1, ke-1)
+        bot = _2ix_vface(TF, scheme, a, g, k, ks+1, ke-1)
+        if top is not None and bot is not None:
+            vert = rhorefh[k+1]*wf(k+1)*top - rhorefh[k]*wf(k)*bot
+        elif top is not None:
+            vert = rhorefh[k+1]*wf(k+1)*top
+        else:
+            vert = -rhorefh[k]*wf(k)*bot
+        at[k, g.jstart:g.jend, g.istart:g.iend] += tx[k-ks] + ty[k-ks] - vert/rhoref[k]*g.dzi[k]
+
+def advec_2ix_u(g, ut, u, v, w, rhoref, rhorefh, scheme): _advec_2ix_cc(g, ut, u, u, v, w, rhoref, rhorefh, scheme, 'u')
+def advec_2ix_v(g, vt, u, v, w, rhoref, rhorefh, scheme): _advec_2ix_cc(g, vt, v, u, v, w, rhoref, rhorefh, scheme, 'v')
+def advec_2ix_s(g, st, s, u, v, w, rhoref, rhorefh, scheme): _advec_2ix_cc(g, st, s, u, v, w, rhoref, rhorefh, scheme, 's')
+
+def advec_2ix_w(g, wt, u, v, w, rhoref, rhorefh, scheme):
+    """advec_w (src/advec_2i4.cxx:341-416, src/advec_2i62.cxx:206-255): levels kstart+1 .. kend-1; the vertical fluxes sit at the
+    cell centres, 2i4: interp2 at the lowest and the highest centre, interp4c in between"""
+    TF = g.TF
+    dxi, dyi = _2ix_dxdy(g, scheme)
+    ks, ke = g.kstart, g.kend
+    k0, k1 = ks+1, ke
+    U = lambda dk=0, dj=0, di=0: _S(g, u, dk, dj, di, k0, k1)
+    V = lambda dk=0, dj=0, di=0: _S(g, v, dk, dj, di, k0, k1)
+    hx = _2ix_h(TF, scheme, w, 'i', g, k0, k1); hy = _2ix_h(TF, scheme, w, 'j', g, k0, k1)
+    tx = -(interp2(U(-1,0,1), U(0,0,1))*hx(1) - interp2(U(-1,0,0), U())*hx(0))*dxi
+    ty = -(interp2(V(-1,1,0), V(0,1,0))*hy(1) - interp2(V(-1,0,0), V())*hy(0))*dyi
+    sl = lambda kk: w[kk, g.jstart:g.jend, g.istart:g.iend]
+    def centre(c):
+        """w interpolated to cell centre c (between faces c and c+1)"""
+        if scheme == "2i62" or c == ks or c == ke-1:
+            return interp2(sl(c), sl(c+1))
+        return _i4c(TF, sl(c-1), sl(c), sl(c+1), sl(c+2))
+    for k in range(k0, k1):
+        vert = rhoref[k]*interp2(sl(k), sl(k+1))*centre(k) - rhoref[k-1]*interp2(sl(k-1), sl(k))*centre(k-1)
+        wt[k, g.jstart:g.jend, g.istart:g.iend] += tx[k-k0] + ty[k-k0] - vert/rhorefh[k]*g.dzhi[k]
+
+def advec_2ix_cfl(g, u, v, w, dt, scheme):
+    """calc_cfl (src/advec_2i4.cxx:53-107, src/advec_2i62.cxx:59-102)"""
+    TF = g.TF
+    ks, ke = g.kstart, g.kend
+    if scheme == "2i4":
+        dxi, dyi = TF(1./np.float64(g.dx)), TF(1./np.float64(g.dy))     # gd.dxi, gd.dyi (src/advec_2i4.cxx:675)
+        uc = _i4c(TF, _S(g, u, 0, 0, -1), _S(g, u), _S(g, u, 0, 0, 1), _S(g, u, 0, 0, 2))
+        vc = _i4c(TF, _S(g, v, 0, -1), _S(g, v), _S(g, v, 0, 1), _S(g, v, 0, 2))
+        wc = _i4c(TF, _S(g, w, -1), _S(g, w), _S(g, w, 1), _S(g, w, 2)).copy()
+        wc[0] = interp2(_S(g, w), _S(g, w, 1))[0]; wc[-1] = interp2(_S(g, w), _S(g, w, 1))[-1]
+    else:
+        dxi, dyi = TF(1./np.float64(g.dx)), TF(1./np.float64(g.dy))     # `const TF dxi = 1./dx;` (:82-83)
+        uc = interp6_ws(_S(g, u, 0, 0, -2), _S(g, u, 0, 0, -1), _S(g, u), _S(g, u, 0, 0, 1), _S(g, u, 0, 0, 2), _S(g, u, 0, 0, 3))
+        vc = interp6_ws(_S(g, v, 0, -2), _S(g, v, 0, -1), _S(g, v), _S(g, v, 0, 1), _S(g, v, 0, 2), _S(g, v, 0, 3))
+        wc = interp2(_S(g, w), _S(g, w, 1))
+    cfl = (np.abs(uc)*dxi + np.abs(vc)*dyi + np.abs(wc)*_K(g, g.dzi)).max()
+    return TF(cfl)*TF(dt)
+
+
+# --------------------------------------------------------------------------------------
 # Thermo_buoy (reference src/thermo_buoy.cxx:41-296, exec :345-391): the prognostic scalar IS the buoyancy.
 # --------------------------------------------------------------------------------------
 def _sin(TF, a):
@@ -2386,6 +2498,16 @@ class NumpyKernels:
     def diff_c(self, at, a, evisc, fluxbot, fluxtop, rhoref, rhorefh, tPr, visc, surface): diff_c(self.g, at, a, evisc, fluxbot, fluxtop, rhoref, rhorefh, tPr, visc, surface)
     def diff_dnmul(self, evisc, tPr): return float(diff_dnmul(self.g, evisc, tPr))
     def thermo_buoy_N2(self, N2, b, bg_n2): thermo_buoy_N2(self.g, N2, b, bg_n2)
+    def advec_2i4_u(self, at, u, v, w, rhoref, rhorefh): advec_2ix_u(self.g, at, u, v, w, rhoref, rhorefh, "2i4")
+    def advec_2i4_v(self, at, u, v, w, rhoref, rhorefh): advec_2ix_v(self.g, at, u, v, w, rhoref, rhorefh, "2i4")
+    def advec_2i4_w(self, at, u, v, w, rhoref, rhorefh): advec_2ix_w(self.g, at, u, v, w, rhoref, rhorefh, "2i4")
+    def advec_2i4_s(self, st, s, u, v, w, rhoref, rhorefh): advec_2ix_s(self.g, st, s, u, v, w, rhoref, rhorefh, "2i4")
+    def advec_2i4_cfl(self, u, v, w, dt): return float(advec_2ix_cfl(self.g, u, v, w, dt, "2i4"))
+    def advec_2i62_u(self, at, u, v, w, rhoref, rhorefh): advec_2ix_u(self.g, at, u, v, w, rhoref, rhorefh, "2i62")
+    def advec_2i62_v(self, at, u, v, w, rhoref, rhorefh): advec_2ix_v(self.g, at, u, v, w, rhoref, rhorefh, "2i62")
+    def advec_2i62_w(self, at, u, v, w, rhoref, rhorefh): advec_2ix_w(self.g, at, u, v, w, rhoref, rhorefh, "2i62")
+    def advec_2i62_s(self, st, s, u, v, w, rhoref, rhorefh): advec_2ix_s(self.g, st, s, u, v, w, rhoref, rhorefh, "2i62")
+    def advec_2i62_cfl(self, u, v, w, dt): return float(advec_2ix_cfl(self.g, u, v, w, dt, "2i62"))
     def moist_base_state(self, thlmean, qtmean, pbot): return moist_base_state(self.g, thlmean, qtmean, pbot)
     def moist_top_and_bot(self, thl0, qt0): moist_top_and_bot(self.g, thl0, qt0)
     def mean_profile(self, fld): return mean_profile(self.g, fld)

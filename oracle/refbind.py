@@ -105,6 +105,40 @@ class RefKernels:
         g = self.g
         return self._call("ref_advec_2_cfl", u, v, w, g.dzi, g.dx, g.dy, float(dt), restype=C.c_double)
 
+    # --- advec_2i4 (oracle/ref/ref_advec_2i4.cpp)
+    def advec_2i4_u(self, at, u, v, w, rhoref, rhorefh):
+        g = self.g; self._call("ref_advec_2i4_u", at, u, v, w, g.dzi, g.dx, g.dy, rhoref, rhorefh)
+
+    def advec_2i4_v(self, at, u, v, w, rhoref, rhorefh):
+        g = self.g; self._call("ref_advec_2i4_v", at, u, v, w, g.dzi, g.dx, g.dy, rhoref, rhorefh)
+
+    def advec_2i4_w(self, at, u, v, w, rhoref, rhorefh):
+        g = self.g; self._call("ref_advec_2i4_w", at, u, v, w, g.dzhi, g.dx, g.dy, rhoref, rhorefh)
+
+    def advec_2i4_s(self, st, s, u, v, w, rhoref, rhorefh):
+        g = self.g; self._call("ref_advec_2i4_s", st, s, u, v, w, g.dzi, g.dx, g.dy, rhoref, rhorefh)
+
+    def advec_2i4_cfl(self, u, v, w, dt):
+        g = self.g
+        return self._call("ref_advec_2i4_cfl", u, v, w, g.dzi, g.dx, g.dy, float(dt), restype=C.c_double)
+
+    # --- advec_2i62 (oracle/ref/ref_advec_2i62.cpp)
+    def advec_2i62_u(self, at, u, v, w, rhoref, rhorefh):
+        g = self.g; self._call("ref_advec_2i62_u", at, u, v, w, g.dzi, g.dx, g.dy, rhoref, rhorefh)
+
+    def advec_2i62_v(self, at, u, v, w, rhoref, rhorefh):
+        g = self.g; self._call("ref_advec_2i62_v", at, u, v, w, g.dzi, g.dx, g.dy, rhoref, rhorefh)
+
+    def advec_2i62_w(self, at, u, v, w, rhoref, rhorefh):
+        g = self.g; self._call("ref_advec_2i62_w", at, u, v, w, g.dzhi, g.dx, g.dy, rhoref, rhorefh)
+
+    def advec_2i62_s(self, st, s, u, v, w, rhoref, rhorefh):
+        g = self.g; self._call("ref_advec_2i62_s", st, s, u, v, w, g.dzi, g.dx, g.dy, rhoref, rhorefh)
+
+    def advec_2i62_cfl(self, u, v, w, dt):
+        g = self.g
+        return self._call("ref_advec_2i62_cfl", u, v, w, g.dzi, g.dx, g.dy, float(dt), restype=C.c_double)
+
     # --- diff_2
     def diff_2_c(self, at, a, visc):
         g = self.g; self._call("ref_diff_2_c", at, a, float(visc), g.dx, g.dy, g.dzi, g.dzhi)

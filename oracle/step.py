@@ -75,12 +75,15 @@ def dycore_substep(g, K, c, prm, substep, dt, pres=None, timers=None, surface_mo
             K.ghost_cells_top_2nd(c[s_], prm["sbctop"], c.get(s_ + "_top"), c.get(s_ + "_gradtop"))
     # advec.exec (Advec_2i5::exec src/advec_2i5.cxx:1017-1063, Advec_2::exec src/advec_2.cxx:311-345)
     A = {"2i5": (K.advec_2i5_u, K.advec_2i5_v, K.advec_2i5_w, K.advec_2i5_s),
-         "2": (getattr(K, "advec_2_u", None), getattr(K, "advec_2_v", None), getattr(K, "advec_2_w", None), getattr(K, "advec_2_s", None))}[swadvec]
+         "2": (getattr(K, "advec_2_u", None), getattr(K, "advec_2_v", None), getattr(K, "advec_2_w", None), getattr(K, "advec_2_s", None)),
+         # Advec_2i4::exec src/advec_2i4.cxx:700-738, Advec_2i62::exec src/advec_2i62.cxx:425-480
+         "2i4": tuple(getattr(K, "advec_2i4_" + x, None) for x in "uvws"),
+         "2i62": tuple(getattr(K, "advec_2i62_" + x, None) for x in "uvws")}[swadvec]
     A[0](c["ut"], c["u"], c["v"], c["w"], rr, rh)
     A[1](c["vt"], c["u"], c["v"], c["w"], rr, rh)
     A[2](c["wt"], c["u"], c["v"], c["w"], rr, rh)
     for s in scal:
-        if swadvec == "2i5" and s in prm.get("fluxlimit_list", ()):
+        if swadvec in ("2i5", "2i62") and s in prm.get("fluxlimit_list", ()):
             K.advec_s_lim(c[s + "t"], c[s], c["u"], c["v"], c["w"], rr, rh)      # src/advec_2i5.cxx:1046-1056
         else:
             A[3](c[s + "t"], c[s], c["u"], c["v"], c["w"], rr, rh)

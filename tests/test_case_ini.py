@@ -64,7 +64,9 @@ def test_out_of_path_switches_are_named():
     with pytest.raises(ValueError):
         bx.make_params()
     assert "swmicro=2mom_warm" in case("dycoms").unsupported()
-    assert "swadvec=2i4" in case("gabls4s3").unsupported()
+    g4 = case("gabls4s3")                                                        # swadvec=2i4 + smag2 + dry
+    assert g4.unsupported() == [] and g4.make_params().swadvec == 24 and g4.ghost_cells() == (2, 2, 2)
+    assert case("weisman_klemp").unsupported() == ["swmicro=nsw6"] and case("weisman_klemp").ghost_cells()[:2] == (3, 3)
     arm = case("arm")
     assert arm.unsupported() == [] and arm.make_params().swthermo == 3
     ws = case("weakscaling")                                                     # 4th-order DNS with swthermo=buoy

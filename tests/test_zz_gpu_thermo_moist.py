@@ -50,6 +50,8 @@ def test_moist_base_state(dtype, cold):
     T.calc_base_state(thl0, qt0)
     profiles_close(g, T.get_profiles(), case["moist_bs"], 1e-13 if dtype == np.float64 else 2e-6)
     assert T.nonconverged() == 0
+    with pytest.raises(RuntimeError, match="both or neither"):
+        T.set_profiles(prefh=case["moist_bs"]["prefh"])                     # a pressure profile travels with its exner function
     T.set_profiles(**case["moist_bs"])
     got = T.get_profiles()
     for n in case["moist_bs"]:
