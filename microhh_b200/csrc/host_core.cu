@@ -531,8 +531,10 @@ int tendencies_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm)
     if (prm->swthermo == 3 && (rc = thermo_moist_impl<TF>(c, f, &c->moist)) != MHH_OK) return rc; // Thermo_moist::exec (base-state update + buoyancy)
     if (prm->swadvec == 24 || prm->swadvec == 262)                                           // 2i4 | 2i62: the advection alone, then the diffusion (+ buoyancy)
     {
+        // Model::exec order: thermo.exec (buoyancy alone), advec.exec, diff.exec -- the diffusion-only launches carry no buoyancy
+        if (buoy && (rc = o2_impl<TF>(c, f, false, false, true)) != MHH_OK) return rc;
         if ((rc = adv2i_impl<TF>(c, f, prm->swadvec)) != MHH_OK) return rc;
-        rc = smag ? tend_impl<TF>(c, f, prm, false, true, buoy, tke) : o2_impl<TF>(c, f, false, true, buoy);
+        rc = smag ? tend_impl<TF>(c, f, prm, false, true, false, tke) : o2_impl<TF>(c, f, false, true, false);
     }
     else if (adv5 && smag) rc = tend_impl<TF>(c, f, prm, true, true, buoy, tke);             // 2i5 + smag2 | tke2 (+ buoyancy)
     else if (!adv5 && !smag) rc = o2_impl<TF>(c, f, true, true, buoy);                       // 2 + 2 (+ buoyancy)

@@ -444,6 +444,7 @@ int tend_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_params* prm, bool adv, 
         else rc = mom_tile_launch<TF>(c, a, surface, buoy);
         if (rc != MHH_OK) return rc;
     }
+    else if (!adv && buoy) { c->err = "tend_impl: the diffusion-only kernel carries no buoyancy (run the buoyancy on its own first)"; return MHH_E_INVALID; }
     else if (adv && diff && surface && buoy) LAUNCH_MOM(true, true, true, true);
     else if (adv && diff && surface) LAUNCH_MOM(true, true, true, false);
     else if (adv && diff && buoy) LAUNCH_MOM(true, true, false, true);
