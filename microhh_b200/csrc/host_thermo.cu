@@ -139,8 +139,9 @@ int thermo_moist_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_thermo_moist* t
     }
     if (g.kmax > 1)
     {
-        dim3 b(64, 4), gr((g.imax + 63) / 64, (g.jmax + 3) / 4, g.kmax - 1);
-        moist_buoyancy_tend_kernel<TF><<<gr, b, 0, c->stream>>>(P<TF>(f->wt), thl, qt, c->moist_profiles().prefh, c->moist_profiles().exh, g.threfh, g, c->d_moist_flag);
+        constexpr int KCH = 8;          // levels per thread
+        dim3 b(64, 4), gr((g.imax + 63) / 64, (g.jmax + 3) / 4, (g.kmax - 1 + KCH - 1) / KCH);
+        moist_buoyancy_tend_kernel<TF, KCH><<<gr, b, 0, c->stream>>>(P<TF>(f->wt), thl, qt, c->moist_profiles().prefh, c->moist_profiles().exh, g.threfh, g, c->d_moist_flag);
         KCHECKN(c, "moist_buoyancy_tend_kernel");
     }
     return MHH_OK;

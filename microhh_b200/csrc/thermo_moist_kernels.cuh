@@ -12,8 +12,8 @@
 // device: one reduction kernel for the two mean profiles and one single-CTA kernel for the hydrostatic integration (as a
 // fixed-point sweep over all levels in parallel, see moist_base_state_kernel), both stream-ordered -- no host round trip, and
 // the sub-step stays capturable in a CUDA graph.
-// The buoyancy kernel is HBM-bound: thl and qt read once (the level below comes out of L2), wt read and written once = 4
-// array passes; the exner function of the level is evaluated by one lane per CTA.
+// The buoyancy kernel is HBM-bound by design: thl and qt read once, wt read and written once = 4 array passes; threads march
+// a few levels up their column with the next level's loads in flight; the exner function comes from the base state.
 #pragma once
 #include "common.cuh"
 
@@ -339,23 +339,40 @@ __global__ void __launch_bounds__(256) moist_base_state_kernel(const MoistProfil
 // calc_buoyancy_tend_2nd (src/thermo_moist.cxx:77-120): wt += buoyancy of (thl, qt) interpolated to the half level, with the
 // condensate of the saturation adjustment at that level's pressure.  One level per blockIdx.z (k = kstart+1 .. kend-1).
 // exnh = exnrefh[k] of the base state: the reference evaluates exner(ph[k]) here, which is the very number its calc_base_state
-// stored in exnrefh[k] (same function, same argument).  A pow per CTA ahead of a 256-point tile was the bottleneck of the first
-// version (0.68 ms per launch at 512 x 512 x 256 fp32 with no cloud at all: 261 k CTAs each waiting for one lane's powf).
-template <typename TF>
+// stored in exnrefh[k] (same function, same argument).
+// A thread marches KCH levels up its column: thl and qt of the level below stay in registers (3 array reads per point instead
+// of 4 out of L2) and the loads of the next level (thl, qt, wt) are issued before the arithmetic of the current one.  The
+// one-point-per-thread version sat on two DRAM latencies in a row per 256-point CTA (loads -> arithmetic -> read-modify-write
+// of wt): 0.61 ms per launch at 512 x 512 x 256 fp32 with no cloud at all (28 % of the HBM roofline; a pow per CTA in the very
+// first version cost another 0.07 ms).
+template <typename TF, int KCH>
 __global__ void __launch_bounds__(256) moist_buoyancy_tend_kernel(TF* __restrict__ wt, const TF* __restrict__ thl, const TF* __restrict__ qt,
         const TF* __restrict__ ph, const TF* __restrict__ exh, const TF* __restrict__ thvrefh, const GridDev<TF> g, int* __restrict__ nonconv)
 {
     const int i = g.istart + blockIdx.x * blockDim.x + threadIdx.x;
     const int j = g.jstart + blockIdx.y * blockDim.y + threadIdx.y;
-    const int k = g.kstart + 1 + blockIdx.z;
-    if (i >= g.iend || j >= g.jend) return;
-    const TF exnh = exh[k], p = ph[k];
-    const long long ijk = i + (long long)j * g.icells + k * g.ijcells;
-    const TF thlh = interp2(thl[ijk - g.ijcells], thl[ijk]);
-    const TF qth  = interp2(qt[ijk - g.ijcells], qt[ijk]);
-    const SatAdjust<TF> ssa = moist_sat_adjust(thlh, qth, p, exnh);
-    if (!ssa.converged) atomicAdd(nonconv, 1);
-    wt[ijk] += moist_buoyancy(exnh, thlh, qth, ssa.ql, ssa.qi, thvrefh[k]);
+    const int k0 = g.kstart + 1 + blockIdx.z * KCH;
+    const int k1 = min(k0 + KCH, g.kend);
+    if (i >= g.iend || j >= g.jend || k0 >= k1) return;
+    const long long kk = g.ijcells;
+    long long ijk = i + (long long)j * g.icells + k0 * kk;
+    TF thl_m = thl[ijk - kk], qt_m = qt[ijk - kk];
+    TF thl_c = thl[ijk], qt_c = qt[ijk], wt_c = wt[ijk];
+    int bad = 0;
+    for (int k = k0; k < k1; ++k, ijk += kk)
+    {
+        TF thl_n = TF(0.), qt_n = TF(0.), wt_n = TF(0.);
+        if (k + 1 < k1) { thl_n = thl[ijk + kk]; qt_n = qt[ijk + kk]; wt_n = wt[ijk + kk]; }
+        const TF exnh = exh[k], p = ph[k];
+        const TF thlh = interp2(thl_m, thl_c);
+        const TF qth  = interp2(qt_m, qt_c);
+        const SatAdjust<TF> ssa = moist_sat_adjust(thlh, qth, p, exnh);
+        bad += ssa.converged ? 0 : 1;
+        wt[ijk] = wt_c + moist_buoyancy(exnh, thlh, qth, ssa.ql, ssa.qi, thvrefh[k]);
+        thl_m = thl_c; qt_m = qt_c;
+        thl_c = thl_n; qt_c = qt_n; wt_c = wt_n;
+    }
+    if (bad) atomicAdd(nonconv, bad);
 }
 
 // get_thermo_field: MODE 0 = "b" (calc_buoyancy: every level, no condensate outside kstart..kend-1), 1 = "ql"
