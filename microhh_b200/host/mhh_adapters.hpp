@@ -8,7 +8,7 @@
 // the Field3d ghost-cell layout stay unchanged.  See INTEGRATION.md for the three factory edits.
 //
 //   reference class (interface)                     adapter                      C ABI
-//   Advec<TF>        include/advec.h:45-71          Advec_{2i5,2,4}_b200<TF>     mhh_advec_exec / mhh_advec_get_cfl
+//   Advec<TF>        include/advec.h:45-71          Advec_b200<TF, SW, TYPE>     mhh_advec_exec / mhh_advec_get_cfl (2i5, 2, 2i4, 2i62, 4, 4m)
 //   Diff<TF>         include/diff.h:38-71           Diff_smag2_b200<TF>          mhh_diff_smag2_exec_viscosity / _exec / _get_dn
 //                                                   Diff_{2,4}_b200<TF>          mhh_diff_2_exec / mhh_diff_4_exec / mhh_diff_2_get_dn
 //   Pres<TF>         include/pres.h:41-92           Pres_{2,4}_b200<TF>          mhh_pres_exec / mhh_pres_check_divergence
@@ -163,7 +163,8 @@ namespace mhhb200
     }
 
     // ---- Advec_2i5 (src/advec_2i5.cxx:955-1063), Advec_2 (src/advec_2.cxx:288-345), Advec_4 (src/advec_4.cxx:573-684):
-    // Advec_4m (src/advec_4m.cxx:511-615).  SW = the C ABI's swadvec code (25, 2, 4, 41)
+    // Advec_4m (src/advec_4m.cxx:511-615), Advec_2i4 (src/advec_2i4.cxx:664-738), Advec_2i62 (src/advec_2i62.cxx:397-480).
+    // SW = the C ABI's swadvec code (25, 2, 24, 262, 4, 41)
     template<typename TF, int SW, Advection_type TYPE>
     class Advec_b200 : public Advec<TF>
     {
@@ -173,12 +174,14 @@ namespace mhhb200
             {
                 // ghost cells as the reference constructors ask for them (src/advec_2i5.cxx:42-45, src/advec_2.cxx:40-43,
                 // src/advec_4.cxx:41-48)
-                if (SW == 25) fluxlimit_list = in.get_list<std::string>("advec", "fluxlimit_list", "", std::vector<std::string>());   // src/advec_2i5.cxx:39-40
+                if (SW == 25 || SW == 262) fluxlimit_list = in.get_list<std::string>("advec", "fluxlimit_list", "", std::vector<std::string>());   // src/advec_2i5.cxx:39-40, src/advec_2i62.cxx:39-40
                 // :42-46 asks for (3, 3, 1|2); FOUR ghost cells in x make the interior start at a 16-byte aligned element (fp64 and
                 // fp32) and, for USESP, the row pitch a multiple of 16 bytes: the TMA-staged kernels then use aligned vector
                 // accesses throughout (with 3 the fp64 path still works, ~3 % slower; fp32 falls back to the cp.async kernels)
                 if (SW == 25) g.set_minimum_ghost_cells(4, 3, fluxlimit_list.empty() ? 1 : 2);
                 else if (SW == 2) g.set_minimum_ghost_cells(1, 1, 1);
+                else if (SW == 24) g.set_minimum_ghost_cells(2, 2, 2);                                        // src/advec_2i4.cxx:38-41
+                else if (SW == 262) g.set_minimum_ghost_cells(3, 3, fluxlimit_list.empty() ? 1 : 2);          // src/advec_2i62.cxx:42-45
                 else g.set_minimum_ghost_cells(3, 3, 3);
             }
 
@@ -214,6 +217,8 @@ namespace mhhb200
     template<typename TF> using Advec_2_b200   = Advec_b200<TF, 2,  Advection_type::Advec_2>;
     template<typename TF> using Advec_4_b200   = Advec_b200<TF, 4,  Advection_type::Advec_4>;
     template<typename TF> using Advec_4m_b200  = Advec_b200<TF, 41, Advection_type::Advec_4m>;
+    template<typename TF> using Advec_2i4_b200  = Advec_b200<TF, 24,  Advection_type::Advec_2i4>;
+    template<typename TF> using Advec_2i62_b200 = Advec_b200<TF, 262, Advection_type::Advec_2i62>;
 
     // ---- Diff_smag2 (src/diff_smag2.cxx:312-607) ------------------------------------------------
     template<typename TF>

@@ -39,6 +39,8 @@ template void mhhb200::dycore_substep_pre_b200<double>(mhhb200::Context<double>&
 template void mhhb200::dycore_set_ghost_cells_b200<double>(mhhb200::Context<double>&, Fields<double>&, Boundary<double>&, const mhh_params&);
 template void mhhb200::dycore_tendencies_b200<float>(mhhb200::Context<float>&, Fields<float>&, Boundary<float>&, const mhh_params&);
 template void mhhb200::dycore_substep_post_b200<double>(mhhb200::Context<double>&, Fields<double>&, Boundary<double>&, const mhh_params&, int, double);
+template class mhhb200::Advec_b200<double, 24, Advection_type::Advec_2i4>;
+template class mhhb200::Advec_b200<float, 262, Advection_type::Advec_2i62>;
 template class mhhb200::Thermo_buoy_b200<double>;
 template class mhhb200::Thermo_buoy_b200<float>;
 template class mhhb200::Thermo_moist_b200<double>;
