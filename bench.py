@@ -191,6 +191,17 @@ def side_config(torch, D, GridData, fill_fields_device, name, shape, dtype, S, p
         return {"workload": name, "error": str(ex)[:300]}
 
 
+def thermo_side(thermo, grid, dtype, steps):
+    """Side lines of the thermo couplings (tools/thermo_bench.py: the step with Thermo_moist / Thermo_buoy registered into the fused
+    sub-step, per-kernel times of the thermo kernels); like every side line it must never cost the main one."""
+    try:
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools"))
+        import thermo_bench
+        return thermo_bench.run(thermo, grid, dtype, steps)
+    except Exception as ex:
+        return {"workload": f"thermo side line {thermo} {grid} {dtype}", "error": str(ex)[:300]}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -355,6 +366,8 @@ def run_ours(args):
             side_config(torch, D, GridData, fill_fields_device, "drycblles 128^3 fp64 (configs[0]'s grid; launch-bound: CUDA-graph replay vs eager)", (128, 128, 128), np.float64, 1, peaks, 4*args.steps),
             side_config(torch, D, GridData, fill_fields_device, "bomex-shaped LES 512x512x256 fp32 (USESP), two scalars", (512, 512, 256), np.float32, 2, peaks, args.steps),
             side_config(torch, D, GridData, fill_fields_device, "moser180-shaped DNS 256x192x128 fp64 (advec_4m + diff_4 + pres_4, as cases/moser180 ships)", (256, 192, 128), np.float64, 1, peaks, args.steps, order=4),
+            thermo_side("moist", "512x512x256", "f32", args.steps),       # bomex-shaped with Thermo_moist (thl + qt, base-state update on the device)
+            thermo_side("buoy", "256x192x128", "f64", args.steps),        # 4th-order DNS with slope-enabled Thermo_buoy (drycblslope-like)
         ]
 
     itot, jtot, ktot_l = gd.imax, gd.jmax, gd.kmax

@@ -9,11 +9,10 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--thermo", default="moist"); ap.add_argument("--grid", default="512x512x256")
-    ap.add_argument("--dtype", default="f32"); ap.add_argument("--steps", type=int, default=5)
-    a = ap.parse_args()
+def run(thermo="moist", grid="512x512x256", dtype="f32", steps=5):
+    """One measurement; returns the JSON-able dict (also used by bench.py for its thermo side lines)."""
+    import types
+    a = types.SimpleNamespace(thermo=thermo, grid=grid, dtype=dtype, steps=steps)
     import torch
     from microhh_b200 import dycore as D
     from microhh_b200.grid import GridData
@@ -98,7 +97,19 @@ def main():
         out["cloud_fraction"] = float((f["evisc"][ks:ke, gd.jstart:gd.jend, gd.istart:gd.iend] > 0).double().mean().item())
         bs = T.get_profiles()
         out["thvrefh_surface"] = float(bs["thvrefh"][ks]); out["prefh_top"] = float(bs["prefh"][ke])
-    print(json.dumps(out))
+    T.unregister()
+    ctx.close()
+    del f
+    torch.cuda.empty_cache()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--thermo", default="moist"); ap.add_argument("--grid", default="512x512x256")
+    ap.add_argument("--dtype", default="f32"); ap.add_argument("--steps", type=int, default=5)
+    a = ap.parse_args()
+    print(json.dumps(run(a.thermo, a.grid, a.dtype, a.steps)))
 
 
 if __name__ == "__main__":
