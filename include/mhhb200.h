@@ -352,7 +352,8 @@ MHH_API int mhh_dycore_set_thermo_buoy(mhh_ctx* ctx, const mhh_thermo_buoy* tb);
  *   _get_profiles     copy them to HOST arrays (NULL = skip); synchronises
  *   _exec             Thermo_moist::exec (:1415-1447): with swupdatebasestate the mean profiles of thl and qt
  *                     (Field3d_operators::calc_mean_profile) and calc_base_state run on the device, stream-ordered, no host
- *                     round trip (single GPU); then calc_buoyancy_tend_2nd (saturation adjustment at the half levels) on wt
+ *                     round trip (y slabs: one ncclAllReduce(sum) of the two partial mean profiles, as master.sum does); then
+ *                     calc_buoyancy_tend_2nd (saturation adjustment at the half levels) on wt
  *   _get_thermo_field get_thermo_field(name) for "b", "ql", "N2" (MHH_MOIST_*); out: DEVICE field
  *   _get_buoyancy_surf / _fluxbot   get_buoyancy_surf (b at kstart + b_bot from s_bot[ithl], s_bot[iqt]) and
  *                     get_buoyancy_fluxbot (from s_fluxbot[ithl], s_fluxbot[iqt]); bbot / bfluxbot: DEVICE planes (ijcells)

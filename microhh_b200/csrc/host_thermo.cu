@@ -131,10 +131,19 @@ int thermo_moist_impl(Ctx<TF>* c, const mhh_fields* f, const mhh_thermo_moist* t
     if (tm->swupdatebasestate)
     {
         // Fields::exec's mean profiles (src/fields.cxx:542-551) + calc_base_state, on the device
-        if (c->nranks > 1) { c->err = "thermo_moist: swupdatebasestate on y slabs needs the sum of the mean profiles over the ranks (not in this version)"; return MHH_E_INVALID; }
         TF* means = c->d_moist + 6 * (size_t)g.kcells;
         moist_mean_profile_kernel<TF><<<dim3(g.kcells, 2), 1024, 0, c->stream>>>(thl, qt, means, means + g.kcells, g, (double)g.itot * (double)g.jtot);
         KCHECKN(c, "moist_mean_profile_kernel");
+        if (c->nranks > 1)
+        {
+            // y slabs: every rank holds sum(local rows) / (itot * jtot); `master.sum(prof, kcells)` of the reference
+            // (src/field3d_operators.cxx:65) is the all-reduce of those TF partial means.  Every rank then integrates the same
+            // base state.  (Same pattern as the fixed-mass-flux sums of Force; NOT yet run on a multi-GPU box.)
+            if (!c->comm) { c->err = "slab context without communicator: call mhh_comm_init first"; return MHH_E_INVALID; }
+            NcclApi* api = nccl_api(c->err);
+            if (!api) return MHH_E_CUDA;
+            NCCL_TRY(c, api, api->AllReduce(means, means, 2 * (size_t)g.kcells, sizeof(TF) == 8 ? ncclFloat64 : ncclFloat32, ncclSum, c->comm, c->stream));
+        }
         if ((rc = moist_base_state_launch<TF>(c, means, means + g.kcells, tm->pbot, false)) != MHH_OK) return rc;   // starts from the previous base state
     }
     if (g.kmax > 1)
