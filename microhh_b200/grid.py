@@ -55,7 +55,8 @@ class GridData:
         dzh[ks-1] = dzh[ks+1]; dzhi[ks-1] = dzhi[ks+1]
         dz = np.zeros(kc, TF); dzi = np.zeros(kc, TF)
         dz[1:kc-1] = zh[2:kc] - zh[1:kc-1]
-        dzi[1:kc-1] = TF(1.)/dz[1:kc-1]
+        with np.errstate(divide="ignore"):      # kgc = 2: the outer ghost level has dz = 0 in the reference too (1/0 = inf, never read)
+            dzi[1:kc-1] = TF(1.)/dz[1:kc-1]
         dz[ks-1] = dz[ks]; dzi[ks-1] = dzi[ks]
         dz[ke] = dz[ke-1]; dzi[ke] = dzi[ke-1]
         self.z, self.zh, self.dz, self.dzh, self.dzi, self.dzhi = zf, zh, dz, dzh, dzi, dzhi

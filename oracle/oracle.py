@@ -127,7 +127,8 @@ class Grid:
         dzhi[ks-1] = dzhi[ks+1]
         for k in range(1, kc-1):
             dz[k] = zh[k+1] - zh[k]
-            dzi[k] = TF(1.)/dz[k]
+            with np.errstate(divide="ignore"):      # kgc = 2: dz = 0 at the outer ghost level, as in the reference (never read)
+                dzi[k] = TF(1.)/dz[k]
         dz[ks-1] = dz[ks]; dzi[ks-1] = dzi[ks]
         dz[ke] = dz[ke-1]; dzi[ke] = dzi[ke-1]
 
