@@ -1079,7 +1079,9 @@ int mhh_comm_open_peers(mhh_ctx* ctx, const void* all, int nbytes)
     if (ctx->nranks > MAX_SLAB_RANKS) { ctx->err = "open_peers: too many ranks"; return MHH_E_INVALID; }
     if (!ctx->comm) { ctx->err = "open_peers: call mhh_comm_init first"; return MHH_E_INVALID; }
     { const char* e = getenv("MHH_NO_PEER"); if (e && e[0] == '1') return MHH_OK; }       // keep the NCCL all-to-all (A/B comparisons)
+#ifdef MHH_TEST_KNOBS       // fault injection for tools/gpu_fallback.sh only: build with `make EXTRA=-DMHH_TEST_KNOBS`; not in the shipped library
     { const char* e = getenv("MHH_FAIL_PEER_RANK"); if (e && atoi(e) == ctx->rank) { ctx->err = "open_peers: failure injected by MHH_FAIL_PEER_RANK (test knob)"; return MHH_E_CUDA; } }
+#endif
     DISPATCH1(ctx, ([&]() -> int {
         if (c->peers.on) { c->err = "open_peers: already open"; return MHH_E_INVALID; }
         if (c->g.jtot == 1) return MHH_OK;

@@ -1,6 +1,9 @@
 #!/bin/bash
 # 2 GPUs: (1) IPC mapping failure injected on rank 1 -> every rank must fall back to NCCL and the parity check must pass;
 # (2) a short bench in the normal (peer) mode.
+# The fault injection is compiled out of the shipped library: this script needs a build with the knob,
+#   make -C microhh_b200/csrc clean && make -C microhh_b200/csrc -j6 EXTRA=-DMHH_TEST_KNOBS
+# (and a plain rebuild afterwards).
 N=2
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
