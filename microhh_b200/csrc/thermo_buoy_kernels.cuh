@@ -6,7 +6,7 @@
 // Thermo_buoy::exec (:345-391) applies them as separate "+=" passes over ut, wt and bt; every term here lands on its own
 // element in that same order (slope term of bt before the baroclinic one), so ONE pass does the work of up to four: b, u, v,
 // w are read once and each tendency is read and written once -- 10 array passes (slope + baroclinic) where the reference's
-// four kernels move 14; the plain case is the reference's single pass (3 arrays).  HBM-bound, point-wise: every stencil is a
+// four kernels move 13; the plain case is the reference's single pass (3 arrays).  HBM-bound, point-wise: every stencil is a
 // two- or four-point interpolation along one axis, the x / y neighbours come out of L1 and the z neighbours out of L2.
 #pragma once
 #include "common.cuh"

@@ -62,7 +62,7 @@ def run(thermo="moist", grid="512x512x256", dtype="f32", steps=5):
         T = D.Thermo_buoy(ctx, alpha=0.1, n2=3., utrans=0.)
         prm = D.make_params(swadvec="4m", swdiff="4", swthermo="buoy", surface_model=False, mbcbot=0, mbctop=0)
         names = ("thermo_buoy_kernel",)
-        passes = {"thermo_buoy_kernel": 8}            # slope-enabled: R b, u, w + RMW ut, wt, bt
+        passes = {"thermo_buoy_kernel": 9}            # slope-enabled: R b, u, w (3) + RMW ut, wt, bt (6)
     T.register()
     dyc = D.Dycore(ctx, prm)
     dt = 1.0 if moist else 1e-3
