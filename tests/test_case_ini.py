@@ -100,3 +100,25 @@ def test_ini_syntax(tmp_path):
     p.write_text("[grid]\nitot=8 # comment\n\n# full-line comment\njtot = 4\n[fields]\nrndamp[th]=0.1\n")
     ini = read_ini(str(p))
     assert ini["grid"] == {"itot": "8", "jtot": "4"} and ini["fields"]["rndamp[th]"] == "0.1"
+
+
+def test_every_shipped_case_is_classified():
+    """The table of DESIGN.md section 8: which shipped cases lie inside the accelerated path, and the one switch that keeps each
+    of the others out."""
+    import glob
+    expect_out = {"bomex": ["mbcbot/mbctop=ustar/freeslip"], "conservation": ["swdiff=0"], "dycoms": ["swmicro=2mom_warm"],
+                  "rcemip": ["swmicro=nsw6"], "rico": ["swmicro=2mom_warm"], "rico_radiation": ["swmicro=2mom_warm"],
+                  "weisman_klemp": ["swmicro=nsw6"]}
+    seen = 0
+    for d in sorted(glob.glob(os.path.join(REF, "*"))):
+        name = os.path.basename(d)
+        f = os.path.join(d, name + ".ini")
+        if not os.path.exists(f):
+            continue
+        seen += 1
+        c = CaseConfig.from_file(f)
+        assert c.unsupported() == expect_out.get(name, []), (name, c.unsupported())
+        if name not in expect_out:
+            p = c.make_params()
+            assert p.swthermo == {"0": 0, "dry": 1, "buoy": 2, "moist": 3}[c.swthermo]
+    assert seen >= 25
