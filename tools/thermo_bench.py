@@ -39,8 +39,10 @@ def run(thermo="moist", grid="512x512x256", dtype="f32", steps=5):
         z = torch.from_numpy(np.asarray(gd.z, np.float64)).to(f["u"].device)
         zrel = (z/float(gd.zsize))[:, None, None]
         f["thl"].copy_((298. + 6.*zrel + (f["thl"].double() - 300. - 0.003*z[:, None, None])).to(f["thl"].dtype))
-        # a cumulus-like layer: the mean profile stays just below saturation, the fluctuations saturate a few per cent of the points
-        f["qt"].copy_((17.e-3*(1. - 0.75*zrel) + 1.1e-3*torch.exp(-((zrel - 0.45)/0.15)**2)
+        # a cumulus-like layer: the mean profile stays just below saturation and the fluctuations saturate ~1 % of all points, up to
+        # ~17 % in the core of the layer (tuned on the CPU with the oracle's saturation adjustment on a sample of this very field;
+        # with 1.1e-3 the field of the first measurements was cloud-free)
+        f["qt"].copy_((17.e-3*(1. - 0.75*zrel) + 1.5e-3*torch.exp(-((zrel - 0.45)/0.15)**2)
                        + 1.e-4*torch.randn(gd.shape, device=z.device, dtype=torch.float64)).clamp_min(1e-5).to(f["qt"].dtype))
         for n, v in (("thl_fluxbot", 8.e-3), ("qt_fluxbot", 5.2e-5), ("thl_gradbot", -1.e-3), ("qt_gradbot", -1.e-6), ("qt_gradtop", -1.e-6)):
             f[n].fill_(v)
